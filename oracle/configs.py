@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE: the env configurations the parity ladder runs (reference kwargs).
+
+Sources: BASELINE.json configs; tutorials/economic_simulation_basic.ipynb cell 11 (c1/c2);
+tutorials/rllib/phase2/config.yaml:7-51 (c3); tests/test_env.py:27-62 (ref_unit_test).
+"""
+
+_GTB = [("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+        ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+        ("Gather", dict())]
+
+CONFIGS = {
+    # c1 / c2: tutorial basic
+    "c1_tutorial": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone", components=_GTB,
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=10,
+        fixed_four_skill_and_loc=True, n_agents=4, world_size=[25, 25], episode_length=1000,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
+    # c3: paper config (phase 2) at 10 agents / 40x40
+    "c3_paper_tax": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=100, rate_disc=0.05,
+                                                tax_model="model_wrapper"))],
+        env_layout_file="quadrant_40x40_50each.txt", starting_agent_coin=0,
+        fixed_four_skill_and_loc=True, n_agents=10, world_size=[40, 40], episode_length=1000,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        isoelastic_eta=0.23, energy_cost=0.21, energy_warmup_constant=0, planner_gets_spatial_info=False,
+        mixing_weight_gini_vs_coin=0.0, planner_reward_type="coin_eq_times_productivity"),
+    # c3 variant: short tax period, spatial planner, random (non-fixed-four) placement, tax annealing
+    "c3_short_period": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=10, rate_disc=0.05,
+                                                tax_model="model_wrapper",
+                                                tax_annealing_schedule=[-100, 0.001]))],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5,
+        fixed_four_skill_and_loc=False, n_agents=6, world_size=[25, 25], episode_length=200,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
+    # fixed us-federal schedule (planner has no actions)
+    "tax_us_federal": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="none")),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict()),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=20,
+                                                tax_model="us-federal-single-filer-2018-scaled"))],
+        env_layout_file="env-pure_and_mixed-15x15.txt", starting_agent_coin=20,
+        n_agents=5, world_size=[15, 15], episode_length=120,
+        multi_action_mode_agents=True, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
+    # the reference's own unit-test config (tests/test_env.py:27-62)
+    "ref_unit_test": dict(
+        scenario_name="uniform/simple_wood_and_stone",
+        components=[("Build", {}), ("ContinuousDoubleAuction", {"max_num_orders": 5}), ("Gather", {})],
+        n_agents=4, world_size=[15, 15], episode_length=100,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        starting_agent_coin=10, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
+    # c5-like (small): multi-action agents, deep book, uniform scenario, >=30 agents (sorted gini branch)
+    "c5_small": dict(
+        scenario_name="uniform/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=50)),
+                    ("Gather", dict(skill_dist="pareto"))],
+        n_agents=32, world_size=[32, 32], episode_length=150,
+        multi_action_mode_agents=True, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
+}
