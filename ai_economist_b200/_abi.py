@@ -1,0 +1,148 @@
+"""ctypes mirror of include/aie_b200.h (the C-ABI of the CUDA library).  No compute happens here."""
+import ctypes as C
+import os
+
+ABI_VERSION = 1
+MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 4, 16, 64
+AIE_OK = 0
+
+COMPONENT_KIND = {"Build": 0, "ContinuousDoubleAuction": 1, "Gather": 2, "PeriodicBracketTax": 3}
+
+CSRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+DEFAULT_LIB = os.path.join(CSRC_DIR, "libaie_b200.so")
+
+
+class AieConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("n_agents", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("episode_length", C.c_int32),
+        ("multi_action_agents", C.c_int32), ("n_components", C.c_int32),
+        ("components", C.c_int32 * MAX_COMPONENTS),
+        ("has_water", C.c_int32), ("obs_range", C.c_int32), ("planner_gets_spatial_info", C.c_int32),
+        ("allow_observation_scaling", C.c_int32),
+        ("regen_weight", C.c_double * 2),
+        ("isoelastic_eta", C.c_double), ("energy_cost", C.c_double), ("energy_warmup_constant", C.c_double),
+        ("energy_warmup_auto", C.c_int32), ("planner_reward_type", C.c_int32),
+        ("mixing_weight_gini_vs_coin", C.c_double),
+        ("build_payment", C.c_double), ("build_labor", C.c_double),
+        ("move_labor", C.c_double), ("collect_labor", C.c_double),
+        ("max_bid_ask", C.c_int32), ("order_duration", C.c_int32), ("max_num_orders", C.c_int32),
+        ("order_labor", C.c_double),
+        ("tax_model", C.c_int32), ("disable_taxes", C.c_int32), ("period", C.c_int32),
+        ("n_brackets", C.c_int32), ("n_disc_rates", C.c_int32),
+        ("bracket_cutoffs", C.c_double * MAX_BRACKETS), ("disc_rates", C.c_double * MAX_RATES),
+        ("fixed_rates", C.c_double * MAX_BRACKETS),
+        ("tax_annealing", C.c_int32), ("annealing_warmup", C.c_double), ("annealing_slope", C.c_double),
+        ("rate_max", C.c_double),
+        ("auto_reset", C.c_int32),
+    ]
+
+
+class AieDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in [
+        "n_envs", "n_agents", "height", "width", "n_map_channels", "window", "flat_agent", "flat_planner",
+        "flat_planner_agent", "mask_agent", "mask_planner", "n_act_agent", "n_act_planner", "state_bytes",
+        "algorithmic_bytes_per_env_step"]]
+
+
+_BUF_NAMES = ["state", "state0", "actions_agent", "actions_planner", "obs_agent_map", "obs_agent_idx",
+              "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx", "obs_planner_flat",
+              "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]
+
+
+class AieBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _BUF_NAMES]
+
+
+class AieHostState(C.Structure):
+    _fields_ = [("n", C.c_int32)] + [(n, C.c_void_p) for n in [
+        "stone", "wood", "stone_src", "wood_src", "water", "loc", "coin", "inv_stone", "inv_wood",
+        "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions"]]
+
+
+_DUMP_PTRS = ["cell", "owner", "loc", "coin", "esc_coin", "labor", "inv", "esc", "n_orders", "bid_hist", "ask_hist",
+              "price_hist", "tax_pos", "rate_idx", "last_coin", "last_income", "last_marg", "mt_key", "mt_pos", "t",
+              "completions", "book_rows", "book_count"]
+
+
+class AieStateDump(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _DUMP_PTRS] + [("book_cap", C.c_int32)]
+
+
+class AieField(C.Structure):
+    _fields_ = [("offset", C.c_int32), ("elem_bytes", C.c_int32), ("is_float", C.c_int32),
+                ("is_signed", C.c_int32), ("ndim", C.c_int32), ("shape", C.c_int32 * 4)]
+
+
+_OUT_NAMES = ["obs_agent_map", "obs_agent_idx", "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx",
+              "obs_planner_flat", "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]
+
+
+class AieHostOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _OUT_NAMES]
+
+
+class AieError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """Open the C-ABI shared library and declare every prototype in include/aie_b200.h."""
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise AieError(
+            "CUDA extension %s not found. Build it first: `python -c \"import __graft_entry__ as g; g.build()\"` "
+            "(nvcc, sm_100a). There is no CPU fallback." % path)
+    L = C.CDLL(path)
+    P = C.c_void_p
+    L.aie_last_error.restype = C.c_char_p
+    L.aie_abi_version.restype = C.c_int
+    L.aie_create.argtypes = [C.POINTER(AieConfig), C.c_int32, C.c_int32, C.POINTER(P)]
+    L.aie_destroy.argtypes = [P]
+    L.aie_get_dims.argtypes = [P, C.POINTER(AieDims)]
+    L.aie_get_field.argtypes = [P, C.c_char_p, C.POINTER(AieField)]
+    L.aie_bind_buffers.argtypes = [P, C.POINTER(AieBuffers)]
+    L.aie_load_state.argtypes = [P, C.POINTER(AieHostState), C.c_int32, P]
+    L.aie_step.argtypes = [P, P]
+    L.aie_observe.argtypes = [P, P]
+    L.aie_step_host.argtypes = [P, P, P, C.POINTER(AieHostOut), P]
+    L.aie_read_state.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
+    L.aie_launch_count.argtypes = [P]
+    L.aie_launch_count.restype = C.c_int64
+    for fn in ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers", "aie_load_state",
+               "aie_step", "aie_observe", "aie_step_host", "aie_read_state"]:
+        getattr(L, fn).restype = C.c_int
+    if L.aie_abi_version() != ABI_VERSION:
+        raise AieError("ABI version mismatch between %s and the Python binding" % path)
+    return L
+
+
+EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers",
+                    "aie_load_state", "aie_step", "aie_observe", "aie_step_host", "aie_read_state",
+                    "aie_launch_count", "aie_last_error", "aie_abi_version"]
+
+
+def config_from_spec(spec, auto_reset=True):
+    """spec: the flat numeric env description produced by foundation.spec.EnvSpec.to_dict()."""
+    cfg = AieConfig()
+    cfg.abi_version = ABI_VERSION
+    for k in ["n_agents", "height", "width", "episode_length", "multi_action_agents", "has_water", "obs_range",
+              "planner_gets_spatial_info", "allow_observation_scaling", "isoelastic_eta", "energy_cost",
+              "energy_warmup_constant", "energy_warmup_auto", "planner_reward_type", "mixing_weight_gini_vs_coin",
+              "build_payment", "build_labor", "move_labor", "collect_labor", "max_bid_ask", "order_duration",
+              "max_num_orders", "order_labor", "tax_model", "disable_taxes", "period", "n_brackets", "n_disc_rates",
+              "tax_annealing", "annealing_warmup", "annealing_slope", "rate_max"]:
+        setattr(cfg, k, spec[k])
+    comps = [COMPONENT_KIND[c] for c in spec["components"]]
+    cfg.n_components = len(comps)
+    for i, c in enumerate(comps):
+        cfg.components[i] = c
+    cfg.regen_weight[0], cfg.regen_weight[1] = spec["regen_weight"]
+    for i, v in enumerate(spec["bracket_cutoffs"]):
+        cfg.bracket_cutoffs[i] = v
+    for i, v in enumerate(spec["disc_rates"]):
+        cfg.disc_rates[i] = v
+    for i, v in enumerate(spec["fixed_rates"]):
+        cfg.fixed_rates[i] = v
+    cfg.auto_reset = int(bool(auto_reset))
+    return cfg

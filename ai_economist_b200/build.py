@@ -1,0 +1,20 @@
+"""Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB = os.path.join(CSRC, "libaie_b200.so")
+SOURCES = ["aie_abi.cu"]
+DEPS = ["aie_abi.cu", "aie_abi.inl", "aie_core.cuh", "aie_host.h", "aie_layout.h", "../../include/aie_b200.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build_library(force=False, verbose=False):
+    newest = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS)
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB

@@ -1,0 +1,270 @@
+// aie_abi.cu — CUDA backend of the C-ABI (the product).  sm_100a only; there is no CPU path.
+//
+// Kernels (see DESIGN.md for the roofline of each):
+//   aie_step_kernel        one warp per env replica.  The env's packed state record is staged HBM -> shared
+//                          memory with one TMA bulk copy (cp.async.bulk + mbarrier), advanced one timestep in
+//                          shared memory (aie_core.cuh: step_env), and written back with one bulk copy.
+//   aie_observe_kernel     one CTA per env replica.  Bulk-loads the observable prefix of the record and streams
+//                          out every observation / mask tensor with coalesced stores (the HBM-bound part).
+//   aie_finish_reset_kernel  one warp per env: tax trackers + utility metric_0 after a host reset upload.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "aie_core.cuh"
+#include "aie_host.h"
+
+struct aie_env;
+
+namespace aie {
+namespace be {
+struct State {
+    int step_wpb;        // warps (envs) per CTA of the step kernel
+    size_t step_smem;    // dynamic shared memory per CTA
+    int obs_threads;
+    size_t obs_smem;
+};
+int init(aie_env *);
+void destroy(aie_env *);
+int upload(aie_env *, void *dst, const void *src, size_t n, void *stream);
+int download(aie_env *, void *dst, const void *src, size_t n, void *stream);
+int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *stream);
+int sync(aie_env *, void *stream);
+int sync_all(aie_env *);
+int launch_finish_reset(aie_env *, int lo, int n, void *stream);
+int launch_step(aie_env *, void *stream);
+int launch_observe(aie_env *, int lo, int n, void *stream);
+}  // namespace be
+}  // namespace aie
+
+#include "aie_abi.inl"
+
+namespace aie {
+
+static_assert(sizeof(DevCfg) <= 4000, "DevCfg is passed by value as a __grid_constant__ kernel parameter");
+
+// ---- TMA bulk-copy / mbarrier primitives (PTX ISA: cp.async.bulk, mbarrier) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory carve-up of the step / finish-reset kernels: [mbarriers | per-warp (record | scratch)]
+__device__ __forceinline__ uint8_t *warp_region(uint8_t *smem, int wpb, int warp, const DevCfg &c) {
+    return smem + ((8 * wpb + 15) & ~15) + (size_t)warp * (c.rec_bytes + c.step_scratch_bytes);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * wpb + warp;
+    if (env >= c.n_envs) return;  // warps are independent: no block-wide barrier below
+    uint64_t *bar = (uint64_t *)smem + warp;
+    uint8_t *rec = warp_region(smem, wpb, warp, c);
+    uint8_t *scratch = rec + c.rec_bytes;
+    uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)c.rec_bytes);
+        bulk_g2s(rec, grec, (uint32_t)c.rec_bytes, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
+    const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
+    step_env(c, rec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
+
+    // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
+    // from the load-time snapshot; the episode counters and the numpy stream carry on.
+    int32_t *hdr = (int32_t *)rec;
+    if (c.auto_reset && hdr[HDR_T] >= c.T) {
+        const int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
+                      episodes = hdr[HDR_EPISODES] + 1;
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)c.off_mt);
+            bulk_g2s(rec, b.state0 + (size_t)env * c.rec_bytes, (uint32_t)c.off_mt, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 1);
+        if (lane == 0) {
+            hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
+            hdr[HDR_EPISODES] = episodes;
+        }
+        __syncwarp();
+        finish_reset_env(c, rec, scratch, lane);  // metric_0 under the new completions count
+    }
+
+    fence_async_smem();  // generic-proxy writes to the record -> visible to the bulk (async-proxy) store
+    __syncwarp();
+    if (lane == 0) {
+        bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
+        bulk_wait_read();
+    }
+}
+
+__global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
+                                                               int lo, int n) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * wpb + warp;
+    if (i >= n) return;
+    const int env = lo + i;
+    uint64_t *bar = (uint64_t *)smem + warp;
+    uint8_t *rec = warp_region(smem, wpb, warp, c);
+    uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)c.rec_bytes);
+        bulk_g2s(rec, grec, (uint32_t)c.rec_bytes, bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    finish_reset_env(c, rec, rec + c.rec_bytes, lane);
+    if (lane == 0) { b.done[env] = 0; }
+    for (int a = lane; a <= c.A; a += 32) b.rew[(size_t)env * (c.A + 1) + a] = 0.0;
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
+        bulk_wait_read();
+    }
+}
+
+__global__ void __launch_bounds__(128) aie_observe_kernel(const __grid_constant__ DevCfg c, const DevBufs b, int lo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int env = lo + blockIdx.x;
+    uint64_t *bar = (uint64_t *)smem;
+    uint8_t *rec = smem + 16;
+    uint8_t *scratch = rec + c.obs_prefix_bytes;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)c.obs_prefix_bytes);
+        bulk_g2s(rec, b.state + (size_t)env * c.rec_bytes, (uint32_t)c.obs_prefix_bytes, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const size_t A = c.A, ww = (size_t)c.win * c.win, e = (size_t)env;
+    ObsOut o;
+    o.a_map = b.a_map + e * A * (c.M + 1) * ww;
+    o.a_idx = b.a_idx + e * A * 2 * ww;
+    o.a_flat = b.a_flat + e * A * c.Fa;
+    o.a_mask = b.a_mask + e * A * c.Na;
+    o.p_map = c.planner_spatial ? b.p_map + e * c.M * c.HW : nullptr;
+    o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
+    o.p_flat = b.p_flat + e * c.Fp;
+    o.p_agents = b.p_agents + e * A * c.Fpa;
+    o.p_mask = b.p_mask + e * c.Np;
+    o.time_obs = b.time_obs + e;
+    observe_env(c, rec, scratch, o, threadIdx.x, blockDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+namespace be {
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    return fail(AIE_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define AIE_CUDA(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+
+int init(aie_env *env) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(AIE_ECUDA, std::string("no CUDA device: this library has no CPU fallback (") +
+                                   (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) + ")");
+    if (env->device < 0 || env->device >= ndev) return fail(AIE_EINVAL, "device ordinal out of range");
+    AIE_CUDA(cudaSetDevice(env->device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    AIE_CUDA(cudaGetDeviceProperties(&prop, env->device), "cudaGetDeviceProperties");
+    if (prop.major < 10) return fail(AIE_ECUDA, "this build targets sm_100a (Blackwell B200) only");
+    const DevCfg &c = env->cfg;
+    const size_t max_smem = prop.sharedMemPerBlockOptin;
+    const size_t per_env = (size_t)c.rec_bytes + c.step_scratch_bytes;
+    int wpb = 8;
+    while (wpb > 1 && align16(8 * wpb) + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
+    if (align16(8 * wpb) + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
+    env->be.step_wpb = wpb;
+    env->be.step_smem = align16(8 * wpb) + wpb * per_env;
+    env->be.obs_threads = 128;
+    env->be.obs_smem = 16 + (size_t)c.obs_prefix_bytes + c.obs_scratch_bytes;
+    if (env->be.obs_smem > max_smem) return fail(AIE_EINVAL, "observation staging does not fit in shared memory");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
+    return AIE_OK;
+}
+void destroy(aie_env *) {}
+
+int upload(aie_env *, void *dst, const void *src, size_t n, void *stream) {
+    AIE_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D copy");
+    return AIE_OK;
+}
+int download(aie_env *, void *dst, const void *src, size_t n, void *stream) {
+    AIE_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H copy");
+    return AIE_OK;
+}
+int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *stream) {
+    AIE_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "D2D copy");
+    return AIE_OK;
+}
+int sync(aie_env *, void *stream) {
+    AIE_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "stream sync");
+    return AIE_OK;
+}
+int sync_all(aie_env *) {
+    AIE_CUDA(cudaDeviceSynchronize(), "device sync");
+    return AIE_OK;
+}
+int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
+    const int wpb = env->be.step_wpb;
+    aie_finish_reset_kernel<<<(n + wpb - 1) / wpb, wpb * 32, env->be.step_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
+    AIE_CUDA(cudaGetLastError(), "aie_finish_reset_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
+int launch_step(aie_env *env, void *stream) {
+    const int wpb = env->be.step_wpb;
+    aie_step_kernel<<<(env->n_envs + wpb - 1) / wpb, wpb * 32, env->be.step_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs);
+    AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
+int launch_observe(aie_env *env, int lo, int n, void *stream) {
+    aie_observe_kernel<<<n, env->be.obs_threads, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo);
+    AIE_CUDA(cudaGetLastError(), "aie_observe_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
+
+}  // namespace be
+}  // namespace aie

@@ -1,0 +1,184 @@
+// aie_abi.inl — the extern "C" entry points declared in include/aie_b200.h.
+// Included by aie_abi.cu (CUDA backend = the product) and by tests/emu/aie_emu.cpp (1-lane host emulation
+// of the same device source, CPU logic tests only).  The includer provides, in namespace aie::be:
+//   struct State;  int init(aie_env*);  void destroy(aie_env*);
+//   int upload(aie_env*, void *dst, const void *src, size_t n, void *stream);
+//   int download(aie_env*, void *dst, const void *src, size_t n, void *stream);
+//   int dev_copy(aie_env*, void *dst, const void *src, size_t n, void *stream);
+//   int sync(aie_env*, void *stream);   int sync_all(aie_env*);
+//   int launch_finish_reset(aie_env*, int lo, int n, void *stream);
+//   int launch_step(aie_env*, void *stream);
+//   int launch_observe(aie_env*, int lo, int n, void *stream);
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+
+struct aie_env {
+    aie::DevCfg cfg;
+    aie_config ucfg;
+    int n_envs, device;
+    aie::DevBufs bufs;
+    bool bound, loaded;
+    int64_t launches;
+    aie::be::State be;
+};
+
+static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+
+extern "C" {
+
+const char *aie_last_error(void) { return g_last_error.c_str(); }
+int aie_abi_version(void) { return AIE_ABI_VERSION; }
+
+int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **out) {
+    if (!cfg || !out) return fail(AIE_EINVAL, "null argument");
+    aie_env *env = new (std::nothrow) aie_env();
+    if (!env) return fail(AIE_ENOMEM, "out of host memory");
+    std::string err;
+    int rc = aie::build_devcfg(*cfg, n_envs, env->cfg, err);
+    if (rc != AIE_OK) { delete env; return fail(rc, "aie_create: " + err); }
+    env->ucfg = *cfg; env->n_envs = n_envs; env->device = device;
+    memset(&env->bufs, 0, sizeof(env->bufs));
+    env->bound = env->loaded = false; env->launches = 0;
+    rc = aie::be::init(env);
+    if (rc != AIE_OK) { delete env; return rc; }
+    *out = env;
+    return AIE_OK;
+}
+
+int aie_destroy(aie_env *env) {
+    if (!env) return AIE_OK;
+    aie::be::destroy(env);
+    delete env;
+    return AIE_OK;
+}
+
+int aie_get_dims(const aie_env *env, aie_dims *out) {
+    if (!env || !out) return fail(AIE_EINVAL, "null argument");
+    aie::fill_dims(env->cfg, *out);
+    return AIE_OK;
+}
+
+int aie_get_field(const aie_env *env, const char *name, aie_field *out) {
+    if (!env || !name || !out) return fail(AIE_EINVAL, "null argument");
+    if (aie::lookup_field(env->cfg, name, out) != AIE_OK) return fail(AIE_EINVAL, std::string("unknown state field ") + name);
+    return AIE_OK;
+}
+
+int aie_bind_buffers(aie_env *env, const aie_buffers *b) {
+    if (!env || !b) return fail(AIE_EINVAL, "null argument");
+    const aie::DevCfg &c = env->cfg;
+    if (!b->state || !b->state0 || !b->actions_agent || !b->obs_agent_map || !b->obs_agent_idx || !b->obs_agent_flat ||
+        !b->mask_agent || !b->obs_planner_flat || !b->obs_planner_agents || !b->mask_planner || !b->obs_time ||
+        !b->reward || !b->done)
+        return fail(AIE_EINVAL, "aie_bind_buffers: a required buffer is NULL");
+    if (c.planner_spatial && (!b->obs_planner_map || !b->obs_planner_idx))
+        return fail(AIE_EINVAL, "aie_bind_buffers: planner map buffers required when planner_gets_spatial_info");
+    if (c.n_act_p > 0 && !b->actions_planner) return fail(AIE_EINVAL, "aie_bind_buffers: actions_planner required");
+    if (((uintptr_t)b->state & 15) || ((uintptr_t)b->state0 & 15)) return fail(AIE_EINVAL, "state buffers must be 16-byte aligned");
+    aie::DevBufs &d = env->bufs;
+    d.state = (uint8_t *)b->state; d.state0 = (uint8_t *)b->state0;
+    d.act_a = b->actions_agent; d.act_p = b->actions_planner;
+    d.a_map = b->obs_agent_map; d.a_idx = b->obs_agent_idx; d.a_flat = b->obs_agent_flat; d.a_mask = b->mask_agent;
+    d.p_map = b->obs_planner_map; d.p_idx = b->obs_planner_idx; d.p_flat = b->obs_planner_flat;
+    d.p_agents = b->obs_planner_agents; d.p_mask = b->mask_planner; d.time_obs = b->obs_time;
+    d.rew = b->reward; d.done = b->done;
+    env->bound = true;
+    return AIE_OK;
+}
+
+int aie_load_state(aie_env *env, const aie_host_state *hs, int32_t env_lo, void *stream) {
+    if (!env || !hs) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound) return fail(AIE_ESTATE, "aie_load_state: buffers not bound");
+    const aie::DevCfg &c = env->cfg;
+    if (hs->n < 1 || env_lo < 0 || env_lo + hs->n > env->n_envs) return fail(AIE_EINVAL, "aie_load_state: env range out of bounds");
+    if (!hs->stone || !hs->wood || !hs->stone_src || !hs->wood_src || !hs->loc || !hs->coin || !hs->build_payment ||
+        !hs->build_skill || !hs->bonus_gather_prob || !hs->mt_key || !hs->mt_pos)
+        return fail(AIE_EINVAL, "aie_load_state: a required host array is NULL");
+    std::vector<uint8_t> host((size_t)hs->n * c.rec_bytes);
+    std::string err;
+    for (int i = 0; i < hs->n; i++) {
+        int rc = aie::pack_record(c, *hs, i, host.data() + (size_t)i * c.rec_bytes, err);
+        if (rc != AIE_OK) return fail(rc, "aie_load_state: " + err);
+    }
+    uint8_t *dst = env->bufs.state + (size_t)env_lo * c.rec_bytes;
+    int rc = aie::be::upload(env, dst, host.data(), host.size(), stream);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::sync(env, stream);  // the staging vector goes out of scope below
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::launch_finish_reset(env, env_lo, hs->n, stream);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::dev_copy(env, env->bufs.state0 + (size_t)env_lo * c.rec_bytes, dst, host.size(), stream);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::launch_observe(env, env_lo, hs->n, stream);
+    if (rc != AIE_OK) return rc;
+    env->loaded = true;
+    return aie::be::sync(env, stream);
+}
+
+int aie_step(aie_env *env, void *stream) {
+    if (!env) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step: bind buffers and load state first");
+    int rc = aie::be::launch_step(env, stream);
+    if (rc != AIE_OK) return rc;
+    return aie::be::launch_observe(env, 0, env->n_envs, stream);
+}
+
+int aie_observe(aie_env *env, void *stream) {
+    if (!env) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_observe: bind buffers and load state first");
+    return aie::be::launch_observe(env, 0, env->n_envs, stream);
+}
+
+int aie_step_host(aie_env *env, const int32_t *act_a, const int32_t *act_p, const aie_host_out *o, void *stream) {
+    if (!env || !act_a || !o) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_host: bind buffers and load state first");
+    const aie::DevCfg &c = env->cfg;
+    const size_t E = env->n_envs, A = c.A, ww = (size_t)c.win * c.win;
+    int rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * A * c.n_act_a * 4, stream);
+    if (rc != AIE_OK) return rc;
+    if (c.n_act_p > 0) {
+        if (!act_p) return fail(AIE_EINVAL, "aie_step_host: planner actions required");
+        rc = aie::be::upload(env, (void *)env->bufs.act_p, act_p, E * c.n_act_p * 4, stream);
+        if (rc != AIE_OK) return rc;
+    }
+    rc = aie_step(env, stream);
+    if (rc != AIE_OK) return rc;
+    const aie::DevBufs &d = env->bufs;
+    struct { void *h; const void *dev; size_t n; } cp[] = {
+        {o->obs_agent_map, d.a_map, E * A * (c.M + 1) * ww * 4}, {o->obs_agent_idx, d.a_idx, E * A * 2 * ww * 2},
+        {o->obs_agent_flat, d.a_flat, E * A * c.Fa * 4}, {o->mask_agent, d.a_mask, E * A * c.Na * 4},
+        {o->obs_planner_map, c.planner_spatial ? d.p_map : nullptr, E * c.M * c.HW * 4},
+        {o->obs_planner_idx, c.planner_spatial ? d.p_idx : nullptr, E * 2 * c.HW * 2},
+        {o->obs_planner_flat, d.p_flat, E * c.Fp * 4}, {o->obs_planner_agents, d.p_agents, E * A * c.Fpa * 4},
+        {o->mask_planner, d.p_mask, E * c.Np * 4}, {o->obs_time, d.time_obs, E * 4},
+        {o->reward, d.rew, E * (A + 1) * 8}, {o->done, d.done, E * 4},
+    };
+    for (auto &x : cp)
+        if (x.h && x.dev) {
+            rc = aie::be::download(env, x.h, x.dev, x.n, stream);
+            if (rc != AIE_OK) return rc;
+        }
+    return aie::be::sync(env, stream);
+}
+
+int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out) {
+    if (!env || !out) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound) return fail(AIE_ESTATE, "aie_read_state: buffers not bound");
+    if (e < 0 || e >= env->n_envs) return fail(AIE_EINVAL, "aie_read_state: env index out of range");
+    const aie::DevCfg &c = env->cfg;
+    std::vector<uint8_t> rec(c.rec_bytes);
+    int rc = aie::be::sync_all(env);  // debug path: order against work on any stream
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::download(env, rec.data(), env->bufs.state + (size_t)e * c.rec_bytes, rec.size(), nullptr);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::sync(env, nullptr);
+    if (rc != AIE_OK) return rc;
+    aie::unpack_record(c, rec.data(), *out);
+    return AIE_OK;
+}
+
+int64_t aie_launch_count(const aie_env *env) { return env ? env->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,955 @@
+// aie_core.cuh — per-env dynamics ("step") and observation ("observe") bodies.
+//
+// Compiled two ways:
+//   * nvcc, sm_100a: NL = 32 lanes.  One warp owns one env replica whose state record lives in shared
+//     memory.  Order-dependent sections (agent loops in np.random.permutation order, auction matching) run
+//     as warp-uniform code — every lane evaluates the same control flow from shared memory, lane 0 commits
+//     the writes — so warp collectives (MT19937 twist, redux/ballot scans of the order book) can be called
+//     from anywhere inside them.  Embarrassingly parallel sections (order creation/expiry, price-history
+//     decay, regeneration over the grid, taxes, utilities) stride agents/cells across lanes.
+//   * g++ with -DAIE_EMU (tests/emu only): NL = 1, collectives degenerate to identities.  This is a logic
+//     check of the same source on the build container, which has no GPU.  It is never built into or loaded
+//     by the product library.
+//
+// Reference semantics restated here (paths relative to ai_economist/foundation/):
+//   Build.component_step                      components/build.py:112-161
+//   ContinuousDoubleAuction.component_step    components/continuous_double_auction.py:440-489 (+168-406)
+//   Gather.component_step                     components/move.py:93-153
+//   PeriodicBracketTax.component_step         components/redistribution.py:945-972 (+419-434, 837-915)
+//   LayoutFromFile.scenario_step              scenarios/simple_wood_and_stone/layout_from_file.py:372-410
+//   compute_reward / optimization metrics     layout_from_file.py:269-318, 519-559; scenarios/utils/*.py
+//   generate_observations / masks             layout_from_file.py:412-517; base/base_env.py:562-756;
+//                                             build.py:163-193; move.py:155-188;
+//                                             continuous_double_auction.py:491-580; redistribution.py:974-1104
+//   numpy legacy RandomState stream           numpy/random/src/mt19937/mt19937.c, legacy-distributions.c
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "aie_layout.h"
+
+#if defined(__CUDACC__) && !defined(AIE_EMU)
+#define AIE_DEV __device__ __forceinline__
+#define AIE_DEV_NOINLINE __device__ __noinline__
+#define AIE_ON_DEVICE 1
+#else
+#define AIE_DEV static inline
+#define AIE_DEV_NOINLINE static
+#define AIE_ON_DEVICE 0
+#endif
+
+namespace aie {
+
+#if AIE_ON_DEVICE
+constexpr int NL = 32;
+AIE_DEV void wsync() { __syncwarp(); }
+AIE_DEV uint32_t wmax(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+AIE_DEV uint32_t wballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+AIE_DEV uint32_t wshfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+AIE_DEV bool wany(bool p) { return __any_sync(0xffffffffu, p); }
+AIE_DEV double wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+AIE_DEV int first_lane(uint32_t m) { return __ffs(m) - 1; }
+#else
+constexpr int NL = 1;
+AIE_DEV void wsync() {}
+AIE_DEV uint32_t wmax(uint32_t v) { return v; }
+AIE_DEV uint32_t wballot(bool p) { return p ? 1u : 0u; }
+AIE_DEV uint32_t wshfl(uint32_t v, int) { return v; }
+AIE_DEV bool wany(bool p) { return p; }
+AIE_DEV double wsum(double v) { return v; }
+AIE_DEV int first_lane(uint32_t m) { return m ? 0 : -1; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Views into a state record
+// ------------------------------------------------------------------------------------------------
+struct Env {
+    int32_t *hdr;
+    double *coin, *esc_coin, *labor, *bpay, *bskill, *bonus, *last_coin, *last_income, *last_marg, *util_prev,
+        *price_hist;
+    int32_t *inv, *esc;  // [A][2]
+    int16_t *loc;        // [A][2]
+    uint8_t *n_orders, *bid_hist, *ask_hist, *rate_idx, *cell;
+    int8_t *owner;
+    uint32_t *orders, *mt;
+};
+
+AIE_DEV Env env_view(uint8_t *rec, const DevCfg &c) {
+    Env e;
+    e.hdr = (int32_t *)rec;
+    e.coin = (double *)(rec + c.off_coin);
+    e.esc_coin = (double *)(rec + c.off_esc_coin);
+    e.labor = (double *)(rec + c.off_labor);
+    e.bpay = (double *)(rec + c.off_bpay);
+    e.bskill = (double *)(rec + c.off_bskill);
+    e.bonus = (double *)(rec + c.off_bonus);
+    e.last_coin = (double *)(rec + c.off_last_coin);
+    e.last_income = (double *)(rec + c.off_last_income);
+    e.last_marg = (double *)(rec + c.off_last_marg);
+    e.util_prev = (double *)(rec + c.off_util_prev);
+    e.price_hist = (double *)(rec + c.off_price_hist);
+    e.inv = (int32_t *)(rec + c.off_inv);
+    e.esc = (int32_t *)(rec + c.off_esc);
+    e.loc = (int16_t *)(rec + c.off_loc);
+    e.n_orders = rec + c.off_n_orders;
+    e.bid_hist = rec + c.off_bid_hist;
+    e.ask_hist = rec + c.off_ask_hist;
+    e.rate_idx = rec + c.off_rate_idx;
+    e.cell = rec + c.off_cell;
+    e.owner = (int8_t *)(rec + c.off_owner);
+    e.orders = (uint32_t *)(rec + c.off_orders);
+    e.mt = (uint32_t *)(rec + c.off_mt);
+    return e;
+}
+
+// per-env scratch of the step body (shared memory on the device)
+struct StepScratch {
+    uint8_t *act_build, *act_move, *act_buy, *act_sell;  // [A], [A], [2][A], [2][A]
+    uint8_t *act_tax;                                    // [16]
+    uint8_t *perm;                                       // [A]
+    double *tmp;                                         // [2A + 4]
+};
+AIE_DEV StepScratch step_scratch_view(uint8_t *p, const DevCfg &c) {
+    StepScratch s;
+    s.tmp = (double *)p;  p += 8 * (2 * c.A + 4);
+    s.act_build = p;      p += c.A;
+    s.act_move = p;       p += c.A;
+    s.act_buy = p;        p += 2 * c.A;
+    s.act_sell = p;       p += 2 * c.A;
+    s.perm = p;           p += c.A;
+    s.act_tax = p;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// numpy legacy MT19937 stream (bit-exact): mt19937_gen / mt19937_next / next_double / random_interval
+// ------------------------------------------------------------------------------------------------
+AIE_DEV uint32_t mt_temper(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+
+// One phase of the in-place twist: key[k] = key[k + MOFF] ^ f(key[k], key[k+1]) for k in [BASE, BASE+N).
+// Every lane first computes all of its outputs from the old values, then the warp syncs, then stores, so
+// reads of key[k+1] never see this phase's writes.
+template <int BASE, int N, int MOFF>
+AIE_DEV void mt_twist_phase(uint32_t *mt, int lane) {
+    constexpr int PER = (N + NL - 1) / NL;
+    uint32_t v[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        int k = BASE + lane + j * NL;
+        if (k < BASE + N) {
+            uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1] & 0x7fffffffu);
+            v[j] = mt[k + MOFF] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+    }
+    wsync();
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        int k = BASE + lane + j * NL;
+        if (k < BASE + N) mt[k] = v[j];
+    }
+    wsync();
+}
+
+// Warp-collective regeneration of the 624-word key.  Dependencies: new[0,227) <- old; new[227,454) <-
+// new[0,227); new[454,623) <- new[227,396); new[623] <- new[396], new[0].
+AIE_DEV void mt_twist(uint32_t *mt, int lane) {
+    wsync();
+    mt_twist_phase<0, 227, 397>(mt, lane);
+    mt_twist_phase<227, 227, -227>(mt, lane);
+    mt_twist_phase<454, 169, -227>(mt, lane);
+    if (lane == 0) {
+        uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    wsync();
+}
+
+struct Rng {
+    uint32_t *mt;
+    int pos;   // warp-uniform
+    int lane;
+};
+
+AIE_DEV uint32_t rng_next(Rng &r) {  // warp-uniform call
+    if (r.pos == 624) { mt_twist(r.mt, r.lane); r.pos = 0; }
+    return mt_temper(r.mt[r.pos++]);
+}
+AIE_DEV double rng_double(Rng &r) {  // np.random.rand()
+    int32_t a = (int32_t)(rng_next(r) >> 5);
+    int32_t b = (int32_t)(rng_next(r) >> 6);
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+}
+AIE_DEV uint32_t rng_interval(Rng &r, uint32_t max) {  // legacy random_interval, 32-bit path
+    if (max == 0) return 0;
+    uint32_t mask = max, v;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    while ((v = (rng_next(r) & mask)) > max) {}
+    return v;
+}
+// np.random.permutation(A) into scratch perm[] (world.get_random_order_agents, base/world.py:418-422)
+AIE_DEV void rng_permutation(Rng &r, uint8_t *perm, int A) {
+    for (int a = r.lane; a < A; a += NL) perm[a] = (uint8_t)a;
+    wsync();
+    for (int i = A - 1; i >= 1; i--) {
+        int j = (int)rng_interval(r, (uint32_t)i);
+        if (r.lane == 0) { uint8_t t = perm[j]; perm[j] = perm[i]; perm[i] = t; }
+        wsync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Actions  (BaseAgent.parse_actions, base/base_agent.py:407-438)
+// ------------------------------------------------------------------------------------------------
+AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t *act_a, const int32_t *act_p,
+                            int lane) {
+    for (int a = lane; a < c.A; a += NL) {
+        uint8_t build = 0, move = 0, buy0 = 0, buy1 = 0, sell0 = 0, sell1 = 0;
+        int g = (!c.multi_action && act_a) ? act_a[a] : 0;
+        for (int si = 0; si < c.n_sub; si++) {
+            int v;
+            if (c.multi_action) v = act_a ? act_a[a * c.n_sub + si] : 0;
+            else v = (g >= c.sub_lo[si] && g < c.sub_lo[si] + c.sub_n[si]) ? g - c.sub_lo[si] + 1 : 0;
+            if (v < 0 || v > c.sub_n[si]) v = 0;  // out-of-range input is treated as NO-OP
+            int kind = c.sub_kind[si];
+            if (kind == SUB_BUILD) build = (uint8_t)v;
+            else if (kind == SUB_GATHER) move = (uint8_t)v;
+            else if (kind == SUB_BUY) { if (c.sub_c[si] == 0) buy0 = (uint8_t)v; else buy1 = (uint8_t)v; }
+            else { if (c.sub_c[si] == 0) sell0 = (uint8_t)v; else sell1 = (uint8_t)v; }
+        }
+        s.act_build[a] = build; s.act_move[a] = move;
+        s.act_buy[a] = buy0; s.act_buy[c.A + a] = buy1;
+        s.act_sell[a] = sell0; s.act_sell[c.A + a] = sell1;
+    }
+    for (int b = lane; b < 16; b += NL) {
+        int v = (act_p && b < c.n_act_p) ? act_p[b] : 0;
+        if (v < 0 || v > c.R) v = 0;
+        s.act_tax[b] = (uint8_t)v;
+    }
+    wsync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Build  (components/build.py:70-83, 112-161)
+// ------------------------------------------------------------------------------------------------
+AIE_DEV bool can_build(const DevCfg &c, const Env &e, int a) {
+    int k = e.loc[2 * a] * c.W + e.loc[2 * a + 1];
+    // needs 1 Wood + 1 Stone; the cell must hold no resource and no landmark (House, Water, source block)
+    return e.inv[2 * a] >= 1 && e.inv[2 * a + 1] >= 1 && e.cell[k] == 0;
+}
+
+AIE_DEV void build_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
+    rng_permutation(r, s.perm, c.A);
+    for (int i = 0; i < c.A; i++) {
+        int a = s.perm[i];
+        const bool do_build = s.act_build[a] == 1 && can_build(c, e, a);
+        wsync();  // every lane has evaluated the predicate before lane 0 changes the state it reads
+        if (do_build) {
+            if (r.lane == 0) {
+                int k = e.loc[2 * a] * c.W + e.loc[2 * a + 1];
+                e.inv[2 * a] -= 1;
+                e.inv[2 * a + 1] -= 1;
+                e.cell[k] |= CELL_HOUSE;
+                e.owner[k] = (int8_t)a;
+                e.coin[a] += e.bpay[a];
+                e.labor[a] += c.build_labor;
+            }
+        }
+        wsync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ContinuousDoubleAuction  (components/continuous_double_auction.py)
+// ------------------------------------------------------------------------------------------------
+AIE_DEV uint32_t order_pack(int birth, int price, int side) { return ((uint32_t)birth << 8) | ((uint32_t)price << 1) | (uint32_t)side; }
+AIE_DEV int order_birth(uint32_t o) { return (int)(o >> 8); }
+AIE_DEV int order_price(uint32_t o) { return (int)((o >> 1) & 127u); }
+AIE_DEV int order_side(uint32_t o) { return (int)(o & 1u); }
+
+AIE_DEV void order_insert(uint32_t *slots, int K, uint32_t o) {
+    for (int k = 0; k < K; k++)
+        if (slots[k] == ORDER_EMPTY) { slots[k] = o; return; }
+}
+
+// :440-489 first half — price-history decay and order creation (create_bid :168-198, create_ask :200-229).
+// Each agent only touches its own state, so agents run lane-parallel; agent-index order of the reference's
+// loop survives as the final tie-break of the matching key.
+AIE_DEV void cda_create(const DevCfg &c, Env &e, const StepScratch &s, int t, int lane) {
+    const int A = c.A, P = c.P, K = c.K;
+    for (int a = lane; a < A; a += NL) {
+        for (int cc = 0; cc < 2; cc++) {
+            double *ph = e.price_hist + (cc * A + a) * P;
+            for (int p = 0; p < P; p++) ph[p] *= 0.995;
+            uint32_t *slots = e.orders + (cc * A + a) * K;
+            int kb = s.act_buy[cc * A + a];
+            if (kb != 0) {
+                int price = kb - 1;
+                if (e.n_orders[cc * A + a] < K && e.coin[a] >= (double)price) {
+                    order_insert(slots, K, order_pack(t, price, 0));
+                    e.bid_hist[(cc * A + a) * P + price] += 1;
+                    e.n_orders[cc * A + a] += 1;
+                    e.coin[a] -= (double)price;
+                    e.esc_coin[a] += (double)price;
+                    e.labor[a] += c.order_labor;
+                }
+            }
+            int ks = s.act_sell[cc * A + a];
+            if (ks != 0) {
+                int price = ks - 1;
+                if (e.n_orders[cc * A + a] < K && e.inv[2 * a + cc] > 0) {
+                    order_insert(slots, K, order_pack(t, price, 1));
+                    e.ask_hist[(cc * A + a) * P + price] += 1;
+                    e.n_orders[cc * A + a] += 1;
+                    e.inv[2 * a + cc] -= 1;
+                    e.esc[2 * a + cc] += 1;
+                    e.labor[a] += c.order_labor;
+                }
+            }
+        }
+    }
+    wsync();
+}
+
+// match_orders :231-350.  The reference stable-sorts bids by (price desc, lifetime desc) and asks by
+// (price asc, lifetime desc); ties keep creation order, i.e. agent index ascending.  Here the "first" bid
+// / ask is found by a warp max-reduction over packed keys (price | lifetime | 255 - agent) computed from the
+// order slots, with the same buyer-level `possible_match` bookkeeping and restart-from-top loop.
+AIE_DEV void cda_match(const DevCfg &c, Env &e, int t, int lane) {
+    const int A = c.A, P = c.P, K = c.K, n = A * K;
+    for (int cc = 0; cc < 2; cc++) {
+        uint32_t *slots = e.orders + cc * n;
+        uint64_t possible = (A >= 64) ? ~0ull : ((1ull << A) - 1ull);
+        for (;;) {
+            // best bid among still-possible buyers
+            uint32_t bk = 0, bi = 0;
+            for (int i = lane; i < n; i += NL) {
+                uint32_t o = slots[i];
+                if (o != ORDER_EMPTY && order_side(o) == 0) {
+                    int a = i / K;
+                    if ((possible >> a) & 1ull) {
+                        uint32_t key = ((uint32_t)(order_price(o) + 1) << 20) | ((uint32_t)(t - order_birth(o)) << 8) |
+                                       (uint32_t)(255 - a);
+                        if (key > bk) { bk = key; bi = (uint32_t)i; }
+                    }
+                }
+            }
+            uint32_t bmax = wmax(bk);
+            if (bmax == 0) break;  // idx_bid ran off the list: keep_checking = False
+            bi = wshfl(bi, first_lane(wballot(bk == bmax)));
+            int buyer = 255 - (int)(bmax & 255u);
+            int bprice = (int)(bmax >> 20) - 1;
+            int blife = (int)((bmax >> 8) & 4095u);
+            // first ask whose seller is not the buyer
+            uint32_t ak = 0, ai = 0;
+            for (int i = lane; i < n; i += NL) {
+                uint32_t o = slots[i];
+                if (o != ORDER_EMPTY && order_side(o) == 1) {
+                    int a = i / K;
+                    if (a != buyer) {
+                        uint32_t key = ((uint32_t)(P - order_price(o)) << 20) | ((uint32_t)(t - order_birth(o)) << 8) |
+                                       (uint32_t)(255 - a);
+                        if (key > ak) { ak = key; ai = (uint32_t)i; }
+                    }
+                }
+            }
+            uint32_t amax = wmax(ak);
+            if (amax == 0) { possible &= ~(1ull << buyer); if (!possible) break; continue; }
+            ai = wshfl(ai, first_lane(wballot(ak == amax)));
+            int seller = 255 - (int)(amax & 255u);
+            int aprice = P - (int)(amax >> 20);
+            int alife = (int)((amax >> 8) & 4095u);
+            if (bprice < aprice) { possible &= ~(1ull << buyer); if (!possible) break; continue; }
+            // trade: price of whichever order came first (:297-304)
+            int price = (blife <= alife) ? aprice : bprice;
+            if (lane == 0) {
+                slots[bi] = ORDER_EMPTY;
+                slots[ai] = ORDER_EMPTY;
+                e.bid_hist[(cc * A + buyer) * P + bprice] -= 1;
+                e.ask_hist[(cc * A + seller) * P + aprice] -= 1;
+                e.n_orders[cc * A + seller] -= 1;
+                e.n_orders[cc * A + buyer] -= 1;
+                e.price_hist[(cc * A + seller) * P + price] += 1.0;
+                e.esc[2 * seller + cc] -= 1;
+                e.inv[2 * buyer + cc] += 1;
+                e.esc_coin[buyer] -= (double)bprice;
+                e.coin[seller] += (double)price;
+                e.coin[buyer] += (double)(bprice - price);
+            }
+            wsync();
+        }
+    }
+}
+
+// remove_expired_orders :352-406.  lifetime after the increment is t - birth + 1; expired iff > D.
+AIE_DEV void cda_expire(const DevCfg &c, Env &e, int t, int lane) {
+    const int A = c.A, P = c.P, K = c.K;
+    for (int a = lane; a < A; a += NL) {
+        for (int cc = 0; cc < 2; cc++) {
+            uint32_t *slots = e.orders + (cc * A + a) * K;
+            for (int side = 0; side < 2; side++) {
+                for (int k = 0; k < K; k++) {
+                    uint32_t o = slots[k];
+                    if (o == ORDER_EMPTY || order_side(o) != side || t - order_birth(o) < c.D) continue;
+                    int price = order_price(o);
+                    if (side == 0) {
+                        e.esc_coin[a] -= (double)price;
+                        e.coin[a] += (double)price;
+                        e.bid_hist[(cc * A + a) * P + price] -= 1;
+                    } else {
+                        e.esc[2 * a + cc] -= 1;
+                        e.inv[2 * a + cc] += 1;
+                        e.ask_hist[(cc * A + a) * P + price] -= 1;
+                    }
+                    e.n_orders[cc * A + a] -= 1;
+                    slots[k] = ORDER_EMPTY;
+                }
+            }
+        }
+    }
+    wsync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather  (components/move.py:93-153; world.py:150-173, 284-288, 424-460, 481-483)
+// ------------------------------------------------------------------------------------------------
+AIE_DEV void gather_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
+    const int A = c.A, W = c.W, H = c.H, lane = r.lane;
+    rng_permutation(r, s.perm, A);
+    for (int i = 0; i < A; i++) {
+        int a = s.perm[i], action = s.act_move[a];
+        int row = e.loc[2 * a], col = e.loc[2 * a + 1], nr = row, nc = col;
+        if (action != 0) {
+            int tr = row + (action == 3 ? -1 : (action == 4 ? 1 : 0));
+            int tc = col + (action == 1 ? -1 : (action == 2 ? 1 : 0));
+            bool ok = tr >= 0 && tr < H && tc >= 0 && tc < W;
+            if (ok) {
+                int k = tr * W + tc;
+                uint8_t cb = e.cell[k];
+                int8_t ow = e.owner[k];
+                ok = !(cb & CELL_WATER) && (ow < 0 || ow == a);  // Maps.accessibility
+            }
+            bool occ = false;  // Maps.unoccupied: is any agent standing on the target cell?
+            if (ok)
+                for (int a2 = lane; a2 < A; a2 += NL) occ |= (e.loc[2 * a2] == tr && e.loc[2 * a2 + 1] == tc);
+            occ = wany(occ);
+            if (ok && !occ) {
+                nr = tr; nc = tc;
+                wsync();
+                if (lane == 0) {
+                    e.loc[2 * a] = (int16_t)nr; e.loc[2 * a + 1] = (int16_t)nc;
+                    e.labor[a] += c.move_labor;
+                }
+            }
+        }
+        // harvest at the (possibly unchanged) location — also on NO-OP.  Resource order Stone, Wood.
+        int k = nr * W + nc;
+        uint8_t cb = e.cell[k];
+        for (int cc = 0; cc < 2; cc++) {
+            if (cb & (1u << cc)) {
+                double u = rng_double(r);  // drawn even when bonus_gather_prob == 0
+                int n_gathered = 1 + (u < e.bonus[a] ? 1 : 0);
+                wsync();
+                if (lane == 0) {
+                    e.inv[2 * a + cc] += n_gathered;
+                    e.cell[k] = (uint8_t)(e.cell[k] & ~(1u << cc));
+                    e.labor[a] += c.collect_labor;
+                }
+            }
+        }
+        wsync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PeriodicBracketTax  (components/redistribution.py)
+// ------------------------------------------------------------------------------------------------
+AIE_DEV double tax_rate(const DevCfg &c, const Env &e, int b) {  // curr_marginal_rates :381-405
+    return c.tax_model == 0 ? c.disc_rates[e.rate_idx[b]] : c.fixed_rates[b];
+}
+AIE_DEV double tax_marginal_rate(const DevCfg &c, const Env &e, double income) {  // :837-844
+    if (income < 0) return 0.0;
+    int arg = 0;
+    for (int b = c.B - 1; b >= 0; b--) {
+        double hi = (b + 1 < c.B) ? c.cutoffs[b + 1] : INFINITY;
+        if (income >= c.cutoffs[b] && income < hi) arg = b;
+    }
+    return tax_rate(c, e, arg);
+}
+AIE_DEV double tax_due(const DevCfg &c, const Env &e, double income) {  // :846-851
+    double sum = 0.0;
+    for (int b = 0; b < c.B; b++) {
+        double size = ((b + 1 < c.B) ? c.cutoffs[b + 1] : INFINITY) - c.cutoffs[b];
+        double past = fmax(0.0, income - c.cutoffs[b]);
+        sum += tax_rate(c, e, b) * fmin(size, past);
+    }
+    return sum;
+}
+
+AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, int lane) {  // :945-972
+    const int A = c.A;
+    int pos = e.hdr[HDR_TAX_POS];
+    if (pos == 1 && c.tax_model == 0 && !c.disable_taxes) {  // set_new_period_rates_model :419-434
+        for (int b = lane; b < c.B; b += NL) {
+            int act = s.act_tax[b];
+            if (act != 0) e.rate_idx[b] = (uint8_t)(act - 1);
+        }
+        wsync();
+    }
+    if (pos >= c.period) {  // enact_taxes :853-915
+        for (int a = lane; a < A; a += NL) {
+            double income = (e.coin[a] + e.esc_coin[a]) - e.last_coin[a];
+            double due = tax_due(c, e, income);
+            double paid = fmin(e.coin[a], due);  // never touches escrow
+            e.last_marg[a] = tax_marginal_rate(c, e, income);
+            e.last_income[a] = income;
+            e.coin[a] -= paid;
+            s.tmp[a] = paid;
+        }
+        wsync();
+        double net = 0.0;
+        for (int a = 0; a < A; a++) net += s.tmp[a];  // sequential, agent order (uniform)
+        double lump = net / A;
+        for (int a = lane; a < A; a += NL) {
+            e.coin[a] += lump;
+            e.last_coin[a] = e.coin[a] + e.esc_coin[a];
+        }
+        pos = 0;
+    }
+    pos += 1;
+    wsync();
+    if (lane == 0) e.hdr[HDR_TAX_POS] = pos;
+    wsync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resource regeneration (layout_from_file.py:372-410): for resource in [Wood, Stone], one uniform per cell
+// in row-major order; an empty source cell respawns iff u < regen_weight.  The whole 2*H*W-word run of the
+// stream is consumed; only empty source cells temper/compare their two words.
+// ------------------------------------------------------------------------------------------------
+AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
+    const int HW = c.HW, lane = r.lane;
+    const uint8_t res_bit = (uint8_t)(1u << cc), src_bit = (uint8_t)(4u << cc);
+    const uint64_t thresh = c.regen_thresh[cc];
+    int w = 0;                 // words of this run consumed so far (warp-uniform)
+    const int total = 2 * HW;
+    uint32_t pend_a = 0;       // first word of a cell that straddles a key regeneration
+    while (w < total) {
+        if (r.pos == 624) { mt_twist(r.mt, lane); r.pos = 0; }
+        int n = 624 - r.pos;
+        if (n > total - w) n = total - w;
+        int w_end = w + n;
+        const int base = r.pos - w;  // key index of run word j is base + j
+        if (w & 1) {                 // finish the straddling cell with its second word
+            int k = w >> 1;
+            if (lane == 0) {
+                uint8_t cb = e.cell[k];
+                if ((cb & src_bit) && !(cb & res_bit)) {
+                    uint64_t v = ((uint64_t)(pend_a >> 5) << 26) | (uint64_t)(mt_temper(e.mt[base + w]) >> 6);
+                    if (v < thresh) e.cell[k] = cb | res_bit;
+                }
+            }
+        }
+        int k_lo = (w + 1) >> 1, k_hi = w_end >> 1;  // cells with both words inside this segment
+        for (int k = k_lo + lane; k < k_hi; k += NL) {
+            uint8_t cb = e.cell[k];
+            if ((cb & src_bit) && !(cb & res_bit)) {
+                uint64_t v = ((uint64_t)(mt_temper(e.mt[base + 2 * k]) >> 5) << 26) |
+                             (uint64_t)(mt_temper(e.mt[base + 2 * k + 1]) >> 6);
+                if (v < thresh) e.cell[k] = cb | res_bit;
+            }
+        }
+        if (w_end & 1) pend_a = mt_temper(e.mt[base + w_end - 1]);
+        wsync();
+        r.pos += n;
+        w = w_end;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Utilities / rewards (layout_from_file.py:249-318, 519-559; rewards.py:12-48, 84-133;
+// social_metrics.py:10-46)
+// ------------------------------------------------------------------------------------------------
+AIE_DEV double energy_weight(const DevCfg &c, const Env &e) {
+    if (c.warm_const <= 0.0) return 1.0;
+    double n = c.warm_auto ? (double)e.hdr[HDR_AUTO_WARMUP] : (double)e.hdr[HDR_COMPLETIONS];
+    return 1.0 - exp(-n / c.warm_const);
+}
+
+// Writes util[0..A] (agents, then planner) into `out` (scratch or record).  Warp-collective.
+AIE_DEV void current_metrics(const DevCfg &c, const Env &e, double *out, double *tmp, int lane) {
+    const int A = c.A;
+    const double coef = energy_weight(c, e) * c.energy_cost;
+    for (int a = lane; a < A; a += NL) {
+        double x = e.coin[a] + e.esc_coin[a];
+        double util_c = (c.eta == 1.0) ? log(fmax(1.0, x)) : (pow(x, 1.0 - c.eta) - 1.0) / (1.0 - c.eta);
+        out[a] = util_c - e.labor[a] * coef;
+    }
+    wsync();
+    double planner;
+    if (c.swf == 0) {  // coin_eq_times_productivity
+        double total = 0.0;
+        for (int a = 0; a < A; a++) total += e.coin[a] + e.esc_coin[a];  // uniform, agent order
+        double gini;
+        if (A < 30) {
+            double part = 0.0;
+            for (int i = lane; i < A; i += NL) {
+                double xi = e.coin[i] + e.esc_coin[i];
+                for (int j = 0; j < A; j++) part += fabs(xi - (e.coin[j] + e.esc_coin[j]));
+            }
+            double diff = wsum(part);
+            gini = (diff / (2 * A * total + 1e-10)) / ((A - 1) / (double)A);
+        } else {  // sort-based branch: rank each endowment, scatter to sorted order, then cumulative sums
+            for (int i = lane; i < A; i += NL) {
+                double xi = e.coin[i] + e.esc_coin[i];
+                int rank = 0;
+                for (int j = 0; j < A; j++) {
+                    double xj = e.coin[j] + e.esc_coin[j];
+                    rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0;
+                }
+                tmp[rank] = xi;
+            }
+            wsync();
+            double tot = 0.0, cum = 0.0, acc = 0.0;
+            for (int i = 0; i < A; i++) tot += tmp[i];
+            for (int i = 0; i < A; i++) { cum += tmp[i]; acc += cum / (tot + 1e-10); }
+            gini = 1.0 - (2.0 / (A + 1)) * acc;
+        }
+        double eqw = 1.0 - c.mix;
+        planner = (eqw * (1.0 - gini) + (1.0 - eqw)) * (total / A);
+    } else {
+        double wsum_ = 0.0, acc = 0.0;
+        for (int a = 0; a < A; a++) wsum_ += 1.0 / fmax(e.coin[a] + e.esc_coin[a], 1.0);
+        for (int a = 0; a < A; a++) {
+            double x = e.coin[a] + e.esc_coin[a];
+            double wgt = (1.0 / fmax(x, 1.0)) / wsum_;
+            acc += (c.swf == 1 ? x : out[a]) * wgt;
+        }
+        planner = acc;
+    }
+    wsync();
+    if (lane == 0) out[A] = planner;
+    wsync();
+}
+
+// numpy's pairwise_sum for n <= 128 (numpy/core/src/umath/loops_utils.h.src): plain loop below 8 elements,
+// otherwise 8 interleaved accumulators combined as a tree plus a sequential tail.  Warp-uniform.
+AIE_DEV double np_pairwise_sum(const double *a, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, double *rew_out, int lane) {
+    const int A = c.A;
+    double *cur = s.tmp;  // [A+1] new metrics; the second half of tmp is sort / staging scratch
+    current_metrics(c, e, cur, cur + (A + 2), lane);
+    double *rw_s = cur + (A + 2);  // rewards staged so the mean can be formed in numpy's summation order
+    for (int a = lane; a <= A; a += NL) {
+        double rw = cur[a] - e.util_prev[a];
+        if (rew_out) rew_out[a] = rw;
+        rw_s[a] = rw;
+    }
+    wsync();
+    const double avg = np_pairwise_sum(rw_s, A) / A;  // np.mean([...]) (layout_from_file.py:552)
+    for (int a = lane; a <= A; a += NL) e.util_prev[a] = cur[a];
+    if (lane == 0 && avg > 0) e.hdr[HDR_AUTO_WARMUP] += 1;
+    wsync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// One env.step() (base/base_env.py:929-1032) without the observation pass.
+// ------------------------------------------------------------------------------------------------
+AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const int32_t *act_a, const int32_t *act_p,
+                      double *rew_out, int32_t *done_out, int lane) {
+    Env e = env_view(rec, c);
+    StepScratch s = step_scratch_view(scratch, c);
+    decode_actions(c, s, act_a, act_p, lane);
+    Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
+    const int t = e.hdr[HDR_T] + 1;
+    wsync();
+    if (lane == 0) e.hdr[HDR_T] = t;
+    for (int i = 0; i < c.n_comp; i++) {
+        switch (c.comp[i]) {
+            case COMP_BUILD: build_step(c, e, s, r); break;
+            case COMP_CDA: cda_create(c, e, s, t, lane); cda_match(c, e, t, lane); cda_expire(c, e, t, lane); break;
+            case COMP_GATHER: gather_step(c, e, s, r); break;
+            case COMP_TAX: tax_step(c, e, s, lane); break;
+        }
+    }
+    regen_resource(c, e, 1, r);  // Wood
+    regen_resource(c, e, 0, r);  // Stone
+    compute_reward(c, e, s, rew_out, lane);
+    if (lane == 0) {
+        e.hdr[HDR_MT_POS] = r.pos;
+        if (done_out) *done_out = (t >= c.T) ? 1 : 0;
+    }
+    wsync();
+}
+
+// Finish a host reset on the device: tax trackers + metric_0 (redistribution.py:1106-1139,
+// layout_from_file.py:588-593).  The host packer has already zeroed books, escrow, labor.
+AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, int lane) {
+    Env e = env_view(rec, c);
+    StepScratch s = step_scratch_view(scratch, c);
+    for (int a = lane; a < c.A; a += NL) {
+        e.last_coin[a] = e.coin[a] + e.esc_coin[a];
+        e.last_income[a] = 0.0;
+        e.last_marg[a] = 0.0;
+    }
+    wsync();
+    current_metrics(c, e, e.util_prev, s.tmp, lane);
+    wsync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Observations + masks.  Block-collective on the device (tid / nthr over one CTA), serial in emulation.
+// ------------------------------------------------------------------------------------------------
+#if AIE_ON_DEVICE
+AIE_DEV void bsync() { __syncthreads(); }
+#else
+AIE_DEV void bsync() {}
+#endif
+
+struct ObsScratch {
+    double *net_hist;     // [2][P]
+    double *market_rate;  // [2]
+    double *marg;         // [A]   marginal rate at current income
+    double *sorted_inc;   // [A]   last incomes / period, ascending
+    double *tax_scalars;  // [4]   is_tax_day, is_first_day, tax_phase, annealed limit
+    uint16_t *full_asks, *full_bids;  // [2][P]
+    uint8_t *locmap;      // [HW]  0 none, a+2
+    uint8_t *agent_bits;  // [A]   bit0 can_build, bits1-4 gather L,R,U,D
+};
+AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
+    ObsScratch s;
+    s.net_hist = (double *)p;     p += 8 * 2 * c.P;
+    s.market_rate = (double *)p;  p += 8 * 2;
+    s.marg = (double *)p;         p += 8 * c.A;
+    s.sorted_inc = (double *)p;   p += 8 * c.A;
+    s.tax_scalars = (double *)p;  p += 8 * 4;
+    s.full_asks = (uint16_t *)p;  p += 2 * 2 * c.P;
+    s.full_bids = (uint16_t *)p;  p += 2 * 2 * c.P;
+    s.agent_bits = p;             p += c.A;
+    s.locmap = p;
+    return s;
+}
+
+AIE_DEV double flat_value(const DevCfg &c, const Env &e, const ObsScratch &s, uint16_t entry, int a, double time_v,
+                          double inv_scale) {
+    const int idx = AIE_PROG_IDX(entry), cc = AIE_PROG_C(entry), A = c.A, P = c.P;
+    switch (AIE_PROG_FIELD(entry)) {
+        case F_BUILD_PAYMENT: return e.bpay[a] / c.build_payment;
+        case F_BUILD_SKILL: return e.bskill[a];
+        case F_AVAIL_ASKS: return (double)((int)s.full_asks[cc * P + idx] - (int)e.ask_hist[(cc * A + a) * P + idx]);
+        case F_AVAIL_BIDS: return (double)((int)s.full_bids[cc * P + idx] - (int)e.bid_hist[(cc * A + a) * P + idx]);
+        case F_MARKET_RATE: return s.market_rate[cc];
+        case F_MY_ASKS: return (double)e.ask_hist[(cc * A + a) * P + idx];
+        case F_MY_BIDS: return (double)e.bid_hist[(cc * A + a) * P + idx];
+        case F_PRICE_HIST: return s.net_hist[cc * P + idx] * inv_scale;
+        case F_BONUS: return e.bonus[a];
+        case F_TAX_CURR_RATES: return tax_rate(c, e, idx);
+        case F_TAX_IS_FIRST: return s.tax_scalars[1];
+        case F_TAX_IS_TAX_DAY: return s.tax_scalars[0];
+        case F_TAX_LAST_INCOMES: return s.sorted_inc[idx];
+        case F_TAX_MARG: return s.marg[a];
+        case F_TAX_PHASE: return s.tax_scalars[2];
+        case F_TIME: return time_v;
+        case F_INV_COIN: return e.coin[a] * inv_scale;
+        case F_INV_STONE: return e.inv[2 * a] * inv_scale;
+        case F_INV_WOOD: return e.inv[2 * a + 1] * inv_scale;
+        case F_LOC_COL: return (double)e.loc[2 * a + 1] / c.W;
+        case F_LOC_ROW: return (double)e.loc[2 * a] / c.H;
+        case F_FULL_ASKS: return (double)s.full_asks[cc * P + idx];
+        case F_FULL_BIDS: return (double)s.full_bids[cc * P + idx];
+        case F_TAX_LAST_INCOME: return e.last_income[a] / c.period;
+        case F_TAX_LAST_MARG: return e.last_marg[a];
+        default: return 0.0;
+    }
+}
+
+// map channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSourceBlock, WoodSourceBlock)
+AIE_DEV uint8_t channel_bit(const DevCfg &c, int ch) {
+    if (ch == 0) return CELL_STONE;
+    if (ch == 1) return CELL_WOOD;
+    if (ch == 2) return CELL_HOUSE;
+    if (c.has_water) { if (ch == 3) return CELL_WATER; ch -= 1; }
+    return ch == 3 ? CELL_STONE_SRC : CELL_WOOD_SRC;
+}
+
+struct ObsOut {  // pointers already offset to this env
+    float *a_map; int16_t *a_idx; float *a_flat; float *a_mask;
+    float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask; float *time_obs;
+};
+
+AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const ObsOut &o, int tid, int nthr) {
+    const Env e = env_view(rec, c);
+    const ObsScratch s = obs_scratch_view(scratch, c);
+    const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
+    const double inv_scale = c.obs_scaling ? 0.01 : 1.0;
+    const double time_v = (double)e.hdr[HDR_T] / (c.obs_scaling ? (double)c.T : 1.0);
+
+    // ---- phase 1: per-env shared quantities -------------------------------------------------------
+    for (int k = tid; k < HW; k += nthr) s.locmap[k] = 0;
+    if (c.has[COMP_CDA]) {
+        for (int i = tid; i < 2 * P; i += nthr) {  // i = cc * P + p; sums over agents in index order
+            int cc = i / P, p = i - cc * P;
+            double acc = 0.0; int fa = 0, fb = 0;
+            for (int a = 0; a < A; a++) {
+                acc += e.price_hist[(cc * A + a) * P + p];
+                fa += e.ask_hist[(cc * A + a) * P + p];
+                fb += e.bid_hist[(cc * A + a) * P + p];
+            }
+            s.net_hist[i] = acc; s.full_asks[i] = (uint16_t)fa; s.full_bids[i] = (uint16_t)fb;
+        }
+    }
+    if (c.has[COMP_TAX]) {
+        int pos = e.hdr[HDR_TAX_POS];
+        if (tid == 0) {
+            s.tax_scalars[0] = pos >= c.period ? 1.0 : 0.0;
+            s.tax_scalars[1] = pos == 1 ? 1.0 : 0.0;
+            s.tax_scalars[2] = (double)pos / c.period;
+            // components/utils.py:10-57: current annealed |rate| limit for the planner mask
+            double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)e.hdr[HDR_COMPLETIONS] - c.ann_warm)));
+            s.tax_scalars[3] = vis * c.ann_full;
+        }
+        for (int a = tid; a < A; a += nthr) {
+            s.marg[a] = tax_marginal_rate(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
+            double v = e.last_income[a] / c.period;  // ascending rank -> sorted position (:908-911)
+            int rank = 0;
+            for (int j = 0; j < A; j++) {
+                double vj = e.last_income[j] / c.period;
+                rank += (vj < v || (vj == v && j < a)) ? 1 : 0;
+            }
+            s.sorted_inc[rank] = v;
+        }
+    }
+    bsync();
+    for (int a = tid; a < A; a += nthr) {
+        const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
+        s.locmap[row * W + col] = (uint8_t)(a + 2);
+    }
+    if (c.has[COMP_CDA])
+        for (int cc = tid; cc < 2; cc += nthr) {  // market_rate (:504-513)
+            double dot = 0.0, tot = 0.0;
+            for (int p = 0; p < P; p++) { dot += p * s.net_hist[cc * P + p]; tot += s.net_hist[cc * P + p]; }
+            s.market_rate[cc] = dot / fmax(0.001, tot);
+        }
+    bsync();
+    for (int a = tid; a < A; a += nthr) {  // build mask + Gather mask bits (build.py:180-193, move.py:167-188)
+        uint8_t bits = can_build(c, e, a) ? 1 : 0;
+        const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
+        const int roff[4] = {0, 0, -1, 1}, coff[4] = {-1, 1, 0, 0};
+        for (int d = 0; d < 4; d++) {
+            int r2 = row + roff[d], c2 = col + coff[d];
+            bool ok = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
+            if (ok) {
+                int k = r2 * W + c2;
+                int8_t ow = e.owner[k];
+                ok = s.locmap[k] == 0 && !(e.cell[k] & CELL_WATER) && (ow < 0 || ow == a);
+            }
+            if (ok) bits |= (uint8_t)(2u << d);
+        }
+        s.agent_bits[a] = bits;
+    }
+    bsync();
+
+    // ---- phase 2: outputs ----------------------------------------------------------------------
+    if (tid == 0) o.time_obs[0] = (float)time_v;
+    if (c.planner_spatial) {
+        for (int i = tid; i < M * HW; i += nthr) {
+            int ch = i / HW, k = i - ch * HW;
+            o.p_map[i] = (e.cell[k] & channel_bit(c, ch)) ? 1.0f : 0.0f;
+        }
+        for (int k = tid; k < HW; k += nthr) {
+            int ow = e.owner[k];
+            o.p_idx[k] = (int16_t)(ow < 0 ? 0 : ow + 2);
+            o.p_idx[HW + k] = (int16_t)s.locmap[k];
+        }
+    }
+    // agent windows (layout_from_file.py:468-515)
+    for (int i = tid; i < A * (M + 1) * ww; i += nthr) {
+        int a = i / ((M + 1) * ww), rem = i - a * (M + 1) * ww;
+        int ch = rem / ww, q = rem - ch * ww;
+        int dr = q / win, dc = q - dr * win;
+        int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
+        bool inside = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
+        float v = 0.0f;
+        if (inside) v = (ch == M) ? 1.0f : ((e.cell[r2 * W + c2] & channel_bit(c, ch)) ? 1.0f : 0.0f);
+        o.a_map[i] = v;
+    }
+    for (int i = tid; i < A * 2 * ww; i += nthr) {
+        int a = i / (2 * ww), rem = i - a * 2 * ww;
+        int ch = rem / ww, q = rem - ch * ww;
+        int dr = q / win, dc = q - dr * win;
+        int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
+        int v = 0;
+        if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W) {
+            int k = r2 * W + c2;
+            if (ch == 0) { int ow = e.owner[k]; v = ow < 0 ? 0 : ow + 2; }
+            else v = s.locmap[k];
+            if (v == a + 2) v = 1;
+        }
+        o.a_idx[i] = (int16_t)v;
+    }
+    // flat vectors (base_env.py:562-612: sorted-key concatenation, float32)
+    for (int i = tid; i < A * c.Fa; i += nthr) {
+        int a = i / c.Fa, j = i - a * c.Fa;
+        o.a_flat[i] = (float)flat_value(c, e, s, c.prog_a[j], a, time_v, inv_scale);
+    }
+    for (int j = tid; j < c.Fp; j += nthr) o.p_flat[j] = (float)flat_value(c, e, s, c.prog_p[j], 0, time_v, inv_scale);
+    for (int i = tid; i < A * c.Fpa; i += nthr) {
+        int a = i / c.Fpa, j = i - a * c.Fpa;
+        o.p_agents[i] = (float)flat_value(c, e, s, c.prog_pa[j], a, time_v, inv_scale);
+    }
+    // masks (base_agent.py:440-460)
+    for (int i = tid; i < A * c.Na; i += nthr) {
+        int a = i / c.Na, j = i - a * c.Na;
+        uint16_t en = c.mprog_a[j];
+        int idx = AIE_PROG_IDX(en), cc = AIE_PROG_C(en);
+        bool v;
+        switch (AIE_PROG_FIELD(en)) {
+            case MK_BUILD: v = s.agent_bits[a] & 1; break;
+            case MK_BUY: v = e.n_orders[cc * A + a] < c.K && (double)idx <= e.coin[a]; break;
+            case MK_SELL: v = e.n_orders[cc * A + a] < c.K && e.inv[2 * a + cc] > 0; break;
+            case MK_GATHER: v = (s.agent_bits[a] >> (1 + idx)) & 1; break;
+            default: v = true;
+        }
+        o.a_mask[i] = v ? 1.0f : 0.0f;
+    }
+    if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
+        for (int j = tid; j < c.Np; j += nthr) {
+            int rr = j % (1 + c.R);
+            float v = 1.0f;
+            if (rr != 0) {
+                bool open = e.hdr[HDR_TAX_POS] == 1;
+                if (open && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.tax_scalars[3];
+                v = open ? 1.0f : 0.0f;
+            }
+            o.p_mask[j] = v;
+        }
+    } else if (tid == 0) {
+        o.p_mask[0] = 1.0f;
+    }
+}
+
+}  // namespace aie

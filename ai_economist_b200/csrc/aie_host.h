@@ -1,0 +1,331 @@
+// aie_host.h — host-side logic of the C-ABI that needs no CUDA: config validation, record layout,
+// observation/mask "programs" (the reference's sorted-key flattening resolved once), packing a host reset
+// snapshot into state records and unpacking a record for test readback.
+#pragma once
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/aie_b200.h"
+#include "aie_layout.h"
+
+namespace aie {
+
+inline int align16(int x) { return (x + 15) & ~15; }
+
+struct FlatKey { std::string key; int field, c, n; };
+
+// Mirrors BaseEnvironment._build_packager / _package (base_env.py:562-612): every scalar / 1-D field is
+// concatenated in sorted key order.  Keys are the reference's: "<Component>-<obs>" / "world-<obs>" / "time".
+inline int build_prog(std::vector<FlatKey> keys, uint16_t *prog, int cap) {
+    std::sort(keys.begin(), keys.end(), [](const FlatKey &a, const FlatKey &b) { return a.key < b.key; });
+    int n = 0;
+    for (const FlatKey &k : keys)
+        for (int i = 0; i < k.n; i++) {
+            if (n >= cap) return -1;
+            prog[n++] = AIE_PROG_ENTRY(k.field, k.c, i);
+        }
+    return n;
+}
+
+// Returns 0 or AIE_EINVAL with a message in err.
+inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, std::string &err) {
+    memset(&c, 0, sizeof(c));
+    auto bad = [&](const char *m) { err = m; return AIE_EINVAL; };
+    if (u.abi_version != AIE_ABI_VERSION) return bad("abi_version mismatch");
+    if (n_envs < 1) return bad("n_envs must be >= 1");
+    if (u.n_agents < 2 || u.n_agents > AIE_MAX_AGENTS) return bad("n_agents must be in [2, 64]");
+    if (u.height < 1 || u.width < 1 || u.height > 256 || u.width > 256) return bad("world size must be within 256x256");
+    if (u.episode_length < 1 || u.episode_length >= (1 << 23)) return bad("episode_length out of range");
+    if (u.n_components < 1 || u.n_components > AIE_MAX_COMPONENTS) return bad("1..4 components");
+    if (u.obs_range < 0 || u.obs_range > 32) return bad("mobile_agent_observation_range out of range");
+    c.A = u.n_agents; c.H = u.height; c.W = u.width; c.HW = u.height * u.width; c.T = u.episode_length;
+    c.multi_action = u.multi_action_agents ? 1 : 0;
+    c.n_comp = u.n_components;
+    for (int i = 0; i < u.n_components; i++) {
+        int k = u.components[i];
+        if (k < 0 || k > 3) return bad("unknown component kind");
+        if (c.has[k]) return bad("duplicate component");
+        c.comp[i] = k; c.has[k] = 1;
+    }
+    c.has_water = u.has_water ? 1 : 0;
+    c.M = c.has_water ? 6 : 5;
+    c.w = u.obs_range; c.win = 2 * u.obs_range + 1;
+    c.planner_spatial = u.planner_gets_spatial_info ? 1 : 0;
+    c.obs_scaling = u.allow_observation_scaling ? 1 : 0;
+    for (int r = 0; r < 2; r++) {
+        double w = u.regen_weight[r];
+        if (!(w >= 0.0 && w <= 1.0)) return bad("regen weight must be in [0, 1]");
+        c.regen_thresh[r] = (uint64_t)ceil(ldexp(w, 53));  // exact: N / 2^53 < w  <=>  N < ceil(w * 2^53)
+    }
+    c.eta = u.isoelastic_eta; c.energy_cost = u.energy_cost; c.warm_const = u.energy_warmup_constant;
+    if (!(c.eta >= 0.0 && c.eta <= 1.0)) return bad("isoelastic_eta must be in [0, 1]");
+    c.warm_auto = u.energy_warmup_auto ? 1 : 0;
+    c.swf = u.planner_reward_type;
+    if (c.swf < 0 || c.swf > 2) return bad("unknown planner_reward_type");
+    c.mix = u.mixing_weight_gini_vs_coin;
+    c.build_payment = u.build_payment; c.build_labor = u.build_labor;
+    c.move_labor = u.move_labor; c.collect_labor = u.collect_labor; c.order_labor = u.order_labor;
+    c.P = u.max_bid_ask + 1; c.D = u.order_duration; c.K = u.max_num_orders;
+    if (c.has[COMP_CDA]) {
+        if (c.P < 2 || c.P > AIE_MAX_PRICE_LEVELS) return bad("max_bid_ask must be in [1, 31]");
+        if (c.D < 1 || c.D > 4095) return bad("order_duration must be in [1, 4095]");
+        if (c.K < 1 || c.K > 255) return bad("max_num_orders must be in [1, 255]");
+    } else { c.P = 1; c.D = 1; c.K = 1; }
+    c.tax_model = u.tax_model; c.disable_taxes = u.disable_taxes ? 1 : 0; c.period = u.period;
+    c.B = u.n_brackets; c.R = u.n_disc_rates;
+    if (c.has[COMP_TAX]) {
+        if (c.tax_model != AIE_TAX_MODEL_WRAPPER && c.tax_model != AIE_TAX_FIXED_RATES) return bad("unsupported tax_model");
+        if (c.B < 2 || c.B > AIE_MAX_BRACKETS) return bad("n_brackets must be in [2, 16]");
+        if (c.tax_model == AIE_TAX_MODEL_WRAPPER && (c.R < 1 || c.R > AIE_MAX_RATES)) return bad("n_disc_rates must be in [1, 64]");
+        if (c.period < 1) return bad("tax period must be >= 1");
+        for (int b = 0; b < c.B; b++) { c.cutoffs[b] = u.bracket_cutoffs[b]; c.fixed_rates[b] = u.fixed_rates[b]; }
+        for (int r = 0; r < c.R; r++) { c.disc_rates[r] = u.disc_rates[r]; c.ann_full = fmax(c.ann_full, fabs(u.disc_rates[r])); }
+    } else { c.B = 0; c.R = 0; c.period = 1; }
+    c.tax_annealing = u.tax_annealing ? 1 : 0;
+    c.ann_warm = u.annealing_warmup; c.ann_slope = u.annealing_slope; c.rate_max = u.rate_max;
+    c.auto_reset = u.auto_reset ? 1 : 0;
+    c.n_envs = n_envs;
+
+    // action subspaces in component-list order (base_agent.py:124-169)
+    int lo = 1, n_single = 0;
+    for (int i = 0; i < c.n_comp; i++) {
+        auto add = [&](int kind, int cc, int n) {
+            c.sub_kind[c.n_sub] = kind; c.sub_c[c.n_sub] = cc; c.sub_n[c.n_sub] = n; c.sub_lo[c.n_sub] = lo;
+            lo += n; n_single += n; c.n_sub++;
+        };
+        if (c.comp[i] == COMP_BUILD) add(SUB_BUILD, 0, 1);
+        else if (c.comp[i] == COMP_CDA) { for (int cc = 0; cc < 2; cc++) { add(SUB_BUY, cc, c.P); add(SUB_SELL, cc, c.P); } }
+        else if (c.comp[i] == COMP_GATHER) add(SUB_GATHER, 0, 4);
+    }
+    c.n_act_a = c.multi_action ? c.n_sub : 1;
+    if (c.n_sub == 0) return bad("mobile agents need at least one action component");
+    c.planner_acts = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_MODEL_WRAPPER && !c.disable_taxes) ? 1 : 0;
+    c.n_act_p = c.planner_acts ? c.B : 0;
+    c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;
+    c.Np = c.planner_acts ? c.B * (1 + c.R) : 1;
+    if (c.Na > MAX_MASK) return bad("agent action mask too long");
+
+    // mask program (base_agent.py:440-460)
+    {
+        int n = 0;
+        if (!c.multi_action) c.mprog_a[n++] = AIE_PROG_ENTRY(MK_ONE, 0, 0);
+        for (int si = 0; si < c.n_sub; si++) {
+            if (c.multi_action) c.mprog_a[n++] = AIE_PROG_ENTRY(MK_ONE, 0, 0);
+            for (int j = 0; j < c.sub_n[si]; j++) {
+                int kind = c.sub_kind[si] == SUB_BUILD ? MK_BUILD : c.sub_kind[si] == SUB_BUY ? MK_BUY
+                           : c.sub_kind[si] == SUB_SELL ? MK_SELL : MK_GATHER;
+                c.mprog_a[n++] = AIE_PROG_ENTRY(kind, c.sub_c[si], j);
+            }
+        }
+    }
+    // flat programs
+    {
+        static const char *CN[2] = {"Stone", "Wood"};
+        std::vector<FlatKey> ka, kp, kpa;
+        auto K = [](const std::string &k, int f, int cc, int n) { return FlatKey{k, f, cc, n}; };
+        ka.push_back(K("world-loc-row", F_LOC_ROW, 0, 1)); ka.push_back(K("world-loc-col", F_LOC_COL, 0, 1));
+        ka.push_back(K("world-inventory-Coin", F_INV_COIN, 0, 1)); ka.push_back(K("world-inventory-Stone", F_INV_STONE, 0, 1));
+        ka.push_back(K("world-inventory-Wood", F_INV_WOOD, 0, 1)); ka.push_back(K("time", F_TIME, 0, 1));
+        kp.push_back(K("world-inventory-Coin", F_ZERO, 0, 1)); kp.push_back(K("world-inventory-Stone", F_ZERO, 0, 1));
+        kp.push_back(K("world-inventory-Wood", F_ZERO, 0, 1)); kp.push_back(K("time", F_TIME, 0, 1));
+        kpa.push_back(K("world-inventory-Coin", F_INV_COIN, 0, 1)); kpa.push_back(K("world-inventory-Stone", F_INV_STONE, 0, 1));
+        kpa.push_back(K("world-inventory-Wood", F_INV_WOOD, 0, 1));
+        if (c.planner_spatial) { kpa.push_back(K("world-loc-row", F_LOC_ROW, 0, 1)); kpa.push_back(K("world-loc-col", F_LOC_COL, 0, 1)); }
+        if (c.has[COMP_BUILD]) { ka.push_back(K("Build-build_payment", F_BUILD_PAYMENT, 0, 1)); ka.push_back(K("Build-build_skill", F_BUILD_SKILL, 0, 1)); }
+        if (c.has[COMP_GATHER]) ka.push_back(K("Gather-bonus_gather_prob", F_BONUS, 0, 1));
+        if (c.has[COMP_CDA])
+            for (int cc = 0; cc < 2; cc++) {
+                std::string s = std::string("ContinuousDoubleAuction-"), r = std::string("-") + CN[cc];
+                ka.push_back(K(s + "market_rate" + r, F_MARKET_RATE, cc, 1)); ka.push_back(K(s + "price_history" + r, F_PRICE_HIST, cc, c.P));
+                ka.push_back(K(s + "available_asks" + r, F_AVAIL_ASKS, cc, c.P)); ka.push_back(K(s + "available_bids" + r, F_AVAIL_BIDS, cc, c.P));
+                ka.push_back(K(s + "my_asks" + r, F_MY_ASKS, cc, c.P)); ka.push_back(K(s + "my_bids" + r, F_MY_BIDS, cc, c.P));
+                kp.push_back(K(s + "market_rate" + r, F_MARKET_RATE, cc, 1)); kp.push_back(K(s + "price_history" + r, F_PRICE_HIST, cc, c.P));
+                kp.push_back(K(s + "full_asks" + r, F_FULL_ASKS, cc, c.P)); kp.push_back(K(s + "full_bids" + r, F_FULL_BIDS, cc, c.P));
+            }
+        if (c.has[COMP_TAX]) {
+            std::string s = "PeriodicBracketTax-";
+            for (std::vector<FlatKey> *v : {&ka, &kp}) {
+                v->push_back(K(s + "is_tax_day", F_TAX_IS_TAX_DAY, 0, 1)); v->push_back(K(s + "is_first_day", F_TAX_IS_FIRST, 0, 1));
+                v->push_back(K(s + "tax_phase", F_TAX_PHASE, 0, 1)); v->push_back(K(s + "last_incomes", F_TAX_LAST_INCOMES, 0, c.A));
+                v->push_back(K(s + "curr_rates", F_TAX_CURR_RATES, 0, c.B));
+            }
+            ka.push_back(K(s + "marginal_rate", F_TAX_MARG, 0, 1));
+            kpa.push_back(K(s + "last_income", F_TAX_LAST_INCOME, 0, 1)); kpa.push_back(K(s + "last_marginal_rate", F_TAX_LAST_MARG, 0, 1));
+            kpa.push_back(K(s + "curr_marginal_rate", F_TAX_MARG, 0, 1));
+        }
+        c.Fa = build_prog(ka, c.prog_a, MAX_FLAT);
+        c.Fp = build_prog(kp, c.prog_p, MAX_FLAT);
+        c.Fpa = build_prog(kpa, c.prog_pa, 16);
+        if (c.Fa < 0 || c.Fp < 0 || c.Fpa < 0) return bad("flat observation too long");
+    }
+    // record layout
+    {
+        const int A = c.A, P = c.P;
+        int off = HDR_WORDS * 4;
+        auto take = [&](int bytes) { int o = off; off = align16(off + bytes); return o; };
+        c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A);
+        c.off_bpay = take(8 * A); c.off_bskill = take(8 * A); c.off_bonus = take(8 * A);
+        c.off_last_coin = take(8 * A); c.off_last_income = take(8 * A); c.off_last_marg = take(8 * A);
+        c.off_util_prev = take(8 * (A + 1));
+        c.off_price_hist = take(8 * 2 * A * P);
+        c.off_inv = take(4 * 2 * A); c.off_esc = take(4 * 2 * A);
+        c.off_loc = take(2 * 2 * A);
+        c.off_n_orders = take(2 * A); c.off_bid_hist = take(2 * A * P); c.off_ask_hist = take(2 * A * P);
+        c.off_rate_idx = take(16);
+        c.off_cell = take(c.HW); c.off_owner = take(c.HW);
+        c.obs_prefix_bytes = off;
+        c.off_orders = take(4 * 2 * A * c.K);
+        c.off_mt = take(4 * 624);
+        c.rec_bytes = off;
+        c.step_scratch_bytes = align16(8 * (2 * A + 4) + 7 * A + 16);
+        c.obs_scratch_bytes = align16(8 * (2 * P + 2 + 2 * A + 4) + 2 * 4 * P + A + c.HW);
+    }
+    return AIE_OK;
+}
+
+inline void fill_dims(const DevCfg &c, aie_dims &d) {
+    memset(&d, 0, sizeof(d));
+    d.n_envs = c.n_envs; d.n_agents = c.A; d.height = c.H; d.width = c.W;
+    d.n_map_channels = c.M; d.window = c.win;
+    d.flat_agent = c.Fa; d.flat_planner = c.Fp; d.flat_planner_agent = c.Fpa;
+    d.mask_agent = c.Na; d.mask_planner = c.Np; d.n_act_agent = c.n_act_a; d.n_act_planner = c.n_act_p;
+    d.state_bytes = c.rec_bytes;
+    const int ww = c.win * c.win;
+    long long obs = (long long)c.A * ((c.M + 1) * ww * 4 + 2 * ww * 2 + c.Fa * 4 + c.Na * 4) + c.Fp * 4 + c.A * c.Fpa * 4 +
+                    c.Np * 4 + 4 + (c.planner_spatial ? (c.M * c.HW * 4 + 2 * c.HW * 2) : 0);
+    long long io = 8 * (c.A + 1) + 4 + 4 * (c.A * c.n_act_a + c.n_act_p);
+    d.algorithmic_bytes_per_env_step = (int32_t)(obs + io + 2LL * c.rec_bytes);
+}
+
+struct FieldDesc { const char *name; int off, eb, flt, sgn, nd, s0, s1, s2; };
+
+inline int lookup_field(const DevCfg &c, const char *name, aie_field *f) {
+    const int A = c.A, P = c.P;
+    const FieldDesc tab[] = {
+        {"t", HDR_T * 4, 4, 0, 1, 0, 0, 0, 0}, {"tax_pos", HDR_TAX_POS * 4, 4, 0, 1, 0, 0, 0, 0},
+        {"completions", HDR_COMPLETIONS * 4, 4, 0, 1, 0, 0, 0, 0}, {"auto_warmup", HDR_AUTO_WARMUP * 4, 4, 0, 1, 0, 0, 0, 0},
+        {"mt_pos", HDR_MT_POS * 4, 4, 0, 1, 0, 0, 0, 0}, {"episodes", HDR_EPISODES * 4, 4, 0, 1, 0, 0, 0, 0},
+        {"coin", c.off_coin, 8, 1, 1, 1, A, 0, 0}, {"esc_coin", c.off_esc_coin, 8, 1, 1, 1, A, 0, 0},
+        {"labor", c.off_labor, 8, 1, 1, 1, A, 0, 0}, {"build_payment", c.off_bpay, 8, 1, 1, 1, A, 0, 0},
+        {"build_skill", c.off_bskill, 8, 1, 1, 1, A, 0, 0}, {"bonus_gather_prob", c.off_bonus, 8, 1, 1, 1, A, 0, 0},
+        {"last_coin", c.off_last_coin, 8, 1, 1, 1, A, 0, 0}, {"last_income", c.off_last_income, 8, 1, 1, 1, A, 0, 0},
+        {"last_marg", c.off_last_marg, 8, 1, 1, 1, A, 0, 0}, {"util_prev", c.off_util_prev, 8, 1, 1, 1, A + 1, 0, 0},
+        {"price_hist", c.off_price_hist, 8, 1, 1, 3, 2, A, P}, {"inv", c.off_inv, 4, 0, 1, 2, A, 2, 0},
+        {"esc", c.off_esc, 4, 0, 1, 2, A, 2, 0}, {"loc", c.off_loc, 2, 0, 1, 2, A, 2, 0},
+        {"n_orders", c.off_n_orders, 1, 0, 0, 2, 2, A, 0}, {"bid_hist", c.off_bid_hist, 1, 0, 0, 3, 2, A, P},
+        {"ask_hist", c.off_ask_hist, 1, 0, 0, 3, 2, A, P}, {"rate_idx", c.off_rate_idx, 1, 0, 0, 1, 16, 0, 0},
+        {"cell", c.off_cell, 1, 0, 0, 2, c.H, c.W, 0}, {"owner", c.off_owner, 1, 0, 1, 2, c.H, c.W, 0},
+        {"orders", c.off_orders, 4, 0, 0, 3, 2, A, c.K}, {"mt_key", c.off_mt, 4, 0, 0, 1, 624, 0, 0},
+    };
+    for (const FieldDesc &t : tab)
+        if (!strcmp(t.name, name)) {
+            f->offset = t.off; f->elem_bytes = t.eb; f->is_float = t.flt; f->is_signed = t.sgn; f->ndim = t.nd;
+            f->shape[0] = t.s0; f->shape[1] = t.s1; f->shape[2] = t.s2; f->shape[3] = 0;
+            return AIE_OK;
+        }
+    return AIE_EINVAL;
+}
+
+// Pack env i of a host reset snapshot into one record (books empty, escrow/labor zero; tax trackers and
+// metric_0 are finished on the device by finish_reset_env).
+inline int pack_record(const DevCfg &c, const aie_host_state &hs, int i, uint8_t *rec, std::string &err) {
+    const int A = c.A, HW = c.HW;
+    memset(rec, 0, c.rec_bytes);
+    int32_t *hdr = (int32_t *)rec;
+    hdr[HDR_T] = 0; hdr[HDR_TAX_POS] = 1;
+    hdr[HDR_COMPLETIONS] = hs.completions ? hs.completions[i] : 0;
+    hdr[HDR_MT_POS] = hs.mt_pos[i];
+    if (hs.mt_pos[i] < 0 || hs.mt_pos[i] > 624) { err = "mt_pos out of range"; return AIE_EINVAL; }
+    double *coin = (double *)(rec + c.off_coin), *bpay = (double *)(rec + c.off_bpay),
+           *bskill = (double *)(rec + c.off_bskill), *bonus = (double *)(rec + c.off_bonus);
+    int32_t *inv = (int32_t *)(rec + c.off_inv);
+    int16_t *loc = (int16_t *)(rec + c.off_loc);
+    uint8_t *cell = rec + c.off_cell;
+    int8_t *owner = (int8_t *)(rec + c.off_owner);
+    for (int k = 0; k < HW; k++) {
+        size_t g = (size_t)i * HW + k;
+        uint8_t b = 0;
+        if (hs.stone[g]) b |= CELL_STONE;
+        if (hs.wood[g]) b |= CELL_WOOD;
+        if (hs.stone_src[g]) b |= CELL_STONE_SRC;
+        if (hs.wood_src[g]) b |= CELL_WOOD_SRC;
+        if (hs.water && hs.water[g]) b |= CELL_WATER;
+        cell[k] = b; owner[k] = -1;
+    }
+    for (int a = 0; a < A; a++) {
+        size_t g = (size_t)i * A + a;
+        int r = hs.loc[2 * g], cc = hs.loc[2 * g + 1];
+        if (r < 0 || r >= c.H || cc < 0 || cc >= c.W) { err = "agent location outside the world"; return AIE_EINVAL; }
+        loc[2 * a] = (int16_t)r; loc[2 * a + 1] = (int16_t)cc;
+        coin[a] = hs.coin[g];
+        if (!(hs.coin[g] >= 0.0)) { err = "negative starting coin"; return AIE_EINVAL; }
+        inv[2 * a] = hs.inv_stone ? hs.inv_stone[g] : 0;
+        inv[2 * a + 1] = hs.inv_wood ? hs.inv_wood[g] : 0;
+        bpay[a] = hs.build_payment[g]; bskill[a] = hs.build_skill[g]; bonus[a] = hs.bonus_gather_prob[g];
+    }
+    uint32_t *orders = (uint32_t *)(rec + c.off_orders);
+    for (int k = 0; k < 2 * A * c.K; k++) orders[k] = ORDER_EMPTY;
+    memcpy(rec + c.off_mt, hs.mt_key + (size_t)i * 624, 624 * 4);
+    return AIE_OK;
+}
+
+// Unpack a record for tests (aie_read_state).
+inline void unpack_record(const DevCfg &c, const uint8_t *rec, const aie_state_dump &d) {
+    const int A = c.A, P = c.P, HW = c.HW, K = c.K;
+    const int32_t *hdr = (const int32_t *)rec;
+    const int t = hdr[HDR_T];
+    if (d.cell) memcpy(d.cell, rec + c.off_cell, HW);
+    if (d.owner) memcpy(d.owner, rec + c.off_owner, HW);
+    if (d.loc) memcpy(d.loc, rec + c.off_loc, 4 * A);
+    if (d.coin) memcpy(d.coin, rec + c.off_coin, 8 * A);
+    if (d.esc_coin) memcpy(d.esc_coin, rec + c.off_esc_coin, 8 * A);
+    if (d.labor) memcpy(d.labor, rec + c.off_labor, 8 * A);
+    if (d.inv) memcpy(d.inv, rec + c.off_inv, 8 * A);
+    if (d.esc) memcpy(d.esc, rec + c.off_esc, 8 * A);
+    if (d.last_coin) memcpy(d.last_coin, rec + c.off_last_coin, 8 * A);
+    if (d.last_income) memcpy(d.last_income, rec + c.off_last_income, 8 * A);
+    if (d.last_marg) memcpy(d.last_marg, rec + c.off_last_marg, 8 * A);
+    if (d.price_hist) memcpy(d.price_hist, rec + c.off_price_hist, 8 * 2 * A * P);
+    for (int i = 0; i < 2 * A; i++) if (d.n_orders) d.n_orders[i] = rec[c.off_n_orders + i];
+    for (int i = 0; i < 2 * A * P; i++) {
+        if (d.bid_hist) d.bid_hist[i] = rec[c.off_bid_hist + i];
+        if (d.ask_hist) d.ask_hist[i] = rec[c.off_ask_hist + i];
+    }
+    if (d.tax_pos) *d.tax_pos = hdr[HDR_TAX_POS];
+    if (d.rate_idx) for (int b = 0; b < c.B; b++) d.rate_idx[b] = rec[c.off_rate_idx + b];
+    if (d.mt_key) memcpy(d.mt_key, rec + c.off_mt, 624 * 4);
+    if (d.mt_pos) *d.mt_pos = hdr[HDR_MT_POS];
+    if (d.t) *d.t = t;
+    if (d.completions) *d.completions = hdr[HDR_COMPLETIONS];
+    if (d.book_rows && d.book_count) {
+        const uint32_t *orders = (const uint32_t *)(rec + c.off_orders);
+        struct Row { int agent, price, life; };
+        for (int cc = 0; cc < 2; cc++)
+            for (int side = 0; side < 2; side++) {
+                std::vector<Row> rows;
+                for (int a = 0; a < A; a++)
+                    for (int k = 0; k < K; k++) {
+                        uint32_t o = orders[(cc * A + a) * K + k];
+                        if (o == ORDER_EMPTY || (int)(o & 1u) != side) continue;
+                        // the reference increments lifetimes at the end of the step (remove_expired_orders)
+                        rows.push_back(Row{a, (int)((o >> 1) & 127u), t - (int)(o >> 8) + 1});
+                    }
+                std::stable_sort(rows.begin(), rows.end(), [side](const Row &x, const Row &y) {
+                    if (x.price != y.price) return side == 0 ? x.price > y.price : x.price < y.price;
+                    if (x.life != y.life) return x.life > y.life;
+                    return x.agent < y.agent;
+                });
+                int n = (int)rows.size();
+                d.book_count[cc * 2 + side] = n;
+                int32_t *out = d.book_rows + (size_t)(cc * 2 + side) * d.book_cap * 3;
+                for (int i = 0; i < n && i < d.book_cap; i++) { out[3 * i] = rows[i].agent; out[3 * i + 1] = rows[i].price; out[3 * i + 2] = rows[i].life; }
+            }
+    }
+}
+
+}  // namespace aie

@@ -1,0 +1,95 @@
+// aie_layout.h — device-side configuration (DevCfg) and the packed per-env state record layout.
+//
+// One env replica = one contiguous, 16-byte aligned record in HBM ("state" tensor, uint8 [E, rec_bytes]).
+// Inside a record the state is struct-of-arrays indexed [agent, ...]; across envs the records are
+// env-major, so every per-field tensor the north star names is a strided view [E, A, ...] over `state`
+// (aie_get_field).  The step kernel moves a whole record HBM -> shared memory with one TMA bulk copy
+// (cp.async.bulk), works on it in shared memory, and bulk-copies it back; the observe kernel bulk-loads
+// only the prefix [0, obs_prefix_bytes) (everything except the order slots and the MT19937 key).
+//
+// Reference state this replaces: Maps (base/world.py:13-329), BaseAgent.state (base/base_agent.py:62),
+// ContinuousDoubleAuction book/histograms (continuous_double_auction.py:79-99), PeriodicBracketTax
+// trackers (redistribution.py:319-330), scenario utility trackers (layout_from_file.py:160-163) and the
+// numpy global MT19937 state (base_env.py:481-494).
+#pragma once
+#include <stdint.h>
+
+namespace aie {
+
+// cell bitfield (1 byte per map cell); max_health == 1 for every entity in the supported configs
+enum : uint8_t {
+    CELL_STONE = 1u << 0, CELL_WOOD = 1u << 1, CELL_STONE_SRC = 1u << 2, CELL_WOOD_SRC = 1u << 3,
+    CELL_WATER = 1u << 4, CELL_HOUSE = 1u << 5
+};
+
+// header words (int32) at the start of a record
+enum { HDR_T = 0, HDR_TAX_POS = 1, HDR_COMPLETIONS = 2, HDR_AUTO_WARMUP = 3, HDR_MT_POS = 4,
+       HDR_ERR = 5, HDR_EPISODES = 6, HDR_RESERVED = 7, HDR_WORDS = 8 };
+
+enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3 };
+enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
+
+// "flat" observation fields
+enum {
+    F_ZERO = 0, F_BUILD_PAYMENT, F_BUILD_SKILL, F_AVAIL_ASKS, F_AVAIL_BIDS, F_MARKET_RATE, F_MY_ASKS, F_MY_BIDS,
+    F_PRICE_HIST, F_BONUS, F_TAX_CURR_RATES, F_TAX_IS_FIRST, F_TAX_IS_TAX_DAY, F_TAX_LAST_INCOMES, F_TAX_MARG,
+    F_TAX_PHASE, F_TIME, F_INV_COIN, F_INV_STONE, F_INV_WOOD, F_LOC_COL, F_LOC_ROW, F_FULL_ASKS, F_FULL_BIDS,
+    F_TAX_LAST_INCOME, F_TAX_LAST_MARG
+};
+// mask program kinds
+enum { MK_ONE = 0, MK_BUILD, MK_BUY, MK_SELL, MK_GATHER };
+
+#define AIE_PROG_ENTRY(field, c, idx) ((uint16_t)(((field) << 8) | ((c) << 7) | (idx)))
+#define AIE_PROG_FIELD(e) ((e) >> 8)
+#define AIE_PROG_C(e) (((e) >> 7) & 1)
+#define AIE_PROG_IDX(e) ((e) & 127)
+
+constexpr int MAX_FLAT = 448;
+constexpr int MAX_MASK = 160;
+constexpr uint32_t ORDER_EMPTY = 0xFFFFFFFFu;  // order slot: birth << 8 | price << 1 | side(0 bid, 1 ask)
+
+struct DevCfg {
+    int32_t A, H, W, HW, T, multi_action, n_comp;
+    int32_t comp[4];
+    int32_t has[4];
+    int32_t has_water, M, w, win, planner_spatial, obs_scaling;
+    uint64_t regen_thresh[2];  // ceil(regen_weight * 2^53): u < weight  <=>  53-bit integer draw < thresh
+    double eta, energy_cost, warm_const;
+    int32_t warm_auto, swf;
+    double mix;
+    double build_payment, build_labor, move_labor, collect_labor, order_labor;
+    int32_t P, D, K;
+    int32_t tax_model, disable_taxes, period, B, R;
+    double cutoffs[16], disc_rates[64], fixed_rates[16];
+    int32_t tax_annealing;
+    double ann_warm, ann_slope, rate_max, ann_full;
+    int32_t auto_reset;
+    // action subspaces in registration order (base_agent.py:97-169)
+    int32_t n_sub;
+    int32_t sub_kind[8], sub_c[8], sub_n[8], sub_lo[8];
+    int32_t n_act_a, n_act_p, planner_acts;
+    // output dims
+    int32_t Fa, Fp, Fpa, Na, Np;
+    // record layout (byte offsets)
+    int32_t off_coin, off_esc_coin, off_labor, off_bpay, off_bskill, off_bonus, off_last_coin, off_last_income,
+        off_last_marg, off_util_prev, off_price_hist, off_inv, off_esc, off_loc, off_n_orders, off_bid_hist,
+        off_ask_hist, off_rate_idx, off_cell, off_owner, off_orders, off_mt;
+    int32_t obs_prefix_bytes, rec_bytes;
+    // step-kernel scratch (per env, shared memory) and observe-kernel scratch
+    int32_t step_scratch_bytes, obs_scratch_bytes;
+    int32_t n_envs;
+    // observation programs
+    uint16_t prog_a[MAX_FLAT], prog_p[MAX_FLAT], prog_pa[16];
+    uint16_t mprog_a[MAX_MASK];
+};
+
+// raw device pointers (mirrors aie_buffers)
+struct DevBufs {
+    uint8_t *state, *state0;
+    const int32_t *act_a, *act_p;
+    float *a_map; int16_t *a_idx; float *a_flat; float *a_mask;
+    float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask;
+    float *time_obs; double *rew; int32_t *done;
+};
+
+}  // namespace aie

@@ -1,0 +1,20 @@
+"""`foundation` — same entry points as ai_economist.foundation (foundation/__init__.py:7-18):
+six registries and make_env_instance(scenario_name, **kwargs)."""
+from . import agents as _agents_mod
+from . import components as _components_mod
+from . import entities as _entities_mod
+from . import scenarios as _scenarios_mod
+from .batched_env import BatchedFoundationEnv
+
+agents = _agents_mod.agent_registry
+components = _components_mod.component_registry
+endogenous = _entities_mod.endogenous_registry
+landmarks = _entities_mod.landmark_registry
+resources = _entities_mod.resource_registry
+scenarios = _scenarios_mod.scenario_registry
+
+
+def make_env_instance(scenario_name, **kwargs):
+    """Same call as the reference; extra kwargs: n_envs (default 1), device ("cuda:0"), seeds, auto_reset."""
+    scenario_cls = scenarios.get(scenario_name)
+    return BatchedFoundationEnv(scenario_cls, **kwargs)

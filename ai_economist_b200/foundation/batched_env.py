@@ -1,0 +1,386 @@
+"""BatchedFoundationEnv — the Gym-style reset/step surface of the reference's BaseEnvironment
+(base/base_env.py:24-1120), over E env replicas that live on one B200.
+
+Differences from the reference API (all additive):
+  * new kwargs `n_envs`, `device`, `seeds`, `auto_reset`;
+  * observations / rewards / done are persistent device tensors with a leading env axis, keyed exactly like
+    the reference's dicts ("0".."n-1", "p"; "world-map", "world-idx_map", "flat", "action_mask", "time", "p<i>");
+  * `reference_view(e)` re-creates the reference's nested numpy dict for one env (tests / debugging).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .agents import agent_registry
+from .components import component_registry
+from .entities import endogenous_registry, landmark_registry, resource_registry
+
+
+class _MapsView:
+    """Read-only mirror of world.maps for one env replica (reference: base/world.py:13-329)."""
+    _BITS = {"Stone": 1, "Wood": 2, "StoneSourceBlock": 4, "WoodSourceBlock": 8, "Water": 16, "House": 32}
+
+    def __init__(self, env, e):
+        self._env, self._e = env, e
+
+    def keys(self):
+        ks = ["Stone", "Wood", "House"] + (["Water"] if self._env._spec["has_water"] else [])
+        return ks + ["StoneSourceBlock", "WoodSourceBlock"]
+
+    def get(self, name, owner=False):
+        st = self._env._stepper.read_state(self._e)
+        if owner:
+            assert name == "House"
+            return st["owner"].astype(np.int16)
+        return ((st["cell"] & self._BITS[name]) > 0).astype(np.float64)
+
+    @property
+    def state(self):
+        return np.stack([self.get(k) for k in self.keys()]).astype(np.float32)
+
+
+class _WorldView:
+    def __init__(self, env, e=0):
+        self._env, self._e = env, e
+        self.maps = _MapsView(env, e)
+        self.world_size = list(env.world_size)
+        self.n_agents = env.n_agents
+
+    @property
+    def agents(self):
+        return self._env._agents
+
+    @property
+    def planner(self):
+        return self._env._planner
+
+    @property
+    def timestep(self):
+        return int(self._env._stepper.read_state(self._e)["t"][0])
+
+
+class BatchedFoundationEnv:
+    def __init__(self, scenario_cls, components=None, n_agents=None, world_size=None, episode_length=1000,
+                 multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True,
+                 flatten_masks=True, allow_observation_scaling=True, dense_log_frequency=None,
+                 world_dense_log_frequency=50, collate_agent_step_and_reset_data=False, seed=None,
+                 n_envs=1, device="cuda:0", seeds=None, auto_reset=True, stepper_factory=None, **scenario_kwargs):
+        # ---- base_env.py:178-366 argument checks ----
+        assert isinstance(world_size, (tuple, list)) and len(world_size) == 2
+        self.world_size = list(world_size)
+        assert isinstance(n_agents, int) and n_agents >= 2
+        self.n_agents = n_agents
+        self.num_agents = n_agents + 1
+        assert isinstance(components, (tuple, list))
+        self._episode_length = int(episode_length)
+        assert self._episode_length >= 1
+        self.multi_action_mode_agents = bool(multi_action_mode_agents)
+        self.multi_action_mode_planner = bool(multi_action_mode_planner)
+        if not self.multi_action_mode_planner:
+            raise NotImplementedError("single-action planner mode is not on the GPU path")
+        if not (flatten_observations and flatten_masks):
+            raise NotImplementedError("the batched stepper always emits flattened observations and masks; "
+                                      "use reference_view() for the nested layout")
+        if collate_agent_step_and_reset_data:
+            raise NotImplementedError("collated ('a') layout: index the [E, A, ...] tensors in obs_tensors instead")
+        self._allow_observation_scaling = bool(allow_observation_scaling)
+        self.n_envs = int(n_envs)
+        assert self.n_envs >= 1
+
+        # ---- entities + components (base_env.py:289-346) ----
+        ents = {"resources": ["Coin"], "landmarks": [], "endogenous": ["Labor"]}
+
+        def register(names):
+            for n in names:
+                for reg, key in ((resource_registry, "resources"), (landmark_registry, "landmarks"),
+                                 (endogenous_registry, "endogenous")):
+                    if reg.has(n):
+                        if n not in ents[key]:
+                            ents[key].append(n)
+                        break
+                else:
+                    raise KeyError("Unknown entity: {}".format(n))
+
+        register(scenario_cls.required_entities)
+        specs = []
+        for spec in components:
+            if isinstance(spec, (tuple, list)):
+                assert len(spec) == 2 and isinstance(spec[0], str) and isinstance(spec[1], dict)
+                cname, ckw = spec
+            else:
+                assert isinstance(spec, dict) and len(spec) == 1
+                cname, ckw = list(spec.items())[0]
+            ccls = component_registry.get(cname)
+            register(ccls.required_entities)
+            specs.append((ccls, ckw))
+        self._entities = ents
+        self._components = [ccls(self.n_agents, self._episode_length, inventory_scale=self.inv_scale, **ckw)
+                            for ccls, ckw in specs]
+        self._components_dict = {c.name: c for c in self._components}
+        self._shorthand_lookup = {c.shorthand: c for c in self._components}
+        if len(self._components_dict) != len(self._components):
+            raise ValueError("duplicate component")
+
+        mobile, planner = agent_registry.get("BasicMobileAgent"), agent_registry.get("BasicPlanner")
+        self._agents = [mobile(i, self.multi_action_mode_agents) for i in range(self.n_agents)]
+        self._planner = planner(self.multi_action_mode_planner)
+        for ag in self._agents + [self._planner]:
+            ag._register(self._components)
+            ag._env = self
+        self._agent_lookup = {str(a.idx): a for a in self.all_agents}
+
+        self.scenario = scenario_cls(self, **scenario_kwargs)
+        self.name = scenario_cls.name
+
+        # ---- flat numeric spec handed to the C-ABI ----
+        spec = dict(components=[c.name for c in self._components], n_agents=self.n_agents,
+                    height=self.world_size[0], width=self.world_size[1], episode_length=self._episode_length,
+                    multi_action_agents=int(self.multi_action_mode_agents),
+                    allow_observation_scaling=int(self._allow_observation_scaling),
+                    build_payment=10.0, build_labor=10.0, move_labor=1.0, collect_labor=1.0,
+                    max_bid_ask=10, order_duration=50, max_num_orders=50, order_labor=0.25,
+                    tax_model=0, disable_taxes=0, period=100, n_brackets=0, n_disc_rates=0, bracket_cutoffs=[],
+                    disc_rates=[], fixed_rates=[], tax_annealing=0, annealing_warmup=0.0, annealing_slope=0.0,
+                    rate_max=1.0)
+        spec.update(self.scenario.scenario_spec_fields())
+        for c in self._components:
+            spec.update(c.spec_fields())
+        self._spec = spec
+
+        if stepper_factory is None:
+            from ..stepper import CudaStepper
+            self._stepper = CudaStepper(spec, self.n_envs, device=device, auto_reset=auto_reset)
+        else:
+            self._stepper = stepper_factory(spec, self.n_envs, auto_reset)
+        self._rs = None
+        self._seeds = None
+        self._loaded = False
+        self._completions = np.zeros(self.n_envs, np.int64)
+        if seeds is not None:
+            self.seed(seeds)
+        elif seed is not None:
+            self.seed(seed)
+        self._build_views()
+
+    # ------------------------------------------------------------------ properties (base_env.py:385-437)
+    @property
+    def episode_length(self):
+        return int(self._episode_length)
+
+    @property
+    def inv_scale(self):
+        return 0.01 if self._allow_observation_scaling else 1
+
+    @property
+    def resources(self):
+        return sorted(self._entities["resources"])
+
+    @property
+    def landmarks(self):
+        return sorted(self._entities["landmarks"])
+
+    @property
+    def endogenous(self):
+        return sorted(self._entities["endogenous"])
+
+    @property
+    def all_agents(self):
+        return self._agents + [self._planner]
+
+    @property
+    def components(self):
+        return self._components
+
+    @property
+    def world(self):
+        return _WorldView(self, 0)
+
+    def world_of(self, e):
+        return _WorldView(self, e)
+
+    @property
+    def spec(self):
+        return dict(self._spec)
+
+    @property
+    def stepper(self):
+        return self._stepper
+
+    def get_component(self, name):
+        if name in self._components_dict:
+            return self._components_dict[name]
+        if name in self._shorthand_lookup:
+            return self._shorthand_lookup[name]
+        raise KeyError("No component with name or shorthand name {} found; registered components are:\n\t{}".format(
+            name, "\n\t".join(self._components_dict)))
+
+    def get_agent(self, agent_idx):
+        agent = self._agent_lookup.get(str(agent_idx))
+        if agent is None:
+            raise ValueError("No agent with associated index {}".format(agent_idx))
+        return agent
+
+    # ------------------------------------------------------------------ seeding (base_env.py:481-494)
+    def seed(self, seed):
+        """int -> env e is seeded with seed + e (n_envs == 1 reproduces the reference's global seeding);
+        a sequence gives each env its own seed."""
+        if isinstance(seed, (int, float)):
+            seed = int(seed)
+            assert seed > 0
+            seeds = [seed + e for e in range(self.n_envs)]
+        else:
+            seeds = [int(s) for s in seed]
+            assert len(seeds) == self.n_envs
+        self._seeds = seeds
+        self._rs = [np.random.RandomState(s) for s in seeds]
+
+    # ------------------------------------------------------------------ reset / step
+    def _sync_streams_from_device(self):
+        """The device advanced each env's numpy-legacy stream while stepping; continue from there
+        (the reference's reset() keeps drawing from the same global stream, base_env.py:896-911)."""
+        st = self._stepper
+        key = st.to_numpy(st.state_view("mt_key")) if hasattr(st, "state_view") else None
+        pos = st.to_numpy(st.state_view("mt_pos")) if hasattr(st, "state_view") else None
+        for e, rs in enumerate(self._rs):
+            if key is None:
+                d = st.read_state(e)
+                k, p = d["mt_key"], int(d["mt_pos"][0])
+            else:
+                k, p = key[e], int(pos[e])
+            s = rs.get_state()
+            rs.set_state((s[0], np.asarray(k, np.uint32), p, s[3], s[4]))
+
+    def host_reset_arrays(self):
+        """Run the reference-faithful host reset for every env; returns the aie_host_state arrays."""
+        if self._rs is None:
+            self._rs = [np.random.RandomState() for _ in range(self.n_envs)]
+        per = []
+        for e in range(self.n_envs):
+            rs = self._rs[e]
+            st = self.scenario.host_reset(rs)
+            key = rs.get_state()
+            st["mt_key"], st["mt_pos"] = np.asarray(key[1], np.uint32), int(key[2])
+            st["completions"] = int(self._completions[e])
+            per.append(st)
+        out = {k: np.stack([np.asarray(p[k]) for p in per]) for k in per[0]}
+        return out
+
+    def reset(self, seed_state=None, force_dense_logging=False):
+        if seed_state is not None:
+            raise NotImplementedError("pass seeds= / call seed() instead of seed_state")
+        if self._loaded and self._rs is not None:
+            self._completions = self._stepper.to_numpy(self._stepper.state_view("completions")).astype(np.int64) \
+                if hasattr(self._stepper, "state_view") else self._completions
+            self._sync_streams_from_device()
+        self._stepper.load_state(self.host_reset_arrays())
+        self._loaded = True
+        return self.obs
+
+    def _write_actions(self, actions):
+        st = self._stepper
+        buf_a, buf_p = st.buf["actions_agent"], st.buf["actions_planner"]
+        if actions is None:
+            buf_a[...] = 0
+            buf_p[...] = 0
+            return
+        if isinstance(actions, dict):
+            buf_a[...] = 0
+            buf_p[...] = 0
+            for k, v in actions.items():
+                k = str(k)
+                if k == "p":
+                    if st.dims.n_act_planner:
+                        buf_p[...] = self._as_buf(v, buf_p, (self.n_envs, st.dims.n_act_planner))
+                else:
+                    i = int(k)
+                    buf_a[:, i, :] = self._as_buf(v, buf_a, (self.n_envs, st.dims.n_act_agent))
+            return
+        a, p = actions if isinstance(actions, (tuple, list)) and len(actions) == 2 else (actions, None)
+        if a is not buf_a:
+            buf_a[...] = self._as_buf(a, buf_a, tuple(buf_a.shape))
+        if p is not None and p is not buf_p and st.dims.n_act_planner:
+            buf_p[...] = self._as_buf(p, buf_p, tuple(buf_p.shape))
+
+    @staticmethod
+    def _as_buf(v, like, shape):
+        if isinstance(like, np.ndarray):
+            return np.asarray(v, dtype=like.dtype).reshape(shape)
+        import torch
+        if isinstance(v, torch.Tensor):
+            return v.to(device=like.device, dtype=like.dtype).reshape(shape)
+        return torch.as_tensor(np.asarray(v, dtype=np.int32), device=like.device).reshape(shape)
+
+    def step(self, actions=None, seed_state=None):
+        """actions: None (all NO-OP) | reference-style dict {agent_idx: action(s)} with a leading env axis |
+        tensor [E, A, n_act] | (agent_actions, planner_actions).  Writing straight into
+        `env.action_buffers` and calling step(env.action_buffers) avoids any copy."""
+        assert self._loaded, "call reset() first"
+        self._write_actions(actions)
+        self._stepper.step()
+        return self.obs, self.rew, self.done, self.info
+
+    @property
+    def action_buffers(self):
+        return self._stepper.buf["actions_agent"], self._stepper.buf["actions_planner"]
+
+    # ------------------------------------------------------------------ outputs
+    def _build_views(self):
+        b = self._stepper.buf
+        A = self.n_agents
+        self.obs_tensors = {k: b[k] for k in b if k.startswith("obs_") or k.startswith("mask_")}
+        obs = {}
+        for i in range(A):
+            obs[str(i)] = {"world-map": b["obs_agent_map"][:, i], "world-idx_map": b["obs_agent_idx"][:, i],
+                           "flat": b["obs_agent_flat"][:, i], "time": b["obs_time"],
+                           "action_mask": b["mask_agent"][:, i]}
+        p = {"flat": b["obs_planner_flat"], "time": b["obs_time"], "action_mask": b["mask_planner"]}
+        if "obs_planner_map" in b:
+            p["world-map"], p["world-idx_map"] = b["obs_planner_map"], b["obs_planner_idx"]
+        for i in range(A):
+            p["p%d" % i] = b["obs_planner_agents"][:, i]
+        obs["p"] = p
+        self.obs = obs
+        self.rew = {str(i): b["reward"][:, i] for i in range(A)}
+        self.rew["p"] = b["reward"][:, A]
+        self.done = {"__all__": b["done"]}
+        self.info = {k: {} for k in obs}
+
+    def reference_view(self, e=0):
+        """(obs, rew, done) of env e as nested numpy dicts in the reference's layout."""
+        o = self._stepper.read_obs(e)
+        A = self.n_agents
+        obs = {}
+        for i in range(A):
+            obs[str(i)] = {"world-map": o["a_map"][i], "world-idx_map": o["a_idx"][i], "flat": o["a_flat"][i],
+                           "time": o["time"].astype(np.float64), "action_mask": o["a_mask"][i]}
+        obs["p"] = {"flat": o["p_flat"], "time": o["time"].astype(np.float64), "action_mask": o["p_mask"]}
+        if "p_map" in o:
+            obs["p"]["world-map"], obs["p"]["world-idx_map"] = o["p_map"], o["p_idx"]
+        for i in range(A):
+            obs["p"]["p%d" % i] = o["p_agents"][i]
+        rew = {str(i): float(o["rew"][i]) for i in range(A)}
+        rew["p"] = float(o["rew"][A])
+        return obs, rew, {"__all__": bool(o["done"][0])}
+
+    def _agent_state(self, idx, e):
+        d = self._stepper.read_state(e)
+        if idx == "p":
+            return dict(inventory={r: 0 for r in self.resources}, escrow={r: 0 for r in self.resources}, endogenous={})
+        i = int(idx)
+        return dict(loc=[int(d["loc"][i, 0]), int(d["loc"][i, 1])],
+                    inventory={"Coin": float(d["coin"][i]), "Stone": int(d["inv"][i, 0]), "Wood": int(d["inv"][i, 1])},
+                    escrow={"Coin": float(d["esc_coin"][i]), "Stone": int(d["esc"][i, 0]), "Wood": int(d["esc"][i, 1])},
+                    endogenous={"Labor": float(d["labor"][i])})
+
+    @property
+    def metrics(self):
+        """Scenario metrics of env 0 that derive from current state (layout_from_file.py:595-650 subset)."""
+        d = self._stepper.read_state(0)
+        tot = d["coin"] + d["esc_coin"]
+        out = {"social/productivity": float(tot.sum())}
+        for i in range(self.n_agents):
+            out["endow/%d/Coin" % i] = float(tot[i])
+            out["endow/%d/Stone" % i] = int(d["inv"][i, 0] + d["esc"][i, 0])
+            out["endow/%d/Wood" % i] = int(d["inv"][i, 1] + d["esc"][i, 1])
+            out["endogenous/%d/Labor" % i] = float(d["labor"][i])
+        return out

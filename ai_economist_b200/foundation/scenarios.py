@@ -1,0 +1,256 @@
+"""Scenario classes: constructor kwargs (same names/defaults as the reference) and the HOST-side reset.
+
+Reset stays on the host in this round: it draws from a per-env numpy legacy RandomState in
+exactly the reference's order, so a seeded env starts from the reference's state and RNG position; the
+post-reset snapshot is uploaded through aie_load_state.  The per-step scenario logic (resource regeneration,
+observations, rewards) runs on the GPU.
+
+reference: scenarios/simple_wood_and_stone/layout_from_file.py:24-650, dynamic_layout.py:27-700
+"""
+import os
+
+import numpy as np
+
+from .registrar import Registry
+
+MAP_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "map_txt")
+_SWF = {"coin_eq_times_productivity": 0, "inv_income_weighted_coin_endowments": 1, "inv_income_weighted_utility": 2}
+
+
+class BaseScenario:
+    """Scenario-level kwargs shared by the simple_wood_and_stone family."""
+    name = ""
+    agent_subclasses = ["BasicMobileAgent", "BasicPlanner"]
+    required_entities = []
+
+    def __init__(self, env, planner_gets_spatial_info=True, full_observability=False,
+                 mobile_agent_observation_range=5, starting_agent_coin=0, isoelastic_eta=0.23, energy_cost=0.21,
+                 energy_warmup_constant=0, energy_warmup_method="decay",
+                 planner_reward_type="coin_eq_times_productivity", mixing_weight_gini_vs_coin=0.0):
+        self.env = env
+        self.planner_gets_spatial_info = bool(planner_gets_spatial_info)
+        if full_observability:
+            raise NotImplementedError("full_observability=True is not on the GPU path")
+        self.obs_range = int(mobile_agent_observation_range)
+        self.starting_agent_coin = float(starting_agent_coin)
+        assert self.starting_agent_coin >= 0.0
+        self.isoelastic_eta = float(isoelastic_eta)
+        assert 0.0 <= self.isoelastic_eta <= 1.0
+        self.energy_cost = float(energy_cost)
+        assert self.energy_cost >= 0
+        self.energy_warmup_method = energy_warmup_method.lower()
+        assert self.energy_warmup_method in ["decay", "auto"]
+        self.energy_warmup_constant = float(energy_warmup_constant)
+        assert self.energy_warmup_constant >= 0
+        self.planner_reward_type = str(planner_reward_type).lower()
+        if self.planner_reward_type not in _SWF:
+            raise NotImplementedError("No valid planner reward selected!")
+        self.mixing_weight_gini_vs_coin = float(mixing_weight_gini_vs_coin)
+        assert 0 <= self.mixing_weight_gini_vs_coin <= 1.0
+
+    # -- shared helpers ---------------------------------------------------------------------------
+    def _place_randomly(self, rs, order, blocked):
+        """Rejection-sample a free, accessible cell for each agent in `order`
+        (layout_from_file.py:359-370 / dynamic_layout.py:418-429)."""
+        H, W = self.env.world_size
+        A = self.env.n_agents
+        loc = -np.ones((A, 2), np.int16)
+        taken = np.zeros((H, W), bool)
+        for a in order:
+            r, c = rs.randint(0, H), rs.randint(0, W)
+            tries = 0
+            while blocked[r, c] or taken[r, c]:
+                r, c = rs.randint(0, H), rs.randint(0, W)
+                tries += 1
+                if tries > 200:
+                    raise TimeoutError
+            loc[a] = (r, c)
+            taken[r, c] = True
+        return loc
+
+    def _component_resets(self, rs, st):
+        """Component.reset() in component-list order (base_env.py:906-908)."""
+        A = self.env.n_agents
+        st["build_payment"], st["build_skill"], st["bonus_gather_prob"] = np.zeros(A), np.zeros(A), np.zeros(A)
+        for comp in self.env.components:
+            if comp.name == "Build":
+                st["build_payment"], st["build_skill"] = comp.sample_skills(rs, A)
+            elif comp.name == "Gather":
+                st["bonus_gather_prob"] = comp.sample_skills(rs, A)
+
+    def scenario_spec_fields(self):
+        return dict(
+            obs_range=self.obs_range, planner_gets_spatial_info=int(self.planner_gets_spatial_info),
+            isoelastic_eta=self.isoelastic_eta, energy_cost=self.energy_cost,
+            energy_warmup_constant=self.energy_warmup_constant,
+            energy_warmup_auto=int(self.energy_warmup_method == "auto"),
+            planner_reward_type=_SWF[self.planner_reward_type],
+            mixing_weight_gini_vs_coin=self.mixing_weight_gini_vs_coin)
+
+
+scenario_registry = Registry(BaseScenario)
+
+
+@scenario_registry.add
+class LayoutFromFile(BaseScenario):
+    name = "layout_from_file/simple_wood_and_stone"
+    required_entities = ["Wood", "Stone", "Water"]
+
+    def __init__(self, env, env_layout_file="quadrant_25x25_20each_30clump.txt", resource_regen_prob=0.01,
+                 fixed_four_skill_and_loc=False, **kw):
+        super().__init__(env, **kw)
+        H, W = env.world_size
+        path = os.path.join(MAP_DIR, env_layout_file)
+        with open(path, "r") as f:
+            self.env_layout_string = f.read()
+        self.env_layout = self.env_layout_string.split(";")
+        sym = {"W": "Wood", "S": "Stone", "@": "Water"}
+        self.source_maps = {k: np.zeros((H, W), np.uint8) for k in sym.values()}
+        for r, row in enumerate(self.env_layout):
+            for c, ch in enumerate(row):
+                if ch in sym:
+                    self.source_maps[sym[ch]][r, c] = 1
+        self.regen_weight = float(resource_regen_prob)
+        assert 0 <= self.regen_weight <= 1
+        self.fixed_four_skill_and_loc = bool(fixed_four_skill_and_loc)
+        if self.fixed_four_skill_and_loc:
+            self._init_fixed_four()
+
+    def _init_fixed_four(self):
+        """Average ranked Pareto skills + corner start cells (layout_from_file.py:165-247)."""
+        env = self.env
+        bm = env.get_component("Build")
+        assert bm.skill_dist == "pareto"
+        pmsm, A = bm.payment_max_skill_multiplier, env.n_agents
+        H, W = env.world_size
+        samples = np.random.RandomState(1).pareto(4, size=(100000, A))  # reference: np.random.seed(seed=1)
+        ranked = np.sort(np.minimum(pmsm, (pmsm - 1) * samples + 1), axis=1).mean(axis=0)
+        self._avg_ranked_skill = ranked * bm.payment
+        corners = [(0, W - 1), (H - 1, 0), (0, 0), (W - 1, W - 1)]  # sic: the reference uses W for the last row
+        groups = np.floor(np.arange(A) * (4 / A)).astype(int)
+        count = np.zeros(4, int)
+        self._ranked_locs = []
+        for g in groups:
+            k = count[g]
+            dr, dc = k // 4, k % 4
+            r0, c0 = corners[g]
+            self._ranked_locs.append({0: (r0 + dr, c0 - dc), 1: (r0 - dr, c0 + dc),
+                                      2: (r0 + dr, c0 + dc), 3: (r0 - dr, c0 - dc)}[int(g)])
+            count[g] += 1
+
+    def host_reset(self, rs):
+        env = self.env
+        A = env.n_agents
+        st = dict(stone=self.source_maps["Stone"].copy(), wood=self.source_maps["Wood"].copy(),
+                  stone_src=self.source_maps["Stone"].copy(), wood_src=self.source_maps["Wood"].copy(),
+                  water=self.source_maps["Water"].copy())
+        st["coin"] = np.full(A, self.starting_agent_coin)
+        st["loc"] = self._place_randomly(rs, range(A), st["water"] > 0)
+        self._component_resets(rs, st)
+        if self.fixed_four_skill_and_loc:  # layout_from_file.py:580-586
+            order = rs.permutation(A)
+            for i, a in enumerate(order):
+                r, c = self._ranked_locs[i]
+                assert not st["water"][r, c], "fixed_four start cell is water"
+                st["loc"][a] = (r, c)
+                st["build_payment"][a] = self._avg_ranked_skill[i]
+        return st
+
+    def scenario_spec_fields(self):
+        d = super().scenario_spec_fields()
+        d.update(has_water=1, regen_weight=[self.regen_weight, self.regen_weight])
+        return d
+
+
+@scenario_registry.add
+class Uniform(BaseScenario):
+    name = "uniform/simple_wood_and_stone"
+    required_entities = ["Wood", "Stone"]
+
+    def __init__(self, env, starting_wood_coverage=0.025, wood_regen_halfwidth=0, wood_regen_weight=0.01,
+                 wood_max_health=1, starting_stone_coverage=0.025, stone_regen_halfwidth=0, stone_regen_weight=0.01,
+                 stone_max_health=1, wood_clumpiness=0.35, stone_clumpiness=0.5, gradient_steepness=8,
+                 checker_source_blocks=False, **kw):
+        super().__init__(env, **kw)
+        H, W = env.world_size
+        if starting_wood_coverage >= 1:
+            starting_wood_coverage /= np.prod(env.world_size)
+        if starting_stone_coverage >= 1:
+            starting_stone_coverage /= np.prod(env.world_size)
+        assert (starting_stone_coverage + starting_wood_coverage) < 0.5
+        self.checker = bool(checker_source_blocks)
+        cc, rr = np.meshgrid(np.arange(W) % 2, np.arange(H) % 2)
+        self._checker_mask = (rr + cc) == 1
+        m = 2 if self.checker else 1
+        self.coverage = {"Wood": float(starting_wood_coverage) * m, "Stone": float(starting_stone_coverage) * m}
+        assert 0 < self.coverage["Wood"] < 1 and 0 < self.coverage["Stone"] < 1
+        if int(wood_regen_halfwidth) or int(stone_regen_halfwidth):
+            raise NotImplementedError("regen_halfwidth > 0 is not on the GPU path")
+        if int(wood_max_health) != 1 or int(stone_max_health) != 1:
+            raise NotImplementedError("max_health != 1 is not on the GPU path")
+        self.regen = {"Wood": float(wood_regen_weight), "Stone": float(stone_regen_weight)}
+        assert 0 <= self.regen["Wood"] <= 1 and 0 <= self.regen["Stone"] <= 1
+        self.clumpiness = {"Wood": float(wood_clumpiness), "Stone": float(stone_clumpiness)}
+        assert all(0 <= v <= 1 for v in self.clumpiness.values())
+        self.gradient_steepness = float(gradient_steepness)
+        assert self.gradient_steepness >= 1.0
+        grad = np.arange(H)[:, None].repeat(W, axis=1) ** self.gradient_steepness
+        grad = grad / np.mean(grad)
+        # sic: both maps are scaled by the Wood coverage (dynamic_layout.py:302-306)
+        self.source_prob_maps = {"Wood": grad * self.coverage["Wood"], "Stone": grad[-1::-1] * self.coverage["Wood"]}
+
+    def _generate_layout(self, rs):
+        """Clumped random source placement, dynamic_layout.py:313-392 (same draws, same order)."""
+        from scipy import signal
+
+        H, W = self.env.world_size
+        src = {}
+        for _ in range(100):
+            occupied = np.zeros((H, W), bool)
+            src = {}
+            for res in ("Wood", "Stone"):
+                clump = 1 - np.clip(self.clumpiness[res], 0.0, 0.99)
+                prob = self.source_prob_maps[res] * 0.1 * clump
+                empty = ~occupied
+                noise = rs.rand(H, W)
+                cand = (noise < prob) * empty
+                tries = 0
+                while np.mean(cand) < self.coverage[res] * clump:
+                    noise *= 0.9
+                    cand = (noise < prob) * empty
+                    tries += 1
+                    if tries > 200:
+                        break
+                while np.mean(cand) < self.coverage[res]:
+                    kernel = rs.randn(7, 7) > 0
+                    grown = signal.convolve2d(cand + (0.2 * rs.randn(H, W)) - 0.25, kernel.astype(np.float32), "same")
+                    cand = np.maximum(grown > 0, cand) * empty
+                src[res] = cand
+                occupied = occupied | (cand > 0)
+            ok = True
+            for res in ("Wood", "Stone"):
+                q = np.mean(src[res]) / self.coverage[res]
+                if not (1 / 1.4) <= q <= 1.4:
+                    ok = False
+            if ok:
+                break
+        if self.checker:
+            src = {k: v * self._checker_mask for k, v in src.items()}
+        return {k: (v > 0).astype(np.uint8) for k, v in src.items()}
+
+    def host_reset(self, rs):
+        A = self.env.n_agents
+        H, W = self.env.world_size
+        src = self._generate_layout(rs)
+        st = dict(stone=src["Stone"].copy(), wood=src["Wood"].copy(), stone_src=src["Stone"].copy(),
+                  wood_src=src["Wood"].copy(), water=np.zeros((H, W), np.uint8))
+        st["coin"] = np.full(A, self.starting_agent_coin)
+        order = rs.permutation(A)  # world.get_random_order_agents()
+        st["loc"] = self._place_randomly(rs, order, np.zeros((H, W), bool))
+        self._component_resets(rs, st)
+        return st
+
+    def scenario_spec_fields(self):
+        d = super().scenario_spec_fields()
+        d.update(has_water=0, regen_weight=[self.regen["Stone"], self.regen["Wood"]])
+        return d

@@ -1,0 +1,245 @@
+/*
+ * aie_b200.h — C-ABI of the B200-native batched Foundation environment stepper.
+ *
+ * Drop-in boundary for the reference's per-timestep hot path
+ *   BaseEnvironment.step()                     ai_economist/foundation/base/base_env.py:929-1032
+ * of the gather-trade-build family (Build, ContinuousDoubleAuction, Gather,
+ * PeriodicBracketTax + resource regeneration + observation/mask/reward generation),
+ * batched over E independent env replicas.  Plain pointers and sizes only; PyTorch (or any
+ * other allocator) owns every device buffer, the library owns only its handle.
+ *
+ * The reference's own GPU plugin convention this replaces (WarpDrive, COVID path only):
+ *   FoundationEnvWrapper.__init__ / reset_all_envs / step_all_envs
+ *                                              ai_economist/foundation/env_wrapper.py:84-418
+ *   data pushed once via get_data_dictionary() -> CUDADataManager.push_data_to_device
+ *                                              env_wrapper.py:281-332
+ *   kernels looked up by name Cuda<Component>Step / Cuda<Scenario>Step / CudaComputeReward
+ *                                              env_wrapper.py:230-252
+ * There is no return code or error channel in that convention (device asserts only); here every
+ * entry point returns 0 on success or a negative AIE_E* code and aie_last_error() describes it.
+ *
+ * Threading: one handle per device; calls on a handle must be serialised by the caller.  All
+ * device work is enqueued on the caller-supplied CUDA stream and is asynchronous unless stated.
+ */
+#ifndef AIE_B200_H
+#define AIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIE_ABI_VERSION 1
+
+#define AIE_MAX_COMPONENTS 4
+#define AIE_MAX_BRACKETS 16
+#define AIE_MAX_RATES 64
+#define AIE_MAX_AGENTS 64      /* mobile agents per env */
+#define AIE_MAX_PRICE_LEVELS 32 /* max_bid_ask + 1 */
+
+/* error codes */
+#define AIE_OK 0
+#define AIE_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define AIE_ECUDA (-2)    /* CUDA runtime error (message in aie_last_error) */
+#define AIE_ESTATE (-3)   /* call out of order (e.g. step before buffers are bound) */
+#define AIE_ENOMEM (-4)
+
+/* Component kinds, in the order the reference's registry names them:
+ *   Build                    components/build.py:16
+ *   ContinuousDoubleAuction  components/continuous_double_auction.py:17
+ *   Gather                   components/move.py:16
+ *   PeriodicBracketTax       components/redistribution.py:78 */
+enum { AIE_COMP_BUILD = 0, AIE_COMP_CDA = 1, AIE_COMP_GATHER = 2, AIE_COMP_TAX = 3 };
+/* tax_model (redistribution.py:160-166): planner-driven discretised rates, or a fixed schedule
+ * ("us-federal-single-filer-2018-scaled" / "fixed-bracket-rates", rates supplied by the host). */
+enum { AIE_TAX_MODEL_WRAPPER = 0, AIE_TAX_FIXED_RATES = 1 };
+/* planner_reward_type (layout_from_file.py:153, scenarios/utils/rewards.py:84-133) */
+enum { AIE_SWF_COIN_EQ_TIMES_PROD = 0, AIE_SWF_INV_INCOME_COIN = 1, AIE_SWF_INV_INCOME_UTIL = 2 };
+
+/* Static configuration of one batch of identical env replicas.  Field meaning and defaults are
+ * the reference constructor kwargs (base_env.py:178-193, layout_from_file.py:68-85,
+ * dynamic_layout.py:80-106, build.py:41-49, move.py:41-48, continuous_double_auction.py:42-50,
+ * redistribution.py:137-155), already resolved to numbers by the host-side mirror. */
+typedef struct aie_config {
+    int32_t abi_version;            /* = AIE_ABI_VERSION */
+    int32_t n_agents, height, width, episode_length;
+    int32_t multi_action_agents;    /* multi_action_mode_agents */
+    int32_t n_components;
+    int32_t components[AIE_MAX_COMPONENTS]; /* AIE_COMP_*, in the env's component-list order */
+    /* scenario */
+    int32_t has_water;              /* Water landmark registered (6 map channels, else 5) */
+    int32_t obs_range;              /* mobile_agent_observation_range (w) */
+    int32_t planner_gets_spatial_info;
+    int32_t allow_observation_scaling;
+    double regen_weight[2];         /* resource_regen_prob / {stone,wood}_regen_weight: [Stone, Wood] */
+    double isoelastic_eta, energy_cost, energy_warmup_constant;
+    int32_t energy_warmup_auto;     /* energy_warmup_method == "auto" */
+    int32_t planner_reward_type;    /* AIE_SWF_* */
+    double mixing_weight_gini_vs_coin;
+    /* Build */
+    double build_payment, build_labor;
+    /* Gather */
+    double move_labor, collect_labor;
+    /* ContinuousDoubleAuction */
+    int32_t max_bid_ask, order_duration, max_num_orders;
+    double order_labor;
+    /* PeriodicBracketTax */
+    int32_t tax_model, disable_taxes, period, n_brackets, n_disc_rates;
+    double bracket_cutoffs[AIE_MAX_BRACKETS];
+    double disc_rates[AIE_MAX_RATES];
+    double fixed_rates[AIE_MAX_BRACKETS];
+    int32_t tax_annealing;          /* tax_annealing_schedule is not None */
+    double annealing_warmup, annealing_slope, rate_max;
+    /* batching (new; no reference equivalent) */
+    int32_t auto_reset;             /* 1: an env that reaches episode_length is restored from its load-time
+                                       snapshot inside the same step (WarpDrive save_copy_and_apply_at_reset
+                                       semantics, env_wrapper.py:299-337); its numpy-legacy RNG stream continues */
+} aie_config;
+
+/* Sizes the caller needs to allocate the device buffers. */
+typedef struct aie_dims {
+    int32_t n_envs, n_agents, height, width;
+    int32_t n_map_channels;   /* M */
+    int32_t window;           /* 2w+1 */
+    int32_t flat_agent;       /* F_a : length of each agent's "flat" vector */
+    int32_t flat_planner;     /* F_p */
+    int32_t flat_planner_agent; /* length of each p<i> vector */
+    int32_t mask_agent;       /* flattened agent action mask length */
+    int32_t mask_planner;
+    int32_t n_act_agent;      /* ints per agent per step (1 single-action, #subspaces multi-action) */
+    int32_t n_act_planner;    /* ints per env per step for the planner (n_brackets or 0) */
+    int32_t state_bytes;      /* bytes per env of the packed state record (multiple of 16) */
+    int32_t algorithmic_bytes_per_env_step; /* obs+mask+rew/done out + actions in + 2*state */
+} aie_dims;
+
+/* Raw device pointers.  All tensors are contiguous, env-major.
+ *   state, state0 : uint8  [E, state_bytes]           packed per-env state records
+ *   actions_agent : int32  [E, A, n_act_agent]        reference action encoding (base_agent.py:407-438)
+ *   actions_planner: int32 [E, n_act_planner]         may be NULL when n_act_planner == 0
+ *   obs_*         : what the reference's step returns per agent key (base_env.py:614-704),
+ *                   stacked over envs:  "world-map", "world-idx_map", "flat", "action_mask", "time",
+ *                   and for the planner "p<i>" vectors stacked as [E, A, flat_planner_agent]
+ *   reward        : float64 [E, A+1]                  agents then planner (layout_from_file.py:519-559)
+ *   done          : int32 [E]                         done["__all__"] (base_env.py:1012) */
+typedef struct aie_buffers {
+    void *state, *state0;
+    const int32_t *actions_agent, *actions_planner;
+    float *obs_agent_map;       /* [E, A, M+1, win, win] */
+    int16_t *obs_agent_idx;     /* [E, A, 2, win, win] */
+    float *obs_agent_flat;      /* [E, A, F_a] */
+    float *mask_agent;          /* [E, A, mask_agent] */
+    float *obs_planner_map;     /* [E, M, H, W]   (ignored unless planner_gets_spatial_info) */
+    int16_t *obs_planner_idx;   /* [E, 2, H, W] */
+    float *obs_planner_flat;    /* [E, F_p] */
+    float *obs_planner_agents;  /* [E, A, flat_planner_agent] */
+    float *mask_planner;        /* [E, mask_planner] */
+    float *obs_time;            /* [E] */
+    double *reward;             /* [E, A+1] */
+    int32_t *done;              /* [E] */
+} aie_buffers;
+
+/* Host-side post-reset snapshot of n envs (struct of arrays, env-major), i.e. what the reference holds
+ * after reset_starting_layout / reset_agent_states / component resets / additional_reset_steps
+ * (base_env.py:899-911).  Maps are 0/1 bytes [n, H, W]. */
+typedef struct aie_host_state {
+    int32_t n;
+    const uint8_t *stone, *wood, *stone_src, *wood_src, *water; /* water may be NULL */
+    const int16_t *loc;                 /* [n, A, 2] (row, col) */
+    const double *coin;                 /* [n, A] starting coin */
+    const int32_t *inv_stone, *inv_wood;/* [n, A] (may be NULL -> 0) */
+    const double *build_payment, *build_skill, *bonus_gather_prob; /* [n, A] */
+    const uint32_t *mt_key;             /* [n, 624] numpy MT19937 key (np.random.get_state()[1]) */
+    const int32_t *mt_pos;              /* [n] */
+    const int32_t *completions;         /* [n] (may be NULL -> 0) */
+} aie_host_state;
+
+/* Debug / test readback of one env (host arrays, any pointer may be NULL).  Layout mirrors the
+ * test oracle's state dump so parity tests compare array-for-array. */
+typedef struct aie_state_dump {
+    uint8_t *cell;        /* [H*W] bit0 Stone bit1 Wood bit2 StoneSrc bit3 WoodSrc bit4 Water bit5 House */
+    int8_t *owner;        /* [H*W] house owner, -1 none */
+    int16_t *loc;         /* [A,2] */
+    double *coin, *esc_coin, *labor;      /* [A] */
+    int32_t *inv, *esc;   /* [A,2] Stone, Wood */
+    int32_t *n_orders;    /* [2,A] */
+    int32_t *bid_hist, *ask_hist; /* [2,A,P] */
+    double *price_hist;   /* [2,A,P] */
+    int32_t *tax_pos;     /* [1] */
+    int32_t *rate_idx;    /* [B] */
+    double *last_coin, *last_income, *last_marg; /* [A] */
+    uint32_t *mt_key;     /* [624] */
+    int32_t *mt_pos, *t, *completions; /* [1] */
+    int32_t *book_rows;   /* [2 commodities][2 sides][book_cap][3] = (agent, price, lifetime), sorted the way
+                             the reference stores its lists (continuous_double_auction.py:246-253, 349-350) */
+    int32_t *book_count;  /* [2][2] */
+    int32_t book_cap;     /* capacity (rows) per (commodity, side) of book_rows */
+} aie_state_dump;
+
+/* A named view into the packed state record, for host frameworks that want struct-of-arrays
+ * tensors [E, ...] (strided views over `state`). */
+typedef struct aie_field {
+    int32_t offset;       /* bytes from the start of an env record */
+    int32_t elem_bytes;   /* 1, 2, 4 or 8 */
+    int32_t is_float;     /* 1 float, 0 integer */
+    int32_t is_signed;
+    int32_t ndim;
+    int32_t shape[4];
+} aie_field;
+
+typedef struct aie_env aie_env;
+
+/* Host outputs for aie_step_host (any pointer may be NULL = do not copy that tensor back). */
+typedef struct aie_host_out {
+    float *obs_agent_map; int16_t *obs_agent_idx; float *obs_agent_flat; float *mask_agent;
+    float *obs_planner_map; int16_t *obs_planner_idx; float *obs_planner_flat; float *obs_planner_agents;
+    float *mask_planner; float *obs_time; double *reward; int32_t *done;
+} aie_host_out;
+
+/* Lifecycle ------------------------------------------------------------------------------------ */
+
+/* Replaces: Scenario construction through foundation.make_env_instance (foundation/__init__.py:16-18,
+ * base_env.py:178-366) for the device-resident part of the env.  `device` is the CUDA ordinal. */
+int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **out);
+int aie_destroy(aie_env *env);
+int aie_get_dims(const aie_env *env, aie_dims *out);
+/* name: "t", "coin", "esc_coin", "labor", "inv", "esc", "loc", "cell", "owner", "n_orders", "bid_hist",
+ * "ask_hist", "price_hist", "tax_pos", "rate_idx", "last_coin", "last_income", "last_marg",
+ * "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions", "orders" */
+int aie_get_field(const aie_env *env, const char *name, aie_field *out);
+
+/* Replaces: CUDADataManager.push_data_to_device + placeholders (env_wrapper.py:297-332). */
+int aie_bind_buffers(aie_env *env, const aie_buffers *bufs);
+
+/* Replaces: env.reset() host->device push (env_wrapper.py:281-332).  Packs envs [env_lo, env_lo+hs->n)
+ * into `state`, saves the same records into `state0` (auto-reset snapshot), finishes the reset on the
+ * device (tax last_coin, utility metric_0; layout_from_file.py:588-593, redistribution.py:1106-1139) and
+ * writes their first observations/masks.  Synchronous. */
+int aie_load_state(aie_env *env, const aie_host_state *hs, int32_t env_lo, void *stream);
+
+/* Replaces: FoundationEnvWrapper.step_all_envs (env_wrapper.py:355-377) == BaseEnvironment.step
+ * (base_env.py:929-1032) for every env: reads actions_*, advances `state`, writes obs/masks/reward/done. */
+int aie_step(aie_env *env, void *stream);
+
+/* Re-emit observations/masks from the current state (no dynamics).  base_env.py:614-756. */
+int aie_observe(aie_env *env, void *stream);
+
+/* End-to-end variant with HOST buffers: copies the actions host->device, steps, copies every non-NULL
+ * output device->host, and synchronises the stream.  Buffers should be pinned for full PCIe rate. */
+int aie_step_host(aie_env *env, const int32_t *actions_agent_host, const int32_t *actions_planner_host,
+                  const aie_host_out *out, void *stream);
+
+/* Test/debug readback of env `e` (synchronous). */
+int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out);
+
+/* Number of kernels the library has launched on this handle since creation (for bench "gpu_launches"). */
+int64_t aie_launch_count(const aie_env *env);
+
+const char *aie_last_error(void);
+int aie_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIE_B200_H */

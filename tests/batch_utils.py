@@ -1,0 +1,89 @@
+"""Helpers for batched product-vs-oracle runs (used by the `-m gpu` tests, smoke-style checks and bench.py)."""
+import numpy as np
+
+from oracle.configs import CONFIGS
+
+
+def product_kwargs(cfg_name):
+    kw = dict(CONFIGS[cfg_name])
+    name = kw.pop("scenario_name")
+    return name, kw
+
+
+def segments(spec, who):
+    """Lengths of the per-subspace slices of the flattened action mask (base_agent.py:440-460)."""
+    P = spec["max_bid_ask"] + 1
+    if who == "p":
+        planner_acts = ("PeriodicBracketTax" in spec["components"] and spec["tax_model"] == 0
+                        and not spec["disable_taxes"])
+        return [1 + spec["n_disc_rates"]] * spec["n_brackets"] if planner_acts else []
+    sizes = []
+    for c in spec["components"]:
+        if c == "Build":
+            sizes += [1]
+        elif c == "ContinuousDoubleAuction":
+            sizes += [P] * 4
+        elif c == "Gather":
+            sizes += [4]
+    if spec["multi_action_agents"]:
+        return [s + 1 for s in sizes]
+    return [1 + sum(sizes)]
+
+
+def sample_from_masks(mask, seg, rng):
+    """mask [..., L] (0/1) -> int32 [..., len(seg)]: uniform over the unmasked entries of each segment."""
+    out = np.zeros(mask.shape[:-1] + (len(seg),), np.int32)
+    off = 0
+    for i, n in enumerate(seg):
+        m = mask[..., off:off + n]
+        out[..., i] = np.argmax(m * (rng.random_sample(m.shape) + 1e-3), axis=-1)
+        off += n
+    return out
+
+
+EXACT_STATE = ["cell", "owner", "loc", "inv", "esc", "n_orders", "bid_hist", "ask_hist", "tax_pos", "rate_idx",
+               "mt_key", "mt_pos", "t"]
+FLOAT_STATE = ["coin", "esc_coin", "labor", "price_hist", "last_coin", "last_income", "last_marg"]
+EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask", "done"]
+FLOAT_OBS = ["a_flat", "p_flat", "p_agents", "time", "rew"]
+
+
+def compare_env(orc, stepper, e, label, spatial=True, rtol=1e-6):
+    """Bit-exact on integer/grid/index/mask work, <= rtol relative on coin/labor/utility floats."""
+    oo, os_ = orc.obs(e), orc.state(e)
+    po, ps = stepper.read_obs(e), stepper.read_state(e)
+    for k in EXACT_STATE:
+        assert np.array_equal(os_[k], np.asarray(ps[k]).reshape(os_[k].shape)), "%s env %d: state %s" % (label, e, k)
+    for k in FLOAT_STATE:
+        assert np.allclose(os_[k], np.asarray(ps[k]).reshape(os_[k].shape), rtol=rtol, atol=1e-9), \
+            "%s env %d: state %s" % (label, e, k)
+    for c in (0, 1):
+        for s in (0, 1):
+            assert np.array_equal(orc.book(e, c, s), ps["books"][(c, s)]), "%s env %d: book %d/%d" % (label, e, c, s)
+    for k in EXACT_OBS:
+        if k in po and (spatial or k not in ("p_map", "p_idx")):
+            assert np.array_equal(oo[k], np.asarray(po[k]).reshape(oo[k].shape)), "%s env %d: obs %s" % (label, e, k)
+    for k in FLOAT_OBS:
+        assert np.allclose(oo[k], np.asarray(po[k]).reshape(oo[k].shape), rtol=rtol, atol=1e-7), \
+            "%s env %d: obs %s" % (label, e, k)
+
+
+def run_pair(env, orc, steps, rng, check_every=0, check_envs=None, on_check=None):
+    """Step the product env and the oracle with identical mask-aware random actions."""
+    spec, st = env.spec, env.stepper
+    seg_a, seg_p = segments(spec, "a"), segments(spec, "p")
+    E = env.n_envs
+    check_envs = list(range(E)) if check_envs is None else check_envs
+    for t in range(1, steps + 1):
+        ma = st.to_numpy(st.buf["mask_agent"])
+        aa = sample_from_masks(ma, seg_a, rng)
+        ap = None
+        if seg_p:
+            ap = sample_from_masks(st.to_numpy(st.buf["mask_planner"]), seg_p, rng)
+        env.step((aa, ap))
+        orc.step(aa, ap)
+        if check_every and (t % check_every == 0 or t == steps):
+            for e in check_envs:
+                compare_env(orc, st, e, "t=%d" % t, spatial=bool(spec["planner_gets_spatial_info"]))
+            if on_check:
+                on_check(t)

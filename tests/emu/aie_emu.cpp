@@ -1,0 +1,98 @@
+// TEST INFRASTRUCTURE ONLY — host emulation of the device source with a 1-lane "warp".
+//
+// The build container has no GPU, so CPU tests compile ai_economist_b200/csrc/aie_core.cuh with g++
+// (-DAIE_EMU, NL = 1: warp collectives become identities) behind the very same C-ABI implementation
+// (aie_abi.inl) and check it against the golden traces and the C oracle.  This validates the algorithmic
+// content of the kernels (not their warp synchronisation, which the `-m gpu` tests and compute-sanitizer
+// cover on the B200).  The product never builds, ships or loads this file: ai_economist_b200/_lib.py only
+// opens libaie_b200.so (CUDA) and raises if it is missing.
+#define AIE_EMU 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../ai_economist_b200/csrc/aie_core.cuh"
+#include "../../ai_economist_b200/csrc/aie_host.h"
+
+struct aie_env;
+namespace aie { namespace be {
+struct State { std::vector<uint8_t> scratch; };
+int init(aie_env *);
+void destroy(aie_env *);
+int upload(aie_env *, void *dst, const void *src, size_t n, void *stream);
+int download(aie_env *, void *dst, const void *src, size_t n, void *stream);
+int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *stream);
+int sync(aie_env *, void *stream);
+int sync_all(aie_env *);
+int launch_finish_reset(aie_env *, int lo, int n, void *stream);
+int launch_step(aie_env *, void *stream);
+int launch_observe(aie_env *, int lo, int n, void *stream);
+} }
+
+#include "../../ai_economist_b200/csrc/aie_abi.inl"
+
+namespace aie { namespace be {
+int init(aie_env *env) {
+    env->be.scratch.assign((size_t)env->cfg.step_scratch_bytes + env->cfg.obs_scratch_bytes + 64, 0);
+    return AIE_OK;
+}
+void destroy(aie_env *) {}
+int upload(aie_env *, void *dst, const void *src, size_t n, void *) { if (dst != src) memcpy(dst, src, n); return AIE_OK; }
+int download(aie_env *, void *dst, const void *src, size_t n, void *) { if (dst != src) memcpy(dst, src, n); return AIE_OK; }
+int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *) { memcpy(dst, src, n); return AIE_OK; }
+int sync(aie_env *, void *) { return AIE_OK; }
+int sync_all(aie_env *) { return AIE_OK; }
+
+int launch_finish_reset(aie_env *env, int lo, int n, void *) {
+    const DevCfg &c = env->cfg;
+    for (int e = lo; e < lo + n; e++) {
+        finish_reset_env(c, env->bufs.state + (size_t)e * c.rec_bytes, env->be.scratch.data(), 0);
+        env->bufs.done[e] = 0;
+        for (int a = 0; a <= c.A; a++) env->bufs.rew[(size_t)e * (c.A + 1) + a] = 0.0;
+    }
+    env->launches++;
+    return AIE_OK;
+}
+int launch_step(aie_env *env, void *) {
+    const DevCfg &c = env->cfg;
+    const DevBufs &b = env->bufs;
+    for (int e = 0; e < env->n_envs; e++) {
+        uint8_t *rec = b.state + (size_t)e * c.rec_bytes;
+        step_env(c, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
+                 (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
+                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0);
+        int32_t *hdr = (int32_t *)rec;
+        if (c.auto_reset && hdr[HDR_T] >= c.T) {  // same sequence as aie_step_kernel
+            int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
+                    episodes = hdr[HDR_EPISODES] + 1;
+            memcpy(rec, b.state0 + (size_t)e * c.rec_bytes, c.off_mt);
+            hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
+            hdr[HDR_EPISODES] = episodes;
+            finish_reset_env(c, rec, env->be.scratch.data(), 0);
+        }
+    }
+    env->launches++;
+    return AIE_OK;
+}
+int launch_observe(aie_env *env, int lo, int n, void *) {
+    const DevCfg &c = env->cfg;
+    const DevBufs &b = env->bufs;
+    const size_t A = c.A, ww = (size_t)c.win * c.win;
+    for (int env_i = lo; env_i < lo + n; env_i++) {
+        size_t e = env_i;
+        ObsOut o;
+        o.a_map = b.a_map + e * A * (c.M + 1) * ww; o.a_idx = b.a_idx + e * A * 2 * ww;
+        o.a_flat = b.a_flat + e * A * c.Fa; o.a_mask = b.a_mask + e * A * c.Na;
+        o.p_map = c.planner_spatial ? b.p_map + e * c.M * c.HW : nullptr;
+        o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
+        o.p_flat = b.p_flat + e * c.Fp; o.p_agents = b.p_agents + e * A * c.Fpa;
+        o.p_mask = b.p_mask + e * c.Np; o.time_obs = b.time_obs + e;
+        observe_env(c, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, 0, 1);
+    }
+    env->launches++;
+    return AIE_OK;
+}
+} }

@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE: drives tests/emu/libaie_emu.so (1-lane host emulation of the device source) through the
+same C-ABI and the same Python BatchStepper as the CUDA product, with numpy arrays as the "device" buffers."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from ai_economist_b200 import _abi
+from ai_economist_b200.stepper import BatchStepper
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libaie_emu.so")
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"], stderr=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def emu_lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = _abi.load_library(_LIB)
+    return _lib
+
+
+class EmuStepper(BatchStepper):
+    def __init__(self, spec, n_envs, auto_reset=False):
+        super().__init__(spec, n_envs, emu_lib(), device_index=0, auto_reset=auto_reset)
+
+    def _alloc(self, shape, dt):
+        return np.zeros(shape, dtype=self._DTYPES[dt])
+
+    def _ptr(self, buf):
+        return buf.ctypes.data_as(C.c_void_p)
+
+    def to_numpy(self, buf):
+        return np.array(buf)
+
+    def state_view(self, name):
+        f = self.field(name)
+        shape = [f.shape[i] for i in range(f.ndim)]
+        n = int(np.prod(shape)) if shape else 1
+        dt = {(1, 0, 0): np.uint8, (1, 0, 1): np.int8, (2, 0, 1): np.int16, (4, 0, 1): np.int32,
+              (4, 0, 0): np.uint32, (8, 1, 1): np.float64}[(f.elem_bytes, f.is_float, f.is_signed)]
+        raw = np.ascontiguousarray(self.buf["state"][:, f.offset:f.offset + n * f.elem_bytes])
+        v = raw.view(dt)
+        return v.reshape([self.n_envs] + shape) if shape else v[:, 0]
+
+
+def emu_factory(spec, n_envs, auto_reset):
+    return EmuStepper(spec, n_envs, auto_reset=auto_reset)

@@ -1,0 +1,150 @@
+"""GPU (B200): the CUDA product, called through the C-ABI, against (1) the golden traces recorded from the
+unmodified reference and (2) the C oracle on identical seeds + action sequences.
+
+Tolerances (BASELINE.json north_star): bit-exact for grid / inventory / index / mask / RNG state; <= 1e-6
+relative for coin / labor / utility / reward floats (atol 1e-9 on float64 state, 1e-7 on float32 observations).
+"""
+import numpy as np
+import pytest
+
+from tests import batch_utils as bu
+from tests import golden_utils as gu
+from tests.stepper_adapters import GoldenStepperAdapter
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda_stepper(spec, n_envs, auto_reset=False):
+    from ai_economist_b200.stepper import CudaStepper
+    return CudaStepper(spec, n_envs, device="cuda:0", auto_reset=auto_reset)
+
+
+def _make_env(cfg_name, n_envs, seed, **extra):
+    from ai_economist_b200 import foundation
+    name, kw = bu.product_kwargs(cfg_name)
+    kw.update(extra)
+    return foundation.make_env_instance(name, n_envs=n_envs, device="cuda:0", seed=seed, **kw)
+
+
+def _load_both(env):
+    from oracle.oracle import OracleBatch
+    host = env.host_reset_arrays()
+    env.stepper.load_state(host)
+    env._loaded = True
+    orc = OracleBatch(env.spec, env.n_envs)
+    for e in range(env.n_envs):
+        orc.load_env(e, {k: v[e] for k, v in host.items()})
+    return orc, host
+
+
+@pytest.mark.parametrize("path", gu.golden_files(), ids=lambda p: p.split("/")[-1])
+def test_cuda_matches_reference_golden_trace(path):
+    def make(spec, init):
+        return GoldenStepperAdapter(_cuda_stepper(spec, 3), init, env_index=1)  # env 1 of 3: exercises indexing
+
+    assert gu.replay(path, make) >= 100
+
+
+@pytest.mark.parametrize("cfg,E,steps,every", [
+    ("c1_tutorial", 96, 400, 50),       # c2 shape: 4 agents, 25x25, single-action
+    ("c3_paper_tax", 48, 320, 40),      # 10 agents 40x40 + PeriodicBracketTax (3 tax days)
+    ("c3_short_period", 32, 200, 25),   # tax annealing, random placement, short order duration
+    ("tax_us_federal", 32, 120, 20),    # multi-action agents, fixed schedule
+    ("c5_small", 8, 150, 25),           # 32 agents, multi-action, K=50 book, sorted-gini branch
+])
+def test_cuda_batch_matches_oracle(cfg, E, steps, every):
+    env = _make_env(cfg, E, seed=4000, auto_reset=False)
+    orc, _ = _load_both(env)
+    for e in range(E):
+        bu.compare_env(orc, env.stepper, e, "reset", spatial=bool(env.spec["planner_gets_spatial_info"]))
+    bu.run_pair(env, orc, steps, np.random.RandomState(123), check_every=every)
+
+
+def test_cuda_full_size_c2_against_oracle_and_invariants():
+    """BASELINE config 2 at full size (8192 env replicas on one GPU), 60 steps: every env is compared with the
+    oracle on a cheap digest (state bytes that must be bit-exact), a sample of envs array-for-array, and
+    size-independent invariants are checked on the whole batch."""
+    import torch
+    E = 8192
+    env = _make_env("c1_tutorial", E, seed=1000, auto_reset=False)
+    orc, host = _load_both(env)
+    rng = np.random.RandomState(7)
+    bu.run_pair(env, orc, 60, rng, check_every=60, check_envs=list(range(0, E, 257)))
+    st = env.stepper
+    loc = st.state_view("loc").cpu().numpy()
+    inv = st.state_view("inv").cpu().numpy()
+    esc = st.state_view("esc").cpu().numpy()
+    n_orders = st.state_view("n_orders").cpu().numpy().astype(np.int64)
+    bid_hist = st.state_view("bid_hist").cpu().numpy().astype(np.int64)
+    ask_hist = st.state_view("ask_hist").cpu().numpy().astype(np.int64)
+    mt_pos = st.state_view("mt_pos").cpu().numpy()
+    for e in range(E):  # oracle digest for every env
+        s = orc.state(e)
+        assert np.array_equal(s["loc"], loc[e]) and np.array_equal(s["inv"], inv[e]), e
+        assert int(s["mt_pos"][0]) == int(mt_pos[e]), e
+    # invariants: order counts equal histogram mass; escrowed units equal open asks; agents on distinct cells
+    assert np.array_equal(n_orders, bid_hist.sum(-1) + ask_hist.sum(-1))
+    assert np.array_equal(esc.transpose(0, 2, 1), ask_hist.sum(-1))
+    flat = loc[..., 0].astype(np.int64) * 25 + loc[..., 1]
+    assert all(len(set(row)) == 4 for row in flat)
+    assert (inv >= 0).all() and (esc >= 0).all()
+    # determinism: a second run from the same snapshot gives bit-identical state records
+    first = st.buf["state"].clone()
+    env.stepper.load_state(host)
+    rng = np.random.RandomState(7)
+    from oracle.oracle import OracleBatch
+    orc2 = OracleBatch(env.spec, 1)  # only used to advance the action RNG identically
+    seg_a = bu.segments(env.spec, "a")
+    for t in range(60):
+        aa = bu.sample_from_masks(st.to_numpy(st.buf["mask_agent"]), seg_a, rng)
+        env.step((aa, None))
+    torch.cuda.synchronize()
+    assert torch.equal(first, st.buf["state"])
+
+
+def test_auto_reset_restores_snapshot_and_continues_stream():
+    """auto_reset=1: an env that reaches episode_length is restored from its load-time snapshot inside the same
+    step (WarpDrive save_copy_and_apply_at_reset semantics); the numpy-legacy stream carries on."""
+    from oracle.oracle import OracleBatch
+    E, T = 16, 12
+    env = _make_env("c1_tutorial", E, seed=77, auto_reset=True, episode_length=T)
+    orc, host = _load_both(env)
+    rng = np.random.RandomState(5)
+    bu.run_pair(env, orc, T - 1, rng, check_every=T - 1)
+    # terminal step: rewards/done come from the finished episode, state+obs are those of the fresh episode
+    st = env.stepper
+    seg_a = bu.segments(env.spec, "a")
+    aa = bu.sample_from_masks(st.to_numpy(st.buf["mask_agent"]), seg_a, rng)
+    env.step((aa, None))
+    orc.step(aa, None)
+    done = st.to_numpy(st.buf["done"])
+    assert done.all()
+    rew = st.to_numpy(st.buf["reward"])
+    fresh = OracleBatch(env.spec, E)
+    for e in range(E):
+        o = orc.obs(e)
+        assert np.allclose(o["rew"], rew[e], rtol=1e-6, atol=1e-9)
+        s_end = orc.state(e)
+        snap = {k: v[e] for k, v in host.items()}
+        snap["mt_key"], snap["mt_pos"] = s_end["mt_key"], int(s_end["mt_pos"][0])
+        snap["completions"] = 1
+        fresh.load_env(e, snap)
+        ps = st.read_state(e)
+        assert int(ps["t"][0]) == 0 and int(ps["completions"][0]) == 1
+    for e in range(E):
+        bu.compare_env(fresh, st, e, "after auto-reset")
+    bu.run_pair(env, fresh, 5, rng, check_every=5)  # and the new episode keeps tracking the oracle
+
+
+def test_public_api_reset_step_shapes_on_device():
+    import torch
+    env = _make_env("c1_tutorial", 5, seed=3)
+    obs = env.reset()
+    assert obs["0"]["world-map"].shape == (5, 7, 11, 11) and obs["0"]["world-map"].is_cuda
+    assert obs["p"]["world-map"].shape == (5, 6, 25, 25)
+    assert obs["0"]["action_mask"].shape == (5, 50) and obs["p"]["action_mask"].shape == (5, 1)
+    o2, rew, done, info = env.step({"0": torch.full((5,), 46, dtype=torch.int32)})
+    assert rew["p"].shape == (5,) and done["__all__"].shape == (5,)
+    assert float(obs["0"]["time"][0]) == pytest.approx(1 / 1000)
+    coin = env.stepper.state_view("coin")
+    assert coin.shape == (5, 4) and torch.all(coin == 10.0)

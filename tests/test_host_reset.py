@@ -1,0 +1,96 @@
+"""CPU: the product's host-side reset (ai_economist_b200/foundation/scenarios.py, numpy legacy RandomState)
+against the post-reset snapshots recorded from the reference (golden init_* arrays), plus API-surface checks
+mirroring the reference's own unit test (tests/test_env.py:68-107)."""
+import json
+
+import numpy as np
+import pytest
+
+from ai_economist_b200 import foundation
+from tests import golden_utils as gu
+from tests.emu.emu_stepper import emu_factory
+
+
+def make_env(meta, n_envs=1, **extra):
+    kw = dict(meta["reference_kwargs"])
+    name = kw.pop("scenario_name")
+    kw["components"] = [tuple(c) for c in kw["components"]]
+    return foundation.make_env_instance(name, n_envs=n_envs, stepper_factory=emu_factory, auto_reset=False,
+                                        **kw, **extra)
+
+
+@pytest.mark.parametrize("path", gu.golden_files(), ids=lambda p: p.split("/")[-1])
+def test_host_reset_matches_reference_snapshot(path):
+    z, meta, init = gu.load_fixture(path)
+    env = make_env(meta)
+    env.seed(meta["seed"])
+    assert env.spec == {**env.spec, **{k: v for k, v in meta["spec"].items() if k != "components"}}
+    st = env.host_reset_arrays()
+    for k in ["stone", "wood", "stone_src", "wood_src", "water", "loc", "inv_stone", "inv_wood", "mt_key"]:
+        if k in st:
+            assert np.array_equal(np.asarray(st[k][0]), init[k]), k
+    for k in ["coin", "build_payment", "build_skill", "bonus_gather_prob"]:
+        assert np.allclose(st[k][0], init[k], rtol=0, atol=0), k
+    assert int(st["mt_pos"][0]) == init["mt_pos"]
+
+
+@pytest.mark.parametrize("path", [p for p in gu.golden_files() if "c1_tutorial_seed1002" in p or "ref_unit" in p],
+                         ids=lambda p: p.split("/")[-1])
+def test_env_api_replays_golden_trace(path):
+    """Full public-API path: make_env_instance -> seed -> reset -> step(dict actions) vs the reference trace."""
+    z, meta, init = gu.load_fixture(path)
+    env = make_env(meta)
+    env.seed(meta["seed"])
+    obs = env.reset()
+    A = env.n_agents
+    assert set(obs.keys()) == {str(i) for i in range(A)} | {"p"}
+    full = {int(t): i for i, t in enumerate(z["full_steps"])}
+    s = env.stepper
+    gu.check_step(z, 0, s.read_obs(0), s.read_state(0), full.get(0), "api")
+    for t in range(1, 61):
+        acts = {str(i): z["act_a"][t - 1][i][None] for i in range(A)}
+        if z["act_p"].shape[1]:
+            acts["p"] = z["act_p"][t - 1][None]
+        obs, rew, done, info = env.step(acts)
+        gu.check_step(z, t, s.read_obs(0), s.read_state(0), full.get(t), "api", books=s.read_state(0)["books"])
+    o, r, d = env.reference_view(0)
+    assert set(o["0"].keys()) == {"world-map", "world-idx_map", "flat", "time", "action_mask"}
+    assert set(r.keys()) == set(o.keys())
+
+
+def test_registry_and_action_spaces_like_reference_unit_test():
+    """tests/test_env.py:68-107: agent counts, planner idx, obs keys, action space sizes."""
+    z, meta, init = gu.load_fixture([p for p in gu.golden_files() if "ref_unit" in p][0])
+    env = make_env(meta, n_envs=3)
+    assert foundation.scenarios.has("uniform/simple_wood_and_stone")
+    assert foundation.components.has("continuousdoubleauction")  # case-insensitive
+    assert env.n_agents == 4 and len(env.all_agents) == 5
+    assert env.get_agent("p").idx == "p"
+    assert env.get_agent(0).action_spaces == 50
+    assert list(env.get_agent("p").action_spaces) == [1]
+    env.seed(5)
+    obs = env.reset()
+    assert obs["0"]["flat"].shape[0] == 3
+    obs, rew, done, info = env.step(None)
+    assert set(obs.keys()) == set(rew.keys()) == set(info.keys())
+    assert "__all__" in done
+    with pytest.raises(KeyError):
+        foundation.scenarios.get("no/such_scenario")
+
+
+def test_second_reset_continues_the_stream_like_the_reference():
+    """reset() after stepping keeps drawing from the env's (device-advanced) numpy stream."""
+    z, meta, init = gu.load_fixture([p for p in gu.golden_files() if "ref_unit" in p][0])
+    env = make_env(meta)
+    env.seed(11)
+    env.reset()
+    for _ in range(5):
+        env.step(None)
+    dev = env.stepper.read_state(0)
+    env.reset()
+    rs = np.random.RandomState(11)
+    rs.set_state(("MT19937", dev["mt_key"], int(dev["mt_pos"][0]), 0, 0.0))
+    # the host stream object now continues from the device's position
+    ref = env.scenario.host_reset(rs)
+    env2 = env.host_reset_arrays  # noqa: F841 (API exists)
+    assert ref["loc"].shape == (4, 2)
