@@ -105,12 +105,15 @@ def load_library(path=None):
     L.aie_load_state.argtypes = [P, C.POINTER(AieHostState), C.c_int32, P]
     L.aie_step.argtypes = [P, P]
     L.aie_observe.argtypes = [P, P]
+    L.aie_step_dynamics.argtypes = [P, P]
+    L.aie_sample_random_actions.argtypes = [P, C.c_uint64, P]
     L.aie_step_host.argtypes = [P, P, P, C.POINTER(AieHostOut), P]
     L.aie_read_state.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
     L.aie_launch_count.argtypes = [P]
     L.aie_launch_count.restype = C.c_int64
     for fn in ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers", "aie_load_state",
-               "aie_step", "aie_observe", "aie_step_host", "aie_read_state"]:
+               "aie_step", "aie_observe", "aie_step_host", "aie_read_state", "aie_step_dynamics",
+               "aie_sample_random_actions"]:
         getattr(L, fn).restype = C.c_int
     if L.aie_abi_version() != ABI_VERSION:
         raise AieError("ABI version mismatch between %s and the Python binding" % path)
@@ -118,8 +121,8 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers",
-                    "aie_load_state", "aie_step", "aie_observe", "aie_step_host", "aie_read_state",
-                    "aie_launch_count", "aie_last_error", "aie_abi_version"]
+                    "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions",
+                    "aie_step_host", "aie_read_state", "aie_launch_count", "aie_last_error", "aie_abi_version"]
 
 
 def config_from_spec(spec, auto_reset=True):

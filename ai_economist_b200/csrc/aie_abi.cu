@@ -36,6 +36,7 @@ int sync_all(aie_env *);
 int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
+int launch_sample(aie_env *, uint64_t seed, void *stream);
 }  // namespace be
 }  // namespace aie
 
@@ -188,6 +189,17 @@ __global__ void __launch_bounds__(128) aie_observe_kernel(const __grid_constant_
     observe_env(c, rec, scratch, o, threadIdx.x, blockDim.x);
 }
 
+__global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
+                                                         uint64_t seed, int items_per_env) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)c.n_envs * items_per_env) return;
+    const int env = (int)(gid / items_per_env), w = (int)(gid - (long long)env * items_per_env);
+    sample_actions_item(c, b.a_mask + (size_t)env * c.A * c.Na, b.p_mask + (size_t)env * c.Np,
+                        const_cast<int32_t *>(b.act_a) + (size_t)env * c.A * c.n_act_a,
+                        c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)env * c.n_act_p : nullptr, w,
+                        mix64(seed ^ mix64((uint64_t)gid)));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 namespace be {
 
@@ -262,6 +274,17 @@ int launch_step(aie_env *env, void *stream) {
 int launch_observe(aie_env *env, int lo, int n, void *stream) {
     aie_observe_kernel<<<n, env->be.obs_threads, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo);
     AIE_CUDA(cudaGetLastError(), "aie_observe_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
+
+int launch_sample(aie_env *env, uint64_t seed, void *stream) {
+    const DevCfg &c = env->cfg;
+    const int items = c.A * (c.multi_action ? c.n_sub : 1) + (c.planner_acts ? c.B : 0);
+    const long long total = (long long)env->n_envs * items;
+    aie_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        env->cfg, env->bufs, host_mix64(seed) ^ host_mix64(++env->sample_calls), items);
+    AIE_CUDA(cudaGetLastError(), "aie_sample_kernel launch");
     env->launches++;
     return AIE_OK;
 }

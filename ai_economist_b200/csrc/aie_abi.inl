@@ -9,6 +9,7 @@
 //   int launch_finish_reset(aie_env*, int lo, int n, void *stream);
 //   int launch_step(aie_env*, void *stream);
 //   int launch_observe(aie_env*, int lo, int n, void *stream);
+//   int launch_sample(aie_env*, uint64_t seed, void *stream);
 #include <string>
 #include <vector>
 
@@ -21,6 +22,7 @@ struct aie_env {
     aie::DevBufs bufs;
     bool bound, loaded;
     int64_t launches;
+    uint64_t sample_calls;
     aie::be::State be;
 };
 
@@ -40,7 +42,7 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     if (rc != AIE_OK) { delete env; return fail(rc, "aie_create: " + err); }
     env->ucfg = *cfg; env->n_envs = n_envs; env->device = device;
     memset(&env->bufs, 0, sizeof(env->bufs));
-    env->bound = env->loaded = false; env->launches = 0;
+    env->bound = env->loaded = false; env->launches = 0; env->sample_calls = 0;
     rc = aie::be::init(env);
     if (rc != AIE_OK) { delete env; return rc; }
     *out = env;
@@ -123,6 +125,18 @@ int aie_step(aie_env *env, void *stream) {
     int rc = aie::be::launch_step(env, stream);
     if (rc != AIE_OK) return rc;
     return aie::be::launch_observe(env, 0, env->n_envs, stream);
+}
+
+int aie_step_dynamics(aie_env *env, void *stream) {
+    if (!env) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_dynamics: bind buffers and load state first");
+    return aie::be::launch_step(env, stream);
+}
+
+int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream) {
+    if (!env) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_sample_random_actions: bind buffers and load state first");
+    return aie::be::launch_sample(env, seed, stream);
 }
 
 int aie_observe(aie_env *env, void *stream) {

@@ -952,4 +952,42 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Random policy (bench / testing utility): uniform over the unmasked entries of one mask segment.
+// ------------------------------------------------------------------------------------------------
+AIE_DEV uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+AIE_DEV int sample_segment(const float *mask, int n, uint64_t key) {
+    int pick = 0, count = 0;
+    for (int j = 0; j < n; j++) {
+        if (mask[j] != 0.0f) {
+            count++;
+            key = mix64(key);
+            if ((uint32_t)(key >> 32) % (uint32_t)count == 0) pick = j;  // reservoir sampling
+        }
+    }
+    return pick;
+}
+// work item w in [0, A * n_seg_a + n_seg_p) of one env
+AIE_DEV void sample_actions_item(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
+                                 int32_t *act_p, int w, uint64_t key) {
+    const int n_seg_a = c.multi_action ? c.n_sub : 1;
+    if (w < c.A * n_seg_a) {
+        const int a = w / n_seg_a, si = w - a * n_seg_a;
+        const float *m = a_mask + (size_t)a * c.Na;
+        if (!c.multi_action) { act_a[a] = sample_segment(m, c.Na, key); return; }
+        int off = 0;
+        for (int j = 0; j < si; j++) off += c.sub_n[j] + 1;
+        act_a[a * c.n_sub + si] = sample_segment(m + off, c.sub_n[si] + 1, key);
+    } else if (c.planner_acts) {
+        const int b = w - c.A * n_seg_a;
+        act_p[b] = sample_segment(p_mask + (size_t)b * (1 + c.R), 1 + c.R, key);
+    }
+}
+
 }  // namespace aie

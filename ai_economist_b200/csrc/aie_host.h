@@ -16,6 +16,12 @@
 namespace aie {
 
 inline int align16(int x) { return (x + 15) & ~15; }
+inline uint64_t host_mix64(uint64_t x) {  // splitmix64 finaliser (same function as mix64 in aie_core.cuh)
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
 
 struct FlatKey { std::string key; int field, c, n; };
 

@@ -160,7 +160,8 @@ class BatchedFoundationEnv:
             self.seed(seeds)
         elif seed is not None:
             self.seed(seed)
-        self._build_views()
+        if self._stepper is not None:  # stepper_factory may return None: host-side reset/spec only (CPU oracle legs)
+            self._build_views()
 
     # ------------------------------------------------------------------ properties (base_env.py:385-437)
     @property

@@ -115,6 +115,13 @@ class BatchStepper:
     def observe(self):
         self._check(self.lib.aie_observe(self._h, self._stream()))
 
+    def step_dynamics(self):
+        self._check(self.lib.aie_step_dynamics(self._h, self._stream()))
+
+    def sample_random_actions(self, seed=0):
+        """Device-side random policy: one uniformly random unmasked action per agent/subspace."""
+        self._check(self.lib.aie_sample_random_actions(self._h, C.c_uint64(int(seed)), self._stream()))
+
     def step_host(self, actions_agent, actions_planner, out_ptrs):
         """End-to-end step with HOST buffers (aie_step_host).  out_ptrs: dict name -> host pointer / None."""
         o = _abi.AieHostOut()

@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — agent-env-steps/sec of the gather-trade-build step (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (random-policy action sampling -> dynamics -> observations) over one batch
+of synthetic env replicas: at N GPUs every rank steps its own `--envs-per-gpu` replicas (weak scaling, no
+collective on the step path).  Rank 0 prints ONE JSON line.
+
+  value   whole-job agent-env-steps/s, inputs and outputs resident in HBM, K steps timed on the device
+          (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks)
+  e2e     the same metric through aie_step_host with HOST (pinned) buffers: actions copied H2D and every
+          observation / mask / reward / done tensor copied D2H inside the timed region, every step
+  roofline  per-kernel algorithmic bytes / CUDA-event duration against MEASURED_PEAKS.json (HBM)
+  cpu_baseline  the CPU oracle (oracle/, a C port of the reference step) on this box's host cores
+--impl reference times that CPU oracle alone (the reference itself is Python and cannot travel to the box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-env-steps/sec gather-trade-build"
+UNIT = "agent-env-steps/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: gather-trade-build, 4 agents, 25x25, 8192 env replicas per B200
+    "c2": dict(cfg="c1_tutorial", envs_per_gpu=8192,
+               desc="gather-trade-build (layout_from_file/simple_wood_and_stone: Build+CDA+Gather), 4 agents, "
+                    "25x25, 8192 env replicas per GPU, uniformly random unmasked actions"),
+    # BASELINE.json configs[2]: + PeriodicBracketTax planner, 10 agents, 40x40, 8192 env replicas per GPU
+    "c3": dict(cfg="c3_paper_tax", envs_per_gpu=8192,
+               desc="gather-trade-build + PeriodicBracketTax, 10 agents, 40x40, 8192 env replicas per GPU"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(cfg_name, n_envs, steps, threads, warmup=2, seed0=500000):
+    """agent-env-steps/s of the CPU oracle (C port of the reference step) with `threads` host threads.
+    Host-side action sampling is excluded from the timed region (as on the GPU side of `value`)."""
+    from oracle.oracle import OracleBatch
+    from tests import batch_utils as bu
+
+    env = _HostOnlyEnv(cfg_name, n_envs, seed0)
+    host = env.host_reset_arrays()
+    orc = OracleBatch(env.spec, n_envs)
+    for e in range(n_envs):
+        orc.load_env(e, {k: v[e] for k, v in host.items()})
+    seg_a, seg_p = bu.segments(env.spec, "a"), bu.segments(env.spec, "p")
+    rng = np.random.RandomState(1)
+    A = env.spec["n_agents"]
+
+    def masks():
+        ma = np.stack([orc.obs(e)["a_mask"] for e in range(n_envs)])
+        mp = np.stack([orc.obs(e)["p_mask"] for e in range(n_envs)]) if seg_p else None
+        return ma, mp
+
+    total = 0.0
+    for t in range(warmup + steps):
+        ma, mp = masks()
+        aa = bu.sample_from_masks(ma, seg_a, rng)
+        ap = bu.sample_from_masks(mp, seg_p, rng) if seg_p else None
+        t0 = time.perf_counter()
+        orc.step(aa, ap, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if t >= warmup:
+            total += dt
+    return n_envs * A * steps / total, total
+
+
+class _HostOnlyEnv:
+    """Host reset + spec without any device (for the CPU oracle legs)."""
+
+    def __init__(self, cfg_name, n_envs, seed0):
+        from ai_economist_b200 import foundation
+        from tests import batch_utils as bu
+
+        name, kw = bu.product_kwargs(cfg_name)
+        self.env = foundation.make_env_instance(name, n_envs=n_envs, seed=seed0,
+                                                stepper_factory=lambda spec, n, auto_reset: None, **kw)
+        self.spec = self.env.spec
+
+    def host_reset_arrays(self):
+        return self.env.host_reset_arrays()
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    n_envs = max(threads * 256, 1024)
+    t0 = time.perf_counter()
+    rate, total = oracle_rate(w["cfg"], n_envs, args.steps, threads, warmup=args.warmup)
+    A = 4 if args.workload == "c2" else 10
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32+f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": "%d env replicas per step on %d host threads" % (n_envs, threads)},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d env replicas x %d steps (C oracle, pthreads), %.1f s" % (n_envs, args.steps, total)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python and does not exist on the GPU box; this arm times oracle/ (a C "
+                "restatement pinned to the reference by golden traces), which is far faster than the reference's "
+                "NumPy step (1 251 env-steps/s/core measured in the build container, BASELINE.md)",
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from ai_economist_b200 import foundation
+    from tests import batch_utils as bu
+
+    w = WORKLOADS[args.workload]
+    E = args.envs_per_gpu or w["envs_per_gpu"]
+    name, kw = bu.product_kwargs(w["cfg"])
+    t_setup = time.perf_counter()
+    env = foundation.make_env_instance(name, n_envs=E, device=str(dev), seed=1000 + rank * E, auto_reset=True, **kw)
+    env.reset()
+    st = env.stepper
+    A = env.n_agents
+    d = st.dims
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
+
+    def one_step(i):
+        st.sample_random_actions(seed=1234 + rank)
+        st.step()  # dynamics + observe
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    launches0 = st.launch_count()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        one_step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = st.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    value = world * E * A * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel durations (separate pass, CUDA events between the kernels, same stream) ----
+    n_prof = min(args.steps, 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_prof)]
+    for i in range(n_prof):
+        evs[i][0].record(); st.sample_random_actions(seed=99)
+        evs[i][1].record(); st.step_dynamics()
+        evs[i][2].record(); st.observe()
+        evs[i][3].record()
+    torch.cuda.synchronize()
+    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(3)]
+    peak, peak_src = peaks()
+    ww = d.window * d.window
+    obs_bytes = (A * ((d.n_map_channels + 1) * ww * 4 + 2 * ww * 2 + d.flat_agent * 4 + d.mask_agent * 4)
+                 + d.flat_planner * 4 + A * d.flat_planner_agent * 4 + d.mask_planner * 4 + 4
+                 + (d.n_map_channels * d.height * d.width * 4 + 2 * d.height * d.width * 2
+                    if env.spec["planner_gets_spatial_info"] else 0))
+    step_bytes = 2 * d.state_bytes + 4 * (A * d.n_act_agent + d.n_act_planner) + 8 * (A + 1) + 4
+    obs_prefix = st.field("orders").offset  # bytes of the record the observe kernel reads
+    kernels = {
+        "aie_observe_kernel": {"ms": k_ms[2], "alg_bytes_per_launch": E * (obs_bytes + obs_prefix)},
+        "aie_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * step_bytes},
+        "aie_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (A * d.mask_agent * 4 + A * d.n_act_agent * 4)},
+    }
+    for k in kernels.values():
+        k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["achieved_gbs"] / peak
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "whole_step": {"alg_bytes_per_env_step": d.algorithmic_bytes_per_env_step,
+                               "achieved": d.algorithmic_bytes_per_env_step * E * args.steps / (ms_total * 1e-3) / 1e9,
+                               "frac": d.algorithmic_bytes_per_env_step * E * args.steps / (ms_total * 1e-3) / 1e9 / peak},
+                "kernels": kernels}
+
+    # ---- e2e through aie_step_host with pinned HOST buffers ----
+    out_host, out_ptrs, d2h = {}, {}, 0
+    import ctypes as C
+    for nm in ["obs_agent_map", "obs_agent_idx", "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx",
+               "obs_planner_flat", "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]:
+        if nm in st.buf:
+            t = torch.empty(st.buf[nm].shape, dtype=st.buf[nm].dtype, pin_memory=True)
+            out_host[nm] = t
+            out_ptrs[nm] = C.c_void_p(t.data_ptr())
+            d2h += t.numel() * t.element_size()
+    act_a = torch.zeros(st.buf["actions_agent"].shape, dtype=torch.int32, pin_memory=True)
+    act_p = torch.zeros(st.buf["actions_planner"].shape, dtype=torch.int32, pin_memory=True)
+    h2d = act_a.numel() * 4 + (act_p.numel() * 4 if d.n_act_planner else 0)
+    seg_a, seg_p = bu.segments(env.spec, "a"), bu.segments(env.spec, "p")
+    rng = np.random.RandomState(rank)
+    out_host["mask_agent"].copy_(st.buf["mask_agent"])
+    out_host["mask_planner"].copy_(st.buf["mask_planner"])
+    e2e_s = 0.0
+    n_e2e = max(3, args.e2e_steps)
+    for i in range(n_e2e + 2):
+        act_a.copy_(torch.from_numpy(bu.sample_from_masks(out_host["mask_agent"].numpy(), seg_a, rng)))
+        if seg_p:
+            act_p.copy_(torch.from_numpy(bu.sample_from_masks(out_host["mask_planner"].numpy(), seg_p, rng)))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.step_host(C.c_void_p(act_a.data_ptr()), C.c_void_p(act_p.data_ptr()) if d.n_act_planner else None, out_ptrs)
+        dt = time.perf_counter() - t0  # aie_step_host synchronises the stream before returning
+        if i >= 2:
+            e2e_s += dt
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * A * n_e2e / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "i32+f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "envs_per_gpu": E, "n_agents": A, "world": [d.height, d.width],
+                   "parallelism": "env replicas sharded over %d GPU(s), no collective on the step path" % world,
+                   "actions": "device random policy over unmasked actions (aie_sample_kernel), inside the timed region",
+                   "l2": "no explicit flush: each step rewrites %.0f MB of observations (> 126 MB L2) and touches "
+                         "%.0f MB of state" % (E * obs_bytes / 1e6, E * d.state_bytes / 1e6),
+                   "auto_reset": True, "setup_s": t_setup},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "what": "aie_step_host: pinned host actions in, every observation/mask/reward/done "
+                                        "tensor copied back to pinned host memory each step (PCIe-bound)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_cpu = max(threads * 256, 1024)
+        probe, _ = oracle_rate(w["cfg"], n_cpu, 5, threads, warmup=1)
+        steps_cpu = int(max(20, min(2000, 12.0 * probe / (n_cpu * A))))
+        rate, total = oracle_rate(w["cfg"], n_cpu, steps_cpu, threads, warmup=2)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%d env replicas x %d steps of the same workload on %d host threads "
+                                          "(C oracle of the reference step), %.1f s" % (n_cpu, steps_cpu, threads, total)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

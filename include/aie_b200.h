@@ -222,8 +222,18 @@ int aie_load_state(aie_env *env, const aie_host_state *hs, int32_t env_lo, void 
  * (base_env.py:929-1032) for every env: reads actions_*, advances `state`, writes obs/masks/reward/done. */
 int aie_step(aie_env *env, void *stream);
 
-/* Re-emit observations/masks from the current state (no dynamics).  base_env.py:614-756. */
+/* The two halves of aie_step, separately launchable (profiling / custom pipelines):
+ * aie_step_dynamics = components + scenario_step + rewards + done (base_env.py:1000-1005, 1011-1012);
+ * aie_observe       = observations + masks from the current state (base_env.py:614-756). */
+int aie_step_dynamics(aie_env *env, void *stream);
 int aie_observe(aie_env *env, void *stream);
+
+/* Random policy on the device: writes into the bound action buffers one uniformly random *unmasked* action
+ * per agent (per subspace in multi-action mode) and per planner bracket, from the current mask tensors.
+ * Replaces: BaseAgent.get_random_action / populate_random_actions (base/base_agent.py:365-405) and the
+ * tutorial's mask-aware random sampler (tutorials/economic_simulation_basic.ipynb, cell 18).  The stream is a
+ * counter-based hash of (seed, call index, env, agent, subspace); it is not the env's numpy stream. */
+int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream);
 
 /* End-to-end variant with HOST buffers: copies the actions host->device, steps, copies every non-NULL
  * output device->host, and synchronises the stream.  Buffers should be pinned for full PCIe rate. */

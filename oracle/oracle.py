@@ -138,6 +138,10 @@ class OracleBatch:
 
     def load_env(self, e, st):
         """st: post-reset host state dict (u8 maps [H,W], loc i16 [A,2], f64 [A] vectors, mt_key, mt_pos)."""
+        A = self.A
+        st = dict(st)
+        st.setdefault("inv_stone", np.zeros(A, np.int32))
+        st.setdefault("inv_wood", np.zeros(A, np.int32))
         g = lambda k, dt: np.ascontiguousarray(st[k], dtype=dt)
         arrs = [g("stone", np.uint8), g("wood", np.uint8), g("stone_src", np.uint8), g("wood_src", np.uint8),
                 g("water", np.uint8), g("loc", np.int16), g("coin", np.float64),

@@ -1,4 +1,6 @@
 """Helpers for batched product-vs-oracle runs (used by the `-m gpu` tests, smoke-style checks and bench.py)."""
+import os
+
 import numpy as np
 
 from oracle.configs import CONFIGS
@@ -81,7 +83,7 @@ def run_pair(env, orc, steps, rng, check_every=0, check_envs=None, on_check=None
         if seg_p:
             ap = sample_from_masks(st.to_numpy(st.buf["mask_planner"]), seg_p, rng)
         env.step((aa, ap))
-        orc.step(aa, ap)
+        orc.step(aa, ap, n_threads=min(os.cpu_count() or 1, max(1, E // 8)))
         if check_every and (t % check_every == 0 or t == steps):
             for e in check_envs:
                 compare_env(orc, st, e, "t=%d" % t, spatial=bool(spec["planner_gets_spatial_info"]))
