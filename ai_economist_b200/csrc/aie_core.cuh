@@ -874,11 +874,14 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     bsync();
 
     // ---- phase 2: outputs ----------------------------------------------------------------------
+    // Loops are arranged so that consecutive threads write consecutive addresses and no index needs a
+    // division by a run-time constant inside the streaming loops.
     if (tid == 0) o.time_obs[0] = (float)time_v;
     if (c.planner_spatial) {
-        for (int i = tid; i < M * HW; i += nthr) {
-            int ch = i / HW, k = i - ch * HW;
-            o.p_map[i] = (e.cell[k] & channel_bit(c, ch)) ? 1.0f : 0.0f;
+        for (int ch = 0; ch < M; ch++) {
+            const uint8_t bit = channel_bit(c, ch);
+            float *dst = o.p_map + (size_t)ch * HW;
+            for (int k = tid; k < HW; k += nthr) dst[k] = (e.cell[k] & bit) ? 1.0f : 0.0f;
         }
         for (int k = tid; k < HW; k += nthr) {
             int ow = e.owner[k];
@@ -886,56 +889,60 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             o.p_idx[HW + k] = (int16_t)s.locmap[k];
         }
     }
-    // agent windows (layout_from_file.py:468-515)
-    for (int i = tid; i < A * (M + 1) * ww; i += nthr) {
-        int a = i / ((M + 1) * ww), rem = i - a * (M + 1) * ww;
-        int ch = rem / ww, q = rem - ch * ww;
-        int dr = q / win, dc = q - dr * win;
-        int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
-        bool inside = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
-        float v = 0.0f;
-        if (inside) v = (ch == M) ? 1.0f : ((e.cell[r2 * W + c2] & channel_bit(c, ch)) ? 1.0f : 0.0f);
-        o.a_map[i] = v;
-    }
-    for (int i = tid; i < A * 2 * ww; i += nthr) {
-        int a = i / (2 * ww), rem = i - a * 2 * ww;
-        int ch = rem / ww, q = rem - ch * ww;
-        int dr = q / win, dc = q - dr * win;
-        int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
-        int v = 0;
-        if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W) {
-            int k = r2 * W + c2;
-            if (ch == 0) { int ow = e.owner[k]; v = ow < 0 ? 0 : ow + 2; }
-            else v = s.locmap[k];
-            if (v == a + 2) v = 1;
+    // agent windows (layout_from_file.py:468-515): one work item per (agent, window cell); the item reads its
+    // cell once and emits all M+1 map channels and both index channels.
+    {
+        uint8_t bits[6];
+        for (int ch = 0; ch < M; ch++) bits[ch] = channel_bit(c, ch);
+        int a = tid / ww, q = tid - a * ww;          // one division per thread, then incremental
+        const int da = nthr / ww, dq = nthr - da * ww;
+        for (int i = tid; i < A * ww; i += nthr) {
+            const int dr = q / win, dc = q - dr * win;   // win is small; q < ww
+            const int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
+            const bool inside = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
+            uint8_t cb = 0; int vo = 0, vl = 0;
+            if (inside) {
+                const int k = r2 * W + c2;
+                cb = e.cell[k];
+                const int ow = e.owner[k];
+                vo = ow < 0 ? 0 : ow + 2;
+                vl = s.locmap[k];
+                if (vo == a + 2) vo = 1;
+                if (vl == a + 2) vl = 1;
+            }
+            float *dst = o.a_map + (size_t)a * (M + 1) * ww + q;
+            for (int ch = 0; ch < M; ch++) dst[(size_t)ch * ww] = (cb & bits[ch]) ? 1.0f : 0.0f;
+            dst[(size_t)M * ww] = inside ? 1.0f : 0.0f;
+            int16_t *di = o.a_idx + (size_t)a * 2 * ww + q;
+            di[0] = (int16_t)vo;
+            di[ww] = (int16_t)vl;
+            a += da; q += dq;
+            if (q >= ww) { q -= ww; a += 1; }
         }
-        o.a_idx[i] = (int16_t)v;
     }
     // flat vectors (base_env.py:562-612: sorted-key concatenation, float32)
-    for (int i = tid; i < A * c.Fa; i += nthr) {
-        int a = i / c.Fa, j = i - a * c.Fa;
-        o.a_flat[i] = (float)flat_value(c, e, s, c.prog_a[j], a, time_v, inv_scale);
-    }
+    for (int a = 0; a < A; a++)
+        for (int j = tid; j < c.Fa; j += nthr)
+            o.a_flat[a * c.Fa + j] = (float)flat_value(c, e, s, c.prog_a[j], a, time_v, inv_scale);
     for (int j = tid; j < c.Fp; j += nthr) o.p_flat[j] = (float)flat_value(c, e, s, c.prog_p[j], 0, time_v, inv_scale);
-    for (int i = tid; i < A * c.Fpa; i += nthr) {
-        int a = i / c.Fpa, j = i - a * c.Fpa;
-        o.p_agents[i] = (float)flat_value(c, e, s, c.prog_pa[j], a, time_v, inv_scale);
-    }
+    for (int a = 0; a < A; a++)
+        for (int j = tid; j < c.Fpa; j += nthr)
+            o.p_agents[a * c.Fpa + j] = (float)flat_value(c, e, s, c.prog_pa[j], a, time_v, inv_scale);
     // masks (base_agent.py:440-460)
-    for (int i = tid; i < A * c.Na; i += nthr) {
-        int a = i / c.Na, j = i - a * c.Na;
-        uint16_t en = c.mprog_a[j];
-        int idx = AIE_PROG_IDX(en), cc = AIE_PROG_C(en);
-        bool v;
-        switch (AIE_PROG_FIELD(en)) {
-            case MK_BUILD: v = s.agent_bits[a] & 1; break;
-            case MK_BUY: v = e.n_orders[cc * A + a] < c.K && (double)idx <= e.coin[a]; break;
-            case MK_SELL: v = e.n_orders[cc * A + a] < c.K && e.inv[2 * a + cc] > 0; break;
-            case MK_GATHER: v = (s.agent_bits[a] >> (1 + idx)) & 1; break;
-            default: v = true;
+    for (int a = 0; a < A; a++)
+        for (int j = tid; j < c.Na; j += nthr) {
+            uint16_t en = c.mprog_a[j];
+            int idx = AIE_PROG_IDX(en), cc = AIE_PROG_C(en);
+            bool v;
+            switch (AIE_PROG_FIELD(en)) {
+                case MK_BUILD: v = s.agent_bits[a] & 1; break;
+                case MK_BUY: v = e.n_orders[cc * A + a] < c.K && (double)idx <= e.coin[a]; break;
+                case MK_SELL: v = e.n_orders[cc * A + a] < c.K && e.inv[2 * a + cc] > 0; break;
+                case MK_GATHER: v = (s.agent_bits[a] >> (1 + idx)) & 1; break;
+                default: v = true;
+            }
+            o.a_mask[a * c.Na + j] = v ? 1.0f : 0.0f;
         }
-        o.a_mask[i] = v ? 1.0f : 0.0f;
-    }
     if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
         for (int j = tid; j < c.Np; j += nthr) {
             int rr = j % (1 + c.R);

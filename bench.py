@@ -209,7 +209,9 @@ def main():
     E = args.envs_per_gpu or w["envs_per_gpu"]
     name, kw = bu.product_kwargs(w["cfg"])
     t_setup = time.perf_counter()
-    env = foundation.make_env_instance(name, n_envs=E, device=str(dev), seed=1000 + rank * E, auto_reset=True, **kw)
+    from ai_economist_b200.sharding import shard_seeds
+    env = foundation.make_env_instance(name, n_envs=E, device=str(dev), seeds=shard_seeds(1000, rank, world, E),
+                                       auto_reset=True, **kw)
     env.reset()
     st = env.stepper
     A = env.n_agents
