@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -22,6 +23,7 @@ namespace aie {
 namespace be {
 struct State {
     int step_wpb;        // warps (envs) per CTA of the step kernel
+    int step_minb;       // register-allocation variant of the step kernel (3, 4 or 5 CTAs per SM)
     size_t step_smem;    // dynamic shared memory per CTA
     int obs_threads;
     size_t obs_smem;
@@ -81,7 +83,9 @@ __device__ __forceinline__ uint8_t *warp_region(uint8_t *smem, int wpb, int warp
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b) {
+// MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * wpb + warp;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_cons
     }
 }
 
-__global__ void __launch_bounds__(128) aie_observe_kernel(const __grid_constant__ DevCfg c, const DevBufs b, int lo) {
+__global__ void __launch_bounds__(128, 12) aie_observe_kernel(const __grid_constant__ DevCfg c, const DevBufs b, int lo) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int env = lo + blockIdx.x;
     uint64_t *bar = (uint64_t *)smem;
@@ -230,7 +234,14 @@ int init(aie_env *env) {
     env->be.obs_threads = 128;
     env->be.obs_smem = 16 + (size_t)c.obs_prefix_bytes + c.obs_scratch_bytes;
     if (env->be.obs_smem > max_smem) return fail(AIE_EINVAL, "observation staging does not fit in shared memory");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    // pick the variant with the most resident warps that shared memory allows (override: AIE_STEP_MINB=3|4|5)
+    const size_t smem_sm = prop.sharedMemPerMultiprocessor;
+    int fit = (int)(smem_sm / (env->be.step_smem + 1024));
+    env->be.step_minb = fit >= 5 ? 5 : (fit >= 4 ? 4 : 3);
+    if (const char *ov = getenv("AIE_STEP_MINB")) { int v = atoi(ov); if (v >= 3 && v <= 5) env->be.step_minb = v; }
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
     return AIE_OK;
@@ -266,7 +277,11 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
 }
 int launch_step(aie_env *env, void *stream) {
     const int wpb = env->be.step_wpb;
-    aie_step_kernel<<<(env->n_envs + wpb - 1) / wpb, wpb * 32, env->be.step_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs);
+    const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (env->be.step_minb == 5) aie_step_kernel<5><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs);
+    else if (env->be.step_minb == 4) aie_step_kernel<4><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs);
+    else aie_step_kernel<3><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs);
     AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
     env->launches++;
     return AIE_OK;

@@ -271,6 +271,15 @@ AIE_DEV void build_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
 // ------------------------------------------------------------------------------------------------
 // ContinuousDoubleAuction  (components/continuous_double_auction.py)
 // ------------------------------------------------------------------------------------------------
+// i / K without a run-time division (K_magic = floor(2^32 / K) + 1, exact for i < 2^32 / K; K == 1 -> magic 0)
+AIE_DEV int div_K(const DevCfg &c, int i) {
+#if AIE_ON_DEVICE
+    return c.K_magic ? (int)__umulhi((uint32_t)i, c.K_magic) : i;
+#else
+    return c.K_magic ? (int)(((uint64_t)(uint32_t)i * c.K_magic) >> 32) : i;
+#endif
+}
+
 AIE_DEV uint32_t order_pack(int birth, int price, int side) { return ((uint32_t)birth << 8) | ((uint32_t)price << 1) | (uint32_t)side; }
 AIE_DEV int order_birth(uint32_t o) { return (int)(o >> 8); }
 AIE_DEV int order_price(uint32_t o) { return (int)((o >> 1) & 127u); }
@@ -286,10 +295,9 @@ AIE_DEV void order_insert(uint32_t *slots, int K, uint32_t o) {
 // loop survives as the final tie-break of the matching key.
 AIE_DEV void cda_create(const DevCfg &c, Env &e, const StepScratch &s, int t, int lane) {
     const int A = c.A, P = c.P, K = c.K;
+    for (int i = lane; i < 2 * A * P; i += NL) e.price_hist[i] *= 0.995;  // independent of order creation
     for (int a = lane; a < A; a += NL) {
         for (int cc = 0; cc < 2; cc++) {
-            double *ph = e.price_hist + (cc * A + a) * P;
-            for (int p = 0; p < P; p++) ph[p] *= 0.995;
             uint32_t *slots = e.orders + (cc * A + a) * K;
             int kb = s.act_buy[cc * A + a];
             if (kb != 0) {
@@ -335,7 +343,7 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, int t, int lane) {
             for (int i = lane; i < n; i += NL) {
                 uint32_t o = slots[i];
                 if (o != ORDER_EMPTY && order_side(o) == 0) {
-                    int a = i / K;
+                    int a = div_K(c, i);
                     if ((possible >> a) & 1ull) {
                         uint32_t key = ((uint32_t)(order_price(o) + 1) << 20) | ((uint32_t)(t - order_birth(o)) << 8) |
                                        (uint32_t)(255 - a);
@@ -354,7 +362,7 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, int t, int lane) {
             for (int i = lane; i < n; i += NL) {
                 uint32_t o = slots[i];
                 if (o != ORDER_EMPTY && order_side(o) == 1) {
-                    int a = i / K;
+                    int a = div_K(c, i);
                     if (a != buyer) {
                         uint32_t key = ((uint32_t)(P - order_price(o)) << 20) | ((uint32_t)(t - order_birth(o)) << 8) |
                                        (uint32_t)(255 - a);
@@ -371,6 +379,7 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, int t, int lane) {
             if (bprice < aprice) { possible &= ~(1ull << buyer); if (!possible) break; continue; }
             // trade: price of whichever order came first (:297-304)
             int price = (blife <= alife) ? aprice : bprice;
+            wsync();  // all lanes have finished scanning the slots lane 0 is about to clear
             if (lane == 0) {
                 slots[bi] = ORDER_EMPTY;
                 slots[ai] = ORDER_EMPTY;
@@ -396,23 +405,23 @@ AIE_DEV void cda_expire(const DevCfg &c, Env &e, int t, int lane) {
     for (int a = lane; a < A; a += NL) {
         for (int cc = 0; cc < 2; cc++) {
             uint32_t *slots = e.orders + (cc * A + a) * K;
-            for (int side = 0; side < 2; side++) {
-                for (int k = 0; k < K; k++) {
-                    uint32_t o = slots[k];
-                    if (o == ORDER_EMPTY || order_side(o) != side || t - order_birth(o) < c.D) continue;
-                    int price = order_price(o);
-                    if (side == 0) {
-                        e.esc_coin[a] -= (double)price;
-                        e.coin[a] += (double)price;
-                        e.bid_hist[(cc * A + a) * P + price] -= 1;
-                    } else {
-                        e.esc[2 * a + cc] -= 1;
-                        e.inv[2 * a + cc] += 1;
-                        e.ask_hist[(cc * A + a) * P + price] -= 1;
-                    }
-                    e.n_orders[cc * A + a] -= 1;
-                    slots[k] = ORDER_EMPTY;
+            // an agent creates at most one bid and one ask per commodity per step, so at most one of each
+            // expires here; they touch different state (coin vs. the commodity), so one pass is order-safe
+            for (int k = 0; k < K; k++) {
+                uint32_t o = slots[k];
+                if (o == ORDER_EMPTY || t - order_birth(o) < c.D) continue;
+                int price = order_price(o);
+                if (order_side(o) == 0) {
+                    e.esc_coin[a] -= (double)price;
+                    e.coin[a] += (double)price;
+                    e.bid_hist[(cc * A + a) * P + price] -= 1;
+                } else {
+                    e.esc[2 * a + cc] -= 1;
+                    e.inv[2 * a + cc] += 1;
+                    e.ask_hist[(cc * A + a) * P + price] -= 1;
                 }
+                e.n_orders[cc * A + a] -= 1;
+                slots[k] = ORDER_EMPTY;
             }
         }
     }
@@ -559,13 +568,25 @@ AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
                 }
             }
         }
+        wsync();  // lane 0's straddle fix-up is visible before the group loads below touch the same word
         int k_lo = (w + 1) >> 1, k_hi = w_end >> 1;  // cells with both words inside this segment
-        for (int k = k_lo + lane; k < k_hi; k += NL) {
-            uint8_t cb = e.cell[k];
-            if ((cb & src_bit) && !(cb & res_bit)) {
+        // 4 cells per lane per iteration: one 32-bit load finds the (rare) empty source cells of a group
+        const uint32_t *cell32 = (const uint32_t *)e.cell;
+        for (int g = (k_lo >> 2) + lane; 4 * g < k_hi; g += NL) {
+            const uint32_t wv = cell32[g];
+            uint32_t cand = ((wv >> (2 + cc)) & ~(wv >> cc)) & 0x01010101u;  // byte LSB: source set, resource clear
+            while (cand) {
+#if AIE_ON_DEVICE
+                const int j = (__ffs(cand) - 1) >> 3;
+#else
+                const int j = (__builtin_ffs(cand) - 1) >> 3;
+#endif
+                cand &= cand - 1;
+                const int k = 4 * g + j;
+                if (k < k_lo || k >= k_hi) continue;
                 uint64_t v = ((uint64_t)(mt_temper(e.mt[base + 2 * k]) >> 5) << 26) |
                              (uint64_t)(mt_temper(e.mt[base + 2 * k + 1]) >> 6);
-                if (v < thresh) e.cell[k] = cb | res_bit;
+                if (v < thresh) e.cell[k] = (uint8_t)(e.cell[k] | res_bit);
             }
         }
         if (w_end & 1) pend_a = mt_temper(e.mt[base + w_end - 1]);
@@ -892,8 +913,6 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     // agent windows (layout_from_file.py:468-515): one work item per (agent, window cell); the item reads its
     // cell once and emits all M+1 map channels and both index channels.
     {
-        uint8_t bits[6];
-        for (int ch = 0; ch < M; ch++) bits[ch] = channel_bit(c, ch);
         int a = tid / ww, q = tid - a * ww;          // one division per thread, then incremental
         const int da = nthr / ww, dq = nthr - da * ww;
         for (int i = tid; i < A * ww; i += nthr) {
@@ -911,8 +930,10 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
                 if (vl == a + 2) vl = 1;
             }
             float *dst = o.a_map + (size_t)a * (M + 1) * ww + q;
-            for (int ch = 0; ch < M; ch++) dst[(size_t)ch * ww] = (cb & bits[ch]) ? 1.0f : 0.0f;
-            dst[(size_t)M * ww] = inside ? 1.0f : 0.0f;
+#pragma unroll
+            for (int ch = 0; ch < 6; ch++)
+                if (ch < M) dst[ch * ww] = (cb & channel_bit(c, ch)) ? 1.0f : 0.0f;
+            dst[M * ww] = inside ? 1.0f : 0.0f;
             int16_t *di = o.a_idx + (size_t)a * 2 * ww + q;
             di[0] = (int16_t)vo;
             di[ww] = (int16_t)vl;

@@ -82,6 +82,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, std::string 
         if (c.D < 1 || c.D > 4095) return bad("order_duration must be in [1, 4095]");
         if (c.K < 1 || c.K > 255) return bad("max_num_orders must be in [1, 255]");
     } else { c.P = 1; c.D = 1; c.K = 1; }
+    c.K_magic = c.K == 1 ? 0u : (uint32_t)((1ull << 32) / (uint64_t)c.K) + 1u;
     c.tax_model = u.tax_model; c.disable_taxes = u.disable_taxes ? 1 : 0; c.period = u.period;
     c.B = u.n_brackets; c.R = u.n_disc_rates;
     if (c.has[COMP_TAX]) {

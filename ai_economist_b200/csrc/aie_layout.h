@@ -59,6 +59,7 @@ struct DevCfg {
     double mix;
     double build_payment, build_labor, move_labor, collect_labor, order_labor;
     int32_t P, D, K;
+    uint32_t K_magic;  // floor(2^32 / K) + 1, or 0 when K == 1
     int32_t tax_model, disable_taxes, period, B, R;
     double cutoffs[16], disc_rates[64], fixed_rates[16];
     int32_t tax_annealing;

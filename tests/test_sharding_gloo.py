@@ -3,14 +3,14 @@ collective.  Each rank steps its shard (1-lane host emulation of the device code
 unsharded run, and the timing reduction must be a max over ranks."""
 import os
 import socket
+import subprocess
 import sys
 
 import numpy as np
-import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from tests._gloo_worker import run_shard
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _free_port():
@@ -21,46 +21,18 @@ def _free_port():
     return p
 
 
-def _run_shard(seeds, steps):
-    sys.path.insert(0, ROOT)
-    from ai_economist_b200 import foundation
-    from tests import batch_utils as bu
-    from tests.emu.emu_stepper import emu_factory
-
-    name, kw = bu.product_kwargs("c1_tutorial")
-    env = foundation.make_env_instance(name, n_envs=len(seeds), seeds=seeds, stepper_factory=emu_factory,
-                                       auto_reset=False, **kw)
-    env.reset()
-    for t in range(steps):
-        env.stepper.sample_random_actions(seed=0)  # keyed by (call index, local env) -> make it shard-invariant below
-        # overwrite with a deterministic function of the GLOBAL seed so shards and the full run agree
-        acts = np.stack([np.random.RandomState(s * 1000 + t).randint(0, 50, size=(4, 1)) for s in seeds]).astype(np.int32)
-        env.step((acts, None))
-    st = env.stepper
-    return np.stack([st.read_state(e)["loc"] for e in range(len(seeds))]), np.array(st.buf["reward"])
-
-
-def _worker(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    sys.path.insert(0, ROOT)
-    from ai_economist_b200.sharding import max_over_ranks, shard_seeds
-
-    seeds = shard_seeds(1000, rank, world, 3)
-    loc, rew = _run_shard(seeds, 12)
-    t = max_over_ranks(1.0 + rank, dist)
-    dist.barrier()
-    np.savez(out % rank, loc=loc, rew=rew, tmax=t, seeds=np.array(seeds))
-    dist.destroy_process_group()
-
-
 def test_two_rank_shards_equal_unsharded_run(tmp_path):
     port = _free_port()
     out = str(tmp_path / "rank%d.npz")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), out], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
     r0, r1 = np.load(out % 0), np.load(out % 1)
     assert list(r0["seeds"]) == [1000, 1001, 1002] and list(r1["seeds"]) == [1003, 1004, 1005]
     assert float(r0["tmax"]) == 2.0 and float(r1["tmax"]) == 2.0  # max over ranks, on every rank
-    loc, rew = _run_shard(list(range(1000, 1006)), 12)
+    loc, rew = run_shard(list(range(1000, 1006)), 12)
     assert np.array_equal(np.concatenate([r0["loc"], r1["loc"]]), loc)
     assert np.array_equal(np.concatenate([r0["rew"], r1["rew"]]), rew)
