@@ -898,14 +898,22 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     // Loops are arranged so that consecutive threads write consecutive addresses and no index needs a
     // division by a run-time constant inside the streaming loops.
     if (tid == 0) o.time_obs[0] = (float)time_v;
+    // channel -> cell bit, hoisted (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc)
+    const uint32_t bit3 = c.has_water ? CELL_WATER : CELL_STONE_SRC;
+    const uint32_t bit4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
     if (c.planner_spatial) {
-        for (int ch = 0; ch < M; ch++) {
-            const uint8_t bit = channel_bit(c, ch);
-            float *dst = o.p_map + (size_t)ch * HW;
-            for (int k = tid; k < HW; k += nthr) dst[k] = (e.cell[k] & bit) ? 1.0f : 0.0f;
-        }
+        // one thread per map cell: the cell byte is read once and fans out to all M channels (consecutive
+        // threads -> consecutive addresses in every channel plane) plus both index planes
         for (int k = tid; k < HW; k += nthr) {
-            int ow = e.owner[k];
+            const uint32_t cb = e.cell[k];
+            float *dst = o.p_map + k;
+            dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += HW;
+            dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += HW;
+            dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += HW;
+            dst[0] = (cb & bit3) ? 1.0f : 0.0f;        dst += HW;
+            dst[0] = (cb & bit4) ? 1.0f : 0.0f;
+            if (M == 6) { dst += HW; dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; }
+            const int ow = e.owner[k];
             o.p_idx[k] = (int16_t)(ow < 0 ? 0 : ow + 2);
             o.p_idx[HW + k] = (int16_t)s.locmap[k];
         }
@@ -919,7 +927,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             const int dr = q / win, dc = q - dr * win;   // win is small; q < ww
             const int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
             const bool inside = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
-            uint8_t cb = 0; int vo = 0, vl = 0;
+            uint32_t cb = 0; int vo = 0, vl = 0;
             if (inside) {
                 const int k = r2 * W + c2;
                 cb = e.cell[k];
@@ -929,12 +937,15 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
                 if (vo == a + 2) vo = 1;
                 if (vl == a + 2) vl = 1;
             }
-            float *dst = o.a_map + (size_t)a * (M + 1) * ww + q;
-#pragma unroll
-            for (int ch = 0; ch < 6; ch++)
-                if (ch < M) dst[ch * ww] = (cb & channel_bit(c, ch)) ? 1.0f : 0.0f;
-            dst[M * ww] = inside ? 1.0f : 0.0f;
-            int16_t *di = o.a_idx + (size_t)a * 2 * ww + q;
+            float *dst = o.a_map + (a * (M + 1) * ww + q);
+            dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += ww;
+            dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += ww;
+            dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += ww;
+            dst[0] = (cb & bit3) ? 1.0f : 0.0f;        dst += ww;
+            dst[0] = (cb & bit4) ? 1.0f : 0.0f;        dst += ww;
+            if (M == 6) { dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; dst += ww; }
+            dst[0] = inside ? 1.0f : 0.0f;
+            int16_t *di = o.a_idx + (a * 2 * ww + q);
             di[0] = (int16_t)vo;
             di[ww] = (int16_t)vl;
             a += da; q += dq;

@@ -132,7 +132,7 @@ def test_auto_reset_restores_snapshot_and_continues_stream():
         ps = st.read_state(e)
         assert int(ps["t"][0]) == 0 and int(ps["completions"][0]) == 1
     for e in range(E):
-        bu.compare_env(fresh, st, e, "after auto-reset")
+        bu.compare_env(fresh, st, e, "after auto-reset", skip=("rew", "done"))  # those belong to the finished episode
     bu.run_pair(env, fresh, 5, rng, check_every=5)  # and the new episode keeps tracking the oracle
 
 
