@@ -27,6 +27,7 @@ struct State {
     size_t step_smem;    // dynamic shared memory per CTA
     int obs_threads;
     size_t obs_smem;
+    uint16_t *tab_dev;   // observation programs (device copy)
 };
 int init(aie_env *);
 void destroy(aie_env *);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(128, 12) aie_observe_kernel(const __grid_const
     o.p_agents = b.p_agents + e * A * c.Fpa;
     o.p_mask = b.p_mask + e * c.Np;
     o.time_obs = b.time_obs + e;
-    observe_env(c, rec, scratch, o, threadIdx.x, blockDim.x);
+    observe_env(c, rec, scratch, o, b.tab, threadIdx.x, blockDim.x);
 }
 
 __global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
@@ -242,11 +243,18 @@ int init(aie_env *env) {
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    {
+        uint16_t tab[TAB_WORDS];
+        fill_tables(c, tab);
+        AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(tab)), "cudaMalloc tables");
+        AIE_CUDA(cudaMemcpy(env->be.tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice), "upload tables");
+        env->bufs.tab = env->be.tab_dev;
+    }
     AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
     return AIE_OK;
 }
-void destroy(aie_env *) {}
+void destroy(aie_env *env) { if (env->be.tab_dev) cudaFree(env->be.tab_dev); }
 
 int upload(aie_env *, void *dst, const void *src, size_t n, void *stream) {
     AIE_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D copy");

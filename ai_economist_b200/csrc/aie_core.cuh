@@ -770,8 +770,8 @@ AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
     s.tax_scalars = (double *)p;  p += 8 * 4;
     s.full_asks = (uint16_t *)p;  p += 2 * 2 * c.P;
     s.full_bids = (uint16_t *)p;  p += 2 * 2 * c.P;
-    s.agent_bits = p;             p += c.A;
-    s.locmap = p;
+    s.agent_bits = p;             p += (c.A + 3) & ~3;
+    s.locmap = p;  // 4-byte aligned, padded to a multiple of 4 bytes
     return s;
 }
 
@@ -822,7 +822,8 @@ struct ObsOut {  // pointers already offset to this env
     float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask; float *time_obs;
 };
 
-AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const ObsOut &o, int tid, int nthr) {
+AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const ObsOut &o, const uint16_t *tab,
+                         int tid, int nthr) {
     const Env e = env_view(rec, c);
     const ObsScratch s = obs_scratch_view(scratch, c);
     const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
@@ -830,7 +831,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     const double time_v = (double)e.hdr[HDR_T] / (c.obs_scaling ? (double)c.T : 1.0);
 
     // ---- phase 1: per-env shared quantities -------------------------------------------------------
-    for (int k = tid; k < HW; k += nthr) s.locmap[k] = 0;
+    for (int k = tid; k < (HW + 3) / 4; k += nthr) ((uint32_t *)s.locmap)[k] = 0u;
     if (c.has[COMP_CDA]) {
         for (int i = tid; i < 2 * P; i += nthr) {  // i = cc * P + p; sums over agents in index order
             int cc = i / P, p = i - cc * P;
@@ -955,15 +956,15 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     // flat vectors (base_env.py:562-612: sorted-key concatenation, float32)
     for (int a = 0; a < A; a++)
         for (int j = tid; j < c.Fa; j += nthr)
-            o.a_flat[a * c.Fa + j] = (float)flat_value(c, e, s, c.prog_a[j], a, time_v, inv_scale);
-    for (int j = tid; j < c.Fp; j += nthr) o.p_flat[j] = (float)flat_value(c, e, s, c.prog_p[j], 0, time_v, inv_scale);
+            o.a_flat[a * c.Fa + j] = (float)flat_value(c, e, s, tab[TAB_PROG_A + j], a, time_v, inv_scale);
+    for (int j = tid; j < c.Fp; j += nthr) o.p_flat[j] = (float)flat_value(c, e, s, tab[TAB_PROG_P + j], 0, time_v, inv_scale);
     for (int a = 0; a < A; a++)
         for (int j = tid; j < c.Fpa; j += nthr)
-            o.p_agents[a * c.Fpa + j] = (float)flat_value(c, e, s, c.prog_pa[j], a, time_v, inv_scale);
+            o.p_agents[a * c.Fpa + j] = (float)flat_value(c, e, s, tab[TAB_PROG_PA + j], a, time_v, inv_scale);
     // masks (base_agent.py:440-460)
     for (int a = 0; a < A; a++)
         for (int j = tid; j < c.Na; j += nthr) {
-            uint16_t en = c.mprog_a[j];
+            uint16_t en = tab[TAB_MPROG_A + j];
             int idx = AIE_PROG_IDX(en), cc = AIE_PROG_C(en);
             bool v;
             switch (AIE_PROG_FIELD(en)) {

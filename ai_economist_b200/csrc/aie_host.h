@@ -190,9 +190,17 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, std::string 
         c.off_mt = take(4 * 624);
         c.rec_bytes = off;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 7 * A + 16);
-        c.obs_scratch_bytes = align16(8 * (2 * P + 2 + 2 * A + 4) + 2 * 4 * P + A + c.HW);
+        c.obs_scratch_bytes = align16(8 * (2 * P + 2 + 2 * A + 4) + 2 * 4 * P + A + 4 + c.HW + 4);
     }
     return AIE_OK;
+}
+
+inline void fill_tables(const DevCfg &c, uint16_t *tab) {
+    memset(tab, 0, TAB_WORDS * sizeof(uint16_t));
+    memcpy(tab + TAB_PROG_A, c.prog_a, sizeof(c.prog_a));
+    memcpy(tab + TAB_PROG_P, c.prog_p, sizeof(c.prog_p));
+    memcpy(tab + TAB_PROG_PA, c.prog_pa, sizeof(c.prog_pa));
+    memcpy(tab + TAB_MPROG_A, c.mprog_a, sizeof(c.mprog_a));
 }
 
 inline void fill_dims(const DevCfg &c, aie_dims &d) {

@@ -91,6 +91,11 @@ struct DevBufs {
     float *a_map; int16_t *a_idx; float *a_flat; float *a_mask;
     float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask;
     float *time_obs; double *rew; int32_t *done;
+    // observation / mask programs in device memory (library-owned, written once at aie_create): indexed by the
+    // thread-varying flat position, which would serialise on the constant bank if read from the kernel params
+    const uint16_t *tab;
 };
+constexpr int TAB_PROG_A = 0, TAB_PROG_P = MAX_FLAT, TAB_PROG_PA = 2 * MAX_FLAT, TAB_MPROG_A = 2 * MAX_FLAT + 16,
+              TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK;
 
 }  // namespace aie

@@ -19,7 +19,7 @@
 
 struct aie_env;
 namespace aie { namespace be {
-struct State { std::vector<uint8_t> scratch; };
+struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; };
 int init(aie_env *);
 void destroy(aie_env *);
 int upload(aie_env *, void *dst, const void *src, size_t n, void *stream);
@@ -38,6 +38,9 @@ int launch_sample(aie_env *, uint64_t seed, void *stream);
 namespace aie { namespace be {
 int init(aie_env *env) {
     env->be.scratch.assign((size_t)env->cfg.step_scratch_bytes + env->cfg.obs_scratch_bytes + 64, 0);
+    env->be.tab.assign(TAB_WORDS, 0);
+    fill_tables(env->cfg, env->be.tab.data());
+    env->bufs.tab = env->be.tab.data();
     return AIE_OK;
 }
 void destroy(aie_env *) {}
@@ -91,7 +94,7 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
         o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
         o.p_flat = b.p_flat + e * c.Fp; o.p_agents = b.p_agents + e * A * c.Fpa;
         o.p_mask = b.p_mask + e * c.Np; o.time_obs = b.time_obs + e;
-        observe_env(c, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, 0, 1);
+        observe_env(c, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0, 1);
     }
     env->launches++;
     return AIE_OK;
