@@ -37,7 +37,7 @@ int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *stream);
 int sync(aie_env *, void *stream);
 int sync_all(aie_env *);
 int launch_finish_reset(aie_env *, int lo, int n, void *stream);
-int launch_step(aie_env *, void *stream);
+int launch_step(aie_env *, int emit_obs, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
 }  // namespace be
@@ -80,13 +80,30 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // shared-memory carve-up of the step / finish-reset kernels: [mbarriers | per-warp (record | scratch)]
 __device__ __forceinline__ uint8_t *warp_region(uint8_t *smem, int wpb, int warp, const DevCfg &c) {
-    return smem + ((8 * wpb + 15) & ~15) + (size_t)warp * (c.rec_bytes + c.step_scratch_bytes);
+    return smem + ((8 * wpb + 15) & ~15) + (size_t)warp * (c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes);
+}
+
+__device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b, int env) {
+    const size_t A = c.A, ww = (size_t)c.win * c.win, e = (size_t)env;
+    ObsOut o;
+    o.a_map = b.a_map + e * A * (c.M + 1) * ww;
+    o.a_idx = b.a_idx + e * A * 2 * ww;
+    o.a_flat = b.a_flat + e * A * c.Fa;
+    o.a_mask = b.a_mask + e * A * c.Na;
+    o.p_map = c.planner_spatial ? b.p_map + e * c.M * c.HW : nullptr;
+    o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
+    o.p_flat = b.p_flat + e * c.Fp;
+    o.p_agents = b.p_agents + e * A * c.Fpa;
+    o.p_mask = b.p_mask + e * c.Np;
+    o.time_obs = b.time_obs + e;
+    return o;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
 template <int MINB>
-__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b) {
+__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
+                                                              const int emit_obs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * wpb + warp;
@@ -132,10 +149,11 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
 
     fence_async_smem();  // generic-proxy writes to the record -> visible to the bulk (async-proxy) store
     __syncwarp();
-    if (lane == 0) {
-        bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
-        bulk_wait_read();
-    }
+    if (lane == 0) bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
+    // observations / masks of the post-step state stream out of the same shared-memory record while the bulk
+    // store drains (both only read the record)
+    if (emit_obs) observe_env(c, rec, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), b.tab, lane);
+    if (lane == 0) bulk_wait_read();
 }
 
 __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
@@ -166,43 +184,33 @@ __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_cons
     }
 }
 
-__global__ void __launch_bounds__(128, 12) aie_observe_kernel(const __grid_constant__ DevCfg c, const DevBufs b, int lo) {
+// Stand-alone observation pass (after a reset upload, or when the caller steps dynamics separately): one warp per
+// env, bulk-loads only the observable prefix of the record.
+__global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant__ DevCfg c, const DevBufs b, int lo, int n) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int env = lo + blockIdx.x;
-    uint64_t *bar = (uint64_t *)smem;
-    uint8_t *rec = smem + 16;
-    uint8_t *scratch = rec + c.obs_prefix_bytes;
-    if (threadIdx.x == 0) {
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * wpb + warp;
+    if (i >= n) return;
+    const int env = lo + i;
+    uint64_t *bar = (uint64_t *)smem + warp;
+    uint8_t *rec = warp_region(smem, wpb, warp, c);
+    if (lane == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, (uint32_t)c.obs_prefix_bytes);
         bulk_g2s(rec, b.state + (size_t)env * c.rec_bytes, (uint32_t)c.obs_prefix_bytes, bar);
     }
-    __syncthreads();
+    __syncwarp();
     mbar_wait(bar, 0);
-    const size_t A = c.A, ww = (size_t)c.win * c.win, e = (size_t)env;
-    ObsOut o;
-    o.a_map = b.a_map + e * A * (c.M + 1) * ww;
-    o.a_idx = b.a_idx + e * A * 2 * ww;
-    o.a_flat = b.a_flat + e * A * c.Fa;
-    o.a_mask = b.a_mask + e * A * c.Na;
-    o.p_map = c.planner_spatial ? b.p_map + e * c.M * c.HW : nullptr;
-    o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
-    o.p_flat = b.p_flat + e * c.Fp;
-    o.p_agents = b.p_agents + e * A * c.Fpa;
-    o.p_mask = b.p_mask + e * c.Np;
-    o.time_obs = b.time_obs + e;
-    observe_env(c, rec, scratch, o, b.tab, threadIdx.x, blockDim.x);
+    observe_env(c, rec, rec + c.rec_bytes + c.step_scratch_bytes, obs_out_for(c, b, env), b.tab, lane);
 }
 
-__global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
-                                                         uint64_t seed, int items_per_env) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)c.n_envs * items_per_env) return;
-    const int env = (int)(gid / items_per_env), w = (int)(gid - (long long)env * items_per_env);
-    sample_actions_item(c, b.a_mask + (size_t)env * c.A * c.Na, b.p_mask + (size_t)env * c.Np,
-                        const_cast<int32_t *>(b.act_a) + (size_t)env * c.A * c.n_act_a,
-                        c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)env * c.n_act_p : nullptr, w,
-                        mix64(seed ^ mix64((uint64_t)gid)));
+__global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed) {
+    const int env = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (env >= c.n_envs) return;
+    sample_actions_env(c, b.a_mask + (size_t)env * c.A * c.Na, b.p_mask + (size_t)env * c.Np,
+                       const_cast<int32_t *>(b.act_a) + (size_t)env * c.A * c.n_act_a,
+                       c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)env * c.n_act_p : nullptr,
+                       mix64(seed ^ mix64((uint64_t)env)), lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -226,15 +234,14 @@ int init(aie_env *env) {
     if (prop.major < 10) return fail(AIE_ECUDA, "this build targets sm_100a (Blackwell B200) only");
     const DevCfg &c = env->cfg;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
-    const size_t per_env = (size_t)c.rec_bytes + c.step_scratch_bytes;
+    const size_t per_env = (size_t)c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes;
     int wpb = 8;
     while (wpb > 1 && align16(8 * wpb) + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
     if (align16(8 * wpb) + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
     env->be.step_wpb = wpb;
     env->be.step_smem = align16(8 * wpb) + wpb * per_env;
-    env->be.obs_threads = 128;
-    env->be.obs_smem = 16 + (size_t)c.obs_prefix_bytes + c.obs_scratch_bytes;
-    if (env->be.obs_smem > max_smem) return fail(AIE_EINVAL, "observation staging does not fit in shared memory");
+    env->be.obs_threads = wpb * 32;
+    env->be.obs_smem = env->be.step_smem;
     // pick the variant with the most resident warps that shared memory allows (override: AIE_STEP_MINB=3|4|5)
     const size_t smem_sm = prop.sharedMemPerMultiprocessor;
     int fit = (int)(smem_sm / (env->be.step_smem + 1024));
@@ -283,19 +290,20 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
     env->launches++;
     return AIE_OK;
 }
-int launch_step(aie_env *env, void *stream) {
+int launch_step(aie_env *env, int emit_obs, void *stream) {
     const int wpb = env->be.step_wpb;
     const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;
-    if (env->be.step_minb == 5) aie_step_kernel<5><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs);
-    else if (env->be.step_minb == 4) aie_step_kernel<4><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs);
-    else aie_step_kernel<3><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs);
+    if (env->be.step_minb == 5) aie_step_kernel<5><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs, emit_obs);
+    else if (env->be.step_minb == 4) aie_step_kernel<4><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs, emit_obs);
+    else aie_step_kernel<3><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs, emit_obs);
     AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
     env->launches++;
     return AIE_OK;
 }
 int launch_observe(aie_env *env, int lo, int n, void *stream) {
-    aie_observe_kernel<<<n, env->be.obs_threads, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo);
+    const int wpb = env->be.step_wpb;
+    aie_observe_kernel<<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
     AIE_CUDA(cudaGetLastError(), "aie_observe_kernel launch");
     env->launches++;
     return AIE_OK;
@@ -303,10 +311,9 @@ int launch_observe(aie_env *env, int lo, int n, void *stream) {
 
 int launch_sample(aie_env *env, uint64_t seed, void *stream) {
     const DevCfg &c = env->cfg;
-    const int items = c.A * (c.multi_action ? c.n_sub : 1) + (c.planner_acts ? c.B : 0);
-    const long long total = (long long)env->n_envs * items;
-    aie_sample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        env->cfg, env->bufs, host_mix64(seed) ^ host_mix64(++env->sample_calls), items);
+    (void)c;
+    aie_sample_kernel<<<(env->n_envs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        env->cfg, env->bufs, host_mix64(seed) ^ host_mix64(++env->sample_calls));
     AIE_CUDA(cudaGetLastError(), "aie_sample_kernel launch");
     env->launches++;
     return AIE_OK;

@@ -7,7 +7,7 @@
 //   int dev_copy(aie_env*, void *dst, const void *src, size_t n, void *stream);
 //   int sync(aie_env*, void *stream);   int sync_all(aie_env*);
 //   int launch_finish_reset(aie_env*, int lo, int n, void *stream);
-//   int launch_step(aie_env*, void *stream);
+//   int launch_step(aie_env*, int emit_obs, void *stream);
 //   int launch_observe(aie_env*, int lo, int n, void *stream);
 //   int launch_sample(aie_env*, uint64_t seed, void *stream);
 #include <string>
@@ -122,15 +122,13 @@ int aie_load_state(aie_env *env, const aie_host_state *hs, int32_t env_lo, void 
 int aie_step(aie_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step: bind buffers and load state first");
-    int rc = aie::be::launch_step(env, stream);
-    if (rc != AIE_OK) return rc;
-    return aie::be::launch_observe(env, 0, env->n_envs, stream);
+    return aie::be::launch_step(env, 1, stream);  // dynamics + observations fused in one launch
 }
 
 int aie_step_dynamics(aie_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_dynamics: bind buffers and load state first");
-    return aie::be::launch_step(env, stream);
+    return aie::be::launch_step(env, 0, stream);
 }
 
 int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream) {

@@ -53,6 +53,7 @@ AIE_DEV double wsum(double v) {
     return v;
 }
 AIE_DEV int first_lane(uint32_t m) { return __ffs(m) - 1; }
+AIE_DEV int __popc_u32(uint32_t m) { return __popc(m); }
 #else
 constexpr int NL = 1;
 AIE_DEV void wsync() {}
@@ -62,6 +63,7 @@ AIE_DEV uint32_t wshfl(uint32_t v, int) { return v; }
 AIE_DEV bool wany(bool p) { return p; }
 AIE_DEV double wsum(double v) { return v; }
 AIE_DEV int first_lane(uint32_t m) { return m ? 0 : -1; }
+AIE_DEV int __popc_u32(uint32_t m) { return __builtin_popcount(m); }
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -743,13 +745,9 @@ AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Observations + masks.  Block-collective on the device (tid / nthr over one CTA), serial in emulation.
+// Observations + masks.  Warp-collective like the step body (one warp streams out its env's tensors straight
+// from the shared-memory record), serial in emulation.
 // ------------------------------------------------------------------------------------------------
-#if AIE_ON_DEVICE
-AIE_DEV void bsync() { __syncthreads(); }
-#else
-AIE_DEV void bsync() {}
-#endif
 
 struct ObsScratch {
     double *net_hist;     // [2][P]
@@ -823,7 +821,8 @@ struct ObsOut {  // pointers already offset to this env
 };
 
 AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const ObsOut &o, const uint16_t *tab,
-                         int tid, int nthr) {
+                         int lane) {
+    const int tid = lane, nthr = NL;
     const Env e = env_view(rec, c);
     const ObsScratch s = obs_scratch_view(scratch, c);
     const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
@@ -865,7 +864,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             s.sorted_inc[rank] = v;
         }
     }
-    bsync();
+    wsync();
     for (int a = tid; a < A; a += nthr) {
         const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
         s.locmap[row * W + col] = (uint8_t)(a + 2);
@@ -876,7 +875,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             for (int p = 0; p < P; p++) { dot += p * s.net_hist[cc * P + p]; tot += s.net_hist[cc * P + p]; }
             s.market_rate[cc] = dot / fmax(0.001, tot);
         }
-    bsync();
+    wsync();
     for (int a = tid; a < A; a += nthr) {  // build mask + Gather mask bits (build.py:180-193, move.py:167-188)
         uint8_t bits = can_build(c, e, a) ? 1 : 0;
         const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
@@ -893,7 +892,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
         }
         s.agent_bits[a] = bits;
     }
-    bsync();
+    wsync();
 
     // ---- phase 2: outputs ----------------------------------------------------------------------
     // Loops are arranged so that consecutive threads write consecutive addresses and no index needs a
@@ -1002,32 +1001,52 @@ AIE_DEV uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
     x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
     return x ^ (x >> 31);
 }
-AIE_DEV int sample_segment(const float *mask, int n, uint64_t key) {
-    int pick = 0, count = 0;
-    for (int j = 0; j < n; j++) {
-        if (mask[j] != 0.0f) {
-            count++;
-            key = mix64(key);
-            if ((uint32_t)(key >> 32) % (uint32_t)count == 0) pick = j;  // reservoir sampling
+// Uniform choice among the set entries of mask[0..n) by one warp: ballots count the open entries, a hashed
+// rank picks one, and the lane holding it is found with popcounts.  Returns the same value on every lane.
+AIE_DEV int sample_segment_warp(const float *mask, int n, uint64_t key, int lane) {
+    int total = 0;
+    for (int base = 0; base < n; base += NL) {
+        const int j = base + lane;
+        total += __popc_u32(wballot(j < n && mask[j] != 0.0f));
+    }
+    if (total == 0) return 0;
+    int r = (int)((uint32_t)(mix64(key) >> 32) % (uint32_t)total);
+    for (int base = 0; base < n; base += NL) {
+        const int j = base + lane;
+        const uint32_t m = wballot(j < n && mask[j] != 0.0f);
+        const int cnt = __popc_u32(m);
+        if (r < cnt) {
+            uint32_t mm = m;
+            for (int i = 0; i < r; i++) mm &= mm - 1;  // drop the r lowest set bits
+            return base + first_lane(mm);
+        }
+        r -= cnt;
+    }
+    return 0;
+}
+
+// One env: every agent (and planner bracket) draws one uniformly random unmasked action per subspace.
+AIE_DEV void sample_actions_env(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
+                                int32_t *act_p, uint64_t key, int lane) {
+    for (int a = 0; a < c.A; a++) {
+        const float *m = a_mask + (size_t)a * c.Na;
+        if (!c.multi_action) {
+            const int v = sample_segment_warp(m, c.Na, key + 0x100 * a, lane);
+            if (lane == 0) act_a[a] = v;
+        } else {
+            int off = 0;
+            for (int si = 0; si < c.n_sub; si++) {
+                const int v = sample_segment_warp(m + off, c.sub_n[si] + 1, key + 0x100 * a + si + 1, lane);
+                if (lane == 0) act_a[a * c.n_sub + si] = v;
+                off += c.sub_n[si] + 1;
+            }
         }
     }
-    return pick;
-}
-// work item w in [0, A * n_seg_a + n_seg_p) of one env
-AIE_DEV void sample_actions_item(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
-                                 int32_t *act_p, int w, uint64_t key) {
-    const int n_seg_a = c.multi_action ? c.n_sub : 1;
-    if (w < c.A * n_seg_a) {
-        const int a = w / n_seg_a, si = w - a * n_seg_a;
-        const float *m = a_mask + (size_t)a * c.Na;
-        if (!c.multi_action) { act_a[a] = sample_segment(m, c.Na, key); return; }
-        int off = 0;
-        for (int j = 0; j < si; j++) off += c.sub_n[j] + 1;
-        act_a[a * c.n_sub + si] = sample_segment(m + off, c.sub_n[si] + 1, key);
-    } else if (c.planner_acts) {
-        const int b = w - c.A * n_seg_a;
-        act_p[b] = sample_segment(p_mask + (size_t)b * (1 + c.R), 1 + c.R, key);
-    }
+    if (c.planner_acts)
+        for (int b = 0; b < c.B; b++) {
+            const int v = sample_segment_warp(p_mask + (size_t)b * (1 + c.R), 1 + c.R, key + 0x10000 + b, lane);
+            if (lane == 0) act_p[b] = v;
+        }
 }
 
 }  // namespace aie

@@ -221,7 +221,7 @@ def main():
 
     def one_step(i):
         st.sample_random_actions(seed=1234 + rank)
-        st.step()  # dynamics + observe
+        st.step()  # fused dynamics + observations
 
     def barrier():
         torch.cuda.synchronize()
@@ -253,14 +253,22 @@ def main():
 
     # ---- per-kernel durations (separate pass, CUDA events between the kernels, same stream) ----
     n_prof = min(args.steps, 50)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_prof)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
     for i in range(n_prof):
         evs[i][0].record(); st.sample_random_actions(seed=99)
-        evs[i][1].record(); st.step_dynamics()
-        evs[i][2].record(); st.observe()
-        evs[i][3].record()
+        evs[i][1].record(); st.step()
+        evs[i][2].record()
     torch.cuda.synchronize()
-    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(3)]
+    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(2)]
+    # the two halves of the fused step kernel, launched separately (informational)
+    ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(10)]
+    for i in range(10):
+        st.sample_random_actions(seed=98)
+        ev2[i][0].record(); st.step_dynamics()
+        ev2[i][1].record(); st.observe()
+        ev2[i][2].record()
+    torch.cuda.synchronize()
+    half_ms = [float(np.mean([ev2[i][j].elapsed_time(ev2[i][j + 1]) for i in range(10)])) for j in range(2)]
     peak, peak_src = peaks()
     ww = d.window * d.window
     obs_bytes = (A * ((d.n_map_channels + 1) * ww * 4 + 2 * ww * 2 + d.flat_agent * 4 + d.mask_agent * 4)
@@ -268,10 +276,10 @@ def main():
                  + (d.n_map_channels * d.height * d.width * 4 + 2 * d.height * d.width * 2
                     if env.spec["planner_gets_spatial_info"] else 0))
     step_bytes = 2 * d.state_bytes + 4 * (A * d.n_act_agent + d.n_act_planner) + 8 * (A + 1) + 4
-    obs_prefix = st.field("orders").offset  # bytes of the record the observe kernel reads
     kernels = {
-        "aie_observe_kernel": {"ms": k_ms[2], "alg_bytes_per_launch": E * (obs_bytes + obs_prefix)},
-        "aie_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * step_bytes},
+        "aie_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * (step_bytes + obs_bytes),
+                            "what": "fused: TMA record in -> dynamics -> rewards -> observations/masks out -> record out",
+                            "unfused_ms": {"dynamics_only": half_ms[0], "observe_only": half_ms[1]}},
         "aie_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (A * d.mask_agent * 4 + A * d.n_act_agent * 4)},
     }
     for k in kernels.values():

@@ -28,7 +28,7 @@ int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *stream);
 int sync(aie_env *, void *stream);
 int sync_all(aie_env *);
 int launch_finish_reset(aie_env *, int lo, int n, void *stream);
-int launch_step(aie_env *, void *stream);
+int launch_step(aie_env *, int emit_obs, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
 } }
@@ -60,7 +60,8 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *) {
     env->launches++;
     return AIE_OK;
 }
-int launch_step(aie_env *env, void *) {
+int launch_observe(aie_env *env, int lo, int n, void *);
+int launch_step(aie_env *env, int emit_obs, void *) {
     const DevCfg &c = env->cfg;
     const DevBufs &b = env->bufs;
     for (int e = 0; e < env->n_envs; e++) {
@@ -79,6 +80,7 @@ int launch_step(aie_env *env, void *) {
         }
     }
     env->launches++;
+    if (emit_obs) { launch_observe(env, 0, env->n_envs, nullptr); env->launches--; }
     return AIE_OK;
 }
 int launch_observe(aie_env *env, int lo, int n, void *) {
@@ -94,7 +96,7 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
         o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
         o.p_flat = b.p_flat + e * c.Fp; o.p_agents = b.p_agents + e * A * c.Fpa;
         o.p_mask = b.p_mask + e * c.Np; o.time_obs = b.time_obs + e;
-        observe_env(c, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0, 1);
+        observe_env(c, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
     }
     env->launches++;
     return AIE_OK;
@@ -102,15 +104,12 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
 int launch_sample(aie_env *env, uint64_t seed, void *) {
     const DevCfg &c = env->cfg;
     const DevBufs &b = env->bufs;
-    const int items = c.A * (c.multi_action ? c.n_sub : 1) + (c.planner_acts ? c.B : 0);
-    const uint64_t s = mix64(seed) ^ mix64(++env->sample_calls);
-    for (long long gid = 0; gid < (long long)env->n_envs * items; gid++) {
-        int e = (int)(gid / items), w = (int)(gid - (long long)e * items);
-        sample_actions_item(c, b.a_mask + (size_t)e * c.A * c.Na, b.p_mask + (size_t)e * c.Np,
-                            const_cast<int32_t *>(b.act_a) + (size_t)e * c.A * c.n_act_a,
-                            c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)e * c.n_act_p : nullptr, w,
-                            mix64(s ^ mix64((uint64_t)gid)));
-    }
+    const uint64_t s = host_mix64(seed) ^ host_mix64(++env->sample_calls);
+    for (int e = 0; e < env->n_envs; e++)
+        sample_actions_env(c, b.a_mask + (size_t)e * c.A * c.Na, b.p_mask + (size_t)e * c.Np,
+                           const_cast<int32_t *>(b.act_a) + (size_t)e * c.A * c.n_act_a,
+                           c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)e * c.n_act_p : nullptr,
+                           mix64(s ^ mix64((uint64_t)e)), 0);
     env->launches++;
     return AIE_OK;
 }

@@ -12,7 +12,5 @@ import json
 d = json.load(open("gpurun_out/bench_quick.json"))
 print("value %.3e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v["ms"]*1e3,1) for k, v in d["roofline"]["kernels"].items()})
 PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_observe_kernel -s 8 -c 1 -f -o gpurun_out/prof_observe \
-    python bench.py --steps 6 --warmup 5 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_observe.log 2>&1; echo "ncu observe rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step_kernel -s 8 -c 1 -f -o gpurun_out/prof_step \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step_kernel -s 12 -c 1 -f -o gpurun_out/prof_step \
     python bench.py --steps 6 --warmup 5 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_step.log 2>&1; echo "ncu step rc=$?"
