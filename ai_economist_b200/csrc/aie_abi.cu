@@ -251,10 +251,8 @@ int init(aie_env *env) {
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     {
-        uint16_t tab[TAB_WORDS];
-        fill_tables(c, tab);
-        AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(tab)), "cudaMalloc tables");
-        AIE_CUDA(cudaMemcpy(env->be.tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice), "upload tables");
+        AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(Tables)), "cudaMalloc tables");
+        AIE_CUDA(cudaMemcpy(env->be.tab_dev, env->tables.w, sizeof(Tables), cudaMemcpyHostToDevice), "upload tables");
         env->bufs.tab = env->be.tab_dev;
     }
     AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");

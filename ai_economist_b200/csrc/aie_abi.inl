@@ -17,6 +17,7 @@ static thread_local std::string g_last_error;
 
 struct aie_env {
     aie::DevCfg cfg;
+    aie::Tables tables;
     aie_config ucfg;
     int n_envs, device;
     aie::DevBufs bufs;
@@ -38,7 +39,7 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     aie_env *env = new (std::nothrow) aie_env();
     if (!env) return fail(AIE_ENOMEM, "out of host memory");
     std::string err;
-    int rc = aie::build_devcfg(*cfg, n_envs, env->cfg, err);
+    int rc = aie::build_devcfg(*cfg, n_envs, env->cfg, env->tables, err);
     if (rc != AIE_OK) { delete env; return fail(rc, "aie_create: " + err); }
     env->ucfg = *cfg; env->n_envs = n_envs; env->device = device;
     memset(&env->bufs, 0, sizeof(env->bufs));

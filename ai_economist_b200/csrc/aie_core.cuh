@@ -750,69 +750,23 @@ AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, i
 // ------------------------------------------------------------------------------------------------
 
 struct ObsScratch {
-    double *net_hist;     // [2][P]
-    double *market_rate;  // [2]
-    double *marg;         // [A]   marginal rate at current income
-    double *sorted_inc;   // [A]   last incomes / period, ascending
-    double *tax_scalars;  // [4]   is_tax_day, is_first_day, tax_phase, annealed limit
+    double *net_hist;     // [2][P] summed price history (fp64, for the market rate); [2P] = annealed tax limit
+    float *shf;           // [sh_count] shared float staging (SH_*): scalars + price history + rates + incomes
+    float *sc_a;          // [A][AS_COUNT] per-agent scalar observations
     uint16_t *full_asks, *full_bids;  // [2][P]
+    uint8_t *lim;         // [A][MS_COUNT] mask limits: mask[j] = idx_j < lim[slot_j]
     uint8_t *locmap;      // [HW]  0 none, a+2
-    uint8_t *agent_bits;  // [A]   bit0 can_build, bits1-4 gather L,R,U,D
 };
 AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
     ObsScratch s;
-    s.net_hist = (double *)p;     p += 8 * 2 * c.P;
-    s.market_rate = (double *)p;  p += 8 * 2;
-    s.marg = (double *)p;         p += 8 * c.A;
-    s.sorted_inc = (double *)p;   p += 8 * c.A;
-    s.tax_scalars = (double *)p;  p += 8 * 4;
+    s.net_hist = (double *)p;     p += 8 * (2 * c.P + 2);
+    s.shf = (float *)p;           p += 4 * c.sh_count;
+    s.sc_a = (float *)p;          p += 4 * c.A * AS_COUNT;
     s.full_asks = (uint16_t *)p;  p += 2 * 2 * c.P;
     s.full_bids = (uint16_t *)p;  p += 2 * 2 * c.P;
-    s.agent_bits = p;             p += (c.A + 3) & ~3;
+    s.lim = p;                    p += (c.A * MS_COUNT + 7) & ~7;
     s.locmap = p;  // 4-byte aligned, padded to a multiple of 4 bytes
     return s;
-}
-
-AIE_DEV double flat_value(const DevCfg &c, const Env &e, const ObsScratch &s, uint16_t entry, int a, double time_v,
-                          double inv_scale) {
-    const int idx = AIE_PROG_IDX(entry), cc = AIE_PROG_C(entry), A = c.A, P = c.P;
-    switch (AIE_PROG_FIELD(entry)) {
-        case F_BUILD_PAYMENT: return e.bpay[a] / c.build_payment;
-        case F_BUILD_SKILL: return e.bskill[a];
-        case F_AVAIL_ASKS: return (double)((int)s.full_asks[cc * P + idx] - (int)e.ask_hist[(cc * A + a) * P + idx]);
-        case F_AVAIL_BIDS: return (double)((int)s.full_bids[cc * P + idx] - (int)e.bid_hist[(cc * A + a) * P + idx]);
-        case F_MARKET_RATE: return s.market_rate[cc];
-        case F_MY_ASKS: return (double)e.ask_hist[(cc * A + a) * P + idx];
-        case F_MY_BIDS: return (double)e.bid_hist[(cc * A + a) * P + idx];
-        case F_PRICE_HIST: return s.net_hist[cc * P + idx] * inv_scale;
-        case F_BONUS: return e.bonus[a];
-        case F_TAX_CURR_RATES: return tax_rate(c, e, idx);
-        case F_TAX_IS_FIRST: return s.tax_scalars[1];
-        case F_TAX_IS_TAX_DAY: return s.tax_scalars[0];
-        case F_TAX_LAST_INCOMES: return s.sorted_inc[idx];
-        case F_TAX_MARG: return s.marg[a];
-        case F_TAX_PHASE: return s.tax_scalars[2];
-        case F_TIME: return time_v;
-        case F_INV_COIN: return e.coin[a] * inv_scale;
-        case F_INV_STONE: return e.inv[2 * a] * inv_scale;
-        case F_INV_WOOD: return e.inv[2 * a + 1] * inv_scale;
-        case F_LOC_COL: return (double)e.loc[2 * a + 1] / c.W;
-        case F_LOC_ROW: return (double)e.loc[2 * a] / c.H;
-        case F_FULL_ASKS: return (double)s.full_asks[cc * P + idx];
-        case F_FULL_BIDS: return (double)s.full_bids[cc * P + idx];
-        case F_TAX_LAST_INCOME: return e.last_income[a] / c.period;
-        case F_TAX_LAST_MARG: return e.last_marg[a];
-        default: return 0.0;
-    }
-}
-
-// map channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSourceBlock, WoodSourceBlock)
-AIE_DEV uint8_t channel_bit(const DevCfg &c, int ch) {
-    if (ch == 0) return CELL_STONE;
-    if (ch == 1) return CELL_WOOD;
-    if (ch == 2) return CELL_HOUSE;
-    if (c.has_water) { if (ch == 3) return CELL_WATER; ch -= 1; }
-    return ch == 3 ? CELL_STONE_SRC : CELL_WOOD_SRC;
 }
 
 struct ObsOut {  // pointers already offset to this env
@@ -820,19 +774,31 @@ struct ObsOut {  // pointers already offset to this env
     float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask; float *time_obs;
 };
 
+// One element of a "flat" vector (warp-divergence is bounded by the 5 kinds, all of them a few instructions)
+AIE_DEV float flat_emit(const DevCfg &c, const Env &e, const ObsScratch &s, uint32_t entry, int a) {
+    const uint32_t pl = AIE_FLAT_PAYLOAD(entry);
+    const int kind = AIE_FLAT_KIND(entry);
+    if (kind == FK_SHARED) return s.shf[pl];
+    if (kind == FK_AGENT) return s.sc_a[a * AS_COUNT + pl];
+    const int side = (pl >> 6) & 1, cc = (pl >> 5) & 1, idx = pl & 31;
+    const uint16_t *full = side ? s.full_asks : s.full_bids;
+    const uint8_t *mine = side ? e.ask_hist : e.bid_hist;
+    const int f = full[cc * c.P + idx], m = mine[(cc * c.A + a) * c.P + idx];
+    return (float)(kind == FK_FULL ? f : (kind == FK_MY ? m : f - m));
+}
+
 AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const ObsOut &o, const uint16_t *tab,
                          int lane) {
-    const int tid = lane, nthr = NL;
     const Env e = env_view(rec, c);
     const ObsScratch s = obs_scratch_view(scratch, c);
     const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
     const double inv_scale = c.obs_scaling ? 0.01 : 1.0;
     const double time_v = (double)e.hdr[HDR_T] / (c.obs_scaling ? (double)c.T : 1.0);
 
-    // ---- phase 1: per-env shared quantities -------------------------------------------------------
-    for (int k = tid; k < (HW + 3) / 4; k += nthr) ((uint32_t *)s.locmap)[k] = 0u;
-    if (c.has[COMP_CDA]) {
-        for (int i = tid; i < 2 * P; i += nthr) {  // i = cc * P + p; sums over agents in index order
+    // ---- phase 1: stage every scalar the flat vectors / masks need (float, final values) -------------
+    for (int k = lane; k < (HW + 3) / 4; k += NL) ((uint32_t *)s.locmap)[k] = 0u;
+    if (c.has[COMP_CDA]) {  // continuous_double_auction.py:491-542
+        for (int i = lane; i < 2 * P; i += NL) {  // i = cc * P + p; sums over agents in index order
             int cc = i / P, p = i - cc * P;
             double acc = 0.0; int fa = 0, fb = 0;
             for (int a = 0; a < A; a++) {
@@ -841,43 +807,59 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
                 fb += e.bid_hist[(cc * A + a) * P + p];
             }
             s.net_hist[i] = acc; s.full_asks[i] = (uint16_t)fa; s.full_bids[i] = (uint16_t)fb;
+            s.shf[SH_PRICE_HIST + i] = (float)(acc * inv_scale);
         }
     }
-    if (c.has[COMP_TAX]) {
-        int pos = e.hdr[HDR_TAX_POS];
-        if (tid == 0) {
-            s.tax_scalars[0] = pos >= c.period ? 1.0 : 0.0;
-            s.tax_scalars[1] = pos == 1 ? 1.0 : 0.0;
-            s.tax_scalars[2] = (double)pos / c.period;
+    if (c.has[COMP_TAX]) {  // redistribution.py:974-1023
+        const int pos = e.hdr[HDR_TAX_POS];
+        if (lane == 0) {
+            s.shf[SH_TAX_IS_TAX_DAY] = pos >= c.period ? 1.0f : 0.0f;
+            s.shf[SH_TAX_IS_FIRST] = pos == 1 ? 1.0f : 0.0f;
+            s.shf[SH_TAX_PHASE] = (float)((double)pos / c.period);
             // components/utils.py:10-57: current annealed |rate| limit for the planner mask
             double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)e.hdr[HDR_COMPLETIONS] - c.ann_warm)));
-            s.tax_scalars[3] = vis * c.ann_full;
+            s.net_hist[2 * P] = vis * c.ann_full;
         }
-        for (int a = tid; a < A; a += nthr) {
-            s.marg[a] = tax_marginal_rate(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
-            double v = e.last_income[a] / c.period;  // ascending rank -> sorted position (:908-911)
+        for (int b = lane; b < c.B; b += NL) s.shf[c.sh_curr_rates + b] = (float)tax_rate(c, e, b);
+        for (int a = lane; a < A; a += NL) {
+            s.sc_a[a * AS_COUNT + AS_TAX_MARG] = (float)tax_marginal_rate(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
+            const double v = e.last_income[a] / c.period;  // ascending rank -> sorted position (:908-911)
             int rank = 0;
             for (int j = 0; j < A; j++) {
                 double vj = e.last_income[j] / c.period;
                 rank += (vj < v || (vj == v && j < a)) ? 1 : 0;
             }
-            s.sorted_inc[rank] = v;
+            s.shf[c.sh_last_incomes + rank] = (float)v;
+            s.sc_a[a * AS_COUNT + AS_TAX_LAST_INCOME] = (float)v;
+            s.sc_a[a * AS_COUNT + AS_TAX_LAST_MARG] = (float)e.last_marg[a];
         }
     }
+    if (lane == 0) { s.shf[SH_ZERO] = 0.0f; s.shf[SH_TIME] = (float)time_v; o.time_obs[0] = (float)time_v; }
     wsync();
-    for (int a = tid; a < A; a += nthr) {
+    for (int a = lane; a < A; a += NL) {
         const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
         s.locmap[row * W + col] = (uint8_t)(a + 2);
+        float *sc = s.sc_a + a * AS_COUNT;
+        sc[AS_LOC_ROW] = (float)((double)row / H);
+        sc[AS_LOC_COL] = (float)((double)col / W);
+        sc[AS_INV_COIN] = (float)(e.coin[a] * inv_scale);
+        sc[AS_INV_STONE] = (float)(e.inv[2 * a] * inv_scale);
+        sc[AS_INV_WOOD] = (float)(e.inv[2 * a + 1] * inv_scale);
+        sc[AS_BUILD_PAYMENT] = (float)(e.bpay[a] / c.build_payment);
+        sc[AS_BUILD_SKILL] = (float)e.bskill[a];
+        sc[AS_BONUS] = (float)e.bonus[a];
     }
     if (c.has[COMP_CDA])
-        for (int cc = tid; cc < 2; cc += nthr) {  // market_rate (:504-513)
+        for (int cc = lane; cc < 2; cc += NL) {  // market_rate (:504-513)
             double dot = 0.0, tot = 0.0;
             for (int p = 0; p < P; p++) { dot += p * s.net_hist[cc * P + p]; tot += s.net_hist[cc * P + p]; }
-            s.market_rate[cc] = dot / fmax(0.001, tot);
+            s.shf[SH_MARKET_RATE + cc] = (float)(dot / fmax(0.001, tot));
         }
     wsync();
-    for (int a = tid; a < A; a += nthr) {  // build mask + Gather mask bits (build.py:180-193, move.py:167-188)
-        uint8_t bits = can_build(c, e, a) ? 1 : 0;
+    for (int a = lane; a < A; a += NL) {  // mask limits (build.py:180-193, move.py:167-188, cda :544-580)
+        uint8_t *lim = s.lim + a * MS_COUNT;
+        lim[MS_ONE] = 1;
+        lim[MS_BUILD] = can_build(c, e, a) ? 1 : 0;
         const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
         const int roff[4] = {0, 0, -1, 1}, coff[4] = {-1, 1, 0, 0};
         for (int d = 0; d < 4; d++) {
@@ -888,23 +870,29 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
                 int8_t ow = e.owner[k];
                 ok = s.locmap[k] == 0 && !(e.cell[k] & CELL_WATER) && (ow < 0 || ow == a);
             }
-            if (ok) bits |= (uint8_t)(2u << d);
+            lim[MS_G0 + d] = ok ? 1 : 0;
         }
-        s.agent_bits[a] = bits;
+        if (c.has[COMP_CDA]) {
+            // Buy_c[p] = (n_orders < K) and (p <= Coin)  <=>  p < min(P, floor(Coin) + 1)
+            const double coin = e.coin[a];
+            const int can_pay = coin >= (double)P ? P : (int)floor(coin) + 1;
+            for (int cc = 0; cc < 2; cc++) {
+                const bool open = e.n_orders[cc * A + a] < c.K;
+                lim[MS_BUY0 + cc] = (uint8_t)(open ? can_pay : 0);
+                lim[MS_SELL0 + cc] = (uint8_t)((open && e.inv[2 * a + cc] > 0) ? P : 0);
+            }
+        }
     }
     wsync();
 
     // ---- phase 2: outputs ----------------------------------------------------------------------
-    // Loops are arranged so that consecutive threads write consecutive addresses and no index needs a
-    // division by a run-time constant inside the streaming loops.
-    if (tid == 0) o.time_obs[0] = (float)time_v;
-    // channel -> cell bit, hoisted (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc)
+    // Consecutive lanes write consecutive addresses; no division by a run-time constant in the loops.
+    // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc)
     const uint32_t bit3 = c.has_water ? CELL_WATER : CELL_STONE_SRC;
     const uint32_t bit4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
     if (c.planner_spatial) {
-        // one thread per map cell: the cell byte is read once and fans out to all M channels (consecutive
-        // threads -> consecutive addresses in every channel plane) plus both index planes
-        for (int k = tid; k < HW; k += nthr) {
+        // one lane per map cell: the cell byte is read once and fans out to all M channel planes + 2 index planes
+        for (int k = lane; k < HW; k += NL) {
             const uint32_t cb = e.cell[k];
             float *dst = o.p_map + k;
             dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += HW;
@@ -918,26 +906,26 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             o.p_idx[HW + k] = (int16_t)s.locmap[k];
         }
     }
-    // agent windows (layout_from_file.py:468-515): one work item per (agent, window cell); the item reads its
-    // cell once and emits all M+1 map channels and both index channels.
-    {
-        int a = tid / ww, q = tid - a * ww;          // one division per thread, then incremental
-        const int da = nthr / ww, dq = nthr - da * ww;
-        for (int i = tid; i < A * ww; i += nthr) {
-            const int dr = q / win, dc = q - dr * win;   // win is small; q < ww
-            const int r2 = e.loc[2 * a] + dr - w, c2 = e.loc[2 * a + 1] + dc - w;
-            const bool inside = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
+    // agent windows (layout_from_file.py:468-515): per agent, one lane per window cell; (dr, dc) come from a
+    // table, the cell is read once and fans out to the M+1 map channels and the 2 index channels
+    for (int a = 0; a < A; a++) {
+        const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;
+        float *amap = o.a_map + a * (M + 1) * ww;
+        int16_t *aidx = o.a_idx + a * 2 * ww;
+        for (int q = lane; q < ww; q += NL) {
+            const uint32_t rc = tab[TAB_Q + q];
+            const int r2 = r0 + (int)(rc >> 8), c2 = c0 + (int)(rc & 255u);
+            const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
             uint32_t cb = 0; int vo = 0, vl = 0;
             if (inside) {
                 const int k = r2 * W + c2;
                 cb = e.cell[k];
                 const int ow = e.owner[k];
-                vo = ow < 0 ? 0 : ow + 2;
+                vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
                 vl = s.locmap[k];
-                if (vo == a + 2) vo = 1;
                 if (vl == a + 2) vl = 1;
             }
-            float *dst = o.a_map + (a * (M + 1) * ww + q);
+            float *dst = amap + q;
             dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += ww;
             dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += ww;
             dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += ww;
@@ -945,52 +933,33 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             dst[0] = (cb & bit4) ? 1.0f : 0.0f;        dst += ww;
             if (M == 6) { dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; dst += ww; }
             dst[0] = inside ? 1.0f : 0.0f;
-            int16_t *di = o.a_idx + (a * 2 * ww + q);
-            di[0] = (int16_t)vo;
-            di[ww] = (int16_t)vl;
-            a += da; q += dq;
-            if (q >= ww) { q -= ww; a += 1; }
+            aidx[q] = (int16_t)vo;
+            aidx[ww + q] = (int16_t)vl;
         }
     }
-    // flat vectors (base_env.py:562-612: sorted-key concatenation, float32)
-    for (int a = 0; a < A; a++)
-        for (int j = tid; j < c.Fa; j += nthr)
-            o.a_flat[a * c.Fa + j] = (float)flat_value(c, e, s, tab[TAB_PROG_A + j], a, time_v, inv_scale);
-    for (int j = tid; j < c.Fp; j += nthr) o.p_flat[j] = (float)flat_value(c, e, s, tab[TAB_PROG_P + j], 0, time_v, inv_scale);
-    for (int a = 0; a < A; a++)
-        for (int j = tid; j < c.Fpa; j += nthr)
-            o.p_agents[a * c.Fpa + j] = (float)flat_value(c, e, s, tab[TAB_PROG_PA + j], a, time_v, inv_scale);
-    // masks (base_agent.py:440-460)
-    for (int a = 0; a < A; a++)
-        for (int j = tid; j < c.Na; j += nthr) {
-            uint16_t en = tab[TAB_MPROG_A + j];
-            int idx = AIE_PROG_IDX(en), cc = AIE_PROG_C(en);
-            bool v;
-            switch (AIE_PROG_FIELD(en)) {
-                case MK_BUILD: v = s.agent_bits[a] & 1; break;
-                case MK_BUY: v = e.n_orders[cc * A + a] < c.K && (double)idx <= e.coin[a]; break;
-                case MK_SELL: v = e.n_orders[cc * A + a] < c.K && e.inv[2 * a + cc] > 0; break;
-                case MK_GATHER: v = (s.agent_bits[a] >> (1 + idx)) & 1; break;
-                default: v = true;
-            }
-            o.a_mask[a * c.Na + j] = v ? 1.0f : 0.0f;
+    // flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
+    for (int a = 0; a < A; a++) {
+        for (int j = lane; j < c.Fa; j += NL) o.a_flat[a * c.Fa + j] = flat_emit(c, e, s, tab[TAB_PROG_A + j], a);
+        for (int j = lane; j < c.Fpa; j += NL) o.p_agents[a * c.Fpa + j] = flat_emit(c, e, s, tab[TAB_PROG_PA + j], a);
+        const uint8_t *lim = s.lim + a * MS_COUNT;
+        for (int j = lane; j < c.Na; j += NL) {
+            const uint32_t en = tab[TAB_MPROG_A + j];
+            o.a_mask[a * c.Na + j] = ((en & 255u) < lim[en >> 8]) ? 1.0f : 0.0f;
         }
+    }
+    for (int j = lane; j < c.Fp; j += NL) o.p_flat[j] = flat_emit(c, e, s, tab[TAB_PROG_P + j], 0);
     if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
-        for (int j = tid; j < c.Np; j += nthr) {
-            int rr = j % (1 + c.R);
-            float v = 1.0f;
-            if (rr != 0) {
-                bool open = e.hdr[HDR_TAX_POS] == 1;
-                if (open && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.tax_scalars[3];
-                v = open ? 1.0f : 0.0f;
+        const bool first_day = e.hdr[HDR_TAX_POS] == 1;
+        for (int b = 0; b < c.B; b++)
+            for (int rr = lane; rr <= c.R; rr += NL) {
+                bool open = rr == 0 || first_day;
+                if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.net_hist[2 * P];
+                o.p_mask[b * (1 + c.R) + rr] = open ? 1.0f : 0.0f;
             }
-            o.p_mask[j] = v;
-        }
-    } else if (tid == 0) {
+    } else if (lane == 0) {
         o.p_mask[0] = 1.0f;
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Random policy (bench / testing utility): uniform over the unmasked entries of one mask segment.

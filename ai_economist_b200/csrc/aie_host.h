@@ -23,7 +23,7 @@ inline uint64_t host_mix64(uint64_t x) {  // splitmix64 finaliser (same function
     return x ^ (x >> 31);
 }
 
-struct FlatKey { std::string key; int field, c, n; };
+struct FlatKey { std::string key; int kind, payload, n; };  // payload of element i = payload + i
 
 // Mirrors BaseEnvironment._build_packager / _package (base_env.py:562-612): every scalar / 1-D field is
 // concatenated in sorted key order.  Keys are the reference's: "<Component>-<obs>" / "world-<obs>" / "time".
@@ -33,14 +33,15 @@ inline int build_prog(std::vector<FlatKey> keys, uint16_t *prog, int cap) {
     for (const FlatKey &k : keys)
         for (int i = 0; i < k.n; i++) {
             if (n >= cap) return -1;
-            prog[n++] = AIE_PROG_ENTRY(k.field, k.c, i);
+            prog[n++] = AIE_FLAT_ENTRY(k.kind, k.payload + i);
         }
     return n;
 }
 
 // Returns 0 or AIE_EINVAL with a message in err.
-inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, std::string &err) {
+inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, std::string &err) {
     memset(&c, 0, sizeof(c));
+    memset(&tb, 0, sizeof(tb));
     auto bad = [&](const char *m) { err = m; return AIE_EINVAL; };
     if (u.abi_version != AIE_ABI_VERSION) return bad("abi_version mismatch");
     if (n_envs < 1) return bad("n_envs must be >= 1");
@@ -117,59 +118,70 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, std::string 
     c.Np = c.planner_acts ? c.B * (1 + c.R) : 1;
     if (c.Na > MAX_MASK) return bad("agent action mask too long");
 
+    c.sh_curr_rates = SH_PRICE_HIST + 2 * c.P;
+    c.sh_last_incomes = c.sh_curr_rates + 16;
+    c.sh_count = c.sh_last_incomes + c.A;
     // mask program (base_agent.py:440-460)
     {
+        uint16_t *mp = tb.w + TAB_MPROG_A;
         int n = 0;
-        if (!c.multi_action) c.mprog_a[n++] = AIE_PROG_ENTRY(MK_ONE, 0, 0);
+        if (!c.multi_action) mp[n++] = AIE_MASK_ENTRY(MS_ONE, 0);
         for (int si = 0; si < c.n_sub; si++) {
-            if (c.multi_action) c.mprog_a[n++] = AIE_PROG_ENTRY(MK_ONE, 0, 0);
+            if (c.multi_action) mp[n++] = AIE_MASK_ENTRY(MS_ONE, 0);
             for (int j = 0; j < c.sub_n[si]; j++) {
-                int kind = c.sub_kind[si] == SUB_BUILD ? MK_BUILD : c.sub_kind[si] == SUB_BUY ? MK_BUY
-                           : c.sub_kind[si] == SUB_SELL ? MK_SELL : MK_GATHER;
-                c.mprog_a[n++] = AIE_PROG_ENTRY(kind, c.sub_c[si], j);
+                if (c.sub_kind[si] == SUB_BUILD) mp[n++] = AIE_MASK_ENTRY(MS_BUILD, 0);
+                else if (c.sub_kind[si] == SUB_BUY) mp[n++] = AIE_MASK_ENTRY(MS_BUY0 + c.sub_c[si], j);
+                else if (c.sub_kind[si] == SUB_SELL) mp[n++] = AIE_MASK_ENTRY(MS_SELL0 + c.sub_c[si], j);
+                else mp[n++] = AIE_MASK_ENTRY(MS_G0 + j, 0);
             }
         }
     }
-    // flat programs
+    // flat programs: every scalar / 1-D observation field, concatenated in sorted key order
     {
         static const char *CN[2] = {"Stone", "Wood"};
         std::vector<FlatKey> ka, kp, kpa;
-        auto K = [](const std::string &k, int f, int cc, int n) { return FlatKey{k, f, cc, n}; };
-        ka.push_back(K("world-loc-row", F_LOC_ROW, 0, 1)); ka.push_back(K("world-loc-col", F_LOC_COL, 0, 1));
-        ka.push_back(K("world-inventory-Coin", F_INV_COIN, 0, 1)); ka.push_back(K("world-inventory-Stone", F_INV_STONE, 0, 1));
-        ka.push_back(K("world-inventory-Wood", F_INV_WOOD, 0, 1)); ka.push_back(K("time", F_TIME, 0, 1));
-        kp.push_back(K("world-inventory-Coin", F_ZERO, 0, 1)); kp.push_back(K("world-inventory-Stone", F_ZERO, 0, 1));
-        kp.push_back(K("world-inventory-Wood", F_ZERO, 0, 1)); kp.push_back(K("time", F_TIME, 0, 1));
-        kpa.push_back(K("world-inventory-Coin", F_INV_COIN, 0, 1)); kpa.push_back(K("world-inventory-Stone", F_INV_STONE, 0, 1));
-        kpa.push_back(K("world-inventory-Wood", F_INV_WOOD, 0, 1));
-        if (c.planner_spatial) { kpa.push_back(K("world-loc-row", F_LOC_ROW, 0, 1)); kpa.push_back(K("world-loc-col", F_LOC_COL, 0, 1)); }
-        if (c.has[COMP_BUILD]) { ka.push_back(K("Build-build_payment", F_BUILD_PAYMENT, 0, 1)); ka.push_back(K("Build-build_skill", F_BUILD_SKILL, 0, 1)); }
-        if (c.has[COMP_GATHER]) ka.push_back(K("Gather-bonus_gather_prob", F_BONUS, 0, 1));
+        auto K = [](const std::string &k, int kind, int payload, int n) { return FlatKey{k, kind, payload, n}; };
+        ka.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); ka.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1));
+        ka.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); ka.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
+        ka.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1)); ka.push_back(K("time", FK_SHARED, SH_TIME, 1));
+        kp.push_back(K("world-inventory-Coin", FK_SHARED, SH_ZERO, 1)); kp.push_back(K("world-inventory-Stone", FK_SHARED, SH_ZERO, 1));
+        kp.push_back(K("world-inventory-Wood", FK_SHARED, SH_ZERO, 1)); kp.push_back(K("time", FK_SHARED, SH_TIME, 1));
+        kpa.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); kpa.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
+        kpa.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1));
+        if (c.planner_spatial) { kpa.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); kpa.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1)); }
+        if (c.has[COMP_BUILD]) { ka.push_back(K("Build-build_payment", FK_AGENT, AS_BUILD_PAYMENT, 1)); ka.push_back(K("Build-build_skill", FK_AGENT, AS_BUILD_SKILL, 1)); }
+        if (c.has[COMP_GATHER]) ka.push_back(K("Gather-bonus_gather_prob", FK_AGENT, AS_BONUS, 1));
         if (c.has[COMP_CDA])
             for (int cc = 0; cc < 2; cc++) {
                 std::string s = std::string("ContinuousDoubleAuction-"), r = std::string("-") + CN[cc];
-                ka.push_back(K(s + "market_rate" + r, F_MARKET_RATE, cc, 1)); ka.push_back(K(s + "price_history" + r, F_PRICE_HIST, cc, c.P));
-                ka.push_back(K(s + "available_asks" + r, F_AVAIL_ASKS, cc, c.P)); ka.push_back(K(s + "available_bids" + r, F_AVAIL_BIDS, cc, c.P));
-                ka.push_back(K(s + "my_asks" + r, F_MY_ASKS, cc, c.P)); ka.push_back(K(s + "my_bids" + r, F_MY_BIDS, cc, c.P));
-                kp.push_back(K(s + "market_rate" + r, F_MARKET_RATE, cc, 1)); kp.push_back(K(s + "price_history" + r, F_PRICE_HIST, cc, c.P));
-                kp.push_back(K(s + "full_asks" + r, F_FULL_ASKS, cc, c.P)); kp.push_back(K(s + "full_bids" + r, F_FULL_BIDS, cc, c.P));
+                ka.push_back(K(s + "market_rate" + r, FK_SHARED, SH_MARKET_RATE + cc, 1));
+                ka.push_back(K(s + "price_history" + r, FK_SHARED, SH_PRICE_HIST + cc * c.P, c.P));
+                ka.push_back(K(s + "available_asks" + r, FK_AVAIL, AIE_HIST_PAYLOAD(1, cc, 0), c.P));
+                ka.push_back(K(s + "available_bids" + r, FK_AVAIL, AIE_HIST_PAYLOAD(0, cc, 0), c.P));
+                ka.push_back(K(s + "my_asks" + r, FK_MY, AIE_HIST_PAYLOAD(1, cc, 0), c.P));
+                ka.push_back(K(s + "my_bids" + r, FK_MY, AIE_HIST_PAYLOAD(0, cc, 0), c.P));
+                kp.push_back(K(s + "market_rate" + r, FK_SHARED, SH_MARKET_RATE + cc, 1));
+                kp.push_back(K(s + "price_history" + r, FK_SHARED, SH_PRICE_HIST + cc * c.P, c.P));
+                kp.push_back(K(s + "full_asks" + r, FK_FULL, AIE_HIST_PAYLOAD(1, cc, 0), c.P));
+                kp.push_back(K(s + "full_bids" + r, FK_FULL, AIE_HIST_PAYLOAD(0, cc, 0), c.P));
             }
         if (c.has[COMP_TAX]) {
             std::string s = "PeriodicBracketTax-";
             for (std::vector<FlatKey> *v : {&ka, &kp}) {
-                v->push_back(K(s + "is_tax_day", F_TAX_IS_TAX_DAY, 0, 1)); v->push_back(K(s + "is_first_day", F_TAX_IS_FIRST, 0, 1));
-                v->push_back(K(s + "tax_phase", F_TAX_PHASE, 0, 1)); v->push_back(K(s + "last_incomes", F_TAX_LAST_INCOMES, 0, c.A));
-                v->push_back(K(s + "curr_rates", F_TAX_CURR_RATES, 0, c.B));
+                v->push_back(K(s + "is_tax_day", FK_SHARED, SH_TAX_IS_TAX_DAY, 1)); v->push_back(K(s + "is_first_day", FK_SHARED, SH_TAX_IS_FIRST, 1));
+                v->push_back(K(s + "tax_phase", FK_SHARED, SH_TAX_PHASE, 1)); v->push_back(K(s + "last_incomes", FK_SHARED, c.sh_last_incomes, c.A));
+                v->push_back(K(s + "curr_rates", FK_SHARED, c.sh_curr_rates, c.B));
             }
-            ka.push_back(K(s + "marginal_rate", F_TAX_MARG, 0, 1));
-            kpa.push_back(K(s + "last_income", F_TAX_LAST_INCOME, 0, 1)); kpa.push_back(K(s + "last_marginal_rate", F_TAX_LAST_MARG, 0, 1));
-            kpa.push_back(K(s + "curr_marginal_rate", F_TAX_MARG, 0, 1));
+            ka.push_back(K(s + "marginal_rate", FK_AGENT, AS_TAX_MARG, 1));
+            kpa.push_back(K(s + "last_income", FK_AGENT, AS_TAX_LAST_INCOME, 1)); kpa.push_back(K(s + "last_marginal_rate", FK_AGENT, AS_TAX_LAST_MARG, 1));
+            kpa.push_back(K(s + "curr_marginal_rate", FK_AGENT, AS_TAX_MARG, 1));
         }
-        c.Fa = build_prog(ka, c.prog_a, MAX_FLAT);
-        c.Fp = build_prog(kp, c.prog_p, MAX_FLAT);
-        c.Fpa = build_prog(kpa, c.prog_pa, 16);
+        c.Fa = build_prog(ka, tb.w + TAB_PROG_A, MAX_FLAT);
+        c.Fp = build_prog(kp, tb.w + TAB_PROG_P, MAX_FLAT);
+        c.Fpa = build_prog(kpa, tb.w + TAB_PROG_PA, 16);
         if (c.Fa < 0 || c.Fp < 0 || c.Fpa < 0) return bad("flat observation too long");
     }
+    for (int q = 0; q < c.win * c.win; q++) tb.w[TAB_Q + q] = (uint16_t)(((q / c.win) << 8) | (q % c.win));
     // record layout
     {
         const int A = c.A, P = c.P;
@@ -190,17 +202,9 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, std::string 
         c.off_mt = take(4 * 624);
         c.rec_bytes = off;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 7 * A + 16);
-        c.obs_scratch_bytes = align16(8 * (2 * P + 2 + 2 * A + 4) + 2 * 4 * P + A + 4 + c.HW + 4);
+        c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT) + 2 * 4 * P + A * MS_COUNT + 8 + c.HW + 4);
     }
     return AIE_OK;
-}
-
-inline void fill_tables(const DevCfg &c, uint16_t *tab) {
-    memset(tab, 0, TAB_WORDS * sizeof(uint16_t));
-    memcpy(tab + TAB_PROG_A, c.prog_a, sizeof(c.prog_a));
-    memcpy(tab + TAB_PROG_P, c.prog_p, sizeof(c.prog_p));
-    memcpy(tab + TAB_PROG_PA, c.prog_pa, sizeof(c.prog_pa));
-    memcpy(tab + TAB_MPROG_A, c.mprog_a, sizeof(c.mprog_a));
 }
 
 inline void fill_dims(const DevCfg &c, aie_dims &d) {

@@ -29,20 +29,24 @@ enum { HDR_T = 0, HDR_TAX_POS = 1, HDR_COMPLETIONS = 2, HDR_AUTO_WARMUP = 3, HDR
 enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3 };
 enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
 
-// "flat" observation fields
-enum {
-    F_ZERO = 0, F_BUILD_PAYMENT, F_BUILD_SKILL, F_AVAIL_ASKS, F_AVAIL_BIDS, F_MARKET_RATE, F_MY_ASKS, F_MY_BIDS,
-    F_PRICE_HIST, F_BONUS, F_TAX_CURR_RATES, F_TAX_IS_FIRST, F_TAX_IS_TAX_DAY, F_TAX_LAST_INCOMES, F_TAX_MARG,
-    F_TAX_PHASE, F_TIME, F_INV_COIN, F_INV_STONE, F_INV_WOOD, F_LOC_COL, F_LOC_ROW, F_FULL_ASKS, F_FULL_BIDS,
-    F_TAX_LAST_INCOME, F_TAX_LAST_MARG
-};
-// mask program kinds
-enum { MK_ONE = 0, MK_BUILD, MK_BUY, MK_SELL, MK_GATHER };
+// Observation "programs" (built once on the host from the reference's sorted-key flattening, base_env.py:562-612).
+// flat entry  = kind << 13 | payload:
+//   FK_SHARED  payload = index into the per-env shared float staging array (SH_*)
+//   FK_AGENT   payload = per-agent scalar slot (AS_*)
+//   FK_MY / FK_AVAIL / FK_FULL  payload = side << 6 | commodity << 5 | price level   (side 0 bids, 1 asks)
+// mask entry  = slot << 8 | idx; the mask value is (idx < limit[agent][slot])
+enum { FK_SHARED = 0, FK_AGENT = 1, FK_MY = 2, FK_AVAIL = 3, FK_FULL = 4 };
+enum { AS_LOC_ROW = 0, AS_LOC_COL, AS_INV_COIN, AS_INV_STONE, AS_INV_WOOD, AS_BUILD_PAYMENT, AS_BUILD_SKILL, AS_BONUS,
+       AS_TAX_MARG, AS_TAX_LAST_INCOME, AS_TAX_LAST_MARG, AS_COUNT = 12 };
+enum { SH_ZERO = 0, SH_TIME = 1, SH_MARKET_RATE = 2, SH_TAX_IS_TAX_DAY = 4, SH_TAX_IS_FIRST = 5, SH_TAX_PHASE = 6,
+       SH_PRICE_HIST = 8 /* [2][P], then curr_rates [16], then sorted last incomes [A] */ };
+enum { MS_ONE = 0, MS_BUILD, MS_BUY0, MS_BUY1, MS_SELL0, MS_SELL1, MS_G0, MS_G1, MS_G2, MS_G3, MS_COUNT = 12 };
 
-#define AIE_PROG_ENTRY(field, c, idx) ((uint16_t)(((field) << 8) | ((c) << 7) | (idx)))
-#define AIE_PROG_FIELD(e) ((e) >> 8)
-#define AIE_PROG_C(e) (((e) >> 7) & 1)
-#define AIE_PROG_IDX(e) ((e) & 127)
+#define AIE_FLAT_ENTRY(kind, payload) ((uint16_t)(((kind) << 13) | (payload)))
+#define AIE_FLAT_KIND(e) ((e) >> 13)
+#define AIE_FLAT_PAYLOAD(e) ((e) & 0x1FFF)
+#define AIE_HIST_PAYLOAD(side, c, idx) (((side) << 6) | ((c) << 5) | (idx))
+#define AIE_MASK_ENTRY(slot, idx) ((uint16_t)(((slot) << 8) | (idx)))
 
 constexpr int MAX_FLAT = 448;
 constexpr int MAX_MASK = 160;
@@ -79,9 +83,7 @@ struct DevCfg {
     // step-kernel scratch (per env, shared memory) and observe-kernel scratch
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;
-    // observation programs
-    uint16_t prog_a[MAX_FLAT], prog_p[MAX_FLAT], prog_pa[16];
-    uint16_t mprog_a[MAX_MASK];
+    int32_t sh_curr_rates, sh_last_incomes, sh_count;  // offsets / size of the shared float staging array
 };
 
 // raw device pointers (mirrors aie_buffers)
@@ -95,7 +97,10 @@ struct DevBufs {
     // thread-varying flat position, which would serialise on the constant bank if read from the kernel params
     const uint16_t *tab;
 };
+constexpr int MAX_WW = 65 * 65;
 constexpr int TAB_PROG_A = 0, TAB_PROG_P = MAX_FLAT, TAB_PROG_PA = 2 * MAX_FLAT, TAB_MPROG_A = 2 * MAX_FLAT + 16,
-              TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK;
+              TAB_Q = 2 * MAX_FLAT + 16 + MAX_MASK,   // window cell q -> (dr << 8 | dc)
+              TAB_WORDS = TAB_Q + MAX_WW + 3;
+struct Tables { uint16_t w[TAB_WORDS]; };
 
 }  // namespace aie

@@ -38,9 +38,7 @@ int launch_sample(aie_env *, uint64_t seed, void *stream);
 namespace aie { namespace be {
 int init(aie_env *env) {
     env->be.scratch.assign((size_t)env->cfg.step_scratch_bytes + env->cfg.obs_scratch_bytes + 64, 0);
-    env->be.tab.assign(TAB_WORDS, 0);
-    fill_tables(env->cfg, env->be.tab.data());
-    env->bufs.tab = env->be.tab.data();
+    env->bufs.tab = env->tables.w;
     return AIE_OK;
 }
 void destroy(aie_env *) {}
