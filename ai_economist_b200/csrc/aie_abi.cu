@@ -78,9 +78,20 @@ __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, u
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// shared-memory carve-up of the step / finish-reset kernels: [mbarriers | per-warp (record | scratch)]
+// shared-memory carve-up: [mbarriers | block-shared observation programs | per-warp (record | scratch | obs scratch)]
+__device__ __forceinline__ int tab_smem_bytes(const DevCfg &c) { return (2 * c.tab_n + 15) & ~15; }
 __device__ __forceinline__ uint8_t *warp_region(uint8_t *smem, int wpb, int warp, const DevCfg &c) {
-    return smem + ((8 * wpb + 15) & ~15) + (size_t)warp * (c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes);
+    return smem + ((8 * wpb + 15) & ~15) + tab_smem_bytes(c) +
+           (size_t)warp * (c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes);
+}
+// The programs are indexed by the lane-varying flat position; reading them from global memory costs an L2 round
+// trip per access here because the L1 carve-out is almost entirely shared memory.  One cooperative copy per CTA.
+__device__ __forceinline__ const uint16_t *stage_tables(uint8_t *smem, int wpb, const DevCfg &c, const DevBufs &b) {
+    uint32_t *dst = (uint32_t *)(smem + ((8 * wpb + 15) & ~15));
+    const uint32_t *src = (const uint32_t *)b.tab;
+    for (int i = threadIdx.x; i < c.tab_n / 2; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return (const uint16_t *)dst;
 }
 
 __device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b, int env) {
@@ -107,7 +118,8 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * wpb + warp;
-    if (env >= c.n_envs) return;  // warps are independent: no block-wide barrier below
+    const uint16_t *tab = stage_tables(smem, wpb, c, b);
+    if (env >= c.n_envs) return;  // from here on warps are independent: no block-wide barrier below
     uint64_t *bar = (uint64_t *)smem + warp;
     uint8_t *rec = warp_region(smem, wpb, warp, c);
     uint8_t *scratch = rec + c.rec_bytes;
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     if (lane == 0) bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
     // observations / masks of the post-step state stream out of the same shared-memory record while the bulk
     // store drains (both only read the record)
-    if (emit_obs) observe_env(c, rec, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), b.tab, lane);
+    if (emit_obs) observe_env(c, rec, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
     if (lane == 0) bulk_wait_read();
 }
 
@@ -190,6 +202,7 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * wpb + warp;
+    const uint16_t *tab = stage_tables(smem, wpb, c, b);
     if (i >= n) return;
     const int env = lo + i;
     uint64_t *bar = (uint64_t *)smem + warp;
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    observe_env(c, rec, rec + c.rec_bytes + c.step_scratch_bytes, obs_out_for(c, b, env), b.tab, lane);
+    observe_env(c, rec, rec + c.rec_bytes + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
 }
 
 __global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed) {
@@ -236,10 +249,11 @@ int init(aie_env *env) {
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_env = (size_t)c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes;
     int wpb = 8;
-    while (wpb > 1 && align16(8 * wpb) + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
-    if (align16(8 * wpb) + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
+    const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;
+    while (wpb > 1 && align16(8 * wpb) + tabs + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
+    if (align16(8 * wpb) + tabs + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
     env->be.step_wpb = wpb;
-    env->be.step_smem = align16(8 * wpb) + wpb * per_env;
+    env->be.step_smem = align16(8 * wpb) + tabs + wpb * per_env;
     env->be.obs_threads = wpb * 32;
     env->be.obs_smem = env->be.step_smem;
     // pick the variant with the most resident warps that shared memory allows (override: AIE_STEP_MINB=3|4|5)

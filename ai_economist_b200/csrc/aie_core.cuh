@@ -906,48 +906,55 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             o.p_idx[HW + k] = (int16_t)s.locmap[k];
         }
     }
-    // agent windows (layout_from_file.py:468-515): per agent, one lane per window cell; (dr, dc) come from a
-    // table, the cell is read once and fans out to the M+1 map channels and the 2 index channels
-    for (int a = 0; a < A; a++) {
-        const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;
-        float *amap = o.a_map + a * (M + 1) * ww;
-        int16_t *aidx = o.a_idx + a * 2 * ww;
-        for (int q = lane; q < ww; q += NL) {
-            const uint32_t rc = tab[TAB_Q + q];
-            const int r2 = r0 + (int)(rc >> 8), c2 = c0 + (int)(rc & 255u);
-            const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
-            uint32_t cb = 0; int vo = 0, vl = 0;
-            if (inside) {
-                const int k = r2 * W + c2;
-                cb = e.cell[k];
-                const int ow = e.owner[k];
-                vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
-                vl = s.locmap[k];
-                if (vl == a + 2) vl = 1;
+    // agent windows (layout_from_file.py:468-515): per agent, one lane per window cell; the cell is read once
+    // and fans out to the M+1 map channels and the 2 index channels
+    {
+        // lane's first window cell and the (dr, dc) step for q += NL: one small division per warp per step
+        const int dr_first = lane / win, dc_first = lane - dr_first * win;
+        const int dr_step = NL / win, dc_step = NL - dr_step * win;
+        for (int a = 0; a < A; a++) {
+            const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;
+            float *amap = o.a_map + a * (M + 1) * ww;
+            int16_t *aidx = o.a_idx + a * 2 * ww;
+            int dr = dr_first, dc = dc_first;
+            for (int q = lane; q < ww; q += NL) {
+                const int r2 = r0 + dr, c2 = c0 + dc;
+                const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
+                uint32_t cb = 0; int vo = 0, vl = 0;
+                if (inside) {
+                    const int k = r2 * W + c2;
+                    cb = e.cell[k];
+                    const int ow = e.owner[k];
+                    vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
+                    vl = s.locmap[k];
+                    if (vl == a + 2) vl = 1;
+                }
+                float *dst = amap + q;
+                dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += ww;
+                dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += ww;
+                dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += ww;
+                dst[0] = (cb & bit3) ? 1.0f : 0.0f;        dst += ww;
+                dst[0] = (cb & bit4) ? 1.0f : 0.0f;        dst += ww;
+                if (M == 6) { dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; dst += ww; }
+                dst[0] = inside ? 1.0f : 0.0f;
+                aidx[q] = (int16_t)vo;
+                aidx[ww + q] = (int16_t)vl;
+                dr += dr_step; dc += dc_step;
+                if (dc >= win) { dc -= win; dr += 1; }
             }
-            float *dst = amap + q;
-            dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += ww;
-            dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += ww;
-            dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += ww;
-            dst[0] = (cb & bit3) ? 1.0f : 0.0f;        dst += ww;
-            dst[0] = (cb & bit4) ? 1.0f : 0.0f;        dst += ww;
-            if (M == 6) { dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; dst += ww; }
-            dst[0] = inside ? 1.0f : 0.0f;
-            aidx[q] = (int16_t)vo;
-            aidx[ww + q] = (int16_t)vl;
         }
     }
     // flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
     for (int a = 0; a < A; a++) {
-        for (int j = lane; j < c.Fa; j += NL) o.a_flat[a * c.Fa + j] = flat_emit(c, e, s, tab[TAB_PROG_A + j], a);
-        for (int j = lane; j < c.Fpa; j += NL) o.p_agents[a * c.Fpa + j] = flat_emit(c, e, s, tab[TAB_PROG_PA + j], a);
+        for (int j = lane; j < c.Fa; j += NL) o.a_flat[a * c.Fa + j] = flat_emit(c, e, s, tab[j], a);
+        for (int j = lane; j < c.Fpa; j += NL) o.p_agents[a * c.Fpa + j] = flat_emit(c, e, s, tab[c.tab_pa + j], a);
         const uint8_t *lim = s.lim + a * MS_COUNT;
         for (int j = lane; j < c.Na; j += NL) {
-            const uint32_t en = tab[TAB_MPROG_A + j];
+            const uint32_t en = tab[c.tab_m + j];
             o.a_mask[a * c.Na + j] = ((en & 255u) < lim[en >> 8]) ? 1.0f : 0.0f;
         }
     }
-    for (int j = lane; j < c.Fp; j += NL) o.p_flat[j] = flat_emit(c, e, s, tab[TAB_PROG_P + j], 0);
+    for (int j = lane; j < c.Fp; j += NL) o.p_flat[j] = flat_emit(c, e, s, tab[c.tab_p + j], 0);
     if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
         const bool first_day = e.hdr[HDR_TAX_POS] == 1;
         for (int b = 0; b < c.B; b++)

@@ -121,9 +121,10 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.sh_curr_rates = SH_PRICE_HIST + 2 * c.P;
     c.sh_last_incomes = c.sh_curr_rates + 16;
     c.sh_count = c.sh_last_incomes + c.A;
+    uint16_t mask_prog[MAX_MASK], prog_a[MAX_FLAT], prog_p[MAX_FLAT], prog_pa[16];
     // mask program (base_agent.py:440-460)
     {
-        uint16_t *mp = tb.w + TAB_MPROG_A;
+        uint16_t *mp = mask_prog;
         int n = 0;
         if (!c.multi_action) mp[n++] = AIE_MASK_ENTRY(MS_ONE, 0);
         for (int si = 0; si < c.n_sub; si++) {
@@ -176,12 +177,14 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             kpa.push_back(K(s + "last_income", FK_AGENT, AS_TAX_LAST_INCOME, 1)); kpa.push_back(K(s + "last_marginal_rate", FK_AGENT, AS_TAX_LAST_MARG, 1));
             kpa.push_back(K(s + "curr_marginal_rate", FK_AGENT, AS_TAX_MARG, 1));
         }
-        c.Fa = build_prog(ka, tb.w + TAB_PROG_A, MAX_FLAT);
-        c.Fp = build_prog(kp, tb.w + TAB_PROG_P, MAX_FLAT);
-        c.Fpa = build_prog(kpa, tb.w + TAB_PROG_PA, 16);
+        c.Fa = build_prog(ka, prog_a, MAX_FLAT);
+        c.Fp = build_prog(kp, prog_p, MAX_FLAT);
+        c.Fpa = build_prog(kpa, prog_pa, 16);
         if (c.Fa < 0 || c.Fp < 0 || c.Fpa < 0) return bad("flat observation too long");
     }
-    for (int q = 0; q < c.win * c.win; q++) tb.w[TAB_Q + q] = (uint16_t)(((q / c.win) << 8) | (q % c.win));
+    c.tab_p = c.Fa; c.tab_pa = c.tab_p + c.Fp; c.tab_m = c.tab_pa + c.Fpa; c.tab_n = (c.tab_m + c.Na + 1) & ~1;
+    memcpy(tb.w, prog_a, 2 * c.Fa); memcpy(tb.w + c.tab_p, prog_p, 2 * c.Fp);
+    memcpy(tb.w + c.tab_pa, prog_pa, 2 * c.Fpa); memcpy(tb.w + c.tab_m, mask_prog, 2 * c.Na);
     // record layout
     {
         const int A = c.A, P = c.P;

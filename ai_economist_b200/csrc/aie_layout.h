@@ -84,6 +84,7 @@ struct DevCfg {
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;
     int32_t sh_curr_rates, sh_last_incomes, sh_count;  // offsets / size of the shared float staging array
+    int32_t tab_p, tab_pa, tab_m, tab_n;               // offsets (u16 words) into the program table, total words (even)
 };
 
 // raw device pointers (mirrors aie_buffers)
@@ -97,10 +98,8 @@ struct DevBufs {
     // thread-varying flat position, which would serialise on the constant bank if read from the kernel params
     const uint16_t *tab;
 };
-constexpr int MAX_WW = 65 * 65;
-constexpr int TAB_PROG_A = 0, TAB_PROG_P = MAX_FLAT, TAB_PROG_PA = 2 * MAX_FLAT, TAB_MPROG_A = 2 * MAX_FLAT + 16,
-              TAB_Q = 2 * MAX_FLAT + 16 + MAX_MASK,   // window cell q -> (dr << 8 | dc)
-              TAB_WORDS = TAB_Q + MAX_WW + 3;
+// compact program table: [agent flat (Fa) | planner flat (Fp) | p<i> flat (Fpa) | agent mask (Na)], offsets in DevCfg
+constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK;
 struct Tables { uint16_t w[TAB_WORDS]; };
 
 }  // namespace aie
