@@ -88,7 +88,7 @@ class AieError(RuntimeError):
 
 def load_library(path=None):
     """Open the C-ABI shared library and declare every prototype in include/aie_b200.h."""
-    path = path or DEFAULT_LIB
+    path = path or os.environ.get("AIE_LIB_PATH") or DEFAULT_LIB  # AIE_LIB_PATH: alternative CUDA build (tuning)
     if not os.path.exists(path):
         raise AieError(
             "CUDA extension %s not found. Build it first: `python -c \"import __graft_entry__ as g; g.build()\"` "

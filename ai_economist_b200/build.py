@@ -10,11 +10,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-Xcompiler", "-fPIC"]
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
     newest = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+    if not force and out is None and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    target = out or LIB
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return target

@@ -249,6 +249,7 @@ int init(aie_env *env) {
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_env = (size_t)c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes;
     int wpb = 8;
+    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4 || v == 8) wpb = v; }
     const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;
     while (wpb > 1 && align16(8 * wpb) + tabs + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
     if (align16(8 * wpb) + tabs + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");

@@ -38,6 +38,15 @@
 #define AIE_ON_DEVICE 0
 #endif
 
+#ifndef AIE_OBS_UNROLL
+#define AIE_OBS_UNROLL 1
+#endif
+#ifndef AIE_TWIST_UNROLL
+#define AIE_TWIST_UNROLL 8
+#endif
+#define AIE_PRAGMA_(x) _Pragma(#x)
+#define AIE_UNROLL(n) AIE_PRAGMA_(unroll n)
+
 namespace aie {
 
 #if AIE_ON_DEVICE
@@ -145,7 +154,9 @@ template <int BASE, int N, int MOFF>
 AIE_DEV void mt_twist_phase(uint32_t *mt, int lane) {
     constexpr int PER = (N + NL - 1) / NL;
     uint32_t v[PER];
-#pragma unroll
+#if AIE_ON_DEVICE
+    AIE_UNROLL(AIE_TWIST_UNROLL)
+#endif
     for (int j = 0; j < PER; j++) {
         int k = BASE + lane + j * NL;
         if (k < BASE + N) {
@@ -154,7 +165,9 @@ AIE_DEV void mt_twist_phase(uint32_t *mt, int lane) {
         }
     }
     wsync();
-#pragma unroll
+#if AIE_ON_DEVICE
+    AIE_UNROLL(AIE_TWIST_UNROLL)
+#endif
     for (int j = 0; j < PER; j++) {
         int k = BASE + lane + j * NL;
         if (k < BASE + N) mt[k] = v[j];
@@ -164,7 +177,9 @@ AIE_DEV void mt_twist_phase(uint32_t *mt, int lane) {
 
 // Warp-collective regeneration of the 624-word key.  Dependencies: new[0,227) <- old; new[227,454) <-
 // new[0,227); new[454,623) <- new[227,396); new[623] <- new[396], new[0].
-AIE_DEV void mt_twist(uint32_t *mt, int lane) {
+// Not inlined: rng_next() is called from a dozen places and each inlined copy of the twist is ~700 instructions;
+// a single copy keeps the kernel inside the instruction cache.
+AIE_DEV_NOINLINE void mt_twist(uint32_t *mt, int lane) {
     wsync();
     mt_twist_phase<0, 227, 397>(mt, lane);
     mt_twist_phase<227, 227, -227>(mt, lane);
@@ -719,8 +734,10 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const int
             case COMP_TAX: tax_step(c, e, s, lane); break;
         }
     }
-    regen_resource(c, e, 1, r);  // Wood
-    regen_resource(c, e, 0, r);  // Stone
+#if AIE_ON_DEVICE
+#pragma unroll 1
+#endif
+    for (int ri = 0; ri < 2; ri++) regen_resource(c, e, 1 - ri, r);  // Wood, then Stone (one inlined copy)
     compute_reward(c, e, s, rew_out, lane);
     if (lane == 0) {
         e.hdr[HDR_MT_POS] = r.pos;
@@ -892,6 +909,9 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
     const uint32_t bit4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
     if (c.planner_spatial) {
         // one lane per map cell: the cell byte is read once and fans out to all M channel planes + 2 index planes
+#if AIE_ON_DEVICE
+        AIE_UNROLL(AIE_OBS_UNROLL)
+#endif
         for (int k = lane; k < HW; k += NL) {
             const uint32_t cb = e.cell[k];
             float *dst = o.p_map + k;
@@ -917,6 +937,9 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const 
             float *amap = o.a_map + a * (M + 1) * ww;
             int16_t *aidx = o.a_idx + a * 2 * ww;
             int dr = dr_first, dc = dc_first;
+#if AIE_ON_DEVICE
+        AIE_UNROLL(AIE_OBS_UNROLL)
+#endif
             for (int q = lane; q < ww; q += NL) {
                 const int r2 = r0 + dr, c2 = c0 + dc;
                 const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
