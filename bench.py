@@ -54,6 +54,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def committed_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    capture of this same command (profiles/); None when no capture exists for the workload."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_%s_raw.csv" % kernel)
+    if workload != "c2" or not os.path.exists(path):
+        return None, None
+    try:
+        rows = list(csv.reader(open(path)))
+        d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+        tot = sum(float(d[k].replace(",", "")) * scale.get(u[k], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        return tot, os.path.relpath(path, ROOT)
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -286,8 +303,9 @@ def main():
         k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
         k["frac"] = k["achieved_gbs"] / peak
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    traffic, traffic_src = committed_traffic(args.workload, dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "whole_step": {"alg_bytes_per_env_step": d.algorithmic_bytes_per_env_step,
                                "achieved": d.algorithmic_bytes_per_env_step * E * args.steps / (ms_total * 1e-3) / 1e9,
                                "frac": d.algorithmic_bytes_per_env_step * E * args.steps / (ms_total * 1e-3) / 1e9 / peak},
