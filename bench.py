@@ -41,6 +41,10 @@ WORKLOADS = {
     # BASELINE.json configs[2]: + PeriodicBracketTax planner, 10 agents, 40x40, 8192 env replicas per GPU
     "c3": dict(cfg="c3_paper_tax", envs_per_gpu=8192,
                desc="gather-trade-build + PeriodicBracketTax, 10 agents, 40x40, 8192 env replicas per GPU"),
+    # BASELINE.json configs[4]: ContinuousDoubleAuction stress, 64 agents, 64x64, deep book, 16384 envs over 8 GPUs
+    "c5": dict(cfg="c5_full", envs_per_gpu=2048,
+               desc="CDA stress (uniform/simple_wood_and_stone: Build+CDA(max_num_orders=50)+Gather, multi-action agents), "
+                    "64 agents, 64x64, 2048 env replicas per GPU"),
 }
 
 
@@ -176,7 +180,7 @@ def run_reference_arm(args, rank, world):
     n_envs = max(threads * 256, 1024)
     t0 = time.perf_counter()
     rate, total = oracle_rate(w["cfg"], n_envs, args.steps, threads, warmup=args.warmup)
-    A = 4 if args.workload == "c2" else 10
+    A = {"c2": 4, "c3": 10, "c5": 64}[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -73,4 +73,14 @@ CONFIGS = {
         multi_action_mode_agents=True, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True,
         starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
+    # c5 at the BASELINE size: 64 agents, 64x64, deep book (K=50), multi-action agents
+    "c5_full": dict(
+        scenario_name="uniform/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=50)),
+                    ("Gather", dict(skill_dist="pareto"))],
+        n_agents=64, world_size=[64, 64], episode_length=150,
+        multi_action_mode_agents=True, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
 }

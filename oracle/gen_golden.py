@@ -31,6 +31,7 @@ PLAN = [
     ("tax_us_federal", 1001, 120, 10),
     ("ref_unit_test", 1001, 100, 10),
     ("c5_small", 1001, 150, 25),
+    ("c5_full", 1001, 60, 20),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

@@ -13,4 +13,4 @@ def test_emulated_device_code_matches_reference_golden_trace(path):
     def make(spec, init):
         return GoldenStepperAdapter(EmuStepper(spec, 1), init)
 
-    assert gu.replay(path, make) >= 100
+    assert gu.replay(path, make) >= 50

@@ -42,7 +42,7 @@ def test_cuda_matches_reference_golden_trace(path):
     def make(spec, init):
         return GoldenStepperAdapter(_cuda_stepper(spec, 3), init, env_index=1)  # env 1 of 3: exercises indexing
 
-    assert gu.replay(path, make) >= 100
+    assert gu.replay(path, make) >= 50
 
 
 @pytest.mark.parametrize("cfg,E,steps,every", [
@@ -51,6 +51,7 @@ def test_cuda_matches_reference_golden_trace(path):
     ("c3_short_period", 32, 200, 25),   # tax annealing, random placement, short order duration
     ("tax_us_federal", 32, 120, 20),    # multi-action agents, fixed schedule
     ("c5_small", 8, 150, 25),           # 32 agents, multi-action, K=50 book, sorted-gini branch
+    ("c5_full", 6, 40, 20),             # BASELINE config 5 shape: 64 agents, 64x64, K=50 (2 agents per lane)
 ])
 def test_cuda_batch_matches_oracle(cfg, E, steps, every):
     env = _make_env(cfg, E, seed=4000, auto_reset=False)

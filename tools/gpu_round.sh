@@ -25,6 +25,10 @@ if [[ $PH == all || $PH == *c3* ]]; then
   timeout 900 python bench.py --workload c3 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
   cat gpurun_out/bench_c3.json; tail -3 gpurun_out/bench_c3.err
 fi
+if [[ $PH == all || $PH == *c5* ]]; then
+  timeout 900 python bench.py --workload c5 --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 3 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"
+  cat gpurun_out/bench_c5.json; tail -3 gpurun_out/bench_c5.err
+fi
 if [[ $PH == all || $PH == *ncu* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 90 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
