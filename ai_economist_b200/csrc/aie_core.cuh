@@ -123,10 +123,12 @@ struct StepScratch {
     uint8_t *act_tax;                                    // [16]
     uint8_t *perm;                                       // [A]
     double *tmp;                                         // [2A + 4]
+    uint32_t *book;                                      // [4][A] per-agent best bid/ask key + slot (matching)
 };
 AIE_DEV StepScratch step_scratch_view(uint8_t *p, const DevCfg &c) {
     StepScratch s;
     s.tmp = (double *)p;  p += 8 * (2 * c.A + 4);
+    s.book = (uint32_t *)p;  p += 16 * c.A;
     s.act_build = p;      p += c.A;
     s.act_move = p;       p += c.A;
     s.act_buy = p;        p += 2 * c.A;
@@ -346,57 +348,76 @@ AIE_DEV void cda_create(const DevCfg &c, Env &e, const StepScratch &s, int t, in
 }
 
 // match_orders :231-350.  The reference stable-sorts bids by (price desc, lifetime desc) and asks by
-// (price asc, lifetime desc); ties keep creation order, i.e. agent index ascending.  Here the "first" bid
-// / ask is found by a warp max-reduction over packed keys (price | lifetime | 255 - agent) computed from the
-// order slots, with the same buyer-level `possible_match` bookkeeping and restart-from-top loop.
-AIE_DEV void cda_match(const DevCfg &c, Env &e, int t, int lane) {
+// (price asc, lifetime desc); ties keep creation order, i.e. agent index ascending.  Here every order maps to a
+// packed key (price | lifetime | 255 - agent) with the same total order.  Each agent's best bid and best ask
+// (key + slot) are found once per step; the restart-from-top loop then only reduces over agents (redux.max),
+// and after a trade just the two agents involved rescan their own K slots.  Same buyer-level `possible_match`
+// bookkeeping as the reference.
+AIE_DEV uint32_t bid_key(int t, uint32_t o, int a) {
+    return ((uint32_t)(order_price(o) + 1) << 20) | ((uint32_t)(t - order_birth(o)) << 8) | (uint32_t)(255 - a);
+}
+AIE_DEV uint32_t ask_key(int t, int P, uint32_t o, int a) {
+    return ((uint32_t)(P - order_price(o)) << 20) | ((uint32_t)(t - order_birth(o)) << 8) | (uint32_t)(255 - a);
+}
+// best order of one side for agent a, scanned by the whole warp over its K slots; lane 0 stores it
+AIE_DEV void refresh_best(const DevCfg &c, const uint32_t *slots, int a, int side, int t, uint32_t *best_key,
+                          uint32_t *best_slot, int lane) {
+    uint32_t bk = 0, bs = 0;
+    for (int k = lane; k < c.K; k += NL) {
+        const uint32_t o = slots[a * c.K + k];
+        if (o != ORDER_EMPTY && order_side(o) == side) {
+            const uint32_t key = side == 0 ? bid_key(t, o, a) : ask_key(t, c.P, o, a);
+            if (key > bk) { bk = key; bs = (uint32_t)(a * c.K + k); }
+        }
+    }
+    const uint32_t m = wmax(bk);
+    bs = wshfl(bs, first_lane(wballot(bk == m)));
+    wsync();
+    if (lane == 0) { best_key[a] = m; best_slot[a] = bs; }
+}
+
+AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int lane) {
     const int A = c.A, P = c.P, K = c.K, n = A * K;
+    uint32_t *bb_key = s.book, *bb_slot = s.book + A, *ba_key = s.book + 2 * A, *ba_slot = s.book + 3 * A;
     for (int cc = 0; cc < 2; cc++) {
         uint32_t *slots = e.orders + cc * n;
+        // one pass over the book: lane-per-agent scan of its K slots
+        for (int a = lane; a < A; a += NL) {
+            uint32_t bk = 0, bs = 0, ak = 0, as = 0;
+            for (int k = 0; k < K; k++) {
+                const uint32_t o = slots[a * K + k];
+                if (o == ORDER_EMPTY) continue;
+                if (order_side(o) == 0) { const uint32_t key = bid_key(t, o, a); if (key > bk) { bk = key; bs = (uint32_t)(a * K + k); } }
+                else { const uint32_t key = ask_key(t, P, o, a); if (key > ak) { ak = key; as = (uint32_t)(a * K + k); } }
+            }
+            bb_key[a] = bk; bb_slot[a] = bs; ba_key[a] = ak; ba_slot[a] = as;
+        }
+        wsync();
         uint64_t possible = (A >= 64) ? ~0ull : ((1ull << A) - 1ull);
         for (;;) {
-            // best bid among still-possible buyers
-            uint32_t bk = 0, bi = 0;
-            for (int i = lane; i < n; i += NL) {
-                uint32_t o = slots[i];
-                if (o != ORDER_EMPTY && order_side(o) == 0) {
-                    int a = div_K(c, i);
-                    if ((possible >> a) & 1ull) {
-                        uint32_t key = ((uint32_t)(order_price(o) + 1) << 20) | ((uint32_t)(t - order_birth(o)) << 8) |
-                                       (uint32_t)(255 - a);
-                        if (key > bk) { bk = key; bi = (uint32_t)i; }
-                    }
-                }
-            }
-            uint32_t bmax = wmax(bk);
+            // first bid whose buyer is still possible
+            uint32_t bk = 0;
+            for (int a = lane; a < A; a += NL)
+                if (((possible >> a) & 1ull) && bb_key[a] > bk) bk = bb_key[a];
+            const uint32_t bmax = wmax(bk);
             if (bmax == 0) break;  // idx_bid ran off the list: keep_checking = False
-            bi = wshfl(bi, first_lane(wballot(bk == bmax)));
-            int buyer = 255 - (int)(bmax & 255u);
-            int bprice = (int)(bmax >> 20) - 1;
-            int blife = (int)((bmax >> 8) & 4095u);
+            const int buyer = 255 - (int)(bmax & 255u);
+            const int bprice = (int)(bmax >> 20) - 1;
+            const int blife = (int)((bmax >> 8) & 4095u);
             // first ask whose seller is not the buyer
-            uint32_t ak = 0, ai = 0;
-            for (int i = lane; i < n; i += NL) {
-                uint32_t o = slots[i];
-                if (o != ORDER_EMPTY && order_side(o) == 1) {
-                    int a = div_K(c, i);
-                    if (a != buyer) {
-                        uint32_t key = ((uint32_t)(P - order_price(o)) << 20) | ((uint32_t)(t - order_birth(o)) << 8) |
-                                       (uint32_t)(255 - a);
-                        if (key > ak) { ak = key; ai = (uint32_t)i; }
-                    }
-                }
-            }
-            uint32_t amax = wmax(ak);
+            uint32_t ak = 0;
+            for (int a = lane; a < A; a += NL)
+                if (a != buyer && ba_key[a] > ak) ak = ba_key[a];
+            const uint32_t amax = wmax(ak);
             if (amax == 0) { possible &= ~(1ull << buyer); if (!possible) break; continue; }
-            ai = wshfl(ai, first_lane(wballot(ak == amax)));
-            int seller = 255 - (int)(amax & 255u);
-            int aprice = P - (int)(amax >> 20);
-            int alife = (int)((amax >> 8) & 4095u);
+            const int seller = 255 - (int)(amax & 255u);
+            const int aprice = P - (int)(amax >> 20);
+            const int alife = (int)((amax >> 8) & 4095u);
             if (bprice < aprice) { possible &= ~(1ull << buyer); if (!possible) break; continue; }
             // trade: price of whichever order came first (:297-304)
-            int price = (blife <= alife) ? aprice : bprice;
-            wsync();  // all lanes have finished scanning the slots lane 0 is about to clear
+            const int price = (blife <= alife) ? aprice : bprice;
+            const uint32_t bi = bb_slot[buyer], ai = ba_slot[seller];
+            wsync();  // all lanes have read the bests lane 0 is about to invalidate
             if (lane == 0) {
                 slots[bi] = ORDER_EMPTY;
                 slots[ai] = ORDER_EMPTY;
@@ -412,7 +433,11 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, int t, int lane) {
                 e.coin[buyer] += (double)(bprice - price);
             }
             wsync();
+            refresh_best(c, slots, buyer, 0, t, bb_key, bb_slot, lane);
+            refresh_best(c, slots, seller, 1, t, ba_key, ba_slot, lane);
+            wsync();
         }
+        wsync();
     }
 }
 
@@ -729,7 +754,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const int
     for (int i = 0; i < c.n_comp; i++) {
         switch (c.comp[i]) {
             case COMP_BUILD: build_step(c, e, s, r); break;
-            case COMP_CDA: cda_create(c, e, s, t, lane); cda_match(c, e, t, lane); cda_expire(c, e, t, lane); break;
+            case COMP_CDA: cda_create(c, e, s, t, lane); cda_match(c, e, s, t, lane); cda_expire(c, e, t, lane); break;
             case COMP_GATHER: gather_step(c, e, s, r); break;
             case COMP_TAX: tax_step(c, e, s, lane); break;
         }

@@ -204,7 +204,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         c.off_orders = take(4 * 2 * A * c.K);
         c.off_mt = take(4 * 624);
         c.rec_bytes = off;
-        c.step_scratch_bytes = align16(8 * (2 * A + 4) + 7 * A + 16);
+        c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
         c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT) + 2 * 4 * P + A * MS_COUNT + 8 + c.HW + 4);
     }
     return AIE_OK;
