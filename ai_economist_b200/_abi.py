@@ -82,6 +82,35 @@ class AieHostOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _OUT_NAMES]
 
 
+class AieCovidConfig(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in [
+        "abi_version", "n_states", "episode_length", "num_stringency_levels", "action_cooldown_period",
+        "subsidy_interval", "num_subsidy_levels", "time_when_vaccine_delivery_begins", "delivery_interval",
+        "t_first_delivery", "beta_delay", "filter_len", "num_filters", "start_date_index", "rw_policy_days",
+        "value_of_life", "auto_reset"]]
+        + [(n, C.c_float) for n in [
+            "gamma", "death_rate", "infection_too_sick_to_work_rate", "pop_between_age_18_65",
+            "risk_free_interest_rate", "crra_eta", "planner_health_norm", "planner_economic_norm",
+            "min_planner_health", "max_planner_health", "min_planner_econ", "max_planner_econ", "w_planner_health",
+            "w_planner_econ"]]
+        + [("reward_normalization_factor", C.c_double), ("time_scale", C.c_double)]
+        + [(n, C.c_void_p) for n in [
+            "population", "num_vaccines_per_delivery", "beta_slopes", "beta_intercepts", "unemployment_bias",
+            "daily_production_per_worker", "maximum_productivity", "agents_health_norm", "agents_economic_norm",
+            "min_agent_health", "max_agent_health", "min_agent_econ", "max_agent_econ", "w_agent_health",
+            "w_agent_econ", "conv_weights", "conv_filters", "max_daily_subsidy_per_state", "rw_policy",
+            "init_state"]])
+
+
+_COVID_BUF_NAMES = ["state", "ints", "hdr", "ring", "actions_agent", "actions_planner", "obs_agent_state",
+                    "obs_postsubsidy", "obs_lagged_stringency", "obs_policy_indicators", "obs_scalars", "mask_agent",
+                    "mask_planner", "reward_agent", "reward_planner", "done"]
+
+
+class AieCovidBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _COVID_BUF_NAMES]
+
+
 class AieError(RuntimeError):
     pass
 
@@ -110,6 +139,17 @@ def load_library(path=None):
     L.aie_step_host.argtypes = [P, P, P, C.POINTER(AieHostOut), P]
     L.aie_read_state.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
     L.aie_launch_count.argtypes = [P]
+    L.aie_covid_create.argtypes = [C.POINTER(AieCovidConfig), C.c_int32, C.c_int32, C.POINTER(P)]
+    L.aie_covid_destroy.argtypes = [P]
+    L.aie_covid_bind_buffers.argtypes = [P, C.POINTER(AieCovidBuffers)]
+    L.aie_covid_reset.argtypes = [P, P]
+    L.aie_covid_step.argtypes = [P, P]
+    L.aie_covid_sample_random_actions.argtypes = [P, C.c_uint64, P]
+    L.aie_covid_launch_count.argtypes = [P]
+    L.aie_covid_launch_count.restype = C.c_int64
+    for fn in ["aie_covid_create", "aie_covid_destroy", "aie_covid_bind_buffers", "aie_covid_reset", "aie_covid_step",
+               "aie_covid_sample_random_actions"]:
+        getattr(L, fn).restype = C.c_int
     L.aie_launch_count.restype = C.c_int64
     for fn in ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers", "aie_load_state",
                "aie_step", "aie_observe", "aie_step_host", "aie_read_state", "aie_step_dynamics",
@@ -122,7 +162,9 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers",
                     "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions",
-                    "aie_step_host", "aie_read_state", "aie_launch_count", "aie_last_error", "aie_abi_version"]
+                    "aie_step_host", "aie_read_state", "aie_launch_count", "aie_last_error", "aie_abi_version",
+                    "aie_covid_create", "aie_covid_destroy", "aie_covid_bind_buffers", "aie_covid_reset", "aie_covid_step",
+                    "aie_covid_sample_random_actions", "aie_covid_launch_count"]
 
 
 def config_from_spec(spec, auto_reset=True):

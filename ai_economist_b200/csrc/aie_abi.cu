@@ -15,9 +15,11 @@
 #include <new>
 
 #include "aie_core.cuh"
+#include "aie_covid_core.cuh"
 #include "aie_host.h"
 
 struct aie_env;
+struct aie_covid_env;
 
 namespace aie {
 namespace be {
@@ -40,10 +42,16 @@ int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, int emit_obs, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
+void *const_upload(const void *host, size_t bytes);
+void const_free(void *dev);
+int covid_launch_reset(aie_covid_env *, void *stream);
+int covid_launch_step(aie_covid_env *, void *stream);
+int covid_launch_sample(aie_covid_env *, uint64_t key, void *stream);
 }  // namespace be
 }  // namespace aie
 
 #include "aie_abi.inl"
+#include "aie_covid_abi.inl"
 
 namespace aie {
 
@@ -332,5 +340,47 @@ int launch_sample(aie_env *env, uint64_t seed, void *stream) {
     return AIE_OK;
 }
 
+}  // namespace be
+
+// ---------------------------------------------------------------------------------------------------------
+// COVID-19 scenario: one CTA per env replica, one thread per US state; a single fused kernel per step.
+__global__ void __launch_bounds__(64) aie_covid_step_kernel(const __grid_constant__ CovidCfg c, const CovidBufs b) {
+    __shared__ float red[3 * 64];
+    covid_step_env(c, blockIdx.x, b, red, threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(64) aie_covid_reset_kernel(const __grid_constant__ CovidCfg c, const CovidBufs b) {
+    covid_reset_env(c, blockIdx.x, b, threadIdx.x, blockDim.x, false);
+}
+
+__global__ void __launch_bounds__(64) aie_covid_sample_kernel(const __grid_constant__ CovidCfg c, const CovidBufs b, uint64_t key) {
+    covid_sample_env(c, blockIdx.x, b, cv_mix64(key ^ cv_mix64(blockIdx.x)), threadIdx.x, blockDim.x);
+}
+
+namespace be {
+void *const_upload(const void *host, size_t bytes) {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+}
+void const_free(void *dev) { cudaFree(dev); }
+int covid_launch_reset(aie_covid_env *env, void *stream) {
+    aie_covid_reset_kernel<<<env->n_envs, 64, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs);
+    AIE_CUDA(cudaGetLastError(), "aie_covid_reset_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
+int covid_launch_sample(aie_covid_env *env, uint64_t key, void *stream) {
+    aie_covid_sample_kernel<<<env->n_envs, 64, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs, key);
+    AIE_CUDA(cudaGetLastError(), "aie_covid_sample_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
+int covid_launch_step(aie_covid_env *env, void *stream) {
+    aie_covid_step_kernel<<<env->n_envs, 64, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs);
+    AIE_CUDA(cudaGetLastError(), "aie_covid_step_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
 }  // namespace be
 }  // namespace aie

@@ -5,6 +5,7 @@ from . import components as _components_mod
 from . import entities as _entities_mod
 from . import scenarios as _scenarios_mod
 from .batched_env import BatchedFoundationEnv
+from . import covid19 as _covid_mod  # noqa: F401  (registers the COVID-19 scenario and its components)
 
 agents = _agents_mod.agent_registry
 components = _components_mod.component_registry
@@ -17,4 +18,7 @@ scenarios = _scenarios_mod.scenario_registry
 def make_env_instance(scenario_name, **kwargs):
     """Same call as the reference; extra kwargs: n_envs (default 1), device ("cuda:0"), seeds, auto_reset."""
     scenario_cls = scenarios.get(scenario_name)
+    env_class = getattr(scenario_cls, "env_class", None)
+    if env_class is not None:  # scenarios with their own device path (COVID-19)
+        return env_class(**kwargs)
     return BatchedFoundationEnv(scenario_cls, **kwargs)

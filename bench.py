@@ -42,6 +42,10 @@ WORKLOADS = {
     "c3": dict(cfg="c3_paper_tax", envs_per_gpu=8192,
                desc="gather-trade-build + PeriodicBracketTax, 10 agents, 40x40, 8192 env replicas per GPU"),
     # BASELINE.json configs[4]: ContinuousDoubleAuction stress, 64 agents, 64x64, deep book, 16384 envs over 8 GPUs
+    # BASELINE.json configs[3]: COVID-19 scenario (51 US-state agents + federal planner), 4096 envs per GPU
+    "c4": dict(cfg="covid", envs_per_gpu=4096,
+               desc="COVID-19 + economy (CovidAndEconomySimulation: ControlUSStateOpenCloseStatus + "
+                    "FederalGovernmentSubsidy + VaccinationCampaign), 51 state agents + planner, 4096 env replicas per GPU"),
     "c5": dict(cfg="c5_full", envs_per_gpu=2048,
                desc="CDA stress (uniform/simple_wood_and_stone: Build+CDA(max_num_orders=50)+Gather, multi-action agents), "
                     "64 agents, 64x64, 2048 env replicas per GPU"),
@@ -123,6 +127,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def covid_oracle_rate(n_envs, steps, warmup=1):
+    """agent-env-steps/s of the numpy COVID oracle (single host thread per env loop; numpy releases no parallelism)."""
+    from ai_economist_b200.foundation.covid19 import build_covid_params
+    from oracle.covid_oracle import CovidOracleEnv
+    from oracle.gen_golden_covid import COVID_KWARGS
+    p = build_covid_params(**COVID_KWARGS)
+    envs = [CovidOracleEnv(p) for _ in range(n_envs)]
+    rng = np.random.RandomState(0)
+    total = 0.0
+    for t in range(warmup + steps):
+        acts = [(rng.randint(0, 11, size=51) * (envs[e].t >= envs[e].cooldown_until), 0) for e in range(n_envs)]
+        t0 = time.perf_counter()
+        for e in range(n_envs):
+            envs[e].step(acts[e][0], acts[e][1])
+        dt = time.perf_counter() - t0
+        if t >= warmup:
+            total += dt
+    return n_envs * 51 * steps / total, total
+
+
 def oracle_rate(cfg_name, n_envs, steps, threads, warmup=2, seed0=500000):
     """agent-env-steps/s of the CPU oracle (C port of the reference step) with `threads` host threads.
     Host-side action sampling is excluded from the timed region (as on the GPU side of `value`)."""
@@ -179,8 +203,12 @@ def run_reference_arm(args, rank, world):
     threads = os.cpu_count() or 1
     n_envs = max(threads * 256, 1024)
     t0 = time.perf_counter()
-    rate, total = oracle_rate(w["cfg"], n_envs, args.steps, threads, warmup=args.warmup)
-    A = {"c2": 4, "c3": 10, "c5": 64}[args.workload]
+    if args.workload == "c4":
+        threads, n_envs = 1, 8
+        rate, total = covid_oracle_rate(n_envs, args.steps, warmup=args.warmup)
+    else:
+        rate, total = oracle_rate(w["cfg"], n_envs, args.steps, threads, warmup=args.warmup)
+    A = {"c2": 4, "c3": 10, "c4": 51, "c5": 64}[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -196,6 +224,123 @@ def run_reference_arm(args, rank, world):
         "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_covid(args, rank, world, dev, E, w):
+    """BASELINE config 4: one fused kernel per step (+ the random-policy sampler)."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from ai_economist_b200 import foundation
+    from oracle.gen_golden_covid import COVID_KWARGS, reference_config
+
+    cfg = reference_config(COVID_KWARGS)
+    name = cfg.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=E, device=str(dev), auto_reset=True, **cfg)
+    env.reset()
+    st = env.stepper
+    S = 51
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        st.sample_random_actions(seed=7 + rank); st.step()
+    l0 = st.launch_count()
+    clocks = ClockSampler(dev.index or 0)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        st.sample_random_actions(seed=7 + rank); st.step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = st.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    value = world * E * S * args.steps / (ms_total * 1e-3)
+    n_prof = min(args.steps, 50)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
+    for i in range(n_prof):
+        evs[i][0].record(); st.sample_random_actions(seed=9)
+        evs[i][1].record(); st.step()
+        evs[i][2].record()
+    torch.cuda.synchronize()
+    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(2)]
+    peak, peak_src = peaks()
+    L = env.params["filter_len"]
+    out_bytes = 4 * (6 * S + 3 * S + 4 + 11 * S + 21 + S) + 8 + 4
+    step_bytes = out_bytes + 2 * (9 * S * 4 + 2 * S * 4 + 16) + (L + 1) * S + S + 4 * S + 4   # + ring read/1-row write + actions
+    kernels = {"aie_covid_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * step_bytes},
+               "aie_covid_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (11 * S * 4 + 21 * 4 + 4 * S)}}
+    for k in kernels.values():
+        k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["achieved_gbs"] / peak
+    dom = "aie_covid_step_kernel"
+    # e2e: pinned host actions in, all outputs back
+    names = ["obs_agent_state", "obs_postsubsidy", "obs_lagged_stringency", "obs_policy_indicators", "obs_scalars",
+             "mask_agent", "mask_planner", "reward_agent", "reward_planner", "done"]
+    host = {n: torch.empty(st.buf[n].shape, dtype=st.buf[n].dtype, pin_memory=True) for n in names}
+    act_a = torch.zeros((E, S), dtype=torch.int32, pin_memory=True)
+    act_p = torch.zeros((E,), dtype=torch.int32, pin_memory=True)
+    d2h = sum(t.numel() * t.element_size() for t in host.values())
+    rng = np.random.RandomState(rank)
+    host["mask_agent"].copy_(st.buf["mask_agent"]); host["mask_planner"].copy_(st.buf["mask_planner"])
+    e2e_s, n_e2e = 0.0, max(3, args.e2e_steps)
+    for i in range(n_e2e + 2):
+        ma, mp = host["mask_agent"].numpy(), host["mask_planner"].numpy()
+        act_a.copy_(torch.from_numpy(np.argmax(ma * (rng.random_sample(ma.shape) + 1e-3), axis=1).astype(np.int32)))
+        act_p.copy_(torch.from_numpy(np.argmax(mp * (rng.random_sample(mp.shape) + 1e-3), axis=1).astype(np.int32)))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.buf["actions_agent"].copy_(act_a, non_blocking=True); st.buf["actions_planner"].copy_(act_p, non_blocking=True)
+        st.step()
+        for n in names:
+            host[n].copy_(st.buf[n], non_blocking=True)
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_s += time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC.replace("gather-trade-build", "covid19"), "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "envs_per_gpu": E, "n_agents": S,
+                   "parallelism": "env replicas sharded over %d GPU(s), no collective on the step path" % world,
+                   "actions": "device random policy over unmasked actions, inside the timed region",
+                   "l2": "per-step footprint %.0f MB (stringency history re-read every step) > 126 MB L2" % (E * step_bytes / 1e6)},
+        "clocks": clk,
+        "e2e": {"value": world * E * S * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": E * (S + 1) * 4,
+                "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                "what": "pinned host actions -> device, step, every observation/mask/reward/done tensor back to pinned host"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src, "kernels": kernels},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, total = covid_oracle_rate(8, 40)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "8 env replicas x 40 steps, numpy oracle (one thread), %.1f s" % total}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -228,6 +373,8 @@ def main():
 
     w = WORKLOADS[args.workload]
     E = args.envs_per_gpu or w["envs_per_gpu"]
+    if args.workload == "c4":
+        return run_covid(args, rank, world, dev, E, w)
     name, kw = bu.product_kwargs(w["cfg"])
     t_setup = time.perf_counter()
     from ai_economist_b200.sharding import shard_seeds

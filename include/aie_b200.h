@@ -246,6 +246,79 @@ int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out);
 /* Number of kernels the library has launched on this handle since creation (for bench "gpu_launches"). */
 int64_t aie_launch_count(const aie_env *env);
 
+/* ================================================================================================
+ * COVID-19 + economy scenario (BASELINE config 4)
+ *
+ * Replaces the reference's WarpDrive kernels for this scenario, which are launched one after the other by
+ * FoundationEnvWrapper.step_all_envs (ai_economist/foundation/env_wrapper.py:355-377):
+ *   CudaControlUSStateOpenCloseStatusStep   components/covid19_components_step.cu:10-113
+ *   CudaFederalGovernmentSubsidyStep        components/covid19_components_step.cu:115-209
+ *   CudaVaccinationCampaignStep             components/covid19_components_step.cu:211-262
+ *   CudaCovidAndEconomySimulationStep       scenarios/covid19/covid19_env_step.cu:274-476
+ *   CudaComputeReward                       scenarios/covid19/covid19_env_step.cu:480-619
+ * by ONE fused kernel per step that follows the *Python* path's arithmetic (covid19_env.py:650-1173,
+ * covid19_components.py:145-627), including its mixed float32 / int32 / float64 promotions.
+ * All fitted parameters are resolved on the host (ai_economist_b200/foundation/covid19.py) and copied into
+ * library-owned device memory at creation.
+ * ================================================================================================ */
+typedef struct aie_covid_config {
+    int32_t abi_version;
+    int32_t n_states;            /* 51 */
+    int32_t episode_length, num_stringency_levels, action_cooldown_period;
+    int32_t subsidy_interval, num_subsidy_levels;
+    int32_t time_when_vaccine_delivery_begins, delivery_interval, t_first_delivery;
+    int32_t beta_delay, filter_len, num_filters, start_date_index, rw_policy_days;
+    int32_t value_of_life;
+    int32_t auto_reset;
+    float gamma, death_rate, infection_too_sick_to_work_rate, pop_between_age_18_65, risk_free_interest_rate, crra_eta;
+    float planner_health_norm, planner_economic_norm;
+    float min_planner_health, max_planner_health, min_planner_econ, max_planner_econ, w_planner_health, w_planner_econ;
+    double reward_normalization_factor, time_scale;
+    /* host arrays, copied at creation ([S] unless noted) */
+    const int32_t *population, *num_vaccines_per_delivery;
+    const float *beta_slopes, *beta_intercepts, *unemployment_bias, *daily_production_per_worker /* [1] */,
+        *maximum_productivity, *agents_health_norm, *agents_economic_norm, *min_agent_health, *max_agent_health,
+        *min_agent_econ, *max_agent_econ, *w_agent_health, *w_agent_econ;
+    const float *conv_weights;      /* [S, F] */
+    const float *conv_filters;      /* [F, L] exp(-(L-1-k)/lambda_f) evaluated in float32 as the reference does */
+    const double *max_daily_subsidy_per_state;
+    const int8_t *rw_policy;        /* [rw_policy_days, S] real-world stringency (initial history, lag before t = beta_delay) */
+    const float *init_state;        /* [6, S] Susceptible, Infected, Recovered, Deaths, Vaccinated, Unemployed at t = 0 */
+} aie_covid_config;
+
+/* Device buffers (contiguous, env-major).  state: float32 [E, 9, S] = S, I, R, D, V, U, stringency, subsidy,
+ * postsubsidy productivity at the current timestep; ints: int32 [E, 2, S] = cooldown_until, vaccines_available;
+ * hdr: int32 [E, 4] = t, subsidy_level, ring_head, episodes; ring: int8 [E, L+1, S] stringency history.
+ * Observations are the reference's collated "a"/"p" fields (covid19_env.py:919-993 + components), float32. */
+typedef struct aie_covid_buffers {
+    float *state; int32_t *ints; int32_t *hdr; int8_t *ring;
+    const int32_t *actions_agent;   /* [E, S] stringency action 0..num_stringency_levels (0 = NO-OP) */
+    const int32_t *actions_planner; /* [E]    subsidy level action 0..num_subsidy_levels */
+    float *obs_agent_state;         /* [E, 6, S]  world-agent_state */
+    float *obs_postsubsidy;         /* [E, S]     world-agent_postsubsidy_productivity */
+    float *obs_lagged_stringency;   /* [E, S]     world-lagged_stringency_level */
+    float *obs_policy_indicators;   /* [E, S]     ControlUSStateOpenCloseStatus-agent_policy_indicators */
+    float *obs_scalars;             /* [E, 4]     time, t_until_next_subsidy, current_subsidy_level, t_until_next_vaccines */
+    float *mask_agent;              /* [E, 1+levels, S] */
+    float *mask_planner;            /* [E, 1+num_subsidy_levels] */
+    float *reward_agent;            /* [E, S] */
+    double *reward_planner;         /* [E] */
+    int32_t *done;                  /* [E] */
+} aie_covid_buffers;
+
+typedef struct aie_covid_env aie_covid_env;
+
+int aie_covid_create(const aie_covid_config *cfg, int32_t n_envs, int32_t device, aie_covid_env **out);
+int aie_covid_destroy(aie_covid_env *env);
+int aie_covid_bind_buffers(aie_covid_env *env, const aie_covid_buffers *bufs);
+/* env.reset() for every replica (covid19_env.py:1175-1290 is deterministic): state, history, first observations. */
+int aie_covid_reset(aie_covid_env *env, void *stream);
+/* One env.step() for every replica: 3 component steps + scenario step + observations + rewards + done. */
+int aie_covid_step(aie_covid_env *env, void *stream);
+/* Random policy on the device (uniform over the unmasked actions of the current masks); see aie_sample_random_actions. */
+int aie_covid_sample_random_actions(aie_covid_env *env, uint64_t seed, void *stream);
+int64_t aie_covid_launch_count(const aie_covid_env *env);
+
 const char *aie_last_error(void);
 int aie_abi_version(void);
 

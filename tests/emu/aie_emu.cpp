@@ -15,9 +15,11 @@
 #include <vector>
 
 #include "../../ai_economist_b200/csrc/aie_core.cuh"
+#include "../../ai_economist_b200/csrc/aie_covid_core.cuh"
 #include "../../ai_economist_b200/csrc/aie_host.h"
 
 struct aie_env;
+struct aie_covid_env;
 namespace aie { namespace be {
 struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; };
 int init(aie_env *);
@@ -31,9 +33,15 @@ int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, int emit_obs, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
+void *const_upload(const void *host, size_t bytes);
+void const_free(void *dev);
+int covid_launch_reset(aie_covid_env *, void *stream);
+int covid_launch_step(aie_covid_env *, void *stream);
+int covid_launch_sample(aie_covid_env *, uint64_t key, void *stream);
 } }
 
 #include "../../ai_economist_b200/csrc/aie_abi.inl"
+#include "../../ai_economist_b200/csrc/aie_covid_abi.inl"
 
 namespace aie { namespace be {
 int init(aie_env *env) {
@@ -108,6 +116,24 @@ int launch_sample(aie_env *env, uint64_t seed, void *) {
                            const_cast<int32_t *>(b.act_a) + (size_t)e * c.A * c.n_act_a,
                            c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)e * c.n_act_p : nullptr,
                            mix64(s ^ mix64((uint64_t)e)), 0);
+    env->launches++;
+    return AIE_OK;
+}
+void *const_upload(const void *host, size_t bytes) { void *d = malloc(bytes ? bytes : 1); if (d) memcpy(d, host, bytes); return d; }
+void const_free(void *dev) { free(dev); }
+int covid_launch_reset(aie_covid_env *env, void *) {
+    for (int e = 0; e < env->n_envs; e++) covid_reset_env(env->cfg, e, env->bufs, 0, 1, false);
+    env->launches++;
+    return AIE_OK;
+}
+int covid_launch_sample(aie_covid_env *env, uint64_t key, void *) {
+    for (int e = 0; e < env->n_envs; e++) covid_sample_env(env->cfg, e, env->bufs, cv_mix64(key ^ cv_mix64((uint64_t)e)), 0, 1);
+    env->launches++;
+    return AIE_OK;
+}
+int covid_launch_step(aie_covid_env *env, void *) {
+    std::vector<float> red(3 * 64);
+    for (int e = 0; e < env->n_envs; e++) covid_step_env(env->cfg, e, env->bufs, red.data(), 0, 1);
     env->launches++;
     return AIE_OK;
 }

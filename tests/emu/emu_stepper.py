@@ -55,3 +55,22 @@ class EmuStepper(BatchStepper):
 
 def emu_factory(spec, n_envs, auto_reset):
     return EmuStepper(spec, n_envs, auto_reset=auto_reset)
+
+
+class EmuCovidStepper:
+    """COVID-19 scenario through the emulated device code (numpy buffers)."""
+
+    def __new__(cls, params, n_envs, auto_reset=False):
+        from ai_economist_b200.covid_stepper import CovidStepperBase
+
+        class _Emu(CovidStepperBase):
+            def _alloc(self, shape, dt):
+                return np.zeros(shape, dtype=self._DT[dt])
+
+            def _ptr(self, buf):
+                return buf.ctypes.data_as(C.c_void_p)
+
+            def to_numpy(self, buf):
+                return np.array(buf)
+
+        return _Emu(params, n_envs, emu_lib(), auto_reset=auto_reset)

@@ -1,0 +1,152 @@
+"""COVID-19 + economy scenario (BASELINE config 4).
+
+CPU: (1) the host-side parameter derivation against constants read off the reference (when present);
+(2) oracle/covid_oracle.py (numpy restatement) against the golden trace recorded from the unmodified reference;
+(3) the device source compiled for the host (tests/emu) against the same trace.
+GPU: the CUDA kernel through the C-ABI against the golden trace and against the numpy oracle on batches.
+
+Tolerance: float32 fields <= 1e-6 relative (atol 1e-9); masks / integer state exact.  In practice all float32
+observations are bit-identical; the tolerance covers powf/exp/log ulp differences between device and glibc.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from ai_economist_b200.foundation.covid19 import build_covid_params
+from oracle.covid_oracle import CovidOracleEnv
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_covid", "covid_seed3.npz")
+OBS_KEYS = ["agent_state", "postsubsidy", "lagged", "policy_ind", "scalars", "mask_a", "mask_p"]
+RTOL, ATOL = 1e-6, 1e-9
+
+
+def load():
+    z = np.load(GOLDEN)
+    meta = json.loads(str(z["meta_json"]))
+    return z, meta, build_covid_params(**meta["kwargs"])
+
+
+def check(z, t, obs, label):
+    for k in OBS_KEYS:
+        assert np.allclose(z[k][t], obs[k], rtol=RTOL, atol=ATOL), "%s step %d: %s" % (label, t, k)
+    assert np.array_equal(z["mask_a"][t], obs["mask_a"]) and np.array_equal(z["mask_p"][t], obs["mask_p"])
+    if t > 0:
+        assert np.allclose(z["rew_a"][t - 1], obs["rew_a"], rtol=RTOL, atol=ATOL), "%s step %d: rew_a" % (label, t)
+        assert np.isclose(float(z["rew_p"][t - 1]), float(obs["rew_p"]), rtol=RTOL, atol=ATOL), "%s step %d: rew_p" % (label, t)
+        assert int(z["done"][t - 1]) == int(obs["done"])
+
+
+def replay(stepper_step, stepper_obs, z, n, label):
+    check(z, 0, stepper_obs(), label)
+    for t in range(1, n + 1):
+        stepper_step(z["act_a"][t - 1].astype(np.int32), np.int32(z["act_p"][t - 1]))
+        check(z, t, stepper_obs(), label)
+
+
+def test_covid_oracle_matches_reference_golden_trace():
+    z, meta, p = load()
+    env = CovidOracleEnv(p)
+    replay(lambda a, pl: env.step(a, pl), env.obs, z, meta["n_steps"], "oracle")
+
+
+def _drive(stepper, e=0):
+    def step(a, pl):
+        ba, bp = stepper.buf["actions_agent"], stepper.buf["actions_planner"]
+        if isinstance(ba, np.ndarray):
+            ba[e] = a; bp[e] = pl
+        else:
+            import torch
+            ba[e] = torch.as_tensor(a, device=ba.device); bp[e] = int(pl)
+        stepper.step()
+    return step, (lambda: stepper.read_obs(e))
+
+
+def test_covid_emulated_device_code_matches_reference_golden_trace():
+    from tests.emu.emu_stepper import EmuCovidStepper
+    z, meta, p = load()
+    s = EmuCovidStepper(p, 2)
+    s.reset()
+    step, obs = _drive(s, e=1)
+    replay(step, obs, z, meta["n_steps"], "emu")
+    st = s.read_state(1)
+    assert np.allclose(st["susceptible"], z["st_susceptible"][-1], rtol=RTOL) and np.allclose(st["deaths"], z["st_deaths"][-1], rtol=RTOL)
+    assert np.array_equal(st["stringency"], z["st_stringency"][-1])
+
+
+def test_covid_emulated_auto_reset_starts_a_fresh_episode():
+    from tests.emu.emu_stepper import EmuCovidStepper
+    z, meta, _ = load()
+    kw = dict(meta["kwargs"], episode_length=12)
+    p = build_covid_params(**kw)
+    s = EmuCovidStepper(p, 1, auto_reset=True)
+    s.reset()
+    first = s.read_obs(0)
+    step, obs = _drive(s)
+    for t in range(12):
+        step(np.zeros(51, np.int32), np.int32(0))
+    o = obs()
+    assert int(o["done"]) == 1 and s.read_state(0)["t"] == 0 and s.read_state(0)["episodes"] == 1
+    for k in OBS_KEYS:
+        assert np.array_equal(o[k], first[k]), k
+
+
+@pytest.mark.gpu
+def test_covid_cuda_matches_reference_golden_trace():
+    from ai_economist_b200.covid_stepper import CudaCovidStepper
+    z, meta, p = load()
+    s = CudaCovidStepper(p, 3, auto_reset=False)
+    s.reset()
+    step, obs = _drive(s, e=2)
+    replay(step, obs, z, meta["n_steps"], "cuda")
+
+
+@pytest.mark.gpu
+def test_covid_cuda_batch_matches_numpy_oracle():
+    import torch
+    from ai_economist_b200.covid_stepper import CudaCovidStepper
+    z, meta, p = load()
+    E, steps = 12, 200
+    s = CudaCovidStepper(p, E, auto_reset=False)
+    s.reset()
+    envs = [CovidOracleEnv(p) for _ in range(E)]
+    rng = np.random.RandomState(11)
+    for t in range(steps):
+        ma = s.to_numpy(s.buf["mask_agent"])      # [E, 11, S]
+        mp = s.to_numpy(s.buf["mask_planner"])    # [E, 21]
+        aa = np.argmax(ma * (rng.random_sample(ma.shape) + 1e-3), axis=1).astype(np.int32)
+        ap = np.argmax(mp * (rng.random_sample(mp.shape) + 1e-3), axis=1).astype(np.int32)
+        s.buf["actions_agent"].copy_(torch.as_tensor(aa)); s.buf["actions_planner"].copy_(torch.as_tensor(ap))
+        s.step()
+        for e in range(E):
+            envs[e].step(aa[e], ap[e])
+        if (t + 1) % 50 == 0:
+            for e in range(E):
+                got, ref = s.read_obs(e), envs[e].obs()
+                for k in OBS_KEYS + ["rew_a"]:
+                    assert np.allclose(ref[k], got[k], rtol=RTOL, atol=ATOL), (t, e, k)
+                assert np.isclose(float(ref["rew_p"]), float(got["rew_p"]), rtol=RTOL, atol=ATOL)
+
+
+def test_covid_env_api_through_make_env_instance():
+    """Same call as the reference (tests/run_covid19_cpu_gpu_consistency_checks.py:44-81 config)."""
+    from ai_economist_b200 import foundation
+    from oracle.gen_golden_covid import COVID_KWARGS, reference_config
+    from tests.emu.emu_stepper import EmuCovidStepper
+    z, meta, p = load()
+    cfg = reference_config(COVID_KWARGS)
+    name = cfg.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=2, auto_reset=False,
+                                       stepper_factory=lambda params, n, ar: EmuCovidStepper(params, n, ar), **cfg)
+    assert foundation.scenarios.has("CovidAndEconomySimulation") and foundation.components.has("VaccinationCampaign")
+    obs = env.reset()
+    assert set(obs.keys()) == {"a", "p"}
+    assert obs["a"]["world-agent_state"].shape == (2, 6, 51) and obs["a"]["action_mask"].shape == (2, 11, 51)
+    assert obs["p"]["action_mask"].shape == (2, 21) and obs["a"]["time"].shape == (2, 51)
+    for t in range(1, 40):
+        a = np.repeat(z["act_a"][t - 1][None].astype(np.int32), 2, axis=0)
+        pl = np.repeat(np.int32(z["act_p"][t - 1]), 2)
+        obs, rew, done, info = env.step({"a": a, "p": pl})
+        check(z, t, env.stepper.read_obs(1), "api")
+    assert rew["a"].shape == (2, 51) and rew["p"].shape == (2,) and "__all__" in done

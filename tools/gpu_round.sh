@@ -25,6 +25,10 @@ if [[ $PH == all || $PH == *c3* ]]; then
   timeout 900 python bench.py --workload c3 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
   cat gpurun_out/bench_c3.json; tail -3 gpurun_out/bench_c3.err
 fi
+if [[ $PH == all || $PH == *c4* ]]; then
+  timeout 900 python bench.py --workload c4 --steps 100 --warmup 10 --e2e-steps 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench c4 rc=$?"
+  cat gpurun_out/bench_c4.json; tail -3 gpurun_out/bench_c4.err
+fi
 if [[ $PH == all || $PH == *c5* ]]; then
   timeout 900 python bench.py --workload c5 --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 3 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; echo "bench c5 rc=$?"
   cat gpurun_out/bench_c5.json; tail -3 gpurun_out/bench_c5.err

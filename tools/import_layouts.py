@@ -11,3 +11,12 @@ if __name__ == "__main__":
     for f in glob.glob(SRC + "/*.txt"):
         shutil.copy(f, DST)
         print("copied", os.path.basename(f))
+
+# COVID-19 scenario data (fitted parameters, model constants, real-world time series): data, not code
+COVID_SRC = "/root/reference/ai_economist/datasets/covid19_datasets/data_and_fitted_params"
+COVID_DST = os.path.join(os.path.dirname(DST), "covid19_data")
+if __name__ == "__main__":
+    os.makedirs(COVID_DST, exist_ok=True)
+    for f in ("fitted_params.json", "model_constants.json", "real_world_data.npz"):
+        shutil.copy(os.path.join(COVID_SRC, f), COVID_DST)
+        print("copied", f)
