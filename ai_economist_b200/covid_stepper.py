@@ -80,7 +80,7 @@ class CovidStepperBase:
         self._h = h
         E, S, L = self.n_envs, params["n_states"], params["filter_len"]
         shapes = {
-            "state": ("f32", (E, 9, S)), "ints": ("i32", (E, 2, S)), "hdr": ("i32", (E, 4)), "ring": ("i8", (E, L + 1, S)),
+            "state": ("f32", (E, 9, S)), "ints": ("i32", (E, 2, S)), "hdr": ("i32", (E, 4)), "ring": ("i8", (E, S, (L + 1 + 15) // 16 * 16)),
             "actions_agent": ("i32", (E, S)), "actions_planner": ("i32", (E,)),
             "obs_agent_state": ("f32", (E, 6, S)), "obs_postsubsidy": ("f32", (E, S)),
             "obs_lagged_stringency": ("f32", (E, S)), "obs_policy_indicators": ("f32", (E, S)),

@@ -88,10 +88,15 @@ CV_DEV float cv_crra(float x, float eta) {  // covid19_env.py:1053-1058 (float32
 }
 CV_DEV float cv_minmax(float x, float lo, float hi) { return (x - lo) / ((hi - lo) + 1e-10f); }
 
-CV_DEV int8_t cv_ring_at(const int8_t *ring, int head, int k, int L1, int S, int a) {  // logical index k (0 = oldest)
+// Stringency history: int8 [S][ROW] per env, time-minor (ROW = L+1 rounded up to 16 bytes) so that one state's
+// history is contiguous and can be scanned with 16-byte loads.  Logical index k (0 = oldest) lives at physical
+// column (head + k) mod (L+1).
+struct alignas(16) cv_b16 { int8_t b[16]; };
+CV_DEV int cv_ring_row(int L1) { return (L1 + 15) & ~15; }
+CV_DEV int8_t cv_ring_at(const int8_t *ring, int head, int k, int L1, int S, int a) {
     int p = head + k;
     if (p >= L1) p -= L1;
-    return ring[(size_t)p * S + a];
+    return ring[(size_t)a * cv_ring_row(L1) + p];
 }
 
 // Observations + masks of the current state (used after a step and after a reset).
@@ -132,7 +137,7 @@ CV_DEV void covid_reset_env(const CovidCfg &c, int e, const CovidBufs &b, int ti
     float *st = b.state + (size_t)e * CVS_FIELDS * S;
     int32_t *ints = b.ints + (size_t)e * 2 * S;
     int32_t *hdr = b.hdr + (size_t)e * 4;
-    int8_t *ring = b.ring + (size_t)e * L1 * S;
+    int8_t *ring = b.ring + (size_t)e * cv_ring_row(L1) * S;
     for (int a = tid; a < S; a += nthr) {
         for (int k = 0; k < 6; k++) st[k * S + a] = c.init_state[k * S + a];
         st[CVS_STRG * S + a] = (float)c.rw_policy[(size_t)c.sdi * S + a];
@@ -142,7 +147,7 @@ CV_DEV void covid_reset_env(const CovidCfg &c, int e, const CovidBufs &b, int ti
         // stringency history = real-world policy up to the start date, padded with 1 before the data begins
         for (int k = 0; k < L1; k++) {
             const int day = c.sdi - c.L + k;
-            ring[(size_t)k * S + a] = day < 0 ? (int8_t)1 : c.rw_policy[(size_t)day * S + a];
+            ring[(size_t)a * cv_ring_row(L1) + k] = day < 0 ? (int8_t)1 : c.rw_policy[(size_t)day * S + a];
         }
         if (!keep_outputs) b.rew_a[(size_t)e * S + a] = 0.0f;
     }
@@ -163,7 +168,7 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
     float *st = b.state + (size_t)e * CVS_FIELDS * S;
     int32_t *ints = b.ints + (size_t)e * 2 * S;
     int32_t *hdr = b.hdr + (size_t)e * 4;
-    int8_t *ring = b.ring + (size_t)e * L1 * S;
+    int8_t *ring = b.ring + (size_t)e * cv_ring_row(L1) * S;
     const int t = hdr[CVH_T] + 1;
     const int head = hdr[CVH_RING_HEAD];                  // physical row of the oldest history entry
     const int new_head = head + 1 == L1 ? 0 : head + 1;
@@ -189,7 +194,7 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
         int vacc = ints[S + a] + (vac_day ? c.vac_per_delivery[a] : 0);
         ints[S + a] = 0;
         // stringency history: drop the oldest entry, append today's level (covid19_env.py:1412-1420)
-        ring[(size_t)head * S + a] = (int8_t)strg;
+        ring[(size_t)a * cv_ring_row(L1) + head] = (int8_t)strg;
         // ---- sir_step (covid19_env.py:1477-1515) ----
         const double tmk = (double)(int)cv_ring_at(ring, new_head, L - c.beta_delay, L1, S, a);
         const float beta_i = (float)((double)c.beta_intercepts[a] + (double)c.beta_slopes[a] * tmk);  // f64: f32 * int32
@@ -206,14 +211,33 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
         const float V_t = fmaxf(V_tm1 + dV, 0.0f);
         const float D_t = c.death_rate * (R_t - V_t);
         // ---- unemployment_step (covid19_env.py:1374-1441): discounted sum of past stringency changes (f64) ----
+        // The row is scanned in PHYSICAL order with 16-byte loads; the pair (p, p+1 mod L1) is the stringency change
+        // at logical index k = (p - new_head) mod L1, and k == L is the seam between newest and oldest (skipped).
         double acc = 0.0;
-        int prev = cv_ring_at(ring, new_head, 0, L1, S, a);
-        for (int k = 0; k < L; k++) {
-            const int cur = cv_ring_at(ring, new_head, k + 1, L1, S, a);
-            const int d = cur - prev;
-            prev = cur;
-            if (d != 0)
-                for (int f = 0; f < F; f++) acc += ((double)d * (double)c.conv_w[a * F + f]) * (double)c.conv_filt[f * L + k];
+        {
+            const int8_t *row = ring + (size_t)a * cv_ring_row(L1);
+            int prev = row[L1 - 1];                       // predecessor of physical column 0
+            for (int p0 = 0; p0 < L1; p0 += 16) {
+                const cv_b16 ld = *(const cv_b16 *)(row + p0);  // one 16-byte load
+                const int8_t *chunk = ld.b;
+#if CV_ON_DEVICE
+#pragma unroll
+#endif
+                for (int j = 0; j < 16; j++) {
+                    const int p = p0 + j;
+                    if (p >= L1) break;
+                    const int cur = chunk[j];
+                    const int d = cur - prev;             // change between physical columns p-1 and p
+                    prev = cur;
+                    if (d != 0) {
+                        int k = (p - 1) - new_head;       // logical index of the older element of the pair
+                        if (k < 0) k += L1;
+                        if (k < L)
+                            for (int f = 0; f < F; f++)
+                                acc += ((double)d * (double)c.conv_w[a * F + f]) * (double)c.conv_filt[f * L + k];
+                    }
+                }
+            }
         }
         const double excess = (acc <= 20.0) ? log(1.0 + exp(acc)) : acc;  // softplus, beta = 1, threshold = 20
         const double unemployed = (excess + (double)c.unemp_bias[a]) * (double)c.pop[a] / 100.0;

@@ -288,7 +288,8 @@ typedef struct aie_covid_config {
 
 /* Device buffers (contiguous, env-major).  state: float32 [E, 9, S] = S, I, R, D, V, U, stringency, subsidy,
  * postsubsidy productivity at the current timestep; ints: int32 [E, 2, S] = cooldown_until, vaccines_available;
- * hdr: int32 [E, 4] = t, subsidy_level, ring_head, episodes; ring: int8 [E, L+1, S] stringency history.
+ * hdr: int32 [E, 4] = t, subsidy_level, ring_head, episodes; ring: int8 [E, S, ROW] stringency history, time-minor
+ * (ROW = filter_len + 1 rounded up to a multiple of 16 bytes; logical entry k sits at column (ring_head + k) mod (L+1)).
  * Observations are the reference's collated "a"/"p" fields (covid19_env.py:919-993 + components), float32. */
 typedef struct aie_covid_buffers {
     float *state; int32_t *ints; int32_t *hdr; int8_t *ring;
