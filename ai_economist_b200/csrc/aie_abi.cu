@@ -90,7 +90,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ int tab_smem_bytes(const DevCfg &c) { return (2 * c.tab_n + 15) & ~15; }
 __device__ __forceinline__ uint8_t *warp_region(uint8_t *smem, int wpb, int warp, const DevCfg &c) {
     return smem + ((8 * wpb + 15) & ~15) + tab_smem_bytes(c) +
-           (size_t)warp * (c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes);
+           (size_t)warp * (c.resident_bytes + c.step_scratch_bytes + c.obs_scratch_bytes);
 }
 // The programs are indexed by the lane-varying flat position; reading them from global memory costs an L2 round
 // trip per access here because the L1 carve-out is almost entirely shared memory.  One cooperative copy per CTA.
@@ -130,20 +130,20 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     if (env >= c.n_envs) return;  // from here on warps are independent: no block-wide barrier below
     uint64_t *bar = (uint64_t *)smem + warp;
     uint8_t *rec = warp_region(smem, wpb, warp, c);
-    uint8_t *scratch = rec + c.rec_bytes;
+    uint8_t *scratch = rec + c.resident_bytes;
     uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
 
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)c.rec_bytes);
-        bulk_g2s(rec, grec, (uint32_t)c.rec_bytes, bar);
+        mbar_expect_tx(bar, (uint32_t)c.resident_bytes);
+        bulk_g2s(rec, grec, (uint32_t)c.resident_bytes, bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
 
     const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
     const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
-    step_env(c, rec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
+    step_env(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
 
     // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
     // from the load-time snapshot; the episode counters and the numpy stream carry on.
@@ -151,11 +151,19 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     if (c.auto_reset && hdr[HDR_T] >= c.T) {
         const int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
                       episodes = hdr[HDR_EPISODES] + 1;
+        const uint8_t *snap = b.state0 + (size_t)env * c.rec_bytes;
+        const uint32_t tail = (uint32_t)(c.rec_bytes - c.off_price_hist);  // price history + order slots
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-            mbar_expect_tx(bar, (uint32_t)c.off_mt);
-            bulk_g2s(rec, b.state0 + (size_t)env * c.rec_bytes, (uint32_t)c.off_mt, bar);
+            mbar_expect_tx(bar, (uint32_t)c.off_mt + (c.split ? 0u : tail));
+            bulk_g2s(rec, snap, (uint32_t)c.off_mt, bar);
+            if (!c.split) bulk_g2s(rec + c.off_price_hist, snap + c.off_price_hist, tail, bar);
+        }
+        if (c.split) {  // the big sections live in global memory: copy them back from the snapshot with plain stores
+            const uint4 *src = (const uint4 *)(snap + c.off_price_hist);
+            uint4 *dst = (uint4 *)(grec + c.off_price_hist);
+            for (uint32_t i = lane; i < tail / 16; i += 32) dst[i] = src[i];
         }
         __syncwarp();
         mbar_wait(bar, 1);
@@ -164,15 +172,15 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
             hdr[HDR_EPISODES] = episodes;
         }
         __syncwarp();
-        finish_reset_env(c, rec, scratch, lane);  // metric_0 under the new completions count
+        finish_reset_env(c, rec, grec, scratch, lane);  // metric_0 under the new completions count
     }
 
     fence_async_smem();  // generic-proxy writes to the record -> visible to the bulk (async-proxy) store
     __syncwarp();
-    if (lane == 0) bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
+    if (lane == 0) bulk_s2g(grec, rec, (uint32_t)c.resident_bytes);
     // observations / masks of the post-step state stream out of the same shared-memory record while the bulk
     // store drains (both only read the record)
-    if (emit_obs) observe_env(c, rec, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
+    if (emit_obs) observe_env(c, rec, grec, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
     if (lane == 0) bulk_wait_read();
 }
 
@@ -188,18 +196,18 @@ __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_cons
     uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)c.rec_bytes);
-        bulk_g2s(rec, grec, (uint32_t)c.rec_bytes, bar);
+        mbar_expect_tx(bar, (uint32_t)c.resident_bytes);
+        bulk_g2s(rec, grec, (uint32_t)c.resident_bytes, bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    finish_reset_env(c, rec, rec + c.rec_bytes, lane);
+    finish_reset_env(c, rec, grec, rec + c.resident_bytes, lane);
     if (lane == 0) { b.done[env] = 0; }
     for (int a = lane; a <= c.A; a += 32) b.rew[(size_t)env * (c.A + 1) + a] = 0.0;
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-        bulk_s2g(grec, rec, (uint32_t)c.rec_bytes);
+        bulk_s2g(grec, rec, (uint32_t)c.resident_bytes);
         bulk_wait_read();
     }
 }
@@ -215,14 +223,17 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     const int env = lo + i;
     uint64_t *bar = (uint64_t *)smem + warp;
     uint8_t *rec = warp_region(smem, wpb, warp, c);
+    uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
     if (lane == 0) {
+        const uint32_t ph = (uint32_t)(c.off_orders - c.off_price_hist);
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)c.obs_prefix_bytes);
-        bulk_g2s(rec, b.state + (size_t)env * c.rec_bytes, (uint32_t)c.obs_prefix_bytes, bar);
+        mbar_expect_tx(bar, (uint32_t)c.obs_prefix_bytes + (c.split ? 0u : ph));
+        bulk_g2s(rec, grec, (uint32_t)c.obs_prefix_bytes, bar);
+        if (!c.split) bulk_g2s(rec + c.off_price_hist, grec + c.off_price_hist, ph, bar);
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    observe_env(c, rec, rec + c.rec_bytes + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
+    observe_env(c, rec, grec, rec + c.resident_bytes + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
 }
 
 __global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed) {
@@ -255,7 +266,7 @@ int init(aie_env *env) {
     if (prop.major < 10) return fail(AIE_ECUDA, "this build targets sm_100a (Blackwell B200) only");
     const DevCfg &c = env->cfg;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
-    const size_t per_env = (size_t)c.rec_bytes + c.step_scratch_bytes + c.obs_scratch_bytes;
+    const size_t per_env = (size_t)c.resident_bytes + c.step_scratch_bytes + c.obs_scratch_bytes;
     int wpb = 8;
     if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4 || v == 8) wpb = v; }
     const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;

@@ -89,8 +89,11 @@ struct Env {
     uint32_t *orders, *mt;
 };
 
-AIE_DEV Env env_view(uint8_t *rec, const DevCfg &c) {
+// rec: the resident image of the record (shared memory on the device); grec: the record in global memory, used for
+// the price-history / order-slot sections when the config is split (large envs).  In emulation rec == grec.
+AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     Env e;
+    uint8_t *big = c.split ? grec : rec;
     e.hdr = (int32_t *)rec;
     e.coin = (double *)(rec + c.off_coin);
     e.esc_coin = (double *)(rec + c.off_esc_coin);
@@ -102,7 +105,7 @@ AIE_DEV Env env_view(uint8_t *rec, const DevCfg &c) {
     e.last_income = (double *)(rec + c.off_last_income);
     e.last_marg = (double *)(rec + c.off_last_marg);
     e.util_prev = (double *)(rec + c.off_util_prev);
-    e.price_hist = (double *)(rec + c.off_price_hist);
+    e.price_hist = (double *)(big + c.off_price_hist);
     e.inv = (int32_t *)(rec + c.off_inv);
     e.esc = (int32_t *)(rec + c.off_esc);
     e.loc = (int16_t *)(rec + c.off_loc);
@@ -112,7 +115,7 @@ AIE_DEV Env env_view(uint8_t *rec, const DevCfg &c) {
     e.rate_idx = rec + c.off_rate_idx;
     e.cell = rec + c.off_cell;
     e.owner = (int8_t *)(rec + c.off_owner);
-    e.orders = (uint32_t *)(rec + c.off_orders);
+    e.orders = (uint32_t *)(big + c.off_orders);
     e.mt = (uint32_t *)(rec + c.off_mt);
     return e;
 }
@@ -742,9 +745,9 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 // ------------------------------------------------------------------------------------------------
 // One env.step() (base/base_env.py:929-1032) without the observation pass.
 // ------------------------------------------------------------------------------------------------
-AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const int32_t *act_a, const int32_t *act_p,
-                      double *rew_out, int32_t *done_out, int lane) {
-    Env e = env_view(rec, c);
+AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
+                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane) {
+    Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     decode_actions(c, s, act_a, act_p, lane);
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
@@ -773,8 +776,8 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const int
 
 // Finish a host reset on the device: tax trackers + metric_0 (redistribution.py:1106-1139,
 // layout_from_file.py:588-593).  The host packer has already zeroed books, escrow, labor.
-AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, int lane) {
-    Env e = env_view(rec, c);
+AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
+    Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     for (int a = lane; a < c.A; a += NL) {
         e.last_coin[a] = e.coin[a] + e.esc_coin[a];
@@ -829,9 +832,9 @@ AIE_DEV float flat_emit(const DevCfg &c, const Env &e, const ObsScratch &s, uint
     return (float)(kind == FK_FULL ? f : (kind == FK_MY ? m : f - m));
 }
 
-AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *scratch, const ObsOut &o, const uint16_t *tab,
-                         int lane) {
-    const Env e = env_view(rec, c);
+AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const ObsOut &o,
+                         const uint16_t *tab, int lane) {
+    const Env e = env_view(rec, grec, c);
     const ObsScratch s = obs_scratch_view(scratch, c);
     const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
     const double inv_scale = c.obs_scaling ? 0.01 : 1.0;

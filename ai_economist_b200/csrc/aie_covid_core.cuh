@@ -218,7 +218,12 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
             const int8_t *row = ring + (size_t)a * cv_ring_row(L1);
             int prev = row[L1 - 1];                       // predecessor of physical column 0
             for (int p0 = 0; p0 < L1; p0 += 16) {
-                const cv_b16 ld = *(const cv_b16 *)(row + p0);  // one 16-byte load
+#if CV_ON_DEVICE
+                union { int4 v; int8_t b[16]; } ld;
+                ld.v = *(const int4 *)(row + p0);               // one 16-byte load (LDG.128)
+#else
+                cv_b16 ld = *(const cv_b16 *)(row + p0);
+#endif
                 const int8_t *chunk = ld.b;
 #if CV_ON_DEVICE
 #pragma unroll

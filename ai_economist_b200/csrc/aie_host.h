@@ -190,20 +190,22 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         const int A = c.A, P = c.P;
         int off = HDR_WORDS * 4;
         auto take = [&](int bytes) { int o = off; off = align16(off + bytes); return o; };
-        c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A);
+c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A);
         c.off_bpay = take(8 * A); c.off_bskill = take(8 * A); c.off_bonus = take(8 * A);
         c.off_last_coin = take(8 * A); c.off_last_income = take(8 * A); c.off_last_marg = take(8 * A);
         c.off_util_prev = take(8 * (A + 1));
-        c.off_price_hist = take(8 * 2 * A * P);
         c.off_inv = take(4 * 2 * A); c.off_esc = take(4 * 2 * A);
         c.off_loc = take(2 * 2 * A);
         c.off_n_orders = take(2 * A); c.off_bid_hist = take(2 * A * P); c.off_ask_hist = take(2 * A * P);
         c.off_rate_idx = take(16);
         c.off_cell = take(c.HW); c.off_owner = take(c.HW);
-        c.obs_prefix_bytes = off;
-        c.off_orders = take(4 * 2 * A * c.K);
+        c.obs_prefix_bytes = off;                      // [0, here): what the observation pass reads besides price_hist
         c.off_mt = take(4 * 624);
+        c.off_price_hist = take(8 * 2 * A * P);
+        c.off_orders = take(4 * 2 * A * c.K);
         c.rec_bytes = off;
+        c.split = (c.rec_bytes > 24 * 1024) ? 1 : 0;   // records this large would leave < 8 warps per SM resident
+        c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
         c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT) + 2 * 4 * P + A * MS_COUNT + 8 + c.HW + 4);
     }

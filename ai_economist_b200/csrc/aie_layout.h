@@ -80,6 +80,9 @@ struct DevCfg {
         off_last_marg, off_util_prev, off_price_hist, off_inv, off_esc, off_loc, off_n_orders, off_bid_hist,
         off_ask_hist, off_rate_idx, off_cell, off_owner, off_orders, off_mt;
     int32_t obs_prefix_bytes, rec_bytes;
+    // Large envs (deep order books, many agents) keep the two big, sparsely touched sections - price history and
+    // order slots, laid out last - in HBM/L2 and stage only [0, resident_bytes) in shared memory (split != 0).
+    int32_t split, resident_bytes;
     // step-kernel scratch (per env, shared memory) and observe-kernel scratch
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;

@@ -59,7 +59,8 @@ int sync_all(aie_env *) { return AIE_OK; }
 int launch_finish_reset(aie_env *env, int lo, int n, void *) {
     const DevCfg &c = env->cfg;
     for (int e = lo; e < lo + n; e++) {
-        finish_reset_env(c, env->bufs.state + (size_t)e * c.rec_bytes, env->be.scratch.data(), 0);
+        finish_reset_env(c, env->bufs.state + (size_t)e * c.rec_bytes, env->bufs.state + (size_t)e * c.rec_bytes,
+                         env->be.scratch.data(), 0);
         env->bufs.done[e] = 0;
         for (int a = 0; a <= c.A; a++) env->bufs.rew[(size_t)e * (c.A + 1) + a] = 0.0;
     }
@@ -72,7 +73,7 @@ int launch_step(aie_env *env, int emit_obs, void *) {
     const DevBufs &b = env->bufs;
     for (int e = 0; e < env->n_envs; e++) {
         uint8_t *rec = b.state + (size_t)e * c.rec_bytes;
-        step_env(c, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
+        step_env(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
                  (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
                  b.rew + (size_t)e * (c.A + 1), b.done + e, 0);
         int32_t *hdr = (int32_t *)rec;
@@ -80,9 +81,10 @@ int launch_step(aie_env *env, int emit_obs, void *) {
             int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
                     episodes = hdr[HDR_EPISODES] + 1;
             memcpy(rec, b.state0 + (size_t)e * c.rec_bytes, c.off_mt);
+            memcpy(rec + c.off_price_hist, b.state0 + (size_t)e * c.rec_bytes + c.off_price_hist, c.rec_bytes - c.off_price_hist);
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
             hdr[HDR_EPISODES] = episodes;
-            finish_reset_env(c, rec, env->be.scratch.data(), 0);
+            finish_reset_env(c, rec, rec, env->be.scratch.data(), 0);
         }
     }
     env->launches++;
@@ -102,7 +104,7 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
         o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
         o.p_flat = b.p_flat + e * c.Fp; o.p_agents = b.p_agents + e * A * c.Fpa;
         o.p_mask = b.p_mask + e * c.Np; o.time_obs = b.time_obs + e;
-        observe_env(c, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
+        observe_env(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
     }
     env->launches++;
     return AIE_OK;
