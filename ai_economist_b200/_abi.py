@@ -35,6 +35,9 @@ class AieConfig(C.Structure):
         ("tax_annealing", C.c_int32), ("annealing_warmup", C.c_double), ("annealing_slope", C.c_double),
         ("rate_max", C.c_double),
         ("auto_reset", C.c_int32),
+        ("reset_mode", C.c_int32), ("build_skill_dist", C.c_int32), ("gather_skill_dist", C.c_int32),
+        ("payment_max_skill_multiplier", C.c_int32), ("fixed_four", C.c_int32),
+        ("ranked_locs", (C.c_int16 * 2) * 64), ("avg_ranked_skill", C.c_double * 64),
     ]
 
 
@@ -190,4 +193,13 @@ def config_from_spec(spec, auto_reset=True):
     for i, v in enumerate(spec["fixed_rates"]):
         cfg.fixed_rates[i] = v
     cfg.auto_reset = int(bool(auto_reset))
+    cfg.reset_mode = int(spec.get("reset_mode", 0))
+    cfg.build_skill_dist = int(spec.get("build_skill_dist", 0))
+    cfg.gather_skill_dist = int(spec.get("gather_skill_dist", 0))
+    cfg.payment_max_skill_multiplier = int(spec.get("payment_max_skill_multiplier", 1))
+    cfg.fixed_four = int(spec.get("fixed_four", 0))
+    for i, rc in enumerate(spec.get("ranked_locs", [])):
+        cfg.ranked_locs[i][0], cfg.ranked_locs[i][1] = int(rc[0]), int(rc[1])
+    for i, v in enumerate(spec.get("avg_ranked_skill", [])):
+        cfg.avg_ranked_skill[i] = float(v)
     return cfg

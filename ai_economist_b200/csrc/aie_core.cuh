@@ -789,6 +789,70 @@ AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint
     wsync();
 }
 
+// Device-side reset draws with reference semantics (reset_mode == 1; layout_from_file scenarios).  The maps,
+// inventories, books and trackers have already been restored from the load-time snapshot; this re-draws, from the
+// env's own numpy stream and in the reference's order, the random placement (layout_from_file.py:336-370),
+// the component skills (build.py:224-254, move.py:193-210) and the fixed_four assignment (:580-586).
+AIE_DEV double rng_pareto(Rng &r, double a) {  // numpy legacy_pareto: exp(-log(1 - U) / a) - 1
+    const double e = -log(1.0 - rng_double(r));
+    return exp(e / a) - 1.0;
+}
+AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
+    const int A = c.A, lane = r.lane;
+    for (int a = 0; a < A; a++) {  // np.random.randint(0, H), randint(0, W) until the cell is free and not water
+        int row = 0, col = 0;
+        for (int tries = 0; tries <= 201; tries++) {
+            row = (int)rng_interval(r, (uint32_t)(c.H - 1));
+            col = (int)rng_interval(r, (uint32_t)(c.W - 1));
+            bool blocked = (e.cell[row * c.W + col] & CELL_WATER) != 0;
+            for (int a2 = 0; a2 < a && !blocked; a2++) blocked = e.loc[2 * a2] == row && e.loc[2 * a2 + 1] == col;
+            if (!blocked) break;
+        }
+        wsync();
+        if (lane == 0) { e.loc[2 * a] = (int16_t)row; e.loc[2 * a + 1] = (int16_t)col; }
+        wsync();
+    }
+    for (int i = 0; i < c.n_comp; i++) {  // component.reset() in list order
+        if (c.comp[i] == COMP_BUILD) {
+            for (int a = 0; a < A; a++) {
+                double skill = 1.0, rate = 1.0;
+                if (c.build_skill_dist == 1) {
+                    skill = rng_pareto(r, 4.0);
+                    rate = fmin((double)c.pmsm, (double)(c.pmsm - 1) * skill + 1.0);
+                }
+                if (lane == 0) { e.bpay[a] = rate * c.build_payment; e.bskill[a] = skill; }
+            }
+        } else if (c.comp[i] == COMP_GATHER) {
+            for (int a = 0; a < A; a++) {
+                double bonus = 0.0;
+                if (c.gather_skill_dist == 1) bonus = fmin(2.0, rng_pareto(r, 3.0)) / 2.0;
+                if (lane == 0) e.bonus[a] = bonus;
+            }
+        }
+    }
+    wsync();
+    if (c.fixed_four) {
+        rng_permutation(r, s.perm, A);
+        for (int i = lane; i < A; i += NL) {
+            const int a = s.perm[i];
+            e.loc[2 * a] = c.ranked_locs[i][0]; e.loc[2 * a + 1] = c.ranked_locs[i][1];
+            e.bpay[a] = c.avg_ranked_skill[i];
+        }
+    }
+    wsync();
+}
+
+// What the step kernel does when an env finishes with auto_reset on and reset_mode == 1, after the snapshot restore.
+AIE_DEV void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
+    Env e = env_view(rec, grec, c);
+    StepScratch s = step_scratch_view(scratch, c);
+    Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
+    wsync();
+    device_reset_draws(c, e, s, r);
+    if (lane == 0) e.hdr[HDR_MT_POS] = r.pos;
+    wsync();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Observations + masks.  Warp-collective like the step body (one warp streams out its env's tensors straight
 // from the shared-memory record), serial in emulation.

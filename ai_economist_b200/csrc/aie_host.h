@@ -97,6 +97,19 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.tax_annealing = u.tax_annealing ? 1 : 0;
     c.ann_warm = u.annealing_warmup; c.ann_slope = u.annealing_slope; c.rate_max = u.rate_max;
     c.auto_reset = u.auto_reset ? 1 : 0;
+    c.reset_mode = u.reset_mode;
+    if (c.reset_mode != 0 && c.reset_mode != 1) return bad("unknown reset_mode");
+    c.build_skill_dist = u.build_skill_dist; c.gather_skill_dist = u.gather_skill_dist;
+    if (c.build_skill_dist < 0 || c.build_skill_dist > 1 || c.gather_skill_dist < 0 || c.gather_skill_dist > 1)
+        return bad("device-side reset supports skill_dist 'none' and 'pareto'");
+    c.pmsm = u.payment_max_skill_multiplier; c.fixed_four = u.fixed_four ? 1 : 0;
+    for (int i = 0; i < c.A; i++) {
+        c.ranked_locs[i][0] = u.ranked_locs[i][0]; c.ranked_locs[i][1] = u.ranked_locs[i][1];
+        c.avg_ranked_skill[i] = u.avg_ranked_skill[i];
+        if (c.reset_mode == 1 && c.fixed_four &&
+            (c.ranked_locs[i][0] < 0 || c.ranked_locs[i][0] >= c.H || c.ranked_locs[i][1] < 0 || c.ranked_locs[i][1] >= c.W))
+            return bad("fixed_four start cell outside the world");
+    }
     c.n_envs = n_envs;
 
     // action subspaces in component-list order (base_agent.py:124-169)

@@ -69,6 +69,9 @@ struct DevCfg {
     int32_t tax_annealing;
     double ann_warm, ann_slope, rate_max, ann_full;
     int32_t auto_reset;
+    int32_t reset_mode, build_skill_dist, gather_skill_dist, pmsm, fixed_four;
+    int16_t ranked_locs[64][2];
+    double avg_ranked_skill[64];
     // action subspaces in registration order (base_agent.py:97-169)
     int32_t n_sub;
     int32_t sub_kind[8], sub_c[8], sub_n[8], sub_lo[8];

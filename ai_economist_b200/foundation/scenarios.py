@@ -159,6 +159,18 @@ class LayoutFromFile(BaseScenario):
     def scenario_spec_fields(self):
         d = super().scenario_spec_fields()
         d.update(has_water=1, regen_weight=[self.regen_weight, self.regen_weight])
+        # device-side reset with reference semantics (used by auto_reset): supported for 'none' / 'pareto' skills
+        dists = {"none": 0, "pareto": 1}
+        comps = {c.name: c for c in self.env.components}
+        b, g = comps.get("Build"), comps.get("Gather")
+        ok = (b is None or b.skill_dist in dists) and (g is None or g.skill_dist in dists)
+        d.update(reset_mode=1 if ok else 0,
+                 build_skill_dist=dists.get(b.skill_dist, 0) if b else 0,
+                 gather_skill_dist=dists.get(g.skill_dist, 0) if g else 0,
+                 payment_max_skill_multiplier=b.payment_max_skill_multiplier if b else 1,
+                 fixed_four=int(self.fixed_four_skill_and_loc),
+                 ranked_locs=[list(map(int, rc)) for rc in getattr(self, "_ranked_locs", [])],
+                 avg_ranked_skill=[float(v) for v in getattr(self, "_avg_ranked_skill", [])])
         return d
 
 

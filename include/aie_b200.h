@@ -96,6 +96,16 @@ typedef struct aie_config {
     int32_t auto_reset;             /* 1: an env that reaches episode_length is restored from its load-time
                                        snapshot inside the same step (WarpDrive save_copy_and_apply_at_reset
                                        semantics, env_wrapper.py:299-337); its numpy-legacy RNG stream continues */
+    /* Device-side reset with reference semantics (used by auto_reset when reset_mode == 1): re-draws, from the
+     * env's own numpy stream, what LayoutFromFile's reset draws - random placement
+     * (layout_from_file.py:336-370), Build / Gather skills (build.py:224-254, move.py:193-210) and the
+     * fixed_four_skill_and_loc assignment (layout_from_file.py:580-586) - instead of re-using the snapshot's. */
+    int32_t reset_mode;             /* 0: restore the load-time snapshot; 1: reference-exact layout_from_file reset */
+    int32_t build_skill_dist, gather_skill_dist;  /* 0 "none", 1 "pareto" */
+    int32_t payment_max_skill_multiplier;
+    int32_t fixed_four;             /* fixed_four_skill_and_loc */
+    int16_t ranked_locs[AIE_MAX_AGENTS][2];       /* start cell of the i-th skill-ranked slot */
+    double avg_ranked_skill[AIE_MAX_AGENTS];      /* build payment of the i-th skill-ranked slot */
 } aie_config;
 
 /* Sizes the caller needs to allocate the device buffers. */

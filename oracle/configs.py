@@ -83,4 +83,23 @@ CONFIGS = {
         multi_action_mode_agents=True, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True,
         starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
+    # short episodes for the multi-episode (device-side reset) traces
+    "c1_reset": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone", components=_GTB,
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=10,
+        fixed_four_skill_and_loc=True, n_agents=4, world_size=[25, 25], episode_length=25,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
+    "c3_reset": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=10, rate_disc=0.05,
+                                                tax_model="model_wrapper",
+                                                tax_annealing_schedule=[-100, 0.001]))],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5,
+        fixed_four_skill_and_loc=False, n_agents=6, world_size=[25, 25], episode_length=30,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True, energy_warmup_constant=5, energy_warmup_method="decay"),
 }

@@ -32,6 +32,9 @@ PLAN = [
     ("ref_unit_test", 1001, 100, 10),
     ("c5_small", 1001, 150, 25),
     ("c5_full", 1001, 60, 20),
+    # multi-episode traces (env.reset() between episodes, the global numpy stream continues): device-side reset
+    ("c1_reset", 1001, 80, 10),
+    ("c3_reset", 1001, 95, 10),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]
@@ -89,6 +92,8 @@ def generate(cfg_name, seed, steps, full_every):
     for t in range(1, steps + 1):
         actions, a_act, p_act = rh.sample_actions(env, obs, arng)
         obs, rew, done, _ = env.step(actions)
+        if done["__all__"] and t < steps:
+            obs = env.reset()   # reference semantics: a fresh episode drawn from the same (continuing) global stream
         acts_a.append(a_act)
         acts_p.append(p_act)
         snapshot(t, obs, rew, done, force_full=(t == steps))
@@ -108,7 +113,9 @@ def generate(cfg_name, seed, steps, full_every):
             if k in ("a_map", "p_map"):
                 arr = arr.astype(np.uint8)  # 0/1-valued float32 planes: stored as u8, compared after cast
             out["full_" + k] = arr
-    path = os.path.join(OUT, "%s_seed%d.npz" % (cfg_name, seed))
+    out_dir = OUT + "_reset" if cfg_name.endswith("_reset") else OUT   # multi-episode traces live apart
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, "%s_seed%d.npz" % (cfg_name, seed))
     np.savez_compressed(path, **out)
     print("%s: %d steps, %.1f KB" % (path, steps, os.path.getsize(path) / 1024))
 

@@ -84,6 +84,7 @@ int launch_step(aie_env *env, int emit_obs, void *) {
             memcpy(rec + c.off_price_hist, b.state0 + (size_t)e * c.rec_bytes + c.off_price_hist, c.rec_bytes - c.off_price_hist);
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
             hdr[HDR_EPISODES] = episodes;
+            if (c.reset_mode == 1) device_reset_env(c, rec, rec, env->be.scratch.data(), 0);
             finish_reset_env(c, rec, rec, env->be.scratch.data(), 0);
         }
     }

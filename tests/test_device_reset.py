@@ -1,0 +1,61 @@
+"""Device-side reset with reference semantics.
+
+Multi-episode golden traces (tests/golden_reset/, recorded from the unmodified reference with env.reset() between
+episodes — the reference keeps drawing from the same global numpy stream) are replayed through the public API with
+auto_reset on: when an env finishes, the step kernel restores maps / inventories / books from the snapshot and then
+re-draws placement, skills and the fixed_four assignment from the env's own MT19937 stream on the device.  Rewards
+and done of the terminal step belong to the finished episode; state and observations to the fresh one.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from ai_economist_b200 import foundation
+from tests import golden_utils as gu
+
+FILES = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_reset", "*.npz")))
+
+
+def _env(meta, factory):
+    kw = dict(meta["reference_kwargs"])
+    name = kw.pop("scenario_name")
+    kw["components"] = [tuple(c) for c in kw["components"]]
+    extra = dict(stepper_factory=factory) if factory else dict(device="cuda:0")
+    return foundation.make_env_instance(name, n_envs=2, auto_reset=True, **kw, **extra)
+
+
+def _replay(path, factory):
+    z, meta, init = gu.load_fixture(path)
+    env = _env(meta, factory)
+    assert env.spec["reset_mode"] == 1
+    env.seed([meta["seed"], meta["seed"]])     # both replicas identical: checks env indexing too
+    env.reset()
+    s = env.stepper
+    full = {int(t): i for i, t in enumerate(z["full_steps"])}
+    A = env.n_agents
+    n_done = 0
+    gu.check_step(z, 0, s.read_obs(1), s.read_state(1), full.get(0), "reset-trace")
+    for t in range(1, int(meta["n_steps"]) + 1):
+        acts = {str(i): np.repeat(z["act_a"][t - 1][i][None], 2, axis=0) for i in range(A)}
+        if z["act_p"].shape[1]:
+            acts["p"] = np.repeat(z["act_p"][t - 1][None], 2, axis=0)
+        env.step(acts)
+        st = s.read_state(1)
+        gu.check_step(z, t, s.read_obs(1), st, full.get(t), "reset-trace", books=st["books"])
+        n_done += int(z["step_done"][t])
+    assert n_done >= 2, "the trace must cross at least two episode boundaries"
+    assert int(s.read_state(1)["completions"][0]) == n_done
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p))
+def test_emulated_device_reset_matches_reference_across_episodes(path):
+    from tests.emu.emu_stepper import emu_factory
+    _replay(path, emu_factory)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p))
+def test_cuda_device_reset_matches_reference_across_episodes(path):
+    _replay(path, None)
