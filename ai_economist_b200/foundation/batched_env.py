@@ -2,7 +2,7 @@
 (base/base_env.py:24-1120), over E env replicas that live on one B200.
 
 Differences from the reference API (all additive):
-  * new kwargs `n_envs`, `device`, `seeds`, `auto_reset`;
+  * new kwargs `n_envs`, `device`, `seeds`, `auto_reset`, `device_reset`;
   * observations / rewards / done are persistent device tensors with a leading env axis, keyed exactly like
     the reference's dicts ("0".."n-1", "p"; "world-map", "world-idx_map", "flat", "action_mask", "time", "p<i>");
   * `reference_view(e)` re-creates the reference's nested numpy dict for one env (tests / debugging).
@@ -64,7 +64,8 @@ class BatchedFoundationEnv:
                  multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True,
                  flatten_masks=True, allow_observation_scaling=True, dense_log_frequency=None,
                  world_dense_log_frequency=50, collate_agent_step_and_reset_data=False, seed=None,
-                 n_envs=1, device="cuda:0", seeds=None, auto_reset=True, stepper_factory=None, **scenario_kwargs):
+                 n_envs=1, device="cuda:0", seeds=None, auto_reset=True, stepper_factory=None, device_reset=None,
+                 **scenario_kwargs):
         # ---- base_env.py:178-366 argument checks ----
         assert isinstance(world_size, (tuple, list)) and len(world_size) == 2
         self.world_size = list(world_size)
@@ -145,6 +146,12 @@ class BatchedFoundationEnv:
         spec.update(self.scenario.scenario_spec_fields())
         for c in self._components:
             spec.update(c.spec_fields())
+        if device_reset is not None:  # "reference" (default where supported) | "snapshot" (WarpDrive-style restore)
+            assert device_reset in ("reference", "snapshot")
+            if device_reset == "snapshot":
+                spec["reset_mode"] = 0
+            else:
+                assert spec.get("reset_mode", 0) == 1, "reference-exact device reset is not available for this config"
         self._spec = spec
 
         if stepper_factory is None:

@@ -108,7 +108,7 @@ def test_auto_reset_restores_snapshot_and_continues_stream():
     step (WarpDrive save_copy_and_apply_at_reset semantics); the numpy-legacy stream carries on."""
     from oracle.oracle import OracleBatch
     E, T = 16, 12
-    env = _make_env("c1_tutorial", E, seed=77, auto_reset=True, episode_length=T)
+    env = _make_env("c1_tutorial", E, seed=77, auto_reset=True, episode_length=T, device_reset="snapshot")
     orc, host = _load_both(env)
     rng = np.random.RandomState(5)
     bu.run_pair(env, orc, T - 1, rng, check_every=T - 1)
