@@ -120,7 +120,7 @@ __device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b,
 
 // ---------------------------------------------------------------------------------------------------------
 // MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
-template <int MINB>
+template <int MINB, bool BIG>
 __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
                                                               const int emit_obs) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
 
     const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
     const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
-    step_env(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
+    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
 
     // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
     // from the load-time snapshot; the episode counters and the numpy stream carry on.
@@ -282,9 +282,12 @@ int init(aie_env *env) {
     int fit = (int)(smem_sm / (env->be.step_smem + 1024));
     env->be.step_minb = fit >= 5 ? 5 : (fit >= 4 ? 4 : 3);
     if (const char *ov = getenv("AIE_STEP_MINB")) { int v = atoi(ov); if (v >= 3 && v <= 5) env->be.step_minb = v; }
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
+    const int sm = (int)env->be.step_smem;
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     {
         AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(Tables)), "cudaMalloc tables");
         AIE_CUDA(cudaMemcpy(env->be.tab_dev, env->tables.w, sizeof(Tables), cudaMemcpyHostToDevice), "upload tables");
@@ -327,9 +330,13 @@ int launch_step(aie_env *env, int emit_obs, void *stream) {
     const int wpb = env->be.step_wpb;
     const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;
-    if (env->be.step_minb == 5) aie_step_kernel<5><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs, emit_obs);
-    else if (env->be.step_minb == 4) aie_step_kernel<4><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs, emit_obs);
-    else aie_step_kernel<3><<<grid, block, env->be.step_smem, st>>>(env->cfg, env->bufs, emit_obs);
+    const size_t sm = env->be.step_smem;
+    if (env->cfg.split) {  // large envs: order slots / price history in global memory, latency-tolerant scans
+        if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    else aie_step_kernel<3, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
     AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
     env->launches++;
     return AIE_OK;

@@ -307,16 +307,33 @@ AIE_DEV int order_birth(uint32_t o) { return (int)(o >> 8); }
 AIE_DEV int order_price(uint32_t o) { return (int)((o >> 1) & 127u); }
 AIE_DEV int order_side(uint32_t o) { return (int)(o & 1u); }
 
+// BIG: the order slots live in global memory (split record).  Scans then avoid early exits and are unrolled so
+// that ~10 independent loads are in flight per lane instead of one L2 round trip per slot.
+template <bool BIG>
 AIE_DEV void order_insert(uint32_t *slots, int K, uint32_t o) {
+    if (!BIG) {
+        for (int k = 0; k < K; k++)
+            if (slots[k] == ORDER_EMPTY) { slots[k] = o; return; }
+        return;
+    }
+    int pos = K;
+#if AIE_ON_DEVICE
+    AIE_UNROLL(10)
+#endif
     for (int k = 0; k < K; k++)
-        if (slots[k] == ORDER_EMPTY) { slots[k] = o; return; }
+        if (slots[k] == ORDER_EMPTY && k < pos) pos = k;
+    if (pos < K) slots[pos] = o;
 }
 
 // :440-489 first half — price-history decay and order creation (create_bid :168-198, create_ask :200-229).
 // Each agent only touches its own state, so agents run lane-parallel; agent-index order of the reference's
 // loop survives as the final tie-break of the matching key.
+template <bool BIG>
 AIE_DEV void cda_create(const DevCfg &c, Env &e, const StepScratch &s, int t, int lane) {
     const int A = c.A, P = c.P, K = c.K;
+#if AIE_ON_DEVICE
+    AIE_UNROLL(4)
+#endif
     for (int i = lane; i < 2 * A * P; i += NL) e.price_hist[i] *= 0.995;  // independent of order creation
     for (int a = lane; a < A; a += NL) {
         for (int cc = 0; cc < 2; cc++) {
@@ -325,7 +342,7 @@ AIE_DEV void cda_create(const DevCfg &c, Env &e, const StepScratch &s, int t, in
             if (kb != 0) {
                 int price = kb - 1;
                 if (e.n_orders[cc * A + a] < K && e.coin[a] >= (double)price) {
-                    order_insert(slots, K, order_pack(t, price, 0));
+                    order_insert<BIG>(slots, K, order_pack(t, price, 0));
                     e.bid_hist[(cc * A + a) * P + price] += 1;
                     e.n_orders[cc * A + a] += 1;
                     e.coin[a] -= (double)price;
@@ -337,7 +354,7 @@ AIE_DEV void cda_create(const DevCfg &c, Env &e, const StepScratch &s, int t, in
             if (ks != 0) {
                 int price = ks - 1;
                 if (e.n_orders[cc * A + a] < K && e.inv[2 * a + cc] > 0) {
-                    order_insert(slots, K, order_pack(t, price, 1));
+                    order_insert<BIG>(slots, K, order_pack(t, price, 1));
                     e.ask_hist[(cc * A + a) * P + price] += 1;
                     e.n_orders[cc * A + a] += 1;
                     e.inv[2 * a + cc] -= 1;
@@ -379,6 +396,7 @@ AIE_DEV void refresh_best(const DevCfg &c, const uint32_t *slots, int a, int sid
     if (lane == 0) { best_key[a] = m; best_slot[a] = bs; }
 }
 
+template <bool BIG>
 AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int lane) {
     const int A = c.A, P = c.P, K = c.K, n = A * K;
     uint32_t *bb_key = s.book, *bb_slot = s.book + A, *ba_key = s.book + 2 * A, *ba_slot = s.book + 3 * A;
@@ -387,6 +405,9 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int
         // one pass over the book: lane-per-agent scan of its K slots
         for (int a = lane; a < A; a += NL) {
             uint32_t bk = 0, bs = 0, ak = 0, as = 0;
+#if AIE_ON_DEVICE
+            AIE_UNROLL(BIG ? 10 : 1)
+#endif
             for (int k = 0; k < K; k++) {
                 const uint32_t o = slots[a * K + k];
                 if (o == ORDER_EMPTY) continue;
@@ -445,6 +466,7 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int
 }
 
 // remove_expired_orders :352-406.  lifetime after the increment is t - birth + 1; expired iff > D.
+template <bool BIG>
 AIE_DEV void cda_expire(const DevCfg &c, Env &e, int t, int lane) {
     const int A = c.A, P = c.P, K = c.K;
     for (int a = lane; a < A; a += NL) {
@@ -452,6 +474,9 @@ AIE_DEV void cda_expire(const DevCfg &c, Env &e, int t, int lane) {
             uint32_t *slots = e.orders + (cc * A + a) * K;
             // an agent creates at most one bid and one ask per commodity per step, so at most one of each
             // expires here; they touch different state (coin vs. the commodity), so one pass is order-safe
+#if AIE_ON_DEVICE
+            AIE_UNROLL(BIG ? 10 : 1)
+#endif
             for (int k = 0; k < K; k++) {
                 uint32_t o = slots[k];
                 if (o == ORDER_EMPTY || t - order_birth(o) < c.D) continue;
@@ -745,6 +770,7 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 // ------------------------------------------------------------------------------------------------
 // One env.step() (base/base_env.py:929-1032) without the observation pass.
 // ------------------------------------------------------------------------------------------------
+template <bool BIG>
 AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
                       const int32_t *act_p, double *rew_out, int32_t *done_out, int lane) {
     Env e = env_view(rec, grec, c);
@@ -757,7 +783,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
     for (int i = 0; i < c.n_comp; i++) {
         switch (c.comp[i]) {
             case COMP_BUILD: build_step(c, e, s, r); break;
-            case COMP_CDA: cda_create(c, e, s, t, lane); cda_match(c, e, s, t, lane); cda_expire(c, e, t, lane); break;
+            case COMP_CDA: cda_create<BIG>(c, e, s, t, lane); cda_match<BIG>(c, e, s, t, lane); cda_expire<BIG>(c, e, t, lane); break;
             case COMP_GATHER: gather_step(c, e, s, r); break;
             case COMP_TAX: tax_step(c, e, s, lane); break;
         }

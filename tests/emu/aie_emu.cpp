@@ -73,7 +73,10 @@ int launch_step(aie_env *env, int emit_obs, void *) {
     const DevBufs &b = env->bufs;
     for (int e = 0; e < env->n_envs; e++) {
         uint8_t *rec = b.state + (size_t)e * c.rec_bytes;
-        step_env(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
+        if (c.split) step_env<true>(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
+                 (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
+                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0);
+        else step_env<false>(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
                  (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
                  b.rew + (size_t)e * (c.A + 1), b.done + e, 0);
         int32_t *hdr = (int32_t *)rec;
