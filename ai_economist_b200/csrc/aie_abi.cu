@@ -90,7 +90,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ int tab_smem_bytes(const DevCfg &c) { return (2 * c.tab_n + 15) & ~15; }
 __device__ __forceinline__ uint8_t *warp_region(uint8_t *smem, int wpb, int warp, const DevCfg &c) {
     return smem + ((8 * wpb + 15) & ~15) + tab_smem_bytes(c) +
-           (size_t)warp * (c.resident_bytes + c.step_scratch_bytes + c.obs_scratch_bytes);
+           (size_t)warp * (c.resident_bytes + c.step_scratch_bytes + c.obs_extra_bytes);
 }
 // The programs are indexed by the lane-varying flat position; reading them from global memory costs an L2 round
 // trip per access here because the L1 carve-out is almost entirely shared memory.  One cooperative copy per CTA.
@@ -179,10 +179,13 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     fence_async_smem();  // generic-proxy writes to the record -> visible to the bulk (async-proxy) store
     __syncwarp();
     if (lane == 0) bulk_s2g(grec, rec, (uint32_t)c.resident_bytes);
-    // observations / masks of the post-step state stream out of the same shared-memory record while the bulk
-    // store drains (both only read the record)
-    if (emit_obs) observe_env(c, rec, grec, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
-    if (lane == 0) bulk_wait_read();
+    // Observations / masks of the post-step state stream out of the same shared-memory record.  When the staging
+    // area aliases the MT19937 key image, the bulk store must have finished READING shared memory first; otherwise
+    // the store drains while the observations are written (both only read the record).
+    if (c.obs_alias_mt) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
+    uint8_t *obs_scratch = c.obs_alias_mt ? rec + c.off_mt : scratch + c.step_scratch_bytes;
+    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, env), tab, lane);
+    if (!c.obs_alias_mt && lane == 0) bulk_wait_read();
 }
 
 __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    observe_env(c, rec, grec, rec + c.resident_bytes + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
+    observe_env(c, rec, grec, c.obs_alias_mt ? rec + c.off_mt : rec + c.resident_bytes + c.step_scratch_bytes,
+                obs_out_for(c, b, env), tab, lane);
 }
 
 __global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed) {
@@ -267,7 +271,7 @@ int init(aie_env *env) {
     if (prop.major < 10) return fail(AIE_ECUDA, "this build targets sm_100a (Blackwell B200) only");
     const DevCfg &c = env->cfg;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
-    const size_t per_env = (size_t)c.resident_bytes + c.step_scratch_bytes + c.obs_scratch_bytes;
+    const size_t per_env = (size_t)c.resident_bytes + c.step_scratch_bytes + c.obs_extra_bytes;
     int wpb = 8;
     if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4 || v == 8) wpb = v; }
     const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;

@@ -86,6 +86,9 @@ struct DevCfg {
     // Large envs (deep order books, many agents) keep the two big, sparsely touched sections - price history and
     // order slots, laid out last - in HBM/L2 and stage only [0, resident_bytes) in shared memory (split != 0).
     int32_t split, resident_bytes;
+    // The observation pass runs after the record has been written back, when the MT19937 key's shared-memory image
+    // is dead: its 2496 bytes double as the observation staging area when that fits (obs_alias_mt).
+    int32_t obs_alias_mt, obs_extra_bytes;
     // step-kernel scratch (per env, shared memory) and observe-kernel scratch
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;

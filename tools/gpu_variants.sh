@@ -12,10 +12,10 @@ print("$label value %.3e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: rou
 PY
 }
 run base X=1
-run u1 AIE_LIB_PATH=$PWD/ai_economist_b200/csrc/libaie_b200_u1.so
-run u4 AIE_LIB_PATH=$PWD/ai_economist_b200/csrc/libaie_b200_u4.so
-run u8 AIE_LIB_PATH=$PWD/ai_economist_b200/csrc/libaie_b200_u8.so
-run wpb4 AIE_STEP_WPB=4
-run wpb2 AIE_STEP_WPB=2
+
+
+
+
+
 run minb3 AIE_STEP_MINB=3
 run minb5 AIE_STEP_MINB=5
