@@ -26,7 +26,6 @@ namespace be {
 struct State {
     int step_wpb;        // warps (envs) per CTA of the step kernel
     int step_minb;       // register-allocation variant of the step kernel (3, 4 or 5 CTAs per SM)
-    int phase_sync;      // align the warps of a CTA at phase boundaries (instruction-cache sharing)
     size_t step_smem;    // dynamic shared memory per CTA
     int obs_threads;
     size_t obs_smem;
@@ -121,16 +120,14 @@ __device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b,
 
 // ---------------------------------------------------------------------------------------------------------
 // MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
-template <int MINB, bool BIG, int MAXT = 256>
-__global__ void __launch_bounds__(MAXT, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
-                                                               const int emit_obs, const int phase_sync) {
+template <int MINB, bool BIG>
+__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
+                                                              const int emit_obs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * wpb + warp;
     const uint16_t *tab = stage_tables(smem, wpb, c, b);
-    if (env >= c.n_envs) return;  // from here on warps only meet at the (optional) phase-alignment barriers
-    const int active = min(wpb, c.n_envs - (int)blockIdx.x * wpb);
-    const int pthr = phase_sync ? active * 32 : 0;
+    if (env >= c.n_envs) return;  // from here on warps are independent: no block-wide barrier below
     uint64_t *bar = (uint64_t *)smem + warp;
     uint8_t *rec = warp_region(smem, wpb, warp, c);
     uint8_t *scratch = rec + c.resident_bytes;
@@ -146,7 +143,7 @@ __global__ void __launch_bounds__(MAXT, MINB) aie_step_kernel(const __grid_const
 
     const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
     const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
-    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane, pthr);
+    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
 
     // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
     // from the load-time snapshot; the episode counters and the numpy stream carry on.
@@ -187,8 +184,7 @@ __global__ void __launch_bounds__(MAXT, MINB) aie_step_kernel(const __grid_const
     // the store drains while the observations are written (both only read the record).
     if (c.obs_alias_mt) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
     uint8_t *obs_scratch = c.obs_alias_mt ? rec + c.off_mt : scratch + c.step_scratch_bytes;
-    psync(pthr);
-    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, env), tab, lane, pthr);
+    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, env), tab, lane);
     if (!c.obs_alias_mt && lane == 0) bulk_wait_read();
 }
 
@@ -277,37 +273,31 @@ int init(aie_env *env) {
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_env = (size_t)c.resident_bytes + c.step_scratch_bytes + c.obs_extra_bytes;
     int wpb = 8;
-    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) wpb = v; }
+    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4 || v == 8) wpb = v; }
     const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;
-    const bool wpb_forced = getenv("AIE_STEP_WPB") != nullptr;
-    while (!wpb_forced && wpb > 1 && align16(8 * wpb) + tabs + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
-    while (wpb > 1 && align16(8 * wpb) + tabs + wpb * per_env > max_smem) wpb >>= 1;
+    while (wpb > 1 && align16(8 * wpb) + tabs + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
     if (align16(8 * wpb) + tabs + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
     env->be.step_wpb = wpb;
     env->be.step_smem = align16(8 * wpb) + tabs + wpb * per_env;
-    const int aux_wpb = wpb > 8 ? 8 : wpb;  // finish-reset / stand-alone observe kernels: at most 256 threads
-    env->be.obs_threads = aux_wpb * 32;
-    env->be.obs_smem = align16(8 * aux_wpb) + tabs + aux_wpb * per_env;
+    env->be.obs_threads = wpb * 32;
+    env->be.obs_smem = env->be.step_smem;
     // pick the variant with the most resident warps that shared memory allows (override: AIE_STEP_MINB=3|4|5)
     const size_t smem_sm = prop.sharedMemPerMultiprocessor;
     int fit = (int)(smem_sm / (env->be.step_smem + 1024));
     env->be.step_minb = fit >= 5 ? 5 : (fit >= 4 ? 4 : 3);
     if (const char *ov = getenv("AIE_STEP_MINB")) { int v = atoi(ov); if (v >= 3 && v <= 5) env->be.step_minb = v; }
-    env->be.phase_sync = 0;
-    if (const char *ov = getenv("AIE_PHASE_SYNC")) env->be.phase_sync = atoi(ov) ? 1 : 0;
     const int sm = (int)env->be.step_smem;
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<1, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     {
         AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(Tables)), "cudaMalloc tables");
         AIE_CUDA(cudaMemcpy(env->be.tab_dev, env->tables.w, sizeof(Tables), cudaMemcpyHostToDevice), "upload tables");
         env->bufs.tab = env->be.tab_dev;
     }
-    AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
     return AIE_OK;
 }
@@ -334,8 +324,8 @@ int sync_all(aie_env *) {
     return AIE_OK;
 }
 int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
-    const int wpb = env->be.obs_threads / 32;
-    aie_finish_reset_kernel<<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
+    const int wpb = env->be.step_wpb;
+    aie_finish_reset_kernel<<<(n + wpb - 1) / wpb, wpb * 32, env->be.step_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
     AIE_CUDA(cudaGetLastError(), "aie_finish_reset_kernel launch");
     env->launches++;
     return AIE_OK;
@@ -345,20 +335,18 @@ int launch_step(aie_env *env, int emit_obs, void *stream) {
     const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = env->be.step_smem;
-    if (wpb > 8) {  // experiment: one large CTA per SM (AIE_STEP_WPB=16|32), phase-aligned
-        aie_step_kernel<1, false, 1024><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs, env->be.phase_sync);
-    } else if (env->cfg.split) {  // large envs: order slots / price history in global memory, latency-tolerant scans
-        if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs, env->be.phase_sync);
-        else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs, env->be.phase_sync);
-    } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs, env->be.phase_sync);
-    else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs, env->be.phase_sync);
-    else aie_step_kernel<3, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs, env->be.phase_sync);
+    if (env->cfg.split) {  // large envs: order slots / price history in global memory, latency-tolerant scans
+        if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    else aie_step_kernel<3, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
     AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
     env->launches++;
     return AIE_OK;
 }
 int launch_observe(aie_env *env, int lo, int n, void *stream) {
-    const int wpb = env->be.obs_threads / 32;
+    const int wpb = env->be.step_wpb;
     aie_observe_kernel<<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
     AIE_CUDA(cudaGetLastError(), "aie_observe_kernel launch");
     env->launches++;

@@ -62,10 +62,6 @@ AIE_DEV double wsum(double v) {
     return v;
 }
 AIE_DEV int first_lane(uint32_t m) { return __ffs(m) - 1; }
-// Phase alignment across the warps (envs) of a CTA: no data is exchanged, the barrier only keeps the warps in the
-// same region of this large kernel at the same time so that they share instruction-cache lines.  nthr = 32 x
-// (active warps of the CTA); 0 disables it.
-AIE_DEV void psync(int nthr) { if (nthr > 32) asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
 AIE_DEV int __popc_u32(uint32_t m) { return __popc(m); }
 #else
 constexpr int NL = 1;
@@ -76,7 +72,6 @@ AIE_DEV uint32_t wshfl(uint32_t v, int) { return v; }
 AIE_DEV bool wany(bool p) { return p; }
 AIE_DEV double wsum(double v) { return v; }
 AIE_DEV int first_lane(uint32_t m) { return m ? 0 : -1; }
-AIE_DEV void psync(int) {}
 AIE_DEV int __popc_u32(uint32_t m) { return __builtin_popcount(m); }
 #endif
 
@@ -777,7 +772,7 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 // ------------------------------------------------------------------------------------------------
 template <bool BIG>
 AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
-                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane, int pthr = 0) {
+                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     decode_actions(c, s, act_a, act_p, lane);
@@ -786,7 +781,6 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
     wsync();
     if (lane == 0) e.hdr[HDR_T] = t;
     for (int i = 0; i < c.n_comp; i++) {
-        psync(pthr);
         switch (c.comp[i]) {
             case COMP_BUILD: build_step(c, e, s, r); break;
             case COMP_CDA: cda_create<BIG>(c, e, s, t, lane); cda_match<BIG>(c, e, s, t, lane); cda_expire<BIG>(c, e, t, lane); break;
@@ -797,9 +791,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
 #if AIE_ON_DEVICE
 #pragma unroll 1
 #endif
-    psync(pthr);
     for (int ri = 0; ri < 2; ri++) regen_resource(c, e, 1 - ri, r);  // Wood, then Stone (one inlined copy)
-    psync(pthr);
     compute_reward(c, e, s, rew_out, lane);
     if (lane == 0) {
         e.hdr[HDR_MT_POS] = r.pos;
@@ -931,7 +923,7 @@ AIE_DEV float flat_emit(const DevCfg &c, const Env &e, const ObsScratch &s, uint
 }
 
 AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const ObsOut &o,
-                         const uint16_t *tab, int lane, int pthr = 0) {
+                         const uint16_t *tab, int lane) {
     const Env e = env_view(rec, grec, c);
     const ObsScratch s = obs_scratch_view(scratch, c);
     const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
@@ -1028,7 +1020,6 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     }
     wsync();
 
-    psync(pthr);
     // ---- phase 2: outputs ----------------------------------------------------------------------
     // Consecutive lanes write consecutive addresses; no division by a run-time constant in the loops.
     // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc)
@@ -1053,7 +1044,6 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             o.p_idx[HW + k] = (int16_t)s.locmap[k];
         }
     }
-    psync(pthr);
     // agent windows (layout_from_file.py:468-515): per agent, one lane per window cell; the cell is read once
     // and fans out to the M+1 map channels and the 2 index channels
     {
@@ -1095,7 +1085,6 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             }
         }
     }
-    psync(pthr);
     // flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
     for (int a = 0; a < A; a++) {
         for (int j = lane; j < c.Fa; j += NL) o.a_flat[a * c.Fa + j] = flat_emit(c, e, s, tab[j], a);
