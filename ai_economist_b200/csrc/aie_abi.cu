@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     // the store drains while the observations are written (both only read the record).
     if (c.obs_alias_mt) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
     uint8_t *obs_scratch = c.obs_alias_mt ? rec + c.off_mt : scratch + c.step_scratch_bytes;
-    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, env), tab, lane);
+    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, emit_obs == 2 ? (env & 63) : env), tab, lane);
     if (!c.obs_alias_mt && lane == 0) bulk_wait_read();
 }
 
@@ -281,10 +281,12 @@ int init(aie_env *env) {
     env->be.step_smem = align16(8 * wpb) + tabs + wpb * per_env;
     env->be.obs_threads = wpb * 32;
     env->be.obs_smem = env->be.step_smem;
-    // pick the variant with the most resident warps that shared memory allows (override: AIE_STEP_MINB=3|4|5)
+    // 4 resident CTAs per SM when shared memory allows: measured fastest on B200 (c2: 182 us; 3 CTAs 192 us, 5 CTAs
+    // 213 us - the tighter register budget of the 5-CTA variant costs more than its extra warps hide).  Override:
+    // AIE_STEP_MINB=3|4|5.
     const size_t smem_sm = prop.sharedMemPerMultiprocessor;
     int fit = (int)(smem_sm / (env->be.step_smem + 1024));
-    env->be.step_minb = fit >= 5 ? 5 : (fit >= 4 ? 4 : 3);
+    env->be.step_minb = fit >= 4 ? 4 : 3;
     if (const char *ov = getenv("AIE_STEP_MINB")) { int v = atoi(ov); if (v >= 3 && v <= 5) env->be.step_minb = v; }
     const int sm = (int)env->be.step_smem;
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
@@ -331,6 +333,7 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
     return AIE_OK;
 }
 int launch_step(aie_env *env, int emit_obs, void *stream) {
+    if (emit_obs && getenv("AIE_DEBUG_OBS_FOLD")) emit_obs = 2;  // EXPERIMENT
     const int wpb = env->be.step_wpb;
     const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;

@@ -63,6 +63,8 @@ AIE_DEV double wsum(double v) {
 }
 AIE_DEV int first_lane(uint32_t m) { return __ffs(m) - 1; }
 AIE_DEV int __popc_u32(uint32_t m) { return __popc(m); }
+AIE_DEV uint32_t fshr(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }  // sh in [0, 31]
+AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 #else
 constexpr int NL = 1;
 AIE_DEV void wsync() {}
@@ -73,6 +75,13 @@ AIE_DEV bool wany(bool p) { return p; }
 AIE_DEV double wsum(double v) { return v; }
 AIE_DEV int first_lane(uint32_t m) { return m ? 0 : -1; }
 AIE_DEV int __popc_u32(uint32_t m) { return __builtin_popcount(m); }
+AIE_DEV uint32_t fshr(uint32_t lo, uint32_t hi, int sh) { return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFFu) << (8 * i);
+    return r;
+}
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -891,6 +900,7 @@ struct ObsScratch {
     uint16_t *full_asks, *full_bids;  // [2][P]
     uint8_t *lim;         // [A][MS_COUNT] mask limits: mask[j] = idx_j < lim[slot_j]
     uint8_t *locmap;      // [HW]  0 none, a+2
+    uint8_t *wstage;      // [3][ww] one agent's window: cell bits | 0x40 inside, owner code, agent-location code
 };
 AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
     ObsScratch s;
@@ -900,7 +910,8 @@ AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
     s.full_asks = (uint16_t *)p;  p += 2 * 2 * c.P;
     s.full_bids = (uint16_t *)p;  p += 2 * 2 * c.P;
     s.lim = p;                    p += (c.A * MS_COUNT + 7) & ~7;
-    s.locmap = p;  // 4-byte aligned, padded to a multiple of 4 bytes
+    s.locmap = p;                 p += (c.HW + 3) & ~3;  // 4-byte aligned, padded to a multiple of 4 bytes
+    s.wstage = p;
     return s;
 }
 
@@ -908,6 +919,92 @@ struct ObsOut {  // pointers already offset to this env
     float *a_map; int16_t *a_idx; float *a_flat; float *a_mask;
     float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask; float *time_obs;
 };
+
+// Contiguous output runs are written FRONT TO BACK with 16-byte stores: lanes take the 16-byte groups of the global
+// address space (whatever the run's own alignment); the few elements before the first / after the last whole group
+// are stored one by one.  Measured on B200 (tools/wpattern.cu): one warp streaming its slice in address order reaches
+// 5.5 TB/s where the same bytes written cell-major (each cell fanning out to every channel plane) reach 3.6 TB/s.
+struct RunSplit { int head, nq, tail0; };
+AIE_DEV RunSplit run_split(const void *dst, int n, int elem_log2) {
+    const int per = 16 >> elem_log2;  // elements per 16-byte group
+    RunSplit r;
+    r.head = (int)((per - (((uintptr_t)dst >> elem_log2) & (per - 1))) & (per - 1));
+    if (r.head > n) r.head = n;
+    r.nq = (n - r.head) / per;
+    r.tail0 = r.head + r.nq * per;
+    return r;
+}
+AIE_DEV void store4(float *p, float v0, float v1, float v2, float v3) {
+#if AIE_ON_DEVICE
+    *reinterpret_cast<float4 *>(p) = make_float4(v0, v1, v2, v3);
+#else
+    p[0] = v0; p[1] = v1; p[2] = v2; p[3] = v3;
+#endif
+}
+AIE_DEV void store8(int16_t *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {  // 8 int16, little endian
+#if AIE_ON_DEVICE
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w0, w1, w2, w3);
+#else
+    const uint32_t w[4] = {w0, w1, w2, w3};
+    for (int j = 0; j < 8; j++) p[j] = (int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
+#endif
+}
+template <typename F>
+AIE_DEV void store_run_f32(float *dst, int n, int lane, F value_at) {
+    const RunSplit r = run_split(dst, n, 2);
+    for (int i = lane; i < r.head; i += NL) dst[i] = value_at(i);
+    for (int i = r.tail0 + lane; i < n; i += NL) dst[i] = value_at(i);
+#if AIE_ON_DEVICE
+    AIE_UNROLL(1)
+#endif
+    for (int g = lane; g < r.nq; g += NL) {
+        const int i0 = r.head + 4 * g;
+        store4(dst + i0, value_at(i0), value_at(i0 + 1), value_at(i0 + 2), value_at(i0 + 3));
+    }
+}
+// dst[i] = (bytes[i] & bit) ? 1 : 0 for i in [0, n).  `bytes` is 4-byte aligned shared memory, readable (not
+// necessarily meaningful) up to the word holding byte n + 3; `bit` is one of the low 7 bits.
+AIE_DEV void store_bitplane_f32(float *dst, int n, const uint8_t *bytes, uint32_t bit, int lane) {
+    const RunSplit r = run_split(dst, n, 2);
+    for (int i = lane; i < r.head; i += NL) dst[i] = (bytes[i] & bit) ? 1.0f : 0.0f;
+    for (int i = r.tail0 + lane; i < n; i += NL) dst[i] = (bytes[i] & bit) ? 1.0f : 0.0f;
+    const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes);
+    const int sh = 8 * r.head;  // head in 0..3: the group's 4 bytes start `head` bytes into word g
+    float *q = dst + r.head;
+#if AIE_ON_DEVICE
+    AIE_UNROLL(1)
+#endif
+    for (int g = lane; g < r.nq; g += NL) {
+        const uint32_t v = fshr(wd[g], wd[g + 1], sh);
+        store4(q + 4 * g, (v & bit) ? 1.0f : 0.0f, (v & (bit << 8)) ? 1.0f : 0.0f, (v & (bit << 16)) ? 1.0f : 0.0f,
+               (v & (bit << 24)) ? 1.0f : 0.0f);
+    }
+}
+// dst[i] = code(bytes[i]) widened to int16, code = identity (OWNER == false) or the house-owner encoding of an
+// int8 owner byte (-1 -> 0, a -> a + 2; layout_from_file.py:438-440) applied four bytes at a time.
+template <bool OWNER>
+AIE_DEV uint32_t idx_code4(uint32_t v) {
+    if (!OWNER) return v;
+    const uint32_t none = (v >> 7) & 0x01010101u;                 // 1 in every byte that held -1
+    return ((v & 0x7F7F7F7Fu) + 0x02020202u) & ~(none * 0xFFu);   // owner indices are < 64: no carry between bytes
+}
+template <bool OWNER>
+AIE_DEV void store_bytes_i16(int16_t *dst, int n, const uint8_t *bytes, int lane) {
+    const RunSplit r = run_split(dst, n, 1);
+    for (int i = lane; i < r.head; i += NL) dst[i] = (int16_t)(idx_code4<OWNER>(bytes[i]) & 0xFFu);
+    for (int i = r.tail0 + lane; i < n; i += NL) dst[i] = (int16_t)(idx_code4<OWNER>(bytes[i]) & 0xFFu);
+    const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes) + (r.head >> 2);
+    const int sh = 8 * (r.head & 3);
+    int16_t *q = dst + r.head;
+#if AIE_ON_DEVICE
+    AIE_UNROLL(1)
+#endif
+    for (int g = lane; g < r.nq; g += NL) {
+        const uint32_t w0 = wd[2 * g], w1 = wd[2 * g + 1], w2 = wd[2 * g + 2];
+        const uint32_t lo = idx_code4<OWNER>(fshr(w0, w1, sh)), hi = idx_code4<OWNER>(fshr(w1, w2, sh));
+        store8(q + 8 * g, prmt(lo, 0u, 0x4140u), prmt(lo, 0u, 0x4342u), prmt(hi, 0u, 0x4140u), prmt(hi, 0u, 0x4342u));
+    }
+}
 
 // One element of a "flat" vector (warp-divergence is bounded by the 5 kinds, all of them a few instructions)
 AIE_DEV float flat_emit(const DevCfg &c, const Env &e, const ObsScratch &s, uint32_t entry, int a) {
@@ -1021,81 +1118,63 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     wsync();
 
     // ---- phase 2: outputs ----------------------------------------------------------------------
-    // Consecutive lanes write consecutive addresses; no division by a run-time constant in the loops.
-    // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc)
-    const uint32_t bit3 = c.has_water ? CELL_WATER : CELL_STONE_SRC;
-    const uint32_t bit4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
+    // Every output tensor's env slice is one contiguous run (or a few) written front to back (store_run_*).
+    // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc); 0x40 = "inside" plane
+    const uint32_t pb3 = c.has_water ? CELL_WATER : CELL_STONE_SRC, pb4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
+    auto plane_bit = [&](int m) -> uint32_t {
+        return m == 0 ? (uint32_t)CELL_STONE : m == 1 ? (uint32_t)CELL_WOOD : m == 2 ? (uint32_t)CELL_HOUSE
+             : m == 3 ? pb3 : m == 4 ? pb4 : (uint32_t)CELL_WOOD_SRC;
+    };
     if (c.planner_spatial) {
-        // one lane per map cell: the cell byte is read once and fans out to all M channel planes + 2 index planes
-#if AIE_ON_DEVICE
-        AIE_UNROLL(AIE_OBS_UNROLL)
-#endif
-        for (int k = lane; k < HW; k += NL) {
-            const uint32_t cb = e.cell[k];
-            float *dst = o.p_map + k;
-            dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += HW;
-            dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += HW;
-            dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += HW;
-            dst[0] = (cb & bit3) ? 1.0f : 0.0f;        dst += HW;
-            dst[0] = (cb & bit4) ? 1.0f : 0.0f;
-            if (M == 6) { dst += HW; dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; }
-            const int ow = e.owner[k];
-            o.p_idx[k] = (int16_t)(ow < 0 ? 0 : ow + 2);
-            o.p_idx[HW + k] = (int16_t)s.locmap[k];
-        }
+        for (int m = 0; m < M; m++) store_bitplane_f32(o.p_map + m * HW, HW, e.cell, plane_bit(m), lane);
+        store_bytes_i16<true>(o.p_idx, HW, (const uint8_t *)e.owner, lane);
+        store_bytes_i16<false>(o.p_idx + HW, HW, s.locmap, lane);
     }
-    // agent windows (layout_from_file.py:468-515): per agent, one lane per window cell; the cell is read once
-    // and fans out to the M+1 map channels and the 2 index channels
+    // agent windows (layout_from_file.py:468-515): per agent, the window's cells are staged once as bytes (one lane
+    // per window cell), then the M+1 map planes and the 2 index planes stream out of the staged bytes
     {
         // lane's first window cell and the (dr, dc) step for q += NL: one small division per warp per step
         const int dr_first = lane / win, dc_first = lane - dr_first * win;
         const int dr_step = NL / win, dc_step = NL - dr_step * win;
+        uint8_t *wc = s.wstage, *wi = s.wstage + ((ww + 7) & ~3);  // wi: [2][ww] owner code, location code
         for (int a = 0; a < A; a++) {
             const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;
-            float *amap = o.a_map + a * (M + 1) * ww;
-            int16_t *aidx = o.a_idx + a * 2 * ww;
             int dr = dr_first, dc = dc_first;
-#if AIE_ON_DEVICE
-        AIE_UNROLL(AIE_OBS_UNROLL)
-#endif
             for (int q = lane; q < ww; q += NL) {
                 const int r2 = r0 + dr, c2 = c0 + dc;
                 const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
                 uint32_t cb = 0; int vo = 0, vl = 0;
                 if (inside) {
                     const int k = r2 * W + c2;
-                    cb = e.cell[k];
+                    cb = e.cell[k] | 0x40u;
                     const int ow = e.owner[k];
                     vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
                     vl = s.locmap[k];
                     if (vl == a + 2) vl = 1;
                 }
-                float *dst = amap + q;
-                dst[0] = (cb & CELL_STONE) ? 1.0f : 0.0f;  dst += ww;
-                dst[0] = (cb & CELL_WOOD) ? 1.0f : 0.0f;   dst += ww;
-                dst[0] = (cb & CELL_HOUSE) ? 1.0f : 0.0f;  dst += ww;
-                dst[0] = (cb & bit3) ? 1.0f : 0.0f;        dst += ww;
-                dst[0] = (cb & bit4) ? 1.0f : 0.0f;        dst += ww;
-                if (M == 6) { dst[0] = (cb & CELL_WOOD_SRC) ? 1.0f : 0.0f; dst += ww; }
-                dst[0] = inside ? 1.0f : 0.0f;
-                aidx[q] = (int16_t)vo;
-                aidx[ww + q] = (int16_t)vl;
+                wc[q] = (uint8_t)cb; wi[q] = (uint8_t)vo; wi[ww + q] = (uint8_t)vl;
                 dr += dr_step; dc += dc_step;
                 if (dc >= win) { dc -= win; dr += 1; }
             }
+            wsync();
+            float *amap = o.a_map + a * (M + 1) * ww;
+            for (int m = 0; m <= M; m++) store_bitplane_f32(amap + m * ww, ww, wc, m == M ? 0x40u : plane_bit(m), lane);
+            store_bytes_i16<false>(o.a_idx + a * 2 * ww, 2 * ww, wi, lane);
+            wsync();
         }
     }
     // flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
     for (int a = 0; a < A; a++) {
-        for (int j = lane; j < c.Fa; j += NL) o.a_flat[a * c.Fa + j] = flat_emit(c, e, s, tab[j], a);
-        for (int j = lane; j < c.Fpa; j += NL) o.p_agents[a * c.Fpa + j] = flat_emit(c, e, s, tab[c.tab_pa + j], a);
+        store_run_f32(o.a_flat + a * c.Fa, c.Fa, lane, [&](int j) { return flat_emit(c, e, s, tab[j], a); });
+        store_run_f32(o.p_agents + a * c.Fpa, c.Fpa, lane, [&](int j) { return flat_emit(c, e, s, tab[c.tab_pa + j], a); });
         const uint8_t *lim = s.lim + a * MS_COUNT;
-        for (int j = lane; j < c.Na; j += NL) {
-            const uint32_t en = tab[c.tab_m + j];
-            o.a_mask[a * c.Na + j] = ((en & 255u) < lim[en >> 8]) ? 1.0f : 0.0f;
-        }
+        const uint16_t *mt = tab + c.tab_m;
+        store_run_f32(o.a_mask + a * c.Na, c.Na, lane, [=](int j) {
+            const uint32_t en = mt[j];
+            return ((en & 255u) < lim[en >> 8]) ? 1.0f : 0.0f;
+        });
     }
-    for (int j = lane; j < c.Fp; j += NL) o.p_flat[j] = flat_emit(c, e, s, tab[c.tab_p + j], 0);
+    store_run_f32(o.p_flat, c.Fp, lane, [&](int j) { return flat_emit(c, e, s, tab[c.tab_p + j], 0); });
     if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
         const bool first_day = e.hdr[HDR_TAX_POS] == 1;
         for (int b = 0; b < c.B; b++)

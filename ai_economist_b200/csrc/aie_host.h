@@ -220,7 +220,7 @@ c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A
         c.split = (c.rec_bytes > 24 * 1024) ? 1 : 0;   // records this large would leave < 8 warps per SM resident
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
-        c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT) + 2 * 4 * P + A * MS_COUNT + 8 + c.HW + 4);
+        c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT) + 2 * 4 * P + A * MS_COUNT + 8 + c.HW + 4 + 3 * c.win * c.win + 24);
         c.obs_alias_mt = (c.obs_scratch_bytes <= 4 * 624) ? 1 : 0;
         c.obs_extra_bytes = c.obs_alias_mt ? 0 : c.obs_scratch_bytes;
     }
