@@ -897,8 +897,9 @@ struct ObsScratch {
     double *net_hist;     // [2][P] summed price history (fp64, for the market rate); [2P] = annealed tax limit
     float *shf;           // [sh_count] shared float staging (SH_*): scalars + price history + rates + incomes
     float *sc_a;          // [A][AS_COUNT] per-agent scalar observations
-    uint16_t *full_asks, *full_bids;  // [2][P]
+    float *agf;           // [AS_COUNT + 8P] the current agent's float staging: scalars, my orders, available orders
     uint8_t *lim;         // [A][MS_COUNT] mask limits: mask[j] = idx_j < lim[slot_j]
+    uint8_t *pbits;       // [8] map plane -> cell bit (maps.state order), plane M = 0x40 ("inside the world")
     uint8_t *locmap;      // [HW]  0 none, a+2
     uint8_t *wstage;      // [3][ww] one agent's window: cell bits | 0x40 inside, owner code, agent-location code
 };
@@ -907,9 +908,9 @@ AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
     s.net_hist = (double *)p;     p += 8 * (2 * c.P + 2);
     s.shf = (float *)p;           p += 4 * c.sh_count;
     s.sc_a = (float *)p;          p += 4 * c.A * AS_COUNT;
-    s.full_asks = (uint16_t *)p;  p += 2 * 2 * c.P;
-    s.full_bids = (uint16_t *)p;  p += 2 * 2 * c.P;
+    s.agf = (float *)p;           p += 4 * (AS_COUNT + 8 * c.P);
     s.lim = p;                    p += (c.A * MS_COUNT + 7) & ~7;
+    s.pbits = p;                  p += 8;
     s.locmap = p;                 p += (c.HW + 3) & ~3;  // 4-byte aligned, padded to a multiple of 4 bytes
     s.wstage = p;
     return s;
@@ -949,11 +950,27 @@ AIE_DEV void store8(int16_t *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t 
     for (int j = 0; j < 8; j++) p[j] = (int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
 #endif
 }
+AIE_DEV uint32_t div_magic(uint32_t x, uint32_t magic) {  // floor(x / n), magic = floor(2^32 / n) + 1, x * n < 2^32
+#if AIE_ON_DEVICE
+    return magic ? __umulhi(x, magic) : x;  // magic == 0 <=> n == 1
+#else
+    return magic ? (uint32_t)(((uint64_t)x * magic) >> 32) : x;
+#endif
+}
+// the (at most per-1 + per-1) elements outside the whole 16-byte groups: one predicated scalar store per lane
+template <typename T, typename F>
+AIE_DEV void store_edges(T *dst, const RunSplit &r, int n, int lane, F value_at) {
+    const int ne = r.head + (n - r.tail0);
+#if AIE_ON_DEVICE
+    if (lane < ne) { const int i = lane < r.head ? lane : r.tail0 + (lane - r.head); dst[i] = (T)value_at(i); }
+#else
+    for (int j = lane; j < ne; j += NL) { const int i = j < r.head ? j : r.tail0 + (j - r.head); dst[i] = (T)value_at(i); }
+#endif
+}
 template <typename F>
 AIE_DEV void store_run_f32(float *dst, int n, int lane, F value_at) {
     const RunSplit r = run_split(dst, n, 2);
-    for (int i = lane; i < r.head; i += NL) dst[i] = value_at(i);
-    for (int i = r.tail0 + lane; i < n; i += NL) dst[i] = value_at(i);
+    store_edges(dst, r, n, lane, value_at);
 #if AIE_ON_DEVICE
     AIE_UNROLL(1)
 #endif
@@ -962,22 +979,59 @@ AIE_DEV void store_run_f32(float *dst, int n, int lane, F value_at) {
         store4(dst + i0, value_at(i0), value_at(i0 + 1), value_at(i0 + 2), value_at(i0 + 3));
     }
 }
-// dst[i] = (bytes[i] & bit) ? 1 : 0 for i in [0, n).  `bytes` is 4-byte aligned shared memory, readable (not
-// necessarily meaningful) up to the word holding byte n + 3; `bit` is one of the low 7 bits.
-AIE_DEV void store_bitplane_f32(float *dst, int n, const uint8_t *bytes, uint32_t bit, int lane) {
-    const RunSplit r = run_split(dst, n, 2);
-    for (int i = lane; i < r.head; i += NL) dst[i] = (bytes[i] & bit) ? 1.0f : 0.0f;
-    for (int i = r.tail0 + lane; i < n; i += NL) dst[i] = (bytes[i] & bit) ? 1.0f : 0.0f;
+// rows x n matrix, contiguous: dst[row * n + i] = value_at(row, i), written as ONE run (n_magic = floor(2^32 / n) + 1)
+template <typename F>
+AIE_DEV void store_rows_f32(float *dst, int rows, int n, uint32_t n_magic, int lane, F value_at) {
+    const int total = rows * n;
+    auto flat_value = [&](int x) { const int row = (int)div_magic((uint32_t)x, n_magic); return value_at(row, x - row * n); };
+    if (n < 4) { for (int x = lane; x < total; x += NL) dst[x] = flat_value(x); return; }
+    const RunSplit r = run_split(dst, total, 2);
+    store_edges(dst, r, total, lane, flat_value);
+#if AIE_ON_DEVICE
+    AIE_UNROLL(1)
+#endif
+    for (int g = lane; g < r.nq; g += NL) {
+        const int x0 = r.head + 4 * g;
+        const int row = (int)div_magic((uint32_t)x0, n_magic), i = x0 - row * n;
+        float v[4];
+        for (int j = 0; j < 4; j++) { const bool nx = i + j >= n; v[j] = value_at(nx ? row + 1 : row, nx ? i + j - n : i + j); }
+        store4(dst + x0, v[0], v[1], v[2], v[3]);
+    }
+}
+// np planes x n floats, contiguous: plane m, element i = (bytes[i] & pbits[m]) ? 1 : 0, written as ONE run.
+// `bytes` is 4-byte aligned shared memory, readable up to the word holding byte n + 3; n >= 4.
+AIE_DEV void store_bitplanes_f32(float *dst, int np, int n, uint32_t n_magic, const uint8_t *bytes, const uint8_t *pbits,
+                                 int lane) {
+    const int total = np * n;
+    if (n < 4) {  // degenerate planes: element-wise
+        for (int x = lane; x < total; x += NL) {
+            const int m = (int)div_magic((uint32_t)x, n_magic);
+            dst[x] = (bytes[x - m * n] & pbits[m]) ? 1.0f : 0.0f;
+        }
+        return;
+    }
+    const RunSplit r = run_split(dst, total, 2);
+    store_edges(dst, r, total, lane, [&](int x) {
+        const int m = x < n ? 0 : np - 1;  // head lies in the first plane, tail in the last
+        return (bytes[x - m * n] & pbits[m]) ? 1.0f : 0.0f;
+    });
     const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes);
-    const int sh = 8 * r.head;  // head in 0..3: the group's 4 bytes start `head` bytes into word g
     float *q = dst + r.head;
 #if AIE_ON_DEVICE
     AIE_UNROLL(1)
 #endif
     for (int g = lane; g < r.nq; g += NL) {
-        const uint32_t v = fshr(wd[g], wd[g + 1], sh);
-        store4(q + 4 * g, (v & bit) ? 1.0f : 0.0f, (v & (bit << 8)) ? 1.0f : 0.0f, (v & (bit << 16)) ? 1.0f : 0.0f,
-               (v & (bit << 24)) ? 1.0f : 0.0f);
+        const int x0 = r.head + 4 * g;
+        const int m = (int)div_magic((uint32_t)x0, n_magic), i = x0 - m * n;
+        const uint32_t v = fshr(wd[i >> 2], wd[(i >> 2) + 1], 8 * (i & 3));
+        uint32_t t = v & (pbits[m] * 0x01010101u);
+        const int left = n - i;  // elements of this group that still belong to plane m
+        if (left < 4) {          // the group runs over into plane m + 1 (once per plane boundary)
+            const uint32_t low = (1u << (8 * left)) - 1u;
+            t = (t & low) | ((wd[0] << (8 * left)) & (pbits[m + 1] * 0x01010101u) & ~low);
+        }
+        store4(q + 4 * g, (t & 0xFFu) ? 1.0f : 0.0f, (t & 0xFF00u) ? 1.0f : 0.0f, (t & 0xFF0000u) ? 1.0f : 0.0f,
+               (t & 0xFF000000u) ? 1.0f : 0.0f);
     }
 }
 // dst[i] = code(bytes[i]) widened to int16, code = identity (OWNER == false) or the house-owner encoding of an
@@ -991,8 +1045,7 @@ AIE_DEV uint32_t idx_code4(uint32_t v) {
 template <bool OWNER>
 AIE_DEV void store_bytes_i16(int16_t *dst, int n, const uint8_t *bytes, int lane) {
     const RunSplit r = run_split(dst, n, 1);
-    for (int i = lane; i < r.head; i += NL) dst[i] = (int16_t)(idx_code4<OWNER>(bytes[i]) & 0xFFu);
-    for (int i = r.tail0 + lane; i < n; i += NL) dst[i] = (int16_t)(idx_code4<OWNER>(bytes[i]) & 0xFFu);
+    store_edges(dst, r, n, lane, [&](int i) { return (int)(idx_code4<OWNER>(bytes[i]) & 0xFFu); });
     const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes) + (r.head >> 2);
     const int sh = 8 * (r.head & 3);
     int16_t *q = dst + r.head;
@@ -1006,17 +1059,9 @@ AIE_DEV void store_bytes_i16(int16_t *dst, int n, const uint8_t *bytes, int lane
     }
 }
 
-// One element of a "flat" vector (warp-divergence is bounded by the 5 kinds, all of them a few instructions)
-AIE_DEV float flat_emit(const DevCfg &c, const Env &e, const ObsScratch &s, uint32_t entry, int a) {
-    const uint32_t pl = AIE_FLAT_PAYLOAD(entry);
-    const int kind = AIE_FLAT_KIND(entry);
-    if (kind == FK_SHARED) return s.shf[pl];
-    if (kind == FK_AGENT) return s.sc_a[a * AS_COUNT + pl];
-    const int side = (pl >> 6) & 1, cc = (pl >> 5) & 1, idx = pl & 31;
-    const uint16_t *full = side ? s.full_asks : s.full_bids;
-    const uint8_t *mine = side ? e.ask_hist : e.bid_hist;
-    const int f = full[cc * c.P + idx], m = mine[(cc * c.A + a) * c.P + idx];
-    return (float)(kind == FK_FULL ? f : (kind == FK_MY ? m : f - m));
+// One element of a "flat" vector: the program entry names a slot of the shared or of the agent's float staging array
+AIE_DEV float flat_value(const float *shf, const float *agf, uint32_t entry) {
+    return (AIE_FLAT_KIND(entry) == FK_AGENT ? agf : shf)[AIE_FLAT_PAYLOAD(entry)];
 }
 
 AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const ObsOut &o,
@@ -1029,6 +1074,12 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
 
     // ---- phase 1: stage every scalar the flat vectors / masks need (float, final values) -------------
     for (int k = lane; k < (HW + 3) / 4; k += NL) ((uint32_t *)s.locmap)[k] = 0u;
+    for (int m = lane; m < 8; m += NL) {  // maps.state channel order: Stone, Wood, House, [Water], StoneSrc, WoodSrc
+        const uint32_t b3 = c.has_water ? CELL_WATER : CELL_STONE_SRC, b4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
+        const uint32_t bit = m == 0 ? (uint32_t)CELL_STONE : m == 1 ? (uint32_t)CELL_WOOD : m == 2 ? (uint32_t)CELL_HOUSE
+                           : m == 3 ? b3 : m == 4 ? b4 : (uint32_t)CELL_WOOD_SRC;
+        s.pbits[m] = (uint8_t)(m == M ? 0x40u : (m < M ? bit : 0u));
+    }
     if (c.has[COMP_CDA]) {  // continuous_double_auction.py:491-542
         for (int i = lane; i < 2 * P; i += NL) {  // i = cc * P + p; sums over agents in index order
             int cc = i / P, p = i - cc * P;
@@ -1038,7 +1089,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
                 fa += e.ask_hist[(cc * A + a) * P + p];
                 fb += e.bid_hist[(cc * A + a) * P + p];
             }
-            s.net_hist[i] = acc; s.full_asks[i] = (uint16_t)fa; s.full_bids[i] = (uint16_t)fb;
+            s.net_hist[i] = acc; s.shf[c.sh_full + i] = (float)fb; s.shf[c.sh_full + 2 * P + i] = (float)fa;
             s.shf[SH_PRICE_HIST + i] = (float)(acc * inv_scale);
         }
     }
@@ -1120,13 +1171,8 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     // ---- phase 2: outputs ----------------------------------------------------------------------
     // Every output tensor's env slice is one contiguous run (or a few) written front to back (store_run_*).
     // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc); 0x40 = "inside" plane
-    const uint32_t pb3 = c.has_water ? CELL_WATER : CELL_STONE_SRC, pb4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
-    auto plane_bit = [&](int m) -> uint32_t {
-        return m == 0 ? (uint32_t)CELL_STONE : m == 1 ? (uint32_t)CELL_WOOD : m == 2 ? (uint32_t)CELL_HOUSE
-             : m == 3 ? pb3 : m == 4 ? pb4 : (uint32_t)CELL_WOOD_SRC;
-    };
     if (c.planner_spatial) {
-        for (int m = 0; m < M; m++) store_bitplane_f32(o.p_map + m * HW, HW, e.cell, plane_bit(m), lane);
+        store_bitplanes_f32(o.p_map, M, HW, c.HW_magic, e.cell, s.pbits, lane);
         store_bytes_i16<true>(o.p_idx, HW, (const uint8_t *)e.owner, lane);
         store_bytes_i16<false>(o.p_idx + HW, HW, s.locmap, lane);
     }
@@ -1156,25 +1202,41 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
                 dr += dr_step; dc += dc_step;
                 if (dc >= win) { dc -= win; dr += 1; }
             }
+            // the agent's float staging: scalars, then my / available order counts (continuous_double_auction.py:515-542)
+            for (int i = lane; i < AS_COUNT; i += NL) s.agf[i] = s.sc_a[a * AS_COUNT + i];
+            if (c.has[COMP_CDA])
+                for (int i = lane; i < 4 * P; i += NL) {  // i = (side * 2 + commodity) * P + price level
+                    const int side = i >= 2 * P ? 1 : 0, r = i - side * 2 * P, cc = r >= P ? 1 : 0, pl = r - cc * P;
+                    const float mine = (float)(side ? e.ask_hist : e.bid_hist)[(cc * A + a) * P + pl];
+                    s.agf[AS_COUNT + i] = mine;
+                    s.agf[AS_COUNT + 4 * P + i] = s.shf[c.sh_full + i] - mine;
+                }
             wsync();
-            float *amap = o.a_map + a * (M + 1) * ww;
-            for (int m = 0; m <= M; m++) store_bitplane_f32(amap + m * ww, ww, wc, m == M ? 0x40u : plane_bit(m), lane);
+            store_bitplanes_f32(o.a_map + a * (M + 1) * ww, M + 1, ww, c.ww_magic, wc, s.pbits, lane);
             store_bytes_i16<false>(o.a_idx + a * 2 * ww, 2 * ww, wi, lane);
+            {
+                const float *shf = s.shf, *agf = s.agf;
+                store_run_f32(o.a_flat + a * c.Fa, c.Fa, lane, [=](int j) { return flat_value(shf, agf, tab[j]); });
+            }
             wsync();
         }
     }
-    // flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
-    for (int a = 0; a < A; a++) {
-        store_run_f32(o.a_flat + a * c.Fa, c.Fa, lane, [&](int j) { return flat_emit(c, e, s, tab[j], a); });
-        store_run_f32(o.p_agents + a * c.Fpa, c.Fpa, lane, [&](int j) { return flat_emit(c, e, s, tab[c.tab_pa + j], a); });
-        const uint8_t *lim = s.lim + a * MS_COUNT;
+    // planner flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
+    {
+        const float *shf = s.shf, *sc = s.sc_a;
+        const uint16_t *tpa = tab + c.tab_pa, *tp = tab + c.tab_p;
+        store_rows_f32(o.p_agents, A, c.Fpa, c.Fpa_magic, lane,
+                       [=](int a, int j) { return flat_value(shf, sc + a * AS_COUNT, tpa[j]); });
+        store_run_f32(o.p_flat, c.Fp, lane, [=](int j) { return flat_value(shf, shf, tp[j]); });
+    }
+    {
         const uint16_t *mt = tab + c.tab_m;
-        store_run_f32(o.a_mask + a * c.Na, c.Na, lane, [=](int j) {
+        const uint8_t *lim = s.lim;
+        store_rows_f32(o.a_mask, A, c.Na, c.Na_magic, lane, [=](int a, int j) {
             const uint32_t en = mt[j];
-            return ((en & 255u) < lim[en >> 8]) ? 1.0f : 0.0f;
+            return ((en & 255u) < lim[a * MS_COUNT + (en >> 8)]) ? 1.0f : 0.0f;
         });
     }
-    store_run_f32(o.p_flat, c.Fp, lane, [&](int j) { return flat_emit(c, e, s, tab[c.tab_p + j], 0); });
     if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
         const bool first_day = e.hdr[HDR_TAX_POS] == 1;
         for (int b = 0; b < c.B; b++)

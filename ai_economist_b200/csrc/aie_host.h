@@ -133,7 +133,8 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
 
     c.sh_curr_rates = SH_PRICE_HIST + 2 * c.P;
     c.sh_last_incomes = c.sh_curr_rates + 16;
-    c.sh_count = c.sh_last_incomes + c.A;
+    c.sh_full = c.sh_last_incomes + c.A;  // full bid / ask counts [side][commodity][P]
+    c.sh_count = c.sh_full + 4 * c.P;
     uint16_t mask_prog[MAX_MASK], prog_a[MAX_FLAT], prog_p[MAX_FLAT], prog_pa[16];
     // mask program (base_agent.py:440-460)
     {
@@ -170,14 +171,14 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
                 std::string s = std::string("ContinuousDoubleAuction-"), r = std::string("-") + CN[cc];
                 ka.push_back(K(s + "market_rate" + r, FK_SHARED, SH_MARKET_RATE + cc, 1));
                 ka.push_back(K(s + "price_history" + r, FK_SHARED, SH_PRICE_HIST + cc * c.P, c.P));
-                ka.push_back(K(s + "available_asks" + r, FK_AVAIL, AIE_HIST_PAYLOAD(1, cc, 0), c.P));
-                ka.push_back(K(s + "available_bids" + r, FK_AVAIL, AIE_HIST_PAYLOAD(0, cc, 0), c.P));
-                ka.push_back(K(s + "my_asks" + r, FK_MY, AIE_HIST_PAYLOAD(1, cc, 0), c.P));
-                ka.push_back(K(s + "my_bids" + r, FK_MY, AIE_HIST_PAYLOAD(0, cc, 0), c.P));
+                ka.push_back(K(s + "available_asks" + r, FK_AGENT, AS_COUNT + 4 * c.P + (2 + cc) * c.P, c.P));
+                ka.push_back(K(s + "available_bids" + r, FK_AGENT, AS_COUNT + 4 * c.P + cc * c.P, c.P));
+                ka.push_back(K(s + "my_asks" + r, FK_AGENT, AS_COUNT + (2 + cc) * c.P, c.P));
+                ka.push_back(K(s + "my_bids" + r, FK_AGENT, AS_COUNT + cc * c.P, c.P));
                 kp.push_back(K(s + "market_rate" + r, FK_SHARED, SH_MARKET_RATE + cc, 1));
                 kp.push_back(K(s + "price_history" + r, FK_SHARED, SH_PRICE_HIST + cc * c.P, c.P));
-                kp.push_back(K(s + "full_asks" + r, FK_FULL, AIE_HIST_PAYLOAD(1, cc, 0), c.P));
-                kp.push_back(K(s + "full_bids" + r, FK_FULL, AIE_HIST_PAYLOAD(0, cc, 0), c.P));
+                kp.push_back(K(s + "full_asks" + r, FK_SHARED, c.sh_full + (2 + cc) * c.P, c.P));
+                kp.push_back(K(s + "full_bids" + r, FK_SHARED, c.sh_full + cc * c.P, c.P));
             }
         if (c.has[COMP_TAX]) {
             std::string s = "PeriodicBracketTax-";
@@ -194,6 +195,11 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         c.Fp = build_prog(kp, prog_p, MAX_FLAT);
         c.Fpa = build_prog(kpa, prog_pa, 16);
         if (c.Fa < 0 || c.Fp < 0 || c.Fpa < 0) return bad("flat observation too long");
+    }
+    {
+        auto magic = [](int n) { return n > 1 ? (uint32_t)((1ull << 32) / (uint64_t)n) + 1u : 0u; };
+        c.HW_magic = magic(c.HW); c.ww_magic = magic(c.win * c.win);
+        c.Fa_magic = magic(c.Fa); c.Fpa_magic = magic(c.Fpa); c.Na_magic = magic(c.Na);
     }
     c.tab_p = c.Fa; c.tab_pa = c.tab_p + c.Fp; c.tab_m = c.tab_pa + c.Fpa; c.tab_n = (c.tab_m + c.Na + 1) & ~1;
     memcpy(tb.w, prog_a, 2 * c.Fa); memcpy(tb.w + c.tab_p, prog_p, 2 * c.Fp);
@@ -220,7 +226,7 @@ c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A
         c.split = (c.rec_bytes > 24 * 1024) ? 1 : 0;   // records this large would leave < 8 warps per SM resident
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
-        c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT) + 2 * 4 * P + A * MS_COUNT + 8 + c.HW + 4 + 3 * c.win * c.win + 24);
+        c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT + AS_COUNT + 8 * P) + A * MS_COUNT + 16 + c.HW + 4 + 3 * c.win * c.win + 24);
         c.obs_alias_mt = (c.obs_scratch_bytes <= 4 * 624) ? 1 : 0;
         c.obs_extra_bytes = c.obs_alias_mt ? 0 : c.obs_scratch_bytes;
     }

@@ -31,11 +31,11 @@ enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
 
 // Observation "programs" (built once on the host from the reference's sorted-key flattening, base_env.py:562-612).
 // flat entry  = kind << 13 | payload:
-//   FK_SHARED  payload = index into the per-env shared float staging array (SH_*)
-//   FK_AGENT   payload = per-agent scalar slot (AS_*)
-//   FK_MY / FK_AVAIL / FK_FULL  payload = side << 6 | commodity << 5 | price level   (side 0 bids, 1 asks)
+//   FK_SHARED  payload = index into the per-env shared float staging array (SH_*, then sh_full: full bid/ask counts)
+//   FK_AGENT   payload = index into the current agent's float staging array: AS_* scalars, then from AS_COUNT on
+//              my orders [side][commodity][P] and available (all - mine) orders [side][commodity][P]  (side 0 bids, 1 asks)
 // mask entry  = slot << 8 | idx; the mask value is (idx < limit[agent][slot])
-enum { FK_SHARED = 0, FK_AGENT = 1, FK_MY = 2, FK_AVAIL = 3, FK_FULL = 4 };
+enum { FK_SHARED = 0, FK_AGENT = 1 };
 enum { AS_LOC_ROW = 0, AS_LOC_COL, AS_INV_COIN, AS_INV_STONE, AS_INV_WOOD, AS_BUILD_PAYMENT, AS_BUILD_SKILL, AS_BONUS,
        AS_TAX_MARG, AS_TAX_LAST_INCOME, AS_TAX_LAST_MARG, AS_COUNT = 12 };
 enum { SH_ZERO = 0, SH_TIME = 1, SH_MARKET_RATE = 2, SH_TAX_IS_TAX_DAY = 4, SH_TAX_IS_FIRST = 5, SH_TAX_PHASE = 6,
@@ -45,7 +45,6 @@ enum { MS_ONE = 0, MS_BUILD, MS_BUY0, MS_BUY1, MS_SELL0, MS_SELL1, MS_G0, MS_G1,
 #define AIE_FLAT_ENTRY(kind, payload) ((uint16_t)(((kind) << 13) | (payload)))
 #define AIE_FLAT_KIND(e) ((e) >> 13)
 #define AIE_FLAT_PAYLOAD(e) ((e) & 0x1FFF)
-#define AIE_HIST_PAYLOAD(side, c, idx) (((side) << 6) | ((c) << 5) | (idx))
 #define AIE_MASK_ENTRY(slot, idx) ((uint16_t)(((slot) << 8) | (idx)))
 
 constexpr int MAX_FLAT = 448;
@@ -92,8 +91,9 @@ struct DevCfg {
     // step-kernel scratch (per env, shared memory) and observe-kernel scratch
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;
-    int32_t sh_curr_rates, sh_last_incomes, sh_count;  // offsets / size of the shared float staging array
+    int32_t sh_curr_rates, sh_last_incomes, sh_full, sh_count;  // offsets / size of the shared float staging array
     int32_t tab_p, tab_pa, tab_m, tab_n;               // offsets (u16 words) into the program table, total words (even)
+    uint32_t HW_magic, ww_magic, Fa_magic, Fpa_magic, Na_magic;  // floor(2^32 / n) + 1: run index -> (row, column)
 };
 
 // raw device pointers (mirrors aie_buffers)
