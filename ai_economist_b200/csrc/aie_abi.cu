@@ -78,12 +78,17 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+__device__ __forceinline__ void bulk_s2g_part(void *gmem_dst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    bulk_s2g_part(gmem_dst, smem_src, bytes);
+    bulk_commit();
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_oldest() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // shared-memory carve-up: [mbarriers | block-shared observation programs | per-warp (record | scratch | obs scratch)]
@@ -139,11 +144,13 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
         bulk_g2s(rec, grec, (uint32_t)c.resident_bytes, bar);
     }
     __syncwarp();
-    mbar_wait(bar, 0);
-
+    // the actions are decoded into the scratch area while the bulk load of the record is in flight
     const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
     const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
-    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane);
+    decode_actions(c, step_scratch_view(scratch, c), act_a, act_p, lane);
+    mbar_wait(bar, 0);
+
+    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane, true);
 
     // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
     // from the load-time snapshot; the episode counters and the numpy stream carry on.
@@ -178,14 +185,25 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
 
     fence_async_smem();  // generic-proxy writes to the record -> visible to the bulk (async-proxy) store
     __syncwarp();
-    if (lane == 0) bulk_s2g(grec, rec, (uint32_t)c.resident_bytes);
-    // Observations / masks of the post-step state stream out of the same shared-memory record.  When the staging
-    // area aliases the MT19937 key image, the bulk store must have finished READING shared memory first; otherwise
-    // the store drains while the observations are written (both only read the record).
-    if (c.obs_alias_mt) { if (lane == 0) bulk_wait_read(); __syncwarp(); }
+    // Observations / masks of the post-step state stream out of the same shared-memory record while the bulk store
+    // drains (both only read the record).  When the staging area aliases the MT19937 key image, the key goes out as
+    // its own (first) bulk group and only that group must have finished READING shared memory before the pass starts.
+    if (lane == 0) {
+        if (c.obs_alias_mt) {
+            const uint32_t mt_end = (uint32_t)c.off_mt + 4u * 624u;
+            bulk_s2g(grec + c.off_mt, rec + c.off_mt, 4u * 624u);
+            bulk_s2g_part(grec, rec, (uint32_t)c.off_mt);
+            if ((uint32_t)c.resident_bytes > mt_end) bulk_s2g_part(grec + mt_end, rec + mt_end, (uint32_t)c.resident_bytes - mt_end);
+            bulk_commit();
+            bulk_wait_read_oldest();
+        } else {
+            bulk_s2g(grec, rec, (uint32_t)c.resident_bytes);
+        }
+    }
+    __syncwarp();
     uint8_t *obs_scratch = c.obs_alias_mt ? rec + c.off_mt : scratch + c.step_scratch_bytes;
-    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, emit_obs == 2 ? (env & 63) : env), tab, lane);
-    if (!c.obs_alias_mt && lane == 0) bulk_wait_read();
+    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, env), tab, lane);
+    if (lane == 0) bulk_wait_read();
 }
 
 __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
@@ -333,7 +351,6 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
     return AIE_OK;
 }
 int launch_step(aie_env *env, int emit_obs, void *stream) {
-    if (emit_obs && getenv("AIE_DEBUG_OBS_FOLD")) emit_obs = 2;  // EXPERIMENT
     const int wpb = env->be.step_wpb;
     const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;

@@ -781,10 +781,10 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 // ------------------------------------------------------------------------------------------------
 template <bool BIG>
 AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
-                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane) {
+                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane, bool decoded = false) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
-    decode_actions(c, s, act_a, act_p, lane);
+    if (!decoded) decode_actions(c, s, act_a, act_p, lane);  // the CUDA kernel decodes while the record is in flight
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
     const int t = e.hdr[HDR_T] + 1;
     wsync();

@@ -16,5 +16,4 @@ except Exception as ex:
 PY
 }
 run normal "" X=1
-run fold "" AIE_DEBUG_OBS_FOLD=1
-run m3 "" AIE_STEP_MINB=3
+run c3 "--workload c3" X=1
