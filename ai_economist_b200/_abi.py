@@ -2,7 +2,7 @@
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 4, 16, 64
 AIE_OK = 0
 
@@ -45,12 +45,12 @@ class AieDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in [
         "n_envs", "n_agents", "height", "width", "n_map_channels", "window", "flat_agent", "flat_planner",
         "flat_planner_agent", "mask_agent", "mask_planner", "n_act_agent", "n_act_planner", "state_bytes",
-        "algorithmic_bytes_per_env_step"]]
+        "algorithmic_bytes_per_env_step", "n_stats", "stats_trade", "stats_tax"]]
 
 
 _BUF_NAMES = ["state", "state0", "actions_agent", "actions_planner", "obs_agent_map", "obs_agent_idx",
               "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx", "obs_planner_flat",
-              "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]
+              "obs_planner_agents", "mask_planner", "obs_time", "reward", "done", "episode_final"]
 
 
 class AieBuffers(C.Structure):
@@ -66,10 +66,12 @@ class AieHostState(C.Structure):
 _DUMP_PTRS = ["cell", "owner", "loc", "coin", "esc_coin", "labor", "inv", "esc", "n_orders", "bid_hist", "ask_hist",
               "price_hist", "tax_pos", "rate_idx", "last_coin", "last_income", "last_marg", "mt_key", "mt_pos", "t",
               "completions", "book_rows", "book_count"]
+_DUMP_PTRS2 = ["stats", "util_prev", "auto_warmup"]  # after book_cap (ABI 2)
 
 
 class AieStateDump(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in _DUMP_PTRS] + [("book_cap", C.c_int32)]
+    _fields_ = ([(n, C.c_void_p) for n in _DUMP_PTRS] + [("book_cap", C.c_int32)] +
+                [(n, C.c_void_p) for n in _DUMP_PTRS2])
 
 
 class AieField(C.Structure):
@@ -141,6 +143,8 @@ def load_library(path=None):
     L.aie_sample_random_actions.argtypes = [P, C.c_uint64, P]
     L.aie_step_host.argtypes = [P, P, P, C.POINTER(AieHostOut), P]
     L.aie_read_state.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
+    L.aie_read_episode_final.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
+    L.aie_read_episode_final.restype = C.c_int
     L.aie_launch_count.argtypes = [P]
     L.aie_covid_create.argtypes = [C.POINTER(AieCovidConfig), C.c_int32, C.c_int32, C.POINTER(P)]
     L.aie_covid_destroy.argtypes = [P]
@@ -165,7 +169,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers",
                     "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions",
-                    "aie_step_host", "aie_read_state", "aie_launch_count", "aie_last_error", "aie_abi_version",
+                    "aie_step_host", "aie_read_state", "aie_read_episode_final", "aie_launch_count", "aie_last_error", "aie_abi_version",
                     "aie_covid_create", "aie_covid_destroy", "aie_covid_bind_buffers", "aie_covid_reset", "aie_covid_step",
                     "aie_covid_sample_random_actions", "aie_covid_launch_count"]
 

@@ -162,6 +162,11 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
         const uint32_t tail = (uint32_t)(c.rec_bytes - c.off_price_hist);  // price history + order slots
         fence_async_smem();
         __syncwarp();
+        if (b.final && lane == 0) {  // end-of-episode snapshot (previous_episode_metrics): the resident record as it stands
+            bulk_s2g(b.final + (size_t)env * c.rec_bytes, rec, (uint32_t)c.resident_bytes);
+            bulk_wait_read();
+        }
+        __syncwarp();
         if (lane == 0) {
             mbar_expect_tx(bar, (uint32_t)c.off_mt + (c.split ? 0u : tail));
             bulk_g2s(rec, snap, (uint32_t)c.off_mt, bar);

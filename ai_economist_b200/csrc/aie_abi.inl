@@ -81,7 +81,8 @@ int aie_bind_buffers(aie_env *env, const aie_buffers *b) {
     if (c.n_act_p > 0 && !b->actions_planner) return fail(AIE_EINVAL, "aie_bind_buffers: actions_planner required");
     if (((uintptr_t)b->state & 15) || ((uintptr_t)b->state0 & 15)) return fail(AIE_EINVAL, "state buffers must be 16-byte aligned");
     aie::DevBufs &d = env->bufs;
-    d.state = (uint8_t *)b->state; d.state0 = (uint8_t *)b->state0;
+    d.state = (uint8_t *)b->state; d.state0 = (uint8_t *)b->state0; d.final = (uint8_t *)b->episode_final;
+    if ((uintptr_t)b->episode_final & 15) return fail(AIE_EINVAL, "episode_final must be 16-byte aligned");
     d.act_a = b->actions_agent; d.act_p = b->actions_planner;
     d.a_map = b->obs_agent_map; d.a_idx = b->obs_agent_idx; d.a_flat = b->obs_agent_flat; d.a_mask = b->mask_agent;
     d.p_map = b->obs_planner_map; d.p_idx = b->obs_planner_idx; d.p_flat = b->obs_planner_flat;
@@ -189,6 +190,24 @@ int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out) {
     rc = aie::be::sync(env, nullptr);
     if (rc != AIE_OK) return rc;
     aie::unpack_record(c, rec.data(), *out);
+    return AIE_OK;
+}
+
+int aie_read_episode_final(aie_env *env, int32_t e, const aie_state_dump *out) {
+    if (!env || !out) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->bufs.final) return fail(AIE_ESTATE, "aie_read_episode_final: no episode_final buffer bound");
+    if (e < 0 || e >= env->n_envs) return fail(AIE_EINVAL, "aie_read_episode_final: env index out of range");
+    const aie::DevCfg &c = env->cfg;
+    std::vector<uint8_t> rec(c.rec_bytes);
+    int rc = aie::be::sync_all(env);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::download(env, rec.data(), env->bufs.final + (size_t)e * c.rec_bytes, rec.size(), nullptr);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::sync(env, nullptr);
+    if (rc != AIE_OK) return rc;
+    aie_state_dump d = *out;
+    d.book_rows = nullptr; d.book_count = nullptr;  // the snapshot holds the resident sections only
+    aie::unpack_record(c, rec.data(), d);
     return AIE_OK;
 }
 

@@ -90,7 +90,7 @@ AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 struct Env {
     int32_t *hdr;
     double *coin, *esc_coin, *labor, *bpay, *bskill, *bonus, *last_coin, *last_income, *last_marg, *util_prev,
-        *price_hist;
+        *price_hist, *stats;
     int32_t *inv, *esc;  // [A][2]
     int16_t *loc;        // [A][2]
     uint8_t *n_orders, *bid_hist, *ask_hist, *rate_idx, *cell;
@@ -105,6 +105,7 @@ AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     uint8_t *big = c.split ? grec : rec;
     e.hdr = (int32_t *)rec;
     e.coin = (double *)(rec + c.off_coin);
+    e.stats = (double *)(rec + c.off_stats);
     e.esc_coin = (double *)(rec + c.off_esc_coin);
     e.labor = (double *)(rec + c.off_labor);
     e.bpay = (double *)(rec + c.off_bpay);
@@ -293,6 +294,7 @@ AIE_DEV void build_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
                 e.owner[k] = (int8_t)a;
                 e.coin[a] += e.bpay[a];
                 e.labor[a] += c.build_labor;
+                e.stats[ST_BUILDS + a] += 1.0;
             }
         }
         wsync();
@@ -464,6 +466,10 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int
                 e.esc_coin[buyer] -= (double)bprice;
                 e.coin[seller] += (double)price;
                 e.coin[buyer] += (double)(bprice - price);
+                e.stats[ST_N_TRADES] += 1.0;
+                double *ts = e.stats + c.st_trade + ((seller * 2 + cc) * 2 + 0) * 2;
+                double *tb = e.stats + c.st_trade + ((buyer * 2 + cc) * 2 + 1) * 2;
+                ts[0] += 1.0; ts[1] += (double)price; tb[0] += 1.0; tb[1] += (double)price;
             }
             wsync();
             refresh_best(c, slots, buyer, 0, t, bb_key, bb_slot, lane);
@@ -564,14 +570,17 @@ AIE_DEV void gather_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) 
 AIE_DEV double tax_rate(const DevCfg &c, const Env &e, int b) {  // curr_marginal_rates :381-405
     return c.tax_model == 0 ? c.disc_rates[e.rate_idx[b]] : c.fixed_rates[b];
 }
-AIE_DEV double tax_marginal_rate(const DevCfg &c, const Env &e, double income) {  // :837-844
-    if (income < 0) return 0.0;
+AIE_DEV int tax_income_bin(const DevCfg &c, double income) {  // :828-835 (bracket index; negative income -> 0)
     int arg = 0;
     for (int b = c.B - 1; b >= 0; b--) {
         double hi = (b + 1 < c.B) ? c.cutoffs[b + 1] : INFINITY;
         if (income >= c.cutoffs[b] && income < hi) arg = b;
     }
-    return tax_rate(c, e, arg);
+    return arg;
+}
+AIE_DEV double tax_marginal_rate(const DevCfg &c, const Env &e, double income) {  // :837-844
+    if (income < 0) return 0.0;
+    return tax_rate(c, e, tax_income_bin(c, income));
 }
 AIE_DEV double tax_due(const DevCfg &c, const Env &e, double income) {  // :846-851
     double sum = 0.0;
@@ -602,10 +611,23 @@ AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, int lane) {
             e.last_income[a] = income;
             e.coin[a] -= paid;
             s.tmp[a] = paid;
+            s.tmp[A + a] = paid / fmax(0.000001, income);  // effective rate (:880)
+            double *ta = e.stats + c.st_tax + ST_TAX_AGENT;
+            ta[a] += fmax(0.0, income); ta[A + a] += paid;
         }
         wsync();
         double net = 0.0;
         for (int a = 0; a < A; a++) net += s.tmp[a];  // sequential, agent order (uniform)
+        if (lane == 0) {  // episode statistics (:862-897): schedule, occupancy, effective rates, revenue
+            double *st = e.stats + c.st_tax;
+            st[ST_TAX_PERIODS] += 1.0;
+            st[ST_TAX_COLLECTED] += net;
+            for (int b = 0; b < c.B; b++) st[ST_TAX_SCHED + b] += tax_rate(c, e, b);
+            for (int a = 0; a < A; a++) {
+                st[ST_TAX_EFF_SUM] += s.tmp[A + a];
+                st[ST_TAX_OCC + tax_income_bin(c, e.last_income[a])] += 1.0;
+            }
+        }
         double lump = net / A;
         for (int a = lane; a < A; a += NL) {
             e.coin[a] += lump;

@@ -219,6 +219,10 @@ c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A
         c.off_rate_idx = take(16);
         c.off_cell = take(c.HW); c.off_owner = take(c.HW);
         c.obs_prefix_bytes = off;                      // [0, here): what the observation pass reads besides price_hist
+        c.st_trade = ST_BUILDS + A;
+        c.st_tax = c.has[COMP_TAX] ? c.st_trade + 8 * A : -1;
+        c.n_stats = c.has[COMP_TAX] ? c.st_tax + ST_TAX_AGENT + 2 * A : c.st_trade + 8 * A;
+        c.off_stats = take(8 * c.n_stats);
         c.off_mt = take(4 * 624);
         c.off_price_hist = take(8 * 2 * A * P);
         c.off_orders = take(4 * 2 * A * c.K);
@@ -240,6 +244,7 @@ inline void fill_dims(const DevCfg &c, aie_dims &d) {
     d.flat_agent = c.Fa; d.flat_planner = c.Fp; d.flat_planner_agent = c.Fpa;
     d.mask_agent = c.Na; d.mask_planner = c.Np; d.n_act_agent = c.n_act_a; d.n_act_planner = c.n_act_p;
     d.state_bytes = c.rec_bytes;
+    d.n_stats = c.n_stats; d.stats_trade = c.st_trade; d.stats_tax = c.st_tax;
     const int ww = c.win * c.win;
     long long obs = (long long)c.A * ((c.M + 1) * ww * 4 + 2 * ww * 2 + c.Fa * 4 + c.Na * 4) + c.Fp * 4 + c.A * c.Fpa * 4 +
                     c.Np * 4 + 4 + (c.planner_spatial ? (c.M * c.HW * 4 + 2 * c.HW * 2) : 0);
@@ -255,6 +260,7 @@ inline int lookup_field(const DevCfg &c, const char *name, aie_field *f) {
         {"t", HDR_T * 4, 4, 0, 1, 0, 0, 0, 0}, {"tax_pos", HDR_TAX_POS * 4, 4, 0, 1, 0, 0, 0, 0},
         {"completions", HDR_COMPLETIONS * 4, 4, 0, 1, 0, 0, 0, 0}, {"auto_warmup", HDR_AUTO_WARMUP * 4, 4, 0, 1, 0, 0, 0, 0},
         {"mt_pos", HDR_MT_POS * 4, 4, 0, 1, 0, 0, 0, 0}, {"episodes", HDR_EPISODES * 4, 4, 0, 1, 0, 0, 0, 0},
+        {"stats", c.off_stats, 8, 1, 1, 1, c.n_stats, 0, 0}, {"util_prev", c.off_util_prev, 8, 1, 1, 1, A + 1, 0, 0},
         {"coin", c.off_coin, 8, 1, 1, 1, A, 0, 0}, {"esc_coin", c.off_esc_coin, 8, 1, 1, 1, A, 0, 0},
         {"labor", c.off_labor, 8, 1, 1, 1, A, 0, 0}, {"build_payment", c.off_bpay, 8, 1, 1, 1, A, 0, 0},
         {"build_skill", c.off_bskill, 8, 1, 1, 1, A, 0, 0}, {"bonus_gather_prob", c.off_bonus, 8, 1, 1, 1, A, 0, 0},
@@ -347,6 +353,9 @@ inline void unpack_record(const DevCfg &c, const uint8_t *rec, const aie_state_d
     if (d.mt_pos) *d.mt_pos = hdr[HDR_MT_POS];
     if (d.t) *d.t = t;
     if (d.completions) *d.completions = hdr[HDR_COMPLETIONS];
+    if (d.stats) memcpy(d.stats, rec + c.off_stats, 8 * c.n_stats);
+    if (d.util_prev) memcpy(d.util_prev, rec + c.off_util_prev, 8 * (A + 1));
+    if (d.auto_warmup) *d.auto_warmup = hdr[HDR_AUTO_WARMUP];
     if (d.book_rows && d.book_count) {
         const uint32_t *orders = (const uint32_t *)(rec + c.off_orders);
         struct Row { int agent, price, life; };

@@ -26,6 +26,18 @@ enum : uint8_t {
 enum { HDR_T = 0, HDR_TAX_POS = 1, HDR_COMPLETIONS = 2, HDR_AUTO_WARMUP = 3, HDR_MT_POS = 4,
        HDR_ERR = 5, HDR_EPISODES = 6, HDR_RESERVED = 7, HDR_WORDS = 8 };
 
+// Episode statistics ("stats" section of the record, float64, zeroed at reset): what the reference's component
+// get_metrics() need beyond the live state (build.py:198-222, continuous_double_auction.py:585-641,
+// redistribution.py:1141-1186).  Counts are stored as doubles (exact below 2^53).
+//   [ST_N_TRADES]                                   executed trades
+//   [ST_BUILDS + a]                                 houses built by agent a
+//   [st_trade + (((a*2 + c)*2 + side)*2 + k)]       side 0 = as seller, 1 = as buyer; k 0 = count, 1 = sum of prices
+//   [st_tax + ST_TAX_*]  (only with PeriodicBracketTax) periods enacted, total collected, sum of effective rates,
+//                        sum of each bracket's rate over periods [16], bracket occupancy [16],
+//                        then per agent: sum of max(0, income) over tax days [A], sum of tax paid [A]
+enum { ST_N_TRADES = 0, ST_BUILDS = 1 };
+enum { ST_TAX_PERIODS = 0, ST_TAX_COLLECTED = 1, ST_TAX_EFF_SUM = 2, ST_TAX_SCHED = 3, ST_TAX_OCC = 19, ST_TAX_AGENT = 35 };
+
 enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3 };
 enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
 
@@ -80,7 +92,8 @@ struct DevCfg {
     // record layout (byte offsets)
     int32_t off_coin, off_esc_coin, off_labor, off_bpay, off_bskill, off_bonus, off_last_coin, off_last_income,
         off_last_marg, off_util_prev, off_price_hist, off_inv, off_esc, off_loc, off_n_orders, off_bid_hist,
-        off_ask_hist, off_rate_idx, off_cell, off_owner, off_orders, off_mt;
+        off_ask_hist, off_rate_idx, off_cell, off_owner, off_orders, off_mt, off_stats;
+    int32_t n_stats, st_trade, st_tax;  // stats section: doubles, sub-offsets (st_tax < 0: no tax component)
     int32_t obs_prefix_bytes, rec_bytes;
     // Large envs (deep order books, many agents) keep the two big, sparsely touched sections - price history and
     // order slots, laid out last - in HBM/L2 and stage only [0, resident_bytes) in shared memory (split != 0).
@@ -98,7 +111,7 @@ struct DevCfg {
 
 // raw device pointers (mirrors aie_buffers)
 struct DevBufs {
-    uint8_t *state, *state0;
+    uint8_t *state, *state0, *final;  // final: optional end-of-episode record snapshots (auto-reset)
     const int32_t *act_a, *act_p;
     float *a_map; int16_t *a_idx; float *a_flat; float *a_mask;
     float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask;

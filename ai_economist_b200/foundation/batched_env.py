@@ -382,13 +382,26 @@ class BatchedFoundationEnv:
 
     @property
     def metrics(self):
-        """Scenario metrics of env 0 that derive from current state (layout_from_file.py:595-650 subset)."""
-        d = self._stepper.read_state(0)
-        tot = d["coin"] + d["esc_coin"]
-        out = {"social/productivity": float(tot.sum())}
-        for i in range(self.n_agents):
-            out["endow/%d/Coin" % i] = float(tot[i])
-            out["endow/%d/Stone" % i] = int(d["inv"][i, 0] + d["esc"][i, 0])
-            out["endow/%d/Wood" % i] = int(d["inv"][i, 1] + d["esc"][i, 1])
-            out["endogenous/%d/Labor" % i] = float(d["labor"][i])
-        return out
+        """The combined scenario + component metrics of env 0 (BaseEnvironment.metrics, base_env.py:421-432)."""
+        return self.metrics_of(0)
+
+    def metrics_of(self, e):
+        """`env.metrics` of replica e: layout_from_file.py:595-650 + every component's get_metrics(), computed from the
+        replica's state record (the event logs are device-side running sums, see foundation/metrics.py)."""
+        from .metrics import metrics_from_state
+        return metrics_from_state(self._spec, self._stepper.read_state(e))
+
+    @property
+    def previous_episode_metrics(self):
+        """Metrics of the episode env 0 finished last (base_env.py:414-418); None before the first auto-reset."""
+        return self.previous_episode_metrics_of(0)
+
+    def previous_episode_metrics_of(self, e):
+        from .metrics import metrics_from_state
+        st = self._stepper
+        if "episode_final" not in st.buf:
+            return None
+        fin = st.read_state(e, final=True)
+        if int(fin["t"][0]) == 0:   # nothing recorded yet
+            return None
+        return metrics_from_state(self._spec, fin)

@@ -45,6 +45,8 @@ class BatchStepper:
             "reward": ("f64", (E, A + 1)),
             "done": ("i32", (E,)),
         }
+        if auto_reset:  # end-of-episode record snapshots (previous_episode_metrics)
+            shapes["episode_final"] = ("u8", (E, d.state_bytes))
         if not spec["planner_gets_spatial_info"]:
             del shapes["obs_planner_map"], shapes["obs_planner_idx"]
         self.buf = {k: self._alloc(shape, dt) for k, (dt, shape) in shapes.items()}
@@ -139,8 +141,9 @@ class BatchStepper:
             self._fields[name] = f
         return self._fields[name]
 
-    def read_state(self, e):
-        """Debug readback of env e in the test oracle's layout (dict of numpy arrays + 'books')."""
+    def read_state(self, e, final=False):
+        """Readback of env e in the test oracle's layout (dict of numpy arrays + 'books').  final=True reads the
+        end-of-episode snapshot of the env's last finished episode instead (auto-reset only; no order books)."""
         A, H, W = self.spec["n_agents"], self.spec["height"], self.spec["width"]
         P = self.spec["max_bid_ask"] + 1 if "ContinuousDoubleAuction" in self.spec["components"] else 1
         B = max(1, self.spec["n_brackets"])
@@ -156,12 +159,14 @@ class BatchStepper:
             mt_key=np.zeros(624, np.uint32), mt_pos=np.zeros(1, np.int32), t=np.zeros(1, np.int32),
             completions=np.zeros(1, np.int32),
             book_rows=np.zeros((2, 2, cap, 3), np.int32), book_count=np.zeros((2, 2), np.int32),
+            stats=np.zeros(self.dims.n_stats), util_prev=np.zeros(A + 1), auto_warmup=np.zeros(1, np.int32),
         )
         d = _abi.AieStateDump()
-        for k in _abi._DUMP_PTRS:
+        for k in _abi._DUMP_PTRS + _abi._DUMP_PTRS2:
             setattr(d, k, out[k].ctypes.data_as(C.c_void_p))
         d.book_cap = cap
-        self._check(self.lib.aie_read_state(self._h, int(e), C.byref(d)))
+        fn = self.lib.aie_read_episode_final if final else self.lib.aie_read_state
+        self._check(fn(self._h, int(e), C.byref(d)))
         out["books"] = {(c, s): out["book_rows"][c, s, :out["book_count"][c, s]].copy()
                         for c in (0, 1) for s in (0, 1)}
         return out

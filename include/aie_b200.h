@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AIE_ABI_VERSION 1
+#define AIE_ABI_VERSION 2
 
 #define AIE_MAX_COMPONENTS 4
 #define AIE_MAX_BRACKETS 16
@@ -122,6 +122,14 @@ typedef struct aie_dims {
     int32_t n_act_planner;    /* ints per env per step for the planner (n_brackets or 0) */
     int32_t state_bytes;      /* bytes per env of the packed state record (multiple of 16) */
     int32_t algorithmic_bytes_per_env_step; /* obs+mask+rew/done out + actions in + 2*state */
+    /* episode statistics ("stats" field of the state record, float64[n_stats], zero at reset): the accumulators
+     * behind the reference's component get_metrics() (build.py:198-222, continuous_double_auction.py:585-641,
+     * redistribution.py:1141-1186).  Layout: [0] executed trades; [1 + a] houses built by agent a;
+     * [stats_trade + ((a*2 + commodity)*2 + side)*2 + k] side 0 = as seller / 1 = as buyer, k 0 = count / 1 = sum
+     * of trade prices; from stats_tax (-1 without PeriodicBracketTax): periods enacted, total collected, sum of
+     * effective rates, sum of bracket rates over periods [16], bracket occupancy [16], sum of max(0, income)
+     * over tax days [A], sum of tax paid [A]. */
+    int32_t n_stats, stats_trade, stats_tax;
 } aie_dims;
 
 /* Raw device pointers.  All tensors are contiguous, env-major.
@@ -148,6 +156,9 @@ typedef struct aie_buffers {
     float *obs_time;            /* [E] */
     double *reward;             /* [E, A+1] */
     int32_t *done;              /* [E] */
+    void *episode_final;        /* optional (may be NULL): uint8 [E, state_bytes]; with auto_reset, the state record
+                                   of an env as it stood at the end of its last finished episode, i.e. what
+                                   BaseEnvironment.previous_episode_metrics is computed from (base_env.py:414-418) */
 } aie_buffers;
 
 /* Host-side post-reset snapshot of n envs (struct of arrays, env-major), i.e. what the reference holds
@@ -185,6 +196,9 @@ typedef struct aie_state_dump {
                              the reference stores its lists (continuous_double_auction.py:246-253, 349-350) */
     int32_t *book_count;  /* [2][2] */
     int32_t book_cap;     /* capacity (rows) per (commodity, side) of book_rows */
+    double *stats;        /* [n_stats] episode statistics (aie_dims) */
+    double *util_prev;    /* [A+1] curr_optimization_metric of agents then planner (layout_from_file.py:160-163) */
+    int32_t *auto_warmup; /* [1] _auto_warmup_integrator */
 } aie_state_dump;
 
 /* A named view into the packed state record, for host frameworks that want struct-of-arrays
@@ -252,6 +266,10 @@ int aie_step_host(aie_env *env, const int32_t *actions_agent_host, const int32_t
 
 /* Test/debug readback of env `e` (synchronous). */
 int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out);
+/* Same readback from the episode_final snapshot of env e (the record as it stood when its last finished episode
+ * ended, before the auto-reset): the input of previous_episode_metrics (base_env.py:414-418).  Order books are
+ * not part of the snapshot (book_rows / book_count are ignored).  AIE_ESTATE when no episode_final buffer is bound. */
+int aie_read_episode_final(aie_env *env, int32_t env_index, const aie_state_dump *out);
 
 /* Number of kernels the library has launched on this handle since creation (for bench "gpu_launches"). */
 int64_t aie_launch_count(const aie_env *env);

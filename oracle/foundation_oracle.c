@@ -47,6 +47,17 @@ typedef struct {
     double curr_rates_obs[ORC_MAX_BRACKETS];
     double *last_coin, *last_income, *last_marg, *last_income_obs, *last_income_obs_sorted;
     double planner_mask_rates[ORC_MAX_RATES]; /* "new_taxes" mask for this episode */
+    /* Episode logs behind get_metrics(), kept as running sums:
+     *   Build.builds (build.py:150-159, 208-212): builds per agent
+     *   ContinuousDoubleAuction.executed_trades (:316, 612-620): per (agent, commodity, seller/buyer) count + price sum
+     *   PeriodicBracketTax._schedules / _occupancy / all_effective_tax_rates / total_collected_taxes / taxes
+     *   (redistribution.py:862-905, 1149-1180) */
+    double *n_builds;               /* [A] */
+    double n_trades;
+    double *trade_n, *trade_price;  /* [A][2 commodities][2: 0 as seller, 1 as buyer] */
+    double tax_periods, tax_collected, tax_eff_sum;
+    double tax_sched_sum[ORC_MAX_BRACKETS], tax_occupancy[ORC_MAX_BRACKETS];
+    double *tax_income_pos, *tax_paid; /* [A] sums over tax days of max(0, income) and tax_paid */
     /* Scenario reward trackers (layout_from_file.py:160-163) */
     double *curr_metric; /* [A+1], planner last */
     int auto_warmup_integrator;
@@ -252,6 +263,11 @@ orc_batch *orc_create(const orc_config *cfg, int32_t n_envs) {
         s->last_income_obs = (double *)zalloc(sizeof(double) * A);
         s->last_income_obs_sorted = (double *)zalloc(sizeof(double) * A);
         s->curr_metric = (double *)zalloc(sizeof(double) * (A + 1));
+        s->n_builds = (double *)zalloc(sizeof(double) * A);
+        s->trade_n = (double *)zalloc(sizeof(double) * A * 4);
+        s->trade_price = (double *)zalloc(sizeof(double) * A * 4);
+        s->tax_income_pos = (double *)zalloc(sizeof(double) * A);
+        s->tax_paid = (double *)zalloc(sizeof(double) * A);
         s->act_build = (int *)zalloc(sizeof(int) * A);
         s->act_move = (int *)zalloc(sizeof(int) * A);
         s->a_map = (float *)zalloc(sizeof(float) * A * (d->n_map_ch + 1) * d->win * d->win);
@@ -285,6 +301,7 @@ void orc_destroy(orc_batch *b) {
         free(s->last_coin); free(s->last_income); free(s->last_marg);
         free(s->last_income_obs); free(s->last_income_obs_sorted);
         free(s->curr_metric); free(s->act_build); free(s->act_move);
+        free(s->n_builds); free(s->trade_n); free(s->trade_price); free(s->tax_income_pos); free(s->tax_paid);
         free(s->a_map); free(s->a_idx); free(s->a_flat); free(s->a_mask);
         free(s->p_map); free(s->p_idx); free(s->p_flat); free(s->p_agents); free(s->p_mask);
         free(s->rew);
@@ -344,6 +361,7 @@ static void build_step(const orc_batch *b, env_t *s) {
             s->owner[k] = (int16_t)a;
             s->coin[a] += s->build_payment[a];
             s->labor[a] += b->cfg.build_labor;
+            s->n_builds[a] += 1; /* self.builds[-1].append({builder, loc, income}) :150-159 */
         }
     }
 }
@@ -454,6 +472,10 @@ static void match_orders(const orc_batch *b, env_t *s) {
                     s->esc_coin[buyer] -= bid.price;
                     s->coin[seller] += price;
                     s->coin[buyer] += bid.price - price;
+                    /* executed_trades[-1].append(trade), cost == income == price :305-316 */
+                    s->n_trades += 1;
+                    s->trade_n[(seller * 2 + c) * 2 + 0] += 1; s->trade_price[(seller * 2 + c) * 2 + 0] += price;
+                    s->trade_n[(buyer * 2 + c) * 2 + 1] += 1;  s->trade_price[(buyer * 2 + c) * 2 + 1] += price;
                     break;
                 }
             }
@@ -598,18 +620,32 @@ static int cmp_double_idx(const void *x, const void *y) {
 
 /* enact_taxes :853-915 */
 static void enact_taxes(const orc_batch *b, env_t *s) {
-    int A = b->cfg.n_agents, a;
-    double net = 0.0, lump;
+    int A = b->cfg.n_agents, B = b->cfg.n_brackets, a, i;
+    double net = 0.0, lump, rates[ORC_MAX_BRACKETS];
+    curr_marginal_rates(b, s, rates);
+    for (i = 0; i < B; i++) s->tax_sched_sum[i] += rates[i]; /* _schedules[k].append(rate) :862-867 */
+    s->tax_periods += 1;
     for (a = 0; a < A; a++) {
         double income = (s->coin[a] + s->esc_coin[a]) - s->last_coin[a];
         double due = taxes_due(b, s, income);
         double eff = fmin(s->coin[a], due); /* don't take from escrow */
         double marg = marginal_rate(b, s, income);
+        int bin = 0, found = 0;
         s->coin[a] -= eff;
         net += eff;
         s->last_income[a] = income;
         s->last_marg[a] = marg;
+        s->tax_eff_sum += eff / fmax(0.000001, income); /* all_effective_tax_rates.append :880, 894 */
+        if (income >= 0) /* income_bin :828-835; negative income -> cutoff 0 = bracket 0 */
+            for (i = 0; i < B; i++) {
+                double lo = b->cfg.bracket_cutoffs[i], hi = (i + 1 < B) ? b->cfg.bracket_cutoffs[i + 1] : INFINITY;
+                if (income >= lo && income < hi && !found) { bin = i; found = 1; }
+            }
+        s->tax_occupancy[bin] += 1;               /* :895 */
+        s->tax_income_pos[a] += fmax(0.0, income); /* :1170-1175 via self.taxes */
+        s->tax_paid[a] += eff;
     }
+    s->tax_collected += net; /* :897 */
     lump = net / A;
     for (a = 0; a < A; a++) {
         s->coin[a] += lump;
@@ -1026,6 +1062,13 @@ int orc_load_env(orc_batch *b, int32_t e,
     s->t = 0;
     s->done = 0;
     if (b->has[ORC_COMP_TAX]) tax_reset(b, s);
+    /* component resets clear the episode logs (build.py:256, continuous_double_auction.py:664, redistribution.py:1131-1135) */
+    memset(s->n_builds, 0, sizeof(double) * A);
+    s->n_trades = 0;
+    memset(s->trade_n, 0, sizeof(double) * A * 4); memset(s->trade_price, 0, sizeof(double) * A * 4);
+    s->tax_periods = s->tax_collected = s->tax_eff_sum = 0;
+    memset(s->tax_sched_sum, 0, sizeof(s->tax_sched_sum)); memset(s->tax_occupancy, 0, sizeof(s->tax_occupancy));
+    memset(s->tax_income_pos, 0, sizeof(double) * A); memset(s->tax_paid, 0, sizeof(double) * A);
     /* planner "new_taxes" mask for this episode (redistribution.py:1051-1092) */
     for (r = 0; r < b->cfg.n_disc_rates; r++) {
         if (!b->cfg.tax_annealing) s->planner_mask_rates[r] = 1.0;
@@ -1185,6 +1228,28 @@ int orc_get_state(const orc_batch *b, int32_t e, uint8_t *cell, int8_t *owner, i
     if (mt_pos) *mt_pos = s->mt_pos;
     if (t) *t = s->t;
     return 0;
+}
+
+/* Episode statistics of env e, packed in the layout include/aie_b200.h documents for aie_dims.n_stats
+ * (n = 1 + A + 8A [+ 35 + 2A with the tax component]); also the scenario's reward trackers. */
+int orc_get_stats(const orc_batch *b, int32_t e, double *stats, double *curr_metric, int32_t *auto_warmup) {
+    const env_t *s = &b->envs[e];
+    int A = b->cfg.n_agents, a, i, n = 0;
+    if (stats) {
+        stats[n++] = s->n_trades;
+        for (a = 0; a < A; a++) stats[n++] = s->n_builds[a];
+        for (i = 0; i < 4 * A; i++) { stats[n++] = s->trade_n[i]; stats[n++] = s->trade_price[i]; }
+        if (b->has[ORC_COMP_TAX]) {
+            stats[n++] = s->tax_periods; stats[n++] = s->tax_collected; stats[n++] = s->tax_eff_sum;
+            for (i = 0; i < 16; i++) stats[n++] = i < ORC_MAX_BRACKETS ? s->tax_sched_sum[i] : 0.0;
+            for (i = 0; i < 16; i++) stats[n++] = i < ORC_MAX_BRACKETS ? s->tax_occupancy[i] : 0.0;
+            for (a = 0; a < A; a++) stats[n++] = s->tax_income_pos[a];
+            for (a = 0; a < A; a++) stats[n++] = s->tax_paid[a];
+        }
+    }
+    if (curr_metric) memcpy(curr_metric, s->curr_metric, sizeof(double) * (A + 1));
+    if (auto_warmup) *auto_warmup = s->auto_warmup_integrator;
+    return n;
 }
 
 int orc_get_book(const orc_batch *b, int32_t e, int32_t c, int32_t side, int32_t *rows, int32_t cap) {

@@ -75,6 +75,8 @@ def lib():
         L.orc_get_state.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 20
         L.orc_get_book.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
         L.orc_get_book.restype = C.c_int32
+        L.orc_get_stats.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_get_stats.restype = C.c_int32
         L.orc_rng_words.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.orc_rng_rand.argtypes = [C.c_void_p, C.c_int32]
         L.orc_rng_rand.restype = C.c_double
@@ -201,6 +203,13 @@ class OracleBatch:
                                            "n_orders", "bid_hist", "ask_hist", "price_hist", "tax_pos",
                                            "rate_idx", "last_coin", "last_income", "last_marg", "mt_key",
                                            "mt_pos", "t"]])
+        has_tax = "PeriodicBracketTax" in self.spec["components"]
+        n_stats = 1 + A + 8 * A + ((35 + 2 * A) if has_tax else 0)
+        out["stats"] = np.zeros(n_stats)
+        out["util_prev"] = np.zeros(A + 1)
+        out["auto_warmup"] = np.zeros(1, np.int32)
+        n = lib().orc_get_stats(self._h, e, _p(out["stats"]), _p(out["util_prev"]), _p(out["auto_warmup"]))
+        assert n == n_stats, (n, n_stats)
         return out
 
     def book(self, e, c, side):

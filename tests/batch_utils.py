@@ -65,6 +65,10 @@ def compare_env(orc, stepper, e, label, spatial=True, rtol=1e-6, skip=()):
             continue
         assert np.allclose(os_[k], np.asarray(ps[k]).reshape(os_[k].shape), rtol=rtol, atol=1e-9), \
             "%s env %d: state %s" % (label, e, k)
+    # episode statistics behind env.metrics (running sums of the reference's event logs) and the reward trackers
+    assert np.allclose(os_["stats"], ps["stats"], rtol=rtol, atol=1e-9), "%s env %d: episode statistics" % (label, e)
+    if "util_prev" not in skip:
+        assert np.allclose(os_["util_prev"], ps["util_prev"], rtol=rtol, atol=1e-9), "%s env %d: util_prev" % (label, e)
     for c in (0, 1):
         for s in (0, 1):
             assert np.array_equal(orc.book(e, c, s), ps["books"][(c, s)]), "%s env %d: book %d/%d" % (label, e, c, s)

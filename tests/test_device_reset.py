@@ -59,3 +59,38 @@ def test_emulated_device_reset_matches_reference_across_episodes(path):
 @pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p))
 def test_cuda_device_reset_matches_reference_across_episodes(path):
     _replay(path, None)
+
+
+def _replay_previous_episode_metrics(path, factory):
+    """env.previous_episode_metrics after each auto-reset == the reference's after its env.reset()."""
+    import json
+    from tests.metrics_utils import compare_metrics
+    ref = json.load(open(path.replace("golden_reset", "golden_metrics_reset").replace(".npz", ".json")))
+    want = dict(zip(ref["steps"], ref["metrics"]))
+    z, meta, init = gu.load_fixture(path)
+    env = _env(meta, factory)
+    env.seed([meta["seed"], meta["seed"]])
+    env.reset()
+    assert env.previous_episode_metrics_of(1) is None
+    A, seen = env.n_agents, 0
+    for t in range(1, int(meta["n_steps"]) + 1):
+        acts = {str(i): np.repeat(z["act_a"][t - 1][i][None], 2, axis=0) for i in range(A)}
+        if z["act_p"].shape[1]:
+            acts["p"] = np.repeat(z["act_p"][t - 1][None], 2, axis=0)
+        env.step(acts)
+        if t in want:
+            compare_metrics(want[t], env.previous_episode_metrics_of(1), "episode ending at t=%d" % t)
+            seen += 1
+    assert seen >= 2
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p))
+def test_emulated_previous_episode_metrics_match_reference(path):
+    from tests.emu.emu_stepper import emu_factory
+    _replay_previous_episode_metrics(path, emu_factory)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p))
+def test_cuda_previous_episode_metrics_match_reference(path):
+    _replay_previous_episode_metrics(path, None)
