@@ -206,8 +206,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
         }
     }
     __syncwarp();
-    uint8_t *obs_scratch = c.obs_alias_mt ? rec + c.off_mt : scratch + c.step_scratch_bytes;
-    if (emit_obs) observe_env(c, rec, grec, obs_scratch, obs_out_for(c, b, env), tab, lane);
+    if (emit_obs) observe_env(c, rec, grec, rec + c.off_mt, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
     if (lane == 0) bulk_wait_read();
 }
 
@@ -260,7 +259,7 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    observe_env(c, rec, grec, c.obs_alias_mt ? rec + c.off_mt : rec + c.resident_bytes + c.step_scratch_bytes,
+    observe_env(c, rec, grec, rec + c.off_mt, rec + c.resident_bytes + c.step_scratch_bytes,
                 obs_out_for(c, b, env), tab, lane);
 }
 
@@ -295,22 +294,35 @@ int init(aie_env *env) {
     const DevCfg &c = env->cfg;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_env = (size_t)c.resident_bytes + c.step_scratch_bytes + c.obs_extra_bytes;
-    int wpb = 8;
-    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v == 1 || v == 2 || v == 4 || v == 8) wpb = v; }
+    // envs (warps) per CTA: the count in 1..8 that keeps the most warps resident per SM (shared memory is the limit;
+    // at most 32 warps = 4 CTAs x 8 with the 64-register variant); ties go to the larger CTA.  AIE_STEP_WPB overrides.
     const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;
-    while (wpb > 1 && align16(8 * wpb) + tabs + wpb * per_env > max_smem / 2) wpb >>= 1;  // keep >= 2 CTAs per SM when possible
-    if (align16(8 * wpb) + tabs + wpb * per_env > max_smem) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
+    auto cta_smem = [&](int w) { return align16(8 * w) + tabs + (size_t)w * per_env; };
+    int wpb = 0, best_warps = 0;
+    for (int w = 8; w >= 1; w--) {
+        if (cta_smem(w) > max_smem) continue;
+        int ctas = (int)(prop.sharedMemPerMultiprocessor / (cta_smem(w) + 1024));
+        if (ctas * w > 32) ctas = 32 / w;
+        if (ctas * w > best_warps) { best_warps = ctas * w; wpb = w; }
+    }
+    if (wpb == 0) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
+    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v >= 1 && v <= 8 && cta_smem(v) <= max_smem) wpb = v; }
     env->be.step_wpb = wpb;
-    env->be.step_smem = align16(8 * wpb) + tabs + wpb * per_env;
+    env->be.step_smem = cta_smem(wpb);
     env->be.obs_threads = wpb * 32;
     env->be.obs_smem = env->be.step_smem;
-    // 4 resident CTAs per SM when shared memory allows: measured fastest on B200 (c2: 182 us; 3 CTAs 192 us, 5 CTAs
-    // 213 us - the tighter register budget of the 5-CTA variant costs more than its extra warps hide).  Override:
-    // AIE_STEP_MINB=3|4|5.
+    // Register budget: the 64-register variant (launch bounds 256 x 4) when more than 24 warps can be resident - measured
+    // fastest on B200 for c2 (32 warps: 151 us; 24 warps at 80 registers 182 us; 40 warps at 48 registers 213 us) -
+    // otherwise the 80-register variant, which does not spill.  Override: AIE_STEP_MINB=3|4|5.
     const size_t smem_sm = prop.sharedMemPerMultiprocessor;
     int fit = (int)(smem_sm / (env->be.step_smem + 1024));
-    env->be.step_minb = fit >= 4 ? 4 : 3;
+    const int resident_warps = (fit * wpb > 32) ? 32 : fit * wpb;
+    env->be.step_minb = resident_warps > 24 ? 4 : 3;
     if (const char *ov = getenv("AIE_STEP_MINB")) { int v = atoi(ov); if (v >= 3 && v <= 5) env->be.step_minb = v; }
+    if (getenv("AIE_VERBOSE"))
+        fprintf(stderr, "[aie] record %d B (resident %d, obs prefix %d), step scratch %d, obs scratch %d (alias mt %d), per env %zu B, "
+                        "%d envs/CTA, %zu B smem/CTA, register variant %d, %d CTAs/SM fit\n", c.rec_bytes, c.resident_bytes, c.obs_prefix_bytes,
+                c.step_scratch_bytes, c.obs_scratch_bytes, c.obs_alias_mt, per_env, wpb, env->be.step_smem, env->be.step_minb, fit);
     const int sm = (int)env->be.step_smem;
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");

@@ -925,16 +925,22 @@ struct ObsScratch {
     uint8_t *locmap;      // [HW]  0 none, a+2
     uint8_t *wstage;      // [3][ww] one agent's window: cell bits | 0x40 inside, owner code, agent-location code
 };
-AIE_DEV ObsScratch obs_scratch_view(uint8_t *p, const DevCfg &c) {
+// mt_img: the dead shared-memory image of the MT19937 key (nullptr when it is live, e.g. in emulation); extra: the
+// additional staging memory.  Each group goes where the host decided (DevCfg::obs_alias_mt).
+AIE_DEV ObsScratch obs_scratch_view(uint8_t *mt_img, uint8_t *extra, const DevCfg &c) {
     ObsScratch s;
+    const int alias = mt_img ? c.obs_alias_mt : 0;
+    uint8_t *pb = (alias & 1) ? mt_img : extra;                                       // byte group
+    uint8_t *p = (alias & 2) ? mt_img + ((alias & 1) ? c.obs_bytes_size : 0)          // float group
+                             : extra + ((alias & 1) ? 0 : c.obs_bytes_size);
     s.net_hist = (double *)p;     p += 8 * (2 * c.P + 2);
     s.shf = (float *)p;           p += 4 * c.sh_count;
     s.sc_a = (float *)p;          p += 4 * c.A * AS_COUNT;
-    s.agf = (float *)p;           p += 4 * (AS_COUNT + 8 * c.P);
-    s.lim = p;                    p += (c.A * MS_COUNT + 7) & ~7;
-    s.pbits = p;                  p += 8;
-    s.locmap = p;                 p += (c.HW + 3) & ~3;  // 4-byte aligned, padded to a multiple of 4 bytes
-    s.wstage = p;
+    s.agf = (float *)p;
+    s.lim = pb;                   pb += (c.A * MS_COUNT + 7) & ~7;
+    s.pbits = pb;                 pb += 8;
+    s.locmap = pb;                pb += (c.HW + 3) & ~3;  // 4-byte aligned, padded to a multiple of 4 bytes
+    s.wstage = pb;
     return s;
 }
 
@@ -1086,10 +1092,10 @@ AIE_DEV float flat_value(const float *shf, const float *agf, uint32_t entry) {
     return (AIE_FLAT_KIND(entry) == FK_AGENT ? agf : shf)[AIE_FLAT_PAYLOAD(entry)];
 }
 
-AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const ObsOut &o,
+AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *mt_img, uint8_t *extra, const ObsOut &o,
                          const uint16_t *tab, int lane) {
     const Env e = env_view(rec, grec, c);
-    const ObsScratch s = obs_scratch_view(scratch, c);
+    const ObsScratch s = obs_scratch_view(mt_img, extra, c);
     const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
     const double inv_scale = c.obs_scaling ? 0.01 : 1.0;
     const double time_v = (double)e.hdr[HDR_T] / (c.obs_scaling ? (double)c.T : 1.0);

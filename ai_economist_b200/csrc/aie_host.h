@@ -230,9 +230,18 @@ c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A
         c.split = (c.rec_bytes > 24 * 1024) ? 1 : 0;   // records this large would leave < 8 warps per SM resident
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
-        c.obs_scratch_bytes = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT + AS_COUNT + 8 * P) + A * MS_COUNT + 16 + c.HW + 4 + 3 * c.win * c.win + 24);
-        c.obs_alias_mt = (c.obs_scratch_bytes <= 4 * 624) ? 1 : 0;
-        c.obs_extra_bytes = c.obs_alias_mt ? 0 : c.obs_scratch_bytes;
+        c.obs_floats_size = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT + AS_COUNT + 8 * P));
+        c.obs_bytes_size = align16(((A * MS_COUNT + 7) & ~7) + 8 + ((c.HW + 3) & ~3) + 3 * c.win * c.win + 24);
+        c.obs_scratch_bytes = c.obs_floats_size + c.obs_bytes_size;
+        {
+            const int mt_bytes = 4 * 624;
+            if (c.obs_scratch_bytes <= mt_bytes) c.obs_alias_mt = 3;
+            else if (c.obs_bytes_size <= mt_bytes && c.obs_bytes_size >= c.obs_floats_size) c.obs_alias_mt = 1;
+            else if (c.obs_floats_size <= mt_bytes) c.obs_alias_mt = 2;
+            else if (c.obs_bytes_size <= mt_bytes) c.obs_alias_mt = 1;
+            else c.obs_alias_mt = 0;
+            c.obs_extra_bytes = ((c.obs_alias_mt & 1) ? 0 : c.obs_bytes_size) + ((c.obs_alias_mt & 2) ? 0 : c.obs_floats_size);
+        }
     }
     return AIE_OK;
 }

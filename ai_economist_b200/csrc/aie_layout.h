@@ -100,7 +100,10 @@ struct DevCfg {
     int32_t split, resident_bytes;
     // The observation pass runs after the record has been written back, when the MT19937 key's shared-memory image
     // is dead: its 2496 bytes double as the observation staging area when that fits (obs_alias_mt).
-    int32_t obs_alias_mt, obs_extra_bytes;
+    // The staging area has two groups - byte arrays (mask limits, agent-location map, window staging) and float arrays -
+    // and each group that fits is placed in the dead key image (obs_alias_mt: bit 0 = bytes, bit 1 = floats); the
+    // rest goes to obs_extra_bytes of additional shared memory per env.
+    int32_t obs_alias_mt, obs_extra_bytes, obs_bytes_size, obs_floats_size;
     // step-kernel scratch (per env, shared memory) and observe-kernel scratch
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;

@@ -109,7 +109,7 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
         o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
         o.p_flat = b.p_flat + e * c.Fp; o.p_agents = b.p_agents + e * A * c.Fpa;
         o.p_mask = b.p_mask + e * c.Np; o.time_obs = b.time_obs + e;
-        observe_env(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
+        observe_env(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
     }
     env->launches++;
     return AIE_OK;

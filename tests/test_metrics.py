@@ -38,4 +38,4 @@ def test_oracle_statistics_match_emulated_device_statistics():
 def test_cuda_metrics_match_reference_env_metrics(path):
     """The CUDA kernels' episode statistics -> env.metrics of the unmodified reference, through the C-ABI."""
     from ai_economist_b200.stepper import CudaStepper
-    assert mu.replay_and_check(path, lambda spec: CudaStepper(spec, 1)) >= 3
+    assert mu.replay_and_check(path, lambda spec: CudaStepper(spec, 1, auto_reset=False)) >= 3
