@@ -166,6 +166,11 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
             bulk_s2g(b.final + (size_t)env * c.rec_bytes, rec, (uint32_t)c.resident_bytes);
             bulk_wait_read();
         }
+        if (b.final && c.split) {  // the statistics of a split record live in global memory
+            const uint4 *src = (const uint4 *)(grec + c.off_stats);
+            uint4 *dst = (uint4 *)(b.final + (size_t)env * c.rec_bytes + c.off_stats);
+            for (int i = lane; i < (8 * c.n_stats + 15) / 16; i += 32) dst[i] = src[i];
+        }
         __syncwarp();
         if (lane == 0) {
             mbar_expect_tx(bar, (uint32_t)c.off_mt + (c.split ? 0u : tail));

@@ -105,7 +105,7 @@ AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     uint8_t *big = c.split ? grec : rec;
     e.hdr = (int32_t *)rec;
     e.coin = (double *)(rec + c.off_coin);
-    e.stats = (double *)(rec + c.off_stats);
+    e.stats = (double *)(big + c.off_stats);  // resident unless the config is split
     e.esc_coin = (double *)(rec + c.off_esc_coin);
     e.labor = (double *)(rec + c.off_labor);
     e.bpay = (double *)(rec + c.off_bpay);

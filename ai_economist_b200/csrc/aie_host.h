@@ -207,27 +207,33 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     // record layout
     {
         const int A = c.A, P = c.P;
-        int off = HDR_WORDS * 4;
-        auto take = [&](int bytes) { int o = off; off = align16(off + bytes); return o; };
-c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A);
-        c.off_bpay = take(8 * A); c.off_bskill = take(8 * A); c.off_bonus = take(8 * A);
-        c.off_last_coin = take(8 * A); c.off_last_income = take(8 * A); c.off_last_marg = take(8 * A);
-        c.off_util_prev = take(8 * (A + 1));
-        c.off_inv = take(4 * 2 * A); c.off_esc = take(4 * 2 * A);
-        c.off_loc = take(2 * 2 * A);
-        c.off_n_orders = take(2 * A); c.off_bid_hist = take(2 * A * P); c.off_ask_hist = take(2 * A * P);
-        c.off_rate_idx = take(16);
-        c.off_cell = take(c.HW); c.off_owner = take(c.HW);
-        c.obs_prefix_bytes = off;                      // [0, here): what the observation pass reads besides price_hist
         c.st_trade = ST_BUILDS + A;
         c.st_tax = c.has[COMP_TAX] ? c.st_trade + 8 * A : -1;
         c.n_stats = c.has[COMP_TAX] ? c.st_tax + ST_TAX_AGENT + 2 * A : c.st_trade + 8 * A;
-        c.off_stats = take(8 * c.n_stats);
-        c.off_mt = take(4 * 624);
-        c.off_price_hist = take(8 * 2 * A * P);
-        c.off_orders = take(4 * 2 * A * c.K);
-        c.rec_bytes = off;
+        // Large envs (split) keep the rarely touched episode statistics with the other big sections in global memory.
+        auto layout = [&](bool stats_last) {
+            int off = HDR_WORDS * 4;
+            auto take = [&](int bytes) { int o = off; off = align16(off + bytes); return o; };
+            c.off_coin = take(8 * A); c.off_esc_coin = take(8 * A); c.off_labor = take(8 * A);
+            c.off_bpay = take(8 * A); c.off_bskill = take(8 * A); c.off_bonus = take(8 * A);
+            c.off_last_coin = take(8 * A); c.off_last_income = take(8 * A); c.off_last_marg = take(8 * A);
+            c.off_util_prev = take(8 * (A + 1));
+            c.off_inv = take(4 * 2 * A); c.off_esc = take(4 * 2 * A);
+            c.off_loc = take(2 * 2 * A);
+            c.off_n_orders = take(2 * A); c.off_bid_hist = take(2 * A * P); c.off_ask_hist = take(2 * A * P);
+            c.off_rate_idx = take(16);
+            c.off_cell = take(c.HW); c.off_owner = take(c.HW);
+            c.obs_prefix_bytes = off;                  // [0, here): what the observation pass reads besides price_hist
+            if (!stats_last) c.off_stats = take(8 * c.n_stats);
+            c.off_mt = take(4 * 624);
+            c.off_price_hist = take(8 * 2 * A * P);
+            c.off_orders = take(4 * 2 * A * c.K);
+            if (stats_last) c.off_stats = take(8 * c.n_stats);
+            c.rec_bytes = off;
+        };
+        layout(false);
         c.split = (c.rec_bytes > 24 * 1024) ? 1 : 0;   // records this large would leave < 8 warps per SM resident
+        if (c.split) layout(true);
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
         c.obs_floats_size = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT + AS_COUNT + 8 * P));
