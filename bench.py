@@ -66,9 +66,11 @@ def committed_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
     capture of this same command (profiles/); None when no capture exists for the workload."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_%s_raw.csv" % kernel)
-    if workload != "c2" or not os.path.exists(path):
+    import glob
+    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_%s_raw.csv" % kernel)))  # newest round last
+    if workload != "c2" or not found:
         return None, None
+    path = found[-1]
     try:
         rows = list(csv.reader(open(path)))
         d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
