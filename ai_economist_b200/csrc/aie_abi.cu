@@ -108,25 +108,14 @@ __device__ __forceinline__ const uint16_t *stage_tables(uint8_t *smem, int wpb, 
 }
 
 __device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b, int env) {
-    const size_t A = c.A, ww = (size_t)c.win * c.win, e = (size_t)env;
-    ObsOut o;
-    o.a_map = b.a_map + e * A * (c.M + 1) * ww;
-    o.a_idx = b.a_idx + e * A * 2 * ww;
-    o.a_flat = b.a_flat + e * A * c.Fa;
-    o.a_mask = b.a_mask + e * A * c.Na;
-    o.p_map = c.planner_spatial ? b.p_map + e * c.M * c.HW : nullptr;
-    o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
-    o.p_flat = b.p_flat + e * c.Fp;
-    o.p_agents = b.p_agents + e * A * c.Fpa;
-    o.p_mask = b.p_mask + e * c.Np;
-    o.time_obs = b.time_obs + e;
+    ObsOut o; o.b = &b; o.c = &c; o.env = (size_t)env;
     return o;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
 template <int MINB, bool BIG>
-__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
+__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
                                                               const int emit_obs) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,7 +234,7 @@ __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_cons
 
 // Stand-alone observation pass (after a reset upload, or when the caller steps dynamics separately): one warp per
 // env, bulk-loads only the observable prefix of the record.
-__global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant__ DevCfg c, const DevBufs b, int lo, int n) {
+__global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b, int lo, int n) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * wpb + warp;

@@ -30,10 +30,12 @@
 
 #if defined(__CUDACC__) && !defined(AIE_EMU)
 #define AIE_DEV __device__ __forceinline__
+#define AIE_DEV_MEMBER __device__ __forceinline__
 #define AIE_DEV_NOINLINE __device__ __noinline__
 #define AIE_ON_DEVICE 1
 #else
 #define AIE_DEV static inline
+#define AIE_DEV_MEMBER inline
 #define AIE_DEV_NOINLINE static
 #define AIE_ON_DEVICE 0
 #endif
@@ -944,9 +946,21 @@ AIE_DEV ObsScratch obs_scratch_view(uint8_t *mt_img, uint8_t *extra, const DevCf
     return s;
 }
 
-struct ObsOut {  // pointers already offset to this env
-    float *a_map; int16_t *a_idx; float *a_flat; float *a_mask;
-    float *p_map; int16_t *p_idx; float *p_flat; float *p_agents; float *p_mask; float *time_obs;
+// Output slices of one env, computed where they are used (keeping ten 64-bit pointers live through the pass would
+// spill under the 64-register budget).
+struct ObsOut {
+    const DevBufs *b; const DevCfg *c; size_t env;
+    AIE_DEV_MEMBER size_t ww() const { return (size_t)c->win * c->win; }
+    AIE_DEV_MEMBER float *a_map() const { return b->a_map + env * c->A * (c->M + 1) * ww(); }
+    AIE_DEV_MEMBER int16_t *a_idx() const { return b->a_idx + env * c->A * 2 * ww(); }
+    AIE_DEV_MEMBER float *a_flat() const { return b->a_flat + env * c->A * c->Fa; }
+    AIE_DEV_MEMBER float *a_mask() const { return b->a_mask + env * c->A * c->Na; }
+    AIE_DEV_MEMBER float *p_map() const { return b->p_map + env * c->M * c->HW; }
+    AIE_DEV_MEMBER int16_t *p_idx() const { return b->p_idx + env * 2 * c->HW; }
+    AIE_DEV_MEMBER float *p_flat() const { return b->p_flat + env * c->Fp; }
+    AIE_DEV_MEMBER float *p_agents() const { return b->p_agents + env * c->A * c->Fpa; }
+    AIE_DEV_MEMBER float *p_mask() const { return b->p_mask + env * c->Np; }
+    AIE_DEV_MEMBER float *time_obs() const { return b->time_obs + env; }
 };
 
 // Contiguous output runs are written FRONT TO BACK with 16-byte stores: lanes take the 16-byte groups of the global
@@ -1145,7 +1159,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             s.sc_a[a * AS_COUNT + AS_TAX_LAST_MARG] = (float)e.last_marg[a];
         }
     }
-    if (lane == 0) { s.shf[SH_ZERO] = 0.0f; s.shf[SH_TIME] = (float)time_v; o.time_obs[0] = (float)time_v; }
+    if (lane == 0) { s.shf[SH_ZERO] = 0.0f; s.shf[SH_TIME] = (float)time_v; o.time_obs()[0] = (float)time_v; }
     wsync();
     for (int a = lane; a < A; a += NL) {
         const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
@@ -1200,9 +1214,9 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     // Every output tensor's env slice is one contiguous run (or a few) written front to back (store_run_*).
     // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc); 0x40 = "inside" plane
     if (c.planner_spatial) {
-        store_bitplanes_f32(o.p_map, M, HW, c.HW_magic, e.cell, s.pbits, lane);
-        store_bytes_i16<true>(o.p_idx, HW, (const uint8_t *)e.owner, lane);
-        store_bytes_i16<false>(o.p_idx + HW, HW, s.locmap, lane);
+        store_bitplanes_f32(o.p_map(), M, HW, c.HW_magic, e.cell, s.pbits, lane);
+        store_bytes_i16<true>(o.p_idx(), HW, (const uint8_t *)e.owner, lane);
+        store_bytes_i16<false>(o.p_idx() + HW, HW, s.locmap, lane);
     }
     // agent windows (layout_from_file.py:468-515): per agent, the window's cells are staged once as bytes (one lane
     // per window cell), then the M+1 map planes and the 2 index planes stream out of the staged bytes
@@ -1240,11 +1254,11 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
                     s.agf[AS_COUNT + 4 * P + i] = s.shf[c.sh_full + i] - mine;
                 }
             wsync();
-            store_bitplanes_f32(o.a_map + a * (M + 1) * ww, M + 1, ww, c.ww_magic, wc, s.pbits, lane);
-            store_bytes_i16<false>(o.a_idx + a * 2 * ww, 2 * ww, wi, lane);
+            store_bitplanes_f32(o.a_map() + a * (M + 1) * ww, M + 1, ww, c.ww_magic, wc, s.pbits, lane);
+            store_bytes_i16<false>(o.a_idx() + a * 2 * ww, 2 * ww, wi, lane);
             {
                 const float *shf = s.shf, *agf = s.agf;
-                store_run_f32(o.a_flat + a * c.Fa, c.Fa, lane, [=](int j) { return flat_value(shf, agf, tab[j]); });
+                store_run_f32(o.a_flat() + a * c.Fa, c.Fa, lane, [=](int j) { return flat_value(shf, agf, tab[j]); });
             }
             wsync();
         }
@@ -1253,14 +1267,14 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     {
         const float *shf = s.shf, *sc = s.sc_a;
         const uint16_t *tpa = tab + c.tab_pa, *tp = tab + c.tab_p;
-        store_rows_f32(o.p_agents, A, c.Fpa, c.Fpa_magic, lane,
+        store_rows_f32(o.p_agents(), A, c.Fpa, c.Fpa_magic, lane,
                        [=](int a, int j) { return flat_value(shf, sc + a * AS_COUNT, tpa[j]); });
-        store_run_f32(o.p_flat, c.Fp, lane, [=](int j) { return flat_value(shf, shf, tp[j]); });
+        store_run_f32(o.p_flat(), c.Fp, lane, [=](int j) { return flat_value(shf, shf, tp[j]); });
     }
     {
         const uint16_t *mt = tab + c.tab_m;
         const uint8_t *lim = s.lim;
-        store_rows_f32(o.a_mask, A, c.Na, c.Na_magic, lane, [=](int a, int j) {
+        store_rows_f32(o.a_mask(), A, c.Na, c.Na_magic, lane, [=](int a, int j) {
             const uint32_t en = mt[j];
             return ((en & 255u) < lim[a * MS_COUNT + (en >> 8)]) ? 1.0f : 0.0f;
         });
@@ -1271,10 +1285,10 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             for (int rr = lane; rr <= c.R; rr += NL) {
                 bool open = rr == 0 || first_day;
                 if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.net_hist[2 * P];
-                o.p_mask[b * (1 + c.R) + rr] = open ? 1.0f : 0.0f;
+                o.p_mask()[b * (1 + c.R) + rr] = open ? 1.0f : 0.0f;
             }
     } else if (lane == 0) {
-        o.p_mask[0] = 1.0f;
+        o.p_mask()[0] = 1.0f;
     }
 }
 

@@ -82,51 +82,77 @@ def committed_traffic(workload, kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region.
+
+    The sampler is started before the warm-up steps (nvidia-smi takes a few hundred ms to come up) at a 20 ms period;
+    mark_begin()/mark_end() bracket the timed region on the host clock and only samples time-stamped inside it are
+    reported.  If the region was shorter than one sampling period, the samples of the warm-up + timed window (the same
+    step loop, back to back) are reported instead and "window" says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_start = self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            self.t_start = time.time()
+            deadline = time.time() + 3.0
+            while not self.rows and time.time() < deadline:  # wait for the first sample: nvidia-smi is up
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        parsed = []
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                parsed.append((ts, float(f[1]), float(f[2]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+        t0, t1 = self.t0 or 0.0, self.t1 or time.time()
+        inside = [p for p in parsed if t0 <= p[0] <= t1 + 0.005]
+        window = "timed region"
+        if not inside:
+            inside = [p for p in parsed if (self.t_start or 0.0) <= p[0] <= t1 + 0.03]
+            window = "warm-up + timed region (timed region shorter than the 20 ms sampling period)"
+        sm, mx, reasons = [p[1] for p in inside], [p[2] for p in inside], set()
+        for p in inside:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def covid_oracle_rate(n_envs, steps, warmup=1):
@@ -251,19 +277,21 @@ def run_covid(args, rank, world, dev, E, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(dev.index or 0)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         st.sample_random_actions(seed=7 + rank); st.step()
     l0 = st.launch_count()
-    clocks = ClockSampler(dev.index or 0)
     barrier()
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
         st.sample_random_actions(seed=7 + rank); st.step()
     ev1.record()
     barrier()
+    clocks.mark_end()
     ms_total = ev0.elapsed_time(ev1)
     launches = st.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
@@ -348,8 +376,8 @@ def run_covid(args, rank, world, dev, E, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=None)
@@ -399,19 +427,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         one_step(i)
     launches0 = st.launch_count()
-    clocks = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        clocks.start()
+    clocks.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
         one_step(i)
     ev1.record()
     barrier()
+    clocks.mark_end()
     ms_total = ev0.elapsed_time(ev1)
     launches = st.launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None

@@ -102,13 +102,7 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
     const size_t A = c.A, ww = (size_t)c.win * c.win;
     for (int env_i = lo; env_i < lo + n; env_i++) {
         size_t e = env_i;
-        ObsOut o;
-        o.a_map = b.a_map + e * A * (c.M + 1) * ww; o.a_idx = b.a_idx + e * A * 2 * ww;
-        o.a_flat = b.a_flat + e * A * c.Fa; o.a_mask = b.a_mask + e * A * c.Na;
-        o.p_map = c.planner_spatial ? b.p_map + e * c.M * c.HW : nullptr;
-        o.p_idx = c.planner_spatial ? b.p_idx + e * 2 * c.HW : nullptr;
-        o.p_flat = b.p_flat + e * c.Fp; o.p_agents = b.p_agents + e * A * c.Fpa;
-        o.p_mask = b.p_mask + e * c.Np; o.time_obs = b.time_obs + e;
+        ObsOut o; o.b = &b; o.c = &c; o.env = e;
         observe_env(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
     }
     env->launches++;
