@@ -835,7 +835,8 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
 
 // Finish a host reset on the device: tax trackers + metric_0 (redistribution.py:1106-1139,
 // layout_from_file.py:588-593).  The host packer has already zeroed books, escrow, labor.
-AIE_DEV void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
+// Reset-only code is kept out of line: inlined it would triple the step kernel's code for a once-per-episode path.
+AIE_DEV_NOINLINE void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     for (int a = lane; a < c.A; a += NL) {
@@ -902,7 +903,7 @@ AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, R
 }
 
 // What the step kernel does when an env finishes with auto_reset on and reset_mode == 1, after the snapshot restore.
-AIE_DEV void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
+AIE_DEV_NOINLINE void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;

@@ -6,16 +6,14 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 run() { # label, bench-args (quoted), env...
   label=$1; shift; bargs=$1; shift
   env AIE_VERBOSE=1 "$@" timeout 600 python bench.py --no-cpu-baseline --e2e-steps 3 $bargs > gpurun_out/bench_$label.json 2> gpurun_out/bench_$label.err
-  grep -m1 "\[aie\]" gpurun_out/bench_$label.err
   python - <<PY
 import json
 try:
     d = json.load(open("gpurun_out/bench_$label.json"))
-    print("$label value %.3e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v["ms"]*1e3,1) for k, v in d["roofline"]["kernels"].items()}, d["roofline"]["kernels"].get("aie_step_kernel", {}).get("unfused_ms"), d["clocks"])
+    print("$label value %.3e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v["ms"]*1e3,1) for k, v in d["roofline"]["kernels"].items()}, d["roofline"]["kernels"].get("aie_step_kernel", {}).get("unfused_ms"), d["clocks"]["sm_mhz"])
 except Exception as ex:
     print("$label FAILED", ex, open("gpurun_out/bench_$label.err").read()[-300:])
 PY
 }
 run c2 "" X=1
-run c2_200 "--steps 200 --warmup 20" X=1
-run c2_20 "--steps 20 --warmup 3" X=1
+run c3 "--workload c3 --steps 300" X=1
