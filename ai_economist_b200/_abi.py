@@ -54,7 +54,8 @@ _BUF_NAMES = ["state", "state0", "actions_agent", "actions_planner", "obs_agent_
 
 
 class AieBuffers(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in _BUF_NAMES]
+    _fields_ = [(n, C.c_void_p) for n in _BUF_NAMES] + [("events", C.c_void_p), ("event_envs", C.c_int32),
+                                                        ("event_cap", C.c_int32)]
 
 
 class AieHostState(C.Structure):

@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     decode_actions(c, step_scratch_view(scratch, c), act_a, act_p, lane);
     mbar_wait(bar, 0);
 
-    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane, true);
+    int32_t *events = (b.events && env < b.event_envs) ? b.events + (size_t)env * 8 * (b.event_cap + 1) : nullptr;
+    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane, true, events,
+                  b.event_cap);
 
     // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
     // from the load-time snapshot; the episode counters and the numpy stream carry on.

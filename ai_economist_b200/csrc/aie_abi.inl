@@ -87,6 +87,9 @@ int aie_bind_buffers(aie_env *env, const aie_buffers *b) {
     d.a_map = b->obs_agent_map; d.a_idx = b->obs_agent_idx; d.a_flat = b->obs_agent_flat; d.a_mask = b->mask_agent;
     d.p_map = b->obs_planner_map; d.p_idx = b->obs_planner_idx; d.p_flat = b->obs_planner_flat;
     d.p_agents = b->obs_planner_agents; d.p_mask = b->mask_planner; d.time_obs = b->obs_time;
+    d.events = b->events; d.event_envs = b->events ? b->event_envs : 0; d.event_cap = b->event_cap;
+    if (b->events && (b->event_envs < 0 || b->event_envs > env->n_envs || b->event_cap < 1))
+        return fail(AIE_EINVAL, "aie_bind_buffers: bad event log shape");
     d.rew = b->reward; d.done = b->done;  // d.tab was set by the backend at creation
     env->bound = true;
     return AIE_OK;

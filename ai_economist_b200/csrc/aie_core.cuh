@@ -98,12 +98,14 @@ struct Env {
     uint8_t *n_orders, *bid_hist, *ask_hist, *rate_idx, *cell;
     int8_t *owner;
     uint32_t *orders, *mt;
+    int32_t *ev; int32_t ev_cap;  // this env's event block for the current step, or nullptr (no dense log)
 };
 
 // rec: the resident image of the record (shared memory on the device); grec: the record in global memory, used for
 // the price-history / order-slot sections when the config is split (large envs).  In emulation rec == grec.
 AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     Env e;
+    e.ev = nullptr; e.ev_cap = 0;
     uint8_t *big = c.split ? grec : rec;
     e.hdr = (int32_t *)rec;
     e.coin = (double *)(rec + c.off_coin);
@@ -130,6 +132,16 @@ AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     e.orders = (uint32_t *)(big + c.off_orders);
     e.mt = (uint32_t *)(rec + c.off_mt);
     return e;
+}
+
+// Append one event row (called by the committing lane only).  Rows beyond the capacity are counted as dropped.
+AIE_DEV void emit_event(const Env &e, int kind, int a0, int a1 = 0, int a2 = 0, int a3 = 0, int a4 = 0, int a5 = 0, int a6 = 0) {
+    if (!e.ev) return;
+    const int n = e.ev[0];
+    if (n >= e.ev_cap) { e.ev[2] += 1; return; }
+    int32_t *row = e.ev + 8 * (n + 1);
+    row[0] = kind; row[1] = a0; row[2] = a1; row[3] = a2; row[4] = a3; row[5] = a4; row[6] = a5; row[7] = a6;
+    e.ev[0] = n + 1;
 }
 
 // per-env scratch of the step body (shared memory on the device)
@@ -297,6 +309,7 @@ AIE_DEV void build_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
                 e.coin[a] += e.bpay[a];
                 e.labor[a] += c.build_labor;
                 e.stats[ST_BUILDS + a] += 1.0;
+                emit_event(e, EV_BUILD, a, e.loc[2 * a], e.loc[2 * a + 1]);
             }
         }
         wsync();
@@ -472,6 +485,7 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int
                 double *ts = e.stats + c.st_trade + ((seller * 2 + cc) * 2 + 0) * 2;
                 double *tb = e.stats + c.st_trade + ((buyer * 2 + cc) * 2 + 1) * 2;
                 ts[0] += 1.0; ts[1] += (double)price; tb[0] += 1.0; tb[1] += (double)price;
+                emit_event(e, EV_TRADE, seller, buyer, cc, aprice, bprice, alife, blife);
             }
             wsync();
             refresh_best(c, slots, buyer, 0, t, bb_key, bb_slot, lane);
@@ -559,6 +573,7 @@ AIE_DEV void gather_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) 
                     e.inv[2 * a + cc] += n_gathered;
                     e.cell[k] = (uint8_t)(e.cell[k] & ~(1u << cc));
                     e.labor[a] += c.collect_labor;
+                    emit_event(e, EV_GATHER, a, cc, n_gathered, nr, nc);
                 }
             }
         }
@@ -805,9 +820,14 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 // ------------------------------------------------------------------------------------------------
 template <bool BIG>
 AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
-                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane, bool decoded = false) {
+                      const int32_t *act_p, double *rew_out, int32_t *done_out, int lane, bool decoded = false,
+                      int32_t *events = nullptr, int event_cap = 0) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
+    if (events) {  // dense-log replicas: this step's event block starts empty
+        e.ev = events; e.ev_cap = event_cap;
+        if (lane == 0) { events[0] = 0; events[1] = e.hdr[HDR_T] + 1; events[2] = 0; }
+    }
     if (!decoded) decode_actions(c, s, act_a, act_p, lane);  // the CUDA kernel decodes while the record is in flight
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
     const int t = e.hdr[HDR_T] + 1;

@@ -38,6 +38,12 @@ enum { HDR_T = 0, HDR_TAX_POS = 1, HDR_COMPLETIONS = 2, HDR_AUTO_WARMUP = 3, HDR
 enum { ST_N_TRADES = 0, ST_BUILDS = 1 };
 enum { ST_TAX_PERIODS = 0, ST_TAX_COLLECTED = 1, ST_TAX_EFF_SUM = 2, ST_TAX_SCHED = 3, ST_TAX_OCC = 19, ST_TAX_AGENT = 35 };
 
+// per-step event rows (int32[8]); row 0 of an env's block is the header {count, t, dropped, 0...}
+//   EV_BUILD  {kind, agent, row, col}
+//   EV_GATHER {kind, agent, resource (0 Stone, 1 Wood), n, row, col}
+//   EV_TRADE  {kind, seller, buyer, commodity, ask, bid, ask_lifetime, bid_lifetime}
+enum { EV_BUILD = 1, EV_GATHER = 2, EV_TRADE = 3 };
+
 enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3 };
 enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
 
@@ -122,6 +128,8 @@ struct DevBufs {
     // observation / mask programs in device memory (library-owned, written once at aie_create): indexed by the
     // thread-varying flat position, which would serialise on the constant bank if read from the kernel params
     const uint16_t *tab;
+    // optional per-step event log of the first event_envs replicas (dense logs): int32 [event_envs][event_cap + 1][8]
+    int32_t *events; int32_t event_envs, event_cap;
 };
 // compact program table: [agent flat (Fa) | planner flat (Fp) | p<i> flat (Fpa) | agent mask (Na)], offsets in DevCfg
 constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK;

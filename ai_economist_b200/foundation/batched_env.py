@@ -154,11 +154,25 @@ class BatchedFoundationEnv:
                 assert spec.get("reset_mode", 0) == 1, "reference-exact device reset is not available for this config"
         self._spec = spec
 
+        # ---- dense logging (base_env.py:273-283): replica 0, every dense_log_frequency-th episode ----
+        self._create_dense_log_every = None if dense_log_frequency is None else int(dense_log_frequency)
+        assert self._create_dense_log_every is None or self._create_dense_log_every >= 1
+        self._world_dense_log_frequency = int(world_dense_log_frequency)
+        assert self._world_dense_log_frequency >= 1
+        self._dense_logger = None
+        self._dense_log = {"world": [], "states": [], "actions": [], "rewards": []}
+        self._last_ep_dense_log = dict(self._dense_log)
+        self._auto_reset = bool(auto_reset)
+        event_envs = 0 if self._create_dense_log_every is None else 1
+
         if stepper_factory is None:
             from ..stepper import CudaStepper
-            self._stepper = CudaStepper(spec, self.n_envs, device=device, auto_reset=auto_reset)
+            self._stepper = CudaStepper(spec, self.n_envs, device=device, auto_reset=auto_reset, event_envs=event_envs)
         else:
-            self._stepper = stepper_factory(spec, self.n_envs, auto_reset)
+            try:
+                self._stepper = stepper_factory(spec, self.n_envs, auto_reset, event_envs=event_envs)
+            except TypeError:
+                self._stepper = stepper_factory(spec, self.n_envs, auto_reset)
         self._rs = None
         self._seeds = None
         self._loaded = False
@@ -282,7 +296,27 @@ class BatchedFoundationEnv:
             self._sync_streams_from_device()
         self._stepper.load_state(self.host_reset_arrays())
         self._loaded = True
+        self._start_dense_log(force_dense_logging, int(self._completions[0]))
         return self.obs
+
+    # ------------------------------------------------------------------ dense logs (base_env.py:440-452, 763-814)
+    @property
+    def dense_log(self):
+        """The contents of the current (potentially incomplete) dense log of replica 0."""
+        return self._dense_logger.log if self._dense_logger is not None else self._dense_log
+
+    @property
+    def previous_episode_dense_log(self):
+        return self._last_ep_dense_log
+
+    def _start_dense_log(self, force, completions):
+        every = self._create_dense_log_every
+        on = bool(force) or (every is not None and completions % every == 0)
+        if on and getattr(self._stepper, "event_envs", 0) < 1:
+            raise RuntimeError("dense logging needs dense_log_frequency to be set at construction (event buffer)")
+        from .dense_log import DenseLogger
+        self._dense_logger = DenseLogger(self, 0, self._world_dense_log_frequency) if on else None
+        self._dense_log = {"world": [], "states": [], "actions": [], "rewards": []}
 
     def _write_actions(self, actions):
         st = self._stepper
@@ -324,7 +358,22 @@ class BatchedFoundationEnv:
         `env.action_buffers` and calling step(env.action_buffers) avoids any copy."""
         assert self._loaded, "call reset() first"
         self._write_actions(actions)
+        lg = self._dense_logger
+        if lg is not None:
+            st = self._stepper
+            lg.before_step(st.to_numpy(st.buf["actions_agent"][0]), st.to_numpy(st.buf["actions_planner"][0])
+                           if st.dims.n_act_planner else None)
         self._stepper.step()
+        if lg is not None:
+            st = self._stepper
+            ended = bool(int(st.to_numpy(st.buf["done"][0])))
+            post = st.read_state(0, final=True) if (ended and self._auto_reset) else st.read_state(0)
+            lg.after_step(st.to_numpy(st.buf["reward"][0]), post)
+            if ended:  # _finalize_logs; under auto-reset the next episode of replica 0 has already begun
+                self._last_ep_dense_log = lg.finalize(post)
+                self._dense_logger = None
+                if self._auto_reset:
+                    self._start_dense_log(False, int(st.read_state(0)["completions"][0]))
         return self.obs, self.rew, self.done, self.info
 
     @property

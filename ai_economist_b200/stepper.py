@@ -16,7 +16,7 @@ class BatchStepper:
 
     _DTYPES = {"u8": np.uint8, "i16": np.int16, "i32": np.int32, "f32": np.float32, "f64": np.float64}
 
-    def __init__(self, spec, n_envs, lib, device_index=0, auto_reset=True):
+    def __init__(self, spec, n_envs, lib, device_index=0, auto_reset=True, event_envs=0):
         self.spec = dict(spec)
         self.n_envs = int(n_envs)
         self.lib = lib
@@ -49,10 +49,19 @@ class BatchStepper:
             shapes["episode_final"] = ("u8", (E, d.state_bytes))
         if not spec["planner_gets_spatial_info"]:
             del shapes["obs_planner_map"], shapes["obs_planner_idx"]
+        # per-step event log of the first event_envs replicas (dense logs): capacity = every agent builds, gathers both
+        # resources and every resting order trades
+        self.event_envs = max(0, min(int(event_envs), E))
+        K = int(spec.get("max_num_orders", 0) or 0) if "ContinuousDoubleAuction" in spec["components"] else 0
+        self.event_cap = int(min(1024, 3 * A + 2 * A * K + 8))
+        if self.event_envs:
+            shapes["events"] = ("i32", (self.event_envs, self.event_cap + 1, 8))
         self.buf = {k: self._alloc(shape, dt) for k, (dt, shape) in shapes.items()}
         bufs = _abi.AieBuffers()
         for name in _abi._BUF_NAMES:
             setattr(bufs, name, self._ptr(self.buf[name]) if name in self.buf else None)
+        bufs.events = self._ptr(self.buf["events"]) if self.event_envs else None
+        bufs.event_envs, bufs.event_cap = self.event_envs, self.event_cap
         self._check(lib.aie_bind_buffers(self._h, C.byref(bufs)))
         self._fields = {}
 
@@ -171,6 +180,14 @@ class BatchStepper:
                         for c in (0, 1) for s in (0, 1)}
         return out
 
+    def read_events(self, e):
+        """Events of replica e's last step (dense logs): list of int rows [kind, ...] (include/aie_b200.h)."""
+        blk = self.to_numpy(self.buf["events"][e])
+        n, dropped = int(blk[0, 0]), int(blk[0, 2])
+        if dropped:
+            raise _abi.AieError("event log overflow: %d events dropped (capacity %d)" % (dropped, self.event_cap))
+        return [tuple(int(v) for v in blk[1 + i]) for i in range(n)]
+
     def read_obs(self, e):
         """Host copy of env e's outputs in the oracle's obs layout (tests)."""
         g = lambda k: self.to_numpy(self.buf[k][e]) if k in self.buf else None
@@ -188,7 +205,7 @@ class CudaStepper(BatchStepper):
 
     _TORCH = None
 
-    def __init__(self, spec, n_envs, device="cuda:0", auto_reset=True, lib_path=None):
+    def __init__(self, spec, n_envs, device="cuda:0", auto_reset=True, lib_path=None, event_envs=0):
         import torch
 
         if not torch.cuda.is_available():
@@ -201,7 +218,7 @@ class CudaStepper(BatchStepper):
         self.device = torch.device("cuda", idx)
         lib = _abi.load_library(lib_path)
         with torch.cuda.device(self.device):
-            super().__init__(spec, n_envs, lib, device_index=idx, auto_reset=auto_reset)
+            super().__init__(spec, n_envs, lib, device_index=idx, auto_reset=auto_reset, event_envs=event_envs)
 
     def _alloc(self, shape, dt):
         t = self.torch

@@ -159,6 +159,13 @@ typedef struct aie_buffers {
     void *episode_final;        /* optional (may be NULL): uint8 [E, state_bytes]; with auto_reset, the state record
                                    of an env as it stood at the end of its last finished episode, i.e. what
                                    BaseEnvironment.previous_episode_metrics is computed from (base_env.py:414-418) */
+    int32_t *events;            /* optional (may be NULL): int32 [event_envs, event_cap + 1, 8], the per-step event log of
+                                   the first event_envs replicas, rewritten by every step - the source of the components'
+                                   dense logs (build.py:150-159, move.py:140-151, continuous_double_auction.py:293-316).
+                                   Row 0 of a replica's block = {count, t, dropped, 0...}; then `count` rows
+                                   {1 BUILD, agent, row, col} | {2 GATHER, agent, resource, n, row, col} |
+                                   {3 TRADE, seller, buyer, commodity, ask, bid, ask_lifetime, bid_lifetime} */
+    int32_t event_envs, event_cap;
 } aie_buffers;
 
 /* Host-side post-reset snapshot of n envs (struct of arrays, env-major), i.e. what the reference holds

@@ -30,8 +30,8 @@ def emu_lib():
 
 
 class EmuStepper(BatchStepper):
-    def __init__(self, spec, n_envs, auto_reset=False):
-        super().__init__(spec, n_envs, emu_lib(), device_index=0, auto_reset=auto_reset)
+    def __init__(self, spec, n_envs, auto_reset=False, event_envs=0):
+        super().__init__(spec, n_envs, emu_lib(), device_index=0, auto_reset=auto_reset, event_envs=event_envs)
 
     def _alloc(self, shape, dt):
         return np.zeros(shape, dtype=self._DTYPES[dt])
@@ -53,8 +53,8 @@ class EmuStepper(BatchStepper):
         return v.reshape([self.n_envs] + shape) if shape else v[:, 0]
 
 
-def emu_factory(spec, n_envs, auto_reset):
-    return EmuStepper(spec, n_envs, auto_reset=auto_reset)
+def emu_factory(spec, n_envs, auto_reset, event_envs=0):
+    return EmuStepper(spec, n_envs, auto_reset=auto_reset, event_envs=event_envs)
 
 
 class EmuCovidStepper:
