@@ -48,9 +48,13 @@ class EmuStepper(BatchStepper):
         n = int(np.prod(shape)) if shape else 1
         dt = {(1, 0, 0): np.uint8, (1, 0, 1): np.int8, (2, 0, 1): np.int16, (4, 0, 1): np.int32,
               (4, 0, 0): np.uint32, (8, 1, 1): np.float64}[(f.elem_bytes, f.is_float, f.is_signed)]
-        raw = np.ascontiguousarray(self.buf["state"][:, f.offset:f.offset + n * f.elem_bytes])
-        v = raw.view(dt)
-        return v.reshape([self.n_envs] + shape) if shape else v[:, 0]
+        state = self.buf["state"]   # a live strided view, like the CUDA stepper's
+        inner, s = [], np.dtype(dt).itemsize
+        for d in reversed(shape):
+            inner.insert(0, s)
+            s *= d
+        return np.ndarray(shape=[self.n_envs] + shape, dtype=dt, buffer=state, offset=f.offset,
+                          strides=[state.strides[0]] + inner)
 
 
 def emu_factory(spec, n_envs, auto_reset, event_envs=0):

@@ -1,0 +1,60 @@
+"""RL-framework adapters: WarpDrive-style names/spaces and the RLlib-style per-replica dict env,
+driven on the CPU through the emulated device code."""
+import numpy as np
+
+from ai_economist_b200 import adapters, foundation
+from oracle.configs import CONFIGS
+from tests.emu.emu_stepper import emu_factory
+
+
+def _env(n_envs=3):
+    kw = dict(CONFIGS["c3_reset"])
+    name = kw.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=n_envs, auto_reset=True, stepper_factory=emu_factory, **kw)
+    env.seed([11 + i for i in range(n_envs)])
+    return env
+
+
+def test_warpdrive_style_wrapper_names_spaces_and_zero_copy():
+    env = _env()
+    w = adapters.WarpDriveStyleEnvWrapper(env)
+    assert w.n_agents == env.n_agents + 1 and w.episode_length == env.episode_length
+    w.reset_all_envs()
+    A = env.n_agents
+    assert set(env.observation_space.keys()) == set(env.action_space.keys()) == {str(i) for i in range(A)} | {"p"}
+    assert env.action_space["0"].n == env.get_agent(0).action_spaces            # single-action agents
+    assert list(env.action_space["p"].nvec) == list(env.get_agent("p").action_spaces)
+    for k, sp in env.observation_space["0"].items():
+        assert tuple(sp.shape) == tuple(env.obs["0"][k].shape[1:]), k
+    # reserved names are views of the very buffers the kernels write
+    assert np.shares_memory(w.tensor("actions_a"), env.stepper.buf["actions_agent"])
+    assert np.shares_memory(w.tensor("rewards_a"), env.stepper.buf["reward"])
+    assert w.tensor("observations_a_flat").shape[:2] == (env.n_envs, A)
+    # a "policy" writes actions in place, the wrapper steps from the buffers
+    mask = w.tensor("observations_a_action_mask")
+    w.tensor("actions_a")[..., 0] = np.argmax(mask * (np.arange(mask.shape[-1]) > 0), axis=-1)
+    obs, rew, done, info = w.step_all_envs()
+    assert int(w.tensor("_timestep_")[0]) == 1 and w.tensor("rewards_p").shape == (env.n_envs,)
+    assert rew["0"].shape == (env.n_envs,) and not bool(done["__all__"][0])
+
+
+def test_rllib_style_dict_env_matches_direct_stepping():
+    env_a, env_b = _env(2), _env(2)
+    env_b.reset(); env_b.reset()    # the wrapper resets once at construction (like the reference's) and once below
+    d = adapters.MultiAgentDictEnv(env_a, e=1)
+    obs = d.reset()
+    assert d.observation_space["flat"].shape == obs["0"]["flat"].shape
+    assert d.observation_space_pl["flat"].shape == obs["p"]["flat"].shape
+    rng = np.random.RandomState(3)
+    for t in range(35):       # crosses an episode boundary (episode_length 30): summary becomes available
+        acts = {}
+        for i in range(env_a.n_agents):
+            m = obs[str(i)]["action_mask"]
+            acts[str(i)] = int(rng.choice(len(m), p=m / m.sum()))
+        full = {k: np.array([0, v], np.int32) for k, v in acts.items()}   # replica 0 idle, replica 1 acts
+        env_b.step(full)
+        obs, rew, done, info = d.step(acts)
+        ob, rb, db = env_b.reference_view(1)
+        assert np.array_equal(obs["0"]["flat"], ob["0"]["flat"]) and rew == rb and done == db
+    s = d.summary
+    assert s["completions"] == 1 and "social/productivity" in s
