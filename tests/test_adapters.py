@@ -58,3 +58,25 @@ def test_rllib_style_dict_env_matches_direct_stepping():
         assert np.array_equal(obs["0"]["flat"], ob["0"]["flat"]) and rew == rb and done == db
     s = d.summary
     assert s["completions"] == 1 and "social/productivity" in s
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_warpdrive_style_wrapper_on_cuda_is_zero_copy():
+    import torch
+    kw = dict(CONFIGS["c3_reset"])
+    name = kw.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=64, device="cuda:0", seeds=list(range(64)), **kw)
+    w = adapters.WarpDriveStyleEnvWrapper(env)
+    w.reset_all_envs()
+    assert w.tensor("actions_a").data_ptr() == env.stepper.buf["actions_agent"].data_ptr()
+    assert w.tensor("observations_a_world-map").is_cuda and w.tensor("rewards_a").shape == (64, env.n_agents)
+    mask = w.tensor("observations_a_action_mask")
+    w.tensor("actions_a")[..., 0] = torch.argmax(mask * (torch.arange(mask.shape[-1], device=mask.device) > 0), dim=-1)
+    w.step_all_envs()
+    assert int(w.tensor("_timestep_")[5]) == 1 and bool(torch.isfinite(w.tensor("rewards_a")).all())
+    d = adapters.MultiAgentDictEnv(env, e=7)
+    obs, rew, done, _ = d.step({"0": 0})
+    assert obs["p"]["flat"].dtype == np.float32 and set(rew) == {str(i) for i in range(env.n_agents)} | {"p"}
