@@ -3,10 +3,11 @@ import ctypes as C
 import os
 
 ABI_VERSION = 2
-MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 4, 16, 64
+MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 8, 16, 64
 AIE_OK = 0
 
-COMPONENT_KIND = {"Build": 0, "ContinuousDoubleAuction": 1, "Gather": 2, "PeriodicBracketTax": 3}
+COMPONENT_KIND = {"Build": 0, "ContinuousDoubleAuction": 1, "Gather": 2, "PeriodicBracketTax": 3,
+                  "WealthRedistribution": 4}
 
 CSRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 DEFAULT_LIB = os.path.join(CSRC_DIR, "libaie_b200.so")

@@ -798,6 +798,20 @@ AIE_DEV double np_pairwise_sum(const double *a, int n) {
     return res;
 }
 
+// ------------------------------------------------------------------------------------------------
+// WealthRedistribution (components/redistribution.py:52-68): every step all agents end up with the same total coin;
+// escrowed coin stays where it is, so inventory coin becomes (sum of inventory + escrow) / A - own escrow.
+// ------------------------------------------------------------------------------------------------
+AIE_DEV void wealth_step(const DevCfg &c, Env &e, const StepScratch &s, int lane) {
+    const int A = c.A;
+    for (int a = lane; a < A; a += NL) s.tmp[a] = e.coin[a] + e.esc_coin[a];
+    wsync();
+    const double target = np_pairwise_sum(s.tmp, A) / A;  // np.sum(ic + ec) / n_agents
+    wsync();
+    for (int a = lane; a < A; a += NL) e.coin[a] = target - e.esc_coin[a];
+    wsync();
+}
+
 AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, double *rew_out, int lane) {
     const int A = c.A;
     double *cur = s.tmp;  // [A+1] new metrics; the second half of tmp is sort / staging scratch
@@ -839,6 +853,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
             case COMP_CDA: cda_create<BIG>(c, e, s, t, lane); cda_match<BIG>(c, e, s, t, lane); cda_expire<BIG>(c, e, t, lane); break;
             case COMP_GATHER: gather_step(c, e, s, r); break;
             case COMP_TAX: tax_step(c, e, s, lane); break;
+            case COMP_WEALTH: wealth_step(c, e, s, lane); break;
         }
     }
 #if AIE_ON_DEVICE

@@ -48,14 +48,14 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     if (u.n_agents < 2 || u.n_agents > AIE_MAX_AGENTS) return bad("n_agents must be in [2, 64]");
     if (u.height < 1 || u.width < 1 || u.height > 256 || u.width > 256) return bad("world size must be within 256x256");
     if (u.episode_length < 1 || u.episode_length >= (1 << 23)) return bad("episode_length out of range");
-    if (u.n_components < 1 || u.n_components > AIE_MAX_COMPONENTS) return bad("1..4 components");
+    if (u.n_components < 1 || u.n_components > AIE_MAX_COMPONENTS) return bad("1..8 components");
     if (u.obs_range < 0 || u.obs_range > 32) return bad("mobile_agent_observation_range out of range");
     c.A = u.n_agents; c.H = u.height; c.W = u.width; c.HW = u.height * u.width; c.T = u.episode_length;
     c.multi_action = u.multi_action_agents ? 1 : 0;
     c.n_comp = u.n_components;
     for (int i = 0; i < u.n_components; i++) {
         int k = u.components[i];
-        if (k < 0 || k > 3) return bad("unknown component kind");
+        if (k < 0 || k >= COMP_KINDS) return bad("unknown component kind");
         if (c.has[k]) return bad("duplicate component");
         c.comp[i] = k; c.has[k] = 1;
     }

@@ -44,7 +44,7 @@ enum { ST_TAX_PERIODS = 0, ST_TAX_COLLECTED = 1, ST_TAX_EFF_SUM = 2, ST_TAX_SCHE
 //   EV_TRADE  {kind, seller, buyer, commodity, ask, bid, ask_lifetime, bid_lifetime}
 enum { EV_BUILD = 1, EV_GATHER = 2, EV_TRADE = 3 };
 
-enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3 };
+enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3, COMP_WEALTH = 4, COMP_KINDS = 5 };
 enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
 
 // Observation "programs" (built once on the host from the reference's sorted-key flattening, base_env.py:562-612).
@@ -71,8 +71,8 @@ constexpr uint32_t ORDER_EMPTY = 0xFFFFFFFFu;  // order slot: birth << 8 | price
 
 struct DevCfg {
     int32_t A, H, W, HW, T, multi_action, n_comp;
-    int32_t comp[4];
-    int32_t has[4];
+    int32_t comp[8];
+    int32_t has[8];
     int32_t has_water, M, w, win, planner_spatial, obs_scaling;
     uint64_t regen_thresh[2];  // ceil(regen_weight * 2^53): u < weight  <=>  53-bit integer draw < thresh
     double eta, energy_cost, warm_const;

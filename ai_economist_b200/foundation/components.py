@@ -224,3 +224,12 @@ class PeriodicBracketTax(BaseComponent):
             tax_annealing=int(self.tax_annealing_schedule is not None),
             annealing_warmup=float(self._annealing_warmup or 0.0), annealing_slope=float(self._annealing_slope or 0.0),
             rate_max=float(self.rate_max))
+
+
+@component_registry.add
+class WealthRedistribution(BaseComponent):
+    """reference: components/redistribution.py:21-75.  No actions, observations or masks: every step it equalises the
+    agents' total coin (inventory + escrow) by resetting inventory coin.  Should be the last component."""
+    name = "WealthRedistribution"
+    required_entities = ["Coin"]
+    agent_subclasses = ["BasicMobileAgent"]

@@ -53,7 +53,8 @@ class DenseLogger:
         self.env, self.e, self.world_every = env, int(e), int(world_every)
         self.spec = env.spec
         self.log = {"world": [], "states": [], "actions": [], "rewards": []}
-        self.comp = {c.shorthand: [] for c in env.components if c.name != "PeriodicBracketTax" or not self.spec["disable_taxes"]}
+        logging = {"Build", "Gather", "ContinuousDoubleAuction"} | (set() if self.spec["disable_taxes"] else {"PeriodicBracketTax"})
+        self.comp = {c.shorthand: [] for c in env.components if c.name in logging}  # the others return None
         self._paid_prev = None
         self._static = None
 

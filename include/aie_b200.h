@@ -33,7 +33,7 @@ extern "C" {
 
 #define AIE_ABI_VERSION 2
 
-#define AIE_MAX_COMPONENTS 4
+#define AIE_MAX_COMPONENTS 8
 #define AIE_MAX_BRACKETS 16
 #define AIE_MAX_RATES 64
 #define AIE_MAX_AGENTS 64      /* mobile agents per env */
@@ -51,7 +51,8 @@ extern "C" {
  *   ContinuousDoubleAuction  components/continuous_double_auction.py:17
  *   Gather                   components/move.py:16
  *   PeriodicBracketTax       components/redistribution.py:78 */
-enum { AIE_COMP_BUILD = 0, AIE_COMP_CDA = 1, AIE_COMP_GATHER = 2, AIE_COMP_TAX = 3 };
+enum { AIE_COMP_BUILD = 0, AIE_COMP_CDA = 1, AIE_COMP_GATHER = 2, AIE_COMP_TAX = 3,
+       AIE_COMP_WEALTH = 4 /* WealthRedistribution, components/redistribution.py:21-75 */ };
 /* tax_model (redistribution.py:160-166): planner-driven discretised rates, or a fixed schedule
  * ("us-federal-single-filer-2018-scaled" / "fixed-bracket-rates", rates supplied by the host). */
 enum { AIE_TAX_MODEL_WRAPPER = 0, AIE_TAX_FIXED_RATES = 1 };

@@ -83,6 +83,17 @@ CONFIGS = {
         multi_action_mode_agents=True, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True,
         starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
+    # WealthRedistribution (components/redistribution.py:21-75) as the last component; pareto gather skills, 6 agents
+    "wealth_redistribution": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("WealthRedistribution", dict())],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=10,
+        fixed_four_skill_and_loc=False, n_agents=9, world_size=[25, 25], episode_length=400,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
     # short episodes for the multi-episode (device-side reset) traces
     "c1_reset": dict(
         scenario_name="layout_from_file/simple_wood_and_stone", components=_GTB,

@@ -675,6 +675,28 @@ static void tax_step(const orc_batch *b, env_t *s) {
     s->tax_pos += 1;
 }
 
+/* numpy's pairwise summation of a contiguous float64 array (np.sum; numpy/core/src/umath/loops_utils.h.src
+ * pairwise_sum, blocks < 128 elements: 8 accumulators, then the remainder) */
+static double np_sum(const double *a, int n) {
+    double r[8], res;
+    int i, j;
+    if (n < 8) { res = 0.0; for (i = 0; i < n; i++) res += a[i]; return res; }
+    for (j = 0; j < 8; j++) r[j] = a[j];
+    for (i = 8; i < n - (n % 8); i += 8) for (j = 0; j < 8; j++) r[j] += a[i + j];
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+/* WealthRedistribution.component_step, redistribution.py:52-68 */
+static void wealth_step(const orc_batch *b, env_t *s) {
+    int A = b->cfg.n_agents, a;
+    double *tot = (double *)alloca(sizeof(double) * A), target_share;
+    for (a = 0; a < A; a++) tot[a] = s->coin[a] + s->esc_coin[a]; /* ic + ec */
+    target_share = np_sum(tot, A) / A;
+    for (a = 0; a < A; a++) s->coin[a] = target_share - s->esc_coin[a];
+}
+
 /* additional_reset_steps :1106-1139 */
 static void tax_reset(const orc_batch *b, env_t *s) {
     int A = b->cfg.n_agents, a, i;
@@ -1122,6 +1144,7 @@ static void step_env(const orc_batch *b, env_t *s, const int32_t *act_a, const i
             case ORC_COMP_CDA: cda_step(b, s); break;
             case ORC_COMP_GATHER: gather_step(b, s); break;
             case ORC_COMP_TAX: tax_step(b, s); break;
+            case ORC_COMP_WEALTH: wealth_step(b, s); break;
         }
     }
     scenario_step(b, s);          /* :1005 */

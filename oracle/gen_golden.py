@@ -32,6 +32,7 @@ PLAN = [
     ("ref_unit_test", 1001, 100, 10),
     ("c5_small", 1001, 150, 25),
     ("c5_full", 1001, 60, 20),
+    ("wealth_redistribution", 1001, 300, 25),
     # multi-episode traces (env.reset() between episodes, the global numpy stream continues): device-side reset
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),

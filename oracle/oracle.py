@@ -12,8 +12,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libfoundation_oracle.so")
 
-MAX_COMP, MAX_BRACKETS, MAX_RATES = 4, 16, 64
-COMP = {"Build": 0, "ContinuousDoubleAuction": 1, "Gather": 2, "PeriodicBracketTax": 3}
+MAX_COMP, MAX_BRACKETS, MAX_RATES = 8, 16, 64
+COMP = {"Build": 0, "ContinuousDoubleAuction": 1, "Gather": 2, "PeriodicBracketTax": 3, "WealthRedistribution": 4}
 
 
 class OrcConfig(C.Structure):

@@ -55,7 +55,7 @@ def load_reference_foundation():
 # Converters: reference env object  ->  plain arrays in the oracle/product layout
 # --------------------------------------------------------------------------- #
 
-COMPONENT_NAMES = ["Build", "ContinuousDoubleAuction", "Gather", "PeriodicBracketTax"]
+COMPONENT_NAMES = ["Build", "ContinuousDoubleAuction", "Gather", "PeriodicBracketTax", "WealthRedistribution"]
 
 
 def spec_from_reference_env(env):

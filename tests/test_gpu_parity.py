@@ -52,6 +52,7 @@ def test_cuda_matches_reference_golden_trace(path):
     ("tax_us_federal", 32, 120, 20),    # multi-action agents, fixed schedule
     ("c5_small", 8, 150, 25),           # 32 agents, multi-action, K=50 book, sorted-gini branch
     ("c5_full", 6, 40, 20),             # BASELINE config 5 shape: 64 agents, 64x64, K=50 (2 agents per lane)
+    ("wealth_redistribution", 32, 200, 25),  # WealthRedistribution as the last component, 9 agents (numpy pairwise sum)
 ])
 def test_cuda_batch_matches_oracle(cfg, E, steps, every):
     env = _make_env(cfg, E, seed=4000, auto_reset=False)
