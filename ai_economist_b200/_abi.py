@@ -34,7 +34,7 @@ class AieConfig(C.Structure):
         ("bracket_cutoffs", C.c_double * MAX_BRACKETS), ("disc_rates", C.c_double * MAX_RATES),
         ("fixed_rates", C.c_double * MAX_BRACKETS),
         ("tax_annealing", C.c_int32), ("annealing_warmup", C.c_double), ("annealing_slope", C.c_double),
-        ("rate_max", C.c_double),
+        ("rate_max", C.c_double), ("rate_min", C.c_double),
         ("auto_reset", C.c_int32),
         ("reset_mode", C.c_int32), ("build_skill_dist", C.c_int32), ("gather_skill_dist", C.c_int32),
         ("payment_max_skill_multiplier", C.c_int32), ("fixed_four", C.c_int32),
@@ -187,6 +187,7 @@ def config_from_spec(spec, auto_reset=True):
               "max_num_orders", "order_labor", "tax_model", "disable_taxes", "period", "n_brackets", "n_disc_rates",
               "tax_annealing", "annealing_warmup", "annealing_slope", "rate_max"]:
         setattr(cfg, k, spec[k])
+    cfg.rate_min = float(spec.get("rate_min", 0.0))
     comps = [COMPONENT_KIND[c] for c in spec["components"]]
     cfg.n_components = len(comps)
     for i, c in enumerate(comps):

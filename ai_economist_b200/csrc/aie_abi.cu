@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     int32_t *hdr = (int32_t *)rec;
     if (c.auto_reset && hdr[HDR_T] >= c.T) {
         const int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
-                      episodes = hdr[HDR_EPISODES] + 1;
+                      episodes = hdr[HDR_EPISODES] + 1, saez_n = hdr[HDR_SAEZ_N];
         const uint8_t *snap = b.state0 + (size_t)env * c.rec_bytes;
         const uint32_t tail = (uint32_t)(c.rec_bytes - c.off_price_hist);  // price history + order slots
         fence_async_smem();
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
         mbar_wait(bar, 1);
         if (lane == 0) {
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
-            hdr[HDR_EPISODES] = episodes;
+            hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
         }
         __syncwarp();
         if (c.reset_mode == 1) device_reset_env(c, rec, grec, scratch, lane);  // reference-exact placement / skills

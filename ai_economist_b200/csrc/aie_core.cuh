@@ -92,7 +92,7 @@ AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 struct Env {
     int32_t *hdr;
     double *coin, *esc_coin, *labor, *bpay, *bskill, *bonus, *last_coin, *last_income, *last_marg, *util_prev,
-        *price_hist, *stats;
+        *price_hist, *stats, *saez;  // saez (Saez model only): [16] bracket rates, [16] running average, [16] observed rates
     int32_t *inv, *esc;  // [A][2]
     int16_t *loc;        // [A][2]
     uint8_t *n_orders, *bid_hist, *ask_hist, *rate_idx, *cell;
@@ -109,6 +109,7 @@ AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     uint8_t *big = c.split ? grec : rec;
     e.hdr = (int32_t *)rec;
     e.coin = (double *)(rec + c.off_coin);
+    e.saez = (double *)(rec + c.off_saez);
     e.stats = (double *)(big + c.off_stats);  // resident unless the config is split
     e.esc_coin = (double *)(rec + c.off_esc_coin);
     e.labor = (double *)(rec + c.off_labor);
@@ -585,7 +586,11 @@ AIE_DEV void gather_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) 
 // PeriodicBracketTax  (components/redistribution.py)
 // ------------------------------------------------------------------------------------------------
 AIE_DEV double tax_rate(const DevCfg &c, const Env &e, int b) {  // curr_marginal_rates :381-405
+    if (c.tax_model == 2) return fmin(e.saez[b], c.rate_max);  // Saez: np.minimum(curr_bracket_tax_rates, curr_rate_max)
     return c.tax_model == 0 ? c.disc_rates[e.rate_idx[b]] : c.fixed_rates[b];
+}
+AIE_DEV double tax_rate_observed(const DevCfg &c, const Env &e, int b) {  // _curr_rates_obs (:960, :1123)
+    return c.tax_model == 2 ? fmin(e.saez[32 + b], c.rate_max) : tax_rate(c, e, b);
 }
 AIE_DEV int tax_income_bin(const DevCfg &c, double income) {  // :828-835 (bracket index; negative income -> 0)
     int arg = 0;
@@ -609,9 +614,23 @@ AIE_DEV double tax_due(const DevCfg &c, const Env &e, double income) {  // :846-
     return sum;
 }
 
-AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, int lane) {  // :945-972
+AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, int lane) {  // :945-972
     const int A = c.A;
     int pos = e.hdr[HDR_TAX_POS];
+    if (pos == 1 && c.tax_model == 2 && e.hdr[HDR_SAEZ_N] < 500) {
+        // Saez warm-up (:444-457): until 500 (income, rate) samples exist the period's rates are
+        // np.random.uniform(rate_min, rate_max, n_brackets) from the env's stream; afterwards the host estimator has
+        // already written this period's rates into the record.
+        for (int b = 0; b < c.B; b++) {
+            const double u = rng_double(r);
+            if (lane == 0) e.saez[b] = c.rate_min + (c.rate_max - c.rate_min) * u;
+        }
+        wsync();
+    }
+    if (pos == 1 && c.tax_model == 2) {  // _curr_rates_obs = curr_marginal_rates (:960): this period's rates
+        for (int b = lane; b < 16; b += NL) e.saez[32 + b] = e.saez[b];
+        wsync();
+    }
     if (pos == 1 && c.tax_model == 0 && !c.disable_taxes) {  // set_new_period_rates_model :419-434
         for (int b = lane; b < c.B; b += NL) {
             int act = s.act_tax[b];
@@ -638,6 +657,7 @@ AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, int lane) {
         if (lane == 0) {  // episode statistics (:862-897): schedule, occupancy, effective rates, revenue
             double *st = e.stats + c.st_tax;
             st[ST_TAX_PERIODS] += 1.0;
+            if (c.tax_model == 2 && e.hdr[HDR_SAEZ_N] < (1 << 30)) e.hdr[HDR_SAEZ_N] += A;  // _update_saez_buffer :535-544
             st[ST_TAX_COLLECTED] += net;
             for (int b = 0; b < c.B; b++) st[ST_TAX_SCHED + b] += tax_rate(c, e, b);
             for (int a = 0; a < A; a++) {
@@ -852,7 +872,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
             case COMP_BUILD: build_step(c, e, s, r); break;
             case COMP_CDA: cda_create<BIG>(c, e, s, t, lane); cda_match<BIG>(c, e, s, t, lane); cda_expire<BIG>(c, e, t, lane); break;
             case COMP_GATHER: gather_step(c, e, s, r); break;
-            case COMP_TAX: tax_step(c, e, s, lane); break;
+            case COMP_TAX: tax_step(c, e, s, r, lane); break;
             case COMP_WEALTH: wealth_step(c, e, s, lane); break;
         }
     }
@@ -879,6 +899,11 @@ AIE_DEV_NOINLINE void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *g
         e.last_income[a] = 0.0;
         e.last_marg[a] = 0.0;
     }
+    // Saez: the reference caches the rate observation BEFORE it resets curr_bracket_tax_rates to the running average
+    // (:1123 vs :1138-1139): the reset observation's curr_rates are the previous episode's last rates while the agents'
+    // marginal_rate observation already uses the running average.
+    if (c.has[COMP_TAX] && c.tax_model == 2)
+        for (int b = lane; b < 16; b += NL) { e.saez[32 + b] = e.saez[b]; e.saez[b] = e.saez[16 + b]; }
     wsync();
     current_metrics(c, e, e.util_prev, s.tmp, lane);
     wsync();
@@ -1181,7 +1206,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)e.hdr[HDR_COMPLETIONS] - c.ann_warm)));
             s.net_hist[2 * P] = vis * c.ann_full;
         }
-        for (int b = lane; b < c.B; b += NL) s.shf[c.sh_curr_rates + b] = (float)tax_rate(c, e, b);
+        for (int b = lane; b < c.B; b += NL) s.shf[c.sh_curr_rates + b] = (float)tax_rate_observed(c, e, b);
         for (int a = lane; a < A; a += NL) {
             s.sc_a[a * AS_COUNT + AS_TAX_MARG] = (float)tax_marginal_rate(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
             const double v = e.last_income[a] / c.period;  // ascending rank -> sorted position (:908-911)

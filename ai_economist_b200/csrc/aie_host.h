@@ -87,7 +87,9 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.tax_model = u.tax_model; c.disable_taxes = u.disable_taxes ? 1 : 0; c.period = u.period;
     c.B = u.n_brackets; c.R = u.n_disc_rates;
     if (c.has[COMP_TAX]) {
-        if (c.tax_model != AIE_TAX_MODEL_WRAPPER && c.tax_model != AIE_TAX_FIXED_RATES) return bad("unsupported tax_model");
+        if (c.tax_model != AIE_TAX_MODEL_WRAPPER && c.tax_model != AIE_TAX_FIXED_RATES && c.tax_model != AIE_TAX_SAEZ)
+            return bad("unsupported tax_model");
+        if (c.tax_model == AIE_TAX_SAEZ && u.tax_annealing) return bad("tax annealing with the Saez model is not supported");
         if (c.B < 2 || c.B > AIE_MAX_BRACKETS) return bad("n_brackets must be in [2, 16]");
         if (c.tax_model == AIE_TAX_MODEL_WRAPPER && (c.R < 1 || c.R > AIE_MAX_RATES)) return bad("n_disc_rates must be in [1, 64]");
         if (c.period < 1) return bad("tax period must be >= 1");
@@ -95,7 +97,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         for (int r = 0; r < c.R; r++) { c.disc_rates[r] = u.disc_rates[r]; c.ann_full = fmax(c.ann_full, fabs(u.disc_rates[r])); }
     } else { c.B = 0; c.R = 0; c.period = 1; }
     c.tax_annealing = u.tax_annealing ? 1 : 0;
-    c.ann_warm = u.annealing_warmup; c.ann_slope = u.annealing_slope; c.rate_max = u.rate_max;
+    c.ann_warm = u.annealing_warmup; c.ann_slope = u.annealing_slope; c.rate_max = u.rate_max; c.rate_min = u.rate_min;
     c.auto_reset = u.auto_reset ? 1 : 0;
     c.reset_mode = u.reset_mode;
     if (c.reset_mode != 0 && c.reset_mode != 1) return bad("unknown reset_mode");
@@ -226,6 +228,10 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             c.obs_prefix_bytes = off;                  // [0, here): what the observation pass reads besides price_hist
             if (!stats_last) c.off_stats = take(8 * c.n_stats);
             c.off_mt = take(4 * 624);
+            // Saez model: current bracket rates [16], their running average [16] and the rates the observations show
+            // [16] (float64), kept across resets
+            c.off_saez = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_SAEZ) ? take(8 * 48) : 0;
+            c.keep_bytes = off - c.off_mt;
             c.off_price_hist = take(8 * 2 * A * P);
             c.off_orders = take(4 * 2 * A * c.K);
             if (stats_last) c.off_stats = take(8 * c.n_stats);
@@ -275,7 +281,9 @@ inline int lookup_field(const DevCfg &c, const char *name, aie_field *f) {
         {"t", HDR_T * 4, 4, 0, 1, 0, 0, 0, 0}, {"tax_pos", HDR_TAX_POS * 4, 4, 0, 1, 0, 0, 0, 0},
         {"completions", HDR_COMPLETIONS * 4, 4, 0, 1, 0, 0, 0, 0}, {"auto_warmup", HDR_AUTO_WARMUP * 4, 4, 0, 1, 0, 0, 0, 0},
         {"mt_pos", HDR_MT_POS * 4, 4, 0, 1, 0, 0, 0, 0}, {"episodes", HDR_EPISODES * 4, 4, 0, 1, 0, 0, 0, 0},
-        {"stats", c.off_stats, 8, 1, 1, 1, c.n_stats, 0, 0}, {"util_prev", c.off_util_prev, 8, 1, 1, 1, A + 1, 0, 0},
+        {"stats", c.off_stats, 8, 1, 1, 1, c.n_stats, 0, 0}, {"saez_n", HDR_SAEZ_N * 4, 4, 0, 1, 0, 0, 0, 0},
+        {"saez_rates", c.off_saez, 8, 1, 1, 1, 16, 0, 0}, {"saez_avg_rates", c.off_saez + 128, 8, 1, 1, 1, 16, 0, 0},
+        {"saez_obs_rates", c.off_saez + 256, 8, 1, 1, 1, 16, 0, 0}, {"util_prev", c.off_util_prev, 8, 1, 1, 1, A + 1, 0, 0},
         {"coin", c.off_coin, 8, 1, 1, 1, A, 0, 0}, {"esc_coin", c.off_esc_coin, 8, 1, 1, 1, A, 0, 0},
         {"labor", c.off_labor, 8, 1, 1, 1, A, 0, 0}, {"build_payment", c.off_bpay, 8, 1, 1, 1, A, 0, 0},
         {"build_skill", c.off_bskill, 8, 1, 1, 1, A, 0, 0}, {"bonus_gather_prob", c.off_bonus, 8, 1, 1, 1, A, 0, 0},
@@ -290,6 +298,7 @@ inline int lookup_field(const DevCfg &c, const char *name, aie_field *f) {
     };
     for (const FieldDesc &t : tab)
         if (!strcmp(t.name, name)) {
+            if (!strncmp(name, "saez_", 5) && name[5] != 'n' && !c.off_saez) return AIE_EINVAL;  // no Saez section in this config
             f->offset = t.off; f->elem_bytes = t.eb; f->is_float = t.flt; f->is_signed = t.sgn; f->ndim = t.nd;
             f->shape[0] = t.s0; f->shape[1] = t.s1; f->shape[2] = t.s2; f->shape[3] = 0;
             return AIE_OK;

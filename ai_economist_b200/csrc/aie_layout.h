@@ -24,7 +24,8 @@ enum : uint8_t {
 
 // header words (int32) at the start of a record
 enum { HDR_T = 0, HDR_TAX_POS = 1, HDR_COMPLETIONS = 2, HDR_AUTO_WARMUP = 3, HDR_MT_POS = 4,
-       HDR_ERR = 5, HDR_EPISODES = 6, HDR_RESERVED = 7, HDR_WORDS = 8 };
+       HDR_ERR = 5, HDR_EPISODES = 6, HDR_SAEZ_N = 7 /* (income, rate) samples seen so far, survives resets */,
+       HDR_WORDS = 8 };
 
 // Episode statistics ("stats" section of the record, float64, zeroed at reset): what the reference's component
 // get_metrics() need beyond the live state (build.py:198-222, continuous_double_auction.py:585-641,
@@ -84,7 +85,7 @@ struct DevCfg {
     int32_t tax_model, disable_taxes, period, B, R;
     double cutoffs[16], disc_rates[64], fixed_rates[16];
     int32_t tax_annealing;
-    double ann_warm, ann_slope, rate_max, ann_full;
+    double ann_warm, ann_slope, rate_max, ann_full, rate_min;
     int32_t auto_reset;
     int32_t reset_mode, build_skill_dist, gather_skill_dist, pmsm, fixed_four;
     int16_t ranked_locs[64][2];
@@ -98,7 +99,8 @@ struct DevCfg {
     // record layout (byte offsets)
     int32_t off_coin, off_esc_coin, off_labor, off_bpay, off_bskill, off_bonus, off_last_coin, off_last_income,
         off_last_marg, off_util_prev, off_price_hist, off_inv, off_esc, off_loc, off_n_orders, off_bid_hist,
-        off_ask_hist, off_rate_idx, off_cell, off_owner, off_orders, off_mt, off_stats;
+        off_ask_hist, off_rate_idx, off_cell, off_owner, off_orders, off_mt, off_stats, off_saez;
+    int32_t keep_bytes;  // [off_mt, off_mt + keep_bytes): what a reset never touches (MT key, then the Saez rates)
     int32_t n_stats, st_trade, st_tax;  // stats section: doubles, sub-offsets (st_tax < 0: no tax component)
     int32_t obs_prefix_bytes, rec_bytes;
     // Large envs (deep order books, many agents) keep the two big, sparsely touched sections - price history and

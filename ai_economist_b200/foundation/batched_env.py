@@ -183,6 +183,12 @@ class BatchedFoundationEnv:
             self.seed(seed)
         if self._stepper is not None:  # stepper_factory may return None: host-side reset/spec only (CPU oracle legs)
             self._build_views()
+        # Saez tax model: the estimator half lives on the host (foundation/saez.py)
+        self._saez = None
+        tax = self._components_dict.get("PeriodicBracketTax")
+        if tax is not None and tax.tax_model == "saez" and self._stepper is not None:
+            from .saez import SaezHost
+            self._saez = SaezHost(self, tax)
 
     # ------------------------------------------------------------------ properties (base_env.py:385-437)
     @property
@@ -294,8 +300,11 @@ class BatchedFoundationEnv:
             self._completions = self._stepper.to_numpy(self._stepper.state_view("completions")).astype(np.int64) \
                 if hasattr(self._stepper, "state_view") else self._completions
             self._sync_streams_from_device()
+        saez_n = self._saez.before_host_reset() if self._saez is not None else None
         self._stepper.load_state(self.host_reset_arrays())
         self._loaded = True
+        if self._saez is not None:
+            self._saez.after_host_reset(saez_n)
         self._start_dense_log(force_dense_logging, int(self._completions[0]))
         return self.obs
 
@@ -364,6 +373,8 @@ class BatchedFoundationEnv:
             lg.before_step(st.to_numpy(st.buf["actions_agent"][0]), st.to_numpy(st.buf["actions_planner"][0])
                            if st.dims.n_act_planner else None)
         self._stepper.step()
+        if self._saez is not None:
+            self._saez.after_step()
         if lg is not None:
             st = self._stepper
             ended = bool(int(st.to_numpy(st.buf["done"][0])))
@@ -438,7 +449,8 @@ class BatchedFoundationEnv:
         """`env.metrics` of replica e: layout_from_file.py:595-650 + every component's get_metrics(), computed from the
         replica's state record (the event logs are device-side running sums, see foundation/metrics.py)."""
         from .metrics import metrics_from_state
-        return metrics_from_state(self._spec, self._stepper.read_state(e))
+        return metrics_from_state(self._spec, self._stepper.read_state(e),
+                                  saez_elasticity=self._saez.est[e].elas_tm1 if self._saez is not None else None)
 
     @property
     def previous_episode_metrics(self):
@@ -453,4 +465,5 @@ class BatchedFoundationEnv:
         fin = st.read_state(e, final=True)
         if int(fin["t"][0]) == 0:   # nothing recorded yet
             return None
-        return metrics_from_state(self._spec, fin)
+        return metrics_from_state(self._spec, fin, saez_elasticity=self._saez.elas_at_episode_end[e]
+                                  if self._saez is not None else None)

@@ -142,7 +142,7 @@ class ContinuousDoubleAuction(BaseComponent):
 
 @component_registry.add
 class PeriodicBracketTax(BaseComponent):
-    """reference: components/redistribution.py:78-360 (Saez model: not on the device path yet)"""
+    """reference: components/redistribution.py:78-360; tax_model="saez" runs as a device/host hybrid (foundation/saez.py)"""
     name = "PeriodicBracketTax"
     component_type = "PeriodicTax"
     required_entities = ["Coin"]
@@ -157,8 +157,10 @@ class PeriodicBracketTax(BaseComponent):
         self.disable_taxes = bool(disable_taxes)
         self.tax_model = tax_model
         assert tax_model in ["model_wrapper", "us-federal-single-filer-2018-scaled", "saez", "fixed-bracket-rates"]
-        if tax_model == "saez":
-            raise NotImplementedError("tax_model='saez' is a host-side estimator outside the GPU hot path (next row)")
+        self.pareto_weight_type = pareto_weight_type
+        assert pareto_weight_type in ["inverse_income", "uniform"]
+        self.saez_fixed_elas = None if saez_fixed_elas is None else float(saez_fixed_elas)
+        assert self.saez_fixed_elas is None or self.saez_fixed_elas >= 0
         self.period = int(period)
         assert self.period > 0
         self.rate_min = 0.0 if self.disable_taxes else float(rate_min)
@@ -217,13 +219,13 @@ class PeriodicBracketTax(BaseComponent):
 
     def spec_fields(self):
         return dict(
-            tax_model=0 if self.tax_model == "model_wrapper" else 1, disable_taxes=int(self.disable_taxes),
+            tax_model={"model_wrapper": 0, "saez": 2}.get(self.tax_model, 1), disable_taxes=int(self.disable_taxes),
             period=self.period, n_brackets=self.n_brackets, n_disc_rates=self.n_disc_rates,
             bracket_cutoffs=[float(x) for x in self.bracket_cutoffs],
             disc_rates=[float(x) for x in self.disc_rates], fixed_rates=[float(x) for x in self.fixed_rates],
             tax_annealing=int(self.tax_annealing_schedule is not None),
             annealing_warmup=float(self._annealing_warmup or 0.0), annealing_slope=float(self._annealing_slope or 0.0),
-            rate_max=float(self.rate_max))
+            rate_max=float(self.rate_max), rate_min=float(self.rate_min))
 
 
 @component_registry.add

@@ -36,7 +36,7 @@ def energy_weight(spec, completions, warmup_integrator):
     return float(1.0 - np.exp(-x / warm))
 
 
-def metrics_from_state(spec, st):
+def metrics_from_state(spec, st, saez_elasticity=None):
     """spec: the env spec (scenario_spec_fields + components); st: dict with coin, esc_coin, inv, esc, labor, util_prev,
     auto_warmup, completions, cell, stats (BatchStepper.read_state layout).  Returns the reference's metrics dict."""
     A = int(spec["n_agents"])
@@ -91,13 +91,18 @@ def metrics_from_state(spec, st):
             inc, paid = stats[t0 + 35: t0 + 35 + A], stats[t0 + 35 + A: t0 + 35 + 2 * A]
             cutoffs = list(spec["bracket_cutoffs"])[: int(spec["n_brackets"])]
             n_obs = max(1.0, float(np.sum(occ)))
+            groups = {}   # the reference keys its logs by "%03d" % int(cutoff): brackets that share a key are pooled
             for b, c in enumerate(cutoffs):
-                k = "%03d" % int(c)
-                m["PeriodicTax/avg_bracket_rate/%s" % k] = float(sched[b] / periods) if periods else float("nan")
-                m["PeriodicTax/bracket_occupancy/%s" % k] = float(occ[b] / n_obs)
+                groups.setdefault("%03d" % int(c), []).append(b)
+            for k, bs in groups.items():
+                m["PeriodicTax/avg_bracket_rate/%s" % k] = (float(sum(sched[b] for b in bs) / (periods * len(bs)))
+                                                            if periods else float("nan"))
+                m["PeriodicTax/bracket_occupancy/%s" % k] = float(sum(occ[b] for b in bs) / n_obs)
             if not spec.get("disable_taxes", False):
                 m["PeriodicTax/avg_effective_tax_rate"] = float(eff_sum / (periods * A)) if periods else float("nan")
                 m["PeriodicTax/total_collected_taxes"] = float(collected)
                 for i, tag in ((int(np.argmin(coin)), "poorest"), (int(np.argmax(coin)), "richest")):
                     m["PeriodicTax/avg_tax_rate/%s" % tag] = float(paid[i] / max(0.001, inc[i]))
+                if int(spec["tax_model"]) == 2:  # the running elasticity estimate lives in the host-side estimator
+                    m["PeriodicTax/saez/estimated_elasticity"] = float(saez_elasticity)
     return m

@@ -234,13 +234,14 @@ class CudaStepper(BatchStepper):
     def to_numpy(self, buf):
         return buf.detach().cpu().numpy()
 
-    def state_view(self, name):
-        """Strided struct-of-arrays view [E, ...] of one state field inside the packed records."""
+    def state_view(self, name, final=False):
+        """Strided struct-of-arrays view [E, ...] of one state field inside the packed records (final=True: inside the
+        end-of-episode snapshots of the last finished episode, auto-reset only)."""
         t = self.torch
         f = self.field(name)
         shape = [f.shape[i] for i in range(f.ndim)]
         n = int(np.prod(shape)) if shape else 1
         dt = {(1, 0, 0): t.uint8, (1, 0, 1): t.int8, (2, 0, 1): t.int16, (4, 0, 1): t.int32, (4, 0, 0): t.int32,
               (8, 1, 1): t.float64}[(f.elem_bytes, f.is_float, f.is_signed)]
-        raw = self.buf["state"][:, f.offset:f.offset + n * f.elem_bytes]
+        raw = self.buf["episode_final" if final else "state"][:, f.offset:f.offset + n * f.elem_bytes]
         return raw.view(dt).view([self.n_envs] + shape) if shape else raw.view(dt)[:, 0]

@@ -55,7 +55,11 @@ enum { AIE_COMP_BUILD = 0, AIE_COMP_CDA = 1, AIE_COMP_GATHER = 2, AIE_COMP_TAX =
        AIE_COMP_WEALTH = 4 /* WealthRedistribution, components/redistribution.py:21-75 */ };
 /* tax_model (redistribution.py:160-166): planner-driven discretised rates, or a fixed schedule
  * ("us-federal-single-filer-2018-scaled" / "fixed-bracket-rates", rates supplied by the host). */
-enum { AIE_TAX_MODEL_WRAPPER = 0, AIE_TAX_FIXED_RATES = 1 };
+enum { AIE_TAX_MODEL_WRAPPER = 0, AIE_TAX_FIXED_RATES = 1,
+       AIE_TAX_SAEZ = 2 /* redistribution.py:437-823, device/host hybrid: the estimator runs on the host once per tax
+                           period and writes the bracket rates into the "saez_rates" field of the state record; until
+                           the income buffer holds 500 samples the device draws uniform random rates from the env's
+                           own stream exactly as the reference does (:444-457) */ };
 /* planner_reward_type (layout_from_file.py:153, scenarios/utils/rewards.py:84-133) */
 enum { AIE_SWF_COIN_EQ_TIMES_PROD = 0, AIE_SWF_INV_INCOME_COIN = 1, AIE_SWF_INV_INCOME_UTIL = 2 };
 
@@ -93,6 +97,7 @@ typedef struct aie_config {
     double fixed_rates[AIE_MAX_BRACKETS];
     int32_t tax_annealing;          /* tax_annealing_schedule is not None */
     double annealing_warmup, annealing_slope, rate_max;
+    double rate_min;                /* lower end of the random Saez warm-up rates (redistribution.py:452-456) */
     /* batching (new; no reference equivalent) */
     int32_t auto_reset;             /* 1: an env that reaches episode_length is restored from its load-time
                                        snapshot inside the same step (WarpDrive save_copy_and_apply_at_reset

@@ -94,6 +94,19 @@ CONFIGS = {
         fixed_four_skill_and_loc=False, n_agents=9, world_size=[25, 25], episode_length=400,
         multi_action_mode_agents=False, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True),
+    # Saez tax model (device/host hybrid): short tax period and 10 agents so that the 500-sample buffer fills after 500
+    # steps; multi-episode, so the estimator state has to survive resets
+    "saez_reset": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=10, tax_model="saez",
+                                                usd_scaling=10000.0))],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5,
+        fixed_four_skill_and_loc=False, n_agents=10, world_size=[25, 25], episode_length=100,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
     # short episodes for the multi-episode (device-side reset) traces
     "c1_reset": dict(
         scenario_name="layout_from_file/simple_wood_and_stone", components=_GTB,

@@ -36,6 +36,7 @@ PLAN = [
     # multi-episode traces (env.reset() between episodes, the global numpy stream continues): device-side reset
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),
+    ("saez_reset", 1001, 790, 50),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

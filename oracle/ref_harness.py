@@ -97,9 +97,9 @@ def spec_from_reference_env(env):
             spec.update(max_bid_ask=c.max_bid_ask, order_duration=c.order_duration,
                         max_num_orders=c.max_num_orders, order_labor=c.order_labor)
         elif c.name == "PeriodicBracketTax":
-            assert c.tax_model in ("model_wrapper", "us-federal-single-filer-2018-scaled", "fixed-bracket-rates")
+            assert c.tax_model in ("model_wrapper", "us-federal-single-filer-2018-scaled", "fixed-bracket-rates", "saez")
             spec.update(
-                tax_model=0 if c.tax_model == "model_wrapper" else 1,
+                tax_model={"model_wrapper": 0, "saez": 2}.get(c.tax_model, 1), rate_min=float(c.rate_min),
                 disable_taxes=int(c.disable_taxes), period=c.period, n_brackets=c.n_brackets,
                 n_disc_rates=c.n_disc_rates, bracket_cutoffs=[float(x) for x in c.bracket_cutoffs],
                 disc_rates=[] if c.disc_rates is None else [float(x) for x in c.disc_rates],

@@ -83,12 +83,12 @@ int launch_step(aie_env *env, int emit_obs, void *) {
         int32_t *hdr = (int32_t *)rec;
         if (c.auto_reset && hdr[HDR_T] >= c.T) {  // same sequence as aie_step_kernel
             int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
-                    episodes = hdr[HDR_EPISODES] + 1;
+                    episodes = hdr[HDR_EPISODES] + 1, saez_n = hdr[HDR_SAEZ_N];
             if (b.final) memcpy(b.final + (size_t)e * c.rec_bytes, rec, c.rec_bytes);
             memcpy(rec, b.state0 + (size_t)e * c.rec_bytes, c.off_mt);
             memcpy(rec + c.off_price_hist, b.state0 + (size_t)e * c.rec_bytes + c.off_price_hist, c.rec_bytes - c.off_price_hist);
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
-            hdr[HDR_EPISODES] = episodes;
+            hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
             if (c.reset_mode == 1) device_reset_env(c, rec, rec, env->be.scratch.data(), 0);
             finish_reset_env(c, rec, rec, env->be.scratch.data(), 0);
         }

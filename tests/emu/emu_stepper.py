@@ -42,13 +42,13 @@ class EmuStepper(BatchStepper):
     def to_numpy(self, buf):
         return np.array(buf)
 
-    def state_view(self, name):
+    def state_view(self, name, final=False):
         f = self.field(name)
         shape = [f.shape[i] for i in range(f.ndim)]
         n = int(np.prod(shape)) if shape else 1
         dt = {(1, 0, 0): np.uint8, (1, 0, 1): np.int8, (2, 0, 1): np.int16, (4, 0, 1): np.int32,
               (4, 0, 0): np.uint32, (8, 1, 1): np.float64}[(f.elem_bytes, f.is_float, f.is_signed)]
-        state = self.buf["state"]   # a live strided view, like the CUDA stepper's
+        state = self.buf["episode_final" if final else "state"]   # a live strided view, like the CUDA stepper's
         inner, s = [], np.dtype(dt).itemsize
         for d in reversed(shape):
             inner.insert(0, s)

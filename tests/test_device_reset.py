@@ -94,3 +94,29 @@ def test_emulated_previous_episode_metrics_match_reference(path):
 @pytest.mark.parametrize("path", FILES, ids=lambda p: os.path.basename(p))
 def test_cuda_previous_episode_metrics_match_reference(path):
     _replay_previous_episode_metrics(path, None)
+
+
+def test_emulated_saez_with_explicit_host_resets_matches_reference():
+    """Saez model, auto_reset off: env.reset() between episodes goes through the host reset path, which has to carry
+    the estimator's persistent state (sample counter, rates in force / observed) across the repacked records."""
+    from tests.emu.emu_stepper import emu_factory
+    path = [p for p in FILES if "saez" in p][0]
+    z, meta, init = gu.load_fixture(path)
+    kw = dict(meta["reference_kwargs"])
+    name = kw.pop("scenario_name")
+    kw["components"] = [tuple(c) for c in kw["components"]]
+    env = foundation.make_env_instance(name, n_envs=1, auto_reset=False, stepper_factory=emu_factory, **kw)
+    env.seed([meta["seed"]])
+    env.reset()
+    s = env.stepper
+    full = {int(t): i for i, t in enumerate(z["full_steps"])}
+    A = env.n_agents
+    for t in range(1, int(meta["n_steps"]) + 1):
+        acts = {str(i): z["act_a"][t - 1][i][None] for i in range(A)}
+        env.step(acts)
+        last = s.read_obs(0)
+        if int(z["step_done"][t]):
+            env.reset()
+        st, ob = s.read_state(0), s.read_obs(0)
+        ob["rew"], ob["done"] = last["rew"], last["done"]   # reward / done belong to the step, not to the reset
+        gu.check_step(z, t, ob, st, full.get(t), "host-reset-trace", books=st["books"])
