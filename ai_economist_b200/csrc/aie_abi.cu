@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     // the actions are decoded into the scratch area while the bulk load of the record is in flight
     const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
     const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
-    decode_actions(c, step_scratch_view(scratch, c), act_a, act_p, lane);
+    decode_actions(c, step_scratch_view(scratch, c), act_a, act_p, lane, tab);
     mbar_wait(bar, 0);
 
     int32_t *events = (b.events && env < b.event_envs) ? b.events + (size_t)env * 8 * (b.event_cap + 1) : nullptr;

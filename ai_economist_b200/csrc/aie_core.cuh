@@ -258,10 +258,22 @@ AIE_DEV void rng_permutation(Rng &r, uint8_t *perm, int A) {
 // Actions  (BaseAgent.parse_actions, base/base_agent.py:407-438)
 // ------------------------------------------------------------------------------------------------
 AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t *act_a, const int32_t *act_p,
-                            int lane) {
+                            int lane, const uint16_t *tab = nullptr) {
     for (int a = lane; a < c.A; a += NL) {
         uint8_t build = 0, move = 0, buy0 = 0, buy1 = 0, sell0 = 0, sell1 = 0;
         int g = (!c.multi_action && act_a) ? act_a[a] : 0;
+        if (tab && !c.multi_action) {
+            // single-action agents: the mask program already maps the flat action index to (subspace, level)
+            if (g > 0 && g < c.Na) {
+                const uint32_t en = tab[c.tab_m + g], slot = en >> 8, idx = en & 255u;
+                if (slot == MS_BUILD) build = 1;
+                else if (slot == MS_BUY0) buy0 = (uint8_t)(idx + 1);
+                else if (slot == MS_BUY1) buy1 = (uint8_t)(idx + 1);
+                else if (slot == MS_SELL0) sell0 = (uint8_t)(idx + 1);
+                else if (slot == MS_SELL1) sell1 = (uint8_t)(idx + 1);
+                else if (slot >= MS_G0) move = (uint8_t)(slot - MS_G0 + 1);
+            }
+        } else
         for (int si = 0; si < c.n_sub; si++) {
             int v;
             if (c.multi_action) v = act_a ? act_a[a * c.n_sub + si] : 0;
@@ -456,9 +468,15 @@ AIE_DEV void cda_match(const DevCfg &c, Env &e, const StepScratch &s, int t, int
             const int bprice = (int)(bmax >> 20) - 1;
             const int blife = (int)((bmax >> 8) & 4095u);
             // first ask whose seller is not the buyer
-            uint32_t ak = 0;
-            for (int a = lane; a < A; a += NL)
+            uint32_t ak = 0, ak_any = 0;
+            for (int a = lane; a < A; a += NL) {
+                if (ba_key[a] > ak_any) ak_any = ba_key[a];
                 if (a != buyer && ba_key[a] > ak) ak = ba_key[a];
+            }
+            // Shortcut with the same outcome as marking the remaining buyers impossible one by one: the best remaining
+            // bid is below the cheapest ask of the whole book (or there is no ask at all), so no remaining buyer can trade.
+            const uint32_t amax_any = wmax(ak_any);
+            if (amax_any == 0 || bprice < P - (int)(amax_any >> 20)) break;
             const uint32_t amax = wmax(ak);
             if (amax == 0) { possible &= ~(1ull << buyer); if (!possible) break; continue; }
             const int seller = 255 - (int)(amax & 255u);
@@ -855,14 +873,14 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 template <bool BIG>
 AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
                       const int32_t *act_p, double *rew_out, int32_t *done_out, int lane, bool decoded = false,
-                      int32_t *events = nullptr, int event_cap = 0) {
+                      int32_t *events = nullptr, int event_cap = 0, const uint16_t *tab = nullptr) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     if (events) {  // dense-log replicas: this step's event block starts empty
         e.ev = events; e.ev_cap = event_cap;
         if (lane == 0) { events[0] = 0; events[1] = e.hdr[HDR_T] + 1; events[2] = 0; }
     }
-    if (!decoded) decode_actions(c, s, act_a, act_p, lane);  // the CUDA kernel decodes while the record is in flight
+    if (!decoded) decode_actions(c, s, act_a, act_p, lane, tab);  // the CUDA kernel decodes while the record is in flight
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
     const int t = e.hdr[HDR_T] + 1;
     wsync();

@@ -76,10 +76,10 @@ int launch_step(aie_env *env, int emit_obs, void *) {
         int32_t *events = (b.events && e < b.event_envs) ? b.events + (size_t)e * 8 * (b.event_cap + 1) : nullptr;
         if (c.split) step_env<true>(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
                  (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
-                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0, false, events, b.event_cap);
+                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0, false, events, b.event_cap, b.tab);
         else step_env<false>(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
                  (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
-                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0, false, events, b.event_cap);
+                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0, false, events, b.event_cap, b.tab);
         int32_t *hdr = (int32_t *)rec;
         if (c.auto_reset && hdr[HDR_T] >= c.T) {  // same sequence as aie_step_kernel
             int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
