@@ -1383,6 +1383,26 @@ AIE_DEV uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
 // Uniform choice among the set entries of mask[0..n) by one warp: ballots count the open entries, a hashed
 // rank picks one, and the lane holding it is found with popcounts.  Returns the same value on every lane.
 AIE_DEV int sample_segment_warp(const float *mask, int n, uint64_t key, int lane) {
+#if AIE_ON_DEVICE
+    // one pass: the segment (at most MAX_MASK = 160 entries) becomes five ballot words held in registers
+    uint32_t w[5];
+    int total = 0;
+#pragma unroll
+    for (int ch = 0; ch < 5; ch++) {
+        const int j = ch * NL + lane;
+        w[ch] = wballot(j < n && mask[j] != 0.0f);
+        total += __popc(w[ch]);
+    }
+    if (total == 0) return 0;
+    int r = (int)((uint32_t)(mix64(key) >> 32) % (uint32_t)total);
+#pragma unroll
+    for (int ch = 0; ch < 5; ch++) {
+        const int cnt = __popc(w[ch]);
+        if (r < cnt) return ch * NL + (int)__fns(w[ch], 0, r + 1);  // position of the (r+1)-th open entry
+        r -= cnt;
+    }
+    return 0;
+#else
     int total = 0;
     for (int base = 0; base < n; base += NL) {
         const int j = base + lane;
@@ -1402,6 +1422,7 @@ AIE_DEV int sample_segment_warp(const float *mask, int n, uint64_t key, int lane
         r -= cnt;
     }
     return 0;
+#endif
 }
 
 // One env: every agent (and planner bracket) draws one uniformly random unmasked action per subspace.
