@@ -1425,10 +1425,12 @@ AIE_DEV int sample_segment_warp(const float *mask, int n, uint64_t key, int lane
 #endif
 }
 
-// One env: every agent (and planner bracket) draws one uniformly random unmasked action per subspace.
-AIE_DEV void sample_actions_env(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
-                                int32_t *act_p, uint64_t key, int lane) {
-    for (int a = 0; a < c.A; a++) {
+// One unit of an env's random policy: unit u < A = agent u (one draw per subspace), unit A + b = planner bracket b.
+// Units are independent, so the kernel gives each its own warp.
+AIE_DEV void sample_actions_unit(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
+                                 int32_t *act_p, uint64_t key, int u, int lane) {
+    if (u < c.A) {
+        const int a = u;
         const float *m = a_mask + (size_t)a * c.Na;
         if (!c.multi_action) {
             const int v = sample_segment_warp(m, c.Na, key + 0x100 * a, lane);
@@ -1441,12 +1443,17 @@ AIE_DEV void sample_actions_env(const DevCfg &c, const float *a_mask, const floa
                 off += c.sub_n[si] + 1;
             }
         }
+    } else if (c.planner_acts) {
+        const int b = u - c.A;
+        const int v = sample_segment_warp(p_mask + (size_t)b * (1 + c.R), 1 + c.R, key + 0x10000 + b, lane);
+        if (lane == 0) act_p[b] = v;
     }
-    if (c.planner_acts)
-        for (int b = 0; b < c.B; b++) {
-            const int v = sample_segment_warp(p_mask + (size_t)b * (1 + c.R), 1 + c.R, key + 0x10000 + b, lane);
-            if (lane == 0) act_p[b] = v;
-        }
+}
+// One env: every agent (and planner bracket) draws one uniformly random unmasked action per subspace.
+AIE_DEV void sample_actions_env(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
+                                int32_t *act_p, uint64_t key, int lane) {
+    const int units = c.A + (c.planner_acts ? c.B : 0);
+    for (int u = 0; u < units; u++) sample_actions_unit(c, a_mask, p_mask, act_a, act_p, key, u, lane);
 }
 
 }  // namespace aie
