@@ -259,14 +259,21 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
                 obs_out_for(c, b, env), tab, lane);
 }
 
-__global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed) {
-    // one warp per env (measured: a warp per (env, agent) is slower - 17.5 vs 15.2 us for c2)
-    const int env = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+// per_unit == 0: one warp per env (fastest for few agents: c2 15.2 us vs 17.5 us);  per_unit == 1: one warp per
+// (env, agent | planner bracket) - many agents x subspaces make the per-env chain long (c5: 64 agents x 6 subspaces).
+__global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed,
+                                                         int per_unit) {
+    const long long wid = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    const int units = per_unit ? c.A + (c.planner_acts ? c.B : 0) : 1;
+    const int env = (int)(wid / units), u = (int)(wid - (long long)env * units);
     if (env >= c.n_envs) return;
-    sample_actions_env(c, b.a_mask + (size_t)env * c.A * c.Na, b.p_mask + (size_t)env * c.Np,
-                       const_cast<int32_t *>(b.act_a) + (size_t)env * c.A * c.n_act_a,
-                       c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)env * c.n_act_p : nullptr,
-                       mix64(seed ^ mix64((uint64_t)env)), lane);
+    const float *am = b.a_mask + (size_t)env * c.A * c.Na, *pm = b.p_mask + (size_t)env * c.Np;
+    int32_t *aa = const_cast<int32_t *>(b.act_a) + (size_t)env * c.A * c.n_act_a;
+    int32_t *ap = c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)env * c.n_act_p : nullptr;
+    const uint64_t key = mix64(seed ^ mix64((uint64_t)env));
+    if (per_unit) sample_actions_unit(c, am, pm, aa, ap, key, u, lane);
+    else sample_actions_env(c, am, pm, aa, ap, key, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -390,8 +397,11 @@ int launch_observe(aie_env *env, int lo, int n, void *stream) {
 int launch_sample(aie_env *env, uint64_t seed, void *stream) {
     const DevCfg &c = env->cfg;
     (void)c;
-    aie_sample_kernel<<<(env->n_envs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        env->cfg, env->bufs, host_mix64(seed) ^ host_mix64(++env->sample_calls));
+    const int units = env->cfg.A + (env->cfg.planner_acts ? env->cfg.B : 0);
+    const int per_unit = (env->cfg.A * (env->cfg.multi_action ? env->cfg.n_sub : 1) >= 64) ? 1 : 0;
+    const long long warps = (long long)env->n_envs * (per_unit ? units : 1);
+    aie_sample_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        env->cfg, env->bufs, host_mix64(seed) ^ host_mix64(++env->sample_calls), per_unit);
     AIE_CUDA(cudaGetLastError(), "aie_sample_kernel launch");
     env->launches++;
     return AIE_OK;
