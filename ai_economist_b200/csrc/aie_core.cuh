@@ -1301,8 +1301,13 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     // per window cell), then the M+1 map planes and the 2 index planes stream out of the staged bytes
     {
         // lane's first window cell and the (dr, dc) step for q += NL: one small division per warp per step
+#if AIE_ON_DEVICE
+        const int dr_first = (int)div_magic((uint32_t)lane, c.win_magic), dc_first = lane - dr_first * win;
+        const int dr_step = c.win_dr32, dc_step = c.win_dc32;  // NL / win and NL % win, from the host
+#else
         const int dr_first = lane / win, dc_first = lane - dr_first * win;
         const int dr_step = NL / win, dc_step = NL - dr_step * win;
+#endif
         uint8_t *wc = s.wstage, *wi = s.wstage + ((ww + 7) & ~3);  // wi: [2][ww] owner code, location code
         for (int a = 0; a < A; a++) {
             const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;

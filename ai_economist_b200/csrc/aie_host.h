@@ -202,6 +202,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         auto magic = [](int n) { return n > 1 ? (uint32_t)((1ull << 32) / (uint64_t)n) + 1u : 0u; };
         c.HW_magic = magic(c.HW); c.ww_magic = magic(c.win * c.win);
         c.Fa_magic = magic(c.Fa); c.Fpa_magic = magic(c.Fpa); c.Na_magic = magic(c.Na);
+        c.win_magic = magic(c.win); c.win_dr32 = 32 / c.win; c.win_dc32 = 32 - c.win_dr32 * c.win;
     }
     c.tab_p = c.Fa; c.tab_pa = c.tab_p + c.Fp; c.tab_m = c.tab_pa + c.Fpa; c.tab_n = (c.tab_m + c.Na + 1) & ~1;
     memcpy(tb.w, prog_a, 2 * c.Fa); memcpy(tb.w + c.tab_p, prog_p, 2 * c.Fp);

@@ -118,6 +118,7 @@ struct DevCfg {
     int32_t sh_curr_rates, sh_last_incomes, sh_full, sh_count;  // offsets / size of the shared float staging array
     int32_t tab_p, tab_pa, tab_m, tab_n;               // offsets (u16 words) into the program table, total words (even)
     uint32_t HW_magic, ww_magic, Fa_magic, Fpa_magic, Na_magic;  // floor(2^32 / n) + 1: run index -> (row, column)
+    uint32_t win_magic; int32_t win_dr32, win_dc32;  // window walk: lane / win, and the (row, col) step of 32 cells
 };
 
 // raw device pointers (mirrors aie_buffers)
