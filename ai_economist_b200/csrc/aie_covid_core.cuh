@@ -219,27 +219,40 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
             int prev = row[L1 - 1];                       // predecessor of physical column 0
             for (int p0 = 0; p0 < L1; p0 += 16) {
 #if CV_ON_DEVICE
-                union { int4 v; int8_t b[16]; } ld;
+                union { int4 v; int8_t b[16]; uint32_t w32[4]; } ld;
                 ld.v = *(const int4 *)(row + p0);               // one 16-byte load (LDG.128)
 #else
                 cv_b16 ld = *(const cv_b16 *)(row + p0);
 #endif
                 const int8_t *chunk = ld.b;
+                // Stringency changes are rare (an action every cooldown period at most): a 4-column word that equals
+                // itself shifted by one column (with the previous column shifted in) holds no change and is skipped.
 #if CV_ON_DEVICE
 #pragma unroll
 #endif
-                for (int j = 0; j < 16; j++) {
-                    const int p = p0 + j;
-                    if (p >= L1) break;
-                    const int cur = chunk[j];
-                    const int d = cur - prev;             // change between physical columns p-1 and p
-                    prev = cur;
-                    if (d != 0) {
-                        int k = (p - 1) - new_head;       // logical index of the older element of the pair
-                        if (k < 0) k += L1;
-                        if (k < L)
-                            for (int f = 0; f < F; f++)
-                                acc += ((double)d * (double)c.conv_w[a * F + f]) * (double)c.conv_filt[f * L + k];
+                for (int wj = 0; wj < 4; wj++) {
+                    const int pw = p0 + 4 * wj;
+                    if (pw >= L1) break;
+#if CV_ON_DEVICE
+                    const uint32_t w = ld.w32[wj];
+#else
+                    const uint32_t w = (uint32_t)(uint8_t)chunk[4 * wj] | ((uint32_t)(uint8_t)chunk[4 * wj + 1] << 8) |
+                                       ((uint32_t)(uint8_t)chunk[4 * wj + 2] << 16) | ((uint32_t)(uint8_t)chunk[4 * wj + 3] << 24);
+#endif
+                    if (pw + 4 <= L1 && w == ((w << 8) | (uint32_t)(uint8_t)prev)) { prev = (int)(int8_t)(w >> 24); continue; }
+                    for (int j = 4 * wj; j < 4 * wj + 4; j++) {
+                        const int p = p0 + j;
+                        if (p >= L1) break;
+                        const int cur = chunk[j];
+                        const int d = cur - prev;             // change between physical columns p-1 and p
+                        prev = cur;
+                        if (d != 0) {
+                            int k = (p - 1) - new_head;       // logical index of the older element of the pair
+                            if (k < 0) k += L1;
+                            if (k < L)
+                                for (int f = 0; f < F; f++)
+                                    acc += ((double)d * (double)c.conv_w[a * F + f]) * (double)c.conv_filt[f * L + k];
+                        }
                     }
                 }
             }

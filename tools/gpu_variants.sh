@@ -10,10 +10,10 @@ run() { # label, bench-args (quoted), env...
 import json
 try:
     d = json.load(open("gpurun_out/bench_$label.json"))
-    print("$label value %.3e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v["ms"]*1e3,1) for k, v in d["roofline"]["kernels"].items()}, d["roofline"]["kernels"].get("aie_step_kernel", {}).get("unfused_ms"), d["clocks"]["sm_mhz"])
+    print("$label value %.3e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v["ms"]*1e3,1) for k, v in d["roofline"]["kernels"].items()}, d["roofline"]["frac"], d["clocks"]["sm_mhz"])
 except Exception as ex:
     print("$label FAILED", ex, open("gpurun_out/bench_$label.err").read()[-300:])
 PY
 }
+run c4 "--workload c4 --steps 300 --warmup 20" X=1
 run c2 "" X=1
-run c3 "--workload c3 --steps 300" X=1
