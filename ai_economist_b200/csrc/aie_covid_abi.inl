@@ -20,6 +20,7 @@ int aie_covid_create(const aie_covid_config *u, int32_t n_envs, int32_t device, 
     if (u->abi_version != AIE_ABI_VERSION) return fail(AIE_EINVAL, "aie_covid_create: abi_version mismatch");
     if (n_envs < 1) return fail(AIE_EINVAL, "aie_covid_create: n_envs must be >= 1");
     if (u->n_states < 1 || u->n_states > 64) return fail(AIE_EINVAL, "aie_covid_create: n_states must be in [1, 64]");
+    if (u->num_filters < 1 || u->num_filters > 8) return fail(AIE_EINVAL, "aie_covid_create: num_filters must be in [1, 8]");
     if (u->filter_len < 1 || u->num_filters < 1 || u->beta_delay < 1 || u->beta_delay > u->filter_len)
         return fail(AIE_EINVAL, "aie_covid_create: bad filter / delay sizes");
     if (u->episode_length < 1 || u->subsidy_interval < 1 || u->delivery_interval < 1 || u->num_subsidy_levels < 1 ||

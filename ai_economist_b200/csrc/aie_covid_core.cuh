@@ -217,10 +217,16 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
         {
             const int8_t *row = ring + (size_t)a * cv_ring_row(L1);
             int prev = row[L1 - 1];                       // predecessor of physical column 0
+            double wf[8];                                 // this state's filter weights (F <= 8), widened once
+            for (int f = 0; f < 8; f++) wf[f] = f < F ? (double)c.conv_w[a * F + f] : 0.0;
+#if CV_ON_DEVICE
+            int4 nxt = *(const int4 *)row;                // software pipeline: the next 16 columns are always in flight
+#endif
             for (int p0 = 0; p0 < L1; p0 += 16) {
 #if CV_ON_DEVICE
                 union { int4 v; int8_t b[16]; uint32_t w32[4]; } ld;
-                ld.v = *(const int4 *)(row + p0);               // one 16-byte load (LDG.128)
+                ld.v = nxt;
+                if (p0 + 16 < L1) nxt = *(const int4 *)(row + p0 + 16);   // rows are padded to 16 bytes (LDG.128)
 #else
                 cv_b16 ld = *(const cv_b16 *)(row + p0);
 #endif
@@ -249,9 +255,13 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
                         if (d != 0) {
                             int k = (p - 1) - new_head;       // logical index of the older element of the pair
                             if (k < 0) k += L1;
-                            if (k < L)
-                                for (int f = 0; f < F; f++)
-                                    acc += ((double)d * (double)c.conv_w[a * F + f]) * (double)c.conv_filt[f * L + k];
+                            if (k < L) {
+#if CV_ON_DEVICE
+#pragma unroll
+#endif
+                                for (int f = 0; f < 8; f++)   // F <= 8 (checked at creation); unrolled so wf[] stays in registers
+                                    if (f < F) acc += ((double)d * wf[f]) * (double)c.conv_filt[f * L + k];
+                            }
                         }
                     }
                 }
