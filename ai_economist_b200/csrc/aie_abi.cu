@@ -413,7 +413,8 @@ int launch_sample(aie_env *env, uint64_t seed, void *stream) {
 // COVID-19 scenario: one CTA per env replica, one thread per US state; a single fused kernel per step.
 __global__ void __launch_bounds__(64) aie_covid_step_kernel(const __grid_constant__ CovidCfg c, const CovidBufs b) {
     __shared__ float red[3 * 64];
-    covid_step_env(c, blockIdx.x, b, red, threadIdx.x, blockDim.x);
+    __shared__ uint32_t chg[64 * CV_CHG_CAP];
+    covid_step_env(c, blockIdx.x, b, red, chg, threadIdx.x, blockDim.x);
 }
 __global__ void __launch_bounds__(64) aie_covid_reset_kernel(const __grid_constant__ CovidCfg c, const CovidBufs b) {
     covid_reset_env(c, blockIdx.x, b, threadIdx.x, blockDim.x, false);

@@ -163,7 +163,23 @@ CV_DEV void covid_reset_env(const CovidCfg &c, int e, const CovidBufs &b, int ti
 }
 
 // red: scratch float [3][S] (shared memory on the device)
-CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *red, int tid, int nthr) {
+// acc += sum over the listed changes (k, d), in list order, of d * w_f * filter_f[k] for f = 0..F-1 (f64 like the reference)
+CV_DEV double cv_accumulate_changes(const CovidCfg &c, const uint32_t *lst, int n, const double *wf, double acc) {
+    for (int i = 0; i < n; i++) {
+        const int k = (int)(lst[i] & 0xFFFFu), d = (int)(lst[i] >> 16) - 128;
+#if CV_ON_DEVICE
+#pragma unroll
+#endif
+        for (int f = 0; f < 8; f++)   // F <= 8 (checked at creation); unrolled so wf[] stays in registers
+            if (f < c.F) acc += ((double)d * wf[f]) * (double)c.conv_filt[f * c.L + k];
+    }
+    return acc;
+}
+
+// chg: scratch uint32 [nthr][CV_CHG_CAP] (shared memory on the device): per-state list of the stringency changes in
+// the history window
+constexpr int CV_CHG_CAP = 32;
+CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *red, uint32_t *chg, int tid, int nthr) {
     const int S = c.S, L = c.L, L1 = c.L + 1, F = c.F;
     float *st = b.state + (size_t)e * CVS_FIELDS * S;
     int32_t *ints = b.ints + (size_t)e * 2 * S;
@@ -217,6 +233,8 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
         {
             const int8_t *row = ring + (size_t)a * cv_ring_row(L1);
             int prev = row[L1 - 1];                       // predecessor of physical column 0
+            uint32_t *my_chg = chg + (size_t)tid * CV_CHG_CAP;
+            int n_chg = 0;
             double wf[8];                                 // this state's filter weights (F <= 8), widened once
             for (int f = 0; f < 8; f++) wf[f] = f < F ? (double)c.conv_w[a * F + f] : 0.0;
 #if CV_ON_DEVICE
@@ -256,16 +274,17 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
                             int k = (p - 1) - new_head;       // logical index of the older element of the pair
                             if (k < 0) k += L1;
                             if (k < L) {
-#if CV_ON_DEVICE
-#pragma unroll
-#endif
-                                for (int f = 0; f < 8; f++)   // F <= 8 (checked at creation); unrolled so wf[] stays in registers
-                                    if (f < F) acc += ((double)d * wf[f]) * (double)c.conv_filt[f * L + k];
+                                // Changes are first collected (in scan order) and accumulated afterwards: the states of a
+                                // warp change on different days, and accumulating inside the scan would run the body once
+                                // per distinct day of the whole warp instead of once per change of the busiest state.
+                                if (n_chg == CV_CHG_CAP) { acc = cv_accumulate_changes(c, my_chg, n_chg, wf, acc); n_chg = 0; }
+                                my_chg[n_chg++] = (uint32_t)k | ((uint32_t)(d + 128) << 16);
                             }
                         }
                     }
                 }
             }
+            acc = cv_accumulate_changes(c, my_chg, n_chg, wf, acc);
         }
         const double excess = (acc <= 20.0) ? log(1.0 + exp(acc)) : acc;  // softplus, beta = 1, threshold = 20
         const double unemployed = (excess + (double)c.unemp_bias[a]) * (double)c.pop[a] / 100.0;

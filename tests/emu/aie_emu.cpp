@@ -135,7 +135,8 @@ int covid_launch_sample(aie_covid_env *env, uint64_t key, void *) {
 }
 int covid_launch_step(aie_covid_env *env, void *) {
     std::vector<float> red(3 * 64);
-    for (int e = 0; e < env->n_envs; e++) covid_step_env(env->cfg, e, env->bufs, red.data(), 0, 1);
+    std::vector<uint32_t> chg(64 * CV_CHG_CAP);
+    for (int e = 0; e < env->n_envs; e++) covid_step_env(env->cfg, e, env->bufs, red.data(), chg.data(), 0, 1);
     env->launches++;
     return AIE_OK;
 }
