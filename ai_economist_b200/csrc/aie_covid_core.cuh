@@ -237,26 +237,14 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
             int n_chg = 0;
             double wf[8];                                 // this state's filter weights (F <= 8), widened once
             for (int f = 0; f < 8; f++) wf[f] = f < F ? (double)c.conv_w[a * F + f] : 0.0;
-            const int n_chunks = (L1 + 15) >> 4;          // rows are padded to a multiple of 16 bytes
 #if CV_ON_DEVICE
-            // software pipeline, four 16-column chunks deep: global-load latency is several hundred cycles, one chunk of
-            // processing only ~100
-            int4 q[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) q[j] = j < n_chunks ? *(const int4 *)(row + 16 * j) : make_int4(0, 0, 0, 0);
+            int4 nxt = *(const int4 *)row;                // software pipeline: the next 16 columns are always in flight
 #endif
-            for (int g0 = 0; g0 < n_chunks; g0 += 4)
-#if CV_ON_DEVICE
-#pragma unroll
-#endif
-            for (int gj = 0; gj < 4; gj++) {
-                const int ci = g0 + gj;
-                if (ci >= n_chunks) break;
-                const int p0 = 16 * ci;
+            for (int p0 = 0; p0 < L1; p0 += 16) {
 #if CV_ON_DEVICE
                 union { int4 v; int8_t b[16]; uint32_t w32[4]; } ld;
-                ld.v = q[gj];
-                if (ci + 4 < n_chunks) q[gj] = *(const int4 *)(row + p0 + 64);   // LDG.128, consumed four chunks later
+                ld.v = nxt;
+                if (p0 + 16 < L1) nxt = *(const int4 *)(row + p0 + 16);   // rows are padded to 16 bytes (LDG.128)
 #else
                 cv_b16 ld = *(const cv_b16 *)(row + p0);
 #endif

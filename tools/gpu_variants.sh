@@ -16,3 +16,4 @@ except Exception as ex:
 PY
 }
 run c4 "--workload c4 --steps 300 --warmup 20" X=1
+run c2 "" X=1
