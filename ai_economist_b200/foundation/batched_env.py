@@ -130,6 +130,14 @@ class BatchedFoundationEnv:
             ag._env = self
         self._agent_lookup = {str(a.idx): a for a in self.all_agents}
 
+        # base_env.py:286-287: a `seed` kwarg seeds the stream before anything is built, so scenario constructors that
+        # draw (split_layout's skill table, multi_zone's first zone shuffle) consume the seeded stream
+        self._rs = None
+        self._seeds = None
+        if seeds is not None:
+            self.seed(seeds)
+        elif seed is not None:
+            self.seed(seed)
         self.scenario = scenario_cls(self, **scenario_kwargs)
         self.name = scenario_cls.name
 
@@ -173,14 +181,8 @@ class BatchedFoundationEnv:
                 self._stepper = stepper_factory(spec, self.n_envs, auto_reset, event_envs=event_envs)
             except TypeError:
                 self._stepper = stepper_factory(spec, self.n_envs, auto_reset)
-        self._rs = None
-        self._seeds = None
         self._loaded = False
         self._completions = np.zeros(self.n_envs, np.int64)
-        if seeds is not None:
-            self.seed(seeds)
-        elif seed is not None:
-            self.seed(seed)
         if self._stepper is not None:  # stepper_factory may return None: host-side reset/spec only (CPU oracle legs)
             self._build_views()
         # Saez tax model: the estimator half lives on the host (foundation/saez.py)
@@ -285,7 +287,7 @@ class BatchedFoundationEnv:
         per = []
         for e in range(self.n_envs):
             rs = self._rs[e]
-            st = self.scenario.host_reset(rs)
+            st = self.scenario.host_reset(rs, e)
             key = rs.get_state()
             st["mt_key"], st["mt_pos"] = np.asarray(key[1], np.uint32), int(key[2])
             st["completions"] = int(self._completions[e])

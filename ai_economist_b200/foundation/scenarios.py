@@ -138,7 +138,7 @@ class LayoutFromFile(BaseScenario):
                                       2: (r0 + dr, c0 + dc), 3: (r0 - dr, c0 - dc)}[int(g)])
             count[g] += 1
 
-    def host_reset(self, rs):
+    def host_reset(self, rs, e=0):
         env = self.env
         A = env.n_agents
         st = dict(stone=self.source_maps["Stone"].copy(), wood=self.source_maps["Wood"].copy(),
@@ -206,10 +206,21 @@ class Uniform(BaseScenario):
         assert all(0 <= v <= 1 for v in self.clumpiness.values())
         self.gradient_steepness = float(gradient_steepness)
         assert self.gradient_steepness >= 1.0
+        self.source_prob_maps = self.make_source_prob_maps(self._ctor_stream())
+
+    def _ctor_stream(self):
+        """The stream the reference's constructor would draw from: the env's seeded stream when `seed=` was passed
+        to make_env_instance (base_env.py:286-287 seeds before anything is built), else an unseeded one."""
+        rs = self.env._rs
+        return rs[0] if rs is not None else np.random.RandomState()
+
+    def make_source_prob_maps(self, rs):
+        """dynamic_layout.py:289-308"""
+        H, W = self.env.world_size
         grad = np.arange(H)[:, None].repeat(W, axis=1) ** self.gradient_steepness
         grad = grad / np.mean(grad)
         # sic: both maps are scaled by the Wood coverage (dynamic_layout.py:302-306)
-        self.source_prob_maps = {"Wood": grad * self.coverage["Wood"], "Stone": grad[-1::-1] * self.coverage["Wood"]}
+        return {"Wood": grad * self.coverage["Wood"], "Stone": grad[-1::-1] * self.coverage["Wood"]}
 
     def _generate_layout(self, rs):
         """Clumped random source placement, dynamic_layout.py:313-392 (same draws, same order)."""
@@ -250,19 +261,191 @@ class Uniform(BaseScenario):
             src = {k: v * self._checker_mask for k, v in src.items()}
         return {k: (v > 0).astype(np.uint8) for k, v in src.items()}
 
-    def host_reset(self, rs):
-        A = self.env.n_agents
+    def _starting_layout(self, rs):
+        """reset_starting_layout (dynamic_layout.py:313-392) -> (source maps, water map)."""
         H, W = self.env.world_size
-        src = self._generate_layout(rs)
+        return self._generate_layout(rs), np.zeros((H, W), np.uint8)
+
+    def host_reset(self, rs, e=0):
+        A = self.env.n_agents
+        src, water = self._starting_layout(rs)
         st = dict(stone=src["Stone"].copy(), wood=src["Wood"].copy(), stone_src=src["Stone"].copy(),
-                  wood_src=src["Wood"].copy(), water=np.zeros((H, W), np.uint8))
+                  wood_src=src["Wood"].copy(), water=water)
         st["coin"] = np.full(A, self.starting_agent_coin)
         order = rs.permutation(A)  # world.get_random_order_agents()
-        st["loc"] = self._place_randomly(rs, order, np.zeros((H, W), bool))
+        st["loc"] = self._place_randomly(rs, order, water > 0)
         self._component_resets(rs, st)
         return st
 
     def scenario_spec_fields(self):
         d = super().scenario_spec_fields()
         d.update(has_water=0, regen_weight=[self.regen["Stone"], self.regen["Wood"]])
+        return d
+
+
+@scenario_registry.add
+class MultiZone(Uniform):
+    """Wood / stone / mixed source zones on a shuffled partition grid (dynamic_layout.py:706-873).  The zone
+    assignment is re-shuffled from the env's stream at every reset, before the clumped layout is drawn."""
+    name = "multi_zone/simple_wood_and_stone"
+
+    def __init__(self, env, num_partitions_row=8, num_partitions_col=8, num_wood_zones=6, num_stone_zones=6,
+                 num_wood_and_stone_zones=4, **kw):
+        self.num_partitions_row = num_partitions_row
+        self.num_partitions_col = num_partitions_col
+        self.zone_specs = {"Wood": (0, num_wood_zones), "Stone": (1, num_stone_zones),
+                           "WoodStone": (2, num_wood_and_stone_zones)}
+        super().__init__(env, **kw)
+        if env._rs is not None:   # the constructor's shuffle advances every replica's seeded stream alike
+            n_regions = self.num_partitions_row * self.num_partitions_col
+            for rs in env._rs[1:]:
+                rs.shuffle(np.arange(n_regions))
+
+    def make_source_prob_maps(self, rs):
+        """dynamic_layout.py:778-864 (one np.random.shuffle of the region -> zone-type vector)."""
+        H, W = self.env.world_size
+        idx = [v[0] for v in self.zone_specs.values()]
+        per_type = [v[1] for v in self.zone_specs.values()]
+        n_zones = sum(per_type)
+        n_regions = self.num_partitions_row * self.num_partitions_col
+        assert n_regions >= n_zones
+        size_r = int(np.ceil(H / self.num_partitions_row))
+        size_c = int(np.ceil(W / self.num_partitions_col))
+        grid = np.concatenate([np.repeat(idx, per_type), np.array([-1] * (n_regions - n_zones))])
+        rs.shuffle(grid)
+        grid = grid.reshape((self.num_partitions_row, self.num_partitions_col))
+        out = {}
+        for res, own in (("Wood", 0), ("Stone", 1)):
+            prob = np.where((grid == own) | (grid == 2), np.ones_like(grid), np.zeros_like(grid))
+            prob = np.kron(prob, np.ones((size_r, size_c)))[:H, :W]
+            assert prob.shape == (H, W), "World not correct size!"
+            out[res] = prob / np.mean(prob)
+        # sic: both maps are scaled by the Wood coverage (dynamic_layout.py:860-863)
+        return {"Wood": out["Wood"] * self.coverage["Wood"], "Stone": out["Stone"] * self.coverage["Wood"]}
+
+    def _starting_layout(self, rs):
+        self.source_prob_maps = self.make_source_prob_maps(rs)  # dynamic_layout.py:866-872
+        return super()._starting_layout(rs)
+
+
+@scenario_registry.add
+class Quadrant(Uniform):
+    """Two water lines with gaps split the world into four quadrants; wood concentrates towards the bottom rows,
+    stone towards the left columns (dynamic_layout.py:876-1021)."""
+    name = "quadrant/simple_wood_and_stone"
+    required_entities = Uniform.required_entities + ["Water"]
+
+    def __init__(self, env, **kw):
+        super().__init__(env, **kw)
+        H, W = env.world_size
+        o0, o1 = 0.2, 0.35
+        rn = (0.5 + np.arange(H)) / H
+        cn = (0.5 + np.arange(W)) / W
+        rseg = ((rn < o0) + (rn > o1)) * ((rn < 1 - o1) + (rn > 1 - o0))
+        cseg = ((cn < o0) + (cn > o1)) * ((cn < 1 - o1) + (cn > 1 - o0))
+        water = np.zeros((H, W))
+        water[:, H // 2] = rseg     # sic: the reference indexes the column with height // 2 ...
+        water[W // 2, :] = cseg     # ... and the row with width // 2 (dynamic_layout.py:951-952)
+        self._water = water
+        for k, v in self.source_prob_maps.items():
+            v = v * (1 - self._water)
+            self.source_prob_maps[k] = v / np.sum(v)
+
+    def make_source_prob_maps(self, rs):
+        """dynamic_layout.py:960-990"""
+        H, W = self.env.world_size
+        g = np.arange(H)[:, None].repeat(W, axis=1) ** (self.gradient_steepness / 2)
+        w_grad = g[::-1]
+        g = np.arange(W)[None].repeat(H, axis=0) ** (self.gradient_steepness / 2)
+        s_grad = g[:, ::-1]
+        tot = s_grad + w_grad
+        s_grad, w_grad = tot * s_grad, tot * w_grad
+        return {"Stone": s_grad / np.sum(s_grad), "Wood": w_grad / np.sum(w_grad)}
+
+    def _starting_layout(self, rs):
+        """dynamic_layout.py:992-1021: the uniform layout, nothing on the water lines, then the water."""
+        H, W = self.env.world_size
+        src, _ = super()._starting_layout(rs)
+        for k in src:
+            src[k][:, H // 2] = 0
+            src[k][W // 2, :] = 0
+        return src, (self._water > 0).astype(np.uint8)
+
+    def scenario_spec_fields(self):
+        d = super().scenario_spec_fields()
+        d.update(has_water=1)
+        return d
+
+
+@scenario_registry.add
+class SplitLayout(LayoutFromFile):
+    """layout_from_file with a water row through the middle, rank-averaged Pareto build skills handed out in a random
+    order, and the agents of the chosen skill ranks placed above the water (layout_from_file.py:654-800)."""
+    name = "split_layout/simple_wood_and_stone"
+
+    def __init__(self, env, water_row=None, skill_rank_of_top_agents=None, **kw):
+        super().__init__(env, **kw)
+        if self.fixed_four_skill_and_loc:
+            raise ValueError("The split layout scenario does not support fixed_four_skill_and_loc. "
+                             "Set this to False.")
+        H, W = env.world_size
+        if water_row is None:
+            self._water_line = H // 2
+        else:
+            self._water_line = int(water_row)
+            assert 0 < self._water_line < H - 1
+        for k, m in self.source_maps.items():
+            m[self._water_line, :] = 1 if k == "Water" else 0
+        if skill_rank_of_top_agents is None:
+            skill_rank_of_top_agents = [0]
+        if isinstance(skill_rank_of_top_agents, (int, float)):
+            self.skill_rank_of_top_agents = [int(skill_rank_of_top_agents)]
+        elif isinstance(skill_rank_of_top_agents, (tuple, list)):
+            self.skill_rank_of_top_agents = list(set(skill_rank_of_top_agents))
+        else:
+            raise TypeError("skill_rank_of_top_agents must be a scalar index, or a list of scalar indices.")
+        for rank in self.skill_rank_of_top_agents:
+            assert 0 <= rank < env.n_agents
+        assert 0 < len(self.skill_rank_of_top_agents) < env.n_agents
+        bm = env.get_component("Build")
+        assert bm.skill_dist == "pareto"
+        # The reference draws its 100000 x n_agents Pareto table from the global stream inside the constructor
+        # (layout_from_file.py:747); here every replica draws its own table from its own stream, at construction
+        # when `seed=` was passed (as base_env.py:286-287 seeds first), else from an unseeded stream.
+        pmsm, A = bm.payment_max_skill_multiplier, env.n_agents
+        self._split_ranked_skill = np.zeros((env.n_envs, A))
+        for e in range(env.n_envs):
+            rs = env._rs[e] if env._rs is not None else np.random.RandomState()
+            samples = rs.pareto(4, size=(100000, A))
+            ranked = np.sort(np.minimum(pmsm, (pmsm - 1) * samples + 1), axis=1).mean(axis=0)
+            self._split_ranked_skill[e] = (ranked * bm.payment)[::-1]
+
+    def host_reset(self, rs, e=0):
+        st = super().host_reset(rs, e)
+        env = self.env
+        A = env.n_agents
+        H, W = env.world_size
+        # additional_reset_steps (layout_from_file.py:766-790): everybody is taken off the map and re-placed
+        order = rs.permutation(A)
+        loc = -np.ones((A, 2), np.int16)
+        taken = np.zeros((H, W), bool)
+        blocked = st["water"] > 0
+        for i, a in enumerate(order):
+            st["build_payment"][a] = self._split_ranked_skill[e, i]
+            r_min, r_max = (0, self._water_line) if i in self.skill_rank_of_top_agents else (self._water_line + 1, H)
+            r, c = rs.randint(r_min, r_max), rs.randint(0, W)
+            tries = 0
+            while blocked[r, c] or taken[r, c]:
+                r, c = rs.randint(r_min, r_max), rs.randint(0, W)
+                tries += 1
+                if tries > 200:
+                    raise TimeoutError
+            loc[a] = (r, c)
+            taken[r, c] = True
+        st["loc"] = loc
+        return st
+
+    def scenario_spec_fields(self):
+        d = super().scenario_spec_fields()
+        d.update(reset_mode=0)   # the rank / half-map placement is host-side; auto-reset restores the snapshot
         return d

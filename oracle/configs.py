@@ -126,4 +126,36 @@ CONFIGS = {
         fixed_four_skill_and_loc=False, n_agents=6, world_size=[25, 25], episode_length=30,
         multi_action_mode_agents=False, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True, energy_warmup_constant=5, energy_warmup_method="decay"),
+    # the other scenario variants of the family (host-side layouts; the step path is the same)
+    "multi_zone": dict(
+        scenario_name="multi_zone/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict(skill_dist="pareto"))],
+        n_agents=5, world_size=[20, 20], episode_length=120,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        num_partitions_row=4, num_partitions_col=4, num_wood_zones=4, num_stone_zones=4, num_wood_and_stone_zones=3,
+        starting_agent_coin=10, starting_wood_coverage=0.10, starting_stone_coverage=0.10,
+        wood_regen_weight=0.05, stone_regen_weight=0.03),
+    "quadrant": dict(
+        scenario_name="quadrant/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="lognormal", payment_max_skill_multiplier=2)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict(skill_dist="lognormal"))],
+        n_agents=6, world_size=[21, 21], episode_length=120,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        starting_agent_coin=10, starting_wood_coverage=0.08, starting_stone_coverage=0.08,
+        wood_regen_weight=0.04, stone_regen_weight=0.04, checker_source_blocks=True),
+    # split_layout draws its skill table inside the constructor: `seed` is a constructor kwarg here
+    "split_layout": dict(
+        scenario_name="split_layout/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict())],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=10, seed=77,
+        skill_rank_of_top_agents=[0, 2], n_agents=5, world_size=[25, 25], episode_length=120,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
 }

@@ -33,6 +33,9 @@ PLAN = [
     ("c5_small", 1001, 150, 25),
     ("c5_full", 1001, 60, 20),
     ("wealth_redistribution", 1001, 300, 25),
+    ("multi_zone", 1001, 120, 20),
+    ("quadrant", 1001, 120, 20),
+    ("split_layout", 1001, 120, 20),
     # multi-episode traces (env.reset() between episodes, the global numpy stream continues): device-side reset
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),
@@ -124,5 +127,7 @@ def generate(cfg_name, seed, steps, full_every):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])   # optional: config names to (re)generate
     for item in PLAN:
-        generate(*item)
+        if not only or item[0] in only:
+            generate(*item)

@@ -94,3 +94,20 @@ def test_second_reset_continues_the_stream_like_the_reference():
     ref = env.scenario.host_reset(rs)
     env2 = env.host_reset_arrays  # noqa: F841 (API exists)
     assert ref["loc"].shape == (4, 2)
+
+
+@pytest.mark.parametrize("name", ["split_layout", "multi_zone"])
+def test_constructor_time_draws_are_per_replica(name):
+    """split_layout draws its skill table and multi_zone its first zone shuffle inside the constructor
+    (layout_from_file.py:747, dynamic_layout.py:809): with `seed=` every replica consumes its own seeded stream, so
+    replica e of a batch equals a single env built with seed + e."""
+    z, meta, init = gu.load_fixture([p for p in gu.golden_files() if name in p][0])
+    meta["reference_kwargs"]["seed"] = 77
+    if name == "split_layout":   # keep the 100000-row table cheap: the draw count is what matters
+        meta["reference_kwargs"]["n_agents"] = 3
+        meta["reference_kwargs"]["skill_rank_of_top_agents"] = [0]
+    batch = make_env(meta, n_envs=3).host_reset_arrays()
+    meta["reference_kwargs"]["seed"] = 79
+    single = make_env(meta, n_envs=1).host_reset_arrays()
+    for k in batch:
+        assert np.array_equal(np.asarray(batch[k][2]), np.asarray(single[k][0])), k
