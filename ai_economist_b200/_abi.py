@@ -2,7 +2,7 @@
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 8, 16, 64
 AIE_OK = 0
 
@@ -39,6 +39,7 @@ class AieConfig(C.Structure):
         ("reset_mode", C.c_int32), ("build_skill_dist", C.c_int32), ("gather_skill_dist", C.c_int32),
         ("payment_max_skill_multiplier", C.c_int32), ("fixed_four", C.c_int32),
         ("ranked_locs", (C.c_int16 * 2) * 64), ("avg_ranked_skill", C.c_double * 64),
+        ("single_action_planner", C.c_int32), ("regen_halfwidth", C.c_int32 * 2),
     ]
 
 
@@ -209,4 +210,6 @@ def config_from_spec(spec, auto_reset=True):
         cfg.ranked_locs[i][0], cfg.ranked_locs[i][1] = int(rc[0]), int(rc[1])
     for i, v in enumerate(spec.get("avg_ranked_skill", [])):
         cfg.avg_ranked_skill[i] = float(v)
+    cfg.single_action_planner = int(spec.get("single_action_planner", 0))
+    cfg.regen_halfwidth[0], cfg.regen_halfwidth[1] = [int(v) for v in spec.get("regen_halfwidth", [0, 0])]
     return cfg

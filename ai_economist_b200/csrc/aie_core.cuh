@@ -290,7 +290,13 @@ AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t
         s.act_sell[a] = sell0; s.act_sell[c.A + a] = sell1;
     }
     for (int b = lane; b < 16; b += NL) {
-        int v = (act_p && b < c.n_act_p) ? act_p[b] : 0;
+        int v;
+        if (c.planner_single) {  // single_action_map (base_agent.py:109-114): bracket (g-1) / R, sub-action (g-1) % R + 1
+            const int g = act_p ? act_p[0] - 1 : -1;
+            v = (g >= 0 && g < c.B * c.R && g / c.R == b) ? g % c.R + 1 : 0;
+        } else {
+            v = (act_p && b < c.n_act_p) ? act_p[b] : 0;
+        }
         if (v < 0 || v > c.R) v = 0;
         s.act_tax[b] = (uint8_t)v;
     }
@@ -701,6 +707,21 @@ AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, int
 // in row-major order; an empty source cell respawns iff u < regen_weight.  The whole 2*H*W-word run of the
 // stream is consumed; only empty source cells temper/compare their two words.
 // ------------------------------------------------------------------------------------------------
+// regen_halfwidth > 0 (dynamic_layout.py:446-461): the respawn probability of source cell k is the box-filtered
+// source map (health = max(resource, source) = source for max_health 1), i.e. a function of the number of source
+// cells in its d x d window.  Cold: only evaluated for empty source cells of configs that set a halfwidth.
+AIE_DEV_NOINLINE uint64_t regen_window_thresh(const DevCfg &c, const Env &e, int cc, int k) {
+    const int hw = c.regen_hw[cc], r0 = k / c.W, c0 = k - r0 * c.W;
+    const uint8_t src_bit = (uint8_t)(4u << cc);
+    int n = 0;
+    for (int r = r0 - hw; r <= r0 + hw; r++) {
+        if (r < 0 || r >= c.H) continue;
+        for (int q = c0 - hw; q <= c0 + hw; q++)
+            if (q >= 0 && q < c.W && (e.cell[r * c.W + q] & src_bit)) n++;
+    }
+    return c.regen_tab[cc][n];
+}
+
 AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
     const int HW = c.HW, lane = r.lane;
     const uint8_t res_bit = (uint8_t)(1u << cc), src_bit = (uint8_t)(4u << cc);
@@ -720,7 +741,7 @@ AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
                 uint8_t cb = e.cell[k];
                 if ((cb & src_bit) && !(cb & res_bit)) {
                     uint64_t v = ((uint64_t)(pend_a >> 5) << 26) | (uint64_t)(mt_temper(e.mt[base + w]) >> 6);
-                    if (v < thresh) e.cell[k] = cb | res_bit;
+                    if (v < (c.regen_hw[cc] ? regen_window_thresh(c, e, cc, k) : thresh)) e.cell[k] = cb | res_bit;
                 }
             }
         }
@@ -742,7 +763,7 @@ AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
                 if (k < k_lo || k >= k_hi) continue;
                 uint64_t v = ((uint64_t)(mt_temper(e.mt[base + 2 * k]) >> 5) << 26) |
                              (uint64_t)(mt_temper(e.mt[base + 2 * k + 1]) >> 6);
-                if (v < thresh) e.cell[k] = (uint8_t)(e.cell[k] | res_bit);
+                if (v < (c.regen_hw[cc] ? regen_window_thresh(c, e, cc, k) : thresh)) e.cell[k] = (uint8_t)(e.cell[k] | res_bit);
             }
         }
         if (w_end & 1) pend_a = mt_temper(e.mt[base + w_end - 1]);
@@ -1369,7 +1390,9 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             for (int rr = lane; rr <= c.R; rr += NL) {
                 bool open = rr == 0 || first_day;
                 if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.net_hist[2 * P];
-                o.p_mask()[b * (1 + c.R) + rr] = open ? 1.0f : 0.0f;
+                // single-action planner: one leading NO-OP, then every bracket's R rates (base_agent.py:452-459)
+                const int at = c.planner_single ? (rr == 0 ? 0 : b * c.R + rr) : b * (1 + c.R) + rr;
+                o.p_mask()[at] = open ? 1.0f : 0.0f;
             }
     } else if (lane == 0) {
         o.p_mask()[0] = 1.0f;
@@ -1447,6 +1470,11 @@ AIE_DEV void sample_actions_unit(const DevCfg &c, const float *a_mask, const flo
                 if (lane == 0) act_a[a * c.n_sub + si] = v;
                 off += c.sub_n[si] + 1;
             }
+        }
+    } else if (c.planner_single) {
+        if (u == c.A) {
+            const int v = sample_segment_warp(p_mask, c.Np, key + 0x10000, lane);
+            if (lane == 0) act_p[0] = v;
         }
     } else if (c.planner_acts) {
         const int b = u - c.A;

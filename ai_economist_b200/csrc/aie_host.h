@@ -68,6 +68,18 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         double w = u.regen_weight[r];
         if (!(w >= 0.0 && w <= 1.0)) return bad("regen weight must be in [0, 1]");
         c.regen_thresh[r] = (uint64_t)ceil(ldexp(w, 53));  // exact: N / 2^53 < w  <=>  N < ceil(w * 2^53)
+        const int hw = u.regen_halfwidth[r];
+        if (hw < 0 || hw > 3) return bad("regen_halfwidth must be in [0, 3]");
+        c.regen_hw[r] = hw;
+        // scipy.signal.convolve2d accumulates health * kernel terms in float64; every kernel entry is
+        // (regen_weight * 1.0) / d^2 and health is 0/1, so the value at a cell is n sequential additions of that entry
+        const int d = 1 + 2 * hw;
+        const double kv = (w * 1.0) / (double)(d * d);
+        double p = 0.0;
+        for (int n = 0; n < 50; n++) {
+            c.regen_tab[r][n] = p >= 1.0 ? (1ull << 53) : (uint64_t)ceil(ldexp(p, 53));
+            p += kv;
+        }
     }
     c.eta = u.isoelastic_eta; c.energy_cost = u.energy_cost; c.warm_const = u.energy_warmup_constant;
     if (!(c.eta >= 0.0 && c.eta <= 1.0)) return bad("isoelastic_eta must be in [0, 1]");
@@ -128,10 +140,12 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.n_act_a = c.multi_action ? c.n_sub : 1;
     if (c.n_sub == 0) return bad("mobile agents need at least one action component");
     c.planner_acts = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_MODEL_WRAPPER && !c.disable_taxes) ? 1 : 0;
-    c.n_act_p = c.planner_acts ? c.B : 0;
+    c.planner_single = (c.planner_acts && u.single_action_planner) ? 1 : 0;
+    c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;
-    c.Np = c.planner_acts ? c.B * (1 + c.R) : 1;
+    c.Np = c.planner_acts ? (c.planner_single ? 1 + c.B * c.R : c.B * (1 + c.R)) : 1;
     if (c.Na > MAX_MASK) return bad("agent action mask too long");
+    if (c.planner_single && c.Np > MAX_MASK) return bad("single-action planner mask too long (1 + n_brackets * n_disc_rates > 160)");
 
     c.sh_curr_rates = SH_PRICE_HIST + 2 * c.P;
     c.sh_last_incomes = c.sh_curr_rates + 16;

@@ -119,6 +119,12 @@ struct DevCfg {
     int32_t tab_p, tab_pa, tab_m, tab_n;               // offsets (u16 words) into the program table, total words (even)
     uint32_t HW_magic, ww_magic, Fa_magic, Fpa_magic, Na_magic;  // floor(2^32 / n) + 1: run index -> (row, column)
     uint32_t win_magic; int32_t win_dr32, win_dc32;  // window walk: lane / win, and the (row, col) step of 32 cells
+    // single-action planner (multi_action_mode_planner=False): act_p is one index into [NO-OP] ++ B x R rates
+    int32_t planner_single;
+    // regen_halfwidth > 0 (cold path): threshold by the number n of source cells in the d x d window of the cell,
+    // regen_tab[c][n] = ceil(p_n * 2^53) with p_n the running float64 sum of n copies of regen_weight / d^2
+    int32_t regen_hw[2];
+    uint64_t regen_tab[2][50];
 };
 
 // raw device pointers (mirrors aie_buffers)

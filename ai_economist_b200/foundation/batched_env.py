@@ -77,8 +77,6 @@ class BatchedFoundationEnv:
         assert self._episode_length >= 1
         self.multi_action_mode_agents = bool(multi_action_mode_agents)
         self.multi_action_mode_planner = bool(multi_action_mode_planner)
-        if not self.multi_action_mode_planner:
-            raise NotImplementedError("single-action planner mode is not on the GPU path")
         if not (flatten_observations and flatten_masks):
             raise NotImplementedError("the batched stepper always emits flattened observations and masks; "
                                       "use reference_view() for the nested layout")
@@ -145,6 +143,7 @@ class BatchedFoundationEnv:
         spec = dict(components=[c.name for c in self._components], n_agents=self.n_agents,
                     height=self.world_size[0], width=self.world_size[1], episode_length=self._episode_length,
                     multi_action_agents=int(self.multi_action_mode_agents),
+                    single_action_planner=int(not self.multi_action_mode_planner),
                     allow_observation_scaling=int(self._allow_observation_scaling),
                     build_payment=10.0, build_labor=10.0, move_labor=1.0, collect_labor=1.0,
                     max_bid_ask=10, order_duration=50, max_num_orders=50, order_labor=0.25,

@@ -72,11 +72,14 @@ class DenseLogger:
         out = {}
         for ag in self.env.all_agents:
             names = list(ag._action_names)
-            if ag.idx == "p":
+            if ag.idx == "p" and ag.multi_action_mode:
                 row = [] if act_p is None else [int(v) for v in np.asarray(act_p).reshape(-1)][:len(names)]
                 out["p"] = {n: v for n, v in zip(names, row) if v > 0}
                 continue
-            row = np.asarray(act_a[int(ag.idx)]).reshape(-1)
+            if ag.idx == "p":   # single-action planner: one index, decoded like the agents' below
+                row = np.zeros(1, np.int64) if act_p is None or not names else np.asarray(act_p).reshape(-1)
+            else:
+                row = np.asarray(act_a[int(ag.idx)]).reshape(-1)
             if ag.multi_action_mode:
                 out[str(ag.idx)] = {n: int(v) for n, v in zip(names, row) if int(v) > 0}
             else:

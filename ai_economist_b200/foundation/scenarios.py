@@ -196,8 +196,8 @@ class Uniform(BaseScenario):
         m = 2 if self.checker else 1
         self.coverage = {"Wood": float(starting_wood_coverage) * m, "Stone": float(starting_stone_coverage) * m}
         assert 0 < self.coverage["Wood"] < 1 and 0 < self.coverage["Stone"] < 1
-        if int(wood_regen_halfwidth) or int(stone_regen_halfwidth):
-            raise NotImplementedError("regen_halfwidth > 0 is not on the GPU path")
+        self.regen_halfwidth = {"Wood": int(wood_regen_halfwidth), "Stone": int(stone_regen_halfwidth)}
+        assert 0 <= self.regen_halfwidth["Wood"] <= 3 and 0 <= self.regen_halfwidth["Stone"] <= 3
         if int(wood_max_health) != 1 or int(stone_max_health) != 1:
             raise NotImplementedError("max_health != 1 is not on the GPU path")
         self.regen = {"Wood": float(wood_regen_weight), "Stone": float(stone_regen_weight)}
@@ -279,7 +279,8 @@ class Uniform(BaseScenario):
 
     def scenario_spec_fields(self):
         d = super().scenario_spec_fields()
-        d.update(has_water=0, regen_weight=[self.regen["Stone"], self.regen["Wood"]])
+        d.update(has_water=0, regen_weight=[self.regen["Stone"], self.regen["Wood"]],
+                 regen_halfwidth=[self.regen_halfwidth["Stone"], self.regen_halfwidth["Wood"]])
         return d
 
 

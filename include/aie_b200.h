@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AIE_ABI_VERSION 2
+#define AIE_ABI_VERSION 3
 
 #define AIE_MAX_COMPONENTS 8
 #define AIE_MAX_BRACKETS 16
@@ -112,6 +112,13 @@ typedef struct aie_config {
     int32_t fixed_four;             /* fixed_four_skill_and_loc */
     int16_t ranked_locs[AIE_MAX_AGENTS][2];       /* start cell of the i-th skill-ranked slot */
     double avg_ranked_skill[AIE_MAX_AGENTS];      /* build payment of the i-th skill-ranked slot */
+    /* ABI 3 */
+    int32_t single_action_planner;  /* multi_action_mode_planner == False (base_env.py:259): the planner sends ONE index
+                                       into [NO-OP] ++ bracket 0's rates ++ bracket 1's rates ... (single_action_map,
+                                       base_agent.py:109-114) and its flattened mask is 1 + n_brackets * n_disc_rates long */
+    int32_t regen_halfwidth[2];     /* {stone,wood}_regen_halfwidth, [Stone, Wood], 0..3 (dynamic_layout.py:150-153):
+                                       a source cell respawns with probability convolve2d(source map, regen_weight /
+                                       d^2 * ones(d, d))[cell], d = 1 + 2 * halfwidth (dynamic_layout.py:446-461) */
 } aie_config;
 
 /* Sizes the caller needs to allocate the device buffers. */
@@ -125,7 +132,7 @@ typedef struct aie_dims {
     int32_t mask_agent;       /* flattened agent action mask length */
     int32_t mask_planner;
     int32_t n_act_agent;      /* ints per agent per step (1 single-action, #subspaces multi-action) */
-    int32_t n_act_planner;    /* ints per env per step for the planner (n_brackets or 0) */
+    int32_t n_act_planner;    /* ints per env per step for the planner (n_brackets, 1 for a single-action planner, or 0) */
     int32_t state_bytes;      /* bytes per env of the packed state record (multiple of 16) */
     int32_t algorithmic_bytes_per_env_step; /* obs+mask+rew/done out + actions in + 2*state */
     /* episode statistics ("stats" field of the state record, float64[n_stats], zero at reset): the accumulators

@@ -158,4 +158,27 @@ CONFIGS = {
         skill_rank_of_top_agents=[0, 2], n_agents=5, world_size=[25, 25], episode_length=120,
         multi_action_mode_agents=False, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True),
+    # single-action planner (multi_action_mode_planner=False): one index over [NO-OP] ++ every bracket's rates
+    "tax_single_planner": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=5, rate_disc=0.05,
+                                                tax_model="model_wrapper"))],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5,
+        fixed_four_skill_and_loc=False, n_agents=5, world_size=[25, 25], episode_length=150,
+        multi_action_mode_agents=False, multi_action_mode_planner=False,
+        flatten_observations=True, flatten_masks=True),
+    # regen_halfwidth > 0: the respawn probability of a source cell counts the source cells in its d x d window
+    "uniform_halfwidth": dict(
+        scenario_name="uniform/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                    ("Gather", dict(skill_dist="pareto"))],
+        n_agents=5, world_size=[18, 18], episode_length=150,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True,
+        starting_agent_coin=10, starting_wood_coverage=0.12, starting_stone_coverage=0.12,
+        wood_regen_halfwidth=2, wood_regen_weight=0.6, stone_regen_halfwidth=1, stone_regen_weight=0.4),
 }

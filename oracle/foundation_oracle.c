@@ -189,7 +189,10 @@ int orc_dims_from_config(const orc_config *cfg, orc_dims *d) {
     /* base_agent.py:440-460 */
     d->mask_a = cfg->multi_action_agents ? (n_single + n_sub) : (1 + n_single);
     d->n_act_a = cfg->multi_action_agents ? n_sub : 1;
-    if (planner_has_tax_actions(cfg)) {
+    if (planner_has_tax_actions(cfg) && cfg->single_action_planner) {
+        d->n_act_p = 1;  /* one index into [NO-OP] ++ bracket 0 rates ++ bracket 1 rates ... (base_agent.py:109-114) */
+        d->mask_p = 1 + B * cfg->n_disc_rates;
+    } else if (planner_has_tax_actions(cfg)) {
         d->n_act_p = B;
         d->mask_p = B * (1 + cfg->n_disc_rates);
     } else {
@@ -712,19 +715,37 @@ static void tax_reset(const orc_batch *b, env_t *s) {
 
 /* ------------------------------------------------------------------------- */
 /* scenario_step: resource regeneration (layout_from_file.py:372-410,         */
-/* identical copy dynamic_layout.py:433-471); regen_halfwidth == 0 and        */
-/* max_health == 1 (the only values the BASELINE configs use).                */
+/* identical copy dynamic_layout.py:433-471); max_health == 1.               */
 /* ------------------------------------------------------------------------- */
+/* scipy.signal.convolve2d(health, kernel, "same") at one cell, zero fill outside the map: a running float64 sum of
+ * health * kernel_value over the d x d window (every kernel entry is regen_weight / d^2, so the term order only
+ * matters through the number of non-zero terms). */
+static double regen_prob(const orc_batch *b, const env_t *s, int c, int k) {
+    int H = b->cfg.height, W = b->cfg.width, hw = b->cfg.regen_halfwidth[c], d = 1 + 2 * hw;
+    double kv = (b->cfg.regen_weight[c] * 1.0) / (double)(d * d), p = 0.0;
+    int r0 = k / W, c0 = k % W, dr, dc;
+    for (dr = -hw; dr <= hw; dr++)
+        for (dc = -hw; dc <= hw; dc++) {
+            int r = r0 + dr, cc = c0 + dc;
+            if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
+            p += fmax(s->res[c][r * W + cc], s->src[c][r * W + cc]) * kv;
+        }
+    return p;
+}
+
 static void scenario_step(const orc_batch *b, env_t *s) {
     int HW = b->cfg.height * b->cfg.width, k, ri;
     static const int order[2] = {WOOD, STONE}; /* resources = ["Wood", "Stone"] */
     for (ri = 0; ri < 2; ri++) {
         int c = order[ri];
         double w = b->cfg.regen_weight[c];
+        /* the convolution reads the pre-update health map; with max_health == 1 health == source map, which this
+         * loop never changes, so evaluating it cell by cell is the same */
         for (k = 0; k < HW; k++) {
             double health = fmax(s->res[c][k], s->src[c][k]);
             double u = np_rand(s); /* np.random.rand(*health.shape): one draw per cell, row-major */
-            int respawn = u < (health * w); /* convolve2d with a 1x1 kernel of value regen_weight */
+            int respawn = b->cfg.regen_halfwidth[c] ? (u < regen_prob(b, s, c, k))
+                                                    : (u < (health * w)); /* 1x1 kernel of value regen_weight */
             int spawnable;
             {   /* maps.empty (all maps sum == 0) + resource + source > 0, then *= source > 0 */
                 double sum = s->res[STONE][k] + s->res[WOOD][k] + s->house[k] + s->water[k] +
@@ -1033,8 +1054,9 @@ static void generate_observations(const orc_batch *b, env_t *s) {
     }
     if (planner_has_tax_actions(cfg)) { /* redistribution.py:1025-1104 (multi-action planner) */
         int n = 0, R = cfg->n_disc_rates, bi, r;
+        if (cfg->single_action_planner) s->p_mask[n++] = 1.0f; /* one global NO-OP (base_agent.py:452-453) */
         for (bi = 0; bi < cfg->n_brackets; bi++) {
-            s->p_mask[n++] = 1.0f;
+            if (!cfg->single_action_planner) s->p_mask[n++] = 1.0f;
             for (r = 0; r < R; r++)
                 s->p_mask[n++] = (s->tax_pos != 1) ? 0.0f : (float)s->planner_mask_rates[r];
         }
@@ -1131,7 +1153,10 @@ static void decode_actions(const orc_batch *b, env_t *s, const int32_t *act_a, c
         }
     }
     for (i = 0; i < ORC_MAX_BRACKETS; i++) s->act_tax[i] = 0;
-    if (act_p) for (i = 0; i < b->dims.n_act_p; i++) s->act_tax[i] = act_p[i];
+    if (act_p && b->cfg.single_action_planner && b->dims.n_act_p == 1) {
+        int g = act_p[0], R = b->cfg.n_disc_rates; /* single_action_map: bracket (g-1) / R, sub-action (g-1) % R + 1 */
+        if (g >= 1 && g <= b->cfg.n_brackets * R) s->act_tax[(g - 1) / R] = (g - 1) % R + 1;
+    } else if (act_p) for (i = 0; i < b->dims.n_act_p; i++) s->act_tax[i] = act_p[i];
 }
 
 static void step_env(const orc_batch *b, env_t *s, const int32_t *act_a, const int32_t *act_p) {

@@ -36,6 +36,8 @@ PLAN = [
     ("multi_zone", 1001, 120, 20),
     ("quadrant", 1001, 120, 20),
     ("split_layout", 1001, 120, 20),
+    ("tax_single_planner", 1001, 150, 10),
+    ("uniform_halfwidth", 1001, 150, 25),
     # multi-episode traces (env.reset() between episodes, the global numpy stream continues): device-side reset
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),
@@ -107,7 +109,7 @@ def generate(cfg_name, seed, steps, full_every):
     for k, v in init.items():
         out["init_" + k] = np.asarray(v)
     out["act_a"] = np.stack(acts_a).astype(np.int8)
-    out["act_p"] = np.stack(acts_p).astype(np.int8)
+    out["act_p"] = np.stack(acts_p).astype(np.int16)   # single-action planner indices exceed int8
     for k, v in rec.items():
         if v:
             out["step_" + k] = np.stack([np.asarray(x) for x in v])

@@ -25,7 +25,7 @@ def actions_dict(env, a_row, p_row):
         ag = env.get_agent(i)
         acts[str(i)] = [int(v) for v in a_row[i]] if ag.multi_action_mode else int(a_row[i][0])
     if len(p_row):
-        acts["p"] = [int(v) for v in p_row]
+        acts["p"] = [int(v) for v in p_row] if env.get_agent("p").multi_action_mode else int(p_row[0])
     return acts
 
 

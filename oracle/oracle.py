@@ -37,6 +37,7 @@ class OrcConfig(C.Structure):
         ("fixed_rates", C.c_double * MAX_BRACKETS),
         ("tax_annealing", C.c_int32), ("annealing_warmup", C.c_double),
         ("annealing_slope", C.c_double), ("rate_max", C.c_double),
+        ("single_action_planner", C.c_int32), ("regen_halfwidth", C.c_int32 * 2),
     ]
 
 
@@ -107,6 +108,8 @@ def config_from_spec(spec):
         cfg.disc_rates[i] = v
     for i, v in enumerate(spec["fixed_rates"]):
         cfg.fixed_rates[i] = v
+    cfg.single_action_planner = int(spec.get("single_action_planner", 0))
+    cfg.regen_halfwidth[0], cfg.regen_halfwidth[1] = spec.get("regen_halfwidth", [0, 0])
     return cfg
 
 

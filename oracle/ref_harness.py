@@ -86,7 +86,12 @@ def spec_from_reference_env(env):
         tax_annealing=0, annealing_warmup=0.0, annealing_slope=0.0, rate_max=1.0,
     )
     for r in ("Stone", "Wood"):
-        assert env.layout_specs[r]["regen_halfwidth"] == 0 and env.layout_specs[r]["max_health"] == 1
+        assert env.layout_specs[r]["max_health"] == 1
+    hw = [int(env.layout_specs[r]["regen_halfwidth"]) for r in ("Stone", "Wood")]
+    if any(hw):
+        spec["regen_halfwidth"] = hw
+    if not env.multi_action_mode_planner:
+        spec["single_action_planner"] = 1
     assert not env._full_observability
     for c in env._components:
         if c.name == "Build":
@@ -236,7 +241,10 @@ def sample_actions(env, obs, rng):
     pl = env.get_agent("p")
     pmask = np.asarray(obs["p"]["action_mask"])
     p_row = []
-    if len(pmask) > 1:
+    if len(pmask) > 1 and not pl.multi_action_mode:   # one index over [NO-OP] ++ every bracket's rates
+        p_row = [int(rng.choice(len(pmask), p=pmask / pmask.sum()))]
+        actions["p"] = p_row[0]
+    elif len(pmask) > 1:
         dims = [pl.action_dim[k] for k in pl._action_names]
         off = 0
         for d in dims:
