@@ -18,6 +18,8 @@ def segments(spec, who):
     if who == "p":
         planner_acts = ("PeriodicBracketTax" in spec["components"] and spec["tax_model"] == 0
                         and not spec["disable_taxes"])
+        if planner_acts and spec.get("single_action_planner", 0):   # one index over [NO-OP] ++ every bracket's rates
+            return [1 + spec["n_disc_rates"] * spec["n_brackets"]]
         return [1 + spec["n_disc_rates"]] * spec["n_brackets"] if planner_acts else []
     sizes = []
     for c in spec["components"]:

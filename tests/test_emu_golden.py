@@ -14,3 +14,29 @@ def test_emulated_device_code_matches_reference_golden_trace(path):
         return GoldenStepperAdapter(EmuStepper(spec, 1), init)
 
     assert gu.replay(path, make) >= 50
+
+
+@pytest.mark.parametrize("cfg,E,steps", [
+    ("tax_single_planner", 4, 60), ("uniform_halfwidth", 4, 60), ("quadrant", 3, 40), ("multi_zone", 3, 40),
+    ("split_layout", 2, 40),
+])
+def test_emulated_batch_matches_oracle(cfg, E, steps):
+    """Distinct seeds per replica through the public API (host reset -> upload -> step) against the C oracle: the
+    CPU twin of tests/test_gpu_parity.py::test_cuda_batch_matches_oracle for the options added after round-1 (e)."""
+    import numpy as np
+
+    from ai_economist_b200 import foundation
+    from oracle.oracle import OracleBatch
+    from tests import batch_utils as bu
+    from tests.emu.emu_stepper import emu_factory
+
+    name, kw = bu.product_kwargs(cfg)
+    kw.pop("seed", None)
+    env = foundation.make_env_instance(name, n_envs=E, stepper_factory=emu_factory, auto_reset=False, seed=4000, **kw)
+    host = env.host_reset_arrays()
+    env.stepper.load_state(host)
+    env._loaded = True
+    orc = OracleBatch(env.spec, E)
+    for e in range(E):
+        orc.load_env(e, {k: v[e] for k, v in host.items()})
+    bu.run_pair(env, orc, steps, np.random.RandomState(9), check_every=20)

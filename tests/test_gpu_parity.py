@@ -22,6 +22,7 @@ def _cuda_stepper(spec, n_envs, auto_reset=False):
 def _make_env(cfg_name, n_envs, seed, **extra):
     from ai_economist_b200 import foundation
     name, kw = bu.product_kwargs(cfg_name)
+    kw.pop("seed", None)   # split_layout carries a constructor seed for its golden trace
     kw.update(extra)
     return foundation.make_env_instance(name, n_envs=n_envs, device="cuda:0", seed=seed, **kw)
 
@@ -53,6 +54,11 @@ def test_cuda_matches_reference_golden_trace(path):
     ("c5_small", 8, 150, 25),           # 32 agents, multi-action, K=50 book, sorted-gini branch
     ("c5_full", 6, 40, 20),             # BASELINE config 5 shape: 64 agents, 64x64, K=50 (2 agents per lane)
     ("wealth_redistribution", 32, 200, 25),  # WealthRedistribution as the last component, 9 agents (numpy pairwise sum)
+    ("tax_single_planner", 32, 150, 25),  # single-action planner: one index over [NO-OP] ++ B x R rates
+    ("uniform_halfwidth", 32, 150, 25),   # regen_halfwidth 1 / 2: window-count respawn thresholds
+    ("quadrant", 16, 120, 30),            # uniform family with water lines, lognormal skills
+    ("multi_zone", 16, 120, 30),
+    ("split_layout", 4, 120, 30),         # (the 100000-row skill table per replica keeps this one small)
 ])
 def test_cuda_batch_matches_oracle(cfg, E, steps, every):
     env = _make_env(cfg, E, seed=4000, auto_reset=False)

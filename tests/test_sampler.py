@@ -40,7 +40,7 @@ def _check(env, rounds=6):
     assert len(seen) > 10
 
 
-@pytest.mark.parametrize("cfg", ["c1_tutorial", "tax_us_federal", "c3_reset"])
+@pytest.mark.parametrize("cfg", ["c1_tutorial", "tax_us_federal", "c3_reset", "tax_single_planner"])
 def test_emulated_sampler_draws_only_unmasked_actions(cfg):
     from tests.emu.emu_stepper import emu_factory
     kw = dict(CONFIGS[cfg])
@@ -52,7 +52,7 @@ def test_emulated_sampler_draws_only_unmasked_actions(cfg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["c1_tutorial", "tax_us_federal", "c3_reset"])
+@pytest.mark.parametrize("cfg", ["c1_tutorial", "tax_us_federal", "c3_reset", "tax_single_planner"])
 def test_cuda_sampler_draws_only_unmasked_actions(cfg):
     kw = dict(CONFIGS[cfg])
     name = kw.pop("scenario_name")
