@@ -80,8 +80,7 @@ class BatchedFoundationEnv:
         if not (flatten_observations and flatten_masks):
             raise NotImplementedError("the batched stepper always emits flattened observations and masks; "
                                       "use reference_view() for the nested layout")
-        if collate_agent_step_and_reset_data:
-            raise NotImplementedError("collated ('a') layout: index the [E, A, ...] tensors in obs_tensors instead")
+        self.collate_agent_step_and_reset_data = bool(collate_agent_step_and_reset_data)
         self._allow_observation_scaling = bool(allow_observation_scaling)
         self.n_envs = int(n_envs)
         assert self.n_envs >= 1
@@ -408,11 +407,23 @@ class BatchedFoundationEnv:
         for i in range(A):
             p["p%d" % i] = b["obs_planner_agents"][:, i]
         obs["p"] = p
-        self.obs = obs
         self.rew = {str(i): b["reward"][:, i] for i in range(A)}
         self.rew["p"] = b["reward"][:, A]
         self.done = {"__all__": b["done"]}
         self.info = {k: {} for k in obs}
+        if self.collate_agent_step_and_reset_data:
+            # base_env.py:816-850: the agents' entries are stacked under "a" with the agent axis LAST
+            # ([E, ..., A]); these are strided views of the same [E, A, ...] device tensors, no copy
+            def last(t):
+                return t.movedim(1, -1) if hasattr(t, "movedim") else np.moveaxis(t, 1, -1)
+            time_a = b["obs_time"].reshape(self.n_envs, 1)
+            time_a = time_a.expand(self.n_envs, A) if hasattr(time_a, "expand") else np.broadcast_to(time_a, (self.n_envs, A))
+            obs = {"a": {"world-map": last(b["obs_agent_map"]), "world-idx_map": last(b["obs_agent_idx"]),
+                         "flat": last(b["obs_agent_flat"]), "time": time_a, "action_mask": last(b["mask_agent"])},
+                   "p": obs["p"]}
+            self.rew = {"a": b["reward"][:, :A], "p": b["reward"][:, A]}
+            self.info = {"a": {str(i): {} for i in range(A)}, "p": {}}
+        self.obs = obs
 
     def reference_view(self, e=0):
         """(obs, rew, done) of env e as nested numpy dicts in the reference's layout."""

@@ -111,3 +111,24 @@ def test_constructor_time_draws_are_per_replica(name):
     single = make_env(meta, n_envs=1).host_reset_arrays()
     for k in batch:
         assert np.array_equal(np.asarray(batch[k][2]), np.asarray(single[k][0])), k
+
+
+def test_collated_layout_stacks_agents_on_the_last_axis():
+    """collate_agent_step_and_reset_data=True (base_env.py:816-850): obs["a"][key] = per-agent entries stacked on
+    the last axis, rew["a"] = per-agent rewards, info["a"] = {idx: {}}; views of the same buffers, no copy."""
+    z, meta, init = gu.load_fixture([p for p in gu.golden_files() if "c1_tutorial_seed1002" in p][0])
+    plain = make_env(meta, n_envs=2)
+    coll = make_env(meta, n_envs=2, collate_agent_step_and_reset_data=True)
+    for env in (plain, coll):
+        env.seed(5)
+        env.reset()
+        env.step(None)
+    A = plain.n_agents
+    assert set(coll.obs.keys()) == {"a", "p"} and set(coll.rew.keys()) == {"a", "p"}
+    for key in ["world-map", "world-idx_map", "flat", "action_mask"]:
+        ref = np.stack([np.asarray(plain.obs[str(i)][key]) for i in range(A)], axis=-1)
+        assert np.array_equal(np.asarray(coll.obs["a"][key]), ref), key
+    assert np.asarray(coll.obs["a"]["time"]).shape == (2, A)
+    assert np.array_equal(np.asarray(coll.rew["a"]), np.stack([np.asarray(plain.rew[str(i)]) for i in range(A)], -1))
+    assert set(coll.info["a"].keys()) == {str(i) for i in range(A)}
+    assert np.shares_memory(np.asarray(coll.obs["a"]["flat"]), coll.stepper.buf["obs_agent_flat"])
