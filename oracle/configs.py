@@ -182,3 +182,70 @@ CONFIGS = {
         starting_agent_coin=10, starting_wood_coverage=0.12, starting_stone_coverage=0.12,
         wood_regen_halfwidth=2, wood_regen_weight=0.6, stone_regen_halfwidth=1, stone_regen_weight=0.4),
 }
+
+# Edge-of-range configurations (tests/test_edge_configs.py): smallest / largest sizes and degenerate options.  They are
+# checked live against the imported reference in the build container, and oracle <-> device code everywhere.
+_LFF = "layout_from_file/simple_wood_and_stone"
+_BASE = dict(multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True,
+             flatten_masks=True)
+EDGE_CONFIGS = {
+    # two agents (the minimum), view radius 0 (1x1 window), K = 1 order, one price level above zero
+    "two_agents_w0": dict(
+        scenario_name=_LFF, components=[("Build", {}), ("ContinuousDoubleAuction", dict(max_num_orders=1, max_bid_ask=1,
+                                                                                       order_duration=1)),
+                                        ("Gather", {})],
+        env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=2, world_size=[15, 15], episode_length=40,
+        mobile_agent_observation_range=0, starting_agent_coin=3, **_BASE),
+    # window wider than the world (radius 9 on 15x15), planner without spatial info, no auction component
+    "wide_window_no_cda": dict(
+        scenario_name=_LFF, components=[("Gather", dict(skill_dist="pareto")), ("Build", dict(skill_dist="lognormal"))],
+        env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=3, world_size=[15, 15], episode_length=40,
+        mobile_agent_observation_range=9, planner_gets_spatial_info=False, **_BASE),
+    # gather only; inventory scaling off; auto energy warm-up; full regeneration probability
+    "gather_only_unscaled": dict(
+        scenario_name=_LFF, components=[("Gather", dict(move_labor=0.5, collect_labor=2.0))],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", n_agents=7, world_size=[25, 25], episode_length=40,
+        allow_observation_scaling=False, resource_regen_prob=1.0, energy_warmup_constant=3,
+        energy_warmup_method="auto", **_BASE),
+    # auction + gather (the reference cannot build its observations without a Gather or Build component),
+    # multi-action agents, long-lived orders, 32 price levels (the ABI maximum)
+    "cda_wide_prices": dict(
+        scenario_name=_LFF, components=[("ContinuousDoubleAuction", dict(max_num_orders=4, max_bid_ask=31,
+                                                                         order_duration=200, order_labor=0.0)),
+                                        ("Gather", {})],
+        env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=4, world_size=[15, 15], episode_length=40,
+        starting_agent_coin=50, multi_action_mode_agents=True, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
+    # tax every step (period 1), taxes disabled, the other two social welfare functions
+    "tax_period_one": dict(
+        scenario_name=_LFF, components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=2)),
+                                        ("Gather", {}),
+                                        ("PeriodicBracketTax", dict(period=1, bracket_spacing="linear", n_brackets=3,
+                                                                    top_bracket_cutoff=30, rate_disc=0.25,
+                                                                    tax_model="model_wrapper"))],
+        env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=3, world_size=[15, 15], episode_length=40,
+        starting_agent_coin=20, planner_reward_type="inv_income_weighted_utility", **_BASE),
+    "tax_disabled_log_brackets": dict(
+        scenario_name=_LFF, components=[("Gather", {}), ("Build", {}),
+                                        ("PeriodicBracketTax", dict(period=7, bracket_spacing="log", n_brackets=5,
+                                                                    top_bracket_cutoff=100, disable_taxes=True))],
+        env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=3, world_size=[15, 15], episode_length=40,
+        starting_agent_coin=20, planner_reward_type="inv_income_weighted_coin_endowments",
+        mixing_weight_gini_vs_coin=0.5, isoelastic_eta=0.0, **_BASE),
+    # eta just below 1 (the reference's eta == 1 branch raises, rewards.py:38), fixed bracket rates, tax every 2nd step
+    "eta_high_fixed_rates": dict(
+        scenario_name=_LFF, components=[("Build", {}), ("ContinuousDoubleAuction", dict(max_num_orders=2)),
+                                        ("Gather", {}),
+                                        ("PeriodicBracketTax", dict(period=2, bracket_spacing="us-federal",
+                                                                    tax_model="fixed-bracket-rates",
+                                                                    fixed_bracket_rates=[0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6]))],
+        env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=4, world_size=[15, 15], episode_length=40,
+        starting_agent_coin=15, isoelastic_eta=0.99, **_BASE),
+    # non-square world (uniform family), 33 agents: one more than a warp, both gini branches straddled
+    "nonsquare_33_agents": dict(
+        scenario_name="uniform/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=7)), ("Gather", dict(skill_dist="pareto"))],
+        n_agents=33, world_size=[12, 37], episode_length=30, starting_agent_coin=30,
+        starting_wood_coverage=0.10, starting_stone_coverage=0.10, **_BASE),
+}

@@ -13,6 +13,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the read-only reference tree at /root/reference")
 
 
+# GPU cases added after the last B200 session of round 1 (the round's GPU budget was spent): they are parity-green on
+# the 1-lane emulation of the same device source and against the oracle / reference, but have not run on a B200 yet.
+# They run LAST, so that with `-x` a surprise there cannot mask the cases that are known to pass on the hardware.
+NOT_YET_RUN_ON_B200 = ("multi_zone", "quadrant", "split_layout", "tax_single_planner", "uniform_halfwidth",
+                       "edge_config")
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
 
@@ -20,3 +27,7 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+    late = [i for i in items if "gpu" in i.keywords and any(n in i.nodeid for n in NOT_YET_RUN_ON_B200)]
+    if late:
+        ids = {id(i) for i in late}
+        items[:] = [i for i in items if id(i) not in ids] + late
