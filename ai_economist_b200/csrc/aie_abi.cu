@@ -114,7 +114,7 @@ __device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b,
 
 // ---------------------------------------------------------------------------------------------------------
 // MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
-template <int MINB, bool BIG>
+template <int MINB, bool BIG, bool EXT = false>
 __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
                                                               const int emit_obs) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -136,11 +136,11 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     // the actions are decoded into the scratch area while the bulk load of the record is in flight
     const int32_t *act_a = b.act_a + (size_t)env * c.A * c.n_act_a;
     const int32_t *act_p = (b.act_p && c.n_act_p) ? b.act_p + (size_t)env * c.n_act_p : nullptr;
-    decode_actions(c, step_scratch_view(scratch, c), act_a, act_p, lane, tab);
+    decode_actions<EXT>(c, step_scratch_view(scratch, c), act_a, act_p, lane, tab);
     mbar_wait(bar, 0);
 
     int32_t *events = (b.events && env < b.event_envs) ? b.events + (size_t)env * 8 * (b.event_cap + 1) : nullptr;
-    step_env<BIG>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane, true, events,
+    step_env<BIG, EXT>(c, rec, grec, scratch, act_a, act_p, b.rew + (size_t)env * (c.A + 1), b.done + env, lane, true, events,
                   b.event_cap);
 
     // auto-reset (WarpDrive save_copy_and_apply_at_reset semantics): restore everything but the RNG stream
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
         }
     }
     __syncwarp();
-    if (emit_obs) observe_env(c, rec, grec, rec + c.off_mt, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
+    if (emit_obs) observe_env<EXT>(c, rec, grec, rec + c.off_mt, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
     if (lane == 0) bulk_wait_read();
 }
 
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_cons
 
 // Stand-alone observation pass (after a reset upload, or when the caller steps dynamics separately): one warp per
 // env, bulk-loads only the observable prefix of the record.
+template <bool EXT>
 __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b, int lo, int n) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,12 +256,13 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     }
     __syncwarp();
     mbar_wait(bar, 0);
-    observe_env(c, rec, grec, rec + c.off_mt, rec + c.resident_bytes + c.step_scratch_bytes,
-                obs_out_for(c, b, env), tab, lane);
+    observe_env<EXT>(c, rec, grec, rec + c.off_mt, rec + c.resident_bytes + c.step_scratch_bytes,
+                     obs_out_for(c, b, env), tab, lane);
 }
 
 // per_unit == 0: one warp per env (fastest for few agents: c2 15.2 us vs 17.5 us);  per_unit == 1: one warp per
 // (env, agent | planner bracket) - many agents x subspaces make the per-env chain long (c5: 64 agents x 6 subspaces).
+template <bool EXT>
 __global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__ DevCfg c, const DevBufs b, uint64_t seed,
                                                          int per_unit) {
     const long long wid = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -272,8 +274,8 @@ __global__ void __launch_bounds__(256) aie_sample_kernel(const __grid_constant__
     int32_t *aa = const_cast<int32_t *>(b.act_a) + (size_t)env * c.A * c.n_act_a;
     int32_t *ap = c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)env * c.n_act_p : nullptr;
     const uint64_t key = mix64(seed ^ mix64((uint64_t)env));
-    if (per_unit) sample_actions_unit(c, am, pm, aa, ap, key, u, lane);
-    else sample_actions_env(c, am, pm, aa, ap, key, lane);
+    if (per_unit) sample_actions_unit<EXT>(c, am, pm, aa, ap, key, u, lane);
+    else sample_actions_env<EXT>(c, am, pm, aa, ap, key, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -333,13 +335,18 @@ int init(aie_env *env) {
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     {
         AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(Tables)), "cudaMalloc tables");
         AIE_CUDA(cudaMemcpy(env->be.tab_dev, env->tables.w, sizeof(Tables), cudaMemcpyHostToDevice), "upload tables");
         env->bufs.tab = env->be.tab_dev;
     }
     AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
     return AIE_OK;
 }
 void destroy(aie_env *env) { if (env->be.tab_dev) cudaFree(env->be.tab_dev); }
@@ -376,7 +383,13 @@ int launch_step(aie_env *env, int emit_obs, void *stream) {
     const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = env->be.step_smem;
-    if (env->cfg.split) {  // large envs: order slots / price history in global memory, latency-tolerant scans
+    if (env->cfg.ext) {  // rarely used options compiled in (single-action planner, regen halfwidth); 48-register variant omitted
+        if (env->cfg.split) {
+            if (env->be.step_minb >= 4) aie_step_kernel<4, true, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+            else aie_step_kernel<3, true, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        } else if (env->be.step_minb >= 4) aie_step_kernel<4, false, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        else aie_step_kernel<3, false, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    } else if (env->cfg.split) {  // large envs: order slots / price history in global memory, latency-tolerant scans
         if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
         else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
     } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
@@ -388,7 +401,8 @@ int launch_step(aie_env *env, int emit_obs, void *stream) {
 }
 int launch_observe(aie_env *env, int lo, int n, void *stream) {
     const int wpb = env->be.step_wpb;
-    aie_observe_kernel<<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
+    if (env->cfg.ext) aie_observe_kernel<true><<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
+    else aie_observe_kernel<false><<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
     AIE_CUDA(cudaGetLastError(), "aie_observe_kernel launch");
     env->launches++;
     return AIE_OK;
@@ -400,8 +414,9 @@ int launch_sample(aie_env *env, uint64_t seed, void *stream) {
     const int units = env->cfg.A + (env->cfg.planner_acts ? env->cfg.B : 0);
     const int per_unit = (env->cfg.A * (env->cfg.multi_action ? env->cfg.n_sub : 1) >= 64) ? 1 : 0;
     const long long warps = (long long)env->n_envs * (per_unit ? units : 1);
-    aie_sample_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        env->cfg, env->bufs, host_mix64(seed) ^ host_mix64(++env->sample_calls), per_unit);
+    const uint64_t sd = host_mix64(seed) ^ host_mix64(++env->sample_calls);
+    if (env->cfg.ext) aie_sample_kernel<true><<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs, sd, per_unit);
+    else aie_sample_kernel<false><<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs, sd, per_unit);
     AIE_CUDA(cudaGetLastError(), "aie_sample_kernel launch");
     env->launches++;
     return AIE_OK;

@@ -257,6 +257,10 @@ AIE_DEV void rng_permutation(Rng &r, uint8_t *perm, int A) {
 // ------------------------------------------------------------------------------------------------
 // Actions  (BaseAgent.parse_actions, base/base_agent.py:407-438)
 // ------------------------------------------------------------------------------------------------
+// EXT (here and below): compile the rarely used options in - single-action planner, regen_halfwidth > 0.  The kernels
+// are instantiated both ways and the host picks by config (DevCfg::ext), so the default configurations run exactly
+// the instruction stream that was profiled without those options.
+template <bool EXT = false>
 AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t *act_a, const int32_t *act_p,
                             int lane, const uint16_t *tab = nullptr) {
     for (int a = lane; a < c.A; a += NL) {
@@ -291,7 +295,7 @@ AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t
     }
     for (int b = lane; b < 16; b += NL) {
         int v;
-        if (c.planner_single) {  // single_action_map (base_agent.py:109-114): bracket (g-1) / R, sub-action (g-1) % R + 1
+        if (EXT && c.planner_single) {  // single_action_map (base_agent.py:109-114): bracket (g-1) / R, sub-action (g-1) % R + 1
             const int g = act_p ? act_p[0] - 1 : -1;
             v = (g >= 0 && g < c.B * c.R && g / c.R == b) ? g % c.R + 1 : 0;
         } else {
@@ -722,6 +726,7 @@ AIE_DEV_NOINLINE uint64_t regen_window_thresh(const DevCfg &c, const Env &e, int
     return c.regen_tab[cc][n];
 }
 
+template <bool EXT>
 AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
     const int HW = c.HW, lane = r.lane;
     const uint8_t res_bit = (uint8_t)(1u << cc), src_bit = (uint8_t)(4u << cc);
@@ -741,7 +746,7 @@ AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
                 uint8_t cb = e.cell[k];
                 if ((cb & src_bit) && !(cb & res_bit)) {
                     uint64_t v = ((uint64_t)(pend_a >> 5) << 26) | (uint64_t)(mt_temper(e.mt[base + w]) >> 6);
-                    if (v < (c.regen_hw[cc] ? regen_window_thresh(c, e, cc, k) : thresh)) e.cell[k] = cb | res_bit;
+                    if (v < ((EXT && c.regen_hw[cc]) ? regen_window_thresh(c, e, cc, k) : thresh)) e.cell[k] = cb | res_bit;
                 }
             }
         }
@@ -763,7 +768,7 @@ AIE_DEV void regen_resource(const DevCfg &c, Env &e, int cc, Rng &r) {
                 if (k < k_lo || k >= k_hi) continue;
                 uint64_t v = ((uint64_t)(mt_temper(e.mt[base + 2 * k]) >> 5) << 26) |
                              (uint64_t)(mt_temper(e.mt[base + 2 * k + 1]) >> 6);
-                if (v < (c.regen_hw[cc] ? regen_window_thresh(c, e, cc, k) : thresh)) e.cell[k] = (uint8_t)(e.cell[k] | res_bit);
+                if (v < ((EXT && c.regen_hw[cc]) ? regen_window_thresh(c, e, cc, k) : thresh)) e.cell[k] = (uint8_t)(e.cell[k] | res_bit);
             }
         }
         if (w_end & 1) pend_a = mt_temper(e.mt[base + w_end - 1]);
@@ -891,7 +896,7 @@ AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, doubl
 // ------------------------------------------------------------------------------------------------
 // One env.step() (base/base_env.py:929-1032) without the observation pass.
 // ------------------------------------------------------------------------------------------------
-template <bool BIG>
+template <bool BIG, bool EXT = false>
 AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, const int32_t *act_a,
                       const int32_t *act_p, double *rew_out, int32_t *done_out, int lane, bool decoded = false,
                       int32_t *events = nullptr, int event_cap = 0, const uint16_t *tab = nullptr) {
@@ -901,7 +906,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
         e.ev = events; e.ev_cap = event_cap;
         if (lane == 0) { events[0] = 0; events[1] = e.hdr[HDR_T] + 1; events[2] = 0; }
     }
-    if (!decoded) decode_actions(c, s, act_a, act_p, lane, tab);  // the CUDA kernel decodes while the record is in flight
+    if (!decoded) decode_actions<EXT>(c, s, act_a, act_p, lane, tab);  // the CUDA kernel decodes while the record is in flight
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
     const int t = e.hdr[HDR_T] + 1;
     wsync();
@@ -918,7 +923,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
 #if AIE_ON_DEVICE
 #pragma unroll 1
 #endif
-    for (int ri = 0; ri < 2; ri++) regen_resource(c, e, 1 - ri, r);  // Wood, then Stone (one inlined copy)
+    for (int ri = 0; ri < 2; ri++) regen_resource<EXT>(c, e, 1 - ri, r);  // Wood, then Stone (one inlined copy)
     compute_reward(c, e, s, rew_out, lane);
     if (lane == 0) {
         e.hdr[HDR_MT_POS] = r.pos;
@@ -1206,6 +1211,7 @@ AIE_DEV float flat_value(const float *shf, const float *agf, uint32_t entry) {
     return (AIE_FLAT_KIND(entry) == FK_AGENT ? agf : shf)[AIE_FLAT_PAYLOAD(entry)];
 }
 
+template <bool EXT = false>
 AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *mt_img, uint8_t *extra, const ObsOut &o,
                          const uint16_t *tab, int lane) {
     const Env e = env_view(rec, grec, c);
@@ -1391,7 +1397,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
                 bool open = rr == 0 || first_day;
                 if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.net_hist[2 * P];
                 // single-action planner: one leading NO-OP, then every bracket's R rates (base_agent.py:452-459)
-                const int at = c.planner_single ? (rr == 0 ? 0 : b * c.R + rr) : b * (1 + c.R) + rr;
+                const int at = (EXT && c.planner_single) ? (rr == 0 ? 0 : b * c.R + rr) : b * (1 + c.R) + rr;
                 o.p_mask()[at] = open ? 1.0f : 0.0f;
             }
     } else if (lane == 0) {
@@ -1455,6 +1461,7 @@ AIE_DEV int sample_segment_warp(const float *mask, int n, uint64_t key, int lane
 
 // One unit of an env's random policy: unit u < A = agent u (one draw per subspace), unit A + b = planner bracket b.
 // Units are independent, so the kernel gives each its own warp.
+template <bool EXT = false>
 AIE_DEV void sample_actions_unit(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
                                  int32_t *act_p, uint64_t key, int u, int lane) {
     if (u < c.A) {
@@ -1471,7 +1478,7 @@ AIE_DEV void sample_actions_unit(const DevCfg &c, const float *a_mask, const flo
                 off += c.sub_n[si] + 1;
             }
         }
-    } else if (c.planner_single) {
+    } else if (EXT && c.planner_single) {
         if (u == c.A) {
             const int v = sample_segment_warp(p_mask, c.Np, key + 0x10000, lane);
             if (lane == 0) act_p[0] = v;
@@ -1483,10 +1490,11 @@ AIE_DEV void sample_actions_unit(const DevCfg &c, const float *a_mask, const flo
     }
 }
 // One env: every agent (and planner bracket) draws one uniformly random unmasked action per subspace.
+template <bool EXT = false>
 AIE_DEV void sample_actions_env(const DevCfg &c, const float *a_mask, const float *p_mask, int32_t *act_a,
                                 int32_t *act_p, uint64_t key, int lane) {
     const int units = c.A + (c.planner_acts ? c.B : 0);
-    for (int u = 0; u < units; u++) sample_actions_unit(c, a_mask, p_mask, act_a, act_p, key, u, lane);
+    for (int u = 0; u < units; u++) sample_actions_unit<EXT>(c, a_mask, p_mask, act_a, act_p, key, u, lane);
 }
 
 }  // namespace aie

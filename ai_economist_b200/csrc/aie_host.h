@@ -141,6 +141,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     if (c.n_sub == 0) return bad("mobile agents need at least one action component");
     c.planner_acts = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_MODEL_WRAPPER && !c.disable_taxes) ? 1 : 0;
     c.planner_single = (c.planner_acts && u.single_action_planner) ? 1 : 0;
+    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1]) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;
     c.Np = c.planner_acts ? (c.planner_single ? 1 + c.B * c.R : c.B * (1 + c.R)) : 1;

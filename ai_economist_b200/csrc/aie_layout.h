@@ -121,6 +121,7 @@ struct DevCfg {
     uint32_t win_magic; int32_t win_dr32, win_dc32;  // window walk: lane / win, and the (row, col) step of 32 cells
     // single-action planner (multi_action_mode_planner=False): act_p is one index into [NO-OP] ++ B x R rates
     int32_t planner_single;
+    int32_t ext;  // planner_single or a regen halfwidth is set: the host launches the EXT instantiations of the kernels
     // regen_halfwidth > 0 (cold path): threshold by the number n of source cells in the d x d window of the cell,
     // regen_tab[c][n] = ceil(p_n * 2^53) with p_n the running float64 sum of n copies of regen_weight / d^2
     int32_t regen_hw[2];

@@ -74,12 +74,14 @@ int launch_step(aie_env *env, int emit_obs, void *) {
     for (int e = 0; e < env->n_envs; e++) {
         uint8_t *rec = b.state + (size_t)e * c.rec_bytes;
         int32_t *events = (b.events && e < b.event_envs) ? b.events + (size_t)e * 8 * (b.event_cap + 1) : nullptr;
-        if (c.split) step_env<true>(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
-                 (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
-                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0, false, events, b.event_cap, b.tab);
-        else step_env<false>(c, rec, rec, env->be.scratch.data(), b.act_a + (size_t)e * c.A * c.n_act_a,
-                 (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr,
-                 b.rew + (size_t)e * (c.A + 1), b.done + e, 0, false, events, b.event_cap, b.tab);
+        const int32_t *aa = b.act_a + (size_t)e * c.A * c.n_act_a;
+        const int32_t *ap = (b.act_p && c.n_act_p) ? b.act_p + (size_t)e * c.n_act_p : nullptr;
+        // same dispatch as the CUDA launcher: the EXT instantiations only for configs that set one of the rare options
+#define AIE_EMU_STEP(BIG, EXT) step_env<BIG, EXT>(c, rec, rec, env->be.scratch.data(), aa, ap, b.rew + (size_t)e * (c.A + 1), \
+                                                  b.done + e, 0, false, events, b.event_cap, b.tab)
+        if (c.ext) { if (c.split) AIE_EMU_STEP(true, true); else AIE_EMU_STEP(false, true); }
+        else { if (c.split) AIE_EMU_STEP(true, false); else AIE_EMU_STEP(false, false); }
+#undef AIE_EMU_STEP
         int32_t *hdr = (int32_t *)rec;
         if (c.auto_reset && hdr[HDR_T] >= c.T) {  // same sequence as aie_step_kernel
             int32_t completions = hdr[HDR_COMPLETIONS] + 1, warm = hdr[HDR_AUTO_WARMUP], mt_pos = hdr[HDR_MT_POS],
@@ -104,7 +106,8 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
     for (int env_i = lo; env_i < lo + n; env_i++) {
         size_t e = env_i;
         ObsOut o; o.b = &b; o.c = &c; o.env = e;
-        observe_env(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
+        if (c.ext) observe_env<true>(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
+        else observe_env<false>(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
     }
     env->launches++;
     return AIE_OK;
@@ -114,7 +117,13 @@ int launch_sample(aie_env *env, uint64_t seed, void *) {
     const DevBufs &b = env->bufs;
     const uint64_t s = host_mix64(seed) ^ host_mix64(++env->sample_calls);
     for (int e = 0; e < env->n_envs; e++)
-        sample_actions_env(c, b.a_mask + (size_t)e * c.A * c.Na, b.p_mask + (size_t)e * c.Np,
+        if (c.ext)
+            sample_actions_env<true>(c, b.a_mask + (size_t)e * c.A * c.Na, b.p_mask + (size_t)e * c.Np,
+                           const_cast<int32_t *>(b.act_a) + (size_t)e * c.A * c.n_act_a,
+                           c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)e * c.n_act_p : nullptr,
+                           mix64(s ^ mix64((uint64_t)e)), 0);
+        else
+            sample_actions_env<false>(c, b.a_mask + (size_t)e * c.A * c.Na, b.p_mask + (size_t)e * c.Np,
                            const_cast<int32_t *>(b.act_a) + (size_t)e * c.A * c.n_act_a,
                            c.n_act_p ? const_cast<int32_t *>(b.act_p) + (size_t)e * c.n_act_p : nullptr,
                            mix64(s ^ mix64((uint64_t)e)), 0);
