@@ -77,6 +77,10 @@ class AieStateDump(C.Structure):
                 [(n, C.c_void_p) for n in _DUMP_PTRS2])
 
 
+class AieFlatField(C.Structure):
+    _fields_ = [("key", C.c_char * 64), ("offset", C.c_int32), ("size", C.c_int32)]
+
+
 class AieField(C.Structure):
     _fields_ = [("offset", C.c_int32), ("elem_bytes", C.c_int32), ("is_float", C.c_int32),
                 ("is_signed", C.c_int32), ("ndim", C.c_int32), ("shape", C.c_int32 * 4)]
@@ -138,6 +142,8 @@ def load_library(path=None):
     L.aie_destroy.argtypes = [P]
     L.aie_get_dims.argtypes = [P, C.POINTER(AieDims)]
     L.aie_get_field.argtypes = [P, C.c_char_p, C.POINTER(AieField)]
+    L.aie_get_flat_layout.argtypes = [P, C.c_int32, C.POINTER(AieFlatField), C.c_int32]
+    L.aie_get_flat_layout.restype = C.c_int
     L.aie_bind_buffers.argtypes = [P, C.POINTER(AieBuffers)]
     L.aie_load_state.argtypes = [P, C.POINTER(AieHostState), C.c_int32, P]
     L.aie_step.argtypes = [P, P]
@@ -170,7 +176,7 @@ def load_library(path=None):
     return L
 
 
-EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers",
+EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_get_flat_layout", "aie_bind_buffers",
                     "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions",
                     "aie_step_host", "aie_read_state", "aie_read_episode_final", "aie_launch_count", "aie_last_error", "aie_abi_version",
                     "aie_covid_create", "aie_covid_destroy", "aie_covid_bind_buffers", "aie_covid_reset", "aie_covid_step",

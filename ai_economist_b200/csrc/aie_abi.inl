@@ -25,6 +25,7 @@ struct aie_env {
     int64_t launches;
     uint64_t sample_calls;
     aie::be::State be;
+    std::vector<aie_flat_field> flat_layout[3];
 };
 
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
@@ -39,7 +40,7 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     aie_env *env = new (std::nothrow) aie_env();
     if (!env) return fail(AIE_ENOMEM, "out of host memory");
     std::string err;
-    int rc = aie::build_devcfg(*cfg, n_envs, env->cfg, env->tables, err);
+    int rc = aie::build_devcfg(*cfg, n_envs, env->cfg, env->tables, err, env->flat_layout);
     if (rc != AIE_OK) { delete env; return fail(rc, "aie_create: " + err); }
     env->ucfg = *cfg; env->n_envs = n_envs; env->device = device;
     memset(&env->bufs, 0, sizeof(env->bufs));
@@ -67,6 +68,13 @@ int aie_get_field(const aie_env *env, const char *name, aie_field *out) {
     if (!env || !name || !out) return fail(AIE_EINVAL, "null argument");
     if (aie::lookup_field(env->cfg, name, out) != AIE_OK) return fail(AIE_EINVAL, std::string("unknown state field ") + name);
     return AIE_OK;
+}
+
+int aie_get_flat_layout(const aie_env *env, int32_t which, aie_flat_field *out, int32_t cap) {
+    if (!env || which < 0 || which > 2 || (cap > 0 && !out)) return fail(AIE_EINVAL, "aie_get_flat_layout: bad argument");
+    const std::vector<aie_flat_field> &v = env->flat_layout[which];
+    for (int i = 0; i < (int)v.size() && i < cap; i++) out[i] = v[i];
+    return (int)v.size();
 }
 
 int aie_bind_buffers(aie_env *env, const aie_buffers *b) {

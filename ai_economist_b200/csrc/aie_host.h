@@ -27,19 +27,28 @@ struct FlatKey { std::string key; int kind, payload, n; };  // payload of elemen
 
 // Mirrors BaseEnvironment._build_packager / _package (base_env.py:562-612): every scalar / 1-D field is
 // concatenated in sorted key order.  Keys are the reference's: "<Component>-<obs>" / "world-<obs>" / "time".
-inline int build_prog(std::vector<FlatKey> keys, uint16_t *prog, int cap) {
+inline int build_prog(std::vector<FlatKey> keys, uint16_t *prog, int cap, std::vector<aie_flat_field> *layout = nullptr) {
     std::sort(keys.begin(), keys.end(), [](const FlatKey &a, const FlatKey &b) { return a.key < b.key; });
     int n = 0;
-    for (const FlatKey &k : keys)
+    for (const FlatKey &k : keys) {
+        if (layout) {  // where this field sits in the flat vector (aie_get_flat_layout)
+            aie_flat_field f;
+            memset(&f, 0, sizeof(f));
+            snprintf(f.key, sizeof(f.key), "%s", k.key.c_str());
+            f.offset = n; f.size = k.n;
+            layout->push_back(f);
+        }
         for (int i = 0; i < k.n; i++) {
             if (n >= cap) return -1;
             prog[n++] = AIE_FLAT_ENTRY(k.kind, k.payload + i);
         }
+    }
     return n;
 }
 
 // Returns 0 or AIE_EINVAL with a message in err.
-inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, std::string &err) {
+inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, std::string &err,
+                        std::vector<aie_flat_field> *layouts = nullptr /* [3]: agent flat, planner flat, p<i> */) {
     memset(&c, 0, sizeof(c));
     memset(&tb, 0, sizeof(tb));
     auto bad = [&](const char *m) { err = m; return AIE_EINVAL; };
@@ -208,9 +217,9 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             kpa.push_back(K(s + "last_income", FK_AGENT, AS_TAX_LAST_INCOME, 1)); kpa.push_back(K(s + "last_marginal_rate", FK_AGENT, AS_TAX_LAST_MARG, 1));
             kpa.push_back(K(s + "curr_marginal_rate", FK_AGENT, AS_TAX_MARG, 1));
         }
-        c.Fa = build_prog(ka, prog_a, MAX_FLAT);
-        c.Fp = build_prog(kp, prog_p, MAX_FLAT);
-        c.Fpa = build_prog(kpa, prog_pa, 16);
+        c.Fa = build_prog(ka, prog_a, MAX_FLAT, layouts ? &layouts[0] : nullptr);
+        c.Fp = build_prog(kp, prog_p, MAX_FLAT, layouts ? &layouts[1] : nullptr);
+        c.Fpa = build_prog(kpa, prog_pa, 16, layouts ? &layouts[2] : nullptr);
         if (c.Fa < 0 || c.Fp < 0 || c.Fpa < 0) return bad("flat observation too long");
     }
     {

@@ -77,9 +77,10 @@ class BatchedFoundationEnv:
         assert self._episode_length >= 1
         self.multi_action_mode_agents = bool(multi_action_mode_agents)
         self.multi_action_mode_planner = bool(multi_action_mode_planner)
-        if not (flatten_observations and flatten_masks):
-            raise NotImplementedError("the batched stepper always emits flattened observations and masks; "
-                                      "use reference_view() for the nested layout")
+        # flatten_observations / flatten_masks = False (base_env.py:260-270): the named fields are handed out as slices
+        # of the flat tensors (aie_get_flat_layout), the per-subspace masks as slices of the flat masks - no copy
+        self._flatten_observations = bool(flatten_observations)
+        self._flatten_masks = bool(flatten_masks)
         self.collate_agent_step_and_reset_data = bool(collate_agent_step_and_reset_data)
         self._allow_observation_scaling = bool(allow_observation_scaling)
         self.n_envs = int(n_envs)
@@ -392,20 +393,57 @@ class BatchedFoundationEnv:
         return self._stepper.buf["actions_agent"], self._stepper.buf["actions_planner"]
 
     # ------------------------------------------------------------------ outputs
+    @staticmethod
+    def _named_fields(flat, layout):
+        """{key: slice of the flat vector} (scalars lose the trailing axis), base_env.py:562-612 undone."""
+        return {k: (flat[..., off] if n == 1 else flat[..., off:off + n]) for k, off, n in layout if k != "time"}
+
+    def _mask_dict(self, agent, flat_mask):
+        """{subspace name: slice of the flat mask} (base_env.py:706-756 with flatten_masks=False)."""
+        out, off = {}, 0 if agent.multi_action_mode else 1
+        for name in agent._action_names:
+            k = int(agent.action_dim[name])
+            if agent.multi_action_mode:
+                out[name] = flat_mask[..., off + 1:off + k]   # the subspace's own NO-OP leads its slice
+            else:
+                out[name] = flat_mask[..., off:off + k]
+            off += k
+        # quirk kept: a PeriodicBracketTax with a fixed schedule falls back to BaseComponent.generate_masks, which
+        # hands every agent type an EMPTY mask for its 0 actions (base_component.py:303-317, redistribution.py:1100-1102)
+        tax = self._components_dict.get("PeriodicBracketTax")
+        if tax is not None and tax.tax_model != "model_wrapper" and not tax.disable_taxes:
+            out[tax.name] = flat_mask[..., 0:0]
+        return out
+
     def _build_views(self):
         b = self._stepper.buf
         A = self.n_agents
         self.obs_tensors = {k: b[k] for k in b if k.startswith("obs_") or k.startswith("mask_")}
+        flat_o, flat_m = self._flatten_observations, self._flatten_masks
+        if not flat_o:
+            st = self._stepper
+            lay_a, lay_p, lay_pa = st.flat_layout("agent"), st.flat_layout("planner"), st.flat_layout("planner_agent")
         obs = {}
         for i in range(A):
             obs[str(i)] = {"world-map": b["obs_agent_map"][:, i], "world-idx_map": b["obs_agent_idx"][:, i],
-                           "flat": b["obs_agent_flat"][:, i], "time": b["obs_time"],
-                           "action_mask": b["mask_agent"][:, i]}
-        p = {"flat": b["obs_planner_flat"], "time": b["obs_time"], "action_mask": b["mask_planner"]}
+                           "time": b["obs_time"]}
+            if flat_o:
+                obs[str(i)]["flat"] = b["obs_agent_flat"][:, i]
+            else:
+                obs[str(i)].update(self._named_fields(b["obs_agent_flat"][:, i], lay_a))
+            obs[str(i)]["action_mask"] = b["mask_agent"][:, i] if flat_m else \
+                self._mask_dict(self._agents[i], b["mask_agent"][:, i])
+        p = {"time": b["obs_time"]}
+        if flat_o:
+            p["flat"] = b["obs_planner_flat"]
+        else:
+            p.update(self._named_fields(b["obs_planner_flat"], lay_p))
+        p["action_mask"] = b["mask_planner"] if flat_m else self._mask_dict(self._planner, b["mask_planner"])
         if "obs_planner_map" in b:
             p["world-map"], p["world-idx_map"] = b["obs_planner_map"], b["obs_planner_idx"]
         for i in range(A):
-            p["p%d" % i] = b["obs_planner_agents"][:, i]
+            p["p%d" % i] = b["obs_planner_agents"][:, i] if flat_o else \
+                self._named_fields(b["obs_planner_agents"][:, i], lay_pa)
         obs["p"] = p
         self.rew = {str(i): b["reward"][:, i] for i in range(A)}
         self.rew["p"] = b["reward"][:, A]
@@ -418,6 +456,8 @@ class BatchedFoundationEnv:
                 return t.movedim(1, -1) if hasattr(t, "movedim") else np.moveaxis(t, 1, -1)
             time_a = b["obs_time"].reshape(self.n_envs, 1)
             time_a = time_a.expand(self.n_envs, A) if hasattr(time_a, "expand") else np.broadcast_to(time_a, (self.n_envs, A))
+            if not (flat_o and flat_m):
+                raise NotImplementedError("collate_agent_step_and_reset_data needs flattened observations and masks")
             obs = {"a": {"world-map": last(b["obs_agent_map"]), "world-idx_map": last(b["obs_agent_idx"]),
                          "flat": last(b["obs_agent_flat"]), "time": time_a, "action_mask": last(b["mask_agent"])},
                    "p": obs["p"]}

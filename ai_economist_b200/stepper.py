@@ -94,6 +94,17 @@ class BatchStepper:
         except Exception:
             pass
 
+    def flat_layout(self, which):
+        """[(key, offset, size)] of the fields concatenated into a flat vector (base_env.py:562-589);
+        which: "agent" | "planner" | "planner_agent"."""
+        idx = {"agent": 0, "planner": 1, "planner_agent": 2}[which]
+        n = self.lib.aie_get_flat_layout(self._h, idx, None, 0)
+        if n < 0:
+            self._check(n)
+        arr = (_abi.AieFlatField * max(1, n))()
+        self.lib.aie_get_flat_layout(self._h, idx, arr, n)
+        return [(arr[i].key.decode(), int(arr[i].offset), int(arr[i].size)) for i in range(n)]
+
     def load_state(self, host_state, env_lo=0):
         """host_state: dict of numpy arrays with a leading env axis (see aie_host_state in the header)."""
         n = int(np.asarray(host_state["loc"]).shape[0])

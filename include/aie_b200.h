@@ -253,6 +253,14 @@ int aie_get_dims(const aie_env *env, aie_dims *out);
  * "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions", "orders" */
 int aie_get_field(const aie_env *env, const char *name, aie_field *out);
 
+/* ABI 3.  The named fields behind a "flat" vector, in concatenation order, i.e. what BaseEnvironment._build_packager
+ * records (base_env.py:562-589: every scalar / 1-D observation, sorted by key "<Component>-<obs>" / "world-<obs>" /
+ * "time").  With it a caller rebuilds the flatten_observations=False dictionaries as slices of the flat tensors.
+ * which: 0 = each agent's "flat", 1 = the planner's "flat", 2 = the planner's per-agent "p<i>" vectors.
+ * Fills at most cap entries; returns the number of fields (or a negative AIE_E* code). */
+typedef struct aie_flat_field { char key[64]; int32_t offset, size; } aie_flat_field;
+int aie_get_flat_layout(const aie_env *env, int32_t which, aie_flat_field *out, int32_t cap);
+
 /* Replaces: CUDADataManager.push_data_to_device + placeholders (env_wrapper.py:297-332). */
 int aie_bind_buffers(aie_env *env, const aie_buffers *bufs);
 
