@@ -188,3 +188,95 @@ class MultiAgentDictEnv:
         self.env.step(self.env.action_buffers)
         obs, rew, done = self.env.reference_view(self.e)
         return obs, rew, done, {k: {} for k in obs}
+
+
+class ReferenceApiEnv:
+    """One replica behind the reference's exact single-env interface (base/base_env.py:852-1032), so that code written
+    against ai_economist.foundation - the tutorials' `sample_random_actions(env, obs)` / `play_random_episode(env)`
+    loops, tutorials/utils/plotting.py - runs unchanged:
+
+        env = foundation.make_env_instance(**env_config, reference_api=True)     # or AIE_REFERENCE_API=1
+        obs = env.reset()                              # nested dicts of numpy arrays / floats, keyed "0".."n-1", "p"
+        obs, rew, done, info = env.step({"0": 3, "1": [0, 2, ...], "p": [...]})
+
+    Observation layout follows flatten_observations / flatten_masks / collate_agent_step_and_reset_data like the
+    reference.  Everything else (get_agent, episode_length, world, metrics, dense logs, seed ...) is the wrapped
+    BatchedFoundationEnv's.  One device->host copy per step: an evaluation / debugging surface, not the training path.
+    One difference is inherent: the env draws from its OWN numpy-legacy stream, not from the process-global
+    np.random, so caller code that samples from np.random between steps no longer perturbs the env's draws.
+    """
+
+    def __init__(self, env_obj, e=0):
+        object.__setattr__(self, "_env", env_obj)
+        object.__setattr__(self, "_e", int(e))
+
+    def __getattr__(self, name):           # get_agent, n_agents, episode_length, world, metrics, dense logs, seed ...
+        return getattr(self._env, name)
+
+    # ---- output conversion -------------------------------------------------------------------------------
+    def _np(self, v):
+        st = self._env.stepper
+        return st.to_numpy(v) if not isinstance(v, np.ndarray) else v
+
+    def _one(self, v):
+        """The replica's slice of a batched value: arrays stay arrays, per-env scalars become Python floats."""
+        if isinstance(v, dict):
+            return {k: self._one(x) for k, x in v.items()}
+        a = np.asarray(self._np(v))[self._e]
+        return float(a) if a.ndim == 0 else np.array(a)
+
+    def _outputs(self):
+        env, e = self._env, self._e
+        if env._flatten_observations and env._flatten_masks and not env.collate_agent_step_and_reset_data:
+            obs, rew, done = env.reference_view(e)          # one readback through aie_read-style debug copies
+            return obs, rew, done
+        obs = {}
+        for idx, d in env.obs.items():
+            o = {}
+            for k, v in d.items():
+                if k == "time":
+                    t = np.asarray(self._np(v))[e]
+                    o[k] = np.array(t, np.float64).reshape(-1) if np.ndim(t) else [float(t)]
+                else:
+                    o[k] = self._one(v)
+            obs[idx] = o
+        rew = {k: (self._one(v) if k != "a" else [float(x) for x in np.asarray(self._np(v))[e]])
+               for k, v in env.rew.items()}
+        done = {"__all__": bool(int(np.asarray(self._np(env.done["__all__"]))[e]))}
+        return obs, rew, done
+
+    # ---- the Gym-style surface ---------------------------------------------------------------------------
+    def reset(self, seed_state=None, force_dense_logging=False):
+        self._env.reset(seed_state=seed_state, force_dense_logging=force_dense_logging)
+        return self._outputs()[0]
+
+    def step(self, actions=None, seed_state=None):
+        """actions: {agent idx (int or str): int | sequence of ints} (BaseAgent.parse_actions, base_agent.py:407-438);
+        missing agents take NO-OPs, like the reference."""
+        env, e = self._env, self._e
+        st = env.stepper
+        ba, bp = st.buf["actions_agent"], st.buf["actions_planner"]
+        ba[e] = 0
+        bp[e] = 0
+        for k, v in (actions or {}).items():
+            if isinstance(v, dict):   # {subspace name: index} form of single-action agents (base_agent.py:419-427)
+                ag = env.get_agent(k)
+                assert len(v) <= 1
+                g, lo = 0, 1
+                for name in ag._action_names:
+                    if name in v and int(v[name]) > 0:
+                        g = lo + int(v[name]) - 1
+                    lo += int(ag.action_dim[name])
+                v = g
+            row = np.atleast_1d(np.asarray(v)).astype(np.int32)
+            if str(k) == "p":
+                if st.dims.n_act_planner:
+                    bp[e] = env._as_buf(row, bp, (st.dims.n_act_planner,))
+            elif str(k) == "a":       # collated: [n_agents] or [n_agents, n_act]
+                ba[e] = env._as_buf(row, ba, tuple(ba.shape[1:]))
+            else:
+                ba[e, int(k)] = env._as_buf(row, ba, (st.dims.n_act_agent,))
+        env.step(env.action_buffers)
+        obs, rew, done = self._outputs()
+        return obs, rew, done, {k: {} for k in obs} if "a" not in obs else \
+            {"a": {str(i): {} for i in range(env.n_agents)}, "p": {}}

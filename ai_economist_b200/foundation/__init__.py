@@ -16,7 +16,17 @@ scenarios = _scenarios_mod.scenario_registry
 
 
 def make_env_instance(scenario_name, **kwargs):
-    """Same call as the reference; extra kwargs: n_envs (default 1), device ("cuda:0"), seeds, auto_reset."""
+    """Same call as the reference; extra kwargs: n_envs (default 1), device ("cuda:0"), seeds, auto_reset, and
+    reference_api (or AIE_REFERENCE_API=1 in the environment): wrap replica 0 in adapters.ReferenceApiEnv, whose
+    reset()/step() take and return the reference's nested numpy dictionaries, so tutorial code runs unchanged."""
+    import os
+    ref_api = kwargs.pop("reference_api", None)
+    if ref_api is None:
+        ref_api = os.environ.get("AIE_REFERENCE_API", "0") not in ("", "0")
+    if ref_api:
+        from ..adapters import ReferenceApiEnv
+        kwargs.setdefault("auto_reset", False)   # the caller resets explicitly, like the reference's loops do
+        return ReferenceApiEnv(make_env_instance(scenario_name, reference_api=False, **kwargs))
     scenario_cls = scenarios.get(scenario_name)
     env_class = getattr(scenario_cls, "env_class", None)
     if env_class is not None:  # scenarios with their own device path (COVID-19)

@@ -39,7 +39,7 @@ class BaseAgent:
         """int (single-action: 1 + sum of subspace sizes) or array of per-subspace sizes (multi-action)."""
         if self.multi_action_mode:
             if not self._action_names:
-                return [1]  # PassiveAgentPlaceholder
+                return np.array([1])  # PassiveAgentPlaceholder (base_agent.py:163-166)
             return np.array([self.action_dim[k] for k in self._action_names])
         return 1 + sum(self.action_dim.values())
 

@@ -297,6 +297,8 @@ class BatchedFoundationEnv:
     def reset(self, seed_state=None, force_dense_logging=False):
         if seed_state is not None:
             raise NotImplementedError("pass seeds= / call seed() instead of seed_state")
+        if self._loaded and "episode_final" not in self._stepper.buf:
+            self._last_ep_metrics_host = self.metrics_of(0)   # base_env.py:893-896: reset() stores the old episode's metrics
         if self._loaded and self._rs is not None:
             self._completions = self._stepper.to_numpy(self._stepper.state_view("completions")).astype(np.int64) \
                 if hasattr(self._stepper, "state_view") else self._completions
@@ -512,8 +514,8 @@ class BatchedFoundationEnv:
     def previous_episode_metrics_of(self, e):
         from .metrics import metrics_from_state
         st = self._stepper
-        if "episode_final" not in st.buf:
-            return None
+        if "episode_final" not in st.buf:   # no auto-reset: what the last explicit reset() stored (replica 0 only)
+            return getattr(self, "_last_ep_metrics_host", None) if e == 0 else None
         fin = st.read_state(e, final=True)
         if int(fin["t"][0]) == 0:   # nothing recorded yet
             return None

@@ -1,0 +1,106 @@
+"""adapters.ReferenceApiEnv: the reference's single-env interface over replica 0, so code written for
+ai_economist.foundation runs unchanged.  The loop below is the one of tutorials/economic_simulation_basic.ipynb
+(cells 11-39: env_config, sample_random_actions, play an episode with dense logging)."""
+import numpy as np
+import pytest
+
+from ai_economist_b200 import foundation
+from oracle import ref_harness as rh
+from tests.emu.emu_stepper import emu_factory
+
+# tutorials/economic_simulation_basic.ipynb cell 11, verbatim apart from a shorter episode
+ENV_CONFIG = {
+    'scenario_name': 'layout_from_file/simple_wood_and_stone',
+    'components': [
+        ('Build', {'skill_dist': "pareto", 'payment_max_skill_multiplier': 3}),
+        ('ContinuousDoubleAuction', {'max_num_orders': 5}),
+        ('Gather', {}),
+    ],
+    'env_layout_file': 'quadrant_25x25_20each_30clump.txt',
+    'starting_agent_coin': 10,
+    'fixed_four_skill_and_loc': True,
+    'n_agents': 4,
+    'world_size': [25, 25],
+    'episode_length': 60,
+    'multi_action_mode_agents': False,
+    'multi_action_mode_planner': True,
+    'flatten_observations': False,
+    'flatten_masks': True,
+}
+
+
+def sample_random_action(agent, mask, rng):   # cell 18 (with an explicit generator instead of np.random)
+    if agent.multi_action_mode:
+        split_masks = np.split(mask, agent.action_spaces.cumsum()[:-1])
+        return [rng.choice(np.arange(len(m_)), p=m_ / m_.sum()) for m_ in split_masks]
+    return rng.choice(np.arange(agent.action_spaces), p=mask / mask.sum())
+
+
+def sample_random_actions(env, obs, rng):
+    return {a_idx: sample_random_action(env.get_agent(a_idx), a_obs['action_mask'], rng) for a_idx, a_obs in obs.items()}
+
+
+def play(env, rng, dense):
+    obs = env.reset(force_dense_logging=dense)
+    trace = [obs]
+    for t in range(env.episode_length):
+        obs, rew, done, info = env.step(sample_random_actions(env, obs, rng))
+        trace.append((obs, rew, done))
+    return trace
+
+
+def test_tutorial_loop_runs_unchanged_on_the_reference_api():
+    env = foundation.make_env_instance(**ENV_CONFIG, reference_api=True, stepper_factory=emu_factory,
+                                       dense_log_frequency=1)
+    env.seed(5)
+    assert env.get_agent(0).action_spaces == 50 and env.episode_length == 60
+    trace = play(env, np.random.RandomState(0), dense=True)
+    obs, rew, done = trace[-1]
+    assert set(obs.keys()) == {"0", "1", "2", "3", "p"} and done["__all__"] is True
+    assert isinstance(rew["0"], float) and isinstance(obs["0"]["world-inventory-Coin"], float)
+    assert obs["0"]["world-map"].shape == (7, 11, 11) and obs["0"]["action_mask"].shape == (50,)
+    assert set(obs["p"]["p0"].keys()) == {"world-inventory-Coin", "world-inventory-Stone", "world-inventory-Wood",
+                                          "world-loc-row", "world-loc-col"}
+    log = env.previous_episode_dense_log
+    assert len(log["states"]) == 61 and len(log["actions"]) == 60 and set(log) >= {"world", "Build", "Gather", "Trade"}
+    env.reset()
+    m = env.previous_episode_metrics
+    assert m is not None and "social/productivity" in m
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
+@pytest.mark.parametrize("flags", [dict(flatten_observations=False, flatten_masks=True),
+                                   dict(flatten_observations=True, flatten_masks=True)])
+def test_reference_api_tracks_the_live_reference(flags):
+    """Same config, same seed, same caller code on both: identical observation structure and values, two episodes."""
+    cfg = dict(ENV_CONFIG)
+    cfg.update(flags)
+    f = rh.load_reference_foundation()
+    ref = f.make_env_instance(**cfg)
+    mine = foundation.make_env_instance(**cfg, reference_api=True, stepper_factory=emu_factory)
+    ref.seed(9)
+    mine.seed(9)
+
+    def same(a, b, label):
+        if isinstance(a, dict):
+            assert set(a.keys()) == set(b.keys()), label
+            for k in a:
+                same(a[k], b[k], label + "/" + str(k))
+        else:
+            assert type(b) in (float, list, np.ndarray, bool), (label, type(b))
+            assert np.allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=1e-6, atol=1e-7), label
+
+    for episode in range(2):
+        ra, rb = np.random.RandomState(episode), np.random.RandomState(episode)
+        o1, o2 = ref.reset(), mine.reset()
+        same(o1, o2, "reset %d" % episode)
+        for t in range(ref.episode_length):
+            a1, a2 = sample_random_actions(ref, o1, ra), sample_random_actions(mine, o2, rb)
+            assert {k: int(v) for k, v in a1.items() if k != "p"} == {k: int(v) for k, v in a2.items() if k != "p"}
+            (o1, r1, d1, _), (o2, r2, d2, _) = ref.step(a1), mine.step(a2)
+            same(o1, o2, "ep %d t %d obs" % (episode, t))
+            same(r1, r2, "ep %d t %d rew" % (episode, t))
+            assert d1 == d2
+    mref, mmine = ref.metrics, mine.metrics
+    assert set(mref) == set(mmine)
