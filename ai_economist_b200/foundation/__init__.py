@@ -25,6 +25,9 @@ def make_env_instance(scenario_name, **kwargs):
         ref_api = os.environ.get("AIE_REFERENCE_API", "0") not in ("", "0")
     if ref_api:
         from ..adapters import ReferenceApiEnv
+        if getattr(scenarios.get(scenario_name), "env_class", None) is not None:
+            raise NotImplementedError("reference_api covers the gather-trade-build scenarios; the COVID-19 env already "
+                                      "returns the reference's collated layout (with a leading env axis)")
         kwargs.setdefault("auto_reset", False)   # the caller resets explicitly, like the reference's loops do
         return ReferenceApiEnv(make_env_instance(scenario_name, reference_api=False, **kwargs))
     scenario_cls = scenarios.get(scenario_name)
