@@ -40,6 +40,7 @@ class AieConfig(C.Structure):
         ("payment_max_skill_multiplier", C.c_int32), ("fixed_four", C.c_int32),
         ("ranked_locs", (C.c_int16 * 2) * 64), ("avg_ranked_skill", C.c_double * 64),
         ("single_action_planner", C.c_int32), ("regen_halfwidth", C.c_int32 * 2),
+        ("full_observability", C.c_int32),
     ]
 
 
@@ -47,7 +48,8 @@ class AieDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in [
         "n_envs", "n_agents", "height", "width", "n_map_channels", "window", "flat_agent", "flat_planner",
         "flat_planner_agent", "mask_agent", "mask_planner", "n_act_agent", "n_act_planner", "state_bytes",
-        "algorithmic_bytes_per_env_step", "n_stats", "stats_trade", "stats_tax"]]
+        "algorithmic_bytes_per_env_step", "n_stats", "stats_trade", "stats_tax", "agent_map_elems",
+        "agent_idx_elems"]]
 
 
 _BUF_NAMES = ["state", "state0", "actions_agent", "actions_planner", "obs_agent_map", "obs_agent_idx",
@@ -218,4 +220,5 @@ def config_from_spec(spec, auto_reset=True):
         cfg.avg_ranked_skill[i] = float(v)
     cfg.single_action_planner = int(spec.get("single_action_planner", 0))
     cfg.regen_halfwidth[0], cfg.regen_halfwidth[1] = [int(v) for v in spec.get("regen_halfwidth", [0, 0])]
+    cfg.full_observability = int(spec.get("full_observability", 0))
     return cfg

@@ -81,7 +81,7 @@ int aie_bind_buffers(aie_env *env, const aie_buffers *b) {
     if (!env || !b) return fail(AIE_EINVAL, "null argument");
     const aie::DevCfg &c = env->cfg;
     if (!b->state || !b->state0 || !b->actions_agent || !b->obs_agent_map || !b->obs_agent_idx || !b->obs_agent_flat ||
-        !b->mask_agent || !b->obs_planner_flat || !b->obs_planner_agents || !b->mask_planner || !b->obs_time ||
+        !b->mask_agent || !b->obs_planner_flat || (c.Fpa > 0 && !b->obs_planner_agents) || !b->mask_planner || !b->obs_time ||
         !b->reward || !b->done)
         return fail(AIE_EINVAL, "aie_bind_buffers: a required buffer is NULL");
     if (c.planner_spatial && (!b->obs_planner_map || !b->obs_planner_idx))
@@ -160,7 +160,7 @@ int aie_step_host(aie_env *env, const int32_t *act_a, const int32_t *act_p, cons
     if (!env || !act_a || !o) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_host: bind buffers and load state first");
     const aie::DevCfg &c = env->cfg;
-    const size_t E = env->n_envs, A = c.A, ww = (size_t)c.win * c.win;
+    const size_t E = env->n_envs, A = c.A;
     int rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * A * c.n_act_a * 4, stream);
     if (rc != AIE_OK) return rc;
     if (c.n_act_p > 0) {
@@ -172,7 +172,7 @@ int aie_step_host(aie_env *env, const int32_t *act_a, const int32_t *act_p, cons
     if (rc != AIE_OK) return rc;
     const aie::DevBufs &d = env->bufs;
     struct { void *h; const void *dev; size_t n; } cp[] = {
-        {o->obs_agent_map, d.a_map, E * A * (c.M + 1) * ww * 4}, {o->obs_agent_idx, d.a_idx, E * A * 2 * ww * 2},
+        {o->obs_agent_map, d.a_map, E * A * (size_t)c.a_map_elems * 4}, {o->obs_agent_idx, d.a_idx, E * A * (size_t)c.a_idx_elems * 2},
         {o->obs_agent_flat, d.a_flat, E * A * c.Fa * 4}, {o->mask_agent, d.a_mask, E * A * c.Na * 4},
         {o->obs_planner_map, c.planner_spatial ? d.p_map : nullptr, E * c.M * c.HW * 4},
         {o->obs_planner_idx, c.planner_spatial ? d.p_idx : nullptr, E * 2 * c.HW * 2},

@@ -1324,6 +1324,38 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
         store_bytes_i16<true>(o.p_idx(), HW, (const uint8_t *)e.owner, lane);
         store_bytes_i16<false>(o.p_idx() + HW, HW, s.locmap, lane);
     }
+    if (EXT && c.full_obs) {
+        // full_observability (layout_from_file.py:465-472): every agent gets the whole map - the same M bit planes as
+        // the planner - and the two index planes with its own index recoded to 1 (staged as bytes per agent)
+        const int HW4 = (HW + 3) & ~3;
+        uint8_t *so = s.wstage, *sl = s.wstage + HW4;
+        for (int a = 0; a < A; a++) {
+            for (int k = lane; k < HW; k += NL) {
+                const int ow = e.owner[k], vl = s.locmap[k];
+                so[k] = (uint8_t)(ow < 0 ? 0 : (ow == a ? 1 : ow + 2));
+                sl[k] = (uint8_t)(vl == a + 2 ? 1 : vl);
+            }
+            for (int i = lane; i < AS_COUNT; i += NL) s.agf[i] = s.sc_a[a * AS_COUNT + i];
+            if (c.has[COMP_CDA])
+                for (int i = lane; i < 4 * P; i += NL) {
+                    const int side = i >= 2 * P ? 1 : 0, r = i - side * 2 * P, cc = r >= P ? 1 : 0, pl = r - cc * P;
+                    const float mine = (float)(side ? e.ask_hist : e.bid_hist)[(cc * A + a) * P + pl];
+                    s.agf[AS_COUNT + i] = mine;
+                    s.agf[AS_COUNT + 4 * P + i] = s.shf[c.sh_full + i] - mine;
+                }
+            wsync();
+            float *am = o.b->a_map + (o.env * A + a) * (size_t)c.a_map_elems;
+            int16_t *ai = o.b->a_idx + (o.env * A + a) * (size_t)c.a_idx_elems;
+            store_bitplanes_f32(am, M, HW, c.HW_magic, e.cell, s.pbits, lane);
+            store_bytes_i16<false>(ai, HW, so, lane);
+            store_bytes_i16<false>(ai + HW, HW, sl, lane);
+            {
+                const float *shf = s.shf, *agf = s.agf;
+                store_run_f32(o.a_flat() + a * c.Fa, c.Fa, lane, [=](int j) { return flat_value(shf, agf, tab[j]); });
+            }
+            wsync();
+        }
+    } else
     // agent windows (layout_from_file.py:468-515): per agent, the window's cells are staged once as bytes (one lane
     // per window cell), then the M+1 map planes and the 2 index planes stream out of the staged bytes
     {
@@ -1378,6 +1410,7 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     {
         const float *shf = s.shf, *sc = s.sc_a;
         const uint16_t *tpa = tab + c.tab_pa, *tp = tab + c.tab_p;
+        if (!EXT || c.Fpa > 0)
         store_rows_f32(o.p_agents(), A, c.Fpa, c.Fpa_magic, lane,
                        [=](int a, int j) { return flat_value(shf, sc + a * AS_COUNT, tpa[j]); });
         store_run_f32(o.p_flat(), c.Fp, lane, [=](int j) { return flat_value(shf, shf, tp[j]); });

@@ -150,7 +150,10 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     if (c.n_sub == 0) return bad("mobile agents need at least one action component");
     c.planner_acts = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_MODEL_WRAPPER && !c.disable_taxes) ? 1 : 0;
     c.planner_single = (c.planner_acts && u.single_action_planner) ? 1 : 0;
-    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1]) ? 1 : 0;
+    c.full_obs = u.full_observability ? 1 : 0;
+    c.a_map_elems = c.full_obs ? c.M * c.HW : (c.M + 1) * c.win * c.win;
+    c.a_idx_elems = c.full_obs ? 2 * c.HW : 2 * c.win * c.win;
+    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;
     c.Np = c.planner_acts ? (c.planner_single ? 1 + c.B * c.R : c.B * (1 + c.R)) : 1;
@@ -182,14 +185,17 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         static const char *CN[2] = {"Stone", "Wood"};
         std::vector<FlatKey> ka, kp, kpa;
         auto K = [](const std::string &k, int kind, int payload, int n) { return FlatKey{k, kind, payload, n}; };
-        ka.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); ka.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1));
+        if (!c.full_obs) { ka.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); ka.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1)); }
         ka.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); ka.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
         ka.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1)); ka.push_back(K("time", FK_SHARED, SH_TIME, 1));
         kp.push_back(K("world-inventory-Coin", FK_SHARED, SH_ZERO, 1)); kp.push_back(K("world-inventory-Stone", FK_SHARED, SH_ZERO, 1));
         kp.push_back(K("world-inventory-Wood", FK_SHARED, SH_ZERO, 1)); kp.push_back(K("time", FK_SHARED, SH_TIME, 1));
-        kpa.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); kpa.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
-        kpa.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1));
-        if (c.planner_spatial) { kpa.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); kpa.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1)); }
+        // with full_observability the scenario sets no p<i> entries at all (layout_from_file.py:465-472 vs :509-513)
+        if (!c.full_obs) {
+            kpa.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); kpa.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
+            kpa.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1));
+        }
+        if (c.planner_spatial && !c.full_obs) { kpa.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); kpa.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1)); }
         if (c.has[COMP_BUILD]) { ka.push_back(K("Build-build_payment", FK_AGENT, AS_BUILD_PAYMENT, 1)); ka.push_back(K("Build-build_skill", FK_AGENT, AS_BUILD_SKILL, 1)); }
         if (c.has[COMP_GATHER]) ka.push_back(K("Gather-bonus_gather_prob", FK_AGENT, AS_BONUS, 1));
         if (c.has[COMP_CDA])
@@ -268,7 +274,8 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
         c.obs_floats_size = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT + AS_COUNT + 8 * P));
-        c.obs_bytes_size = align16(((A * MS_COUNT + 7) & ~7) + 8 + ((c.HW + 3) & ~3) + 3 * c.win * c.win + 24);
+        const int stage_win = 3 * c.win * c.win + 24, stage_full = c.full_obs ? 2 * ((c.HW + 3) & ~3) + 16 : 0;
+        c.obs_bytes_size = align16(((A * MS_COUNT + 7) & ~7) + 8 + ((c.HW + 3) & ~3) + (stage_full > stage_win ? stage_full : stage_win));
         c.obs_scratch_bytes = c.obs_floats_size + c.obs_bytes_size;
         {
             const int mt_bytes = 4 * 624;
@@ -291,8 +298,8 @@ inline void fill_dims(const DevCfg &c, aie_dims &d) {
     d.mask_agent = c.Na; d.mask_planner = c.Np; d.n_act_agent = c.n_act_a; d.n_act_planner = c.n_act_p;
     d.state_bytes = c.rec_bytes;
     d.n_stats = c.n_stats; d.stats_trade = c.st_trade; d.stats_tax = c.st_tax;
-    const int ww = c.win * c.win;
-    long long obs = (long long)c.A * ((c.M + 1) * ww * 4 + 2 * ww * 2 + c.Fa * 4 + c.Na * 4) + c.Fp * 4 + c.A * c.Fpa * 4 +
+    d.agent_map_elems = c.a_map_elems; d.agent_idx_elems = c.a_idx_elems;
+    long long obs = (long long)c.A * (c.a_map_elems * 4 + c.a_idx_elems * 2 + c.Fa * 4 + c.Na * 4) + c.Fp * 4 + c.A * c.Fpa * 4 +
                     c.Np * 4 + 4 + (c.planner_spatial ? (c.M * c.HW * 4 + 2 * c.HW * 2) : 0);
     long long io = 8 * (c.A + 1) + 4 + 4 * (c.A * c.n_act_a + c.n_act_p);
     d.algorithmic_bytes_per_env_step = (int32_t)(obs + io + 2LL * c.rec_bytes);

@@ -126,6 +126,8 @@ struct DevCfg {
     // regen_tab[c][n] = ceil(p_n * 2^53) with p_n the running float64 sum of n copies of regen_weight / d^2
     int32_t regen_hw[2];
     uint64_t regen_tab[2][50];
+    // full_observability: agents get the whole map; a_map_elems / a_idx_elems = elements per agent of the two tensors
+    int32_t full_obs, a_map_elems, a_idx_elems;
 };
 
 // raw device pointers (mirrors aie_buffers)

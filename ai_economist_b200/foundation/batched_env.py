@@ -443,7 +443,7 @@ class BatchedFoundationEnv:
         p["action_mask"] = b["mask_planner"] if flat_m else self._mask_dict(self._planner, b["mask_planner"])
         if "obs_planner_map" in b:
             p["world-map"], p["world-idx_map"] = b["obs_planner_map"], b["obs_planner_idx"]
-        for i in range(A):
+        for i in range(A if self._stepper.dims.flat_planner_agent else 0):   # (no p<i> with full observability and no tax)
             p["p%d" % i] = b["obs_planner_agents"][:, i] if flat_o else \
                 self._named_fields(b["obs_planner_agents"][:, i], lay_pa)
         obs["p"] = p
@@ -478,7 +478,7 @@ class BatchedFoundationEnv:
         obs["p"] = {"flat": o["p_flat"], "time": o["time"].astype(np.float64), "action_mask": o["p_mask"]}
         if "p_map" in o:
             obs["p"]["world-map"], obs["p"]["world-idx_map"] = o["p_map"], o["p_idx"]
-        for i in range(A):
+        for i in range(A if o["p_agents"].shape[-1] else 0):
             obs["p"]["p%d" % i] = o["p_agents"][i]
         rew = {str(i): float(o["rew"][i]) for i in range(A)}
         rew["p"] = float(o["rew"][A])

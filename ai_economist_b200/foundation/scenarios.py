@@ -29,8 +29,7 @@ class BaseScenario:
                  planner_reward_type="coin_eq_times_productivity", mixing_weight_gini_vs_coin=0.0):
         self.env = env
         self.planner_gets_spatial_info = bool(planner_gets_spatial_info)
-        if full_observability:
-            raise NotImplementedError("full_observability=True is not on the GPU path")
+        self.full_observability = bool(full_observability)
         self.obs_range = int(mobile_agent_observation_range)
         self.starting_agent_coin = float(starting_agent_coin)
         assert self.starting_agent_coin >= 0.0
@@ -81,6 +80,7 @@ class BaseScenario:
     def scenario_spec_fields(self):
         return dict(
             obs_range=self.obs_range, planner_gets_spatial_info=int(self.planner_gets_spatial_info),
+            full_observability=int(self.full_observability),
             isoelastic_eta=self.isoelastic_eta, energy_cost=self.energy_cost,
             energy_warmup_constant=self.energy_warmup_constant,
             energy_warmup_auto=int(self.energy_warmup_method == "auto"),

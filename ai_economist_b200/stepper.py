@@ -28,12 +28,15 @@ class BatchStepper:
         self._check(lib.aie_get_dims(self._h, C.byref(self.dims)))
         d, E, A = self.dims, self.n_envs, spec["n_agents"]
         H, W = spec["height"], spec["width"]
+        full = bool(spec.get("full_observability", 0))   # agents see the whole map: [M, H, W] / [2, H, W] per agent
+        assert d.agent_map_elems == (d.n_map_channels * H * W if full else (d.n_map_channels + 1) * d.window ** 2)
         shapes = {
             "state": ("u8", (E, d.state_bytes)), "state0": ("u8", (E, d.state_bytes)),
             "actions_agent": ("i32", (E, A, d.n_act_agent)),
             "actions_planner": ("i32", (E, max(1, d.n_act_planner))),
-            "obs_agent_map": ("f32", (E, A, d.n_map_channels + 1, d.window, d.window)),
-            "obs_agent_idx": ("i16", (E, A, 2, d.window, d.window)),
+            "obs_agent_map": ("f32", (E, A, d.n_map_channels, H, W) if full else
+                              (E, A, d.n_map_channels + 1, d.window, d.window)),
+            "obs_agent_idx": ("i16", (E, A, 2, H, W) if full else (E, A, 2, d.window, d.window)),
             "obs_agent_flat": ("f32", (E, A, d.flat_agent)),
             "mask_agent": ("f32", (E, A, d.mask_agent)),
             "obs_planner_map": ("f32", (E, d.n_map_channels, H, W)),
@@ -59,7 +62,8 @@ class BatchStepper:
         self.buf = {k: self._alloc(shape, dt) for k, (dt, shape) in shapes.items()}
         bufs = _abi.AieBuffers()
         for name in _abi._BUF_NAMES:
-            setattr(bufs, name, self._ptr(self.buf[name]) if name in self.buf else None)
+            ok = name in self.buf and int(np.prod(self.buf[name].shape)) > 0   # zero-size tensors have no storage
+            setattr(bufs, name, self._ptr(self.buf[name]) if ok else None)
         bufs.events = self._ptr(self.buf["events"]) if self.event_envs else None
         bufs.event_envs, bufs.event_cap = self.event_envs, self.event_cap
         self._check(lib.aie_bind_buffers(self._h, C.byref(bufs)))

@@ -119,6 +119,10 @@ typedef struct aie_config {
     int32_t regen_halfwidth[2];     /* {stone,wood}_regen_halfwidth, [Stone, Wood], 0..3 (dynamic_layout.py:150-153):
                                        a source cell respawns with probability convolve2d(source map, regen_weight /
                                        d^2 * ones(d, d))[cell], d = 1 + 2 * halfwidth (dynamic_layout.py:446-461) */
+    int32_t full_observability;     /* layout_from_file.py:465-472 / dynamic_layout.py:526-533: every mobile agent's
+                                       "world-map" is the whole map [M, H, W] (no window, no "inside" plane), its
+                                       "world-idx_map" [2, H, W] with the agent's own index recoded to 1; the loc-row /
+                                       loc-col scalars and the scenario's share of the planner's p<i> vectors are absent */
 } aie_config;
 
 /* Sizes the caller needs to allocate the device buffers. */
@@ -143,6 +147,9 @@ typedef struct aie_dims {
      * effective rates, sum of bracket rates over periods [16], bracket occupancy [16], sum of max(0, income)
      * over tax days [A], sum of tax paid [A]. */
     int32_t n_stats, stats_trade, stats_tax;
+    /* ABI 3: elements per agent of obs_agent_map / obs_agent_idx: (M+1)*win*win and 2*win*win, or M*H*W and 2*H*W
+     * with full_observability */
+    int32_t agent_map_elems, agent_idx_elems;
 } aie_dims;
 
 /* Raw device pointers.  All tensors are contiguous, env-major.
@@ -157,14 +164,14 @@ typedef struct aie_dims {
 typedef struct aie_buffers {
     void *state, *state0;
     const int32_t *actions_agent, *actions_planner;
-    float *obs_agent_map;       /* [E, A, M+1, win, win] */
-    int16_t *obs_agent_idx;     /* [E, A, 2, win, win] */
+    float *obs_agent_map;       /* [E, A, M+1, win, win]  ([E, A, M, H, W] with full_observability) */
+    int16_t *obs_agent_idx;     /* [E, A, 2, win, win]    ([E, A, 2, H, W]) */
     float *obs_agent_flat;      /* [E, A, F_a] */
     float *mask_agent;          /* [E, A, mask_agent] */
     float *obs_planner_map;     /* [E, M, H, W]   (ignored unless planner_gets_spatial_info) */
     int16_t *obs_planner_idx;   /* [E, 2, H, W] */
     float *obs_planner_flat;    /* [E, F_p] */
-    float *obs_planner_agents;  /* [E, A, flat_planner_agent] */
+    float *obs_planner_agents;  /* [E, A, flat_planner_agent]  (may be NULL when flat_planner_agent == 0) */
     float *mask_planner;        /* [E, mask_planner] */
     float *obs_time;            /* [E] */
     double *reward;             /* [E, A+1] */

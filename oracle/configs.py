@@ -183,6 +183,18 @@ CONFIGS = {
         wood_regen_halfwidth=2, wood_regen_weight=0.6, stone_regen_halfwidth=1, stone_regen_weight=0.4),
 }
 
+# full_observability=True: agents get the whole map (no window, no loc scalars); p<i> carry only the tax entries
+CONFIGS["full_obs_tax"] = dict(
+    scenario_name="layout_from_file/simple_wood_and_stone",
+    components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=3)),
+                ("Gather", dict(skill_dist="pareto")),
+                ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=10, rate_disc=0.05,
+                                            tax_model="model_wrapper"))],
+    env_layout_file="env-pure_and_mixed-15x15.txt", starting_agent_coin=8, full_observability=True,
+    n_agents=5, world_size=[15, 15], episode_length=100,
+    multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True, flatten_masks=True)
+
 # Edge-of-range configurations (tests/test_edge_configs.py): smallest / largest sizes and degenerate options.  They are
 # checked live against the imported reference in the build container, and oracle <-> device code everywhere.
 _LFF = "layout_from_file/simple_wood_and_stone"
@@ -241,6 +253,12 @@ EDGE_CONFIGS = {
                                                                     fixed_bracket_rates=[0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6]))],
         env_layout_file="env-pure_and_mixed-15x15.txt", n_agents=4, world_size=[15, 15], episode_length=40,
         starting_agent_coin=15, isoelastic_eta=0.99, **_BASE),
+    # full observability without a tax component: the planner has no p<i> vectors at all; non-square world
+    "full_obs_plain": dict(
+        scenario_name="uniform/simple_wood_and_stone",
+        components=[("Build", {}), ("ContinuousDoubleAuction", dict(max_num_orders=2)), ("Gather", {})],
+        n_agents=3, world_size=[9, 14], episode_length=40, starting_agent_coin=5, full_observability=True,
+        starting_wood_coverage=0.10, starting_stone_coverage=0.10, **_BASE),
     # non-square world (uniform family), 33 agents: one more than a warp, both gini branches straddled
     "nonsquare_33_agents": dict(
         scenario_name="uniform/simple_wood_and_stone",

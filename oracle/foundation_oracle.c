@@ -175,9 +175,12 @@ int orc_dims_from_config(const orc_config *cfg, orc_dims *d) {
     d->win = 2 * cfg->obs_range + 1;
     /* agent flat: see SURVEY 8(a) row O2 / base_env.py:562-612 */
     d->flat_a = (has_build ? 2 : 0) + (has_cda ? C * (5 * P + 1) : 0) + (has_gather ? 1 : 0) +
-                (has_tax ? (B + 2 + A + 1 + 1) : 0) + 1 /* time */ + 3 /* inventory */ + 2 /* loc */;
+                (has_tax ? (B + 2 + A + 1 + 1) : 0) + 1 /* time */ + 3 /* inventory */ +
+                (cfg->full_observability ? 0 : 2) /* loc */;
     d->flat_p = (has_cda ? C * (3 * P + 1) : 0) + (has_tax ? (B + 2 + A + 1) : 0) + 1 + 3;
-    d->flat_pa = (has_tax ? 3 : 0) + 3 + (cfg->planner_gets_spatial_info ? 2 : 0);
+    d->flat_pa = (has_tax ? 3 : 0) + (cfg->full_observability ? 0 : 3 + (cfg->planner_gets_spatial_info ? 2 : 0));
+    d->a_map_elems = cfg->full_observability ? d->n_map_ch * cfg->height * cfg->width : (d->n_map_ch + 1) * d->win * d->win;
+    d->a_idx_elems = cfg->full_observability ? 2 * cfg->height * cfg->width : 2 * d->win * d->win;
     {
         int i;
         for (i = 0; i < cfg->n_comp; i++) {
@@ -273,14 +276,14 @@ orc_batch *orc_create(const orc_config *cfg, int32_t n_envs) {
         s->tax_paid = (double *)zalloc(sizeof(double) * A);
         s->act_build = (int *)zalloc(sizeof(int) * A);
         s->act_move = (int *)zalloc(sizeof(int) * A);
-        s->a_map = (float *)zalloc(sizeof(float) * A * (d->n_map_ch + 1) * d->win * d->win);
-        s->a_idx = (int16_t *)zalloc(sizeof(int16_t) * A * 2 * d->win * d->win);
+        s->a_map = (float *)zalloc(sizeof(float) * A * d->a_map_elems);
+        s->a_idx = (int16_t *)zalloc(sizeof(int16_t) * A * d->a_idx_elems);
         s->a_flat = (float *)zalloc(sizeof(float) * A * d->flat_a);
         s->a_mask = (float *)zalloc(sizeof(float) * A * d->mask_a);
         s->p_map = (float *)zalloc(sizeof(float) * d->n_map_ch * HW);
         s->p_idx = (int16_t *)zalloc(sizeof(int16_t) * 2 * HW);
         s->p_flat = (float *)zalloc(sizeof(float) * d->flat_p);
-        s->p_agents = (float *)zalloc(sizeof(float) * A * d->flat_pa);
+        s->p_agents = (float *)zalloc(sizeof(float) * A * (d->flat_pa > 0 ? d->flat_pa : 1));
         s->p_mask = (float *)zalloc(sizeof(float) * d->mask_p);
         s->rew = (double *)zalloc(sizeof(double) * (A + 1));
     }
@@ -880,6 +883,14 @@ static void generate_observations(const orc_batch *b, env_t *s) {
     /* agent windows (layout_from_file.py:468-515): zero pad, extra channel = 1 inside padding?  No:
      * constant_values=[(0,1),...] pads ONE extra channel after the last with value 1 everywhere,
      * and the spatial padding of every channel (including that one) is 0. */
+    if (cfg->full_observability) { /* layout_from_file.py:465-472: curr_map and a self-recoded copy of agent_idx_maps */
+        for (a = 0; a < A; a++) {
+            float *am = s->a_map + (size_t)a * d->a_map_elems;
+            int16_t *ai = s->a_idx + (size_t)a * d->a_idx_elems;
+            memcpy(am, s->p_map, sizeof(float) * M * HW);
+            for (k = 0; k < 2 * HW; k++) ai[k] = (s->p_idx[k] == a + 2) ? 1 : s->p_idx[k];
+        }
+    } else
     for (a = 0; a < A; a++) {
         float *am = s->a_map + (size_t)a * (M + 1) * win * win;
         int16_t *ai = s->a_idx + (size_t)a * 2 * win * win;
@@ -936,16 +947,20 @@ static void generate_observations(const orc_batch *b, env_t *s) {
                    inv_wood = s->inv[WOOD][a] * inv_scale;
             double bp = 0, marg = 0;
             double my_av_asks[2][64], my_av_bids[2][64];
-            add_field(f, &nf, "world-loc-row", &loc_row, 1);
-            add_field(f, &nf, "world-loc-col", &loc_col, 1);
+            if (!cfg->full_observability) {
+                add_field(f, &nf, "world-loc-row", &loc_row, 1);
+                add_field(f, &nf, "world-loc-col", &loc_col, 1);
+            }
             add_field(f, &nf, "world-inventory-Coin", &inv_coin, 1);
             add_field(f, &nf, "world-inventory-Stone", &inv_stone, 1);
             add_field(f, &nf, "world-inventory-Wood", &inv_wood, 1);
             add_field(f, &nf, "time", &time_v, 1);
-            add_field(fp, &nfp, "world-inventory-Coin", &inv_coin, 1);
-            add_field(fp, &nfp, "world-inventory-Stone", &inv_stone, 1);
-            add_field(fp, &nfp, "world-inventory-Wood", &inv_wood, 1);
-            if (cfg->planner_gets_spatial_info) {
+            if (!cfg->full_observability) { /* the p<i> entries are only set in the windowed branch (:509-513) */
+                add_field(fp, &nfp, "world-inventory-Coin", &inv_coin, 1);
+                add_field(fp, &nfp, "world-inventory-Stone", &inv_stone, 1);
+                add_field(fp, &nfp, "world-inventory-Wood", &inv_wood, 1);
+            }
+            if (cfg->planner_gets_spatial_info && !cfg->full_observability) {
                 add_field(fp, &nfp, "world-loc-row", &loc_row, 1);
                 add_field(fp, &nfp, "world-loc-col", &loc_col, 1);
             }
@@ -1224,9 +1239,9 @@ int orc_get_obs(const orc_batch *b, int32_t e, float *a_map, int16_t *a_idx, flo
                 float *time_obs, double *rew, int32_t *done) {
     const env_t *s = &b->envs[e];
     const orc_dims *d = &b->dims;
-    int A = b->cfg.n_agents, HW = b->cfg.height * b->cfg.width, ww = d->win * d->win;
-    if (a_map) memcpy(a_map, s->a_map, sizeof(float) * A * (d->n_map_ch + 1) * ww);
-    if (a_idx) memcpy(a_idx, s->a_idx, sizeof(int16_t) * A * 2 * ww);
+    int A = b->cfg.n_agents, HW = b->cfg.height * b->cfg.width;
+    if (a_map) memcpy(a_map, s->a_map, sizeof(float) * A * d->a_map_elems);
+    if (a_idx) memcpy(a_idx, s->a_idx, sizeof(int16_t) * A * d->a_idx_elems);
     if (a_flat) memcpy(a_flat, s->a_flat, sizeof(float) * A * d->flat_a);
     if (a_mask) memcpy(a_mask, s->a_mask, sizeof(float) * A * d->mask_a);
     if (p_map) memcpy(p_map, s->p_map, sizeof(float) * d->n_map_ch * HW);

@@ -38,6 +38,7 @@ PLAN = [
     ("split_layout", 1001, 120, 20),
     ("tax_single_planner", 1001, 150, 10),
     ("uniform_halfwidth", 1001, 150, 25),
+    ("full_obs_tax", 1001, 100, 20),
     # multi-episode traces (env.reset() between episodes, the global numpy stream continues): device-side reset
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),

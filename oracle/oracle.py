@@ -38,13 +38,14 @@ class OrcConfig(C.Structure):
         ("tax_annealing", C.c_int32), ("annealing_warmup", C.c_double),
         ("annealing_slope", C.c_double), ("rate_max", C.c_double),
         ("single_action_planner", C.c_int32), ("regen_halfwidth", C.c_int32 * 2),
+        ("full_observability", C.c_int32),
     ]
 
 
 class OrcDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ["n_map_ch", "win", "flat_a", "flat_p", "flat_pa", "mask_a", "mask_p",
-                 "n_act_a", "n_act_p", "book_cap"]]
+                 "n_act_a", "n_act_p", "book_cap", "a_map_elems", "a_idx_elems"]]
 
 
 def build(force=False):
@@ -110,6 +111,7 @@ def config_from_spec(spec):
         cfg.fixed_rates[i] = v
     cfg.single_action_planner = int(spec.get("single_action_planner", 0))
     cfg.regen_halfwidth[0], cfg.regen_halfwidth[1] = spec.get("regen_halfwidth", [0, 0])
+    cfg.full_observability = int(spec.get("full_observability", 0))
     return cfg
 
 
@@ -169,9 +171,10 @@ class OracleBatch:
 
     def obs(self, e):
         d, A, H, W = self.dims, self.A, self.H, self.W
+        full = bool(self.spec.get("full_observability", 0))
         out = dict(
-            a_map=np.zeros((A, d.n_map_ch + 1, d.win, d.win), np.float32),
-            a_idx=np.zeros((A, 2, d.win, d.win), np.int16),
+            a_map=np.zeros((A, d.n_map_ch, H, W) if full else (A, d.n_map_ch + 1, d.win, d.win), np.float32),
+            a_idx=np.zeros((A, 2, H, W) if full else (A, 2, d.win, d.win), np.int16),
             a_flat=np.zeros((A, d.flat_a), np.float32),
             a_mask=np.zeros((A, d.mask_a), np.float32),
             p_map=np.zeros((d.n_map_ch, H, W), np.float32),

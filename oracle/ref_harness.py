@@ -92,7 +92,8 @@ def spec_from_reference_env(env):
         spec["regen_halfwidth"] = hw
     if not env.multi_action_mode_planner:
         spec["single_action_planner"] = 1
-    assert not env._full_observability
+    if env._full_observability:
+        spec["full_observability"] = 1
     for c in env._components:
         if c.name == "Build":
             spec.update(build_payment=float(c.payment), build_labor=c.build_labor)
@@ -155,7 +156,8 @@ def obs_arrays_from_reference(env, obs, rew=None, done=None):
         a_flat=np.stack([obs[str(i)]["flat"] for i in range(A)]).astype(np.float32),
         a_mask=np.stack([obs[str(i)]["action_mask"] for i in range(A)]).astype(np.float32),
         p_flat=np.asarray(obs["p"]["flat"], np.float32),
-        p_agents=np.stack([obs["p"]["p%d" % i] for i in range(A)]).astype(np.float32),
+        p_agents=(np.stack([obs["p"]["p%d" % i] for i in range(A)]).astype(np.float32) if "p0" in obs["p"]
+                  else np.zeros((A, 0), np.float32)),   # full_observability without a tax component: no p<i> at all
         p_mask=np.asarray(obs["p"]["action_mask"], np.float32),
         time=np.asarray(obs["p"]["time"], np.float32),
     )

@@ -59,6 +59,7 @@ def test_cuda_matches_reference_golden_trace(path):
     ("quadrant", 16, 120, 30),            # uniform family with water lines, lognormal skills
     ("multi_zone", 16, 120, 30),
     ("split_layout", 4, 120, 30),         # (the 100000-row skill table per replica keeps this one small)
+    ("full_obs_tax", 24, 100, 25),        # full_observability: whole-map agent observations
 ])
 def test_cuda_batch_matches_oracle(cfg, E, steps, every):
     env = _make_env(cfg, E, seed=4000, auto_reset=False)

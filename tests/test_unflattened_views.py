@@ -16,7 +16,7 @@ def _product(cfg, **over):
     return foundation.make_env_instance(name, n_envs=2, stepper_factory=emu_factory, auto_reset=False, **kw)
 
 
-@pytest.mark.parametrize("cfg", ["c1_tutorial", "c3_short_period", "tax_us_federal"])
+@pytest.mark.parametrize("cfg", ["c1_tutorial", "c3_short_period", "tax_us_federal", "full_obs_tax"])
 def test_named_fields_are_slices_of_the_flat_vectors(cfg):
     flat = _product(cfg)
     named = _product(cfg, flatten_observations=False, flatten_masks=False)
@@ -49,7 +49,7 @@ def test_named_fields_are_slices_of_the_flat_vectors(cfg):
 
 @pytest.mark.reference
 @pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
-@pytest.mark.parametrize("cfg", ["c1_tutorial", "c3_short_period", "tax_us_federal"])
+@pytest.mark.parametrize("cfg", ["c1_tutorial", "c3_short_period", "tax_us_federal", "full_obs_tax"])
 def test_unflattened_observations_match_live_reference(cfg):
     f = rh.load_reference_foundation()
     kw = dict(CONFIGS[cfg])
