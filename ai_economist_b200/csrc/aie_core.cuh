@@ -46,6 +46,9 @@
 #ifndef AIE_TWIST_UNROLL
 #define AIE_TWIST_UNROLL 8
 #endif
+#ifndef AIE_PLANES_V2
+#define AIE_PLANES_V2 0
+#endif
 #define AIE_PRAGMA_(x) _Pragma(#x)
 #define AIE_UNROLL(n) AIE_PRAGMA_(unroll n)
 
@@ -68,7 +71,10 @@ AIE_DEV int __popc_u32(uint32_t m) { return __popc(m); }
 AIE_DEV uint32_t fshr(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }  // sh in [0, 31]
 AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 #else
-constexpr int NL = 1;
+#ifndef AIE_EMU_NL
+#define AIE_EMU_NL 1   // tests/emu/planes_check.cpp sets 32 to walk the per-lane store loops lane by lane (no collectives there)
+#endif
+constexpr int NL = AIE_EMU_NL;
 AIE_DEV void wsync() {}
 AIE_DEV uint32_t wmax(uint32_t v) { return v; }
 AIE_DEV uint32_t wballot(bool p) { return p ? 1u : 0u; }
@@ -1163,6 +1169,34 @@ AIE_DEV void store_bitplanes_f32(float *dst, int np, int n, uint32_t n_magic, co
         return (bytes[x - m * n] & pbits[m]) ? 1.0f : 0.0f;
     });
     const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes);
+#if AIE_PLANES_V2
+    // Tuning variant (-DAIE_PLANES_V2=1, not the default build): the plane index / in-plane offset of a lane's group
+    // are carried from one iteration to the next (the run advances by 4 * NL floats) and the output pointer is a running
+    // one, instead of a multiply-high, a multiply and a 64-bit address build per group.
+    if (n >= 2 * NL) {
+        const int x_first = r.head + 4 * lane;
+        int m = (int)div_magic((uint32_t)x_first, n_magic), i = x_first - m * n;
+        float *qq = dst + x_first;
+#if AIE_ON_DEVICE
+        AIE_UNROLL(1)
+#endif
+        for (int g = lane; g < r.nq; g += NL) {
+            const uint32_t v = fshr(wd[i >> 2], wd[(i >> 2) + 1], 8 * (i & 3));
+            uint32_t t = v & (pbits[m] * 0x01010101u);
+            const int left = n - i;
+            if (left < 4) {
+                const uint32_t low = (1u << (8 * left)) - 1u;
+                t = (t & low) | ((wd[0] << (8 * left)) & (pbits[m + 1] * 0x01010101u) & ~low);
+            }
+            store4(qq, (t & 0xFFu) ? 1.0f : 0.0f, (t & 0xFF00u) ? 1.0f : 0.0f, (t & 0xFF0000u) ? 1.0f : 0.0f,
+                   (t & 0xFF000000u) ? 1.0f : 0.0f);
+            qq += 4 * NL; i += 4 * NL;
+            if (i >= n) { i -= n; m++; }   // 4 * NL <= 2 * n: at most two plane boundaries per step
+            if (i >= n) { i -= n; m++; }
+        }
+        return;
+    }
+#endif
     float *q = dst + r.head;
 #if AIE_ON_DEVICE
     AIE_UNROLL(1)

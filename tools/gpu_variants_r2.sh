@@ -1,0 +1,25 @@
+#!/bin/bash
+# Round-2 opener (one gpurun call): for the default library and every prebuilt tuning variant (tools/build_variants.py,
+# built in the CPU container; the .so files travel with the snapshot) - the golden / batch parity tests of the
+# BASELINE shapes, then a c2 and a c3 bench line.  Prints one summary line per variant.
+set -u
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+V=ai_economist_b200/csrc/variants
+for lib in default $(ls $V/*.so 2>/dev/null); do
+  name=$(basename $lib .so)
+  if [[ $lib == default ]]; then unset AIE_LIB_PATH; else export AIE_LIB_PATH=$PWD/$lib; fi
+  timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "c1_tutorial or c3_paper_tax or c5_small or full_size" > gpurun_out/pytest_$name.log 2>&1
+  echo "$name parity rc=$? $(tail -1 gpurun_out/pytest_$name.log)"
+  for w in c2 c3; do
+    timeout 300 python bench.py --workload $w --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 3 > gpurun_out/bench_${name}_$w.json 2> gpurun_out/bench_${name}_$w.err
+    python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_${name}_$w.json"))
+    print("$name $w value %.4e ms/step %.4f" % (d["value"], d["ms_per_step"]), {k: round(v["ms"] * 1e3, 1) for k, v in d["roofline"]["kernels"].items()}, "frac %.3f" % d["roofline"]["frac"], d["clocks"]["sm_mhz"])
+except Exception as ex:
+    print("$name $w FAILED", ex)
+PY
+  done
+done
