@@ -17,6 +17,7 @@
 #include "aie_core.cuh"
 #include "aie_covid_core.cuh"
 #include "aie_host.h"
+#include "aie_compact.cuh"
 
 struct aie_env;
 struct aie_covid_env;
@@ -30,6 +31,8 @@ struct State {
     int obs_threads;
     size_t obs_smem;
     uint16_t *tab_dev;   // observation programs (device copy)
+    uint8_t *compact_dev = nullptr, *compact_host = nullptr;   // aie_step_host_compact: device + pinned host staging
+    size_t compact_bytes = 0;
 };
 int init(aie_env *);
 void destroy(aie_env *);
@@ -42,6 +45,8 @@ int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, int emit_obs, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
+int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
+int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
 void *const_upload(const void *host, size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
@@ -54,6 +59,14 @@ int covid_launch_sample(aie_covid_env *, uint64_t key, void *stream);
 #include "aie_covid_abi.inl"
 
 namespace aie {
+
+// compacted D2H transfer (aie_compact.cuh): one warp rewrites one env's outputs as a compact record
+__global__ void __launch_bounds__(256) aie_pack_kernel(const __grid_constant__ DevCfg c, const DevBufs b, const CompactLayout L,
+                                                       uint8_t *dst) {
+    const size_t env = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (env >= (size_t)c.n_envs) return;
+    pack_env(c, b, L, env, dst + env * (size_t)L.bytes, threadIdx.x & 31);
+}
 
 static_assert(sizeof(DevCfg) <= 4000, "DevCfg is passed by value as a __grid_constant__ kernel parameter");
 
@@ -349,7 +362,30 @@ int init(aie_env *env) {
     AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
     return AIE_OK;
 }
-void destroy(aie_env *env) { if (env->be.tab_dev) cudaFree(env->be.tab_dev); }
+void destroy(aie_env *env) {
+    if (env->be.tab_dev) cudaFree(env->be.tab_dev);
+    if (env->be.compact_dev) cudaFree(env->be.compact_dev);
+    if (env->be.compact_host) cudaFreeHost(env->be.compact_host);
+}
+int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
+    if (env->be.compact_bytes < bytes) {
+        if (env->be.compact_dev) cudaFree(env->be.compact_dev);
+        if (env->be.compact_host) cudaFreeHost(env->be.compact_host);
+        env->be.compact_dev = env->be.compact_host = nullptr; env->be.compact_bytes = 0;
+        AIE_CUDA(cudaMalloc((void **)&env->be.compact_dev, bytes), "cudaMalloc compact buffer");
+        AIE_CUDA(cudaHostAlloc((void **)&env->be.compact_host, bytes, cudaHostAllocDefault), "cudaHostAlloc compact buffer");
+        env->be.compact_bytes = bytes;
+    }
+    *dev = env->be.compact_dev; *host = env->be.compact_host;
+    return AIE_OK;
+}
+int launch_pack(aie_env *env, const CompactLayout &L, uint8_t *dev, void *stream) {
+    const long long warps = env->n_envs;
+    aie_pack_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs, L, dev);
+    AIE_CUDA(cudaGetLastError(), "aie_pack_kernel launch");
+    env->launches++;
+    return AIE_OK;
+}
 
 int upload(aie_env *, void *dst, const void *src, size_t n, void *stream) {
     AIE_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D copy");

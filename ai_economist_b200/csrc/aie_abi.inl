@@ -10,8 +10,12 @@
 //   int launch_step(aie_env*, int emit_obs, void *stream);
 //   int launch_observe(aie_env*, int lo, int n, void *stream);
 //   int launch_sample(aie_env*, uint64_t seed, void *stream);
+//   int compact_buffers(aie_env*, size_t bytes, uint8_t **dev, uint8_t **host);   (library-owned, allocated once)
+//   int launch_pack(aie_env*, const aie::CompactLayout&, uint8_t *dev, void *stream);
 #include <string>
 #include <vector>
+
+#include "aie_compact_host.h"
 
 static thread_local std::string g_last_error;
 
@@ -26,6 +30,7 @@ struct aie_env {
     uint64_t sample_calls;
     aie::be::State be;
     std::vector<aie_flat_field> flat_layout[3];
+    aie::HostPool *pool = nullptr;   // aie_step_host_compact: created on first use
 };
 
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
@@ -54,6 +59,7 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
 int aie_destroy(aie_env *env) {
     if (!env) return AIE_OK;
     aie::be::destroy(env);
+    delete env->pool;
     delete env;
     return AIE_OK;
 }
@@ -186,6 +192,46 @@ int aie_step_host(aie_env *env, const int32_t *act_a, const int32_t *act_p, cons
             if (rc != AIE_OK) return rc;
         }
     return aie::be::sync(env, stream);
+}
+
+int32_t aie_compact_bytes_per_env(const aie_env *env) { return env ? aie::compact_layout(env->cfg).bytes : 0; }
+
+int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act_p, const aie_host_out *o, int32_t n_threads,
+                          void *stream) {
+    if (!env || !act_a || !o) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_host_compact: bind buffers and load state first");
+    const aie::DevCfg &c = env->cfg;
+    const size_t E = env->n_envs;
+    int rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * c.A * c.n_act_a * 4, stream);
+    if (rc != AIE_OK) return rc;
+    if (c.n_act_p > 0) {
+        if (!act_p) return fail(AIE_EINVAL, "aie_step_host_compact: planner actions required");
+        rc = aie::be::upload(env, (void *)env->bufs.act_p, act_p, E * c.n_act_p * 4, stream);
+        if (rc != AIE_OK) return rc;
+    }
+    rc = aie_step(env, stream);
+    if (rc != AIE_OK) return rc;
+    const aie::CompactLayout L = aie::compact_layout(c);
+    uint8_t *dev = nullptr, *host = nullptr;
+    rc = aie::be::compact_buffers(env, E * (size_t)L.bytes, &dev, &host);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::launch_pack(env, L, dev, stream);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::download(env, host, dev, E * (size_t)L.bytes, stream);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::sync(env, stream);
+    if (rc != AIE_OK) return rc;
+    int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    if (!env->pool || env->pool->size() != want - 1) { delete env->pool; env->pool = new aie::HostPool(want - 1); }
+    const aie_host_out out = *o;
+    const int chunk = 64, n_chunks = (int)((E + chunk - 1) / chunk);   // envs per work item
+    env->pool->run(n_chunks, [&](int k) {
+        const size_t hi = (size_t)(k + 1) * chunk < E ? (size_t)(k + 1) * chunk : E;
+        for (size_t e = (size_t)k * chunk; e < hi; e++) aie::expand_env(L, host + e * (size_t)L.bytes, e, out);
+    });
+    return AIE_OK;
 }
 
 int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out) {

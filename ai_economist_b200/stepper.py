@@ -148,12 +148,20 @@ class BatchStepper:
         """Device-side random policy: one uniformly random unmasked action per agent/subspace."""
         self._check(self.lib.aie_sample_random_actions(self._h, C.c_uint64(int(seed)), self._stream()))
 
-    def step_host(self, actions_agent, actions_planner, out_ptrs):
-        """End-to-end step with HOST buffers (aie_step_host).  out_ptrs: dict name -> host pointer / None."""
+    def step_host(self, actions_agent, actions_planner, out_ptrs, compact=False, n_threads=0):
+        """End-to-end step with HOST buffers (aie_step_host).  out_ptrs: dict name -> host pointer / None.
+        compact=True: same bytes in the host tensors, bit- / byte-packed over PCIe (aie_step_host_compact)."""
         o = _abi.AieHostOut()
         for name in _abi._OUT_NAMES:
             setattr(o, name, out_ptrs.get(name))
-        self._check(self.lib.aie_step_host(self._h, actions_agent, actions_planner, C.byref(o), self._stream()))
+        if compact:
+            self._check(self.lib.aie_step_host_compact(self._h, actions_agent, actions_planner, C.byref(o),
+                                                       int(n_threads), self._stream()))
+        else:
+            self._check(self.lib.aie_step_host(self._h, actions_agent, actions_planner, C.byref(o), self._stream()))
+
+    def compact_bytes_per_env(self):
+        return int(self.lib.aie_compact_bytes_per_env(self._h))
 
     def launch_count(self):
         return int(self.lib.aie_launch_count(self._h))

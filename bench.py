@@ -387,6 +387,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-mode", choices=["plain", "compact"], default="plain",
+                    help="transfer format of the e2e leg: plain D2H copies, or the compacted transfer (aie_step_host_compact)")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads expanding the compacted transfer (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -524,8 +527,9 @@ def main():
             act_p.copy_(torch.from_numpy(bu.sample_from_masks(out_host["mask_planner"].numpy(), seg_p, rng)))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        st.step_host(C.c_void_p(act_a.data_ptr()), C.c_void_p(act_p.data_ptr()) if d.n_act_planner else None, out_ptrs)
-        dt = time.perf_counter() - t0  # aie_step_host synchronises the stream before returning
+        st.step_host(C.c_void_p(act_a.data_ptr()), C.c_void_p(act_p.data_ptr()) if d.n_act_planner else None, out_ptrs,
+                     compact=(args.e2e_mode == "compact"), n_threads=args.e2e_threads)
+        dt = time.perf_counter() - t0  # aie_step_host[_compact] synchronises the stream before returning
         if i >= 2:
             e2e_s += dt
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -548,9 +552,15 @@ def main():
                          "%.0f MB of state" % (E * obs_bytes / 1e6, E * d.state_bytes / 1e6),
                    "auto_reset": True, "setup_s": t_setup},
         "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "what": "aie_step_host: pinned host actions in, every observation/mask/reward/done "
-                                        "tensor copied back to pinned host memory each step (PCIe-bound)"},
+        "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                 "steps": n_e2e, "what": "aie_step_host: pinned host actions in, every observation/mask/reward/done "
+                                         "tensor copied back to pinned host memory each step (PCIe-bound)"}
+                if args.e2e_mode == "plain" else
+                {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": E * st.compact_bytes_per_env(), "host_tensor_bytes_per_step": d2h, "steps": n_e2e,
+                 "what": "aie_step_host_compact: pinned host actions in; every observation/mask/reward/done tensor "
+                         "lands in pinned host memory each step, bit-/byte-packed over PCIe and expanded by host "
+                         "threads (same bytes as the plain path)"}),
         "gpu_launches": launches,
         "roofline": roofline,
     }

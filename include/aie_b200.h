@@ -299,6 +299,17 @@ int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream);
 int aie_step_host(aie_env *env, const int32_t *actions_agent_host, const int32_t *actions_planner_host,
                   const aie_host_out *out, void *stream);
 
+/* ABI 3.  Same contract as aie_step_host - the caller's host tensors receive exactly the same bytes - with a compacted
+ * device->host transfer: the 0/1-valued float planes (maps, masks) cross PCIe as bits and the int16 index planes as
+ * bytes.  A pack kernel rewrites each env's outputs into a library-owned compact device buffer, one D2H copy moves it
+ * into a library-owned pinned host buffer, and n_threads host threads (<= 0: hardware concurrency, at most 64) expand it
+ * into the caller's tensors (a transfer format: no simulation work runs on the host).  c2: 5.5 KB instead of 36 KB
+ * per env-step over PCIe.  Synchronous. */
+int aie_step_host_compact(aie_env *env, const int32_t *actions_agent, const int32_t *actions_planner,
+                          const aie_host_out *out, int32_t n_threads, void *stream);
+/* bytes one env contributes to the compacted transfer (0 on error) */
+int32_t aie_compact_bytes_per_env(const aie_env *env);
+
 /* Test/debug readback of env `e` (synchronous). */
 int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out);
 /* Same readback from the episode_final snapshot of env e (the record as it stood when its last finished episode

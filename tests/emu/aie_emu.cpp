@@ -17,11 +17,12 @@
 #include "../../ai_economist_b200/csrc/aie_core.cuh"
 #include "../../ai_economist_b200/csrc/aie_covid_core.cuh"
 #include "../../ai_economist_b200/csrc/aie_host.h"
+#include "../../ai_economist_b200/csrc/aie_compact.cuh"
 
 struct aie_env;
 struct aie_covid_env;
 namespace aie { namespace be {
-struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; };
+struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; std::vector<uint8_t> compact_dev, compact_host; };
 int init(aie_env *);
 void destroy(aie_env *);
 int upload(aie_env *, void *dst, const void *src, size_t n, void *stream);
@@ -33,6 +34,8 @@ int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, int emit_obs, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
+int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
+int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
 void *const_upload(const void *host, size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
@@ -50,6 +53,15 @@ int init(aie_env *env) {
     return AIE_OK;
 }
 void destroy(aie_env *) {}
+int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
+    if (env->be.compact_dev.size() < bytes) { env->be.compact_dev.assign(bytes, 0); env->be.compact_host.assign(bytes, 0); }
+    *dev = env->be.compact_dev.data(); *host = env->be.compact_host.data();
+    return AIE_OK;
+}
+int launch_pack(aie_env *env, const CompactLayout &L, uint8_t *dev, void *) {
+    for (int e = 0; e < env->n_envs; e++) pack_env(env->cfg, env->bufs, L, (size_t)e, dev + (size_t)e * L.bytes, 0);
+    return AIE_OK;
+}
 int upload(aie_env *, void *dst, const void *src, size_t n, void *) { if (dst != src) memcpy(dst, src, n); return AIE_OK; }
 int download(aie_env *, void *dst, const void *src, size_t n, void *) { if (dst != src) memcpy(dst, src, n); return AIE_OK; }
 int dev_copy(aie_env *, void *dst, const void *src, size_t n, void *) { memcpy(dst, src, n); return AIE_OK; }

@@ -1,0 +1,69 @@
+"""aie_step_host_compact: the caller's host tensors must receive exactly the bytes aie_step_host delivers, for every
+output tensor, whatever the layout (window / full observability, spatial planner or not, no p<i> vectors, odd sizes that
+do not fill a 32-bit word).  CPU: emulation build (same aie_abi.inl, pack / expand code and thread pool); GPU: CUDA."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ai_economist_b200 import _abi, foundation
+from oracle import configs
+from tests import batch_utils as bu
+
+CASES = ["c1_tutorial", "c3_paper_tax", "tax_us_federal", "full_obs_tax", "tax_single_planner"]
+
+
+def _env(cfg, n_envs, factory, device):
+    allc = dict(configs.CONFIGS)
+    allc.update(configs.EDGE_CONFIGS)
+    kw = dict(allc[cfg])
+    kw.pop("seed", None)
+    name = kw.pop("scenario_name")
+    extra = dict(stepper_factory=factory) if factory is not None else dict(device=device)
+    env = foundation.make_env_instance(name, n_envs=n_envs, auto_reset=True, seed=31, **kw, **extra)
+    env.reset()
+    return env
+
+
+def _host_outputs(st):
+    out, ptrs = {}, {}
+    for nm in _abi._OUT_NAMES:
+        if nm in st.buf and int(np.prod(st.buf[nm].shape)) > 0:
+            a = np.full(tuple(st.buf[nm].shape), 77, dtype=st.to_numpy(st.buf[nm][:1]).dtype)   # poisoned
+            out[nm] = a
+            ptrs[nm] = a.ctypes.data_as(C.c_void_p)
+    return out, ptrs
+
+
+def _check(cfg, n_envs, factory=None, device=None, threads=(1, 3, 0)):
+    plain, compact = _env(cfg, n_envs, factory, device), _env(cfg, n_envs, factory, device)
+    sp, sc = plain.stepper, compact.stepper
+    assert 0 < sc.compact_bytes_per_env() < sum(int(np.prod(sp.buf[n].shape[1:])) * sp.to_numpy(sp.buf[n][:1]).itemsize
+                                                for n in _abi._OUT_NAMES if n in sp.buf)
+    seg_a, seg_p = bu.segments(plain.spec, "a"), bu.segments(plain.spec, "p")
+    rng = np.random.RandomState(2)
+    op, pp = _host_outputs(sp)
+    oc, pc = _host_outputs(sc)
+    for t in range(12):
+        aa = np.ascontiguousarray(bu.sample_from_masks(sp.to_numpy(sp.buf["mask_agent"]), seg_a, rng), np.int32)
+        ap = np.ascontiguousarray(bu.sample_from_masks(sp.to_numpy(sp.buf["mask_planner"]), seg_p, rng), np.int32) \
+            if seg_p else None
+        pa = aa.ctypes.data_as(C.c_void_p)
+        ppn = ap.ctypes.data_as(C.c_void_p) if ap is not None else None
+        sp.step_host(pa, ppn, pp)
+        sc.step_host(pa, ppn, pc, compact=True, n_threads=threads[t % len(threads)])
+        for nm in op:
+            assert np.array_equal(op[nm], oc[nm]), "%s step %d: %s differs" % (cfg, t, nm)
+            assert np.array_equal(op[nm], sp.to_numpy(sp.buf[nm])), nm      # and both equal the device tensors
+
+
+@pytest.mark.parametrize("cfg", CASES + ["full_obs_plain", "two_agents_w0", "nonsquare_33_agents"])
+def test_emulated_compact_transfer_delivers_the_same_bytes(cfg):
+    from tests.emu.emu_stepper import emu_factory
+    _check(cfg, 5, factory=emu_factory)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", CASES)
+def test_cuda_compact_transfer_delivers_the_same_bytes(cfg):
+    _check(cfg, 300, device="cuda:0")

@@ -23,3 +23,20 @@ except Exception as ex:
 PY
   done
 done
+# end-to-end leg: plain D2H copies vs the compacted transfer (same host bytes), default library
+unset AIE_LIB_PATH
+timeout 200 python -m pytest tests/test_compact_transfer.py -m gpu -x -q > gpurun_out/pytest_compact.log 2>&1; echo "compact parity rc=$? $(tail -1 gpurun_out/pytest_compact.log)"
+for mode in plain compact; do
+  for th in 0 16 64; do
+    [[ $mode == plain && $th != 0 ]] && continue
+    timeout 300 python bench.py --steps 50 --warmup 10 --no-cpu-baseline --e2e-steps 20 --e2e-mode $mode --e2e-threads $th > gpurun_out/bench_e2e_${mode}_$th.json 2> gpurun_out/bench_e2e_${mode}_$th.err
+    python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_e2e_${mode}_$th.json"))
+    print("e2e $mode threads=$th: %.4e agent-env-steps/s, d2h %.1f MB/step" % (d["e2e"]["value"], d["e2e"]["d2h_bytes_per_step"] / 1e6))
+except Exception as ex:
+    print("e2e $mode $th FAILED", ex)
+PY
+  done
+done
