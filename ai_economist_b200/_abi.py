@@ -122,7 +122,7 @@ _COVID_BUF_NAMES = ["state", "ints", "hdr", "ring", "actions_agent", "actions_pl
 
 
 class AieCovidBuffers(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in _COVID_BUF_NAMES]
+    _fields_ = [(n, C.c_void_p) for n in _COVID_BUF_NAMES] + [("changes", C.c_void_p)]
 
 
 class AieError(RuntimeError):

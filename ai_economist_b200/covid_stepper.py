@@ -70,7 +70,13 @@ def covid_config_from_params(p, auto_reset=True):
 class CovidStepperBase:
     _DT = {"f32": np.float32, "f64": np.float64, "i32": np.int32, "i8": np.int8}
 
-    def __init__(self, params, n_envs, lib, device_index=0, auto_reset=True):
+    def __init__(self, params, n_envs, lib, device_index=0, auto_reset=True, change_list=None):
+        # change_list: keep a persistent per-state list of stringency changes (O(changes) unemployment response instead
+        # of a history scan).  Default off until it has been timed on a B200 (AIE_COVID_CHANGE_LIST=1 turns it on).
+        if change_list is None:
+            import os
+            change_list = os.environ.get("AIE_COVID_CHANGE_LIST", "0") not in ("", "0")
+        self.change_list = bool(change_list)
         self.p = params
         self.n_envs = int(n_envs)
         self.lib = lib
@@ -88,10 +94,13 @@ class CovidStepperBase:
             "mask_planner": ("f32", (E, 1 + params["num_subsidy_levels"])), "reward_agent": ("f32", (E, S)),
             "reward_planner": ("f64", (E,)), "done": ("i32", (E,)),
         }
+        if self.change_list:
+            shapes["changes"] = ("i32", (E, 33, S))
         self.buf = {k: self._alloc(shape, dt) for k, (dt, shape) in shapes.items()}
         bufs = _abi.AieCovidBuffers()
         for name in _abi._COVID_BUF_NAMES:
             setattr(bufs, name, self._ptr(self.buf[name]))
+        bufs.changes = self._ptr(self.buf["changes"]) if self.change_list else None
         self._check(lib.aie_covid_bind_buffers(self._h, C.byref(bufs)))
 
     def _check(self, rc):
@@ -141,7 +150,7 @@ class CovidStepperBase:
 
 
 class CudaCovidStepper(CovidStepperBase):
-    def __init__(self, params, n_envs, device="cuda:0", auto_reset=True, lib_path=None):
+    def __init__(self, params, n_envs, device="cuda:0", auto_reset=True, lib_path=None, change_list=None):
         import torch
 
         if not torch.cuda.is_available():
@@ -152,7 +161,7 @@ class CudaCovidStepper(CovidStepperBase):
         self.device = torch.device("cuda", idx)
         lib = _abi.load_library(lib_path)
         with torch.cuda.device(self.device):
-            super().__init__(params, n_envs, lib, device_index=idx, auto_reset=auto_reset)
+            super().__init__(params, n_envs, lib, device_index=idx, auto_reset=auto_reset, change_list=change_list)
 
     def _alloc(self, shape, dt):
         t = self.torch

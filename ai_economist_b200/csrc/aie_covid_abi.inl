@@ -99,6 +99,7 @@ int aie_covid_bind_buffers(aie_covid_env *env, const aie_covid_buffers *b) {
     d.o_state = b->obs_agent_state; d.o_post = b->obs_postsubsidy; d.o_lag = b->obs_lagged_stringency;
     d.o_pol = b->obs_policy_indicators; d.o_scal = b->obs_scalars; d.mask_a = b->mask_agent; d.mask_p = b->mask_planner;
     d.rew_a = b->reward_agent; d.rew_p = b->reward_planner; d.done = b->done;
+    d.chg = b->changes;   // optional
     env->bound = true;
     return AIE_OK;
 }

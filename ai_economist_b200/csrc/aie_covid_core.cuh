@@ -46,7 +46,14 @@ struct CovidBufs {
     float *o_state, *o_post, *o_lag, *o_pol, *o_scal, *mask_a, *mask_p, *rew_a;
     double *rew_p;
     int32_t *done;
+    // optional persistent per-state list of the stringency changes inside the history window (NULL: scan the history):
+    // uint32 [E][CV_LIST_CAP + 1][S], entry-major so that an env's S threads read coalesced.  Row 0 = head | count << 8
+    // (count 255: the list overflowed, this state scans its history again); rows 1.. = ring of
+    // (day the newer value was appended + 2^20) | (change + 128) << 24, oldest first.
+    uint32_t *chg;
 };
+constexpr int CV_LIST_CAP = 32;
+constexpr uint32_t CV_LIST_DAY0 = 1u << 20;
 
 enum { CVS_S = 0, CVS_I, CVS_R, CVS_D, CVS_V, CVS_U, CVS_STRG, CVS_SUBSIDY, CVS_POST, CVS_FIELDS = 9 };
 enum { CVH_T = 0, CVH_SUBSIDY_LEVEL, CVH_RING_HEAD, CVH_EPISODES };
@@ -150,6 +157,19 @@ CV_DEV void covid_reset_env(const CovidCfg &c, int e, const CovidBufs &b, int ti
             ring[(size_t)a * cv_ring_row(L1) + k] = day < 0 ? (int8_t)1 : c.rw_policy[(size_t)day * S + a];
         }
         if (!keep_outputs) b.rew_a[(size_t)e * S + a] = 0.0f;
+        if (b.chg) {  // the changes already inside the initial window; pair (k, k + 1) reaches index k - t at step t
+            uint32_t *col = b.chg + (size_t)e * (CV_LIST_CAP + 1) * S + a;
+            const int8_t *row = ring + (size_t)a * cv_ring_row(L1);
+            int cnt = 0;
+            for (int k = 0; k < c.L && cnt != 255; k++) {
+                const int d = (int)row[k + 1] - (int)row[k];
+                if (d == 0) continue;
+                if (cnt == CV_LIST_CAP) { cnt = 255; break; }
+                col[(size_t)(1 + cnt) * S] = (uint32_t)((int)CV_LIST_DAY0 + k - (c.L - 1)) | ((uint32_t)(d + 128) << 24);
+                cnt++;
+            }
+            col[0] = (uint32_t)cnt << 8;
+        }
     }
     cv_bsync();
     if (tid == 0) {
@@ -200,7 +220,8 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
         // ControlUSStateOpenCloseStatus (covid19_components.py:180-221)
         int action = b.act_a[(size_t)e * S + a];
         if (action < 0 || action > c.levels) action = 0;
-        const float strg = st[CVS_STRG * S + a] * (action == 0 ? 1.0f : 0.0f) + (float)action;
+        const float strg_prev = st[CVS_STRG * S + a];   // == the newest history entry
+        const float strg = strg_prev * (action == 0 ? 1.0f : 0.0f) + (float)action;
         st[CVS_STRG * S + a] = strg;
         if (t == ints[a] + 1) ints[a] += (action == 0) ? 1 : c.cooldown;
         // subsidy for this state (f64 product stored into the float32 series)
@@ -230,7 +251,46 @@ CV_DEV void covid_step_env(const CovidCfg &c, int e, const CovidBufs &b, float *
         // The row is scanned in PHYSICAL order with 16-byte loads; the pair (p, p+1 mod L1) is the stringency change
         // at logical index k = (p - new_head) mod L1, and k == L is the seam between newest and oldest (skipped).
         double acc = 0.0;
-        {
+        bool scan = true;
+        if (b.chg) {
+            // Persistent change list: a change appended on day tc sits at window index L - 1 - (t - tc); entries leave
+            // at the front when that index drops below 0.  Same (index, change) pairs as the scan finds, accumulated
+            // oldest first.  O(changes) instead of O(filter_len) per state and step.
+            uint32_t *col = b.chg + (size_t)e * (CV_LIST_CAP + 1) * S + a;
+            const uint32_t hd = col[0];
+            int lhead = (int)(hd & 0xFFu), cnt = (int)((hd >> 8) & 0xFFu);
+            if (cnt != 255) {
+                const int d_new = (int)strg - (int)strg_prev;
+                if (d_new != 0) {
+                    if (cnt == CV_LIST_CAP) cnt = 255;
+                    else {
+                        int slot = lhead + cnt; if (slot >= CV_LIST_CAP) slot -= CV_LIST_CAP;
+                        col[(size_t)(1 + slot) * S] = (CV_LIST_DAY0 + (uint32_t)t) | ((uint32_t)(d_new + 128) << 24);
+                        cnt++;
+                    }
+                }
+            }
+            if (cnt != 255) {
+                uint32_t *my_chg = chg + (size_t)tid * CV_CHG_CAP;
+                double wf[8];
+                for (int f = 0; f < 8; f++) wf[f] = f < F ? (double)c.conv_w[a * F + f] : 0.0;
+                int n_chg = 0, drop = 0;
+                for (int i = 0; i < cnt; i++) {
+                    int slot = lhead + i; if (slot >= CV_LIST_CAP) slot -= CV_LIST_CAP;
+                    const uint32_t en = col[(size_t)(1 + slot) * S];
+                    const int tc = (int)(en & 0xFFFFFFu) - (int)CV_LIST_DAY0, d = (int)(en >> 24) - 128;
+                    const int k = L - 1 - (t - tc);
+                    if (k < 0) { drop++; continue; }   // (oldest first: only leading entries can have left the window)
+                    my_chg[n_chg++] = (uint32_t)k | ((uint32_t)(d + 128) << 16);
+                }
+                acc = cv_accumulate_changes(c, my_chg, n_chg, wf, 0.0);
+                lhead += drop; if (lhead >= CV_LIST_CAP) lhead -= CV_LIST_CAP;
+                cnt -= drop;
+                scan = false;
+            }
+            col[0] = (uint32_t)lhead | ((uint32_t)cnt << 8);
+        }
+        if (scan) {
             const int8_t *row = ring + (size_t)a * cv_ring_row(L1);
             int prev = row[L1 - 1];                       // predecessor of physical column 0
             uint32_t *my_chg = chg + (size_t)tid * CV_CHG_CAP;

@@ -379,6 +379,10 @@ typedef struct aie_covid_buffers {
     float *reward_agent;            /* [E, S] */
     double *reward_planner;         /* [E] */
     int32_t *done;                  /* [E] */
+    uint32_t *changes;              /* optional (may be NULL), ABI 3: uint32 [E, 33, S] scratch state owned by the kernels -
+                                       per-state list of the stringency changes inside the filter window, so that the
+                                       unemployment response costs O(changes) instead of a scan of the filter_len-day
+                                       history (covid19_env.py:1374-1441) per state and step */
 } aie_covid_buffers;
 
 typedef struct aie_covid_env aie_covid_env;

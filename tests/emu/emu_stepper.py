@@ -64,7 +64,7 @@ def emu_factory(spec, n_envs, auto_reset, event_envs=0):
 class EmuCovidStepper:
     """COVID-19 scenario through the emulated device code (numpy buffers)."""
 
-    def __new__(cls, params, n_envs, auto_reset=False):
+    def __new__(cls, params, n_envs, auto_reset=False, change_list=None):
         from ai_economist_b200.covid_stepper import CovidStepperBase
 
         class _Emu(CovidStepperBase):
@@ -77,4 +77,4 @@ class EmuCovidStepper:
             def to_numpy(self, buf):
                 return np.array(buf)
 
-        return _Emu(params, n_envs, emu_lib(), auto_reset=auto_reset)
+        return _Emu(params, n_envs, emu_lib(), auto_reset=auto_reset, change_list=change_list)

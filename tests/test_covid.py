@@ -63,10 +63,11 @@ def _drive(stepper, e=0):
     return step, (lambda: stepper.read_obs(e))
 
 
-def test_covid_emulated_device_code_matches_reference_golden_trace():
+@pytest.mark.parametrize("change_list", [False, True], ids=["scan", "change_list"])
+def test_covid_emulated_device_code_matches_reference_golden_trace(change_list):
     from tests.emu.emu_stepper import EmuCovidStepper
     z, meta, p = load()
-    s = EmuCovidStepper(p, 2)
+    s = EmuCovidStepper(p, 2, change_list=change_list)
     s.reset()
     step, obs = _drive(s, e=1)
     replay(step, obs, z, meta["n_steps"], "emu")
@@ -75,12 +76,50 @@ def test_covid_emulated_device_code_matches_reference_golden_trace():
     assert np.array_equal(st["stringency"], z["st_stringency"][-1])
 
 
-def test_covid_emulated_auto_reset_starts_a_fresh_episode():
+@pytest.mark.parametrize("cooldown,steps", [(None, 130), (1, 90)], ids=["default_cooldown", "cooldown_1_overflows_the_list"])
+def test_covid_emulated_change_list_equals_history_scan(cooldown, steps):
+    """The O(changes) unemployment response against the O(filter_len) scan under random policies, across an auto-reset;
+    with a 1-day cooldown the 32-entry lists overflow and those states fall back to scanning."""
+    from tests.emu.emu_stepper import EmuCovidStepper
+    from ai_economist_b200 import foundation
+    from oracle.gen_golden_covid import COVID_KWARGS, reference_config
+    cfg = reference_config(COVID_KWARGS)
+    name = cfg.pop("scenario_name")
+    cfg["episode_length"] = 60
+    if cooldown is not None:
+        pairs = [list(c.items())[0] if isinstance(c, dict) else tuple(c) for c in cfg["components"]]
+        cfg["components"] = [(n, dict(k, action_cooldown_period=cooldown) if n == "ControlUSStateOpenCloseStatus" else k)
+                             for n, k in pairs]
+    envs = [foundation.make_env_instance(name, n_envs=2, auto_reset=True,
+                                         stepper_factory=lambda params, n, ar, cl=cl: EmuCovidStepper(params, n, ar, change_list=cl),
+                                         **cfg) for cl in (False, True)]
+    a, b = envs[0].stepper, envs[1].stepper
+    a.reset(); b.reset()
+    rng = np.random.RandomState(5)
+    for t in range(steps):
+        ma, mp = a.to_numpy(a.buf["mask_agent"]), a.to_numpy(a.buf["mask_planner"])
+        aa = np.argmax(ma * (rng.random_sample(ma.shape) + 1e-3), axis=1).astype(np.int32)
+        ap = np.argmax(mp * (rng.random_sample(mp.shape) + 1e-3), axis=1).astype(np.int32)
+        for s in (a, b):
+            s.buf["actions_agent"][...] = aa
+            s.buf["actions_planner"][...] = ap
+            s.step()
+        for e in range(2):
+            oa, ob = a.read_obs(e), b.read_obs(e)
+            for k in OBS_KEYS + ["rew_a"]:
+                assert np.allclose(oa[k], ob[k], rtol=RTOL, atol=ATOL), (t, e, k)
+            assert np.isclose(float(oa["rew_p"]), float(ob["rew_p"]), rtol=RTOL, atol=ATOL) and int(oa["done"]) == int(ob["done"])
+    counts = (b.buf["changes"][:, 0, :] >> 8) & 0xFF
+    assert (counts == 255).any() == (cooldown == 1), counts.max()
+
+
+@pytest.mark.parametrize("change_list", [False, True], ids=["scan", "change_list"])
+def test_covid_emulated_auto_reset_starts_a_fresh_episode(change_list):
     from tests.emu.emu_stepper import EmuCovidStepper
     z, meta, _ = load()
     kw = dict(meta["kwargs"], episode_length=12)
     p = build_covid_params(**kw)
-    s = EmuCovidStepper(p, 1, auto_reset=True)
+    s = EmuCovidStepper(p, 1, auto_reset=True, change_list=change_list)
     s.reset()
     first = s.read_obs(0)
     step, obs = _drive(s)
@@ -93,22 +132,24 @@ def test_covid_emulated_auto_reset_starts_a_fresh_episode():
 
 
 @pytest.mark.gpu
-def test_covid_cuda_matches_reference_golden_trace():
+@pytest.mark.parametrize("change_list", [False, True], ids=["scan", "change_list"])
+def test_covid_cuda_matches_reference_golden_trace(change_list):
     from ai_economist_b200.covid_stepper import CudaCovidStepper
     z, meta, p = load()
-    s = CudaCovidStepper(p, 3, auto_reset=False)
+    s = CudaCovidStepper(p, 3, auto_reset=False, change_list=change_list)
     s.reset()
     step, obs = _drive(s, e=2)
     replay(step, obs, z, meta["n_steps"], "cuda")
 
 
 @pytest.mark.gpu
-def test_covid_cuda_batch_matches_numpy_oracle():
+@pytest.mark.parametrize("change_list", [False, True], ids=["scan", "change_list"])
+def test_covid_cuda_batch_matches_numpy_oracle(change_list):
     import torch
     from ai_economist_b200.covid_stepper import CudaCovidStepper
     z, meta, p = load()
     E, steps = 12, 200
-    s = CudaCovidStepper(p, E, auto_reset=False)
+    s = CudaCovidStepper(p, E, auto_reset=False, change_list=change_list)
     s.reset()
     envs = [CovidOracleEnv(p) for _ in range(E)]
     rng = np.random.RandomState(11)

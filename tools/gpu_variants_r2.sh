@@ -40,3 +40,16 @@ except Exception as ex:
 PY
   done
 done
+# COVID (c4): history scan vs the persistent change list
+timeout 300 python -m pytest tests/test_covid.py -m gpu -x -q > gpurun_out/pytest_covid.log 2>&1; echo "covid parity rc=$? $(tail -1 gpurun_out/pytest_covid.log)"
+for cl in 0 1; do
+  AIE_COVID_CHANGE_LIST=$cl timeout 300 python bench.py --workload c4 --steps 300 --warmup 20 --no-cpu-baseline --e2e-steps 3 > gpurun_out/bench_c4_cl$cl.json 2> gpurun_out/bench_c4_cl$cl.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_c4_cl$cl.json"))
+    print("c4 change_list=$cl value %.4e ms/step %.4f frac %.3f" % (d["value"], d["ms_per_step"], d["roofline"]["frac"]))
+except Exception as ex:
+    print("c4 change_list=$cl FAILED", ex)
+PY
+done
