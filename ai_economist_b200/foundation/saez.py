@@ -138,7 +138,7 @@ class SaezBatch:
     replica axis (sample buffers [E, 500, 2] kept in arrival order, masked sums for the regression, one bincount for the
     histograms, the cumulative / interpolation recurrences run over the 101 bins with vector state).  Agrees with the
     per-replica estimator to float64 rounding of the reordered sums (tests/test_saez_batch.py: <= 1e-10 relative); at
-    8 192 replicas a tax period costs tens of milliseconds instead of about a second."""
+    8 192 replicas a tax period costs 0.55 s instead of 4.8 s in the build container."""
 
     def __init__(self, n, cutoffs, rate_min, rate_max, pareto_weight_type="inverse_income", fixed_elas=None):
         one = SaezEstimator(cutoffs, rate_min, rate_max, pareto_weight_type, fixed_elas)
@@ -254,9 +254,13 @@ class SaezBatch:
         out[:, -1] = bin_rates[:, -1]
         return out
 
+    CHUNK = 256   # replicas per pass: keeps the [chunk, 500] temporaries inside the CPU caches
+
     def new_period_rates(self, rows):
         """Rates [R, B] of the replicas in `rows` (all with a full buffer); updates their smoothed state."""
         rows = np.asarray(rows, np.int64)
+        if len(rows) > self.CHUNK:
+            return np.concatenate([self.new_period_rates(rows[i:i + self.CHUNK]) for i in range(0, len(rows), self.CHUNK)])
         data = self._data(rows)
         self.elas_tm1[rows], self.log_z0_tm1[rows] = self.elas_t[rows], self.log_z0_t[rows]
         elas_t, log_z0_t = self._elasticity(rows, data)
