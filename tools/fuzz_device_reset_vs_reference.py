@@ -1,0 +1,93 @@
+"""Randomised multi-episode fuzz (build container only): the device-side reference-exact reset (auto_reset, 1-lane
+emulation of the device source) against the LIVE reference, which calls env.reset() between episodes on one continuing
+global numpy stream.  layout_from_file configurations with skill_dist in {none, pareto}, with / without
+fixed_four_skill_and_loc.   python tools/fuzz_device_reset_vs_reference.py [n] [seed]"""
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ai_economist_b200 import foundation  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+from tests.emu.emu_stepper import emu_factory  # noqa: E402
+
+LAYOUTS = {(15, 15): "env-pure_and_mixed-15x15.txt", (25, 25): "quadrant_25x25_20each_30clump.txt",
+           (40, 40): "quadrant_40x40_50each.txt"}
+
+
+def random_config(rng):
+    size = list(LAYOUTS)[rng.randint(len(LAYOUTS))]
+    fixed_four = bool(rng.rand() < 0.4)
+    A = int(rng.choice([2, 3, 4, 6, 9, 12]))
+    comps = [("Build", dict(skill_dist="pareto" if fixed_four else str(rng.choice(["none", "pareto"])),
+                            payment_max_skill_multiplier=int(rng.randint(1, 4)))),
+             ("ContinuousDoubleAuction", dict(max_num_orders=int(rng.choice([1, 3, 5])), order_duration=int(rng.choice([2, 50])))),
+             ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto"]))))]
+    if rng.rand() < 0.5:
+        comps.append(("PeriodicBracketTax", dict(period=int(rng.choice([3, 10])), bracket_spacing="us-federal",
+                                                 tax_model=str(rng.choice(["model_wrapper", "us-federal-single-filer-2018-scaled"])))))
+    return dict(scenario_name="layout_from_file/simple_wood_and_stone", components=comps, n_agents=A,
+                world_size=list(size), env_layout_file=LAYOUTS[size], episode_length=int(rng.choice([8, 15, 30])),
+                fixed_four_skill_and_loc=fixed_four, starting_agent_coin=float(rng.choice([0, 10])),
+                multi_action_mode_agents=bool(rng.rand() < 0.3), multi_action_mode_planner=True,
+                flatten_observations=True, flatten_masks=True,
+                energy_warmup_constant=float(rng.choice([0, 4])), energy_warmup_method="decay")
+
+
+def run_one(cfg, seed, episodes=4):
+    f = rh.load_reference_foundation()
+    ref = f.make_env_instance(**cfg)
+    ref.seed(seed)
+    obs = ref.reset()
+    kw = dict(cfg)
+    name = kw.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=2, stepper_factory=emu_factory, auto_reset=True, **kw)
+    assert env.spec["reset_mode"] == 1
+    env.seed([seed, seed])
+    env.reset()
+    s = env.stepper
+    arng = np.random.RandomState(seed + 1)
+    T = cfg["episode_length"]
+
+    def compare(label):
+        ro = rh.obs_arrays_from_reference(ref, obs)
+        rs = rh.state_arrays_from_reference(ref)
+        po, ps = s.read_obs(1), s.read_state(1)
+        for k in ["cell", "owner", "loc", "inv", "esc", "mt_key", "mt_pos", "n_orders"]:
+            if k in rs:
+                assert np.array_equal(rs[k], np.asarray(ps[k]).reshape(np.asarray(rs[k]).shape)), "%s: state %s" % (label, k)
+        for k in ["coin", "labor"]:
+            assert np.allclose(rs[k], ps[k], rtol=1e-9, atol=1e-9), "%s: state %s" % (label, k)
+        for k in ["a_map", "a_idx", "a_mask", "p_mask"]:
+            assert np.array_equal(ro[k], np.asarray(po[k]).reshape(ro[k].shape)), "%s: obs %s" % (label, k)
+        for k in ["a_flat", "p_flat", "p_agents"]:
+            assert np.allclose(ro[k], np.asarray(po[k]).reshape(ro[k].shape), rtol=1e-6, atol=1e-7), "%s: obs %s" % (label, k)
+
+    compare("reset")
+    for t in range(1, episodes * T + 1):
+        actions, a_act, p_act = rh.sample_actions(ref, obs, arng)
+        obs, rew, done, _ = ref.step(actions)
+        env.step((np.repeat(a_act[None], 2, axis=0), np.repeat(p_act[None], 2, axis=0) if p_act.size else None))
+        got_rew = s.to_numpy(s.buf["reward"])[1]
+        want_rew = np.array([rew[str(i)] for i in range(ref.n_agents)] + [rew["p"]])
+        assert np.allclose(want_rew, got_rew, rtol=1e-6, atol=1e-9), "t=%d rewards" % t
+        if done["__all__"]:
+            obs = ref.reset()
+        compare("t=%d%s" % (t, " (after reset)" if done["__all__"] else ""))
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+    rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    bad = 0
+    for i in range(n):
+        cfg = random_config(rng)
+        try:
+            run_one(cfg, seed=500 + i)
+        except Exception as ex:  # noqa: BLE001
+            bad += 1
+            print("[%d] FAILED %r\n    %s" % (i, cfg, "".join(traceback.format_exception_only(type(ex), ex)).strip()[:500]))
+    print("%d configs x 4 episodes, %d failures" % (n, bad))
