@@ -213,6 +213,10 @@ class ReferenceApiEnv:
     def __getattr__(self, name):           # get_agent, n_agents, episode_length, world, metrics, dense logs, seed ...
         return getattr(self._env, name)
 
+    @property
+    def _completions(self):                # int, like the reference's (tutorials/rllib/env_wrapper.py:176 reads it)
+        return int(self._env.completions()[self._e])
+
     # ---- output conversion -------------------------------------------------------------------------------
     def _np(self, v):
         st = self._env.stepper

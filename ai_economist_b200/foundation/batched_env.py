@@ -300,8 +300,7 @@ class BatchedFoundationEnv:
         if self._loaded and "episode_final" not in self._stepper.buf:
             self._last_ep_metrics_host = self.metrics_of(0)   # base_env.py:893-896: reset() stores the old episode's metrics
         if self._loaded and self._rs is not None:
-            self._completions = self._stepper.to_numpy(self._stepper.state_view("completions")).astype(np.int64) \
-                if hasattr(self._stepper, "state_view") else self._completions
+            self._completions = self.completions()
             self._sync_streams_from_device()
         saez_n = self._saez.before_host_reset() if self._saez is not None else None
         self._stepper.load_state(self.host_reset_arrays())
@@ -310,6 +309,16 @@ class BatchedFoundationEnv:
             self._saez.after_host_reset(saez_n)
         self._start_dense_log(force_dense_logging, int(self._completions[0]))
         return self.obs
+
+    def completions(self):
+        """Completed episodes per replica (BaseEnvironment._completions, base_env.py:1021-1025: incremented on the step
+        that ends an episode).  The device counts an episode when it auto-resets it; a finished episode still waiting
+        for an explicit reset() (auto_reset off) is added here."""
+        st = self._stepper
+        if not self._loaded or not hasattr(st, "state_view"):
+            return self._completions
+        done_waiting = st.to_numpy(st.state_view("t")).astype(np.int64) >= self._episode_length
+        return st.to_numpy(st.state_view("completions")).astype(np.int64) + done_waiting
 
     # ------------------------------------------------------------------ dense logs (base_env.py:440-452, 763-814)
     @property

@@ -96,11 +96,14 @@ def test_cuda_previous_episode_metrics_match_reference(path):
     _replay_previous_episode_metrics(path, None)
 
 
-def test_emulated_saez_with_explicit_host_resets_matches_reference():
-    """Saez model, auto_reset off: env.reset() between episodes goes through the host reset path, which has to carry
-    the estimator's persistent state (sample counter, rates in force / observed) across the repacked records."""
+@pytest.mark.parametrize("which", ["saez", "c3_reset", "c1_reset"])
+def test_emulated_explicit_host_resets_match_reference(which):
+    """auto_reset off: env.reset() between episodes goes through the host reset path.  It has to carry the Saez
+    estimator's persistent state (sample counter, rates in force / observed) across the repacked records, and the
+    completed-episode count that drives the tax-annealing and energy-warm-up schedules (c3_reset; base_env.py:1021-1025
+    increments it on the step that ends the episode)."""
     from tests.emu.emu_stepper import emu_factory
-    path = [p for p in FILES if "saez" in p][0]
+    path = [p for p in FILES if which in p][0]
     z, meta, init = gu.load_fixture(path)
     kw = dict(meta["reference_kwargs"])
     name = kw.pop("scenario_name")
@@ -113,6 +116,8 @@ def test_emulated_saez_with_explicit_host_resets_matches_reference():
     A = env.n_agents
     for t in range(1, int(meta["n_steps"]) + 1):
         acts = {str(i): z["act_a"][t - 1][i][None] for i in range(A)}
+        if z["act_p"].shape[1]:
+            acts["p"] = z["act_p"][t - 1][None]
         env.step(acts)
         last = s.read_obs(0)
         if int(z["step_done"][t]):

@@ -61,6 +61,7 @@ def test_tutorial_loop_runs_unchanged_on_the_reference_api():
     assert obs["0"]["world-map"].shape == (7, 11, 11) and obs["0"]["action_mask"].shape == (50,)
     assert set(obs["p"]["p0"].keys()) == {"world-inventory-Coin", "world-inventory-Stone", "world-inventory-Wood",
                                           "world-loc-row", "world-loc-col"}
+    assert env._completions == 1 and isinstance(env._completions, int)   # counted on the step that ended the episode
     log = env.previous_episode_dense_log
     assert len(log["states"]) == 61 and len(log["actions"]) == 60 and set(log) >= {"world", "Build", "Gather", "Trade"}
     env.reset()
