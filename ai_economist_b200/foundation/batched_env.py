@@ -303,7 +303,19 @@ class BatchedFoundationEnv:
             self._completions = self.completions()
             self._sync_streams_from_device()
         saez_n = self._saez.before_host_reset() if self._saez is not None else None
+        # the "auto" energy warm-up integrator survives resets in the reference (layout_from_file.py:153, 557: only the
+        # constructor zeroes it); a host reset repacks the records, so carry it over
+        warm = None
+        if self._loaded and hasattr(self._stepper, "state_view"):
+            warm = self._stepper.to_numpy(self._stepper.state_view("auto_warmup")).copy()
         self._stepper.load_state(self.host_reset_arrays())
+        if warm is not None and warm.any():
+            v = self._stepper.state_view("auto_warmup")
+            if isinstance(v, np.ndarray):
+                v[...] = warm
+            else:
+                import torch
+                v.copy_(torch.as_tensor(warm, device=v.device, dtype=v.dtype))
         self._loaded = True
         if self._saez is not None:
             self._saez.after_host_reset(saez_n)

@@ -72,7 +72,11 @@ def test_tutorial_loop_runs_unchanged_on_the_reference_api():
 @pytest.mark.reference
 @pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
 @pytest.mark.parametrize("flags", [dict(flatten_observations=False, flatten_masks=True),
-                                   dict(flatten_observations=True, flatten_masks=True)])
+                                   dict(flatten_observations=True, flatten_masks=True),
+                                   # schedules that live across resets: the "auto" warm-up integrator, completions
+                                   dict(energy_warmup_constant=3, energy_warmup_method="auto", episode_length=30),
+                                   dict(energy_warmup_constant=2, energy_warmup_method="decay", episode_length=30)],
+                         ids=["named_fields", "flat", "auto_warmup", "decay_warmup"])
 def test_reference_api_tracks_the_live_reference(flags):
     """Same config, same seed, same caller code on both: identical observation structure and values, two episodes."""
     cfg = dict(ENV_CONFIG)
@@ -92,7 +96,7 @@ def test_reference_api_tracks_the_live_reference(flags):
             assert type(b) in (float, list, np.ndarray, bool), (label, type(b))
             assert np.allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=1e-6, atol=1e-7), label
 
-    for episode in range(2):
+    for episode in range(3):
         ra, rb = np.random.RandomState(episode), np.random.RandomState(episode)
         o1, o2 = ref.reset(), mine.reset()
         same(o1, o2, "reset %d" % episode)
