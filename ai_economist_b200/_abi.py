@@ -65,7 +65,7 @@ class AieBuffers(C.Structure):
 class AieHostState(C.Structure):
     _fields_ = [("n", C.c_int32)] + [(n, C.c_void_p) for n in [
         "stone", "wood", "stone_src", "wood_src", "water", "loc", "coin", "inv_stone", "inv_wood",
-        "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions"]]
+        "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions", "gauss_has", "gauss_val"]]
 
 
 _DUMP_PTRS = ["cell", "owner", "loc", "coin", "esc_coin", "labor", "inv", "esc", "n_orders", "bid_hist", "ask_hist",

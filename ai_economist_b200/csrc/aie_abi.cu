@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
             hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
         }
         __syncwarp();
-        if (c.reset_mode == 1) device_reset_env(c, rec, grec, scratch, lane);  // reference-exact placement / skills
+        if (c.reset_mode == 1) device_reset_env<EXT>(c, rec, grec, scratch, lane);  // reference-exact placement / skills
         finish_reset_env(c, rec, grec, scratch, lane);  // metric_0 under the new completions count
     }
 

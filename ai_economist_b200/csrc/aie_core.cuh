@@ -98,7 +98,7 @@ AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 struct Env {
     int32_t *hdr;
     double *coin, *esc_coin, *labor, *bpay, *bskill, *bonus, *last_coin, *last_income, *last_marg, *util_prev,
-        *price_hist, *stats, *saez;  // saez (Saez model only): [16] bracket rates, [16] running average, [16] observed rates
+        *price_hist, *stats, *gauss, *saez;  // gauss: numpy legacy_gauss cache {value, has}; saez (Saez model only): [16] bracket rates, [16] running average, [16] observed rates
     int32_t *inv, *esc;  // [A][2]
     int16_t *loc;        // [A][2]
     uint8_t *n_orders, *bid_hist, *ask_hist, *rate_idx, *cell;
@@ -116,6 +116,7 @@ AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     e.hdr = (int32_t *)rec;
     e.coin = (double *)(rec + c.off_coin);
     e.saez = (double *)(rec + c.off_saez);
+    e.gauss = (double *)(rec + c.off_gauss);
     e.stats = (double *)(big + c.off_stats);  // resident unless the config is split
     e.esc_coin = (double *)(rec + c.off_esc_coin);
     e.labor = (double *)(rec + c.off_labor);
@@ -967,6 +968,31 @@ AIE_DEV double rng_pareto(Rng &r, double a) {  // numpy legacy_pareto: exp(-log(
     const double e = -log(1.0 - rng_double(r));
     return exp(e / a) - 1.0;
 }
+// numpy's legacy_gauss (legacy-distributions.c): polar Box-Muller; the second variate of a pair is cached in the stream
+// state (here: the record's gauss section) and returned by the next call - across components, resets and episodes.
+AIE_DEV double rng_gauss(Rng &r, double *g) {   // warp-uniform call
+    if (g[1] != 0.0) {
+        const double cached = g[0];
+        wsync();
+        if (r.lane == 0) { g[0] = 0.0; g[1] = 0.0; }
+        wsync();
+        return cached;
+    }
+    double x1, x2, r2;
+    do {
+        x1 = 2.0 * rng_double(r) - 1.0;
+        x2 = 2.0 * rng_double(r) - 1.0;
+        r2 = x1 * x1 + x2 * x2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    const double f = sqrt(-2.0 * log(r2) / r2);
+    wsync();
+    if (r.lane == 0) { g[0] = f * x1; g[1] = 1.0; }
+    wsync();
+    return f * x2;
+}
+AIE_DEV double rng_lognormal(Rng &r, double *g, double mean, double sigma) { return exp(mean + sigma * rng_gauss(r, g)); }
+
+template <bool EXT>
 AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
     const int A = c.A, lane = r.lane;
     for (int a = 0; a < A; a++) {  // np.random.randint(0, H), randint(0, W) until the cell is free and not water
@@ -989,6 +1015,9 @@ AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, R
                 if (c.build_skill_dist == 1) {
                     skill = rng_pareto(r, 4.0);
                     rate = fmin((double)c.pmsm, (double)(c.pmsm - 1) * skill + 1.0);
+                } else if (EXT && c.build_skill_dist == 2) {   // build.py:243-245
+                    skill = rng_lognormal(r, e.gauss, -1.0, 0.5);
+                    rate = fmin((double)c.pmsm, (double)(c.pmsm - 1) * skill + 1.0);
                 }
                 if (lane == 0) { e.bpay[a] = rate * c.build_payment; e.bskill[a] = skill; }
             }
@@ -996,6 +1025,7 @@ AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, R
             for (int a = 0; a < A; a++) {
                 double bonus = 0.0;
                 if (c.gather_skill_dist == 1) bonus = fmin(2.0, rng_pareto(r, 3.0)) / 2.0;
+                else if (EXT && c.gather_skill_dist == 2) bonus = fmin(2.0, rng_lognormal(r, e.gauss, -2.022, 0.938)) / 2.0;  // move.py:204-205
                 if (lane == 0) e.bonus[a] = bonus;
             }
         }
@@ -1013,12 +1043,13 @@ AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, R
 }
 
 // What the step kernel does when an env finishes with auto_reset on and reset_mode == 1, after the snapshot restore.
+template <bool EXT = false>
 AIE_DEV_NOINLINE void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
     wsync();
-    device_reset_draws(c, e, s, r);
+    device_reset_draws<EXT>(c, e, s, r);
     if (lane == 0) e.hdr[HDR_MT_POS] = r.pos;
     wsync();
 }

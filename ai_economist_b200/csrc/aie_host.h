@@ -123,8 +123,8 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.reset_mode = u.reset_mode;
     if (c.reset_mode != 0 && c.reset_mode != 1) return bad("unknown reset_mode");
     c.build_skill_dist = u.build_skill_dist; c.gather_skill_dist = u.gather_skill_dist;
-    if (c.build_skill_dist < 0 || c.build_skill_dist > 1 || c.gather_skill_dist < 0 || c.gather_skill_dist > 1)
-        return bad("device-side reset supports skill_dist 'none' and 'pareto'");
+    if (c.build_skill_dist < 0 || c.build_skill_dist > 2 || c.gather_skill_dist < 0 || c.gather_skill_dist > 2)
+        return bad("device-side reset supports skill_dist 'none', 'pareto' and 'lognormal'");
     c.pmsm = u.payment_max_skill_multiplier; c.fixed_four = u.fixed_four ? 1 : 0;
     for (int i = 0; i < c.A; i++) {
         c.ranked_locs[i][0] = u.ranked_locs[i][0]; c.ranked_locs[i][1] = u.ranked_locs[i][1];
@@ -153,7 +153,8 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.full_obs = u.full_observability ? 1 : 0;
     c.a_map_elems = c.full_obs ? c.M * c.HW : (c.M + 1) * c.win * c.win;
     c.a_idx_elems = c.full_obs ? 2 * c.HW : 2 * c.win * c.win;
-    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs) ? 1 : 0;
+    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs ||
+             (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2))) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;
     c.Np = c.planner_acts ? (c.planner_single ? 1 + c.B * c.R : c.B * (1 + c.R)) : 1;
@@ -262,6 +263,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             // Saez model: current bracket rates [16], their running average [16] and the rates the observations show
             // [16] (float64), kept across resets
             c.off_saez = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_SAEZ) ? take(8 * 48) : 0;
+            c.off_gauss = (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2)) ? take(16) : 0;
             c.keep_bytes = off - c.off_mt;
             c.off_price_hist = take(8 * 2 * A * P);
             c.off_orders = take(4 * 2 * A * c.K);
@@ -316,6 +318,7 @@ inline int lookup_field(const DevCfg &c, const char *name, aie_field *f) {
         {"stats", c.off_stats, 8, 1, 1, 1, c.n_stats, 0, 0}, {"saez_n", HDR_SAEZ_N * 4, 4, 0, 1, 0, 0, 0, 0},
         {"saez_rates", c.off_saez, 8, 1, 1, 1, 16, 0, 0}, {"saez_avg_rates", c.off_saez + 128, 8, 1, 1, 1, 16, 0, 0},
         {"saez_obs_rates", c.off_saez + 256, 8, 1, 1, 1, 16, 0, 0}, {"util_prev", c.off_util_prev, 8, 1, 1, 1, A + 1, 0, 0},
+        {"gauss_state", c.off_gauss, 8, 1, 1, 1, 2, 0, 0},
         {"coin", c.off_coin, 8, 1, 1, 1, A, 0, 0}, {"esc_coin", c.off_esc_coin, 8, 1, 1, 1, A, 0, 0},
         {"labor", c.off_labor, 8, 1, 1, 1, A, 0, 0}, {"build_payment", c.off_bpay, 8, 1, 1, 1, A, 0, 0},
         {"build_skill", c.off_bskill, 8, 1, 1, 1, A, 0, 0}, {"bonus_gather_prob", c.off_bonus, 8, 1, 1, 1, A, 0, 0},
@@ -331,6 +334,7 @@ inline int lookup_field(const DevCfg &c, const char *name, aie_field *f) {
     for (const FieldDesc &t : tab)
         if (!strcmp(t.name, name)) {
             if (!strncmp(name, "saez_", 5) && name[5] != 'n' && !c.off_saez) return AIE_EINVAL;  // no Saez section in this config
+            if (!strcmp(name, "gauss_state") && !c.off_gauss) return AIE_EINVAL;
             f->offset = t.off; f->elem_bytes = t.eb; f->is_float = t.flt; f->is_signed = t.sgn; f->ndim = t.nd;
             f->shape[0] = t.s0; f->shape[1] = t.s1; f->shape[2] = t.s2; f->shape[3] = 0;
             return AIE_OK;
@@ -378,6 +382,11 @@ inline int pack_record(const DevCfg &c, const aie_host_state &hs, int i, uint8_t
     uint32_t *orders = (uint32_t *)(rec + c.off_orders);
     for (int k = 0; k < 2 * A * c.K; k++) orders[k] = ORDER_EMPTY;
     memcpy(rec + c.off_mt, hs.mt_key + (size_t)i * 624, 624 * 4);
+    if (c.off_gauss) {
+        double *g = (double *)(rec + c.off_gauss);
+        g[0] = hs.gauss_val ? hs.gauss_val[i] : 0.0;
+        g[1] = (hs.gauss_has && hs.gauss_has[i]) ? 1.0 : 0.0;
+    }
     return AIE_OK;
 }
 

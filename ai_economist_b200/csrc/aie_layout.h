@@ -128,6 +128,9 @@ struct DevCfg {
     uint64_t regen_tab[2][50];
     // full_observability: agents get the whole map; a_map_elems / a_idx_elems = elements per agent of the two tensors
     int32_t full_obs, a_map_elems, a_idx_elems;
+    // lognormal skills on the device reset: numpy's legacy_gauss cache {cached value, has_gauss as 0.0 / 1.0}, f64[2], in the
+    // part of the record a reset keeps (0: no such section)
+    int32_t off_gauss;
 };
 
 // raw device pointers (mirrors aie_buffers)

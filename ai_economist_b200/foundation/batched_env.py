@@ -270,6 +270,10 @@ class BatchedFoundationEnv:
         st = self._stepper
         key = st.to_numpy(st.state_view("mt_key")) if hasattr(st, "state_view") else None
         pos = st.to_numpy(st.state_view("mt_pos")) if hasattr(st, "state_view") else None
+        gauss = None
+        if key is not None and self._spec.get("reset_mode", 0) == 1 and 2 in (self._spec.get("build_skill_dist", 0),
+                                                                             self._spec.get("gather_skill_dist", 0)):
+            gauss = st.to_numpy(st.state_view("gauss_state"))   # the device reset may have consumed / refilled the cache
         for e, rs in enumerate(self._rs):
             if key is None:
                 d = st.read_state(e)
@@ -277,7 +281,8 @@ class BatchedFoundationEnv:
             else:
                 k, p = key[e], int(pos[e])
             s = rs.get_state()
-            rs.set_state((s[0], np.asarray(k, np.uint32), p, s[3], s[4]))
+            has_g, val_g = (s[3], s[4]) if gauss is None else (int(gauss[e][1] != 0.0), float(gauss[e][0]))
+            rs.set_state((s[0], np.asarray(k, np.uint32), p, has_g, val_g))
 
     def host_reset_arrays(self):
         """Run the reference-faithful host reset for every env; returns the aie_host_state arrays."""
@@ -289,6 +294,7 @@ class BatchedFoundationEnv:
             st = self.scenario.host_reset(rs, e)
             key = rs.get_state()
             st["mt_key"], st["mt_pos"] = np.asarray(key[1], np.uint32), int(key[2])
+            st["gauss_has"], st["gauss_val"] = int(key[3]), float(key[4])   # legacy Gaussian cache (lognormal skills)
             st["completions"] = int(self._completions[e])
             per.append(st)
         out = {k: np.stack([np.asarray(p[k]) for p in per]) for k in per[0]}

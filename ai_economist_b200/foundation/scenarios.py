@@ -159,8 +159,8 @@ class LayoutFromFile(BaseScenario):
     def scenario_spec_fields(self):
         d = super().scenario_spec_fields()
         d.update(has_water=1, regen_weight=[self.regen_weight, self.regen_weight])
-        # device-side reset with reference semantics (used by auto_reset): supported for 'none' / 'pareto' skills
-        dists = {"none": 0, "pareto": 1}
+        # device-side reset with reference semantics (used by auto_reset)
+        dists = {"none": 0, "pareto": 1, "lognormal": 2}
         comps = {c.name: c for c in self.env.components}
         b, g = comps.get("Build"), comps.get("Gather")
         ok = (b is None or b.skill_dist in dists) and (g is None or g.skill_dist in dists)

@@ -107,7 +107,8 @@ typedef struct aie_config {
      * (layout_from_file.py:336-370), Build / Gather skills (build.py:224-254, move.py:193-210) and the
      * fixed_four_skill_and_loc assignment (layout_from_file.py:580-586) - instead of re-using the snapshot's. */
     int32_t reset_mode;             /* 0: restore the load-time snapshot; 1: reference-exact layout_from_file reset */
-    int32_t build_skill_dist, gather_skill_dist;  /* 0 "none", 1 "pareto" */
+    int32_t build_skill_dist, gather_skill_dist;  /* 0 "none", 1 "pareto", 2 "lognormal" (numpy legacy_gauss incl. its
+                                                     cached second variate, which lives in the state record) */
     int32_t payment_max_skill_multiplier;
     int32_t fixed_four;             /* fixed_four_skill_and_loc */
     int16_t ranked_locs[AIE_MAX_AGENTS][2];       /* start cell of the i-th skill-ranked slot */
@@ -201,6 +202,10 @@ typedef struct aie_host_state {
     const uint32_t *mt_key;             /* [n, 624] numpy MT19937 key (np.random.get_state()[1]) */
     const int32_t *mt_pos;              /* [n] */
     const int32_t *completions;         /* [n] (may be NULL -> 0) */
+    /* ABI 3, optional: the legacy Gaussian cache of the numpy stream (np.random.get_state()[3:5]); only read by configs
+     * with a lognormal skill distribution, whose device-side reset continues that stream */
+    const int32_t *gauss_has;           /* [n] has_gauss */
+    const double *gauss_val;            /* [n] cached_gaussian */
 } aie_host_state;
 
 /* Debug / test readback of one env (host arrays, any pointer may be NULL).  Layout mirrors the

@@ -183,6 +183,18 @@ CONFIGS = {
         wood_regen_halfwidth=2, wood_regen_weight=0.6, stone_regen_halfwidth=1, stone_regen_weight=0.4),
 }
 
+# device-side reset with lognormal skills: numpy's legacy Gaussian cache carries over between components and resets
+CONFIGS["lognormal_reset"] = dict(
+    scenario_name="layout_from_file/simple_wood_and_stone",
+    # 5 agents, Build alone lognormal: 5 Gaussians per reset, so every other reset starts with the cached second variate
+    # of the previous reset's last pair; Gather's Pareto draws sit in between
+    components=[("Build", dict(skill_dist="lognormal", payment_max_skill_multiplier=3)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                ("Gather", dict(skill_dist="pareto"))],
+    env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5,
+    fixed_four_skill_and_loc=False, n_agents=5, world_size=[25, 25], episode_length=22,
+    multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True, flatten_masks=True)
+
 # full_observability=True: agents get the whole map (no window, no loc scalars); p<i> carry only the tax entries
 CONFIGS["full_obs_tax"] = dict(
     scenario_name="layout_from_file/simple_wood_and_stone",

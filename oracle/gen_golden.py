@@ -43,6 +43,7 @@ PLAN = [
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),
     ("saez_reset", 1001, 790, 50),
+    ("lognormal_reset", 1001, 95, 10),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

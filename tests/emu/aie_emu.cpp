@@ -103,7 +103,7 @@ int launch_step(aie_env *env, int emit_obs, void *) {
             memcpy(rec + c.off_price_hist, b.state0 + (size_t)e * c.rec_bytes + c.off_price_hist, c.rec_bytes - c.off_price_hist);
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
             hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
-            if (c.reset_mode == 1) device_reset_env(c, rec, rec, env->be.scratch.data(), 0);
+            if (c.reset_mode == 1) { if (c.ext) device_reset_env<true>(c, rec, rec, env->be.scratch.data(), 0); else device_reset_env<false>(c, rec, rec, env->be.scratch.data(), 0); }
             finish_reset_env(c, rec, rec, env->be.scratch.data(), 0);
         }
     }

@@ -1,6 +1,6 @@
 """Randomised multi-episode fuzz (build container only): the device-side reference-exact reset (auto_reset, 1-lane
 emulation of the device source) against the LIVE reference, which calls env.reset() between episodes on one continuing
-global numpy stream.  layout_from_file configurations with skill_dist in {none, pareto}, with / without
+global numpy stream.  layout_from_file configurations with skill_dist in {none, pareto, lognormal}, with / without
 fixed_four_skill_and_loc.   python tools/fuzz_device_reset_vs_reference.py [n] [seed]"""
 import os
 import sys
@@ -22,10 +22,10 @@ def random_config(rng):
     size = list(LAYOUTS)[rng.randint(len(LAYOUTS))]
     fixed_four = bool(rng.rand() < 0.4)
     A = int(rng.choice([2, 3, 4, 6, 9, 12]))
-    comps = [("Build", dict(skill_dist="pareto" if fixed_four else str(rng.choice(["none", "pareto"])),
+    comps = [("Build", dict(skill_dist="pareto" if fixed_four else str(rng.choice(["none", "pareto", "lognormal"])),
                             payment_max_skill_multiplier=int(rng.randint(1, 4)))),
              ("ContinuousDoubleAuction", dict(max_num_orders=int(rng.choice([1, 3, 5])), order_duration=int(rng.choice([2, 50])))),
-             ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto"]))))]
+             ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto", "lognormal"]))))]
     if rng.rand() < 0.5:
         comps.append(("PeriodicBracketTax", dict(period=int(rng.choice([3, 10])), bracket_spacing="us-federal",
                                                  tax_model=str(rng.choice(["model_wrapper", "us-federal-single-filer-2018-scaled"])))))
