@@ -55,14 +55,34 @@ private:
     bool stop_ = false;
 };
 
+// bits -> 0.0f / 1.0f.  The expansion is a pure write stream (296 MB per step for c2 at 8 192 envs), so on x86 the
+// 16-byte groups go out with non-temporal stores (no read-for-ownership of the destination lines); a 16-entry table maps
+// four bits to four floats.  `src` must be readable up to the 8 bytes holding the last bit (true inside a compact record).
+#if defined(__SSE2__)
+#include <emmintrin.h>
+struct NibbleTable {
+    __m128 v[16];
+    NibbleTable() { for (int k = 0; k < 16; k++) v[k] = _mm_set_ps((float)((k >> 3) & 1), (float)((k >> 2) & 1), (float)((k >> 1) & 1), (float)(k & 1)); }
+};
 inline void expand_bits(const uint32_t *src, int n, float *dst) {
+    static const NibbleTable T;
+    auto bit = [&](int i) { return (float)((src[i >> 5] >> (i & 31)) & 1u); };
     int i = 0;
-    for (int w = 0; i + 32 <= n; w++, i += 32) {
-        const uint32_t b = src[w];
-        for (int j = 0; j < 32; j++) dst[i + j] = (float)((b >> j) & 1u);
+    while (i < n && ((uintptr_t)(dst + i) & 15)) { dst[i] = bit(i); i++; }
+    for (; i + 4 <= n; i += 4) {
+        uint64_t w;
+        memcpy(&w, (const uint8_t *)src + 4 * (i >> 5), 8);     // the word holding bit i and the next one
+        _mm_stream_ps(dst + i, T.v[(w >> (i & 31)) & 15u]);
     }
-    if (i < n) { const uint32_t b = src[i >> 5]; for (int j = 0; i + j < n; j++) dst[i + j] = (float)((b >> j) & 1u); }
+    for (; i < n; i++) dst[i] = bit(i);
 }
+inline void expand_fence() { _mm_sfence(); }
+#else
+inline void expand_bits(const uint32_t *src, int n, float *dst) {
+    for (int i = 0; i < n; i++) dst[i] = (float)((src[i >> 5] >> (i & 31)) & 1u);
+}
+inline void expand_fence() {}
+#endif
 
 // one env: compact record -> the caller's (host) tensors; NULL outputs are skipped
 inline void expand_env(const CompactLayout &L, const uint8_t *rec, size_t env, const aie_host_out &o) {
@@ -78,6 +98,7 @@ inline void expand_env(const CompactLayout &L, const uint8_t *rec, size_t env, c
     if (o.obs_time) o.obs_time[env] = *(const float *)(rec + L.off_time);
     if (o.done) o.done[env] = *(const int32_t *)(rec + L.off_done);
     if (o.reward) memcpy(o.reward + env * L.n_rew, rec + L.off_rew, 8 * (size_t)L.n_rew);
+    expand_fence();   // the non-temporal stores of this env are globally visible before the work item is reported done
 }
 
 }  // namespace aie
