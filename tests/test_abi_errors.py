@@ -120,3 +120,44 @@ def test_bound_but_not_loaded_and_bad_load_arguments():
     bad["loc"][1, 0] = (99, 0)
     with pytest.raises(_abi.AieError):
         st.load_state(bad)
+
+
+def _covid_cfg():
+    import json, os
+    from ai_economist_b200.covid_stepper import covid_config_from_params
+    from ai_economist_b200.foundation.covid19 import build_covid_params
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_covid", "covid_seed3.npz"))
+    return covid_config_from_params(build_covid_params(**json.loads(str(z["meta_json"]))["kwargs"]), auto_reset=False)
+
+
+@pytest.mark.parametrize("mutate,needle", [
+    (lambda c: setattr(c, "abi_version", 2), "abi_version"),
+    (lambda c: setattr(c, "n_states", 65), "n_states"),
+    (lambda c: setattr(c, "num_filters", 9), "num_filters"),
+    (lambda c: setattr(c, "beta_delay", 10 ** 6), "filter / delay"),
+    (lambda c: setattr(c, "subsidy_interval", 0), "schedule"),
+    (lambda c: setattr(c, "num_stringency_levels", 1), "schedule"),
+    (lambda c: setattr(c, "start_date_index", 10 ** 6), "start_date_index"),
+    (lambda c: setattr(c, "conv_filters", None), "NULL"),
+])
+def test_covid_create_rejects_bad_configuration_with_a_message(mutate, needle):
+    L = emu_lib()
+    cfg, keep = _covid_cfg()
+    mutate(cfg)
+    h = C.c_void_p()
+    rc = L.aie_covid_create(C.byref(cfg), 2, 0, C.byref(h))
+    assert rc == AIE_EINVAL and needle in L.aie_last_error().decode(), L.aie_last_error()
+
+
+def test_covid_calls_out_of_order_return_estate():
+    L = emu_lib()
+    cfg, keep = _covid_cfg()
+    h = C.c_void_p()
+    assert L.aie_covid_create(C.byref(cfg), 0, 0, C.byref(h)) == AIE_EINVAL
+    assert L.aie_covid_create(C.byref(cfg), 2, 0, C.byref(h)) == 0
+    assert L.aie_covid_reset(h, None) == AIE_ESTATE and L.aie_covid_step(h, None) == AIE_ESTATE
+    assert L.aie_covid_sample_random_actions(h, 1, None) == AIE_ESTATE
+    bufs = _abi.AieCovidBuffers()
+    assert L.aie_covid_bind_buffers(h, C.byref(bufs)) == AIE_EINVAL and b"NULL" in L.aie_last_error()
+    assert L.aie_covid_step(None, None) == AIE_EINVAL and L.aie_covid_destroy(None) == 0
+    assert L.aie_covid_destroy(h) == 0
