@@ -33,6 +33,7 @@ struct State {
     uint16_t *tab_dev;   // observation programs (device copy)
     uint8_t *compact_dev = nullptr, *compact_host = nullptr;   // aie_step_host_compact: device + pinned host staging
     size_t compact_bytes = 0;
+    cudaEvent_t slice_ev[8] = {};   // one per transfer slice of the compacted D2H copy
 };
 int init(aie_env *);
 void destroy(aie_env *);
@@ -47,6 +48,8 @@ int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
 int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
 int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
+int download_slice(aie_env *, int k, void *host, const void *dev, size_t n, void *stream);
+int wait_slice(aie_env *, int k);
 void *const_upload(const void *host, size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
@@ -366,7 +369,16 @@ void destroy(aie_env *env) {
     if (env->be.tab_dev) cudaFree(env->be.tab_dev);
     if (env->be.compact_dev) cudaFree(env->be.compact_dev);
     if (env->be.compact_host) cudaFreeHost(env->be.compact_host);
+    for (cudaEvent_t &ev : env->be.slice_ev) if (ev) cudaEventDestroy(ev);
 }
+int download_slice(aie_env *env, int k, void *host, const void *dev, size_t n, void *stream) {
+    if (k < 0 || k >= 8) return fail(AIE_EINVAL, "transfer slice index");
+    if (!env->be.slice_ev[k]) AIE_CUDA(cudaEventCreateWithFlags(&env->be.slice_ev[k], cudaEventDisableTiming), "cudaEventCreate");
+    AIE_CUDA(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H slice");
+    AIE_CUDA(cudaEventRecord(env->be.slice_ev[k], (cudaStream_t)stream), "cudaEventRecord");
+    return AIE_OK;
+}
+int wait_slice(aie_env *env, int k) { return cudaEventSynchronize(env->be.slice_ev[k]) == cudaSuccess ? AIE_OK : AIE_ECUDA; }
 int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
     if (env->be.compact_bytes < bytes) {
         if (env->be.compact_dev) cudaFree(env->be.compact_dev);

@@ -12,6 +12,8 @@
 //   int launch_sample(aie_env*, uint64_t seed, void *stream);
 //   int compact_buffers(aie_env*, size_t bytes, uint8_t **dev, uint8_t **host);   (library-owned, allocated once)
 //   int launch_pack(aie_env*, const aie::CompactLayout&, uint8_t *dev, void *stream);
+//   int download_slice(aie_env*, int k, void *host, const void *dev, size_t n, void *stream);   (async copy + event k)
+//   int wait_slice(aie_env*, int k);                                                           (any thread)
 #include <string>
 #include <vector>
 
@@ -217,20 +219,31 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     if (rc != AIE_OK) return rc;
     rc = aie::be::launch_pack(env, L, dev, stream);
     if (rc != AIE_OK) return rc;
-    rc = aie::be::download(env, host, dev, E * (size_t)L.bytes, stream);
-    if (rc != AIE_OK) return rc;
-    rc = aie::be::sync(env, stream);
-    if (rc != AIE_OK) return rc;
+    // The compact records go down in up to 8 slices, each followed by an event; a work item first waits for the slice
+    // holding its envs, so the expansion of the early slices overlaps the transfer of the later ones.
+    const int chunk = 64, n_items = (int)((E + chunk - 1) / chunk);   // envs per work item
+    int n_slices = n_items < 8 ? n_items : 8;
+    const int items_per_slice = (n_items + n_slices - 1) / n_slices;
+    n_slices = (n_items + items_per_slice - 1) / items_per_slice;
+    for (int k = 0; k < n_slices; k++) {
+        const size_t lo = (size_t)k * items_per_slice * chunk, hi = (size_t)(k + 1) * items_per_slice * chunk < E ? (size_t)(k + 1) * items_per_slice * chunk : E;
+        rc = aie::be::download_slice(env, k, host + lo * (size_t)L.bytes, dev + lo * (size_t)L.bytes, (hi - lo) * (size_t)L.bytes, stream);
+        if (rc != AIE_OK) return rc;
+    }
     int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     if (want < 1) want = 1;
     if (want > 64) want = 64;
     if (!env->pool || env->pool->size() != want - 1) { delete env->pool; env->pool = new aie::HostPool(want - 1); }
     const aie_host_out out = *o;
-    const int chunk = 64, n_chunks = (int)((E + chunk - 1) / chunk);   // envs per work item
-    env->pool->run(n_chunks, [&](int k) {
-        const size_t hi = (size_t)(k + 1) * chunk < E ? (size_t)(k + 1) * chunk : E;
-        for (size_t e = (size_t)k * chunk; e < hi; e++) aie::expand_env(L, host + e * (size_t)L.bytes, e, out);
+    std::atomic<int> failed{0};
+    env->pool->run(n_items, [&](int item) {
+        if (aie::be::wait_slice(env, item / items_per_slice) != AIE_OK) { failed.store(1); return; }
+        const size_t hi = (size_t)(item + 1) * chunk < E ? (size_t)(item + 1) * chunk : E;
+        for (size_t e = (size_t)item * chunk; e < hi; e++) aie::expand_env(L, host + e * (size_t)L.bytes, e, out);
     });
+    if (failed.load()) return fail(AIE_ECUDA, "aie_step_host_compact: waiting for a transfer slice failed");
+    rc = aie::be::sync(env, stream);
+    if (rc != AIE_OK) return rc;
     return AIE_OK;
 }
 

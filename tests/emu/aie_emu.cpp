@@ -36,6 +36,8 @@ int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
 int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
 int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
+int download_slice(aie_env *, int k, void *host, const void *dev, size_t n, void *stream);
+int wait_slice(aie_env *, int k);
 void *const_upload(const void *host, size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
@@ -58,6 +60,8 @@ int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
     *dev = env->be.compact_dev.data(); *host = env->be.compact_host.data();
     return AIE_OK;
 }
+int download_slice(aie_env *, int, void *host, const void *dev, size_t n, void *) { memcpy(host, dev, n); return AIE_OK; }
+int wait_slice(aie_env *, int) { return AIE_OK; }
 int launch_pack(aie_env *env, const CompactLayout &L, uint8_t *dev, void *) {
     for (int e = 0; e < env->n_envs; e++) pack_env(env->cfg, env->bufs, L, (size_t)e, dev + (size_t)e * L.bytes, 0);
     return AIE_OK;
