@@ -41,6 +41,7 @@ class AieConfig(C.Structure):
         ("ranked_locs", (C.c_int16 * 2) * 64), ("avg_ranked_skill", C.c_double * 64),
         ("single_action_planner", C.c_int32), ("regen_halfwidth", C.c_int32 * 2),
         ("full_observability", C.c_int32),
+        ("split_layout", C.c_int32), ("split_water_row", C.c_int32), ("split_top_ranks", C.c_uint64),
     ]
 
 
@@ -65,7 +66,7 @@ class AieBuffers(C.Structure):
 class AieHostState(C.Structure):
     _fields_ = [("n", C.c_int32)] + [(n, C.c_void_p) for n in [
         "stone", "wood", "stone_src", "wood_src", "water", "loc", "coin", "inv_stone", "inv_wood",
-        "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions", "gauss_has", "gauss_val"]]
+        "build_payment", "build_skill", "bonus_gather_prob", "mt_key", "mt_pos", "completions", "gauss_has", "gauss_val", "split_skill"]]
 
 
 _DUMP_PTRS = ["cell", "owner", "loc", "coin", "esc_coin", "labor", "inv", "esc", "n_orders", "bid_hist", "ask_hist",
@@ -225,4 +226,7 @@ def config_from_spec(spec, auto_reset=True):
     cfg.single_action_planner = int(spec.get("single_action_planner", 0))
     cfg.regen_halfwidth[0], cfg.regen_halfwidth[1] = [int(v) for v in spec.get("regen_halfwidth", [0, 0])]
     cfg.full_observability = int(spec.get("full_observability", 0))
+    cfg.split_layout = int(spec.get("split_layout", 0))
+    cfg.split_water_row = int(spec.get("split_water_row", 0))
+    cfg.split_top_ranks = int(spec.get("split_top_ranks", 0))
     return cfg

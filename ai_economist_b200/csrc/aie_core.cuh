@@ -98,7 +98,7 @@ AIE_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 struct Env {
     int32_t *hdr;
     double *coin, *esc_coin, *labor, *bpay, *bskill, *bonus, *last_coin, *last_income, *last_marg, *util_prev,
-        *price_hist, *stats, *gauss, *saez;  // gauss: numpy legacy_gauss cache {value, has}; saez (Saez model only): [16] bracket rates, [16] running average, [16] observed rates
+        *price_hist, *stats, *gauss, *split_skill, *saez;  // gauss: numpy legacy_gauss cache {value, has}; saez (Saez model only): [16] bracket rates, [16] running average, [16] observed rates
     int32_t *inv, *esc;  // [A][2]
     int16_t *loc;        // [A][2]
     uint8_t *n_orders, *bid_hist, *ask_hist, *rate_idx, *cell;
@@ -117,6 +117,7 @@ AIE_DEV Env env_view(uint8_t *rec, uint8_t *grec, const DevCfg &c) {
     e.coin = (double *)(rec + c.off_coin);
     e.saez = (double *)(rec + c.off_saez);
     e.gauss = (double *)(rec + c.off_gauss);
+    e.split_skill = (double *)(rec + c.off_split_skill);
     e.stats = (double *)(big + c.off_stats);  // resident unless the config is split
     e.esc_coin = (double *)(rec + c.off_esc_coin);
     e.labor = (double *)(rec + c.off_labor);
@@ -1031,6 +1032,29 @@ AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, R
         }
     }
     wsync();
+    if (EXT && c.split_layout) {
+        // SplitLayout.additional_reset_steps (layout_from_file.py:766-790): everybody is taken off the map; a random order
+        // hands out the rank-averaged payments and re-places the agents, the chosen ranks above the water row
+        rng_permutation(r, s.perm, A);
+        for (int a = lane; a < A; a += NL) { e.loc[2 * a] = -1; e.loc[2 * a + 1] = -1; }
+        wsync();
+        for (int i = 0; i < A; i++) {
+            const int a = s.perm[i];
+            const bool top = (c.split_top_ranks >> i) & 1ull;
+            const int r_min = top ? 0 : c.split_water_row + 1, r_max = top ? c.split_water_row : c.H;
+            int row = 0, col = 0;
+            for (int tries = 0; tries <= 201; tries++) {
+                row = r_min + (int)rng_interval(r, (uint32_t)(r_max - r_min - 1));
+                col = (int)rng_interval(r, (uint32_t)(c.W - 1));
+                bool blocked = (e.cell[row * c.W + col] & CELL_WATER) != 0;
+                for (int a2 = 0; a2 < A && !blocked; a2++) blocked = e.loc[2 * a2] == row && e.loc[2 * a2 + 1] == col;
+                if (!blocked) break;
+            }
+            wsync();
+            if (lane == 0) { e.loc[2 * a] = (int16_t)row; e.loc[2 * a + 1] = (int16_t)col; e.bpay[a] = e.split_skill[i]; }
+            wsync();
+        }
+    }
     if (c.fixed_four) {
         rng_permutation(r, s.perm, A);
         for (int i = lane; i < A; i += NL) {

@@ -153,7 +153,11 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.full_obs = u.full_observability ? 1 : 0;
     c.a_map_elems = c.full_obs ? c.M * c.HW : (c.M + 1) * c.win * c.win;
     c.a_idx_elems = c.full_obs ? 2 * c.HW : 2 * c.win * c.win;
-    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs ||
+    c.split_layout = (u.split_layout && c.reset_mode == 1) ? 1 : 0;
+    c.split_water_row = u.split_water_row; c.split_top_ranks = u.split_top_ranks;
+    if (c.split_layout && (c.split_water_row < 1 || c.split_water_row >= c.H - 1)) return bad("split_water_row outside the world");
+    if (c.split_layout && c.fixed_four) return bad("split_layout does not support fixed_four_skill_and_loc");
+    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs || c.split_layout ||
              (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2))) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;
@@ -264,6 +268,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             // [16] (float64), kept across resets
             c.off_saez = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_SAEZ) ? take(8 * 48) : 0;
             c.off_gauss = (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2)) ? take(16) : 0;
+            c.off_split_skill = c.split_layout ? take(8 * A) : 0;
             c.keep_bytes = off - c.off_mt;
             c.off_price_hist = take(8 * 2 * A * P);
             c.off_orders = take(4 * 2 * A * c.K);
@@ -382,6 +387,10 @@ inline int pack_record(const DevCfg &c, const aie_host_state &hs, int i, uint8_t
     uint32_t *orders = (uint32_t *)(rec + c.off_orders);
     for (int k = 0; k < 2 * A * c.K; k++) orders[k] = ORDER_EMPTY;
     memcpy(rec + c.off_mt, hs.mt_key + (size_t)i * 624, 624 * 4);
+    if (c.off_split_skill) {
+        if (!hs.split_skill) { err = "split_layout device reset needs aie_host_state.split_skill"; return AIE_EINVAL; }
+        memcpy(rec + c.off_split_skill, hs.split_skill + (size_t)i * c.A, 8 * (size_t)c.A);
+    }
     if (c.off_gauss) {
         double *g = (double *)(rec + c.off_gauss);
         g[0] = hs.gauss_val ? hs.gauss_val[i] : 0.0;

@@ -131,6 +131,9 @@ struct DevCfg {
     // lognormal skills on the device reset: numpy's legacy_gauss cache {cached value, has_gauss as 0.0 / 1.0}, f64[2], in the
     // part of the record a reset keeps (0: no such section)
     int32_t off_gauss;
+    // split_layout device reset: per-replica rank -> build payment table f64[A] in the kept part of the record
+    int32_t split_layout, split_water_row, off_split_skill;
+    uint64_t split_top_ranks;
 };
 
 // raw device pointers (mirrors aie_buffers)

@@ -444,9 +444,13 @@ class SplitLayout(LayoutFromFile):
             loc[a] = (r, c)
             taken[r, c] = True
         st["loc"] = loc
+        st["split_skill"] = self._split_ranked_skill[e].copy()   # the device-side reset hands these out again
         return st
 
     def scenario_spec_fields(self):
-        d = super().scenario_spec_fields()
-        d.update(reset_mode=0)   # the rank / half-map placement is host-side; auto-reset restores the snapshot
+        d = super().scenario_spec_fields()   # reset_mode 1 when the skill distributions have a device-side sampler
+        top = 0
+        for rank in self.skill_rank_of_top_agents:
+            top |= 1 << int(rank)
+        d.update(split_layout=1, split_water_row=int(self._water_line), split_top_ranks=top)
         return d

@@ -131,7 +131,8 @@ class BatchStepper:
                              ("build_payment", np.float64, True), ("build_skill", np.float64, True),
                              ("bonus_gather_prob", np.float64, True), ("mt_key", np.uint32, True),
                              ("mt_pos", np.int32, True), ("completions", np.int32, False),
-                             ("gauss_has", np.int32, False), ("gauss_val", np.float64, False)]:
+                             ("gauss_has", np.int32, False), ("gauss_val", np.float64, False),
+                             ("split_skill", np.float64, False)]:
             setattr(hs, key, arr(key, dt, req))
         self._check(self.lib.aie_load_state(self._h, C.byref(hs), int(env_lo), self._stream()))
 

@@ -124,6 +124,11 @@ typedef struct aie_config {
                                        "world-map" is the whole map [M, H, W] (no window, no "inside" plane), its
                                        "world-idx_map" [2, H, W] with the agent's own index recoded to 1; the loc-row /
                                        loc-col scalars and the scenario's share of the planner's p<i> vectors are absent */
+    /* split_layout/simple_wood_and_stone, device-side reset (layout_from_file.py:766-790): after the layout_from_file
+     * reset, a random order hands out the rank-averaged skills (aie_host_state.split_skill, one table per replica) and
+     * re-places everybody - the agents at the ranks in split_top_ranks above split_water_row, the others below */
+    int32_t split_layout, split_water_row;
+    uint64_t split_top_ranks;       /* bit i: the i-th agent of the random order starts above the water row */
 } aie_config;
 
 /* Sizes the caller needs to allocate the device buffers. */
@@ -206,6 +211,7 @@ typedef struct aie_host_state {
      * with a lognormal skill distribution, whose device-side reset continues that stream */
     const int32_t *gauss_has;           /* [n] has_gauss */
     const double *gauss_val;            /* [n] cached_gaussian */
+    const double *split_skill;          /* [n, A] optional: split_layout's rank -> build payment table of each replica */
 } aie_host_state;
 
 /* Debug / test readback of one env (host arrays, any pointer may be NULL).  Layout mirrors the

@@ -183,6 +183,16 @@ CONFIGS = {
         wood_regen_halfwidth=2, wood_regen_weight=0.6, stone_regen_halfwidth=1, stone_regen_weight=0.4),
 }
 
+# device-side reset of split_layout (rank table per replica, drawn in the constructor: `seed` is a constructor kwarg)
+CONFIGS["split_reset"] = dict(
+    scenario_name="split_layout/simple_wood_and_stone",
+    components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                ("Gather", dict(skill_dist="pareto"))],
+    env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5, seed=77,
+    skill_rank_of_top_agents=[0, 3], n_agents=5, world_size=[25, 25], episode_length=20,
+    multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True, flatten_masks=True)
+
 # device-side reset with lognormal skills: numpy's legacy Gaussian cache carries over between components and resets
 CONFIGS["lognormal_reset"] = dict(
     scenario_name="layout_from_file/simple_wood_and_stone",

@@ -44,6 +44,7 @@ PLAN = [
     ("c3_reset", 1001, 95, 10),
     ("saez_reset", 1001, 790, 50),
     ("lognormal_reset", 1001, 95, 10),
+    ("split_reset", 1001, 90, 10),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

@@ -22,6 +22,8 @@ def _env(meta, factory):
     kw = dict(meta["reference_kwargs"])
     name = kw.pop("scenario_name")
     kw["components"] = [tuple(c) for c in kw["components"]]
+    if "seed" in kw:   # a constructor seed (split_layout's skill table): both replicas like the reference's single env
+        kw["seeds"] = [kw.pop("seed")] * 2
     extra = dict(stepper_factory=factory) if factory else dict(device="cuda:0")
     return foundation.make_env_instance(name, n_envs=2, auto_reset=True, **kw, **extra)
 
