@@ -29,6 +29,14 @@ def random_config(rng):
     if rng.rand() < 0.5:
         comps.append(("PeriodicBracketTax", dict(period=int(rng.choice([3, 10])), bracket_spacing="us-federal",
                                                  tax_model=str(rng.choice(["model_wrapper", "us-federal-single-filer-2018-scaled"])))))
+    split = (not fixed_four) and comps[0][1]["skill_dist"] == "pareto" and rng.rand() < 0.5
+    if split:   # split_layout: constructor-time skill table (needs a constructor seed), ranks above the water row
+        n_top = int(rng.randint(1, A))
+        extra = dict(seed=int(rng.randint(1, 1000)), skill_rank_of_top_agents=[int(x) for x in rng.choice(A, n_top, replace=False)])
+        return dict(scenario_name="split_layout/simple_wood_and_stone", components=comps, n_agents=A,
+                    world_size=list(size), env_layout_file=LAYOUTS[size], episode_length=int(rng.choice([8, 15])),
+                    starting_agent_coin=float(rng.choice([0, 10])), multi_action_mode_agents=bool(rng.rand() < 0.3),
+                    multi_action_mode_planner=True, flatten_observations=True, flatten_masks=True, **extra)
     return dict(scenario_name="layout_from_file/simple_wood_and_stone", components=comps, n_agents=A,
                 world_size=list(size), env_layout_file=LAYOUTS[size], episode_length=int(rng.choice([8, 15, 30])),
                 fixed_four_skill_and_loc=fixed_four, starting_agent_coin=float(rng.choice([0, 10])),
@@ -44,6 +52,8 @@ def run_one(cfg, seed, episodes=4):
     obs = ref.reset()
     kw = dict(cfg)
     name = kw.pop("scenario_name")
+    if "seed" in kw:
+        kw["seeds"] = [kw.pop("seed")] * 2
     env = foundation.make_env_instance(name, n_envs=2, stepper_factory=emu_factory, auto_reset=True, **kw)
     assert env.spec["reset_mode"] == 1
     env.seed([seed, seed])
