@@ -22,14 +22,14 @@ def random_config(rng):
     size = list(LAYOUTS)[rng.randint(len(LAYOUTS))]
     fixed_four = bool(rng.rand() < 0.4)
     A = int(rng.choice([2, 3, 4, 6, 9, 12]))
-    comps = [("Build", dict(skill_dist="pareto" if fixed_four else str(rng.choice(["none", "pareto", "lognormal"])),
+    comps = [("Build", dict(skill_dist="pareto" if fixed_four else str(rng.choice(["none", "pareto", "lognormal"], p=[0.2, 0.6, 0.2])),
                             payment_max_skill_multiplier=int(rng.randint(1, 4)))),
              ("ContinuousDoubleAuction", dict(max_num_orders=int(rng.choice([1, 3, 5])), order_duration=int(rng.choice([2, 50])))),
              ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto", "lognormal"]))))]
     if rng.rand() < 0.5:
         comps.append(("PeriodicBracketTax", dict(period=int(rng.choice([3, 10])), bracket_spacing="us-federal",
                                                  tax_model=str(rng.choice(["model_wrapper", "us-federal-single-filer-2018-scaled"])))))
-    split = (not fixed_four) and comps[0][1]["skill_dist"] == "pareto" and rng.rand() < 0.5
+    split = (not fixed_four) and comps[0][1]["skill_dist"] == "pareto" and rng.rand() < 0.7
     if split:   # split_layout: constructor-time skill table (needs a constructor seed), ranks above the water row
         n_top = int(rng.randint(1, A))
         extra = dict(seed=int(rng.randint(1, 1000)), skill_rank_of_top_agents=[int(x) for x in rng.choice(A, n_top, replace=False)])
@@ -92,12 +92,13 @@ def run_one(cfg, seed, episodes=4):
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    bad = 0
+    bad, kinds = 0, {}
     for i in range(n):
         cfg = random_config(rng)
+        kinds[cfg["scenario_name"].split("/")[0]] = kinds.get(cfg["scenario_name"].split("/")[0], 0) + 1
         try:
             run_one(cfg, seed=500 + i)
         except Exception as ex:  # noqa: BLE001
             bad += 1
             print("[%d] FAILED %r\n    %s" % (i, cfg, "".join(traceback.format_exception_only(type(ex), ex)).strip()[:500]))
-    print("%d configs x 4 episodes, %d failures" % (n, bad))
+    print("%d configs x 4 episodes, %d failures" % (n, bad), kinds)
