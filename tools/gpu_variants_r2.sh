@@ -53,3 +53,9 @@ except Exception as ex:
     print("c4 change_list=$cl FAILED", ex)
 PY
 done
+# source-level captures of the step kernel on the two heavier gather-trade-build workloads (c3: paper config with taxes,
+# c5: 64 agents / deep book), read offline with tools/ncu_by_line.py: round 1 only profiled c2 by line
+for w in c3 c5; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:aie_step_kernel -s 8 -c 1 -f -o gpurun_out/prof_step_$w \
+      python bench.py --workload $w --steps 6 --warmup 5 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_step_$w.log 2>&1; echo "ncu $w rc=$?"
+done
