@@ -49,6 +49,9 @@
 #ifndef AIE_PLANES_V2
 #define AIE_PLANES_V2 0
 #endif
+#ifndef AIE_FUSED_POLICY
+#define AIE_FUSED_POLICY 0
+#endif
 #define AIE_PRAGMA_(x) _Pragma(#x)
 #define AIE_UNROLL(n) AIE_PRAGMA_(unroll n)
 
@@ -1300,6 +1303,36 @@ AIE_DEV float flat_value(const float *shf, const float *agf, uint32_t entry) {
     return (AIE_FLAT_KIND(entry) == FK_AGENT ? agf : shf)[AIE_FLAT_PAYLOAD(entry)];
 }
 
+#if AIE_FUSED_POLICY
+// Tuning variant (-DAIE_FUSED_POLICY=1): the bench's random policy fused into the observation pass.  Uniform choice among
+// the open entries j in [0, n) of a predicate, by one warp (same ballot / popcount scheme as sample_segment_warp).
+AIE_DEV uint64_t fp_mix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+template <typename F>
+AIE_DEV int fp_sample(F open_at, int n, uint64_t key, int lane) {
+    int total = 0;
+    for (int base = 0; base < n; base += NL) { const int j = base + lane; total += __popc_u32(wballot(j < n && open_at(j))); }
+    if (total == 0) return 0;
+    int r = (int)((uint32_t)(fp_mix64(key) >> 32) % (uint32_t)total);
+    for (int base = 0; base < n; base += NL) {
+        const int j = base + lane;
+        const uint32_t m = wballot(j < n && open_at(j));
+        const int cnt = __popc_u32(m);
+        if (r < cnt) {
+            uint32_t mm = m;
+            for (int i = 0; i < r; i++) mm &= mm - 1;   // drop the r lowest set bits
+            return base + first_lane(mm);
+        }
+        r -= cnt;
+    }
+    return 0;
+}
+#endif
+
 template <bool EXT = false>
 AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *mt_img, uint8_t *extra, const ObsOut &o,
                          const uint16_t *tab, int lane) {
@@ -1525,6 +1558,48 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     } else if (lane == 0) {
         o.p_mask()[0] = 1.0f;
     }
+#if AIE_FUSED_POLICY
+    if (o.b->policy_seed) {   // the next step's random actions, drawn from the limits / conditions the masks were written from
+        const uint64_t key0 = fp_mix64(o.b->policy_seed ^ fp_mix64((uint64_t)o.env)) + ((uint64_t)(uint32_t)e.hdr[HDR_T] << 20);
+        const uint16_t *mtab = tab + c.tab_m;
+        int32_t *aa = const_cast<int32_t *>(o.b->act_a) + o.env * (size_t)(A * c.n_act_a);
+        for (int a = 0; a < A; a++) {
+            const uint8_t *lim = s.lim + a * MS_COUNT;
+            if (!c.multi_action) {
+                const int v = fp_sample([&](int j) { const uint32_t en = mtab[j]; return (en & 255u) < lim[en >> 8]; },
+                                        c.Na, key0 + 0x100 * a, lane);
+                if (lane == 0) aa[a] = v;
+            } else {
+                int off = 0;
+                for (int si = 0; si < c.n_sub; si++) {
+                    const int v = fp_sample([&](int j) { const uint32_t en = mtab[off + j]; return (en & 255u) < lim[en >> 8]; },
+                                            c.sub_n[si] + 1, key0 + 0x100 * a + si + 1, lane);
+                    if (lane == 0) aa[a * c.n_sub + si] = v;
+                    off += c.sub_n[si] + 1;
+                }
+            }
+        }
+        if (c.planner_acts && o.b->act_p) {
+            int32_t *ap = const_cast<int32_t *>(o.b->act_p) + o.env * (size_t)c.n_act_p;
+            const bool first_day = e.hdr[HDR_TAX_POS] == 1;
+            const double limit = s.net_hist[2 * P];
+            auto rate_open = [&](int rr) {   // rr = 0: NO-OP; else discretised rate rr - 1 (same rule as the mask above)
+                bool open = rr == 0 || first_day;
+                if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= limit;
+                return open;
+            };
+            if (EXT && c.planner_single) {
+                const int v = fp_sample([&](int j) { return j == 0 || rate_open((j - 1) % c.R + 1); }, c.Np, key0 + 0x10000, lane);
+                if (lane == 0) ap[0] = v;
+            } else {
+                for (int b = 0; b < c.B; b++) {
+                    const int v = fp_sample(rate_open, 1 + c.R, key0 + 0x10000 + b, lane);
+                    if (lane == 0) ap[b] = v;
+                }
+            }
+        }
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

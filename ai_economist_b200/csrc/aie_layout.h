@@ -148,6 +148,9 @@ struct DevBufs {
     const uint16_t *tab;
     // optional per-step event log of the first event_envs replicas (dense logs): int32 [event_envs][event_cap + 1][8]
     int32_t *events; int32_t event_envs, event_cap;
+    // tuning variant -DAIE_FUSED_POLICY=1 only: non-zero = the step kernel's observation pass also draws the next step's
+    // random actions (bench policy) from the mask limits it has just staged, instead of a separate sampler launch
+    uint64_t policy_seed;
 };
 // compact program table: [agent flat (Fa) | planner flat (Fp) | p<i> flat (Fpa) | agent mask (Na)], offsets in DevCfg
 constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK;

@@ -14,6 +14,10 @@ VARIANTS = {
     # MT19937 twist unroll depth (code size vs. ILP); the default 8 is the loop's full trip count
     "twist4": ["-DAIE_TWIST_UNROLL=4"],
     "planes_v2_twist4": ["-DAIE_PLANES_V2=1", "-DAIE_TWIST_UNROLL=4"],
+    # the bench's random policy drawn inside the step kernel's observation pass (from the mask limits it has just staged)
+    # instead of a separate 16 us sampler launch per step; aie_sample_random_actions only refreshes the seed
+    "fused_policy": ["-DAIE_FUSED_POLICY=1"],
+    "planes_v2_fused_policy": ["-DAIE_PLANES_V2=1", "-DAIE_FUSED_POLICY=1"],
 }
 
 if __name__ == "__main__":
