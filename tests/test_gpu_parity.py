@@ -111,6 +111,38 @@ def test_cuda_full_size_c2_against_oracle_and_invariants():
     assert torch.equal(first, st.buf["state"])
 
 
+@pytest.mark.parametrize("cfg,E,steps", [("c3_paper_tax", 8192, 30), ("c5_full", 2048, 12)],
+                         ids=["c3_full_size", "c5_full_size"])
+def test_cuda_full_size_c3_c5_against_oracle_and_invariants(cfg, E, steps):
+    """BASELINE configs 3 and 5 at their per-GPU sizes (8 192 replicas of 10 agents on 40x40 with taxes; 2 048 replicas of
+    64 agents on 64x64 with a 50-deep book): every replica digest-compared with the oracle, a sample array-for-array, and
+    the size-independent invariants on the whole batch."""
+    env = _make_env(cfg, E, seed=2000, auto_reset=False)
+    orc, host = _load_both(env)
+    A, (H, W) = env.n_agents, env.world_size
+    bu.run_pair(env, orc, steps, np.random.RandomState(3), check_every=steps, check_envs=list(range(0, E, 509)))
+    st = env.stepper
+    loc = st.state_view("loc").cpu().numpy()
+    inv = st.state_view("inv").cpu().numpy()
+    esc = st.state_view("esc").cpu().numpy()
+    coin = st.state_view("coin").cpu().numpy()
+    n_orders = st.state_view("n_orders").cpu().numpy().astype(np.int64)
+    bid_hist = st.state_view("bid_hist").cpu().numpy().astype(np.int64)
+    ask_hist = st.state_view("ask_hist").cpu().numpy().astype(np.int64)
+    mt_pos = st.state_view("mt_pos").cpu().numpy()
+    for e in range(E):  # oracle digest for every replica
+        s = orc.state(e)
+        assert np.array_equal(s["loc"], loc[e]) and np.array_equal(s["inv"], inv[e]), e
+        assert int(s["mt_pos"][0]) == int(mt_pos[e]), e
+    assert np.array_equal(n_orders, bid_hist.sum(-1) + ask_hist.sum(-1))          # order counts = histogram mass
+    assert np.array_equal(esc.transpose(0, 2, 1), ask_hist.sum(-1))               # escrowed units = open asks
+    assert n_orders.max() <= env.spec["max_num_orders"]
+    flat = loc[..., 0].astype(np.int64) * W + loc[..., 1]
+    assert all(len(set(row)) == A for row in flat)                                # agents on distinct cells
+    assert (loc >= 0).all() and (loc[..., 0] < H).all() and (loc[..., 1] < W).all()
+    assert (inv >= 0).all() and (esc >= 0).all() and (coin > -1e-9).all()
+
+
 def test_auto_reset_restores_snapshot_and_continues_stream():
     """auto_reset=1: an env that reaches episode_length is restored from its load-time snapshot inside the same
     step (WarpDrive save_copy_and_apply_at_reset semantics); the numpy-legacy stream carries on."""
