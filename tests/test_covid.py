@@ -170,6 +170,46 @@ def test_covid_cuda_batch_matches_numpy_oracle(change_list):
                 assert np.isclose(float(ref["rew_p"]), float(got["rew_p"]), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.gpu
+def test_covid_cuda_full_size_sample_vs_oracle_and_invariants():
+    """BASELINE config 4 at full size (4 096 replicas): device random policy, a sample of replicas replayed through the
+    numpy oracle with the actions the device drew, state invariants on the whole batch, run-to-run determinism."""
+    import torch
+    from ai_economist_b200.covid_stepper import CudaCovidStepper
+    z, meta, p = load()
+    E, steps = 4096, 60
+    sample = list(range(0, E, 455))
+
+    def run():
+        s = CudaCovidStepper(p, E, auto_reset=False)
+        s.reset()
+        envs = {e: CovidOracleEnv(p) for e in sample}
+        for t in range(steps):
+            s.sample_random_actions(seed=900 + t)
+            aa, ap = s.to_numpy(s.buf["actions_agent"]), s.to_numpy(s.buf["actions_planner"])
+            ma, mp = s.to_numpy(s.buf["mask_agent"]), s.to_numpy(s.buf["mask_planner"])
+            assert np.all(np.take_along_axis(ma, aa[:, None, :], axis=1) == 1.0)          # drawn actions are unmasked
+            assert np.all(np.take_along_axis(mp, ap[:, None], axis=1) == 1.0)
+            s.step()
+            for e in sample:
+                envs[e].step(aa[e], ap[e])
+        for e in sample:
+            got, ref = s.read_obs(e), envs[e].obs()
+            for k in OBS_KEYS + ["rew_a"]:
+                assert np.allclose(ref[k], got[k], rtol=RTOL, atol=ATOL), (e, k)
+        return s
+
+    s = run()
+    st = s.to_numpy(s.buf["state"])                      # [E, 9, S]
+    assert np.isfinite(st).all() and (st[:, :6] >= 0).all()                                   # S, I, R, D, V, U >= 0
+    assert (st[:, 6] >= 1).all() and (st[:, 6] <= p["num_stringency_levels"]).all()           # stringency level in range
+    pop = np.asarray(p["population"], np.float64)[None]
+    assert np.all(np.abs(st[:, 0] + st[:, 1] + st[:, 2] - pop) <= 1e-3 * pop)                 # S + I + R stays the population
+    assert int(s.to_numpy(s.buf["hdr"])[:, 0].min()) == steps == int(s.to_numpy(s.buf["hdr"])[:, 0].max())
+    s2 = run()
+    assert torch.equal(s.buf["state"], s2.buf["state"]) and torch.equal(s.buf["obs_agent_state"], s2.buf["obs_agent_state"])
+
+
 def test_covid_env_api_through_make_env_instance():
     """Same call as the reference (tests/run_covid19_cpu_gpu_consistency_checks.py:44-81 config)."""
     from ai_economist_b200 import foundation
