@@ -109,3 +109,30 @@ def test_reference_api_tracks_the_live_reference(flags):
             assert d1 == d2
     mref, mmine = ref.metrics, mine.metrics
     assert set(mref) == set(mmine)
+
+
+@pytest.mark.gpu
+def test_reference_api_cuda_matches_the_emulated_facade():
+    """The facade over the CUDA stepper: same nested outputs as over the emulation, same caller code, two episodes."""
+    cfg = dict(ENV_CONFIG, episode_length=25, flatten_observations=False, flatten_masks=True)
+    cuda = foundation.make_env_instance(**cfg, reference_api=True, device="cuda:0")
+    emu = foundation.make_env_instance(**cfg, reference_api=True, stepper_factory=emu_factory)
+    cuda.seed(4); emu.seed(4)
+
+    def same(a, b, label):
+        if isinstance(a, dict):
+            assert set(a) == set(b), label
+            for k in a:
+                same(a[k], b[k], label + "/" + str(k))
+        else:
+            assert np.allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=1e-6, atol=1e-7), label
+
+    for episode in range(2):
+        ra, rb = np.random.RandomState(episode), np.random.RandomState(episode)
+        o1, o2 = cuda.reset(), emu.reset()
+        same(o1, o2, "reset")
+        for t in range(25):
+            (o1, r1, d1, _), (o2, r2, d2, _) = cuda.step(sample_random_actions(cuda, o1, ra)), emu.step(sample_random_actions(emu, o2, rb))
+            same(o1, o2, "obs t=%d" % t); same(r1, r2, "rew t=%d" % t)
+            assert d1 == d2
+    assert cuda._completions == emu._completions == 2
