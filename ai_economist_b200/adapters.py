@@ -249,9 +249,27 @@ class ReferenceApiEnv:
         done = {"__all__": bool(int(np.asarray(self._np(env.done["__all__"]))[e]))}
         return obs, rew, done
 
+    # ---- replay logs (base_env.py:358-360, 444-471, 980-982) -----------------------------------------------
+    @property
+    def replay_log(self):
+        """The current (possibly incomplete) replay log: {"reset": {"seed_state"}, "step": [{"actions", "seed_state"}]}."""
+        return self.__dict__.get("_replay", {"reset": dict(seed_state=None), "step": []})
+
+    @property
+    def previous_episode_replay_log(self):
+        """Replay log of the last completed episode: `env.reset(**log["reset"])` then `env.step(**s)` for every s in
+        log["step"] reproduces it exactly (logs recorded by the reference itself replay here too)."""
+        return self.__dict__.get("_last_replay", {"reset": dict(seed_state=None), "step": []})
+
     # ---- the Gym-style surface ---------------------------------------------------------------------------
     def reset(self, seed_state=None, force_dense_logging=False):
-        self._env.reset(seed_state=seed_state, force_dense_logging=force_dense_logging)
+        env, e = self._env, self._e
+        mine = env._np_state(seed_state) if seed_state is not None else env.stream_state(e)
+        # like the reference (base_env.py:899): the log holds the stream state the reset cycle starts from
+        object.__setattr__(self, "_replay", {"reset": dict(seed_state=mine), "step": []})
+        if seed_state is not None and env.n_envs > 1:   # only this replica's stream moves
+            seed_state = [mine if i == e else env.stream_state(i) for i in range(env.n_envs)]
+        env.reset(seed_state=seed_state, force_dense_logging=force_dense_logging)
         return self._outputs()[0]
 
     def step(self, actions=None, seed_state=None):
@@ -259,6 +277,10 @@ class ReferenceApiEnv:
         missing agents take NO-OPs, like the reference."""
         env, e = self._env, self._e
         st = env.stepper
+        if seed_state is not None:
+            env.set_stream_state(seed_state, e)
+        if "_replay" in self.__dict__:
+            self._replay["step"].append(dict(actions=actions, seed_state=env.stream_state(e)))
         ba, bp = st.buf["actions_agent"], st.buf["actions_planner"]
         ba[e] = 0
         bp[e] = 0
@@ -282,5 +304,7 @@ class ReferenceApiEnv:
                 ba[e, int(k)] = env._as_buf(row, ba, (st.dims.n_act_agent,))
         env.step(env.action_buffers)
         obs, rew, done = self._outputs()
+        if done["__all__"] and "_replay" in self.__dict__:
+            object.__setattr__(self, "_last_replay", self._replay)   # _finalize_logs (base_env.py:763-765)
         return obs, rew, done, {k: {} for k in obs} if "a" not in obs else \
             {"a": {str(i): {} for i in range(env.n_agents)}, "p": {}}

@@ -300,14 +300,60 @@ class BatchedFoundationEnv:
         out = {k: np.stack([np.asarray(p[k]) for p in per]) for k in per[0]}
         return out
 
+    @staticmethod
+    def _np_state(seed_state):
+        """The 5-tuple np.random.set_state() expects (base_env.py:873-883)."""
+        assert isinstance(seed_state, (tuple, list)) and len(seed_state) == 5
+        return (str(seed_state[0]), np.array(seed_state[1], dtype=np.uint32), int(seed_state[2]), int(seed_state[3]),
+                float(seed_state[4]))
+
+    def stream_state(self, e=0):
+        """np.random.get_state() of replica e's stream as it stands now (on the device once the env is loaded)."""
+        if self._rs is None:
+            self._rs = [np.random.RandomState() for _ in range(self.n_envs)]
+        if self._loaded:
+            self._sync_streams_from_device()
+        return self._rs[e].get_state()
+
+    def set_stream_state(self, seed_state, e=0):
+        """np.random.set_state(seed_state) for replica e: host stream and, once loaded, the key inside its record."""
+        ss = self._np_state(seed_state)
+        if self._rs is None:
+            self._rs = [np.random.RandomState() for _ in range(self.n_envs)]
+        self._rs[e].set_state(ss)
+        if self._loaded:
+            st = self._stepper
+            for name, val in (("mt_key", ss[1].astype(np.int64)), ("mt_pos", ss[2])):
+                v = st.state_view(name)
+                if isinstance(v, np.ndarray):
+                    v[e] = val
+                else:
+                    import torch
+                    v[e] = torch.as_tensor(val, device=v.device).to(v.dtype)
+            if self._spec.get("reset_mode", 0) == 1 and 2 in (self._spec.get("build_skill_dist", 0), self._spec.get("gather_skill_dist", 0)):
+                g = st.state_view("gauss_state")
+                vals = np.array([ss[4], float(ss[3])])
+                if isinstance(g, np.ndarray):
+                    g[e] = vals
+                else:
+                    import torch
+                    g[e] = torch.as_tensor(vals, device=g.device, dtype=g.dtype)
+
     def reset(self, seed_state=None, force_dense_logging=False):
-        if seed_state is not None:
-            raise NotImplementedError("pass seeds= / call seed() instead of seed_state")
+        """seed_state: optional numpy stream state(s) to start the reset from (base_env.py:873-884) - one 5-tuple (every
+        replica when n_envs == 1, else replica 0) or a list with one 5-tuple per replica."""
         if self._loaded and "episode_final" not in self._stepper.buf:
             self._last_ep_metrics_host = self.metrics_of(0)   # base_env.py:893-896: reset() stores the old episode's metrics
         if self._loaded and self._rs is not None:
             self._completions = self.completions()
             self._sync_streams_from_device()
+        if seed_state is not None:
+            if self._rs is None:
+                self._rs = [np.random.RandomState() for _ in range(self.n_envs)]
+            per_env = seed_state if (isinstance(seed_state, (tuple, list)) and len(seed_state) == self.n_envs
+                                     and isinstance(seed_state[0], (tuple, list))) else [seed_state]
+            for e, ss in enumerate(per_env):
+                self._rs[e].set_state(self._np_state(ss))
         saez_n = self._saez.before_host_reset() if self._saez is not None else None
         # the "auto" energy warm-up integrator survives resets in the reference (layout_from_file.py:153, 557: only the
         # constructor zeroes it); a host reset repacks the records, so carry it over

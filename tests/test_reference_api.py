@@ -136,3 +136,67 @@ def test_reference_api_cuda_matches_the_emulated_facade():
             same(o1, o2, "obs t=%d" % t); same(r1, r2, "rew t=%d" % t)
             assert d1 == d2
     assert cuda._completions == emu._completions == 2
+
+
+def _final_state(env):
+    d = env.stepper.read_state(0)
+    return {k: np.array(d[k]) for k in ["cell", "owner", "loc", "inv", "esc", "coin", "labor", "mt_key", "mt_pos"]}
+
+
+def test_replay_log_reproduces_an_episode():
+    """previous_episode_replay_log (base_env.py:455-471): reset(**log["reset"]) + step(**s) for every logged step
+    reproduces the episode exactly - state, metrics and dense log - whatever the env's stream did in between."""
+    env = foundation.make_env_instance(**ENV_CONFIG, reference_api=True, stepper_factory=emu_factory, dense_log_frequency=1)
+    env.seed(12)
+    play(env, np.random.RandomState(0), dense=True)
+    want_state, want_metrics, want_log = _final_state(env), env.metrics, env.previous_episode_dense_log
+    log = env.previous_episode_replay_log
+    assert len(log["step"]) == env.episode_length and len(log["reset"]["seed_state"]) == 5
+    play(env, np.random.RandomState(99), dense=False)          # something else in between: the stream has moved on
+    obs = env.reset(force_dense_logging=True, **log["reset"])
+    for s in log["step"]:
+        obs, rew, done, info = env.step(**s)
+    got = _final_state(env)
+    for k in want_state:
+        assert np.array_equal(want_state[k], got[k]), k
+    got_metrics = env.metrics
+    assert set(got_metrics) == set(want_metrics)
+    # (the auto warm-up integrator counts steps over the env's whole life, in the reference too)
+    assert all(np.array_equal(got_metrics[k], want_metrics[k], equal_nan=True) for k in want_metrics if k != "labor/warmup_integrator")
+    assert env.previous_episode_dense_log["states"] == want_log["states"]
+    assert env.previous_episode_dense_log["Trade"] == want_log["Trade"]
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
+def test_a_replay_log_recorded_by_the_reference_replays_here():
+    """Cross-implementation replay: the unmodified reference plays an episode and hands over its replay log; replaying
+    that log through the facade ends in the reference's final state and metrics (and the other way round)."""
+    f = rh.load_reference_foundation()
+    ref = f.make_env_instance(**ENV_CONFIG)
+    ref.seed(5)
+    play(ref, np.random.RandomState(3), dense=False)
+    log = ref.previous_episode_replay_log
+    want = rh.state_arrays_from_reference(ref)
+    mine = foundation.make_env_instance(**ENV_CONFIG, reference_api=True, stepper_factory=emu_factory)
+    mine.reset(**log["reset"])
+    for s in log["step"]:
+        mine.step(**s)
+    got = _final_state(mine)
+    for k in ["cell", "owner", "loc", "inv", "esc", "mt_key"]:
+        assert np.array_equal(np.asarray(want[k]), got[k].reshape(np.asarray(want[k]).shape)), k
+    assert np.allclose(want["coin"], got["coin"], rtol=1e-9) and np.allclose(want["labor"], got["labor"], rtol=1e-9)
+    m_ref, m_mine = ref.metrics, mine.metrics
+    assert set(m_ref) == set(m_mine)
+    for k, v in m_ref.items():
+        assert np.isclose(float(v), float(m_mine[k]), rtol=1e-6, atol=1e-9, equal_nan=True), k
+    # ... and a log recorded here drives the reference to the same end state
+    mine.seed(8)
+    play(mine, np.random.RandomState(4), dense=False)
+    log2, want2 = mine.previous_episode_replay_log, _final_state(mine)
+    ref.reset(**log2["reset"])
+    for s in log2["step"]:
+        ref.step(**s)
+    got2 = rh.state_arrays_from_reference(ref)
+    for k in ["cell", "owner", "loc", "inv", "esc", "mt_key"]:
+        assert np.array_equal(np.asarray(got2[k]), want2[k].reshape(np.asarray(got2[k]).shape)), k
