@@ -89,6 +89,9 @@ class WarpDriveStyleEnvWrapper:
         self.reset_on_host = True
         A = env_obj.n_agents
         b = env_obj.stepper.buf
+        if hasattr(env_obj, "params"):   # the COVID-19 scenario: the env the reference's wrapper was written for
+            self._init_covid(env_obj, A, b)
+            return
         # ---- spaces (env_wrapper.py:139-172): per agent id, from the per-replica slice of each tensor ----
         self.env.observation_space = Dict({k: Dict({kk: _space_of(tuple(v.shape[1:]), self._np_dtype(v))
                                                     for kk, v in d.items()}) for k, d in env_obj.obs.items()})
@@ -108,6 +111,25 @@ class WarpDriveStyleEnvWrapper:
             if k in b:
                 d["observations_" + n] = b[k]
         d["observations_p_time"] = b["obs_time"]
+        self.data = d
+
+    def _init_covid(self, env_obj, A, b):
+        """CovidAndEconomySimulation (collated "a" / "p" observations, single-action agents and planner): per-state
+        observation spaces as the reference builds them by un-collating "a" (env_wrapper.py:139-150), Discrete action
+        spaces, and the reserved array names of covid19_env.py:700-722, 1002-1040 as views of the device tensors."""
+        p = env_obj.params
+        per_agent = Dict({k: _space_of(tuple(v.shape[1:-1]), self._np_dtype(v)) for k, v in env_obj.obs["a"].items()})
+        spaces = {str(i): per_agent for i in range(A)}
+        spaces["p"] = Dict({k: _space_of(tuple(v.shape[1:]), self._np_dtype(v)) for k, v in env_obj.obs["p"].items()})
+        self.env.observation_space = Dict(spaces)
+        self.env.action_space = {str(i): Discrete(1 + int(p["num_stringency_levels"])) for i in range(A)}
+        self.env.action_space["p"] = Discrete(1 + int(p["num_subsidy_levels"]))
+        assert set(self.env.observation_space.keys()) == set(self.env.action_space.keys())
+        d = {"_done_": b["done"], "_timestep_": b["hdr"][:, 0], "actions_a": b["actions_agent"], "actions_p": b["actions_planner"],
+             "rewards_a": b["reward_agent"], "rewards_p": b["reward_planner"]}
+        for who in ("a", "p"):
+            for k, v in env_obj.obs[who].items():
+                d["observations_%s_%s" % (who, k)] = v
         self.data = d
 
     @staticmethod

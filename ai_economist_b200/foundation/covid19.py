@@ -276,6 +276,11 @@ class CovidBatchedEnv:
     def seed(self, seed):  # the scenario is deterministic
         return None
 
+    @property
+    def action_buffers(self):
+        """(agent actions [E, S], planner actions [E]): write in place and call step(env.action_buffers) for zero copies."""
+        return self._stepper.buf["actions_agent"], self._stepper.buf["actions_planner"]
+
     def _build_views(self):
         b = self._stepper.buf
         S = self.n_agents

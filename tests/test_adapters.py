@@ -80,3 +80,34 @@ def test_warpdrive_style_wrapper_on_cuda_is_zero_copy():
     d = adapters.MultiAgentDictEnv(env, e=7)
     obs, rew, done, _ = d.step({"0": 0})
     assert obs["p"]["flat"].dtype == np.float32 and set(rew) == {str(i) for i in range(env.n_agents)} | {"p"}
+
+
+def test_warpdrive_style_wrapper_over_the_covid_env():
+    """The env the reference's FoundationEnvWrapper was written for (env_wrapper.py:84-418 + covid19_env.py's reserved
+    array names): spaces per US state + planner, zero-copy named tensors, reset_all_envs / step_all_envs."""
+    import json
+    import os
+    from ai_economist_b200 import foundation
+    from ai_economist_b200.adapters import WarpDriveStyleEnvWrapper
+    from oracle.gen_golden_covid import COVID_KWARGS, reference_config
+    from tests.emu.emu_stepper import EmuCovidStepper
+    cfg = reference_config(COVID_KWARGS)
+    name = cfg.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=3, auto_reset=True,
+                                       stepper_factory=lambda p, n, ar: EmuCovidStepper(p, n, ar), **cfg)
+    w = WarpDriveStyleEnvWrapper(env)
+    assert w.n_agents == 52 and w.n_envs == 3 and w.episode_length == env.episode_length
+    assert set(env.action_space.keys()) == {str(i) for i in range(51)} | {"p"}
+    assert env.action_space["0"].n == 11 and env.action_space["p"].n == 21
+    assert env.observation_space["7"]["world-agent_state"].shape == (6,) and env.observation_space["p"]["world-agent_state"].shape == (6, 51)
+    w.reset_all_envs()
+    assert np.shares_memory(w.tensor("actions_a"), env.stepper.buf["actions_agent"])
+    w.tensor("actions_a")[...] = 0
+    w.tensor("actions_a")[1, 5] = 3                      # state 5 of replica 1 goes to stringency level 3
+    w.tensor("actions_p")[...] = 2
+    w.step_all_envs()
+    assert int(w.tensor("_timestep_")[0]) == 1 and not w.tensor("_done_").any()
+    pol = w.tensor("observations_a_ControlUSStateOpenCloseStatus-agent_policy_indicators")
+    assert w.tensor("rewards_a").shape == (3, 51) and w.tensor("rewards_p").shape == (3,)
+    st = env.stepper.read_state(1)
+    assert int(st["stringency"][5]) == 3 and np.asarray(pol).shape == (3, 51)
