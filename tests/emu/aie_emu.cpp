@@ -118,7 +118,6 @@ int launch_step(aie_env *env, int emit_obs, void *) {
 int launch_observe(aie_env *env, int lo, int n, void *) {
     const DevCfg &c = env->cfg;
     const DevBufs &b = env->bufs;
-    const size_t A = c.A, ww = (size_t)c.win * c.win;
     for (int env_i = lo; env_i < lo + n; env_i++) {
         size_t e = env_i;
         ObsOut o; o.b = &b; o.c = &c; o.env = e;
