@@ -311,7 +311,17 @@ class BatchedFoundationEnv:
         """np.random.get_state() of replica e's stream as it stands now (on the device once the env is loaded)."""
         if self._rs is None:
             self._rs = [np.random.RandomState() for _ in range(self.n_envs)]
-        if self._loaded:
+        if self._loaded and hasattr(self._stepper, "state_view"):   # only this replica's 2.5 KB key
+            st = self._stepper
+            key = st.to_numpy(st.state_view("mt_key")[e])
+            pos = int(st.to_numpy(st.state_view("mt_pos")[e]))
+            s = self._rs[e].get_state()
+            has_g, val_g = s[3], s[4]
+            if self._spec.get("reset_mode", 0) == 1 and 2 in (self._spec.get("build_skill_dist", 0), self._spec.get("gather_skill_dist", 0)):
+                g = st.to_numpy(st.state_view("gauss_state")[e])
+                has_g, val_g = int(g[1] != 0.0), float(g[0])
+            self._rs[e].set_state((s[0], np.asarray(key, np.uint32), pos, has_g, val_g))
+        elif self._loaded:
             self._sync_streams_from_device()
         return self._rs[e].get_state()
 
