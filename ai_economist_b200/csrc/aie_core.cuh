@@ -624,12 +624,24 @@ AIE_DEV void gather_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) 
 // ------------------------------------------------------------------------------------------------
 // PeriodicBracketTax  (components/redistribution.py)
 // ------------------------------------------------------------------------------------------------
+template <bool EXT = false>
 AIE_DEV double tax_rate(const DevCfg &c, const Env &e, int b) {  // curr_marginal_rates :381-405
     if (c.tax_model == 2) return fmin(e.saez[b], c.rate_max);  // Saez: np.minimum(curr_bracket_tax_rates, curr_rate_max)
+    if (EXT && c.tax_model == 1 && c.tax_annealing) {
+        // a fixed schedule under a tax_annealing_schedule: np.minimum(schedule, curr_rate_max) with the annealed maximum of
+        // this episode (:390-394, :400-413; components/utils.py:10-57, refreshed whenever the completion count changes)
+        // Quirk kept: the limit is refreshed in generate_masks, which runs AFTER the observations of a reset are built
+        // (base_env.py:614-704), so the reset observation (t == 0) still shows the previous episode's limit.
+        int done_eps = e.hdr[HDR_COMPLETIONS];
+        if (e.hdr[HDR_T] == 0 && done_eps > 0) done_eps -= 1;
+        const double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)done_eps - c.ann_warm)));
+        return fmin(c.fixed_rates[b], vis * c.rate_max);
+    }
     return c.tax_model == 0 ? c.disc_rates[e.rate_idx[b]] : c.fixed_rates[b];
 }
+template <bool EXT = false>
 AIE_DEV double tax_rate_observed(const DevCfg &c, const Env &e, int b) {  // _curr_rates_obs (:960, :1123)
-    return c.tax_model == 2 ? fmin(e.saez[32 + b], c.rate_max) : tax_rate(c, e, b);
+    return c.tax_model == 2 ? fmin(e.saez[32 + b], c.rate_max) : tax_rate<EXT>(c, e, b);
 }
 AIE_DEV int tax_income_bin(const DevCfg &c, double income) {  // :828-835 (bracket index; negative income -> 0)
     int arg = 0;
@@ -639,20 +651,23 @@ AIE_DEV int tax_income_bin(const DevCfg &c, double income) {  // :828-835 (brack
     }
     return arg;
 }
+template <bool EXT = false>
 AIE_DEV double tax_marginal_rate(const DevCfg &c, const Env &e, double income) {  // :837-844
     if (income < 0) return 0.0;
-    return tax_rate(c, e, tax_income_bin(c, income));
+    return tax_rate<EXT>(c, e, tax_income_bin(c, income));
 }
+template <bool EXT = false>
 AIE_DEV double tax_due(const DevCfg &c, const Env &e, double income) {  // :846-851
     double sum = 0.0;
     for (int b = 0; b < c.B; b++) {
         double size = ((b + 1 < c.B) ? c.cutoffs[b + 1] : INFINITY) - c.cutoffs[b];
         double past = fmax(0.0, income - c.cutoffs[b]);
-        sum += tax_rate(c, e, b) * fmin(size, past);
+        sum += tax_rate<EXT>(c, e, b) * fmin(size, past);
     }
     return sum;
 }
 
+template <bool EXT = false>
 AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, int lane) {  // :945-972
     const int A = c.A;
     int pos = e.hdr[HDR_TAX_POS];
@@ -680,9 +695,9 @@ AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, int
     if (pos >= c.period) {  // enact_taxes :853-915
         for (int a = lane; a < A; a += NL) {
             double income = (e.coin[a] + e.esc_coin[a]) - e.last_coin[a];
-            double due = tax_due(c, e, income);
+            double due = tax_due<EXT>(c, e, income);
             double paid = fmin(e.coin[a], due);  // never touches escrow
-            e.last_marg[a] = tax_marginal_rate(c, e, income);
+            e.last_marg[a] = tax_marginal_rate<EXT>(c, e, income);
             e.last_income[a] = income;
             e.coin[a] -= paid;
             s.tmp[a] = paid;
@@ -698,7 +713,7 @@ AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, int
             st[ST_TAX_PERIODS] += 1.0;
             if (c.tax_model == 2 && e.hdr[HDR_SAEZ_N] < (1 << 30)) e.hdr[HDR_SAEZ_N] += A;  // _update_saez_buffer :535-544
             st[ST_TAX_COLLECTED] += net;
-            for (int b = 0; b < c.B; b++) st[ST_TAX_SCHED + b] += tax_rate(c, e, b);
+            for (int b = 0; b < c.B; b++) st[ST_TAX_SCHED + b] += tax_rate<EXT>(c, e, b);
             for (int a = 0; a < A; a++) {
                 st[ST_TAX_EFF_SUM] += s.tmp[A + a];
                 st[ST_TAX_OCC + tax_income_bin(c, e.last_income[a])] += 1.0;
@@ -927,7 +942,7 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
             case COMP_BUILD: build_step(c, e, s, r); break;
             case COMP_CDA: cda_create<BIG>(c, e, s, t, lane); cda_match<BIG>(c, e, s, t, lane); cda_expire<BIG>(c, e, t, lane); break;
             case COMP_GATHER: gather_step(c, e, s, r); break;
-            case COMP_TAX: tax_step(c, e, s, r, lane); break;
+            case COMP_TAX: tax_step<EXT>(c, e, s, r, lane); break;
             case COMP_WEALTH: wealth_step(c, e, s, lane); break;
         }
     }
@@ -1373,9 +1388,9 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)e.hdr[HDR_COMPLETIONS] - c.ann_warm)));
             s.net_hist[2 * P] = vis * c.ann_full;
         }
-        for (int b = lane; b < c.B; b += NL) s.shf[c.sh_curr_rates + b] = (float)tax_rate_observed(c, e, b);
+        for (int b = lane; b < c.B; b += NL) s.shf[c.sh_curr_rates + b] = (float)tax_rate_observed<EXT>(c, e, b);
         for (int a = lane; a < A; a += NL) {
-            s.sc_a[a * AS_COUNT + AS_TAX_MARG] = (float)tax_marginal_rate(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
+            s.sc_a[a * AS_COUNT + AS_TAX_MARG] = (float)tax_marginal_rate<EXT>(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
             const double v = e.last_income[a] / c.period;  // ascending rank -> sorted position (:908-911)
             int rank = 0;
             for (int j = 0; j < A; j++) {

@@ -158,6 +158,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     if (c.split_layout && (c.split_water_row < 1 || c.split_water_row >= c.H - 1)) return bad("split_water_row outside the world");
     if (c.split_layout && c.fixed_four) return bad("split_layout does not support fixed_four_skill_and_loc");
     c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs || c.split_layout ||
+             (c.has[COMP_TAX] && c.tax_model == AIE_TAX_FIXED_RATES && u.tax_annealing) ||
              (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2))) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;

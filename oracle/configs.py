@@ -183,6 +183,20 @@ CONFIGS = {
         wood_regen_halfwidth=2, wood_regen_weight=0.6, stone_regen_halfwidth=1, stone_regen_weight=0.4),
 }
 
+# a FIXED tax schedule under a tax_annealing_schedule: the schedule is clipped by the annealed maximum of each episode
+# (0.5, 0.75, 1.0 x rate_max over the first three episodes)
+CONFIGS["us_federal_annealed_reset"] = dict(
+    scenario_name="layout_from_file/simple_wood_and_stone",
+    components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                ("Gather", dict(skill_dist="pareto")),
+                ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=5, rate_max=0.3,
+                                            tax_model="us-federal-single-filer-2018-scaled",
+                                            tax_annealing_schedule=[-2, 0.25]))],
+    env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=30,
+    fixed_four_skill_and_loc=False, n_agents=5, world_size=[25, 25], episode_length=20,
+    multi_action_mode_agents=False, multi_action_mode_planner=True, flatten_observations=True, flatten_masks=True)
+
 # device-side reset of split_layout (rank table per replica, drawn in the constructor: `seed` is a constructor kwarg)
 CONFIGS["split_reset"] = dict(
     scenario_name="split_layout/simple_wood_and_stone",

@@ -587,7 +587,16 @@ static void curr_marginal_rates(const orc_batch *b, const env_t *s, double *out)
     int i;
     for (i = 0; i < b->cfg.n_brackets; i++) {
         if (b->cfg.tax_model == ORC_TAX_MODEL_WRAPPER) out[i] = b->cfg.disc_rates[s->rate_idx[i]];
-        else out[i] = b->cfg.fixed_rates[i];
+        else {
+            out[i] = b->cfg.fixed_rates[i];
+            if (b->cfg.tax_annealing) { /* np.minimum(schedule, curr_rate_max), :390-394, :400-413; utils.py:10-57 */
+                /* the limit is refreshed in generate_masks, i.e. after the observations of a reset were built: the reset
+                 * observation (t == 0) still uses the previous episode's limit */
+                int done_eps = (s->t == 0 && s->completions > 0) ? s->completions - 1 : s->completions;
+                double vis = fmax(0.0, fmin(1.0, b->cfg.annealing_slope * ((double)done_eps - b->cfg.annealing_warmup)));
+                out[i] = fmin(out[i], vis * b->cfg.rate_max);
+            }
+        }
     }
 }
 

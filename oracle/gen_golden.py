@@ -45,6 +45,7 @@ PLAN = [
     ("saez_reset", 1001, 790, 50),
     ("lognormal_reset", 1001, 95, 10),
     ("split_reset", 1001, 90, 10),
+    ("us_federal_annealed_reset", 1001, 90, 5),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

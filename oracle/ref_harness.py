@@ -109,8 +109,11 @@ def spec_from_reference_env(env):
                 disable_taxes=int(c.disable_taxes), period=c.period, n_brackets=c.n_brackets,
                 n_disc_rates=c.n_disc_rates, bracket_cutoffs=[float(x) for x in c.bracket_cutoffs],
                 disc_rates=[] if c.disc_rates is None else [float(x) for x in c.disc_rates],
-                fixed_rates=([0.0] * c.n_brackets if c.tax_model == "model_wrapper"
-                             else [float(x) for x in c.curr_marginal_rates]),
+                # fixed schedules: the schedule clipped by rate_max; a tax_annealing_schedule clips it further per episode
+                fixed_rates=([0.0] * c.n_brackets if c.tax_model in ("model_wrapper", "saez") else
+                             [float(x) for x in np.minimum(np.array(c.us_federal_single_filer_2018_scaled
+                                                                    if c.tax_model == "us-federal-single-filer-2018-scaled"
+                                                                    else c.fixed_bracket_rates), c.rate_max)]),
                 tax_annealing=int(c.tax_annealing_schedule is not None),
                 annealing_warmup=float(c._annealing_warmup or 0.0),
                 annealing_slope=float(c._annealing_slope or 0.0), rate_max=float(c.rate_max),

@@ -27,8 +27,11 @@ def random_config(rng):
              ("ContinuousDoubleAuction", dict(max_num_orders=int(rng.choice([1, 3, 5])), order_duration=int(rng.choice([2, 50])))),
              ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto", "lognormal"]))))]
     if rng.rand() < 0.5:
-        comps.append(("PeriodicBracketTax", dict(period=int(rng.choice([3, 10])), bracket_spacing="us-federal",
-                                                 tax_model=str(rng.choice(["model_wrapper", "us-federal-single-filer-2018-scaled"])))))
+        tkw = dict(period=int(rng.choice([3, 10])), bracket_spacing="us-federal",
+                   tax_model=str(rng.choice(["model_wrapper", "us-federal-single-filer-2018-scaled"])))
+        if rng.rand() < 0.6:
+            tkw["tax_annealing_schedule"] = [int(rng.choice([-2, 0, 1])), float(rng.choice([0.25, 0.5]))]
+        comps.append(("PeriodicBracketTax", tkw))
     split = (not fixed_four) and comps[0][1]["skill_dist"] == "pareto" and rng.rand() < 0.7
     if split:   # split_layout: constructor-time skill table (needs a constructor seed), ranks above the water row
         n_top = int(rng.randint(1, A))

@@ -37,8 +37,8 @@ def random_config(rng):
             kw["fixed_bracket_rates"] = [round(float(x), 2) for x in np.sort(rng.rand(7))]
         if model == "model_wrapper":
             kw["rate_disc"] = float(rng.choice([0.05, 0.1, 0.25]))
-            if rng.rand() < 0.4:
-                kw["tax_annealing_schedule"] = [int(rng.choice([-100, 0])), float(rng.choice([0.001, 0.5]))]
+        if rng.rand() < 0.4:   # planner-mask annealing (model_wrapper) / per-episode clipping of a fixed schedule
+            kw["tax_annealing_schedule"] = [int(rng.choice([-100, 0, -2])), float(rng.choice([0.001, 0.5, 0.25]))]
         comps.append(("PeriodicBracketTax", kw))
     elif rng.rand() < 0.3:
         comps.append(("WealthRedistribution", {}))
