@@ -353,7 +353,8 @@ class BatchedFoundationEnv:
         """seed_state: optional numpy stream state(s) to start the reset from (base_env.py:873-884) - one 5-tuple (every
         replica when n_envs == 1, else replica 0) or a list with one 5-tuple per replica."""
         if self._loaded and "episode_final" not in self._stepper.buf:
-            self._last_ep_metrics_host = self.metrics_of(0)   # base_env.py:893-896: reset() stores the old episode's metrics
+            # base_env.py:763-765: the finished episode's metrics as _finalize_logs saw them (before it was counted)
+            self._last_ep_metrics_host = self.metrics_of(0, _count_finished=False)
         if self._loaded and self._rs is not None:
             self._completions = self.completions()
             self._sync_streams_from_device()
@@ -582,11 +583,17 @@ class BatchedFoundationEnv:
         """The combined scenario + component metrics of env 0 (BaseEnvironment.metrics, base_env.py:421-432)."""
         return self.metrics_of(0)
 
-    def metrics_of(self, e):
+    def metrics_of(self, e, _count_finished=True):
         """`env.metrics` of replica e: layout_from_file.py:595-650 + every component's get_metrics(), computed from the
         replica's state record (the event logs are device-side running sums, see foundation/metrics.py)."""
         from .metrics import metrics_from_state
-        return metrics_from_state(self._spec, self._stepper.read_state(e),
+        st = self._stepper.read_state(e)
+        if _count_finished and int(np.asarray(st["t"]).reshape(-1)[0]) >= self._episode_length:
+            # a finished episode waiting for its reset(): the reference has already counted it (base_env.py:1021-1025),
+            # which shows in the completion-driven labor/weighted_cost
+            st = dict(st)
+            st["completions"] = np.asarray(st["completions"]) + 1
+        return metrics_from_state(self._spec, st,
                                   saez_elasticity=self._saez.est[e].elas_tm1 if self._saez is not None else None)
 
     @property

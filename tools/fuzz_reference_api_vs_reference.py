@@ -66,12 +66,26 @@ def run_one(name, kw, seed):
         rng = np.random.RandomState(seed * 10 + ep)
         o1, o2 = ref.reset(), mine.reset()
         same(o1, o2, "ep %d reset" % ep)
+        if ep > 0:   # previous_episode_metrics: what _finalize_logs stored when the last episode ended
+            with np.errstate(all="ignore"):
+                p1, p2 = ref.previous_episode_metrics, mine.previous_episode_metrics
+            assert set(p1) == set(p2)
+            for k, v in p1.items():
+                a, b = float(v), float(p2[k])
+                assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-6 * max(1.0, abs(a)), "ep %d prev metric %s: %r vs %r" % (ep, k, a, b)
         for t in range(12):
             a = pick(ref, o1, rng)
             (o1, r1, d1, _), (o2, r2, d2, _) = ref.step(a), mine.step(a)
             same(o1, o2, "ep %d t %d obs" % (ep, t)); same(r1, r2, "ep %d t %d rew" % (ep, t))
             assert d1 == d2
         assert int(ref._completions) == mine._completions
+        # env.metrics at the end of the episode (scenario + every component's get_metrics)
+        with np.errstate(all="ignore"):
+            m1, m2 = ref.metrics, mine.metrics
+        assert set(m1) == set(m2), "ep %d metrics keys %s" % (ep, sorted(set(m1) ^ set(m2))[:6])
+        for k, v in m1.items():
+            a, b = float(v), float(m2[k])
+            assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-6 * max(1.0, abs(a)), "ep %d metric %s: %r vs %r" % (ep, k, a, b)
 
 
 if __name__ == "__main__":
