@@ -124,7 +124,7 @@ def save_episode_log(game_object, filepath, compression_level=16):
     try:
         import lz4.frame
         payload = lz4.frame.compress(log_bytes, compression_level=max(0, min(16, int(compression_level))))
-    except ImportError:
+    except (ImportError, AttributeError):   # no lz4 package (or an empty stand-in module): the built-in frame writer
         payload = lz4_frame_compress(log_bytes)
     with open(filepath, "wb") as fh:
         fh.write(payload)
@@ -137,5 +137,5 @@ def load_episode_log(filepath):
     try:
         import lz4.frame
         return json.loads(lz4.frame.decompress(buf))
-    except ImportError:
+    except (ImportError, AttributeError):
         return json.loads(lz4_frame_decompress(buf))
