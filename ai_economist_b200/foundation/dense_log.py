@@ -146,6 +146,12 @@ class DenseLogger:
             rates = [float(spec["disc_rates"][int(i)]) for i in np.asarray(st["rate_idx"])[:B]]
         else:
             rates = [float(v) for v in list(spec["fixed_rates"])[:B]]
+            if spec["tax_model"] == 1 and int(spec.get("tax_annealing", 0)):
+                # a fixed schedule under a tax_annealing_schedule is clipped by this episode's annealed maximum
+                # (redistribution.py:390-413; components/utils.py:10-57)
+                done_eps = int(np.asarray(st["completions"]).reshape(-1)[0])
+                vis = max(0.0, min(1.0, float(spec["annealing_slope"]) * (done_eps - float(spec["annealing_warmup"]))))
+                rates = [min(r, vis * float(spec["rate_max"])) for r in rates]
         d = {"schedule": rates, "cutoffs": [float(v) for v in list(spec["bracket_cutoffs"])[:B]]}
         lump = float(np.sum(paid) / A)
         for a in range(A):

@@ -57,7 +57,7 @@ def pick(env, obs, rng):
 
 def run_one(name, kw, seed):
     cfg = dict(kw, scenario_name=name, flatten_observations=bool(seed % 2), flatten_masks=bool((seed // 2) % 2),
-               episode_length=12)
+               episode_length=12, dense_log_frequency=1, world_dense_log_frequency=5)
     f = rh.load_reference_foundation()
     ref = f.make_env_instance(**cfg)
     mine = foundation.make_env_instance(**cfg, reference_api=True, stepper_factory=emu_factory)
@@ -79,6 +79,11 @@ def run_one(name, kw, seed):
             same(o1, o2, "ep %d t %d obs" % (ep, t)); same(r1, r2, "ep %d t %d rew" % (ep, t))
             assert d1 == d2
         assert int(ref._completions) == mine._completions
+        # the dense log of the episode that just ended (world / states / actions / rewards + every component's log)
+        from tests.test_dense_log import same as same_log
+        import json
+        same_log(json.loads(json.dumps(ref.previous_episode_dense_log)), json.loads(json.dumps(mine.previous_episode_dense_log)),
+                 "ep %d dense log" % ep)
         # env.metrics at the end of the episode (scenario + every component's get_metrics)
         with np.errstate(all="ignore"):
             m1, m2 = ref.metrics, mine.metrics
