@@ -89,6 +89,12 @@ def run_one(cfg, seed, episodes=4):
         assert np.allclose(want_rew, got_rew, rtol=1e-6, atol=1e-9), "t=%d rewards" % t
         if done["__all__"]:
             obs = ref.reset()
+            with np.errstate(all="ignore"):   # the finished episode's metrics: _finalize_logs vs the device's end-of-episode snapshot
+                p1, p2 = ref.previous_episode_metrics, env.previous_episode_metrics_of(1)
+            assert set(p1) == set(p2), "t=%d previous metrics keys %s" % (t, sorted(set(p1) ^ set(p2))[:5])
+            for k, v in p1.items():
+                a, b = float(v), float(p2[k])
+                assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-6 * max(1.0, abs(a)), "t=%d previous metric %s: %r vs %r" % (t, k, a, b)
         compare("t=%d%s" % (t, " (after reset)" if done["__all__"] else ""))
 
 
