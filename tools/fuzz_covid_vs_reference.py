@@ -1,0 +1,78 @@
+"""Randomised fuzz (build container only): the COVID-19 device code (1-lane emulation; history scan and persistent change
+list) against the LIVE reference under random unmasked policies, over scenario / component parameter variants.
+python tools/fuzz_covid_vs_reference.py [n] [seed]"""
+import contextlib
+import io
+import os
+import sys
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ai_economist_b200.foundation.covid19 import build_covid_params  # noqa: E402
+from oracle import gen_golden_covid as gg  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+from tests.emu.emu_stepper import EmuCovidStepper  # noqa: E402
+
+KEYS = ["agent_state", "postsubsidy", "lagged", "policy_ind", "scalars", "mask_a", "mask_p"]
+
+
+def random_kwargs(rng):
+    kw = dict(gg.COVID_KWARGS)
+    kw.update(episode_length=int(rng.choice([40, 90])), action_cooldown_period=int(rng.choice([1, 7, 28])),
+              subsidy_interval=int(rng.choice([1, 30, 90])), num_subsidy_levels=int(rng.choice([5, 20])),
+              start_date=str(rng.choice(["2020-03-22", "2020-06-01", "2020-10-15"])),
+              economic_reward_crra_eta=float(rng.choice([0.5, 2.0, 3.0])),   # (eta = 1 is 0 / 0 in the reference)
+              health_priority_scaling_agents=float(rng.choice([0.3, 1.0])),
+              health_priority_scaling_planner=float(rng.choice([0.45, 2.0])), delivery_interval=int(rng.choice([1, 7])),
+              vaccine_delivery_start_date=str(rng.choice(["2021-01-12", "2020-07-01"])),
+              daily_vaccines_per_million_people=int(rng.choice([3000, 10000])))
+    return kw
+
+
+def run_one(kw, seed):
+    f = rh.load_reference_foundation()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = f.make_env_instance(**gg.reference_config(kw))
+        obs = ref.reset()
+    p = build_covid_params(**kw)
+    emus = [EmuCovidStepper(p, 1, auto_reset=False, change_list=cl) for cl in (False, True)]
+    for s in emus:
+        s.reset()
+    rng = np.random.RandomState(seed)
+
+    def check(t, ra):
+        for s in emus:
+            o = s.read_obs(0)
+            for k in KEYS + (["rew_a"] if t else []):
+                assert np.allclose(ra[k], o[k], rtol=1e-6, atol=1e-9), "t=%d %s (change_list=%s)" % (t, k, s.change_list)
+            if t:
+                assert np.isclose(float(ra["rew_p"]), float(o["rew_p"]), rtol=1e-6, atol=1e-9) and int(ra["done"]) == int(o["done"])
+
+    check(0, gg.ref_arrays(ref, obs))
+    for t in range(1, kw["episode_length"] + 1):
+        act_a, act_p = gg.sample(obs, rng)
+        actions = {str(i): int(act_a[i]) for i in range(51)}
+        actions["p"] = int(act_p)
+        obs, rew, done, _ = ref.step(actions)
+        for s in emus:
+            s.buf["actions_agent"][0] = act_a
+            s.buf["actions_planner"][0] = act_p
+            s.step()
+        check(t, gg.ref_arrays(ref, obs, rew, done))
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    bad = 0
+    for i in range(n):
+        kw = random_kwargs(rng)
+        try:
+            run_one(kw, 900 + i)
+        except Exception as ex:  # noqa: BLE001
+            bad += 1
+            print("[%d] FAILED %r\n    %s" % (i, kw, "".join(traceback.format_exception_only(type(ex), ex)).strip()[:400]))
+    print("%d configs, %d failures" % (n, bad))
