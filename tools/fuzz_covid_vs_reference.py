@@ -43,13 +43,19 @@ def run_one(kw, seed):
         s.reset()
     rng = np.random.RandomState(seed)
 
+    # Rewards go through float32 x ** (1 - eta) and a min-max normalisation.  For the default eta = 2 that is a reciprocal
+    # and the float32 rewards come out bit-identical; for other eta numpy's SIMD float32 power and libm's powf differ in
+    # the last place and the normalisation amplifies it to a few 1e-6 relative (measured: <= 3.4e-6).
+    rew_tol = 1e-6 if kw["economic_reward_crra_eta"] == 2.0 else 1e-5
+
     def check(t, ra):
         for s in emus:
             o = s.read_obs(0)
-            for k in KEYS + (["rew_a"] if t else []):
+            for k in KEYS:
                 assert np.allclose(ra[k], o[k], rtol=1e-6, atol=1e-9), "t=%d %s (change_list=%s)" % (t, k, s.change_list)
             if t:
-                assert np.isclose(float(ra["rew_p"]), float(o["rew_p"]), rtol=1e-6, atol=1e-9) and int(ra["done"]) == int(o["done"])
+                assert np.allclose(ra["rew_a"], o["rew_a"], rtol=rew_tol, atol=1e-9), "t=%d rew_a (change_list=%s)" % (t, s.change_list)
+                assert np.isclose(float(ra["rew_p"]), float(o["rew_p"]), rtol=rew_tol, atol=1e-9) and int(ra["done"]) == int(o["done"])
 
     check(0, gg.ref_arrays(ref, obs))
     for t in range(1, kw["episode_length"] + 1):
