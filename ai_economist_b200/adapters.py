@@ -307,15 +307,22 @@ class ReferenceApiEnv:
         ba[e] = 0
         bp[e] = 0
         for k, v in (actions or {}).items():
-            if isinstance(v, dict):   # {subspace name: index} form of single-action agents (base_agent.py:419-427)
+            if isinstance(v, dict):   # {subspace name: index}
                 ag = env.get_agent(k)
-                assert len(v) <= 1
-                g, lo = 0, 1
-                for name in ag._action_names:
-                    if name in v and int(v[name]) > 0:
-                        g = lo + int(v[name]) - 1
-                    lo += int(ag.action_dim[name])
-                v = g
+                unknown = set(v) - set(ag._action_names)
+                assert not unknown, "unknown action subspace(s) %s" % sorted(unknown)
+                if ag.multi_action_mode:
+                    # one entry per named subspace, the others stay NO-OP (set_component_action per name,
+                    # base_agent.py:367-383; the reference's own dict branch only covers single-action agents)
+                    v = [int(v.get(name, 0)) for name in ag._action_names]
+                else:         # single-action agents (base_agent.py:419-427): at most one named sub-action
+                    assert len(v) <= 1
+                    g, lo = 0, 1
+                    for name in ag._action_names:
+                        if name in v and int(v[name]) > 0:
+                            g = lo + int(v[name]) - 1
+                        lo += int(ag.action_dim[name])
+                    v = g
             row = np.atleast_1d(np.asarray(v)).astype(np.int32)
             if str(k) == "p":
                 if st.dims.n_act_planner:

@@ -35,6 +35,20 @@ struct State {
     size_t compact_bytes = 0;
     cudaEvent_t slice_ev[8] = {};   // one per transfer slice of the compacted D2H copy
 };
+// Makes `device` current for the lifetime of the object and restores the caller's device afterwards, so a handle
+// created for cuda:1 works while cuda:0 is current (streams passed in must belong to the handle's device).
+struct DevScope {
+    int prev = -1; bool ok_ = true;
+    explicit DevScope(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev == device) { prev = -1; return; }
+        ok_ = cudaSetDevice(device) == cudaSuccess;
+        if (!ok_) cudaGetLastError();
+    }
+    ~DevScope() { if (prev >= 0) cudaSetDevice(prev); }
+    bool ok() const { return ok_; }
+};
+int check_device(int device);
 int init(aie_env *);
 void destroy(aie_env *);
 int upload(aie_env *, void *dst, const void *src, size_t n, void *stream);
@@ -302,17 +316,27 @@ static int cuda_fail(cudaError_t e, const char *what) {
 }
 #define AIE_CUDA(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
 
-int init(aie_env *env) {
+int check_device(int device) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return fail(AIE_ECUDA, std::string("no CUDA device: this library has no CPU fallback (") +
                                    (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)) + ")");
-    if (env->device < 0 || env->device >= ndev) return fail(AIE_EINVAL, "device ordinal out of range");
+    if (device < 0 || device >= ndev) return fail(AIE_EINVAL, "device ordinal out of range");
+    int major = 0;
+    AIE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device), "cudaDeviceGetAttribute");
+    if (major < 10) return fail(AIE_ECUDA, "this build targets sm_100a (Blackwell B200) only");
+    return AIE_OK;
+}
+
+int init(aie_env *env) {
+    {
+        const int rc = check_device(env->device);
+        if (rc != AIE_OK) return rc;
+    }
     AIE_CUDA(cudaSetDevice(env->device), "cudaSetDevice");
     cudaDeviceProp prop;
     AIE_CUDA(cudaGetDeviceProperties(&prop, env->device), "cudaGetDeviceProperties");
-    if (prop.major < 10) return fail(AIE_ECUDA, "this build targets sm_100a (Blackwell B200) only");
     const DevCfg &c = env->cfg;
     const size_t max_smem = prop.sharedMemPerBlockOptin;
     const size_t per_env = (size_t)c.resident_bytes + c.step_scratch_bytes + c.obs_extra_bytes;
@@ -345,7 +369,9 @@ int init(aie_env *env) {
         fprintf(stderr, "[aie] record %d B (resident %d, obs prefix %d), step scratch %d, obs scratch %d (alias mt %d), per env %zu B, "
                         "%d envs/CTA, %zu B smem/CTA, register variant %d, %d CTAs/SM fit\n", c.rec_bytes, c.resident_bytes, c.obs_prefix_bytes,
                 c.step_scratch_bytes, c.obs_scratch_bytes, c.obs_alias_mt, per_env, wpb, env->be.step_smem, env->be.step_minb, fit);
-    const int sm = (int)env->be.step_smem;
+    // The attribute belongs to the function (per device, process-wide), not to this handle: a second env with a smaller
+    // record must not lower it under the first one, so every kernel is simply opted in to the device maximum.
+    const int sm = (int)max_smem;
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
@@ -360,9 +386,9 @@ int init(aie_env *env) {
         AIE_CUDA(cudaMemcpy(env->be.tab_dev, env->tables.w, sizeof(Tables), cudaMemcpyHostToDevice), "upload tables");
         env->bufs.tab = env->be.tab_dev;
     }
-    AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.step_smem), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->be.obs_smem), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     return AIE_OK;
 }
 void destroy(aie_env *env) {

@@ -14,6 +14,8 @@
 //   int launch_pack(aie_env*, const aie::CompactLayout&, uint8_t *dev, void *stream);
 //   int download_slice(aie_env*, int k, void *host, const void *dev, size_t n, void *stream);   (async copy + event k)
 //   int wait_slice(aie_env*, int k);                                                           (any thread)
+//   struct DevScope { DevScope(int device); ~DevScope(); bool ok() const; };   makes `device` current for the scope of one
+//       entry point and restores the caller's device on exit (a handle can be used while another device is current)
 #include <string>
 #include <vector>
 
@@ -36,6 +38,9 @@ struct aie_env {
 };
 
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+// every entry point that touches the device runs with the handle's own device current (and puts the caller's back)
+#define AIE_DEVICE_SCOPE(dev) aie::be::DevScope dev_scope_(dev); \
+    if (!dev_scope_.ok()) return fail(AIE_ECUDA, "cannot make the handle's CUDA device current")
 
 extern "C" {
 
@@ -52,6 +57,7 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     env->ucfg = *cfg; env->n_envs = n_envs; env->device = device;
     memset(&env->bufs, 0, sizeof(env->bufs));
     env->bound = env->loaded = false; env->launches = 0; env->sample_calls = 0;
+    aie::be::DevScope dev_scope_(device);   // init() validates the ordinal itself and reports the precise error
     rc = aie::be::init(env);
     if (rc != AIE_OK) { delete env; return rc; }
     *out = env;
@@ -60,6 +66,7 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
 
 int aie_destroy(aie_env *env) {
     if (!env) return AIE_OK;
+    aie::be::DevScope dev_scope_(env->device);
     aie::be::destroy(env);
     delete env->pool;
     delete env;
@@ -114,6 +121,7 @@ int aie_bind_buffers(aie_env *env, const aie_buffers *b) {
 int aie_load_state(aie_env *env, const aie_host_state *hs, int32_t env_lo, void *stream) {
     if (!env || !hs) return fail(AIE_EINVAL, "null argument");
     if (!env->bound) return fail(AIE_ESTATE, "aie_load_state: buffers not bound");
+    AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     if (hs->n < 1 || env_lo < 0 || env_lo + hs->n > env->n_envs) return fail(AIE_EINVAL, "aie_load_state: env range out of bounds");
     if (!hs->stone || !hs->wood || !hs->stone_src || !hs->wood_src || !hs->loc || !hs->coin || !hs->build_payment ||
@@ -143,18 +151,21 @@ int aie_load_state(aie_env *env, const aie_host_state *hs, int32_t env_lo, void 
 int aie_step(aie_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
     return aie::be::launch_step(env, 1, stream);  // dynamics + observations fused in one launch
 }
 
 int aie_step_dynamics(aie_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_dynamics: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
     return aie::be::launch_step(env, 0, stream);
 }
 
 int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_sample_random_actions: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
 #if AIE_FUSED_POLICY
     // tuning variant: after the first call (which still samples for the very first step) the step kernel draws the next
     // step's actions itself; later calls only refresh the seed
@@ -168,12 +179,14 @@ int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream) {
 int aie_observe(aie_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_observe: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
     return aie::be::launch_observe(env, 0, env->n_envs, stream);
 }
 
 int aie_step_host(aie_env *env, const int32_t *act_a, const int32_t *act_p, const aie_host_out *o, void *stream) {
     if (!env || !act_a || !o) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_host: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     const size_t E = env->n_envs, A = c.A;
     int rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * A * c.n_act_a * 4, stream);
@@ -209,6 +222,7 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
                           void *stream) {
     if (!env || !act_a || !o) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_host_compact: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     const size_t E = env->n_envs;
     int rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * c.A * c.n_act_a * 4, stream);
@@ -258,6 +272,7 @@ int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out) {
     if (!env || !out) return fail(AIE_EINVAL, "null argument");
     if (!env->bound) return fail(AIE_ESTATE, "aie_read_state: buffers not bound");
     if (e < 0 || e >= env->n_envs) return fail(AIE_EINVAL, "aie_read_state: env index out of range");
+    AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     std::vector<uint8_t> rec(c.rec_bytes);
     int rc = aie::be::sync_all(env);  // debug path: order against work on any stream
@@ -274,6 +289,7 @@ int aie_read_episode_final(aie_env *env, int32_t e, const aie_state_dump *out) {
     if (!env || !out) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->bufs.final) return fail(AIE_ESTATE, "aie_read_episode_final: no episode_final buffer bound");
     if (e < 0 || e >= env->n_envs) return fail(AIE_EINVAL, "aie_read_episode_final: env index out of range");
+    AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     std::vector<uint8_t> rec(c.rec_bytes);
     int rc = aie::be::sync_all(env);

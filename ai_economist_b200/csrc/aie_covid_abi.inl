@@ -34,6 +34,11 @@ int aie_covid_create(const aie_covid_config *u, int32_t n_envs, int32_t device, 
                          u->max_agent_econ, u->w_agent_health, u->w_agent_econ, u->conv_weights, u->conv_filters,
                          u->max_daily_subsidy_per_state, u->rw_policy, u->init_state};
     for (const void *p : req) if (!p) return fail(AIE_EINVAL, "aie_covid_create: a parameter array is NULL");
+    {
+        const int rc_dev = aie::be::check_device(device);   // same rules as aie_create: a real sm_100 device, no CPU path
+        if (rc_dev != AIE_OK) return rc_dev;
+    }
+    AIE_DEVICE_SCOPE(device);
     aie_covid_env *env = new (std::nothrow) aie_covid_env();
     if (!env) return fail(AIE_ENOMEM, "out of host memory");
     env->n_envs = n_envs; env->device = device; env->bound = env->loaded = false; env->launches = 0; env->sample_calls = 0;
@@ -83,6 +88,7 @@ int aie_covid_create(const aie_covid_config *u, int32_t n_envs, int32_t device, 
 
 int aie_covid_destroy(aie_covid_env *env) {
     if (!env) return AIE_OK;
+    aie::be::DevScope dev_scope_(env->device);
     for (void *d : env->owned) aie::be::const_free(d);
     delete env;
     return AIE_OK;
@@ -107,6 +113,7 @@ int aie_covid_bind_buffers(aie_covid_env *env, const aie_covid_buffers *b) {
 int aie_covid_reset(aie_covid_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound) return fail(AIE_ESTATE, "aie_covid_reset: buffers not bound");
+    AIE_DEVICE_SCOPE(env->device);
     int rc = aie::be::covid_launch_reset(env, stream);
     if (rc == AIE_OK) env->loaded = true;
     return rc;
@@ -115,12 +122,14 @@ int aie_covid_reset(aie_covid_env *env, void *stream) {
 int aie_covid_step(aie_covid_env *env, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_covid_step: bind buffers and reset first");
+    AIE_DEVICE_SCOPE(env->device);
     return aie::be::covid_launch_step(env, stream);
 }
 
 int aie_covid_sample_random_actions(aie_covid_env *env, uint64_t seed, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_covid_sample_random_actions: bind buffers and reset first");
+    AIE_DEVICE_SCOPE(env->device);
     return aie::be::covid_launch_sample(env, aie::host_mix64(seed) ^ aie::host_mix64(++env->sample_calls), stream);
 }
 

@@ -352,8 +352,9 @@ class BatchedFoundationEnv:
     def reset(self, seed_state=None, force_dense_logging=False):
         """seed_state: optional numpy stream state(s) to start the reset from (base_env.py:873-884) - one 5-tuple (every
         replica when n_envs == 1, else replica 0) or a list with one 5-tuple per replica."""
-        if self._loaded and "episode_final" not in self._stepper.buf:
-            # base_env.py:763-765: the finished episode's metrics as _finalize_logs saw them (before it was counted)
+        if self._loaded and "episode_final" not in self._stepper.buf and self._episode_finished(0):
+            # base_env.py:763-765, 1022-1025: _finalize_logs stores the metrics only on the step that ENDS an episode, so
+            # resetting an unfinished episode (or resetting twice) leaves previous_episode_metrics untouched
             self._last_ep_metrics_host = self.metrics_of(0, _count_finished=False)
         if self._loaded and self._rs is not None:
             self._completions = self.completions()
@@ -384,6 +385,12 @@ class BatchedFoundationEnv:
             self._saez.after_host_reset(saez_n)
         self._start_dense_log(force_dense_logging, int(self._completions[0]))
         return self.obs
+
+    def _episode_finished(self, e):
+        st = self._stepper
+        if not hasattr(st, "state_view"):
+            return True
+        return int(st.to_numpy(st.state_view("t")[e:e + 1])[0]) >= self._episode_length
 
     def completions(self):
         """Completed episodes per replica (BaseEnvironment._completions, base_env.py:1021-1025: incremented on the step

@@ -23,6 +23,8 @@ struct aie_env;
 struct aie_covid_env;
 namespace aie { namespace be {
 struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; std::vector<uint8_t> compact_dev, compact_host; };
+struct DevScope { explicit DevScope(int) {} bool ok() const { return true; } };
+int check_device(int device);
 int init(aie_env *);
 void destroy(aie_env *);
 int upload(aie_env *, void *dst, const void *src, size_t n, void *stream);
@@ -49,6 +51,7 @@ int covid_launch_sample(aie_covid_env *, uint64_t key, void *stream);
 #include "../../ai_economist_b200/csrc/aie_covid_abi.inl"
 
 namespace aie { namespace be {
+int check_device(int) { return AIE_OK; }
 int init(aie_env *env) {
     env->be.scratch.assign((size_t)env->cfg.step_scratch_bytes + env->cfg.obs_scratch_bytes + 64, 0);
     env->bufs.tab = env->tables.w;
