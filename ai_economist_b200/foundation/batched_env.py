@@ -284,6 +284,14 @@ class BatchedFoundationEnv:
             has_g, val_g = (s[3], s[4]) if gauss is None else (int(gauss[e][1] != 0.0), float(gauss[e][0]))
             rs.set_state((s[0], np.asarray(k, np.uint32), p, has_g, val_g))
 
+    def load_host_state(self, host_state, env_lo=0):
+        """Upload host reset snapshots (the arrays `host_reset_arrays()` returns, or a caller's own states in the same
+        layout) for replicas [env_lo, env_lo + n) and mark the env ready to step - the public form of what `reset()`
+        does after running the host reset (aie_load_state)."""
+        self._stepper.load_state(host_state, env_lo=env_lo)
+        self._loaded = True
+        return self.obs
+
     def host_reset_arrays(self):
         """Run the reference-faithful host reset for every env; returns the aie_host_state arrays."""
         if self._rs is None:

@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — agent-env-steps/sec of the gather-trade-build step (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path (random-policy action sampling -> dynamics -> observations) over one batch
-of synthetic env replicas: at N GPUs every rank steps its own `--envs-per-gpu` replicas (weak scaling, no
+of synthetic env replicas: at N GPUs every rank steps its own `envs_per_gpu` replicas (weak scaling, no
 collective on the step path).  Rank 0 prints ONE JSON line.
 
-  value   whole-job agent-env-steps/s, inputs and outputs resident in HBM, K steps timed on the device
-          (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks)
-  e2e     the same metric through aie_step_host with HOST (pinned) buffers: actions copied H2D and every
-          observation / mask / reward / done tensor copied D2H inside the timed region, every step
+  value     whole-job agent-env-steps/s, inputs and outputs resident in HBM, K steps timed on the device
+            (CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks)
+  sustained the same K-step region repeated until >= ~1 s of device time has been measured: median over repeats
+            (the driver's K is small; this is the number that does not depend on one 3 ms window)
+  e2e       the same metric through the C-ABI host entry point with HOST (pinned) buffers: actions copied H2D and
+            every observation / mask / reward / done tensor delivered to host memory inside the timed region
   roofline  per-kernel algorithmic bytes / CUDA-event duration against MEASURED_PEAKS.json (HBM)
   cpu_baseline  the CPU oracle (oracle/, a C port of the reference step) on this box's host cores
---impl reference times that CPU oracle alone (the reference itself is Python and cannot travel to the box).
+  workloads the other BASELINE configs (c3, c4 = COVID, c5) measured the same way in the same process (headline c2 only)
+
+Episode phases are staggered before anything is timed (replica e starts at t = e*T/E and one full episode of steps is
+run untimed), so every timed window sees the whole episode distribution - full order books, houses, tax days and the
+per-step share of auto-resets - instead of 8192 replicas in lock-step at t = 5..25.
+
+--impl reference times the CPU oracle alone (the reference itself is Python and cannot travel to the box).
 """
 import argparse
 import json
@@ -35,21 +43,42 @@ UNIT = "agent-env-steps/s"
 
 WORKLOADS = {
     # BASELINE.json configs[1]: gather-trade-build, 4 agents, 25x25, 8192 env replicas per B200
-    "c2": dict(cfg="c1_tutorial", envs_per_gpu=8192,
+    "c2": dict(cfg="c1_tutorial", envs_per_gpu=8192, agents=4, world=[25, 25], steps=None,
                desc="gather-trade-build (layout_from_file/simple_wood_and_stone: Build+CDA+Gather), 4 agents, "
-                    "25x25, 8192 env replicas per GPU, uniformly random unmasked actions"),
-    # BASELINE.json configs[2]: + PeriodicBracketTax planner, 10 agents, 40x40, 8192 env replicas per GPU
-    "c3": dict(cfg="c3_paper_tax", envs_per_gpu=8192,
-               desc="gather-trade-build + PeriodicBracketTax, 10 agents, 40x40, 8192 env replicas per GPU"),
-    # BASELINE.json configs[4]: ContinuousDoubleAuction stress, 64 agents, 64x64, deep book, 16384 envs over 8 GPUs
+                    "25x25, 8192 env replicas per GPU, uniformly random unmasked actions",
+               l2="no explicit flush: each step rewrites 296 MB of observations (> 126 MB L2) and touches 46 MB of state"),
+    # BASELINE.json configs[2]: + PeriodicBracketTax planner, 10 agents, 40x40, 65536 envs over 8 GPUs = 8192 per GPU
+    "c3": dict(cfg="c3_paper_tax", envs_per_gpu=8192, agents=10, world=[40, 40], steps=100,
+               desc="gather-trade-build + PeriodicBracketTax, 10 agents, 40x40, 8192 env replicas per GPU",
+               l2="no explicit flush: each step rewrites 390 MB of observations (> 126 MB L2) and touches 87 MB of state"),
     # BASELINE.json configs[3]: COVID-19 scenario (51 US-state agents + federal planner), 4096 envs per GPU
-    "c4": dict(cfg="covid", envs_per_gpu=4096,
+    "c4": dict(cfg="covid", envs_per_gpu=4096, agents=51, world=[1, 1], steps=540,
                desc="COVID-19 + economy (CovidAndEconomySimulation: ControlUSStateOpenCloseStatus + "
-                    "FederalGovernmentSubsidy + VaccinationCampaign), 51 state agents + planner, 4096 env replicas per GPU"),
-    "c5": dict(cfg="c5_full", envs_per_gpu=2048,
+                    "FederalGovernmentSubsidy + VaccinationCampaign), 51 state agents + planner, 4096 env replicas per GPU",
+               l2="no explicit flush: per-step footprint 163 MB (stringency history re-read every step) > 126 MB L2"),
+    # BASELINE.json configs[4]: ContinuousDoubleAuction stress, 64 agents, 64x64, deep book, 16384 envs over 8 GPUs
+    "c5": dict(cfg="c5_full", envs_per_gpu=2048, agents=64, world=[64, 64], steps=60,
                desc="CDA stress (uniform/simple_wood_and_stone: Build+CDA(max_num_orders=50)+Gather, multi-action agents), "
-                    "64 agents, 64x64, 2048 env replicas per GPU"),
+                    "64 agents, 64x64, 2048 env replicas per GPU",
+               l2="no explicit flush: each step rewrites 740 MB of observations (> 126 MB L2) and touches 126 MB of state"),
 }
+
+
+def workload_config(key, E):
+    """The `config` object of the JSON line - identical for the GPU arm and the reference (CPU) arm."""
+    w = WORKLOADS[key]
+    return {"workload": w["desc"], "envs_per_gpu": E, "n_agents": w["agents"], "world": w["world"],
+            "actions": "uniformly random unmasked actions, drawn inside the timed region", "auto_reset": True,
+            "episode_phase": "staggered: replica e starts at t = e*T/E, one untimed episode of steps before timing",
+            "l2": w["l2"]}
+
+
+def host_cores():
+    """Host threads this process may actually use (cgroup / affinity aware)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def peaks():
@@ -63,12 +92,16 @@ def peaks():
 
 
 def committed_traffic(workload, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
-    capture of this same command (profiles/); None when no capture exists for the workload."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the newest committed `ncu --set full`
+    capture of this workload (profiles/r*_ncu_full_<kernel>[_<workload>]_raw.csv); None when there is none."""
     import csv
     import glob
-    found = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_%s_raw.csv" % kernel)))  # newest round last
-    if workload != "c2" or not found:
+    pats = ["r*_ncu_full_%s_%s_raw.csv" % (kernel, workload)]
+    if workload == "c2":
+        pats.append("r*_ncu_full_%s_raw.csv" % kernel)
+    found = sorted(sum((glob.glob(os.path.join(ROOT, "profiles", p)) for p in pats), []),
+                   key=lambda p: os.path.basename(p)[:4])  # by round tag
+    if not found:
         return None, None
     path = found[-1]
     try:
@@ -82,12 +115,11 @@ def committed_traffic(workload, kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region.
+    """nvidia-smi clocks + throttle reasons sampled DURING the measured regions.
 
-    The sampler is started before the warm-up steps (nvidia-smi takes a few hundred ms to come up) at a 20 ms period;
-    mark_begin()/mark_end() bracket the timed region on the host clock and only samples time-stamped inside it are
-    reported.  If the region was shorter than one sampling period, the samples of the warm-up + timed window (the same
-    step loop, back to back) are reported instead and "window" says so."""
+    Started before the warm-up steps (nvidia-smi takes a few hundred ms to come up) at a 20 ms period; mark_begin() /
+    mark_end() bracket, on the host clock, the K-step timed region plus its `sustained` repeats (the same loop, back to
+    back) and only samples time-stamped inside are reported."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -142,10 +174,10 @@ class ClockSampler:
                 continue
         t0, t1 = self.t0 or 0.0, self.t1 or time.time()
         inside = [p for p in parsed if t0 <= p[0] <= t1 + 0.005]
-        window = "timed region"
+        window = "timed region + sustained repeats"
         if not inside:
             inside = [p for p in parsed if (self.t_start or 0.0) <= p[0] <= t1 + 0.03]
-            window = "warm-up + timed region (timed region shorter than the 20 ms sampling period)"
+            window = "warm-up + timed region (measured regions shorter than the 20 ms sampling period)"
         sm, mx, reasons = [p[1] for p in inside], [p[2] for p in inside], set()
         for p in inside:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[3]):
@@ -155,11 +187,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is test infrastructure; bench.py may execute it only here: cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------------
 def covid_oracle_rate(n_envs, steps, warmup=1):
     """agent-env-steps/s of the numpy COVID oracle (single host thread per env loop; numpy releases no parallelism)."""
     from ai_economist_b200.foundation.covid19 import build_covid_params
+    from ai_economist_b200.workloads import COVID_KWARGS
     from oracle.covid_oracle import CovidOracleEnv
-    from oracle.gen_golden_covid import COVID_KWARGS
     p = build_covid_params(**COVID_KWARGS)
     envs = [CovidOracleEnv(p) for _ in range(n_envs)]
     rng = np.random.RandomState(0)
@@ -175,292 +210,193 @@ def covid_oracle_rate(n_envs, steps, warmup=1):
     return n_envs * 51 * steps / total, total
 
 
-def oracle_rate(cfg_name, n_envs, steps, threads, warmup=2, seed0=500000):
-    """agent-env-steps/s of the CPU oracle (C port of the reference step) with `threads` host threads.
-    Host-side action sampling is excluded from the timed region (as on the GPU side of `value`)."""
-    from oracle.oracle import OracleBatch
-    from tests import batch_utils as bu
+class OracleRunner:
+    """The C oracle (port of the reference step) over n_envs replicas of one workload, driven with a host-side random
+    policy whose sampling is excluded from the timed region (as the device-side sampler is on the GPU side of `value`)."""
 
-    env = _HostOnlyEnv(cfg_name, n_envs, seed0)
-    host = env.host_reset_arrays()
-    orc = OracleBatch(env.spec, n_envs)
-    for e in range(n_envs):
-        orc.load_env(e, {k: v[e] for k, v in host.items()})
-    seg_a, seg_p = bu.segments(env.spec, "a"), bu.segments(env.spec, "p")
-    rng = np.random.RandomState(1)
-    A = env.spec["n_agents"]
+    def __init__(self, cfg_name, n_envs, threads, seed0=500000):
+        from ai_economist_b200 import foundation, workloads as wl
+        from oracle.oracle import OracleBatch
 
-    def masks():
-        ma = np.stack([orc.obs(e)["a_mask"] for e in range(n_envs)])
-        mp = np.stack([orc.obs(e)["p_mask"] for e in range(n_envs)]) if seg_p else None
-        return ma, mp
+        name, kw = wl.product_kwargs(cfg_name)
+        env = foundation.make_env_instance(name, n_envs=n_envs, seed=seed0,
+                                           stepper_factory=lambda spec, n, auto_reset: None, **kw)
+        self.spec, self.n_envs, self.threads = env.spec, n_envs, threads
+        host = env.host_reset_arrays()
+        self.orc = OracleBatch(env.spec, n_envs)
+        for e in range(n_envs):
+            self.orc.load_env(e, {k: v[e] for k, v in host.items()})
+        self.seg_a, self.seg_p = wl.mask_segments(env.spec, "a"), wl.mask_segments(env.spec, "p")
+        self.sample = wl.sample_from_masks
+        self.rng = np.random.RandomState(1)
+        self.A = env.spec["n_agents"]
 
-    total = 0.0
-    for t in range(warmup + steps):
-        ma, mp = masks()
-        aa = bu.sample_from_masks(ma, seg_a, rng)
-        ap = bu.sample_from_masks(mp, seg_p, rng) if seg_p else None
-        t0 = time.perf_counter()
-        orc.step(aa, ap, n_threads=threads)
-        dt = time.perf_counter() - t0
-        if t >= warmup:
-            total += dt
-    return n_envs * A * steps / total, total
+    def run(self, steps, warmup=2):
+        total = 0.0
+        for t in range(warmup + steps):
+            ma, mp = self.orc.masks()           # one C call for every env's masks
+            aa = self.sample(ma, self.seg_a, self.rng)
+            ap = self.sample(mp, self.seg_p, self.rng) if self.seg_p else None
+            t0 = time.perf_counter()
+            self.orc.step(aa, ap, n_threads=self.threads)
+            dt = time.perf_counter() - t0
+            if t >= warmup:
+                total += dt
+        return self.n_envs * self.A * steps / total, total
 
 
-class _HostOnlyEnv:
-    """Host reset + spec without any device (for the CPU oracle legs)."""
+def cpu_baseline_for(key, min_seconds=6.0):
+    """cpu_baseline object: the oracle on this box's host cores over a bounded sample of the workload (>= ~6 s timed)."""
+    w = WORKLOADS[key]
+    if key == "c4":
+        rate, total = covid_oracle_rate(8, 40)
+        return {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "8 env replicas x 40 steps, numpy oracle (one thread), %.1f s" % total}
+    threads = host_cores()
+    per_thread = {"c2": 64, "c3": 32, "c5": 4}[key]
+    n_cpu = max(threads * per_thread, 256)
+    runner = OracleRunner(w["cfg"], n_cpu, threads)
+    probe, _ = runner.run(5, warmup=2)
+    steps_cpu = int(max(10, min(5000, min_seconds * probe / (n_cpu * runner.A))))
+    rate, total = runner.run(steps_cpu, warmup=0)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d env replicas x %d steps of the same workload on %d pinned host threads "
+                      "(C oracle of the reference step), %.1f s" % (n_cpu, steps_cpu, threads, total)}
 
-    def __init__(self, cfg_name, n_envs, seed0):
-        from ai_economist_b200 import foundation
-        from tests import batch_utils as bu
 
-        name, kw = bu.product_kwargs(cfg_name)
-        self.env = foundation.make_env_instance(name, n_envs=n_envs, seed=seed0,
-                                                stepper_factory=lambda spec, n, auto_reset: None, **kw)
-        self.spec = self.env.spec
-
-    def host_reset_arrays(self):
-        return self.env.host_reset_arrays()
+def reference_numpy_note():
+    """The reference's own NumPy step cannot run on the GPU box (/root/reference is not there and its sources may not be
+    copied); its per-core rate measured in the build container is committed with the script that produced it."""
+    p = os.path.join(ROOT, "profiles", "reference_numpy_step.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
-    n_envs = max(threads * 256, 1024)
+    key = args.workload
+    w = WORKLOADS[key]
     t0 = time.perf_counter()
-    if args.workload == "c4":
+    if key == "c4":
         threads, n_envs = 1, 8
         rate, total = covid_oracle_rate(n_envs, args.steps, warmup=args.warmup)
+        steps_run = args.steps
     else:
-        rate, total = oracle_rate(w["cfg"], n_envs, args.steps, threads, warmup=args.warmup)
-    A = {"c2": 4, "c3": 10, "c4": 51, "c5": 64}[args.workload]
+        threads = host_cores()
+        # every timed step is one pass over a bounded sample of the workload: for c2 at least the full per-GPU batch
+        n_envs = max(threads * {"c2": 256, "c3": 64, "c5": 4}[key], {"c2": 8192, "c3": 2048, "c5": 256}[key])
+        runner = OracleRunner(w["cfg"], n_envs, threads)
+        runner.run(max(0, args.warmup - 2), warmup=2)   # W untimed warm-up steps
+        rate, total = runner.run(args.steps, warmup=0)  # exactly K timed steps, each a bounded sample of the workload
+        steps_run = args.steps
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "i32+f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "sample": "%d env replicas per step on %d host threads" % (n_envs, threads)},
+        "impl": "reference", "metric": METRIC if key != "c4" else METRIC.replace("gather-trade-build", "covid19"),
+        "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / steps_run, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32+f64" if key != "c4" else "f32+f64", "data": "synthetic",
+        "config": workload_config(key, w["envs_per_gpu"]),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d env replicas x %d steps (C oracle, pthreads), %.1f s" % (n_envs, args.steps, total)},
+                         "sample": "%d env replicas x %d steps per step-sample (C oracle, %d pinned pthreads), %.1f s"
+                                   % (n_envs, steps_run, threads, total)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_numpy_step": reference_numpy_note(),
         "note": "the reference is pure Python and does not exist on the GPU box; this arm times oracle/ (a C "
-                "restatement pinned to the reference by golden traces), which is far faster than the reference's "
-                "NumPy step (1 251 env-steps/s/core measured in the build container, BASELINE.md)",
+                "restatement pinned to the reference by golden traces) on every host core it may use, which is far "
+                "faster than the reference's own NumPy step (see reference_numpy_step: measured in the build container)",
         "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_covid(args, rank, world, dev, E, w):
-    """BASELINE config 4: one fused kernel per step (+ the random-policy sampler)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, args, rank, world, dev):
+        import torch
+        import torch.distributed as dist
+        self.args, self.rank, self.world, self.dev, self.torch, self.dist = args, rank, world, dev, torch, dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(self, one_step, k):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+        torch = self.torch
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(k):
+            one_step(i)
+        ev1.record()
+        self.barrier()
+        return self.max_over_ranks(ev0.elapsed_time(ev1))
+
+    def sustained(self, one_step, k, first_ms, target_ms=1000.0, max_repeats=200):
+        """Repeat the K-step region until ~target_ms of device time is covered; median ms per step over the repeats."""
+        reps = int(min(max_repeats, max(2, np.ceil(target_ms / max(first_ms, 1e-3)))))
+        per = [first_ms / k]
+        for _ in range(reps - 1):
+            per.append(self.time_steps(one_step, k) / k)
+        return float(np.median(per)), len(per), float(min(per)), float(max(per))
+
+
+def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="compact", e2e_threads=0):
+    """One gather-trade-build workload on this rank's GPU: value / sustained / per-kernel roofline / e2e."""
     import ctypes as C
 
-    import torch
-    import torch.distributed as dist
-
-    from ai_economist_b200 import foundation
-    from oracle.gen_golden_covid import COVID_KWARGS, reference_config
-
-    cfg = reference_config(COVID_KWARGS)
-    name = cfg.pop("scenario_name")
-    env = foundation.make_env_instance(name, n_envs=E, device=str(dev), auto_reset=True, **cfg)
-    env.reset()
-    st = env.stepper
-    S = 51
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    clocks = ClockSampler(dev.index or 0)
-    if rank == 0:
-        clocks.start()
-    for i in range(args.warmup):
-        st.sample_random_actions(seed=7 + rank); st.step()
-    l0 = st.launch_count()
-    barrier()
-    clocks.mark_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        st.sample_random_actions(seed=7 + rank); st.step()
-    ev1.record()
-    barrier()
-    clocks.mark_end()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = st.launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
-    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
-    value = world * E * S * args.steps / (ms_total * 1e-3)
-    # per-kernel durations: the cost of the history scan depends on how many stringency changes the window holds, so
-    # the event-separated pass replays the SAME stretch of the episode as the timed region (reset, same warm-up)
-    env.reset()
-    for i in range(args.warmup):
-        st.sample_random_actions(seed=7 + rank); st.step()
-    n_prof = min(args.steps, 300)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
-    for i in range(n_prof):
-        evs[i][0].record(); st.sample_random_actions(seed=7 + rank)
-        evs[i][1].record(); st.step()
-        evs[i][2].record()
-    torch.cuda.synchronize()
-    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(2)]
-    peak, peak_src = peaks()
-    L = env.params["filter_len"]
-    out_bytes = 4 * (6 * S + 3 * S + 4 + 11 * S + 21 + S) + 8 + 4
-    step_bytes = out_bytes + 2 * (9 * S * 4 + 2 * S * 4 + 16) + (L + 1) * S + S + 4 * S + 4   # + ring read/1-row write + actions
-    kernels = {"aie_covid_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * step_bytes},
-               "aie_covid_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (11 * S * 4 + 21 * 4 + 4 * S)}}
-    for k in kernels.values():
-        k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
-        k["frac"] = k["achieved_gbs"] / peak
-    dom = "aie_covid_step_kernel"
-    # e2e: pinned host actions in, all outputs back
-    names = ["obs_agent_state", "obs_postsubsidy", "obs_lagged_stringency", "obs_policy_indicators", "obs_scalars",
-             "mask_agent", "mask_planner", "reward_agent", "reward_planner", "done"]
-    host = {n: torch.empty(st.buf[n].shape, dtype=st.buf[n].dtype, pin_memory=True) for n in names}
-    act_a = torch.zeros((E, S), dtype=torch.int32, pin_memory=True)
-    act_p = torch.zeros((E,), dtype=torch.int32, pin_memory=True)
-    d2h = sum(t.numel() * t.element_size() for t in host.values())
-    rng = np.random.RandomState(rank)
-    host["mask_agent"].copy_(st.buf["mask_agent"]); host["mask_planner"].copy_(st.buf["mask_planner"])
-    e2e_s, n_e2e = 0.0, max(3, args.e2e_steps)
-    for i in range(n_e2e + 2):
-        ma, mp = host["mask_agent"].numpy(), host["mask_planner"].numpy()
-        act_a.copy_(torch.from_numpy(np.argmax(ma * (rng.random_sample(ma.shape) + 1e-3), axis=1).astype(np.int32)))
-        act_p.copy_(torch.from_numpy(np.argmax(mp * (rng.random_sample(mp.shape) + 1e-3), axis=1).astype(np.int32)))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        st.buf["actions_agent"].copy_(act_a, non_blocking=True); st.buf["actions_planner"].copy_(act_p, non_blocking=True)
-        st.step()
-        for n in names:
-            host[n].copy_(st.buf[n], non_blocking=True)
-        torch.cuda.synchronize()
-        if i >= 2:
-            e2e_s += time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    line = {
-        "metric": METRIC.replace("gather-trade-build", "covid19"), "value": value, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "envs_per_gpu": E, "n_agents": S,
-                   "parallelism": "env replicas sharded over %d GPU(s), no collective on the step path" % world,
-                   "actions": "device random policy over unmasked actions, inside the timed region",
-                   "l2": "per-step footprint %.0f MB (stringency history re-read every step) > 126 MB L2" % (E * step_bytes / 1e6)},
-        "clocks": clk,
-        "e2e": {"value": world * E * S * n_e2e / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": E * (S + 1) * 4,
-                "d2h_bytes_per_step": d2h, "steps": n_e2e,
-                "what": "pinned host actions -> device, step, every observation/mask/reward/done tensor back to pinned host"},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src, "kernels": kernels},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        rate, total = covid_oracle_rate(8, 40)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "8 env replicas x 40 steps, numpy oracle (one thread), %.1f s" % total}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--envs-per-gpu", type=int, default=None)
-    ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--e2e-mode", choices=["plain", "compact"], default="plain",
-                    help="transfer format of the e2e leg: plain D2H copies, or the compacted transfer (aie_step_host_compact)")
-    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads expanding the compacted transfer (0: auto)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
-        return run_reference_arm(args, rank, world)
-
-    import torch
-    import torch.distributed as dist
-
-    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    from ai_economist_b200 import foundation
-    from tests import batch_utils as bu
-
-    w = WORKLOADS[args.workload]
-    E = args.envs_per_gpu or w["envs_per_gpu"]
-    if args.workload == "c4":
-        return run_covid(args, rank, world, dev, E, w)
-    name, kw = bu.product_kwargs(w["cfg"])
-    t_setup = time.perf_counter()
+    torch, args, rank, world, dev = ctx.torch, ctx.args, ctx.rank, ctx.world, ctx.dev
+    from ai_economist_b200 import foundation, workloads as wl
     from ai_economist_b200.sharding import shard_seeds
+
+    w = WORKLOADS[key]
+    E = args.envs_per_gpu or w["envs_per_gpu"]
+    name, kw = wl.product_kwargs(w["cfg"])
+    t_setup = time.perf_counter()
     env = foundation.make_env_instance(name, n_envs=E, device=str(dev), seeds=shard_seeds(1000, rank, world, E),
                                        auto_reset=True, **kw)
     env.reset()
     st = env.stepper
-    A = env.n_agents
-    d = st.dims
-    torch.cuda.synchronize()
-    t_setup = time.perf_counter() - t_setup
+    A, d, T = env.n_agents, st.dims, int(env.episode_length)
+    # stagger the episode phase: replica e starts its first episode at t = e*T/E, then one episode of untimed steps
+    st.state_view("t").copy_((torch.arange(E, device=dev, dtype=torch.int64) * T // E).to(torch.int32))
 
     def one_step(i):
         st.sample_random_actions(seed=1234 + rank)
         st.step()  # fused dynamics + observations
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    for i in range(T):
+        one_step(i)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t_setup
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    for i in range(args.warmup):
+    for i in range(W):
         one_step(i)
     launches0 = st.launch_count()
-    barrier()
-    clocks.mark_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        one_step(i)
-    ev1.record()
-    barrier()
-    clocks.mark_end()
-    ms_total = ev0.elapsed_time(ev1)
+    if clocks:
+        clocks.mark_begin()
+    ms_total = ctx.time_steps(one_step, K)
     launches = st.launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
-    tt = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total = float(tt.item())
-    value = world * E * A * args.steps / (ms_total * 1e-3)
+    sus_ms, sus_n, sus_min, sus_max = ctx.sustained(one_step, K, ms_total)
+    if clocks:
+        clocks.mark_end()
+    value = world * E * A * K / (ms_total * 1e-3)
 
     # ---- per-kernel durations (separate pass, CUDA events between the kernels, same stream) ----
-    n_prof = min(args.steps, 50)
+    n_prof = 50
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
     for i in range(n_prof):
         evs[i][0].record(); st.sample_random_actions(seed=99)
@@ -484,6 +420,8 @@ def main():
                  + (d.n_map_channels * d.height * d.width * 4 + 2 * d.height * d.width * 2
                     if env.spec["planner_gets_spatial_info"] else 0))
     step_bytes = 2 * d.state_bytes + 4 * (A * d.n_act_agent + d.n_act_planner) + 8 * (A + 1) + 4
+    # SURVEY §8(d)'s own figure counts a leaner record (no MT19937 key / episode statistics inside it)
+    lean_state = d.state_bytes - 4 * 624 - 8 * d.n_stats
     kernels = {
         "aie_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * (step_bytes + obs_bytes),
                             "what": "fused: TMA record in -> dynamics -> rewards -> observations/masks out -> record out",
@@ -494,17 +432,22 @@ def main():
         k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
         k["frac"] = k["achieved_gbs"] / peak
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
-    traffic, traffic_src = committed_traffic(args.workload, dom)
+    traffic, traffic_src = committed_traffic(key, dom)
+    survey_bytes = step_bytes - 2 * d.state_bytes + 2 * lean_state + obs_bytes
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "alg_bytes_per_env_step": step_bytes + obs_bytes,
+                "frac_on_survey_8d_bytes": {"alg_bytes_per_env_step": survey_bytes,
+                                            "frac": E * survey_bytes / (kernels[dom]["ms"] * 1e-3) / 1e9 / peak,
+                                            "what": "SURVEY §8(d)'s accounting: record without the 2.5 KB MT19937 key and the "
+                                                    "episode statistics (both travel in and out with the record here)"},
                 "whole_step": {"alg_bytes_per_env_step": d.algorithmic_bytes_per_env_step,
-                               "achieved": d.algorithmic_bytes_per_env_step * E * args.steps / (ms_total * 1e-3) / 1e9,
-                               "frac": d.algorithmic_bytes_per_env_step * E * args.steps / (ms_total * 1e-3) / 1e9 / peak},
+                               "achieved": d.algorithmic_bytes_per_env_step * E / (sus_ms * 1e-3) / 1e9,
+                               "frac": d.algorithmic_bytes_per_env_step * E / (sus_ms * 1e-3) / 1e9 / peak},
                 "kernels": kernels}
 
-    # ---- e2e through aie_step_host with pinned HOST buffers ----
+    # ---- e2e through the host entry point with pinned HOST buffers ----
     out_host, out_ptrs, d2h = {}, {}, 0
-    import ctypes as C
     for nm in ["obs_agent_map", "obs_agent_idx", "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx",
                "obs_planner_flat", "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]:
         if nm in st.buf:
@@ -515,64 +458,247 @@ def main():
     act_a = torch.zeros(st.buf["actions_agent"].shape, dtype=torch.int32, pin_memory=True)
     act_p = torch.zeros(st.buf["actions_planner"].shape, dtype=torch.int32, pin_memory=True)
     h2d = act_a.numel() * 4 + (act_p.numel() * 4 if d.n_act_planner else 0)
-    seg_a, seg_p = bu.segments(env.spec, "a"), bu.segments(env.spec, "p")
+    seg_a, seg_p = wl.mask_segments(env.spec, "a"), wl.mask_segments(env.spec, "p")
     rng = np.random.RandomState(rank)
     out_host["mask_agent"].copy_(st.buf["mask_agent"])
     out_host["mask_planner"].copy_(st.buf["mask_planner"])
-    e2e_s = 0.0
-    n_e2e = max(3, args.e2e_steps)
+    e2e_s, n_e2e = 0.0, max(3, e2e_steps)
     for i in range(n_e2e + 2):
-        act_a.copy_(torch.from_numpy(bu.sample_from_masks(out_host["mask_agent"].numpy(), seg_a, rng)))
+        act_a.copy_(torch.from_numpy(wl.sample_from_masks(out_host["mask_agent"].numpy(), seg_a, rng)))
         if seg_p:
-            act_p.copy_(torch.from_numpy(bu.sample_from_masks(out_host["mask_planner"].numpy(), seg_p, rng)))
-        torch.cuda.synchronize()
+            act_p.copy_(torch.from_numpy(wl.sample_from_masks(out_host["mask_planner"].numpy(), seg_p, rng)))
+        ctx.barrier() if i == 2 else torch.cuda.synchronize()
         t0 = time.perf_counter()
         st.step_host(C.c_void_p(act_a.data_ptr()), C.c_void_p(act_p.data_ptr()) if d.n_act_planner else None, out_ptrs,
-                     compact=(args.e2e_mode == "compact"), n_threads=args.e2e_threads)
-        dt = time.perf_counter() - t0  # aie_step_host[_compact] synchronises the stream before returning
+                     compact=(e2e_mode == "compact"), n_threads=e2e_threads)
+        dt = time.perf_counter() - t0  # the host entry points synchronise the stream before returning
         if i >= 2:
             e2e_s += dt
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * A * n_e2e / float(te.item())
+    e2e_value = world * E * A * n_e2e / ctx.max_over_ranks(e2e_s)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "steps": n_e2e, "mode": e2e_mode}
+    if e2e_mode == "plain":
+        e2e.update(d2h_bytes_per_step=d2h,
+                   what="aie_step_host: pinned host actions in, every observation/mask/reward/done tensor copied back "
+                        "to pinned host memory each step (PCIe-bound)")
+    else:
+        e2e.update(d2h_bytes_per_step=E * st.compact_bytes_per_env(), host_tensor_bytes_per_step=d2h,
+                   what="aie_step_host_compact: pinned host actions in; every observation/mask/reward/done tensor lands "
+                        "in pinned host memory each step, bit-/byte-packed over PCIe and expanded by host threads "
+                        "(same bytes in the host tensors as the plain path)")
+    res = {
+        "value": value, "ms_per_step": ms_total / K, "steps": K, "warmup": W,
+        "sustained": {"ms_per_step": sus_ms, "value": world * E * A / (sus_ms * 1e-3), "repeats": sus_n,
+                      "min_ms_per_step": sus_min, "max_ms_per_step": sus_max,
+                      "what": "median over repeats of the K-step timed region (same loop, same synchronisation)"},
+        "config": dict(workload_config(key, E), parallelism="env replicas sharded over %d GPU(s), no collective on "
+                       "the step path" % world, setup_s=t_setup, device_reset=("reference-exact (reset_mode 1)"
+                       if env.spec.get("reset_mode", 0) == 1 else "snapshot restore (reset_mode 0)")),
+        "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "dtype": "i32+f64", "n_agents": A,
+    }
+    if with_cpu:
+        res["cpu_baseline"] = cpu_baseline_for(key)
+    del env, st, out_host, act_a, act_p
+    torch.cuda.empty_cache()
+    return res
 
+
+def measure_covid(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20):
+    """BASELINE config 4: one fused kernel per step (+ the random-policy sampler)."""
+    torch, args, rank, world, dev = ctx.torch, ctx.args, ctx.rank, ctx.world, ctx.dev
+    from ai_economist_b200 import foundation
+    from ai_economist_b200.workloads import covid_reference_config
+
+    w = WORKLOADS[key]
+    E = args.envs_per_gpu or w["envs_per_gpu"]
+    cfg = covid_reference_config()
+    name = cfg.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=E, device=str(dev), auto_reset=True, **cfg)
+    env.reset()
+    st = env.stepper
+    S = 51
+
+    def one_step(i):
+        st.sample_random_actions(seed=7 + rank)
+        st.step()
+
+    for i in range(W):
+        one_step(i)
+    l0 = st.launch_count()
+    if clocks:
+        clocks.mark_begin()
+    ms_total = ctx.time_steps(one_step, K)
+    launches = st.launch_count() - l0
+    sus_ms, sus_n, sus_min, sus_max = ctx.sustained(one_step, K, ms_total, max_repeats=20)
+    if clocks:
+        clocks.mark_end()
+    value = world * E * S * K / (ms_total * 1e-3)
+    # per-kernel durations: the cost of the history scan depends on how many stringency changes the window holds, so
+    # the event-separated pass replays the SAME stretch of the episode as the timed region (reset, same warm-up)
+    env.reset()
+    for i in range(W):
+        one_step(i)
+    n_prof = min(K, 300)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
+    for i in range(n_prof):
+        evs[i][0].record(); st.sample_random_actions(seed=7 + rank)
+        evs[i][1].record(); st.step()
+        evs[i][2].record()
+    torch.cuda.synchronize()
+    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(2)]
+    peak, peak_src = peaks()
+    L = env.params["filter_len"]
+    out_bytes = 4 * (6 * S + 3 * S + 4 + 11 * S + 21 + S) + 8 + 4
+    step_bytes = out_bytes + 2 * (9 * S * 4 + 2 * S * 4 + 16) + (L + 1) * S + S + 4 * S + 4   # + ring read/1-row write + actions
+    kernels = {"aie_covid_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * step_bytes},
+               "aie_covid_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (11 * S * 4 + 21 * 4 + 4 * S)}}
+    for k in kernels.values():
+        k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["achieved_gbs"] / peak
+    dom = "aie_covid_step_kernel"
+    traffic, traffic_src = committed_traffic(key, dom)
+    # e2e: pinned host actions in, all outputs back
+    names = ["obs_agent_state", "obs_postsubsidy", "obs_lagged_stringency", "obs_policy_indicators", "obs_scalars",
+             "mask_agent", "mask_planner", "reward_agent", "reward_planner", "done"]
+    host = {n: torch.empty(st.buf[n].shape, dtype=st.buf[n].dtype, pin_memory=True) for n in names}
+    act_a = torch.zeros((E, S), dtype=torch.int32, pin_memory=True)
+    act_p = torch.zeros((E,), dtype=torch.int32, pin_memory=True)
+    d2h = sum(t.numel() * t.element_size() for t in host.values())
+    rng = np.random.RandomState(rank)
+    host["mask_agent"].copy_(st.buf["mask_agent"]); host["mask_planner"].copy_(st.buf["mask_planner"])
+    e2e_s, n_e2e = 0.0, max(3, e2e_steps)
+    for i in range(n_e2e + 2):
+        ma, mp = host["mask_agent"].numpy(), host["mask_planner"].numpy()
+        act_a.copy_(torch.from_numpy(np.argmax(ma * (rng.random_sample(ma.shape) + 1e-3), axis=1).astype(np.int32)))
+        act_p.copy_(torch.from_numpy(np.argmax(mp * (rng.random_sample(mp.shape) + 1e-3), axis=1).astype(np.int32)))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st.buf["actions_agent"].copy_(act_a, non_blocking=True); st.buf["actions_planner"].copy_(act_p, non_blocking=True)
+        st.step()
+        for n in names:
+            host[n].copy_(st.buf[n], non_blocking=True)
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_s += time.perf_counter() - t0
+    e2e_value = world * E * S * n_e2e / ctx.max_over_ranks(e2e_s)
+    res = {
+        "value": value, "ms_per_step": ms_total / K, "steps": K, "warmup": W,
+        "sustained": {"ms_per_step": sus_ms, "value": world * E * S / (sus_ms * 1e-3), "repeats": sus_n,
+                      "min_ms_per_step": sus_min, "max_ms_per_step": sus_max,
+                      "what": "median over repeats of the K-step timed region"},
+        "config": dict(workload_config(key, E), parallelism="env replicas sharded over %d GPU(s), no collective on the "
+                       "step path" % world, episode_phase="lock-step (deterministic scenario); the timed region covers "
+                       "the episode from the warm-up on, K = 540 is one whole episode"),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * (S + 1) * 4, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "what": "pinned host actions -> device, step, every observation/mask/reward/done tensor "
+                                        "back to pinned host"},
+        "gpu_launches": launches, "dtype": "f32+f64", "n_agents": S,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "alg_bytes_per_env_step": step_bytes, "kernels": kernels},
+    }
+    if with_cpu:
+        res["cpu_baseline"] = cpu_baseline_for(key)
+    ref = reference_cuda_note()
+    if ref:
+        res["vs_reference_cuda"] = ref
+    del env, st, host
+    torch.cuda.empty_cache()
+    return res
+
+
+def reference_cuda_note():
+    """Same-box timing of the reference's own COVID CUDA kernels (oracle/_ref, built from /root/reference by
+    oracle/build_ref_covid.py), if tools/time_ref_covid.py left one for this box."""
+    p = os.path.join(ROOT, "gpurun_out", "ref_covid_cuda.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "ref_covid_cuda.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def compact(res):
+    """What a sub-workload contributes to the headline line's `workloads` object."""
+    r = res["roofline"]
+    return {"value": res["value"], "ms_per_step": res["ms_per_step"], "steps": res["steps"],
+            "sustained": {k: res["sustained"][k] for k in ("ms_per_step", "value", "repeats")},
+            "roofline": {"kernel": r["kernel"], "frac": r["frac"], "achieved": r["achieved"], "traffic": r["traffic"],
+                         "traffic_source": r.get("traffic_source"), "alg_bytes_per_env_step": r["alg_bytes_per_env_step"],
+                         "kernel_ms": {k: v["ms"] for k, v in r["kernels"].items()}},
+            "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "n_agents": res["n_agents"],
+            "envs_per_gpu": res["config"]["envs_per_gpu"], "device_reset": res["config"].get("device_reset"),
+            **({"vs_reference_cuda": res["vs_reference_cuda"]} if "vs_reference_cuda" in res else {}),
+            **({"cpu_baseline": res["cpu_baseline"]} if "cpu_baseline" in res else {})}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-mode", choices=["plain", "compact"], default="compact",
+                    help="transfer format of the e2e leg: plain D2H copies, or the compacted transfer (aie_step_host_compact)")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads expanding the compacted transfer (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true",
+                    help="headline workload only (skip the c3/c4/c5 entries of `workloads`)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Ctx(args, rank, world, dev)
+    key = args.workload
+    with_cpu = world == 1 and not args.no_cpu_baseline
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    fn = measure_covid if key == "c4" else measure_gtb
+    kw = {} if key == "c4" else dict(e2e_mode=args.e2e_mode, e2e_threads=args.e2e_threads)
+    res = fn(ctx, key, args.steps, args.warmup, with_cpu, clocks=clocks, e2e_steps=args.e2e_steps, **kw)
+    clk = clocks.stop() if clocks else None
+    extra = {}
+    if key == "c2" and not args.no_extra_workloads and not args.envs_per_gpu:
+        for k2 in ("c3", "c4", "c5"):
+            f2 = measure_covid if k2 == "c4" else measure_gtb
+            kw2 = {} if k2 == "c4" else dict(e2e_mode=args.e2e_mode, e2e_threads=args.e2e_threads)
+            try:
+                extra[k2] = compact(f2(ctx, k2, WORKLOADS[k2]["steps"], max(3, min(args.warmup, 20)), False, e2e_steps=5, **kw2))
+            except Exception as ex:   # the headline line must survive a failing extra workload (all ranks fail alike)
+                extra[k2] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "i32+f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "envs_per_gpu": E, "n_agents": A, "world": [d.height, d.width],
-                   "parallelism": "env replicas sharded over %d GPU(s), no collective on the step path" % world,
-                   "actions": "device random policy over unmasked actions (aie_sample_kernel), inside the timed region",
-                   "l2": "no explicit flush: each step rewrites %.0f MB of observations (> 126 MB L2) and touches "
-                         "%.0f MB of state" % (E * obs_bytes / 1e6, E * d.state_bytes / 1e6),
-                   "auto_reset": True, "setup_s": t_setup},
-        "clocks": clk,
-        "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                 "steps": n_e2e, "what": "aie_step_host: pinned host actions in, every observation/mask/reward/done "
-                                         "tensor copied back to pinned host memory each step (PCIe-bound)"}
-                if args.e2e_mode == "plain" else
-                {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                 "d2h_bytes_per_step": E * st.compact_bytes_per_env(), "host_tensor_bytes_per_step": d2h, "steps": n_e2e,
-                 "what": "aie_step_host_compact: pinned host actions in; every observation/mask/reward/done tensor "
-                         "lands in pinned host memory each step, bit-/byte-packed over PCIe and expanded by host "
-                         "threads (same bytes as the plain path)"}),
-        "gpu_launches": launches,
-        "roofline": roofline,
+        "metric": METRIC if key != "c4" else METRIC.replace("gather-trade-build", "covid19"),
+        "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": res["dtype"], "data": "synthetic", "config": res["config"], "clocks": clk, "sustained": res["sustained"],
+        "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "roofline": res["roofline"],
     }
-    if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_cpu = max(threads * 256, 1024)
-        probe, _ = oracle_rate(w["cfg"], n_cpu, 5, threads, warmup=1)
-        steps_cpu = int(max(20, min(2000, 12.0 * probe / (n_cpu * A))))
-        rate, total = oracle_rate(w["cfg"], n_cpu, steps_cpu, threads, warmup=2)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d env replicas x %d steps of the same workload on %d host threads "
-                                          "(C oracle of the reference step), %.1f s" % (n_cpu, steps_cpu, threads, total)}
+    if "cpu_baseline" in res:
+        line["cpu_baseline"] = res["cpu_baseline"]
+        line["reference_numpy_step"] = reference_numpy_note()
+    if "vs_reference_cuda" in res:
+        line["vs_reference_cuda"] = res["vs_reference_cuda"]
+    if extra:
+        line["workloads"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

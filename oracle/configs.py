@@ -4,32 +4,12 @@ Sources: BASELINE.json configs; tutorials/economic_simulation_basic.ipynb cell 1
 tutorials/rllib/phase2/config.yaml:7-51 (c3); tests/test_env.py:27-62 (ref_unit_test).
 """
 
-_GTB = [("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
-        ("ContinuousDoubleAuction", dict(max_num_orders=5)),
-        ("Gather", dict())]
+from ai_economist_b200.workloads import BASELINE_CONFIGS, _GTB  # the BASELINE workloads live with the product
 
 CONFIGS = {
-    # c1 / c2: tutorial basic
-    "c1_tutorial": dict(
-        scenario_name="layout_from_file/simple_wood_and_stone", components=_GTB,
-        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=10,
-        fixed_four_skill_and_loc=True, n_agents=4, world_size=[25, 25], episode_length=1000,
-        multi_action_mode_agents=False, multi_action_mode_planner=True,
-        flatten_observations=True, flatten_masks=True),
-    # c3: paper config (phase 2) at 10 agents / 40x40
-    "c3_paper_tax": dict(
-        scenario_name="layout_from_file/simple_wood_and_stone",
-        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
-                    ("ContinuousDoubleAuction", dict(max_num_orders=5)),
-                    ("Gather", dict(skill_dist="pareto")),
-                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=100, rate_disc=0.05,
-                                                tax_model="model_wrapper"))],
-        env_layout_file="quadrant_40x40_50each.txt", starting_agent_coin=0,
-        fixed_four_skill_and_loc=True, n_agents=10, world_size=[40, 40], episode_length=1000,
-        multi_action_mode_agents=False, multi_action_mode_planner=True,
-        flatten_observations=True, flatten_masks=True,
-        isoelastic_eta=0.23, energy_cost=0.21, energy_warmup_constant=0, planner_gets_spatial_info=False,
-        mixing_weight_gini_vs_coin=0.0, planner_reward_type="coin_eq_times_productivity"),
+    # c1 / c2: tutorial basic; c3: paper config (phase 2) at 10 agents / 40x40 (see ai_economist_b200/workloads.py)
+    "c1_tutorial": BASELINE_CONFIGS["c1_tutorial"],
+    "c3_paper_tax": BASELINE_CONFIGS["c3_paper_tax"],
     # c3 variant: short tax period, spatial planner, random (non-fixed-four) placement, tax annealing
     "c3_short_period": dict(
         scenario_name="layout_from_file/simple_wood_and_stone",
@@ -74,15 +54,7 @@ CONFIGS = {
         flatten_observations=True, flatten_masks=True,
         starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
     # c5 at the BASELINE size: 64 agents, 64x64, deep book (K=50), multi-action agents
-    "c5_full": dict(
-        scenario_name="uniform/simple_wood_and_stone",
-        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
-                    ("ContinuousDoubleAuction", dict(max_num_orders=50)),
-                    ("Gather", dict(skill_dist="pareto"))],
-        n_agents=64, world_size=[64, 64], episode_length=150,
-        multi_action_mode_agents=True, multi_action_mode_planner=True,
-        flatten_observations=True, flatten_masks=True,
-        starting_agent_coin=100, starting_wood_coverage=0.10, starting_stone_coverage=0.10),
+    "c5_full": BASELINE_CONFIGS["c5_full"],
     # WealthRedistribution (components/redistribution.py:21-75) as the last component; pareto gather skills, 6 agents
     "wealth_redistribution": dict(
         scenario_name="layout_from_file/simple_wood_and_stone",

@@ -9,7 +9,10 @@
  *
  * Reference paths are relative to /root/reference/ai_economist/foundation/.
  */
+#define _GNU_SOURCE /* pthread_setaffinity_np, sched_getaffinity (CPU baseline threads are pinned) */
 #include "foundation_oracle.h"
+
+#include <sched.h>
 
 #include <math.h>
 #include <pthread.h>
@@ -1202,9 +1205,14 @@ static void step_env(const orc_batch *b, env_t *s, const int32_t *act_a, const i
     s->done = s->t >= b->cfg.episode_length; /* :1012 */
 }
 
-typedef struct { orc_batch *b; const int32_t *aa, *ap; int lo, hi; } job_t;
+typedef struct { orc_batch *b; const int32_t *aa, *ap; int lo, hi, cpu; } job_t;
 static void *worker(void *arg) {
     job_t *j = (job_t *)arg;
+    if (j->cpu >= 0) {  /* cpu_baseline only: one thread per allowed core, each pinned to its own */
+        cpu_set_t one;
+        CPU_ZERO(&one); CPU_SET(j->cpu, &one);
+        pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+    }
     int e, na = j->b->cfg.n_agents * j->b->dims.n_act_a, np = j->b->dims.n_act_p;
     for (e = j->lo; e < j->hi; e++)
         step_env(j->b, &j->b->envs[e], j->aa ? j->aa + (size_t)e * na : NULL,
@@ -1215,15 +1223,23 @@ static void *worker(void *arg) {
 int orc_step(orc_batch *b, const int32_t *actions_a, const int32_t *actions_p, int32_t n_threads) {
     int i;
     if (n_threads <= 1) {
-        job_t j = {b, actions_a, actions_p, 0, b->n_envs};
+        job_t j = {b, actions_a, actions_p, 0, b->n_envs, -1};
         worker(&j);
         return 0;
     }
     {
         pthread_t *th = (pthread_t *)alloca(sizeof(pthread_t) * n_threads);
         job_t *jobs = (job_t *)alloca(sizeof(job_t) * n_threads);
+        cpu_set_t allowed;
+        int n_allowed = 0, next_cpu = -1;
+        if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) n_allowed = CPU_COUNT(&allowed);
         for (i = 0; i < n_threads; i++) {
             jobs[i].b = b; jobs[i].aa = actions_a; jobs[i].ap = actions_p;
+            jobs[i].cpu = -1;
+            if (n_allowed >= n_threads) {  /* the i-th allowed core */
+                do { next_cpu++; } while (next_cpu < CPU_SETSIZE && !CPU_ISSET(next_cpu, &allowed));
+                if (next_cpu < CPU_SETSIZE) jobs[i].cpu = next_cpu;
+            }
             jobs[i].lo = (int)((long long)b->n_envs * i / n_threads);
             jobs[i].hi = (int)((long long)b->n_envs * (i + 1) / n_threads);
             pthread_create(&th[i], NULL, worker, &jobs[i]);
@@ -1261,6 +1277,18 @@ int orc_get_obs(const orc_batch *b, int32_t e, float *a_map, int16_t *a_idx, flo
     if (time_obs) *time_obs = s->time_obs;
     if (rew) memcpy(rew, s->rew, sizeof(double) * (A + 1));
     if (done) *done = s->done;
+    return 0;
+}
+
+/* Action masks of every env in one call (bench.py's host-side random policy; not part of the restated path). */
+int orc_get_masks(const orc_batch *b, float *a_mask /* [E, A, mask_a] */, float *p_mask /* [E, mask_p] */) {
+    const orc_dims *d = &b->dims;
+    const size_t na = (size_t)b->cfg.n_agents * d->mask_a, np_ = (size_t)d->mask_p;
+    int e;
+    for (e = 0; e < b->n_envs; e++) {
+        if (a_mask) memcpy(a_mask + (size_t)e * na, b->envs[e].a_mask, sizeof(float) * na);
+        if (p_mask) memcpy(p_mask + (size_t)e * np_, b->envs[e].p_mask, sizeof(float) * np_);
+    }
     return 0;
 }
 

@@ -16,36 +16,11 @@ from oracle import ref_harness as rh  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden_covid")
 
-COVID_KWARGS = dict(
-    episode_length=540, start_date="2020-03-22", pop_between_age_18_65=0.6, infection_too_sick_to_work_rate=0.1,
-    risk_free_interest_rate=0.03, economic_reward_crra_eta=2, health_priority_scaling_agents=0.3,
-    health_priority_scaling_planner=0.45, action_cooldown_period=28, subsidy_interval=90, num_subsidy_levels=20,
-    max_annual_subsidy_per_person=20000, daily_vaccines_per_million_people=3000, delivery_interval=1,
-    vaccine_delivery_start_date="2021-01-12")
+from ai_economist_b200.workloads import COVID_KWARGS, covid_reference_config  # noqa: E402
 
 
 def reference_config(kw):
-    return {
-        "scenario_name": "CovidAndEconomySimulation",
-        "components": [
-            {"ControlUSStateOpenCloseStatus": {"action_cooldown_period": kw["action_cooldown_period"]}},
-            {"FederalGovernmentSubsidy": {"num_subsidy_levels": kw["num_subsidy_levels"],
-                                          "subsidy_interval": kw["subsidy_interval"],
-                                          "max_annual_subsidy_per_person": kw["max_annual_subsidy_per_person"]}},
-            {"VaccinationCampaign": {"daily_vaccines_per_million_people": kw["daily_vaccines_per_million_people"],
-                                     "delivery_interval": kw["delivery_interval"],
-                                     "vaccine_delivery_start_date": kw["vaccine_delivery_start_date"]}},
-        ],
-        "use_real_world_data": False, "use_real_world_policies": False, "start_date": kw["start_date"],
-        "path_to_data_and_fitted_params": "", "economic_reward_crra_eta": kw["economic_reward_crra_eta"],
-        "health_priority_scaling_agents": kw["health_priority_scaling_agents"],
-        "health_priority_scaling_planner": kw["health_priority_scaling_planner"],
-        "infection_too_sick_to_work_rate": kw["infection_too_sick_to_work_rate"],
-        "pop_between_age_18_65": kw["pop_between_age_18_65"], "risk_free_interest_rate": kw["risk_free_interest_rate"],
-        "n_agents": 51, "world_size": [1, 1], "episode_length": kw["episode_length"],
-        "multi_action_mode_agents": False, "multi_action_mode_planner": False, "flatten_observations": False,
-        "flatten_masks": True, "collate_agent_step_and_reset_data": True,
-    }
+    return covid_reference_config(kw)
 
 
 def ref_arrays(env, obs, rew=None, done=None):

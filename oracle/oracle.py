@@ -74,6 +74,7 @@ def lib():
         L.orc_load_env.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 13 + [C.c_int32, C.c_int32]
         L.orc_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_get_obs.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 12
+        L.orc_get_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_get_state.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 20
         L.orc_get_book.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
         L.orc_get_book.restype = C.c_int32
@@ -190,6 +191,14 @@ class OracleBatch:
                                         ["a_map", "a_idx", "a_flat", "a_mask", "p_map", "p_idx", "p_flat",
                                          "p_agents", "p_mask", "time", "rew", "done"]])
         return out
+
+    def masks(self):
+        """(a_mask [E, A, mask_a], p_mask [E, mask_p]) of every env, one C call."""
+        d = self.dims
+        ma = np.zeros((self.n_envs, self.A, d.mask_a), np.float32)
+        mp = np.zeros((self.n_envs, d.mask_p), np.float32)
+        lib().orc_get_masks(self._h, _p(ma), _p(mp))
+        return ma, mp
 
     def state(self, e):
         A, H, W, P = self.A, self.H, self.W, self.P

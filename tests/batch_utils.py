@@ -3,46 +3,16 @@ import os
 
 import numpy as np
 
+from ai_economist_b200 import workloads as _wl
 from oracle.configs import CONFIGS
 
 
 def product_kwargs(cfg_name):
-    kw = dict(CONFIGS[cfg_name])
-    name = kw.pop("scenario_name")
-    return name, kw
+    return _wl.product_kwargs(cfg_name, CONFIGS)
 
 
-def segments(spec, who):
-    """Lengths of the per-subspace slices of the flattened action mask (base_agent.py:440-460)."""
-    P = spec["max_bid_ask"] + 1
-    if who == "p":
-        planner_acts = ("PeriodicBracketTax" in spec["components"] and spec["tax_model"] == 0
-                        and not spec["disable_taxes"])
-        if planner_acts and spec.get("single_action_planner", 0):   # one index over [NO-OP] ++ every bracket's rates
-            return [1 + spec["n_disc_rates"] * spec["n_brackets"]]
-        return [1 + spec["n_disc_rates"]] * spec["n_brackets"] if planner_acts else []
-    sizes = []
-    for c in spec["components"]:
-        if c == "Build":
-            sizes += [1]
-        elif c == "ContinuousDoubleAuction":
-            sizes += [P] * 4
-        elif c == "Gather":
-            sizes += [4]
-    if spec["multi_action_agents"]:
-        return [s + 1 for s in sizes]
-    return [1 + sum(sizes)]
-
-
-def sample_from_masks(mask, seg, rng):
-    """mask [..., L] (0/1) -> int32 [..., len(seg)]: uniform over the unmasked entries of each segment."""
-    out = np.zeros(mask.shape[:-1] + (len(seg),), np.int32)
-    off = 0
-    for i, n in enumerate(seg):
-        m = mask[..., off:off + n]
-        out[..., i] = np.argmax(m * (rng.random_sample(m.shape) + 1e-3), axis=-1)
-        off += n
-    return out
+segments = _wl.mask_segments
+sample_from_masks = _wl.sample_from_masks
 
 
 EXACT_STATE = ["cell", "owner", "loc", "inv", "esc", "n_orders", "bid_hist", "ask_hist", "tax_pos", "rate_idx",

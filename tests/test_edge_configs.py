@@ -31,8 +31,7 @@ def run_against_oracle(env, steps, check_every):
     from oracle.oracle import OracleBatch
     from tests import batch_utils as bu
     host = env.host_reset_arrays()
-    env.stepper.load_state(host)
-    env._loaded = True
+    env.load_host_state(host)
     orc = OracleBatch(env.spec, env.n_envs)
     for e in range(env.n_envs):
         orc.load_env(e, {k: v[e] for k, v in host.items()})

@@ -34,8 +34,7 @@ def test_emulated_batch_matches_oracle(cfg, E, steps):
     kw.pop("seed", None)
     env = foundation.make_env_instance(name, n_envs=E, stepper_factory=emu_factory, auto_reset=False, seed=4000, **kw)
     host = env.host_reset_arrays()
-    env.stepper.load_state(host)
-    env._loaded = True
+    env.load_host_state(host)
     orc = OracleBatch(env.spec, E)
     for e in range(E):
         orc.load_env(e, {k: v[e] for k, v in host.items()})

@@ -32,8 +32,7 @@ def _make_env(cfg_name, n_envs, seed, **extra):
 def _load_both(env):
     from oracle.oracle import OracleBatch
     host = env.host_reset_arrays()
-    env.stepper.load_state(host)
-    env._loaded = True
+    env.load_host_state(host)
     orc = OracleBatch(env.spec, env.n_envs)
     for e in range(env.n_envs):
         orc.load_env(e, {k: v[e] for k, v in host.items()})
@@ -129,8 +128,7 @@ def test_cuda_full_size_c3_c5_against_oracle_and_invariants(cfg, E, steps):
         host = {k: np.concatenate([np.asarray(v)] * (E // 64)) for k, v in h64.items()}
         host["mt_key"] = np.stack([np.random.RandomState(70000 + e).get_state()[1] for e in range(E)]).astype(np.uint32)
         host["mt_pos"] = np.full(E, 624, np.int32)
-        env.stepper.load_state(host)
-        env._loaded = True
+        env.load_host_state(host)
         orc = OracleBatch(env.spec, E)
         for e in range(E):
             orc.load_env(e, {k: v[e] for k, v in host.items()})

@@ -72,8 +72,7 @@ def random_config(rng):
 def run_one(name, kw, seed, steps=120):
     env = foundation.make_env_instance(name, n_envs=2, stepper_factory=emu_factory, auto_reset=False, seed=seed, **kw)
     host = env.host_reset_arrays()
-    env.stepper.load_state(host)
-    env._loaded = True
+    env.load_host_state(host)
     orc = OracleBatch(env.spec, 2)
     for e in range(2):
         orc.load_env(e, {k: v[e] for k, v in host.items()})
