@@ -153,6 +153,7 @@ def load_library(path=None):
     L.aie_observe.argtypes = [P, P]
     L.aie_step_dynamics.argtypes = [P, P]
     L.aie_sample_random_actions.argtypes = [P, C.c_uint64, P]
+    L.aie_set_fused_policy.argtypes = [P, C.c_uint64, P]
     L.aie_step_host.argtypes = [P, P, P, C.POINTER(AieHostOut), P]
     L.aie_step_host_compact.argtypes = [P, P, P, C.POINTER(AieHostOut), C.c_int32, P]
     L.aie_step_host_compact.restype = C.c_int
@@ -176,7 +177,7 @@ def load_library(path=None):
     L.aie_launch_count.restype = C.c_int64
     for fn in ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_bind_buffers", "aie_load_state",
                "aie_step", "aie_observe", "aie_step_host", "aie_step_host_compact", "aie_compact_bytes_per_env", "aie_read_state", "aie_step_dynamics",
-               "aie_sample_random_actions"]:
+               "aie_sample_random_actions", "aie_set_fused_policy"]:
         getattr(L, fn).restype = C.c_int
     if L.aie_abi_version() != ABI_VERSION:
         raise AieError("ABI version mismatch between %s and the Python binding" % path)
@@ -184,7 +185,7 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_get_flat_layout", "aie_bind_buffers",
-                    "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions",
+                    "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions", "aie_set_fused_policy",
                     "aie_step_host", "aie_step_host_compact", "aie_compact_bytes_per_env", "aie_read_state", "aie_read_episode_final", "aie_launch_count", "aie_last_error", "aie_abi_version",
                     "aie_covid_create", "aie_covid_destroy", "aie_covid_bind_buffers", "aie_covid_reset", "aie_covid_step",
                     "aie_covid_sample_random_actions", "aie_covid_launch_count"]

@@ -142,21 +142,27 @@ __device__ __forceinline__ ObsOut obs_out_for(const DevCfg &c, const DevBufs &b,
     return o;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// MINB = minimum resident CTAs per SM the register allocation targets (occupancy vs. registers per thread).
-template <int MINB, bool BIG, bool EXT = false>
-__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
-                                                              const int emit_obs) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * wpb + warp;
-    const uint16_t *tab = stage_tables(smem, wpb, c, b);
-    if (env >= c.n_envs) return;  // from here on warps are independent: no block-wide barrier below
-    uint64_t *bar = (uint64_t *)smem + warp;
-    uint8_t *rec = warp_region(smem, wpb, warp, c);
+// Executor of the observation pass on the device (aie_obs.cuh): thread `tid` of the NT threads that own one env runs
+// the phase body, then the group's barrier.  FUSED: the pass runs behind the record's write-back in the step kernel.
+template <int NT, bool FUSED>
+struct DevExec {
+    int tid;
+    __device__ __forceinline__ int nt() const { return NT; }
+    __device__ __forceinline__ void sync() const { if (NT == 32) __syncwarp(); else __syncthreads(); }
+    template <class F> __device__ __forceinline__ void operator()(F f) const { f(tid); sync(); }
+    // the record image's tail (price history, order slots) is about to be reused as staging memory
+    __device__ __forceinline__ void record_stored() const {
+        if (FUSED) { if (tid == 0) bulk_wait_read(); sync(); }
+    }
+};
+
+// One warp: bulk-load env's record, advance it one timestep (auto-reset included), start the write-back.  On return the
+// record image is final; with obs_alias_mt the MT19937 key went out as its own first group and has been read already.
+template <bool BIG, bool EXT>
+__device__ __forceinline__ void warp_step(const DevCfg &c, const DevBufs &b, int env, uint8_t *rec, uint64_t *bar,
+                                          const uint16_t *tab, int lane) {
     uint8_t *scratch = rec + c.resident_bytes;
     uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
-
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, (uint32_t)c.resident_bytes);
@@ -217,8 +223,9 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     fence_async_smem();  // generic-proxy writes to the record -> visible to the bulk (async-proxy) store
     __syncwarp();
     // Observations / masks of the post-step state stream out of the same shared-memory record while the bulk store
-    // drains (both only read the record).  When the staging area aliases the MT19937 key image, the key goes out as
-    // its own (first) bulk group and only that group must have finished READING shared memory before the pass starts.
+    // drains (both only read the record).  When observation staging aliases the MT19937 key image, the key goes out as
+    // its own (first) bulk group and only that group must have finished READING shared memory before the pass starts;
+    // the pass itself waits for the rest before it reuses the record's tail (DevExec::record_stored).
     if (lane == 0) {
         if (c.obs_alias_mt) {
             const uint32_t mt_end = (uint32_t)c.off_mt + 4u * 624u;
@@ -232,8 +239,38 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
         }
     }
     __syncwarp();
-    if (emit_obs) observe_env<EXT>(c, rec, grec, rec + c.off_mt, scratch + c.step_scratch_bytes, obs_out_for(c, b, env), tab, lane);
-    if (lane == 0) bulk_wait_read();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One warp per env, up to 8 envs per CTA.  MINB = minimum resident CTAs per SM the register allocation targets
+// (occupancy vs. registers per thread).
+template <int MINB, bool EXT = false>
+__global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
+                                                              const int emit_obs) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * wpb + warp;
+    const uint16_t *tab = stage_tables(smem, wpb, c, b);
+    if (env >= c.n_envs) return;  // from here on warps are independent: no block-wide barrier below
+    uint64_t *bar = (uint64_t *)smem + warp;
+    uint8_t *rec = warp_region(smem, wpb, warp, c);
+    warp_step<false, EXT>(c, b, env, rec, bar, tab, lane);
+    if (emit_obs) observe_env<EXT>(c, rec, b.state + (size_t)env * c.rec_bytes, rec, c.ob, obs_out_for(c, b, env), tab, DevExec<32, true>{lane});
+    else if (lane == 0) bulk_wait_read();
+}
+
+// Large records: one CTA of four warps per env.  Warp 0 runs the (serial) dynamics; all four stream the observations.
+template <bool BIG, bool EXT = false>
+__global__ void __launch_bounds__(128, 4) aie_step_mw_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
+                                                             const int emit_obs) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int env = blockIdx.x;
+    const uint16_t *tab = stage_tables(smem, 1, c, b);
+    uint8_t *rec = warp_region(smem, 1, 0, c);
+    if (threadIdx.x < 32) warp_step<BIG, EXT>(c, b, env, rec, (uint64_t *)smem, tab, threadIdx.x);
+    __syncthreads();
+    if (emit_obs) observe_env<EXT>(c, rec, b.state + (size_t)env * c.rec_bytes, rec, c.ob, obs_out_for(c, b, env), tab, DevExec<128, true>{(int)threadIdx.x});
+    else if (threadIdx.x == 0) bulk_wait_read();
 }
 
 __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_constant__ DevCfg c, const DevBufs b,
@@ -264,8 +301,15 @@ __global__ void __launch_bounds__(256) aie_finish_reset_kernel(const __grid_cons
     }
 }
 
-// Stand-alone observation pass (after a reset upload, or when the caller steps dynamics separately): one warp per
-// env, bulk-loads only the observable prefix of the record.
+// Stand-alone observation pass (after a reset upload, or when the caller steps dynamics separately): bulk-loads only
+// the observable prefix of the record (+ the price history).  One warp per env, or (MW) one CTA of four warps per env.
+__device__ __forceinline__ void load_obs_prefix(const DevCfg &c, uint8_t *rec, const uint8_t *grec, uint64_t *bar) {
+    const uint32_t ph = (uint32_t)(c.off_orders - c.off_price_hist);
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, (uint32_t)c.obs_prefix_bytes + (c.split ? 0u : ph));
+    bulk_g2s(rec, grec, (uint32_t)c.obs_prefix_bytes, bar);
+    if (!c.split) bulk_g2s(rec + c.off_price_hist, grec + c.off_price_hist, ph, bar);
+}
 template <bool EXT>
 __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b, int lo, int n) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -277,17 +321,23 @@ __global__ void __launch_bounds__(256) aie_observe_kernel(const __grid_constant_
     uint64_t *bar = (uint64_t *)smem + warp;
     uint8_t *rec = warp_region(smem, wpb, warp, c);
     uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
-    if (lane == 0) {
-        const uint32_t ph = (uint32_t)(c.off_orders - c.off_price_hist);
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)c.obs_prefix_bytes + (c.split ? 0u : ph));
-        bulk_g2s(rec, grec, (uint32_t)c.obs_prefix_bytes, bar);
-        if (!c.split) bulk_g2s(rec + c.off_price_hist, grec + c.off_price_hist, ph, bar);
-    }
+    if (lane == 0) load_obs_prefix(c, rec, grec, bar);
     __syncwarp();
     mbar_wait(bar, 0);
-    observe_env<EXT>(c, rec, grec, rec + c.off_mt, rec + c.resident_bytes + c.step_scratch_bytes,
-                     obs_out_for(c, b, env), tab, lane);
+    observe_env<EXT>(c, rec, grec, rec, c.ob, obs_out_for(c, b, env), tab, DevExec<32, false>{lane});
+}
+template <bool EXT>
+__global__ void __launch_bounds__(128, 4) aie_observe_mw_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b, int lo, int n) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int env = lo + blockIdx.x;
+    const uint16_t *tab = stage_tables(smem, 1, c, b);
+    uint64_t *bar = (uint64_t *)smem;
+    uint8_t *rec = warp_region(smem, 1, 0, c);
+    uint8_t *grec = b.state + (size_t)env * c.rec_bytes;
+    if (threadIdx.x == 0) load_obs_prefix(c, rec, grec, bar);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    observe_env<EXT>(c, rec, grec, rec, c.ob, obs_out_for(c, b, env), tab, DevExec<128, false>{(int)threadIdx.x});
 }
 
 // per_unit == 0: one warp per env (fastest for few agents: c2 15.2 us vs 17.5 us);  per_unit == 1: one warp per
@@ -345,14 +395,14 @@ int init(aie_env *env) {
     const size_t tabs = (2 * (size_t)c.tab_n + 15) & ~(size_t)15;
     auto cta_smem = [&](int w) { return align16(8 * w) + tabs + (size_t)w * per_env; };
     int wpb = 0, best_warps = 0;
-    for (int w = 8; w >= 1; w--) {
+    for (int w = (c.mw > 1 ? 1 : 8); w >= 1; w--) {   // mw > 1: one env per CTA, c.mw warps
         if (cta_smem(w) > max_smem) continue;
         int ctas = (int)(prop.sharedMemPerMultiprocessor / (cta_smem(w) + 1024));
         if (ctas * w > 32) ctas = 32 / w;
         if (ctas * w > best_warps) { best_warps = ctas * w; wpb = w; }
     }
     if (wpb == 0) return fail(AIE_EINVAL, "env state record does not fit in shared memory");
-    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (v >= 1 && v <= 8 && cta_smem(v) <= max_smem) wpb = v; }
+    if (const char *ov = getenv("AIE_STEP_WPB")) { int v = atoi(ov); if (c.mw == 1 && v >= 1 && v <= 8 && cta_smem(v) <= max_smem) wpb = v; }
     env->be.step_wpb = wpb;
     env->be.step_smem = cta_smem(wpb);
     env->be.obs_threads = wpb * 32;
@@ -372,23 +422,20 @@ int init(aie_env *env) {
     // The attribute belongs to the function (per device, process-wide), not to this handle: a second env with a smaller
     // record must not lower it under the first one, so every kernel is simply opted in to the device maximum.
     const int sm = (int)max_smem;
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_step_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
+#define AIE_OPT_IN(k) AIE_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr")
+    AIE_OPT_IN((aie_step_kernel<3, false>)); AIE_OPT_IN((aie_step_kernel<4, false>)); AIE_OPT_IN((aie_step_kernel<5, false>));
+    AIE_OPT_IN((aie_step_kernel<3, true>)); AIE_OPT_IN((aie_step_kernel<4, true>));
+    AIE_OPT_IN((aie_step_mw_kernel<false, false>)); AIE_OPT_IN((aie_step_mw_kernel<false, true>));
+    AIE_OPT_IN((aie_step_mw_kernel<true, false>)); AIE_OPT_IN((aie_step_mw_kernel<true, true>));
+    AIE_OPT_IN(aie_finish_reset_kernel);
+    AIE_OPT_IN(aie_observe_kernel<false>); AIE_OPT_IN(aie_observe_kernel<true>);
+    AIE_OPT_IN(aie_observe_mw_kernel<false>); AIE_OPT_IN(aie_observe_mw_kernel<true>);
+#undef AIE_OPT_IN
     {
         AIE_CUDA(cudaMalloc((void **)&env->be.tab_dev, sizeof(Tables)), "cudaMalloc tables");
         AIE_CUDA(cudaMemcpy(env->be.tab_dev, env->tables.w, sizeof(Tables), cudaMemcpyHostToDevice), "upload tables");
         env->bufs.tab = env->be.tab_dev;
     }
-    AIE_CUDA(cudaFuncSetAttribute(aie_finish_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
-    AIE_CUDA(cudaFuncSetAttribute(aie_observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm), "smem attr");
     return AIE_OK;
 }
 void destroy(aie_env *env) {
@@ -454,29 +501,36 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
 }
 int launch_step(aie_env *env, int emit_obs, void *stream) {
     const int wpb = env->be.step_wpb;
-    const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = env->be.step_smem;
-    if (env->cfg.ext) {  // rarely used options compiled in (single-action planner, regen halfwidth); 48-register variant omitted
-        if (env->cfg.split) {
-            if (env->be.step_minb >= 4) aie_step_kernel<4, true, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-            else aie_step_kernel<3, true, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        } else if (env->be.step_minb >= 4) aie_step_kernel<4, false, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        else aie_step_kernel<3, false, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-    } else if (env->cfg.split) {  // large envs: order slots / price history in global memory, latency-tolerant scans
-        if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-    } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-    else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-    else aie_step_kernel<3, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    if (env->cfg.mw > 1) {   // large records: one CTA of four warps per env
+        const dim3 grid(env->n_envs), block(32 * env->cfg.mw);
+        if (env->cfg.ext) {
+            if (env->cfg.split) aie_step_mw_kernel<true, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+            else aie_step_mw_kernel<false, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        } else if (env->cfg.split) aie_step_mw_kernel<true, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        else aie_step_mw_kernel<false, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    } else {
+        const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
+        if (env->cfg.ext) {  // rarely used options compiled in (single-action planner, regen halfwidth); 48-register variant omitted
+            if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+            else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+        else aie_step_kernel<3, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+    }
     AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
     env->launches++;
     return AIE_OK;
 }
 int launch_observe(aie_env *env, int lo, int n, void *stream) {
     const int wpb = env->be.step_wpb;
-    if (env->cfg.ext) aie_observe_kernel<true><<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
-    else aie_observe_kernel<false><<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, (cudaStream_t)stream>>>(env->cfg, env->bufs, lo, n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (env->cfg.mw > 1) {
+        if (env->cfg.ext) aie_observe_mw_kernel<true><<<n, 32 * env->cfg.mw, env->be.obs_smem, st>>>(env->cfg, env->bufs, lo, n);
+        else aie_observe_mw_kernel<false><<<n, 32 * env->cfg.mw, env->be.obs_smem, st>>>(env->cfg, env->bufs, lo, n);
+    } else if (env->cfg.ext) aie_observe_kernel<true><<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, st>>>(env->cfg, env->bufs, lo, n);
+    else aie_observe_kernel<false><<<(n + wpb - 1) / wpb, wpb * 32, env->be.obs_smem, st>>>(env->cfg, env->bufs, lo, n);
     AIE_CUDA(cudaGetLastError(), "aie_observe_kernel launch");
     env->launches++;
     return AIE_OK;

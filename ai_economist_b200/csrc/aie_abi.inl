@@ -166,14 +166,15 @@ int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream) {
     if (!env) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_sample_random_actions: bind buffers and load state first");
     AIE_DEVICE_SCOPE(env->device);
-#if AIE_FUSED_POLICY
-    // tuning variant: after the first call (which still samples for the very first step) the step kernel draws the next
-    // step's actions itself; later calls only refresh the seed
-    const bool first = env->bufs.policy_seed == 0;
-    env->bufs.policy_seed = (aie::host_mix64(seed) ^ aie::host_mix64(++env->sample_calls)) | 1ull;
-    if (!first) return AIE_OK;
-#endif
     return aie::be::launch_sample(env, seed, stream);
+}
+
+int aie_set_fused_policy(aie_env *env, uint64_t seed, void *stream) {
+    if (!env) return fail(AIE_EINVAL, "null argument");
+    if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_set_fused_policy: bind buffers and load state first");
+    AIE_DEVICE_SCOPE(env->device);
+    env->bufs.policy_seed = seed ? (aie::host_mix64(seed) | 1ull) : 0ull;
+    return seed ? aie::be::launch_sample(env, seed, stream) : AIE_OK;   // actions for the very next step
 }
 
 int aie_observe(aie_env *env, void *stream) {

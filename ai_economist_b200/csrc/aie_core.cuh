@@ -40,17 +40,8 @@
 #define AIE_ON_DEVICE 0
 #endif
 
-#ifndef AIE_OBS_UNROLL
-#define AIE_OBS_UNROLL 1
-#endif
 #ifndef AIE_TWIST_UNROLL
 #define AIE_TWIST_UNROLL 8
-#endif
-#ifndef AIE_PLANES_V2
-#define AIE_PLANES_V2 0
-#endif
-#ifndef AIE_FUSED_POLICY
-#define AIE_FUSED_POLICY 0
 #endif
 #define AIE_PRAGMA_(x) _Pragma(#x)
 #define AIE_UNROLL(n) AIE_PRAGMA_(unroll n)
@@ -1096,526 +1087,11 @@ AIE_DEV_NOINLINE void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *g
     wsync();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Observations + masks.  Warp-collective like the step body (one warp streams out its env's tensors straight
-// from the shared-memory record), serial in emulation.
-// ------------------------------------------------------------------------------------------------
+}  // namespace aie
 
-struct ObsScratch {
-    double *net_hist;     // [2][P] summed price history (fp64, for the market rate); [2P] = annealed tax limit
-    float *shf;           // [sh_count] shared float staging (SH_*): scalars + price history + rates + incomes
-    float *sc_a;          // [A][AS_COUNT] per-agent scalar observations
-    float *agf;           // [AS_COUNT + 8P] the current agent's float staging: scalars, my orders, available orders
-    uint8_t *lim;         // [A][MS_COUNT] mask limits: mask[j] = idx_j < lim[slot_j]
-    uint8_t *pbits;       // [8] map plane -> cell bit (maps.state order), plane M = 0x40 ("inside the world")
-    uint8_t *locmap;      // [HW]  0 none, a+2
-    uint8_t *wstage;      // [3][ww] one agent's window: cell bits | 0x40 inside, owner code, agent-location code
-};
-// mt_img: the dead shared-memory image of the MT19937 key (nullptr when it is live, e.g. in emulation); extra: the
-// additional staging memory.  Each group goes where the host decided (DevCfg::obs_alias_mt).
-AIE_DEV ObsScratch obs_scratch_view(uint8_t *mt_img, uint8_t *extra, const DevCfg &c) {
-    ObsScratch s;
-    const int alias = mt_img ? c.obs_alias_mt : 0;
-    uint8_t *pb = (alias & 1) ? mt_img : extra;                                       // byte group
-    uint8_t *p = (alias & 2) ? mt_img + ((alias & 1) ? c.obs_bytes_size : 0)          // float group
-                             : extra + ((alias & 1) ? 0 : c.obs_bytes_size);
-    s.net_hist = (double *)p;     p += 8 * (2 * c.P + 2);
-    s.shf = (float *)p;           p += 4 * c.sh_count;
-    s.sc_a = (float *)p;          p += 4 * c.A * AS_COUNT;
-    s.agf = (float *)p;
-    s.lim = pb;                   pb += (c.A * MS_COUNT + 7) & ~7;
-    s.pbits = pb;                 pb += 8;
-    s.locmap = pb;                pb += (c.HW + 3) & ~3;  // 4-byte aligned, padded to a multiple of 4 bytes
-    s.wstage = pb;
-    return s;
-}
+#include "aie_obs.cuh"   // observations + masks (the other half of the fused step kernel)
 
-// Output slices of one env, computed where they are used (keeping ten 64-bit pointers live through the pass would
-// spill under the 64-register budget).
-struct ObsOut {
-    const DevBufs *b; const DevCfg *c; size_t env;
-    AIE_DEV_MEMBER size_t ww() const { return (size_t)c->win * c->win; }
-    AIE_DEV_MEMBER float *a_map() const { return b->a_map + env * c->A * (c->M + 1) * ww(); }
-    AIE_DEV_MEMBER int16_t *a_idx() const { return b->a_idx + env * c->A * 2 * ww(); }
-    AIE_DEV_MEMBER float *a_flat() const { return b->a_flat + env * c->A * c->Fa; }
-    AIE_DEV_MEMBER float *a_mask() const { return b->a_mask + env * c->A * c->Na; }
-    AIE_DEV_MEMBER float *p_map() const { return b->p_map + env * c->M * c->HW; }
-    AIE_DEV_MEMBER int16_t *p_idx() const { return b->p_idx + env * 2 * c->HW; }
-    AIE_DEV_MEMBER float *p_flat() const { return b->p_flat + env * c->Fp; }
-    AIE_DEV_MEMBER float *p_agents() const { return b->p_agents + env * c->A * c->Fpa; }
-    AIE_DEV_MEMBER float *p_mask() const { return b->p_mask + env * c->Np; }
-    AIE_DEV_MEMBER float *time_obs() const { return b->time_obs + env; }
-};
-
-// Contiguous output runs are written FRONT TO BACK with 16-byte stores: lanes take the 16-byte groups of the global
-// address space (whatever the run's own alignment); the few elements before the first / after the last whole group
-// are stored one by one.  Measured on B200 (tools/wpattern.cu): one warp streaming its slice in address order reaches
-// 5.5 TB/s where the same bytes written cell-major (each cell fanning out to every channel plane) reach 3.6 TB/s.
-struct RunSplit { int head, nq, tail0; };
-AIE_DEV RunSplit run_split(const void *dst, int n, int elem_log2) {
-    const int per = 16 >> elem_log2;  // elements per 16-byte group
-    RunSplit r;
-    r.head = (int)((per - (((uintptr_t)dst >> elem_log2) & (per - 1))) & (per - 1));
-    if (r.head > n) r.head = n;
-    r.nq = (n - r.head) / per;
-    r.tail0 = r.head + r.nq * per;
-    return r;
-}
-AIE_DEV void store4(float *p, float v0, float v1, float v2, float v3) {
-#if AIE_ON_DEVICE
-    *reinterpret_cast<float4 *>(p) = make_float4(v0, v1, v2, v3);
-#else
-    p[0] = v0; p[1] = v1; p[2] = v2; p[3] = v3;
-#endif
-}
-AIE_DEV void store8(int16_t *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {  // 8 int16, little endian
-#if AIE_ON_DEVICE
-    *reinterpret_cast<uint4 *>(p) = make_uint4(w0, w1, w2, w3);
-#else
-    const uint32_t w[4] = {w0, w1, w2, w3};
-    for (int j = 0; j < 8; j++) p[j] = (int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-#endif
-}
-AIE_DEV uint32_t div_magic(uint32_t x, uint32_t magic) {  // floor(x / n), magic = floor(2^32 / n) + 1, x * n < 2^32
-#if AIE_ON_DEVICE
-    return magic ? __umulhi(x, magic) : x;  // magic == 0 <=> n == 1
-#else
-    return magic ? (uint32_t)(((uint64_t)x * magic) >> 32) : x;
-#endif
-}
-// the (at most per-1 + per-1) elements outside the whole 16-byte groups: one predicated scalar store per lane
-template <typename T, typename F>
-AIE_DEV void store_edges(T *dst, const RunSplit &r, int n, int lane, F value_at) {
-    const int ne = r.head + (n - r.tail0);
-#if AIE_ON_DEVICE
-    if (lane < ne) { const int i = lane < r.head ? lane : r.tail0 + (lane - r.head); dst[i] = (T)value_at(i); }
-#else
-    for (int j = lane; j < ne; j += NL) { const int i = j < r.head ? j : r.tail0 + (j - r.head); dst[i] = (T)value_at(i); }
-#endif
-}
-template <typename F>
-AIE_DEV void store_run_f32(float *dst, int n, int lane, F value_at) {
-    const RunSplit r = run_split(dst, n, 2);
-    store_edges(dst, r, n, lane, value_at);
-#if AIE_ON_DEVICE
-    AIE_UNROLL(1)
-#endif
-    for (int g = lane; g < r.nq; g += NL) {
-        const int i0 = r.head + 4 * g;
-        store4(dst + i0, value_at(i0), value_at(i0 + 1), value_at(i0 + 2), value_at(i0 + 3));
-    }
-}
-// rows x n matrix, contiguous: dst[row * n + i] = value_at(row, i), written as ONE run (n_magic = floor(2^32 / n) + 1)
-template <typename F>
-AIE_DEV void store_rows_f32(float *dst, int rows, int n, uint32_t n_magic, int lane, F value_at) {
-    const int total = rows * n;
-    auto flat_value = [&](int x) { const int row = (int)div_magic((uint32_t)x, n_magic); return value_at(row, x - row * n); };
-    if (n < 4) { for (int x = lane; x < total; x += NL) dst[x] = flat_value(x); return; }
-    const RunSplit r = run_split(dst, total, 2);
-    store_edges(dst, r, total, lane, flat_value);
-#if AIE_ON_DEVICE
-    AIE_UNROLL(1)
-#endif
-    for (int g = lane; g < r.nq; g += NL) {
-        const int x0 = r.head + 4 * g;
-        const int row = (int)div_magic((uint32_t)x0, n_magic), i = x0 - row * n;
-        float v[4];
-        for (int j = 0; j < 4; j++) { const bool nx = i + j >= n; v[j] = value_at(nx ? row + 1 : row, nx ? i + j - n : i + j); }
-        store4(dst + x0, v[0], v[1], v[2], v[3]);
-    }
-}
-// np planes x n floats, contiguous: plane m, element i = (bytes[i] & pbits[m]) ? 1 : 0, written as ONE run.
-// `bytes` is 4-byte aligned shared memory, readable up to the word holding byte n + 3; n >= 4.
-AIE_DEV void store_bitplanes_f32(float *dst, int np, int n, uint32_t n_magic, const uint8_t *bytes, const uint8_t *pbits,
-                                 int lane) {
-    const int total = np * n;
-    if (n < 4) {  // degenerate planes: element-wise
-        for (int x = lane; x < total; x += NL) {
-            const int m = (int)div_magic((uint32_t)x, n_magic);
-            dst[x] = (bytes[x - m * n] & pbits[m]) ? 1.0f : 0.0f;
-        }
-        return;
-    }
-    const RunSplit r = run_split(dst, total, 2);
-    store_edges(dst, r, total, lane, [&](int x) {
-        const int m = x < n ? 0 : np - 1;  // head lies in the first plane, tail in the last
-        return (bytes[x - m * n] & pbits[m]) ? 1.0f : 0.0f;
-    });
-    const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes);
-#if AIE_PLANES_V2
-    // Tuning variant (-DAIE_PLANES_V2=1, not the default build): the plane index / in-plane offset of a lane's group
-    // are carried from one iteration to the next (the run advances by 4 * NL floats) and the output pointer is a running
-    // one, instead of a multiply-high, a multiply and a 64-bit address build per group.
-    if (n >= 2 * NL) {
-        const int x_first = r.head + 4 * lane;
-        int m = (int)div_magic((uint32_t)x_first, n_magic), i = x_first - m * n;
-        float *qq = dst + x_first;
-#if AIE_ON_DEVICE
-        AIE_UNROLL(1)
-#endif
-        for (int g = lane; g < r.nq; g += NL) {
-            const uint32_t v = fshr(wd[i >> 2], wd[(i >> 2) + 1], 8 * (i & 3));
-            uint32_t t = v & (pbits[m] * 0x01010101u);
-            const int left = n - i;
-            if (left < 4) {
-                const uint32_t low = (1u << (8 * left)) - 1u;
-                t = (t & low) | ((wd[0] << (8 * left)) & (pbits[m + 1] * 0x01010101u) & ~low);
-            }
-            store4(qq, (t & 0xFFu) ? 1.0f : 0.0f, (t & 0xFF00u) ? 1.0f : 0.0f, (t & 0xFF0000u) ? 1.0f : 0.0f,
-                   (t & 0xFF000000u) ? 1.0f : 0.0f);
-            qq += 4 * NL; i += 4 * NL;
-            if (i >= n) { i -= n; m++; }   // 4 * NL <= 2 * n: at most two plane boundaries per step
-            if (i >= n) { i -= n; m++; }
-        }
-        return;
-    }
-#endif
-    float *q = dst + r.head;
-#if AIE_ON_DEVICE
-    AIE_UNROLL(1)
-#endif
-    for (int g = lane; g < r.nq; g += NL) {
-        const int x0 = r.head + 4 * g;
-        const int m = (int)div_magic((uint32_t)x0, n_magic), i = x0 - m * n;
-        const uint32_t v = fshr(wd[i >> 2], wd[(i >> 2) + 1], 8 * (i & 3));
-        uint32_t t = v & (pbits[m] * 0x01010101u);
-        const int left = n - i;  // elements of this group that still belong to plane m
-        if (left < 4) {          // the group runs over into plane m + 1 (once per plane boundary)
-            const uint32_t low = (1u << (8 * left)) - 1u;
-            t = (t & low) | ((wd[0] << (8 * left)) & (pbits[m + 1] * 0x01010101u) & ~low);
-        }
-        store4(q + 4 * g, (t & 0xFFu) ? 1.0f : 0.0f, (t & 0xFF00u) ? 1.0f : 0.0f, (t & 0xFF0000u) ? 1.0f : 0.0f,
-               (t & 0xFF000000u) ? 1.0f : 0.0f);
-    }
-}
-// dst[i] = code(bytes[i]) widened to int16, code = identity (OWNER == false) or the house-owner encoding of an
-// int8 owner byte (-1 -> 0, a -> a + 2; layout_from_file.py:438-440) applied four bytes at a time.
-template <bool OWNER>
-AIE_DEV uint32_t idx_code4(uint32_t v) {
-    if (!OWNER) return v;
-    const uint32_t none = (v >> 7) & 0x01010101u;                 // 1 in every byte that held -1
-    return ((v & 0x7F7F7F7Fu) + 0x02020202u) & ~(none * 0xFFu);   // owner indices are < 64: no carry between bytes
-}
-template <bool OWNER>
-AIE_DEV void store_bytes_i16(int16_t *dst, int n, const uint8_t *bytes, int lane) {
-    const RunSplit r = run_split(dst, n, 1);
-    store_edges(dst, r, n, lane, [&](int i) { return (int)(idx_code4<OWNER>(bytes[i]) & 0xFFu); });
-    const uint32_t *wd = reinterpret_cast<const uint32_t *>(bytes) + (r.head >> 2);
-    const int sh = 8 * (r.head & 3);
-    int16_t *q = dst + r.head;
-#if AIE_ON_DEVICE
-    AIE_UNROLL(1)
-#endif
-    for (int g = lane; g < r.nq; g += NL) {
-        const uint32_t w0 = wd[2 * g], w1 = wd[2 * g + 1], w2 = wd[2 * g + 2];
-        const uint32_t lo = idx_code4<OWNER>(fshr(w0, w1, sh)), hi = idx_code4<OWNER>(fshr(w1, w2, sh));
-        store8(q + 8 * g, prmt(lo, 0u, 0x4140u), prmt(lo, 0u, 0x4342u), prmt(hi, 0u, 0x4140u), prmt(hi, 0u, 0x4342u));
-    }
-}
-
-// One element of a "flat" vector: the program entry names a slot of the shared or of the agent's float staging array
-AIE_DEV float flat_value(const float *shf, const float *agf, uint32_t entry) {
-    return (AIE_FLAT_KIND(entry) == FK_AGENT ? agf : shf)[AIE_FLAT_PAYLOAD(entry)];
-}
-
-#if AIE_FUSED_POLICY
-// Tuning variant (-DAIE_FUSED_POLICY=1): the bench's random policy fused into the observation pass.  Uniform choice among
-// the open entries j in [0, n) of a predicate, by one warp (same ballot / popcount scheme as sample_segment_warp).
-AIE_DEV uint64_t fp_mix64(uint64_t x) {
-    x += 0x9e3779b97f4a7c15ull;
-    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
-    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
-    return x ^ (x >> 31);
-}
-template <typename F>
-AIE_DEV int fp_sample(F open_at, int n, uint64_t key, int lane) {
-    int total = 0;
-    for (int base = 0; base < n; base += NL) { const int j = base + lane; total += __popc_u32(wballot(j < n && open_at(j))); }
-    if (total == 0) return 0;
-    int r = (int)((uint32_t)(fp_mix64(key) >> 32) % (uint32_t)total);
-    for (int base = 0; base < n; base += NL) {
-        const int j = base + lane;
-        const uint32_t m = wballot(j < n && open_at(j));
-        const int cnt = __popc_u32(m);
-        if (r < cnt) {
-            uint32_t mm = m;
-            for (int i = 0; i < r; i++) mm &= mm - 1;   // drop the r lowest set bits
-            return base + first_lane(mm);
-        }
-        r -= cnt;
-    }
-    return 0;
-}
-#endif
-
-template <bool EXT = false>
-AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *mt_img, uint8_t *extra, const ObsOut &o,
-                         const uint16_t *tab, int lane) {
-    const Env e = env_view(rec, grec, c);
-    const ObsScratch s = obs_scratch_view(mt_img, extra, c);
-    const int A = c.A, H = c.H, W = c.W, HW = c.HW, P = c.P, M = c.M, win = c.win, w = c.w, ww = win * win;
-    const double inv_scale = c.obs_scaling ? 0.01 : 1.0;
-    const double time_v = (double)e.hdr[HDR_T] / (c.obs_scaling ? (double)c.T : 1.0);
-
-    // ---- phase 1: stage every scalar the flat vectors / masks need (float, final values) -------------
-    for (int k = lane; k < (HW + 3) / 4; k += NL) ((uint32_t *)s.locmap)[k] = 0u;
-    for (int m = lane; m < 8; m += NL) {  // maps.state channel order: Stone, Wood, House, [Water], StoneSrc, WoodSrc
-        const uint32_t b3 = c.has_water ? CELL_WATER : CELL_STONE_SRC, b4 = c.has_water ? CELL_STONE_SRC : CELL_WOOD_SRC;
-        const uint32_t bit = m == 0 ? (uint32_t)CELL_STONE : m == 1 ? (uint32_t)CELL_WOOD : m == 2 ? (uint32_t)CELL_HOUSE
-                           : m == 3 ? b3 : m == 4 ? b4 : (uint32_t)CELL_WOOD_SRC;
-        s.pbits[m] = (uint8_t)(m == M ? 0x40u : (m < M ? bit : 0u));
-    }
-    if (c.has[COMP_CDA]) {  // continuous_double_auction.py:491-542
-        for (int i = lane; i < 2 * P; i += NL) {  // i = cc * P + p; sums over agents in index order
-            int cc = i / P, p = i - cc * P;
-            double acc = 0.0; int fa = 0, fb = 0;
-            for (int a = 0; a < A; a++) {
-                acc += e.price_hist[(cc * A + a) * P + p];
-                fa += e.ask_hist[(cc * A + a) * P + p];
-                fb += e.bid_hist[(cc * A + a) * P + p];
-            }
-            s.net_hist[i] = acc; s.shf[c.sh_full + i] = (float)fb; s.shf[c.sh_full + 2 * P + i] = (float)fa;
-            s.shf[SH_PRICE_HIST + i] = (float)(acc * inv_scale);
-        }
-    }
-    if (c.has[COMP_TAX]) {  // redistribution.py:974-1023
-        const int pos = e.hdr[HDR_TAX_POS];
-        if (lane == 0) {
-            s.shf[SH_TAX_IS_TAX_DAY] = pos >= c.period ? 1.0f : 0.0f;
-            s.shf[SH_TAX_IS_FIRST] = pos == 1 ? 1.0f : 0.0f;
-            s.shf[SH_TAX_PHASE] = (float)((double)pos / c.period);
-            // components/utils.py:10-57: current annealed |rate| limit for the planner mask
-            double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)e.hdr[HDR_COMPLETIONS] - c.ann_warm)));
-            s.net_hist[2 * P] = vis * c.ann_full;
-        }
-        for (int b = lane; b < c.B; b += NL) s.shf[c.sh_curr_rates + b] = (float)tax_rate_observed<EXT>(c, e, b);
-        for (int a = lane; a < A; a += NL) {
-            s.sc_a[a * AS_COUNT + AS_TAX_MARG] = (float)tax_marginal_rate<EXT>(c, e, (e.coin[a] + e.esc_coin[a]) - e.last_coin[a]);
-            const double v = e.last_income[a] / c.period;  // ascending rank -> sorted position (:908-911)
-            int rank = 0;
-            for (int j = 0; j < A; j++) {
-                double vj = e.last_income[j] / c.period;
-                rank += (vj < v || (vj == v && j < a)) ? 1 : 0;
-            }
-            s.shf[c.sh_last_incomes + rank] = (float)v;
-            s.sc_a[a * AS_COUNT + AS_TAX_LAST_INCOME] = (float)v;
-            s.sc_a[a * AS_COUNT + AS_TAX_LAST_MARG] = (float)e.last_marg[a];
-        }
-    }
-    if (lane == 0) { s.shf[SH_ZERO] = 0.0f; s.shf[SH_TIME] = (float)time_v; o.time_obs()[0] = (float)time_v; }
-    wsync();
-    for (int a = lane; a < A; a += NL) {
-        const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
-        s.locmap[row * W + col] = (uint8_t)(a + 2);
-        float *sc = s.sc_a + a * AS_COUNT;
-        sc[AS_LOC_ROW] = (float)((double)row / H);
-        sc[AS_LOC_COL] = (float)((double)col / W);
-        sc[AS_INV_COIN] = (float)(e.coin[a] * inv_scale);
-        sc[AS_INV_STONE] = (float)(e.inv[2 * a] * inv_scale);
-        sc[AS_INV_WOOD] = (float)(e.inv[2 * a + 1] * inv_scale);
-        sc[AS_BUILD_PAYMENT] = (float)(e.bpay[a] / c.build_payment);
-        sc[AS_BUILD_SKILL] = (float)e.bskill[a];
-        sc[AS_BONUS] = (float)e.bonus[a];
-    }
-    if (c.has[COMP_CDA])
-        for (int cc = lane; cc < 2; cc += NL) {  // market_rate (:504-513)
-            double dot = 0.0, tot = 0.0;
-            for (int p = 0; p < P; p++) { dot += p * s.net_hist[cc * P + p]; tot += s.net_hist[cc * P + p]; }
-            s.shf[SH_MARKET_RATE + cc] = (float)(dot / fmax(0.001, tot));
-        }
-    wsync();
-    for (int a = lane; a < A; a += NL) {  // mask limits (build.py:180-193, move.py:167-188, cda :544-580)
-        uint8_t *lim = s.lim + a * MS_COUNT;
-        lim[MS_ONE] = 1;
-        lim[MS_BUILD] = can_build(c, e, a) ? 1 : 0;
-        const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
-        const int roff[4] = {0, 0, -1, 1}, coff[4] = {-1, 1, 0, 0};
-        for (int d = 0; d < 4; d++) {
-            int r2 = row + roff[d], c2 = col + coff[d];
-            bool ok = r2 >= 0 && r2 < H && c2 >= 0 && c2 < W;
-            if (ok) {
-                int k = r2 * W + c2;
-                int8_t ow = e.owner[k];
-                ok = s.locmap[k] == 0 && !(e.cell[k] & CELL_WATER) && (ow < 0 || ow == a);
-            }
-            lim[MS_G0 + d] = ok ? 1 : 0;
-        }
-        if (c.has[COMP_CDA]) {
-            // Buy_c[p] = (n_orders < K) and (p <= Coin)  <=>  p < min(P, floor(Coin) + 1)
-            const double coin = e.coin[a];
-            const int can_pay = coin >= (double)P ? P : (int)floor(coin) + 1;
-            for (int cc = 0; cc < 2; cc++) {
-                const bool open = e.n_orders[cc * A + a] < c.K;
-                lim[MS_BUY0 + cc] = (uint8_t)(open ? can_pay : 0);
-                lim[MS_SELL0 + cc] = (uint8_t)((open && e.inv[2 * a + cc] > 0) ? P : 0);
-            }
-        }
-    }
-    wsync();
-
-    // ---- phase 2: outputs ----------------------------------------------------------------------
-    // Every output tensor's env slice is one contiguous run (or a few) written front to back (store_run_*).
-    // channel -> cell bit (maps.state order: Stone, Wood, House, [Water], StoneSrc, WoodSrc); 0x40 = "inside" plane
-    if (c.planner_spatial) {
-        store_bitplanes_f32(o.p_map(), M, HW, c.HW_magic, e.cell, s.pbits, lane);
-        store_bytes_i16<true>(o.p_idx(), HW, (const uint8_t *)e.owner, lane);
-        store_bytes_i16<false>(o.p_idx() + HW, HW, s.locmap, lane);
-    }
-    if (EXT && c.full_obs) {
-        // full_observability (layout_from_file.py:465-472): every agent gets the whole map - the same M bit planes as
-        // the planner - and the two index planes with its own index recoded to 1 (staged as bytes per agent)
-        const int HW4 = (HW + 3) & ~3;
-        uint8_t *so = s.wstage, *sl = s.wstage + HW4;
-        for (int a = 0; a < A; a++) {
-            for (int k = lane; k < HW; k += NL) {
-                const int ow = e.owner[k], vl = s.locmap[k];
-                so[k] = (uint8_t)(ow < 0 ? 0 : (ow == a ? 1 : ow + 2));
-                sl[k] = (uint8_t)(vl == a + 2 ? 1 : vl);
-            }
-            for (int i = lane; i < AS_COUNT; i += NL) s.agf[i] = s.sc_a[a * AS_COUNT + i];
-            if (c.has[COMP_CDA])
-                for (int i = lane; i < 4 * P; i += NL) {
-                    const int side = i >= 2 * P ? 1 : 0, r = i - side * 2 * P, cc = r >= P ? 1 : 0, pl = r - cc * P;
-                    const float mine = (float)(side ? e.ask_hist : e.bid_hist)[(cc * A + a) * P + pl];
-                    s.agf[AS_COUNT + i] = mine;
-                    s.agf[AS_COUNT + 4 * P + i] = s.shf[c.sh_full + i] - mine;
-                }
-            wsync();
-            float *am = o.b->a_map + (o.env * A + a) * (size_t)c.a_map_elems;
-            int16_t *ai = o.b->a_idx + (o.env * A + a) * (size_t)c.a_idx_elems;
-            store_bitplanes_f32(am, M, HW, c.HW_magic, e.cell, s.pbits, lane);
-            store_bytes_i16<false>(ai, HW, so, lane);
-            store_bytes_i16<false>(ai + HW, HW, sl, lane);
-            {
-                const float *shf = s.shf, *agf = s.agf;
-                store_run_f32(o.a_flat() + a * c.Fa, c.Fa, lane, [=](int j) { return flat_value(shf, agf, tab[j]); });
-            }
-            wsync();
-        }
-    } else
-    // agent windows (layout_from_file.py:468-515): per agent, the window's cells are staged once as bytes (one lane
-    // per window cell), then the M+1 map planes and the 2 index planes stream out of the staged bytes
-    {
-        // lane's first window cell and the (dr, dc) step for q += NL: one small division per warp per step
-#if AIE_ON_DEVICE
-        const int dr_first = (int)div_magic((uint32_t)lane, c.win_magic), dc_first = lane - dr_first * win;
-        const int dr_step = c.win_dr32, dc_step = c.win_dc32;  // NL / win and NL % win, from the host
-#else
-        const int dr_first = lane / win, dc_first = lane - dr_first * win;
-        const int dr_step = NL / win, dc_step = NL - dr_step * win;
-#endif
-        uint8_t *wc = s.wstage, *wi = s.wstage + ((ww + 7) & ~3);  // wi: [2][ww] owner code, location code
-        for (int a = 0; a < A; a++) {
-            const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;
-            int dr = dr_first, dc = dc_first;
-            for (int q = lane; q < ww; q += NL) {
-                const int r2 = r0 + dr, c2 = c0 + dc;
-                const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
-                uint32_t cb = 0; int vo = 0, vl = 0;
-                if (inside) {
-                    const int k = r2 * W + c2;
-                    cb = e.cell[k] | 0x40u;
-                    const int ow = e.owner[k];
-                    vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
-                    vl = s.locmap[k];
-                    if (vl == a + 2) vl = 1;
-                }
-                wc[q] = (uint8_t)cb; wi[q] = (uint8_t)vo; wi[ww + q] = (uint8_t)vl;
-                dr += dr_step; dc += dc_step;
-                if (dc >= win) { dc -= win; dr += 1; }
-            }
-            // the agent's float staging: scalars, then my / available order counts (continuous_double_auction.py:515-542)
-            for (int i = lane; i < AS_COUNT; i += NL) s.agf[i] = s.sc_a[a * AS_COUNT + i];
-            if (c.has[COMP_CDA])
-                for (int i = lane; i < 4 * P; i += NL) {  // i = (side * 2 + commodity) * P + price level
-                    const int side = i >= 2 * P ? 1 : 0, r = i - side * 2 * P, cc = r >= P ? 1 : 0, pl = r - cc * P;
-                    const float mine = (float)(side ? e.ask_hist : e.bid_hist)[(cc * A + a) * P + pl];
-                    s.agf[AS_COUNT + i] = mine;
-                    s.agf[AS_COUNT + 4 * P + i] = s.shf[c.sh_full + i] - mine;
-                }
-            wsync();
-            store_bitplanes_f32(o.a_map() + a * (M + 1) * ww, M + 1, ww, c.ww_magic, wc, s.pbits, lane);
-            store_bytes_i16<false>(o.a_idx() + a * 2 * ww, 2 * ww, wi, lane);
-            {
-                const float *shf = s.shf, *agf = s.agf;
-                store_run_f32(o.a_flat() + a * c.Fa, c.Fa, lane, [=](int j) { return flat_value(shf, agf, tab[j]); });
-            }
-            wsync();
-        }
-    }
-    // planner flat vectors (base_env.py:562-612: sorted-key concatenation, float32) and masks (base_agent.py:440-460)
-    {
-        const float *shf = s.shf, *sc = s.sc_a;
-        const uint16_t *tpa = tab + c.tab_pa, *tp = tab + c.tab_p;
-        if (!EXT || c.Fpa > 0)
-        store_rows_f32(o.p_agents(), A, c.Fpa, c.Fpa_magic, lane,
-                       [=](int a, int j) { return flat_value(shf, sc + a * AS_COUNT, tpa[j]); });
-        store_run_f32(o.p_flat(), c.Fp, lane, [=](int j) { return flat_value(shf, shf, tp[j]); });
-    }
-    {
-        const uint16_t *mt = tab + c.tab_m;
-        const uint8_t *lim = s.lim;
-        store_rows_f32(o.a_mask(), A, c.Na, c.Na_magic, lane, [=](int a, int j) {
-            const uint32_t en = mt[j];
-            return ((en & 255u) < lim[a * MS_COUNT + (en >> 8)]) ? 1.0f : 0.0f;
-        });
-    }
-    if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
-        const bool first_day = e.hdr[HDR_TAX_POS] == 1;
-        for (int b = 0; b < c.B; b++)
-            for (int rr = lane; rr <= c.R; rr += NL) {
-                bool open = rr == 0 || first_day;
-                if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= s.net_hist[2 * P];
-                // single-action planner: one leading NO-OP, then every bracket's R rates (base_agent.py:452-459)
-                const int at = (EXT && c.planner_single) ? (rr == 0 ? 0 : b * c.R + rr) : b * (1 + c.R) + rr;
-                o.p_mask()[at] = open ? 1.0f : 0.0f;
-            }
-    } else if (lane == 0) {
-        o.p_mask()[0] = 1.0f;
-    }
-#if AIE_FUSED_POLICY
-    if (o.b->policy_seed) {   // the next step's random actions, drawn from the limits / conditions the masks were written from
-        const uint64_t key0 = fp_mix64(o.b->policy_seed ^ fp_mix64((uint64_t)o.env)) + ((uint64_t)(uint32_t)e.hdr[HDR_T] << 20);
-        const uint16_t *mtab = tab + c.tab_m;
-        int32_t *aa = const_cast<int32_t *>(o.b->act_a) + o.env * (size_t)(A * c.n_act_a);
-        for (int a = 0; a < A; a++) {
-            const uint8_t *lim = s.lim + a * MS_COUNT;
-            if (!c.multi_action) {
-                const int v = fp_sample([&](int j) { const uint32_t en = mtab[j]; return (en & 255u) < lim[en >> 8]; },
-                                        c.Na, key0 + 0x100 * a, lane);
-                if (lane == 0) aa[a] = v;
-            } else {
-                int off = 0;
-                for (int si = 0; si < c.n_sub; si++) {
-                    const int v = fp_sample([&](int j) { const uint32_t en = mtab[off + j]; return (en & 255u) < lim[en >> 8]; },
-                                            c.sub_n[si] + 1, key0 + 0x100 * a + si + 1, lane);
-                    if (lane == 0) aa[a * c.n_sub + si] = v;
-                    off += c.sub_n[si] + 1;
-                }
-            }
-        }
-        if (c.planner_acts && o.b->act_p) {
-            int32_t *ap = const_cast<int32_t *>(o.b->act_p) + o.env * (size_t)c.n_act_p;
-            const bool first_day = e.hdr[HDR_TAX_POS] == 1;
-            const double limit = s.net_hist[2 * P];
-            auto rate_open = [&](int rr) {   // rr = 0: NO-OP; else discretised rate rr - 1 (same rule as the mask above)
-                bool open = rr == 0 || first_day;
-                if (open && rr != 0 && c.tax_annealing) open = fabs(c.disc_rates[rr - 1]) <= limit;
-                return open;
-            };
-            if (EXT && c.planner_single) {
-                const int v = fp_sample([&](int j) { return j == 0 || rate_open((j - 1) % c.R + 1); }, c.Np, key0 + 0x10000, lane);
-                if (lane == 0) ap[0] = v;
-            } else {
-                for (int b = 0; b < c.B; b++) {
-                    const int v = fp_sample(rate_open, 1 + c.R, key0 + 0x10000 + b, lane);
-                    if (lane == 0) ap[b] = v;
-                }
-            }
-        }
-    }
-#endif
-}
+namespace aie {
 
 // ------------------------------------------------------------------------------------------------
 // Random policy (bench / testing utility): uniform over the unmasked entries of one mask segment.

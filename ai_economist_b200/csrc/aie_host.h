@@ -209,10 +209,10 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
                 std::string s = std::string("ContinuousDoubleAuction-"), r = std::string("-") + CN[cc];
                 ka.push_back(K(s + "market_rate" + r, FK_SHARED, SH_MARKET_RATE + cc, 1));
                 ka.push_back(K(s + "price_history" + r, FK_SHARED, SH_PRICE_HIST + cc * c.P, c.P));
-                ka.push_back(K(s + "available_asks" + r, FK_AGENT, AS_COUNT + 4 * c.P + (2 + cc) * c.P, c.P));
-                ka.push_back(K(s + "available_bids" + r, FK_AGENT, AS_COUNT + 4 * c.P + cc * c.P, c.P));
-                ka.push_back(K(s + "my_asks" + r, FK_AGENT, AS_COUNT + (2 + cc) * c.P, c.P));
-                ka.push_back(K(s + "my_bids" + r, FK_AGENT, AS_COUNT + cc * c.P, c.P));
+                ka.push_back(K(s + "available_asks" + r, FK_AVAIL, (2 + cc) * c.P, c.P));
+                ka.push_back(K(s + "available_bids" + r, FK_AVAIL, cc * c.P, c.P));
+                ka.push_back(K(s + "my_asks" + r, FK_MY, (2 + cc) * c.P, c.P));
+                ka.push_back(K(s + "my_bids" + r, FK_MY, cc * c.P, c.P));
                 kp.push_back(K(s + "market_rate" + r, FK_SHARED, SH_MARKET_RATE + cc, 1));
                 kp.push_back(K(s + "price_history" + r, FK_SHARED, SH_PRICE_HIST + cc * c.P, c.P));
                 kp.push_back(K(s + "full_asks" + r, FK_SHARED, c.sh_full + (2 + cc) * c.P, c.P));
@@ -240,9 +240,33 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         c.Fa_magic = magic(c.Fa); c.Fpa_magic = magic(c.Fpa); c.Na_magic = magic(c.Na);
         c.win_magic = magic(c.win); c.win_dr32 = 32 / c.win; c.win_dc32 = 32 - c.win_dr32 * c.win;
     }
-    c.tab_p = c.Fa; c.tab_pa = c.tab_p + c.Fp; c.tab_m = c.tab_pa + c.Fpa; c.tab_n = (c.tab_m + c.Na + 1) & ~1;
+    c.tab_p = c.Fa; c.tab_pa = c.tab_p + c.Fp; c.tab_m = c.tab_pa + c.Fpa;
+    c.tab_hoff = c.tab_m + c.Na;
+    c.tab_seg = c.tab_hoff + 4 * c.P;
     memcpy(tb.w, prog_a, 2 * c.Fa); memcpy(tb.w + c.tab_p, prog_p, 2 * c.Fp);
     memcpy(tb.w + c.tab_pa, prog_pa, 2 * c.Fpa); memcpy(tb.w + c.tab_m, mask_prog, 2 * c.Na);
+    {
+        // mask segments (random policy): runs of consecutive mask entries of one slot with idx 0 .. count-1
+        int n_seg = 0, si = 0;
+        c.seg_lo[0] = 0;
+        for (int j = 0; j < c.Na;) {
+            const int slot = mask_prog[j] >> 8;
+            int cnt = 0;
+            while (j + cnt < c.Na && (mask_prog[j + cnt] >> 8) == slot && (mask_prog[j + cnt] & 255) == cnt) cnt++;
+            // a multi-action subspace starts with its own NO-OP entry (slot MS_ONE): close the previous subspace there
+            if (c.multi_action && slot == MS_ONE && n_seg > 0) c.seg_lo[++si] = n_seg;
+            if (n_seg >= 64) return bad("too many action mask segments");
+            tb.w[c.tab_seg + n_seg++] = (uint16_t)((cnt << 8) | slot);
+            j += cnt;
+        }
+        c.seg_lo[++si] = n_seg;
+        if (si != c.n_act_a) return bad("internal: mask segments do not match the action subspaces");
+        c.tab_lut = (c.tab_seg + n_seg + 7) & ~7;   // 16-byte aligned (u16 words)
+        float *lut = (float *)(tb.w + c.tab_lut);   // nibble -> four floats (bit k of the nibble -> element k)
+        for (int k = 0; k < 16; k++) for (int j = 0; j < 4; j++) lut[4 * k + j] = (float)((k >> j) & 1);
+        c.tab_n = c.tab_lut + 128;
+        if (c.tab_n > TAB_WORDS) return bad("internal: table overflow");
+    }
     // record layout
     {
         const int A = c.A, P = c.P;
@@ -277,22 +301,85 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             c.rec_bytes = off;
         };
         layout(false);
-        c.split = (c.rec_bytes > 24 * 1024) ? 1 : 0;   // records this large would leave < 8 warps per SM resident
+        // Large records (deep order books, many agents): one CTA of four warps per env (mw = 4), the whole record resident in
+        // shared memory.  Records too large even for that keep the two big, sparsely touched sections in HBM/L2 (split).
+        c.mw = (c.rec_bytes > 24 * 1024) ? 4 : 1;
+        c.split = (c.rec_bytes > 100 * 1024) ? 1 : 0;
         if (c.split) layout(true);
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
-        c.obs_floats_size = align16(8 * (2 * P + 2) + 4 * (c.sh_count + A * AS_COUNT + AS_COUNT + 8 * P));
-        const int stage_win = 3 * c.win * c.win + 24, stage_full = c.full_obs ? 2 * ((c.HW + 3) & ~3) + 16 : 0;
-        c.obs_bytes_size = align16(((A * MS_COUNT + 7) & ~7) + 8 + ((c.HW + 3) & ~3) + (stage_full > stage_win ? stage_full : stage_win));
-        c.obs_scratch_bytes = c.obs_floats_size + c.obs_bytes_size;
+        {   // histogram offsets of the FK_MY / FK_AVAIL entries: i = (side * 2 + commodity) * P + level -> byte offset from
+            // bid_hist of agent 0's counter (agent a adds a * P)
+            for (int i = 0; i < 4 * P; i++) {
+                const int side = i / (2 * P), r = i - side * 2 * P, cc = r / P, pl = r - cc * P;
+                tb.w[c.tab_hoff + i] = (uint16_t)(side * (c.off_ask_hist - c.off_bid_hist) + cc * A * P + pl);
+            }
+        }
+        // ---- observation staging (aie_obs.cuh: ObsScratch) ----
+        const int ww = c.win * c.win, HW4 = (c.HW + 3) & ~3;
+        c.wc_stride = (ww + 7) & ~7;
+        c.pl_stride_a = 4 * ((ww + 31) / 32);
+        c.pl_stride_p = 4 * ((c.HW + 31) / 32);
+        int need[OB_COUNT];
+        need[OB_NET_HIST] = align16(8 * (2 * P + 2));
+        need[OB_SHF] = align16(4 * c.sh_count);
+        need[OB_SC_A] = align16(4 * A * AS_COUNT);
+        need[OB_LIM] = align16(A * MS_COUNT);
+        need[OB_PSH] = 16;
+        need[OB_LOCMAP] = align16(HW4 + 8);
+        const bool whole_map = c.planner_spatial || c.full_obs;
+        auto chunk_needs = [&](int ac) {
+            need[OB_WC] = align16(ac * c.wc_stride + 16);
+            need[OB_WI] = align16(std::max(ac * 2 * ww, c.full_obs ? 2 * HW4 : 0) + 16);
+            need[OB_PL] = align16(std::max(ac * (c.M + 1) * c.pl_stride_a, whole_map ? c.M * c.pl_stride_p : 0) + 16);
+            need[OB_BITS] = align16(4 * ((std::max(ac * (c.M + 1) * ww, whole_map ? c.M * c.HW : 0) + 31) / 32) + 16);
+        };
+        const int early_ids[] = {OB_NET_HIST, OB_SHF, OB_SC_A, OB_LIM, OB_PSH, OB_LOCMAP};
+        const int late_ids[] = {OB_WI, OB_PL, OB_BITS, OB_WC};
+        // device placement.  Pools (byte ranges of the env's shared-memory region): the MT19937 key image (free from the
+        // start of the pass), the dead tail of the record image + the step scratch (free once the scalars are staged), and
+        // extra memory behind them (grows as needed).
+        const int mt_lo = c.off_mt, mt_hi = c.off_mt + 4 * 624;
+        const int late_lo = c.split ? c.resident_bytes : c.off_price_hist, late_hi = c.resident_bytes + c.step_scratch_bytes;
+        auto place = [&](int ac, bool commit) {
+            chunk_needs(ac);
+            int cur_mt = mt_lo, cur_late = late_lo, extra = 0;
+            int off[OB_COUNT];
+            auto take_extra = [&](int bytes) { int o = late_hi + extra; extra += bytes; return o; };
+            int early_total = 0;
+            for (int id : early_ids) early_total += need[id];
+            const bool early_in_mt = early_total <= mt_hi - mt_lo;
+            for (int id : early_ids) {
+                if (early_in_mt) { off[id] = cur_mt; cur_mt += need[id]; }
+                else off[id] = take_extra(need[id]);
+            }
+            for (int id : late_ids) {
+                if (need[id] <= mt_hi - cur_mt) { off[id] = cur_mt; cur_mt += need[id]; }
+                else if (need[id] <= late_hi - cur_late) { off[id] = cur_late; cur_late += need[id]; }
+                else off[id] = take_extra(need[id]);
+            }
+            if (commit) {
+                for (int i = 0; i < OB_COUNT; i++) c.ob[i] = off[i];
+                c.obs_extra_bytes = align16(extra);
+                c.obs_alias_mt = early_in_mt ? 1 : 0;
+            }
+            return extra;
+        };
         {
-            const int mt_bytes = 4 * 624;
-            if (c.obs_scratch_bytes <= mt_bytes) c.obs_alias_mt = 3;
-            else if (c.obs_bytes_size <= mt_bytes && c.obs_bytes_size >= c.obs_floats_size) c.obs_alias_mt = 1;
-            else if (c.obs_floats_size <= mt_bytes) c.obs_alias_mt = 2;
-            else if (c.obs_bytes_size <= mt_bytes) c.obs_alias_mt = 1;
-            else c.obs_alias_mt = 0;
-            c.obs_extra_bytes = ((c.obs_alias_mt & 1) ? 0 : c.obs_bytes_size) + ((c.obs_alias_mt & 2) ? 0 : c.obs_floats_size);
+            // agents per chunk: the largest count (<= 16) whose staging needs no extra shared memory, else 4
+            int best = 0;
+            for (int ac = std::min(A, 16); ac >= 1; ac--) {
+                const int base_extra = place(1, false) ;
+                if (place(ac, false) <= base_extra) { best = ac; break; }
+            }
+            c.ob_chunk = best ? best : std::min(A, 4);
+            place(c.ob_chunk, true);
+        }
+        {   // emulation: everything in a separate scratch allocation, nothing aliases the (live) record
+            chunk_needs(c.ob_chunk);
+            int off = 0;
+            for (int i = 0; i < OB_COUNT; i++) { c.ob_emu[i] = off; off += need[i]; }
+            c.obs_scratch_bytes = off;
         }
     }
     return AIE_OK;

@@ -51,10 +51,15 @@ enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
 // Observation "programs" (built once on the host from the reference's sorted-key flattening, base_env.py:562-612).
 // flat entry  = kind << 13 | payload:
 //   FK_SHARED  payload = index into the per-env shared float staging array (SH_*, then sh_full: full bid/ask counts)
-//   FK_AGENT   payload = index into the current agent's float staging array: AS_* scalars, then from AS_COUNT on
-//              my orders [side][commodity][P] and available (all - mine) orders [side][commodity][P]  (side 0 bids, 1 asks)
+//   FK_AGENT   payload = index of one of the agent's scalar observations (AS_*)
+//   FK_MY      payload = i = (side * 2 + commodity) * P + price level (side 0 bids, 1 asks): the agent's own open orders there,
+//              read from the record's uint8 histograms at hoff[i] + agent * P (hoff: table built on the host)
+//   FK_AVAIL   same i: everybody else's open orders = full count (shared staging at sh_full + i) - own
 // mask entry  = slot << 8 | idx; the mask value is (idx < limit[agent][slot])
-enum { FK_SHARED = 0, FK_AGENT = 1 };
+// mask segment = count << 8 | slot: `count` consecutive mask entries of one slot with idx 0 .. count-1 (random policy)
+enum { FK_SHARED = 0, FK_AGENT = 1, FK_MY = 2, FK_AVAIL = 3 };
+// observation staging buffers (see ObsScratch in aie_obs.cuh); offsets DevCfg::ob[] / ob_emu[]
+enum { OB_NET_HIST = 0, OB_SHF, OB_SC_A, OB_LIM, OB_PSH, OB_LOCMAP, OB_WC, OB_WI, OB_PL, OB_BITS, OB_COUNT };
 enum { AS_LOC_ROW = 0, AS_LOC_COL, AS_INV_COIN, AS_INV_STONE, AS_INV_WOOD, AS_BUILD_PAYMENT, AS_BUILD_SKILL, AS_BONUS,
        AS_TAX_MARG, AS_TAX_LAST_INCOME, AS_TAX_LAST_MARG, AS_COUNT = 12 };
 enum { SH_ZERO = 0, SH_TIME = 1, SH_MARKET_RATE = 2, SH_TAX_IS_TAX_DAY = 4, SH_TAX_IS_FIRST = 5, SH_TAX_PHASE = 6,
@@ -106,17 +111,28 @@ struct DevCfg {
     // Large envs (deep order books, many agents) keep the two big, sparsely touched sections - price history and
     // order slots, laid out last - in HBM/L2 and stage only [0, resident_bytes) in shared memory (split != 0).
     int32_t split, resident_bytes;
-    // The observation pass runs after the record has been written back, when the MT19937 key's shared-memory image
-    // is dead: its 2496 bytes double as the observation staging area when that fits (obs_alias_mt).
-    // The staging area has two groups - byte arrays (mask limits, agent-location map, window staging) and float arrays -
-    // and each group that fits is placed in the dead key image (obs_alias_mt: bit 0 = bytes, bit 1 = floats); the
-    // rest goes to obs_extra_bytes of additional shared memory per env.
-    int32_t obs_alias_mt, obs_extra_bytes, obs_bytes_size, obs_floats_size;
+    // The observation pass runs after the record has been written back.  Its staging buffers live, where they fit, on top
+    // of DEAD parts of the record's shared-memory image: the MT19937 key (dead from the start of the pass: obs_alias_mt
+    // != 0 makes the kernel write the key back as its own first bulk group) and, once the scalars are staged, the price
+    // history / order slots (kernel waits for the whole write-back to have been read first).  What does not fit goes to
+    // obs_extra_bytes of additional shared memory per env.  ob[]: byte offsets from the env's shared-memory region
+    // (device); ob_emu[]: offsets inside a separate scratch allocation of obs_scratch_bytes (host emulation, where the
+    // record is live global memory and nothing may alias it).
+    int32_t obs_alias_mt, obs_extra_bytes;
+    int32_t ob[OB_COUNT], ob_emu[OB_COUNT];
+    int32_t ob_chunk;       // agents whose windows are staged / streamed together
+    int32_t wc_stride;      // bytes per agent of the window-cell staging (window cells rounded up to 8)
+    int32_t pl_stride_a, pl_stride_p;   // bytes per plane-local bitmap: one agent window / the whole map
+    // mw: warps cooperating on one env in the step / observe kernels (1: one warp per env, several envs per CTA;
+    // 4: one CTA per env for large records - warp 0 runs the dynamics, all four stream the observations)
+    int32_t mw;
     // step-kernel scratch (per env, shared memory) and observe-kernel scratch
     int32_t step_scratch_bytes, obs_scratch_bytes;
     int32_t n_envs;
     int32_t sh_curr_rates, sh_last_incomes, sh_full, sh_count;  // offsets / size of the shared float staging array
     int32_t tab_p, tab_pa, tab_m, tab_n;               // offsets (u16 words) into the program table, total words (even)
+    int32_t tab_hoff, tab_seg, tab_lut;                // more tables in the same array: histogram offsets [4P], mask segments, nibble -> float4 table (16-byte aligned)
+    int32_t seg_lo[10];                                // mask segments of action subspace si: [seg_lo[si], seg_lo[si + 1]) (single-action agents: si = 0 covers everything)
     uint32_t HW_magic, ww_magic, Fa_magic, Fpa_magic, Na_magic;  // floor(2^32 / n) + 1: run index -> (row, column)
     uint32_t win_magic; int32_t win_dr32, win_dc32;  // window walk: lane / win, and the (row, col) step of 32 cells
     // single-action planner (multi_action_mode_planner=False): act_p is one index into [NO-OP] ++ B x R rates
@@ -148,12 +164,13 @@ struct DevBufs {
     const uint16_t *tab;
     // optional per-step event log of the first event_envs replicas (dense logs): int32 [event_envs][event_cap + 1][8]
     int32_t *events; int32_t event_envs, event_cap;
-    // tuning variant -DAIE_FUSED_POLICY=1 only: non-zero = the step kernel's observation pass also draws the next step's
-    // random actions (bench policy) from the mask limits it has just staged, instead of a separate sampler launch
+    // non-zero (aie_set_fused_policy): the observation pass also draws the NEXT step's uniformly random unmasked actions
+    // into the action buffers, from the mask limits it has just staged - instead of a separate sampler launch per step
     uint64_t policy_seed;
 };
 // compact program table: [agent flat (Fa) | planner flat (Fp) | p<i> flat (Fpa) | agent mask (Na)], offsets in DevCfg
-constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK;
+// then: histogram offsets u16 [4P <= 128], mask segments u16 [<= 64], nibble -> float4 table (64 floats = 128 u16)
+constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK + 128 + 64 + 128 + 16;
 struct Tables { uint16_t w[TAB_WORDS]; };
 
 }  // namespace aie

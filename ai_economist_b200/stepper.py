@@ -150,6 +150,11 @@ class BatchStepper:
         """Device-side random policy: one uniformly random unmasked action per agent/subspace."""
         self._check(self.lib.aie_sample_random_actions(self._h, C.c_uint64(int(seed)), self._stream()))
 
+    def set_fused_policy(self, seed):
+        """seed != 0: every following step() also draws the NEXT step's uniformly random unmasked actions into the action
+        buffers inside the observation pass (no sampler launch per step); 0 turns it off (aie_set_fused_policy)."""
+        self._check(self.lib.aie_set_fused_policy(self._h, C.c_uint64(int(seed)), self._stream()))
+
     def step_host(self, actions_agent, actions_planner, out_ptrs, compact=False, n_threads=0):
         """End-to-end step with HOST buffers (aie_step_host).  out_ptrs: dict name -> host pointer / None.
         compact=True: same bytes in the host tensors, bit- / byte-packed over PCIe (aie_step_host_compact)."""

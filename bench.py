@@ -68,7 +68,7 @@ def workload_config(key, E):
     """The `config` object of the JSON line - identical for the GPU arm and the reference (CPU) arm."""
     w = WORKLOADS[key]
     return {"workload": w["desc"], "envs_per_gpu": E, "n_agents": w["agents"], "world": w["world"],
-            "actions": "uniformly random unmasked actions, drawn inside the timed region", "auto_reset": True,
+            "actions": "uniformly random unmasked actions, drawn on the device inside the timed region", "auto_reset": True,
             "episode_phase": "staggered: replica e starts at t = e*T/E, one untimed episode of steps before timing",
             "l2": w["l2"]}
 
@@ -374,11 +374,13 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     # stagger the episode phase: replica e starts its first episode at t = e*T/E, then one episode of untimed steps
     st.state_view("t").copy_((torch.arange(E, device=dev, dtype=torch.int64) * T // E).to(torch.int32))
 
-    def one_step(i):
-        st.sample_random_actions(seed=1234 + rank)
-        st.step()  # fused dynamics + observations
+    # random policy fused into the step: the observation pass draws the next step's unmasked actions (aie_set_fused_policy)
+    st.set_fused_policy(1234 + rank)
 
-    for i in range(T):
+    def one_step(i):
+        st.step()  # ONE launch: dynamics + observations/masks + next actions
+
+    for i in range(T if args.preroll is None else args.preroll):
         one_step(i)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
@@ -397,22 +399,23 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
 
     # ---- per-kernel durations (separate pass, CUDA events between the kernels, same stream) ----
     n_prof = 50
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_prof)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n_prof)]
     for i in range(n_prof):
-        evs[i][0].record(); st.sample_random_actions(seed=99)
-        evs[i][1].record(); st.step()
-        evs[i][2].record()
+        evs[i][0].record(); st.step()
+        evs[i][1].record()
     torch.cuda.synchronize()
-    k_ms = [float(np.mean([evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(n_prof)])) for j in range(2)]
-    # the two halves of the fused step kernel, launched separately (informational)
-    ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(10)]
+    k_ms = [None, float(np.mean([evs[i][0].elapsed_time(evs[i][1]) for i in range(n_prof)]))]
+    # informational: the stand-alone sampler kernel (not launched in the timed loop) and the two halves of the fused step
+    # kernel launched separately
+    ev2 = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(10)]
     for i in range(10):
-        st.sample_random_actions(seed=98)
-        ev2[i][0].record(); st.step_dynamics()
-        ev2[i][1].record(); st.observe()
-        ev2[i][2].record()
+        ev2[i][0].record(); st.sample_random_actions(seed=98)
+        ev2[i][1].record(); st.step_dynamics()
+        ev2[i][2].record(); st.observe()
+        ev2[i][3].record()
     torch.cuda.synchronize()
-    half_ms = [float(np.mean([ev2[i][j].elapsed_time(ev2[i][j + 1]) for i in range(10)])) for j in range(2)]
+    k_ms[0] = float(np.mean([ev2[i][0].elapsed_time(ev2[i][1]) for i in range(10)]))
+    half_ms = [float(np.mean([ev2[i][j + 1].elapsed_time(ev2[i][j + 2]) for i in range(10)])) for j in range(2)]
     peak, peak_src = peaks()
     ww = d.window * d.window
     obs_bytes = (A * ((d.n_map_channels + 1) * ww * 4 + 2 * ww * 2 + d.flat_agent * 4 + d.mask_agent * 4)
@@ -426,12 +429,14 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
         "aie_step_kernel": {"ms": k_ms[1], "alg_bytes_per_launch": E * (step_bytes + obs_bytes),
                             "what": "fused: TMA record in -> dynamics -> rewards -> observations/masks out -> record out",
                             "unfused_ms": {"dynamics_only": half_ms[0], "observe_only": half_ms[1]}},
-        "aie_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (A * d.mask_agent * 4 + A * d.n_act_agent * 4)},
+        "aie_sample_kernel": {"ms": k_ms[0], "alg_bytes_per_launch": E * (A * d.mask_agent * 4 + A * d.n_act_agent * 4),
+                              "what": "stand-alone random policy (aie_sample_random_actions); NOT launched in the timed loop, "
+                                      "where the step kernel draws the actions itself"},
     }
     for k in kernels.values():
         k["achieved_gbs"] = k["alg_bytes_per_launch"] / (k["ms"] * 1e-3) / 1e9
         k["frac"] = k["achieved_gbs"] / peak
-    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    dom = "aie_step_kernel"
     traffic, traffic_src = committed_traffic(key, dom)
     survey_bytes = step_bytes - 2 * d.state_bytes + 2 * lean_state + obs_bytes
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -460,6 +465,7 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     h2d = act_a.numel() * 4 + (act_p.numel() * 4 if d.n_act_planner else 0)
     seg_a, seg_p = wl.mask_segments(env.spec, "a"), wl.mask_segments(env.spec, "p")
     rng = np.random.RandomState(rank)
+    st.set_fused_policy(0)   # the e2e leg takes its actions from the host
     out_host["mask_agent"].copy_(st.buf["mask_agent"])
     out_host["mask_planner"].copy_(st.buf["mask_planner"])
     e2e_s, n_e2e = 0.0, max(3, e2e_steps)
@@ -645,6 +651,7 @@ def main():
                     help="transfer format of the e2e leg: plain D2H copies, or the compacted transfer (aie_step_host_compact)")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads expanding the compacted transfer (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preroll", type=int, default=None, help="untimed steps after staggering the episode phases (default: one episode)")
     ap.add_argument("--no-extra-workloads", action="store_true",
                     help="headline workload only (skip the c3/c4/c5 entries of `workloads`)")
     args = ap.parse_args()

@@ -305,6 +305,14 @@ int aie_observe(aie_env *env, void *stream);
  * counter-based hash of (seed, call index, env, agent, subspace); it is not the env's numpy stream. */
 int aie_sample_random_actions(aie_env *env, uint64_t seed, void *stream);
 
+/* The same random policy fused into the step: with a non-zero seed every following aie_step / aie_observe also writes
+ * the NEXT step's uniformly random unmasked actions into the bound action buffers, drawn by the observation pass from
+ * the mask limits it has just computed (no mask read-back, no sampler launch per step).  The call itself samples once
+ * from the current masks so that the very next aie_step has actions.  seed == 0 turns it off.  Rollout loops with a
+ * random policy (the benchmark's "random actions", tutorials/economic_simulation_basic.ipynb cell 18) call this once
+ * and then only aie_step. */
+int aie_set_fused_policy(aie_env *env, uint64_t seed, void *stream);
+
 /* End-to-end variant with HOST buffers: copies the actions host->device, steps, copies every non-NULL
  * output device->host, and synchronises the stream.  Buffers should be pinned for full PCIe rate. */
 int aie_step_host(aie_env *env, const int32_t *actions_agent_host, const int32_t *actions_planner_host,

@@ -22,7 +22,7 @@
 struct aie_env;
 struct aie_covid_env;
 namespace aie { namespace be {
-struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; std::vector<uint8_t> compact_dev, compact_host; };
+struct State { std::vector<uint8_t> scratch; std::vector<uint16_t> tab; std::vector<uint8_t> compact_dev, compact_host; int nt = 1; };
 struct DevScope { explicit DevScope(int) {} bool ok() const { return true; } };
 int check_device(int device);
 int init(aie_env *);
@@ -54,6 +54,10 @@ namespace aie { namespace be {
 int check_device(int) { return AIE_OK; }
 int init(aie_env *env) {
     env->be.scratch.assign((size_t)env->cfg.step_scratch_bytes + env->cfg.obs_scratch_bytes + 64, 0);
+    // threads per env in the observation pass: 1 for the logic tests; AIE_EMU_NT=32 / 128 walks the phases with the
+    // device's thread counts, one thread index after the other (thread-layout check of the writers)
+    env->be.nt = 1;
+    if (const char *v = getenv("AIE_EMU_NT")) { const int n = atoi(v); if (n >= 1 && n <= 1024) env->be.nt = n; }
     env->bufs.tab = env->tables.w;
     return AIE_OK;
 }
@@ -124,8 +128,9 @@ int launch_observe(aie_env *env, int lo, int n, void *) {
     for (int env_i = lo; env_i < lo + n; env_i++) {
         size_t e = env_i;
         ObsOut o; o.b = &b; o.c = &c; o.env = e;
-        if (c.ext) observe_env<true>(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
-        else observe_env<false>(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, nullptr, env->be.scratch.data() + c.step_scratch_bytes, o, b.tab, 0);
+        uint8_t *stage = env->be.scratch.data() + ((c.step_scratch_bytes + 15) & ~15);
+        if (c.ext) observe_env<true>(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, stage, c.ob_emu, o, b.tab, SeqExec{env->be.nt});
+        else observe_env<false>(c, b.state + e * c.rec_bytes, b.state + e * c.rec_bytes, stage, c.ob_emu, o, b.tab, SeqExec{env->be.nt});
     }
     env->launches++;
     return AIE_OK;

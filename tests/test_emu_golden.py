@@ -16,6 +16,23 @@ def test_emulated_device_code_matches_reference_golden_trace(path):
     assert gu.replay(path, make) >= 50
 
 
+@pytest.mark.parametrize("nt", [32, 128])
+@pytest.mark.parametrize("path", [p for p in gu.golden_files() if any(k in p for k in
+                                  ("c1_tutorial_seed1", "c3_paper_tax", "c3_short_period", "c5_small", "full_obs", "tax_us_federal"))],
+                         ids=lambda p: p.split("/")[-1])
+def test_observation_pass_thread_layouts_match_golden_trace(path, nt, monkeypatch):
+    """The observation pass is written for NT cooperating threads (32: one warp per env; 128: one CTA per env for large
+    records).  The emulation walks every phase for thread index 0..NT-1 in turn (phases only read what earlier phases
+    wrote), which checks each thread's slice of the staging / transpose / concat / stream loops - unaligned heads and
+    tails, plane boundaries, chunk boundaries - against the reference's observations."""
+    monkeypatch.setenv("AIE_EMU_NT", str(nt))
+
+    def make(spec, init):
+        return GoldenStepperAdapter(EmuStepper(spec, 1), init)
+
+    assert gu.replay(path, make) >= 50
+
+
 @pytest.mark.parametrize("cfg,E,steps", [
     ("tax_single_planner", 4, 60), ("uniform_halfwidth", 4, 60), ("quadrant", 3, 40), ("multi_zone", 3, 40),
     ("split_layout", 2, 40),

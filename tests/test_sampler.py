@@ -1,5 +1,6 @@
-"""The device random policy (aie_sample_random_actions: bench / smoke-test utility): every drawn action is unmasked,
-every unmasked action of a segment can be drawn, and a different seed gives different draws."""
+"""The device random policy (aie_sample_random_actions, and the same policy fused into the step's observation pass by
+aie_set_fused_policy): every drawn action is unmasked, every unmasked action of a segment can be drawn, and the draws
+change from step to step."""
 import numpy as np
 import pytest
 
@@ -8,14 +9,17 @@ from oracle.configs import CONFIGS
 from tests import batch_utils as bu
 
 
-def _check(env, rounds=6):
+def _check(env, rounds=6, fused=False, min_seen=10):
     st = env.stepper
     spec = env.spec
     seg_a, seg_p = bu.segments(spec, "a"), bu.segments(spec, "p")
     seen = set()
     prev = None
+    if fused:
+        st.set_fused_policy(77)   # samples once now; afterwards every step refreshes the action buffers itself
     for it in range(rounds):
-        st.sample_random_actions(seed=100 + it)
+        if not fused:
+            st.sample_random_actions(seed=100 + it)
         aa = st.to_numpy(st.buf["actions_agent"]).copy()
         ma = st.to_numpy(st.buf["mask_agent"])
         off = 0
@@ -37,7 +41,7 @@ def _check(env, rounds=6):
         assert prev is None or not np.array_equal(prev, aa)
         prev = aa
         env.step(env.action_buffers)
-    assert len(seen) > 10
+    assert len(seen) > min_seen
 
 
 @pytest.mark.parametrize("cfg", ["c1_tutorial", "tax_us_federal", "c3_reset", "tax_single_planner"])
@@ -49,6 +53,20 @@ def test_emulated_sampler_draws_only_unmasked_actions(cfg):
     env.seed(list(range(5)))
     env.reset()
     _check(env)
+    _check(env, rounds=12, fused=True, min_seen=3)   # same env, a few steps later: less coin, fewer open price levels
+
+
+@pytest.mark.parametrize("nt", [1, 32, 128])
+@pytest.mark.parametrize("cfg", ["c1_tutorial", "tax_us_federal", "c3_reset", "tax_single_planner"])
+def test_emulated_fused_policy_draws_only_unmasked_actions(cfg, nt, monkeypatch):
+    from tests.emu.emu_stepper import emu_factory
+    monkeypatch.setenv("AIE_EMU_NT", str(nt))
+    kw = dict(CONFIGS[cfg])
+    name = kw.pop("scenario_name")
+    env = foundation.make_env_instance(name, n_envs=5, stepper_factory=emu_factory, **kw)
+    env.seed(list(range(5)))
+    env.reset()
+    _check(env, rounds=12, fused=True)
 
 
 @pytest.mark.gpu
@@ -59,3 +77,4 @@ def test_cuda_sampler_draws_only_unmasked_actions(cfg):
     env = foundation.make_env_instance(name, n_envs=257, device="cuda:0", seeds=list(range(257)), **kw)
     env.reset()
     _check(env)
+    _check(env, rounds=12, fused=True, min_seen=3)   # same env, a few steps later: less coin, fewer open price levels

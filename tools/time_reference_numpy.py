@@ -36,7 +36,7 @@ def worker(args):
     rng = np.random.RandomState(seed)
     total, n = 0.0, 0
     for t in range(steps + 5):
-        acts = rh.sample_actions(env, obs, rng)     # sampling excluded from the timed region
+        acts = rh.sample_actions(env, obs, rng)[0]  # sampling excluded from the timed region
         t0 = time.perf_counter()
         obs, rew, done, info = env.step(acts)
         dt = time.perf_counter() - t0
