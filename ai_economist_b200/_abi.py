@@ -159,6 +159,8 @@ def load_library(path=None):
     L.aie_step_host_compact.restype = C.c_int
     L.aie_compact_bytes_per_env.argtypes = [P]
     L.aie_compact_bytes_per_env.restype = C.c_int32
+    L.aie_get_host_timing.argtypes = [P, C.POINTER(C.c_double), C.c_int32]
+    L.aie_get_host_timing.restype = C.c_int
     L.aie_read_state.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
     L.aie_read_episode_final.argtypes = [P, C.c_int32, C.POINTER(AieStateDump)]
     L.aie_read_episode_final.restype = C.c_int
@@ -186,7 +188,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = ["aie_create", "aie_destroy", "aie_get_dims", "aie_get_field", "aie_get_flat_layout", "aie_bind_buffers",
                     "aie_load_state", "aie_step", "aie_step_dynamics", "aie_observe", "aie_sample_random_actions", "aie_set_fused_policy",
-                    "aie_step_host", "aie_step_host_compact", "aie_compact_bytes_per_env", "aie_read_state", "aie_read_episode_final", "aie_launch_count", "aie_last_error", "aie_abi_version",
+                    "aie_step_host", "aie_step_host_compact", "aie_compact_bytes_per_env", "aie_get_host_timing", "aie_read_state", "aie_read_episode_final", "aie_launch_count", "aie_last_error", "aie_abi_version",
                     "aie_covid_create", "aie_covid_destroy", "aie_covid_bind_buffers", "aie_covid_reset", "aie_covid_step",
                     "aie_covid_sample_random_actions", "aie_covid_launch_count"]
 

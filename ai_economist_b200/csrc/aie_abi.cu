@@ -24,6 +24,7 @@ struct aie_covid_env;
 
 namespace aie {
 namespace be {
+constexpr int AIE_MAX_SLICES_BE = 16;   // = AIE_MAX_SLICES (aie_compact_host.h)
 struct State {
     int step_wpb;        // warps (envs) per CTA of the step kernel
     int step_minb;       // register-allocation variant of the step kernel (3, 4 or 5 CTAs per SM)
@@ -33,7 +34,7 @@ struct State {
     uint16_t *tab_dev;   // observation programs (device copy)
     uint8_t *compact_dev = nullptr, *compact_host = nullptr;   // aie_step_host_compact: device + pinned host staging
     size_t compact_bytes = 0;
-    cudaEvent_t slice_ev[8] = {};   // one per transfer slice of the compacted D2H copy
+    cudaEvent_t slice_ev[AIE_MAX_SLICES_BE] = {};   // one per transfer slice of the compacted D2H copy
 };
 // Makes `device` current for the lifetime of the object and restores the caller's device afterwards, so a handle
 // created for cuda:1 works while cuda:0 is current (streams passed in must belong to the handle's device).
@@ -445,7 +446,7 @@ void destroy(aie_env *env) {
     for (cudaEvent_t &ev : env->be.slice_ev) if (ev) cudaEventDestroy(ev);
 }
 int download_slice(aie_env *env, int k, void *host, const void *dev, size_t n, void *stream) {
-    if (k < 0 || k >= 8) return fail(AIE_EINVAL, "transfer slice index");
+    if (k < 0 || k >= AIE_MAX_SLICES_BE) return fail(AIE_EINVAL, "transfer slice index");
     if (!env->be.slice_ev[k]) AIE_CUDA(cudaEventCreateWithFlags(&env->be.slice_ev[k], cudaEventDisableTiming), "cudaEventCreate");
     AIE_CUDA(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H slice");
     AIE_CUDA(cudaEventRecord(env->be.slice_ev[k], (cudaStream_t)stream), "cudaEventRecord");

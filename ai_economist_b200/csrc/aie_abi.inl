@@ -16,6 +16,7 @@
 //   int wait_slice(aie_env*, int k);                                                           (any thread)
 //   struct DevScope { DevScope(int device); ~DevScope(); bool ok() const; };   makes `device` current for the scope of one
 //       entry point and restores the caller's device on exit (a handle can be used while another device is current)
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,7 @@ struct aie_env {
     aie::be::State be;
     std::vector<aie_flat_field> flat_layout[3];
     aie::HostPool *pool = nullptr;   // aie_step_host_compact: created on first use
+    double host_timing[AIE_HOST_TIMING_WORDS] = {};   // last aie_step_host_compact call (aie_get_host_timing)
 };
 
 static int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
@@ -223,6 +225,7 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
                           void *stream) {
     if (!env || !act_a || !o) return fail(AIE_EINVAL, "null argument");
     if (!env->bound || !env->loaded) return fail(AIE_ESTATE, "aie_step_host_compact: bind buffers and load state first");
+    const std::chrono::steady_clock::time_point t_call = std::chrono::steady_clock::now();
     AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     const size_t E = env->n_envs;
@@ -241,10 +244,13 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     if (rc != AIE_OK) return rc;
     rc = aie::be::launch_pack(env, L, dev, stream);
     if (rc != AIE_OK) return rc;
-    // The compact records go down in up to 8 slices, each followed by an event; a work item first waits for the slice
-    // holding its envs, so the expansion of the early slices overlaps the transfer of the later ones.
-    const int chunk = 64, n_items = (int)((E + chunk - 1) / chunk);   // envs per work item
-    int n_slices = n_items < 8 ? n_items : 8;
+    // The compact records go down in up to AIE_MAX_SLICES slices, each followed by an event; a work item first waits for
+    // the slice holding its envs, so the expansion of the early slices overlaps the transfer of the later ones.
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t0 = clk::now();
+    auto ms_since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(t - t0).count(); };
+    const int chunk = 32, n_items = (int)((E + chunk - 1) / chunk);   // envs per work item
+    int n_slices = n_items < aie::AIE_MAX_SLICES ? n_items : aie::AIE_MAX_SLICES;
     const int items_per_slice = (n_items + n_slices - 1) / n_slices;
     n_slices = (n_items + items_per_slice - 1) / items_per_slice;
     for (int k = 0; k < n_slices; k++) {
@@ -252,21 +258,37 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
         rc = aie::be::download_slice(env, k, host + lo * (size_t)L.bytes, dev + lo * (size_t)L.bytes, (hi - lo) * (size_t)L.bytes, stream);
         if (rc != AIE_OK) return rc;
     }
+    const double t_enqueued = ms_since(clk::now());
     int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     if (want < 1) want = 1;
-    if (want > 64) want = 64;
+    if (want > aie::AIE_MAX_HOST_THREADS) want = aie::AIE_MAX_HOST_THREADS;
     if (!env->pool || env->pool->size() != want - 1) { delete env->pool; env->pool = new aie::HostPool(want - 1); }
     const aie_host_out out = *o;
     std::atomic<int> failed{0};
+    std::atomic<int64_t> first_slice_us{-1}, last_slice_us{-1};
     env->pool->run(n_items, [&](int item) {
-        if (aie::be::wait_slice(env, item / items_per_slice) != AIE_OK) { failed.store(1); return; }
+        const int k = item / items_per_slice;
+        if (aie::be::wait_slice(env, k) != AIE_OK) { failed.store(1); return; }
+        if (item % items_per_slice == 0 && (k == 0 || k == n_slices - 1))
+            (k == 0 ? first_slice_us : last_slice_us).store((int64_t)(1e3 * ms_since(clk::now())));
         const size_t hi = (size_t)(item + 1) * chunk < E ? (size_t)(item + 1) * chunk : E;
         for (size_t e = (size_t)item * chunk; e < hi; e++) aie::expand_env(L, host + e * (size_t)L.bytes, e, out);
     });
+    const double t_expanded = ms_since(clk::now());
+    double *ht = env->host_timing;
+    ht[0] = t_enqueued; ht[1] = 1e-3 * first_slice_us.load(); ht[2] = 1e-3 * (n_slices > 1 ? last_slice_us.load() : first_slice_us.load());
+    ht[3] = t_expanded; ht[4] = (double)n_slices; ht[5] = (double)want; ht[6] = (double)(E * (size_t)L.bytes);
+    ht[7] = std::chrono::duration<double, std::milli>(t0 - t_call).count();
     if (failed.load()) return fail(AIE_ECUDA, "aie_step_host_compact: waiting for a transfer slice failed");
     rc = aie::be::sync(env, stream);
     if (rc != AIE_OK) return rc;
     return AIE_OK;
+}
+
+int aie_get_host_timing(const aie_env *env, double *out, int32_t cap) {
+    if (!env || (cap > 0 && !out)) return fail(AIE_EINVAL, "null argument");
+    for (int i = 0; i < cap && i < AIE_HOST_TIMING_WORDS; i++) out[i] = env->host_timing[i];
+    return AIE_HOST_TIMING_WORDS;
 }
 
 int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out) {

@@ -13,6 +13,9 @@
 
 namespace aie {
 
+constexpr int AIE_MAX_SLICES = 16;         // transfer slices of the compacted D2H copy (one event each)
+constexpr int AIE_MAX_HOST_THREADS = 128;  // expansion threads
+
 // Persistent workers: run(n, fn) calls fn(i) for i in [0, n) on the pool plus the calling thread and returns when all
 // are done.  One job at a time (calls on a handle are serialised by contract).
 class HostPool {
@@ -55,34 +58,10 @@ private:
     bool stop_ = false;
 };
 
-// bits -> 0.0f / 1.0f.  The expansion is a pure write stream (296 MB per step for c2 at 8 192 envs), so on x86 the
-// 16-byte groups go out with non-temporal stores (no read-for-ownership of the destination lines); a 16-entry table maps
-// four bits to four floats.  `src` must be readable up to the 8 bytes holding the last bit (true inside a compact record).
-#if defined(__SSE2__)
-#include <emmintrin.h>
-struct NibbleTable {
-    __m128 v[16];
-    NibbleTable() { for (int k = 0; k < 16; k++) v[k] = _mm_set_ps((float)((k >> 3) & 1), (float)((k >> 2) & 1), (float)((k >> 1) & 1), (float)(k & 1)); }
-};
-inline void expand_bits(const uint32_t *src, int n, float *dst) {
-    static const NibbleTable T;
-    auto bit = [&](int i) { return (float)((src[i >> 5] >> (i & 31)) & 1u); };
-    int i = 0;
-    while (i < n && ((uintptr_t)(dst + i) & 15)) { dst[i] = bit(i); i++; }
-    for (; i + 4 <= n; i += 4) {
-        uint64_t w;
-        memcpy(&w, (const uint8_t *)src + 4 * (i >> 5), 8);     // the word holding bit i and the next one
-        _mm_stream_ps(dst + i, T.v[(w >> (i & 31)) & 15u]);
-    }
-    for (; i < n; i++) dst[i] = bit(i);
-}
-inline void expand_fence() { _mm_sfence(); }
-#else
-inline void expand_bits(const uint32_t *src, int n, float *dst) {
-    for (int i = 0; i < n; i++) dst[i] = (float)((src[i >> 5] >> (i & 31)) & 1u);
-}
-inline void expand_fence() {}
-#endif
+// bits -> 0.0f / 1.0f with non-temporal stores, AVX-512 or SSE2 picked at run time (aie_expand_host.cpp, host compiler)
+void expand_bits(const uint32_t *src, int n, float *dst);
+void expand_fence();
+const char *expand_isa();
 
 // one env: compact record -> the caller's (host) tensors; NULL outputs are skipped
 inline void expand_env(const CompactLayout &L, const uint8_t *rec, size_t env, const aie_host_out &o) {

@@ -167,6 +167,13 @@ class BatchStepper:
         else:
             self._check(self.lib.aie_step_host(self._h, actions_agent, actions_planner, C.byref(o), self._stream()))
 
+    def host_timing(self):
+        """Host-clock breakdown (ms) of the last compacted step_host call (aie_get_host_timing)."""
+        out = (C.c_double * 8)()
+        self.lib.aie_get_host_timing(self._h, out, 8)
+        k = ["enqueued", "first_slice", "last_slice", "expanded", "slices", "threads", "d2h_bytes", "before_transfer"]
+        return dict(zip(k, list(out)))
+
     def compact_bytes_per_env(self):
         return int(self.lib.aie_compact_bytes_per_env(self._h))
 

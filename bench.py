@@ -604,7 +604,7 @@ def measure_covid(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20):
     }
     if with_cpu:
         res["cpu_baseline"] = cpu_baseline_for(key)
-    ref = reference_cuda_note()
+    ref = reference_cuda_leg(ctx, env.params, E, min(K, 540), ms_total / K, k_ms[1])
     if ref:
         res["vs_reference_cuda"] = ref
     del env, st, host
@@ -612,16 +612,39 @@ def measure_covid(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20):
     return res
 
 
-def reference_cuda_note():
-    """Same-box timing of the reference's own COVID CUDA kernels (oracle/_ref, built from /root/reference by
-    oracle/build_ref_covid.py), if tools/time_ref_covid.py left one for this box."""
-    p = os.path.join(ROOT, "gpurun_out", "ref_covid_cuda.json")
-    if not os.path.exists(p):
-        p = os.path.join(ROOT, "profiles", "ref_covid_cuda.json")
+def reference_cuda_leg(ctx, params, E, K, ours_ms_per_step, ours_step_kernel_ms):
+    """Baseline leg for config 4: the reference's OWN CUDA kernels (covid19_env_step.cu / covid19_components_step.cu,
+    compiled for sm_100a from /root/reference into oracle/_ref/ by oracle/build_ref_covid.py) on the same GPU, same
+    number of replicas, launched the way the reference's wrapper launches them (grid = envs, block = 52, five launches
+    per step).  Like cpu_baseline this is a reported baseline, never the thing shipped; None when the library was not
+    built (no /root/reference at build time).  Its kernels' cost does not depend on the actions (they rewrite the whole
+    convolution signal every step), so a fixed action tensor is stepped and its reset copy is left out (in its favour)."""
     try:
-        return json.load(open(p))
+        from oracle import build_ref_covid
+        if not build_ref_covid.available():
+            return None
+        from oracle.ref_covid_cuda import RefCovidCuda
     except Exception:
         return None
+    torch = ctx.torch
+    try:
+        ref = RefCovidCuda(params, E, device=str(ctx.dev))
+        g = torch.Generator(device=ctx.dev); g.manual_seed(5)
+        ref.t["actions_a"].copy_(torch.randint(0, 11, ref.t["actions_a"].shape, device=ctx.dev, generator=g, dtype=torch.int32))
+        for i in range(5):
+            ref.step()
+        ms = ctx.time_steps(lambda i: ref.step(), K)
+        out = {"ms_per_step": ms / K, "value": ctx.world * E * 51 * K / (ms * 1e-3), "unit": UNIT, "steps": K, "envs_per_gpu": E,
+               "launches_per_step": ref.launches_per_step(), "speedup_whole_step": (ms / K) / ours_ms_per_step,
+               "speedup_step_kernel_only": (ms / K) / ours_step_kernel_ms,
+               "what": "reference CUDA kernels (sm_100a build of the unmodified sources, nvcc -O3) on this GPU: "
+                       "CudaControlUSStateOpenCloseStatusStep, CudaFederalGovernmentSubsidyStep, CudaVaccinationCampaignStep, "
+                       "CudaCovidAndEconomySimulationStep, CudaComputeReward; speedup = its ms/step over ours (sampler + step)"}
+        del ref
+        torch.cuda.empty_cache()
+        return out
+    except Exception as ex:
+        return {"error": "%s: %s" % (type(ex).__name__, ex)}
 
 
 def compact(res):

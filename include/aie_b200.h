@@ -328,6 +328,12 @@ int aie_step_host_compact(aie_env *env, const int32_t *actions_agent, const int3
                           const aie_host_out *out, int32_t n_threads, void *stream);
 /* bytes one env contributes to the compacted transfer (0 on error) */
 int32_t aie_compact_bytes_per_env(const aie_env *env);
+/* Host-clock breakdown of the last aie_step_host_compact call, milliseconds from the start of its transfer phase:
+ * [0] copies enqueued, [1] first transfer slice on the host, [2] last slice on the host, [3] expansion finished,
+ * [4] number of slices, [5] host threads used, [6] bytes moved device->host, [7] time before the transfer phase (action
+ * upload + launches enqueued).  Returns the number of words defined (diagnostics for tuning n_threads). */
+#define AIE_HOST_TIMING_WORDS 8
+int aie_get_host_timing(const aie_env *env, double *out, int32_t cap);
 
 /* Test/debug readback of env `e` (synchronous). */
 int aie_read_state(aie_env *env, int32_t e, const aie_state_dump *out);

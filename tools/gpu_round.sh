@@ -38,6 +38,11 @@ if [[ $PH == all || $PH == *ncu* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step -s 1030 -c 1 -f -o gpurun_out/prof_step_c2 \
       python bench.py $B > gpurun_out/ncu_step_c2.log 2>&1; echo "ncu step c2 rc=$?"
 fi
+if [[ $PH == *ncuo* ]]; then   # the stand-alone observation kernel (c2), launched in the bench's per-kernel section
+  B="--no-cpu-baseline --no-extra-workloads --e2e-steps 3 --steps 20 --warmup 5"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_observe -s 4 -c 1 -f -o gpurun_out/prof_observe_c2 \
+      python bench.py $B > gpurun_out/ncu_observe_c2.log 2>&1; echo "ncu observe c2 rc=$?"
+fi
 if [[ $PH == all || $PH == *ncx* ]]; then   # full captures of the other workloads' dominant kernels (dram bytes for `traffic`)
   B="--no-cpu-baseline --no-extra-workloads --e2e-steps 3 --steps 20 --warmup 5"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step -s 1030 -c 1 -f -o gpurun_out/prof_step_c3 \

@@ -26,3 +26,7 @@ for k, w in (d.get("workloads") or {}).items():
         print("  %s: value %.4e ms/step %.4f (sustained %.4f) frac %.3f e2e %.4e kernels %s" % (
             k, w["value"], w["ms_per_step"], w["sustained"]["ms_per_step"], w["roofline"]["frac"], w["e2e"]["value"],
             {kk: round(v * 1e3, 1) for kk, v in w["roofline"]["kernel_ms"].items()}))
+        if "vs_reference_cuda" in w:
+            v = w["vs_reference_cuda"]
+            print("      vs reference CUDA:", v if "error" in v else "ref %.4f ms/step (%d launches) -> x%.2f whole step, x%.2f step kernel" % (
+                v["ms_per_step"], v["launches_per_step"], v["speedup_whole_step"], v["speedup_step_kernel_only"]))
