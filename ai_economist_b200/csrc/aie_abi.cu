@@ -34,7 +34,8 @@ struct State {
     uint16_t *tab_dev;   // observation programs (device copy)
     uint8_t *compact_dev = nullptr, *compact_host = nullptr;   // aie_step_host_compact: device + pinned host staging
     size_t compact_bytes = 0;
-    cudaEvent_t slice_ev[AIE_MAX_SLICES_BE] = {};   // one per transfer slice of the compacted D2H copy
+    cudaEvent_t slice_ev[AIE_MAX_SLICES_BE] = {};
+    cudaEvent_t call_ev = nullptr;   // recorded when a host-buffer step starts enqueueing (timing reference of the slices)   // one per transfer slice of the compacted D2H copy
 };
 // Makes `device` current for the lifetime of the object and restores the caller's device afterwards, so a handle
 // created for cuda:1 works while cuda:0 is current (streams passed in must belong to the handle's device).
@@ -65,6 +66,8 @@ int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
 int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
 int download_slice(aie_env *, int k, void *host, const void *dev, size_t n, void *stream);
 int wait_slice(aie_env *, int k);
+double slice_device_ms(aie_env *, int k);
+int mark_call_start(aie_env *, void *stream);
 void *const_upload(const void *host, size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
@@ -444,15 +447,27 @@ void destroy(aie_env *env) {
     if (env->be.compact_dev) cudaFree(env->be.compact_dev);
     if (env->be.compact_host) cudaFreeHost(env->be.compact_host);
     for (cudaEvent_t &ev : env->be.slice_ev) if (ev) cudaEventDestroy(ev);
+    if (env->be.call_ev) cudaEventDestroy(env->be.call_ev);
 }
 int download_slice(aie_env *env, int k, void *host, const void *dev, size_t n, void *stream) {
     if (k < 0 || k >= AIE_MAX_SLICES_BE) return fail(AIE_EINVAL, "transfer slice index");
-    if (!env->be.slice_ev[k]) AIE_CUDA(cudaEventCreateWithFlags(&env->be.slice_ev[k], cudaEventDisableTiming), "cudaEventCreate");
+    if (!env->be.slice_ev[k]) AIE_CUDA(cudaEventCreate(&env->be.slice_ev[k]), "cudaEventCreate");
     AIE_CUDA(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H slice");
     AIE_CUDA(cudaEventRecord(env->be.slice_ev[k], (cudaStream_t)stream), "cudaEventRecord");
     return AIE_OK;
 }
 int wait_slice(aie_env *env, int k) { return cudaEventSynchronize(env->be.slice_ev[k]) == cudaSuccess ? AIE_OK : AIE_ECUDA; }
+int mark_call_start(aie_env *env, void *stream) {
+    if (!env->be.call_ev) AIE_CUDA(cudaEventCreate(&env->be.call_ev), "cudaEventCreate");
+    AIE_CUDA(cudaEventRecord(env->be.call_ev, (cudaStream_t)stream), "cudaEventRecord");
+    return AIE_OK;
+}
+double slice_device_ms(aie_env *env, int k) {
+    float ms = -1.0f;
+    if (!env->be.call_ev || k < 0 || k >= AIE_MAX_SLICES_BE || !env->be.slice_ev[k]) return -1.0;
+    if (cudaEventElapsedTime(&ms, env->be.call_ev, env->be.slice_ev[k]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return (double)ms;
+}
 int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
     if (env->be.compact_bytes < bytes) {
         if (env->be.compact_dev) cudaFree(env->be.compact_dev);

@@ -14,8 +14,11 @@
 //   int launch_pack(aie_env*, const aie::CompactLayout&, uint8_t *dev, void *stream);
 //   int download_slice(aie_env*, int k, void *host, const void *dev, size_t n, void *stream);   (async copy + event k)
 //   int wait_slice(aie_env*, int k);                                                           (any thread)
+//   double slice_device_ms(aie_env*, int k);   device-clock time of slice k's arrival since the call's first enqueue (-1: n/a)
 //   struct DevScope { DevScope(int device); ~DevScope(); bool ok() const; };   makes `device` current for the scope of one
 //       entry point and restores the caller's device on exit (a handle can be used while another device is current)
+#include <stdio.h>
+#include <stdlib.h>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -57,6 +60,15 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     int rc = aie::build_devcfg(*cfg, n_envs, env->cfg, env->tables, err, env->flat_layout);
     if (rc != AIE_OK) { delete env; return fail(rc, "aie_create: " + err); }
     env->ucfg = *cfg; env->n_envs = n_envs; env->device = device;
+    if (getenv("AIE_VERBOSE")) {   // record / staging layout (host-side facts; the backend adds its launch geometry)
+        const aie::DevCfg &c = env->cfg;
+        fprintf(stderr, "[aie] A %d map %dx%d: record %d B (resident %d, obs prefix %d, mt @%d, price_hist @%d), step scratch %d, obs extra %d "
+                        "(alias mt %d), chunk %d agents, mw %d, Fa %d Fp %d Fpa %d Na %d Np %d; ob:", c.A, c.H, c.W, c.rec_bytes, c.resident_bytes,
+                c.obs_prefix_bytes, c.off_mt, c.off_price_hist, c.step_scratch_bytes, c.obs_extra_bytes, c.obs_alias_mt, c.ob_chunk, c.mw,
+                c.Fa, c.Fp, c.Fpa, c.Na, c.Np);
+        for (int i = 0; i < aie::OB_COUNT; i++) fprintf(stderr, " %d", c.ob[i]);
+        fprintf(stderr, "\n");
+    }
     memset(&env->bufs, 0, sizeof(env->bufs));
     env->bound = env->loaded = false; env->launches = 0; env->sample_calls = 0;
     aie::be::DevScope dev_scope_(device);   // init() validates the ordinal itself and reports the precise error
@@ -229,7 +241,9 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     AIE_DEVICE_SCOPE(env->device);
     const aie::DevCfg &c = env->cfg;
     const size_t E = env->n_envs;
-    int rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * c.A * c.n_act_a * 4, stream);
+    int rc = aie::be::mark_call_start(env, stream);
+    if (rc != AIE_OK) return rc;
+    rc = aie::be::upload(env, (void *)env->bufs.act_a, act_a, E * c.A * c.n_act_a * 4, stream);
     if (rc != AIE_OK) return rc;
     if (c.n_act_p > 0) {
         if (!act_p) return fail(AIE_EINVAL, "aie_step_host_compact: planner actions required");
@@ -265,20 +279,34 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     if (!env->pool || env->pool->size() != want - 1) { delete env->pool; env->pool = new aie::HostPool(want - 1); }
     const aie_host_out out = *o;
     std::atomic<int> failed{0};
-    std::atomic<int64_t> first_slice_us{-1}, last_slice_us{-1};
-    env->pool->run(n_items, [&](int item) {
+    std::atomic<int64_t> first_slice_us{-1}, last_slice_us{-1}, wait_us{0}, busy_us{0};
+    auto job = [&](int item) {
         const int k = item / items_per_slice;
+        const clk::time_point w0 = clk::now();
         if (aie::be::wait_slice(env, k) != AIE_OK) { failed.store(1); return; }
+        const clk::time_point w1 = clk::now();
         if (item % items_per_slice == 0 && (k == 0 || k == n_slices - 1))
-            (k == 0 ? first_slice_us : last_slice_us).store((int64_t)(1e3 * ms_since(clk::now())));
+            (k == 0 ? first_slice_us : last_slice_us).store((int64_t)(1e3 * ms_since(w1)));
         const size_t hi = (size_t)(item + 1) * chunk < E ? (size_t)(item + 1) * chunk : E;
         for (size_t e = (size_t)item * chunk; e < hi; e++) aie::expand_env(L, host + e * (size_t)L.bytes, e, out);
-    });
+        const clk::time_point w2 = clk::now();
+        wait_us.fetch_add(std::chrono::duration_cast<std::chrono::microseconds>(w1 - w0).count());
+        busy_us.fetch_add(std::chrono::duration_cast<std::chrono::microseconds>(w2 - w1).count());
+    };
+    env->pool->run(n_items, job);
     const double t_expanded = ms_since(clk::now());
     double *ht = env->host_timing;
     ht[0] = t_enqueued; ht[1] = 1e-3 * first_slice_us.load(); ht[2] = 1e-3 * (n_slices > 1 ? last_slice_us.load() : first_slice_us.load());
     ht[3] = t_expanded; ht[4] = (double)n_slices; ht[5] = (double)want; ht[6] = (double)(E * (size_t)L.bytes);
     ht[7] = std::chrono::duration<double, std::milli>(t0 - t_call).count();
+    ht[8] = 1e-3 * wait_us.load(); ht[9] = 1e-3 * busy_us.load();   // summed over the threads
+    ht[10] = aie::be::slice_device_ms(env, 0); ht[11] = aie::be::slice_device_ms(env, n_slices - 1);
+    if (const char *rep = getenv("AIE_E2E_REPEAT_EXPAND")) {   // tuning aid: the expansion alone, every slice already on the host
+        const int n = atoi(rep);
+        const clk::time_point r0 = clk::now();
+        for (int i = 0; i < n; i++) env->pool->run(n_items, job);
+        ht[12] = n > 0 ? std::chrono::duration<double, std::milli>(clk::now() - r0).count() / n : 0.0;
+    }
     if (failed.load()) return fail(AIE_ECUDA, "aie_step_host_compact: waiting for a transfer slice failed");
     rc = aie::be::sync(env, stream);
     if (rc != AIE_OK) return rc;

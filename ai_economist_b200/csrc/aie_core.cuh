@@ -211,6 +211,49 @@ AIE_DEV void mt_twist_phase(uint32_t *mt, int lane) {
 // new[0,227); new[454,623) <- new[227,396); new[623] <- new[396], new[0].
 // Not inlined: rng_next() is called from a dozen places and each inlined copy of the twist is ~700 instructions;
 // a single copy keeps the kernel inside the instruction cache.
+#if AIE_ON_DEVICE
+// Device version: the same recurrence in chunks of 128 words, four consecutive words per lane (one 16-byte load of the
+// old values, one 16-byte store).  Any split into chunks of at most 227 words keeps the dependencies of the in-place
+// twist: word k takes key[k + 397] (still old: it lies in a later chunk) for k < 227 and key[k - 227] (already new: it
+// lies in an earlier chunk) otherwise, and every chunk reads all its inputs before it stores.  Word 623 wraps around to
+// the new key[0] and is done last by one lane.
+__device__ __forceinline__ uint32_t mt_mix(uint32_t a, uint32_t b, uint32_t src) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return src ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+}
+template <int BASE>
+__device__ __forceinline__ void mt_twist_chunk(uint32_t *mt, int lane) {
+    const int k0 = BASE + 4 * lane;
+    const bool act = k0 < 623;
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    if (act) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(mt + k0);
+        const uint32_t xs[5] = {x.x, x.y, x.z, x.w, mt[k0 + 4 < 624 ? k0 + 4 : 623]};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j;
+            const int src = (BASE + 127 < 227) ? k + 397 : (BASE >= 227 ? k - 227 : (k < 227 ? k + 397 : k - 227));
+            v[j] = mt_mix(xs[j], xs[j + 1], mt[src < 624 ? src : 623]);
+        }
+    }
+    __syncwarp();
+    if (act) {
+        if (k0 + 4 <= 623) *reinterpret_cast<uint4 *>(mt + k0) = make_uint4(v[0], v[1], v[2], v[3]);
+        else { for (int j = 0; j < 4; j++) if (k0 + j < 623) mt[k0 + j] = v[j]; }
+    }
+    __syncwarp();
+}
+AIE_DEV_NOINLINE void mt_twist(uint32_t *mt, int lane) {
+    __syncwarp();
+    mt_twist_chunk<0>(mt, lane);
+    mt_twist_chunk<128>(mt, lane);
+    mt_twist_chunk<256>(mt, lane);
+    mt_twist_chunk<384>(mt, lane);
+    mt_twist_chunk<512>(mt, lane);
+    if (lane == 0) mt[623] = mt_mix(mt[623], mt[0], mt[396]);
+    __syncwarp();
+}
+#else
 AIE_DEV_NOINLINE void mt_twist(uint32_t *mt, int lane) {
     wsync();
     mt_twist_phase<0, 227, 397>(mt, lane);
@@ -222,6 +265,7 @@ AIE_DEV_NOINLINE void mt_twist(uint32_t *mt, int lane) {
     }
     wsync();
 }
+#endif
 
 struct Rng {
     uint32_t *mt;

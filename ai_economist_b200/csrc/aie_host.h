@@ -4,6 +4,7 @@
 #pragma once
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -305,6 +306,8 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         // shared memory.  Records too large even for that keep the two big, sparsely touched sections in HBM/L2 (split).
         c.mw = (c.rec_bytes > 24 * 1024) ? 4 : 1;
         c.split = (c.rec_bytes > 100 * 1024) ? 1 : 0;
+        if (const char *v = getenv("AIE_MW")) { const int k = atoi(v); if (k == 1 || k == 4) c.mw = k; }          // tuning aids
+        if (const char *v = getenv("AIE_SPLIT")) { const int k = atoi(v); if (k == 0 || k == 1) c.split = k; }
         if (c.split) layout(true);
         c.resident_bytes = c.split ? c.off_price_hist : c.rec_bytes;
         c.step_scratch_bytes = align16(8 * (2 * A + 4) + 16 * A + 7 * A + 16);
@@ -318,6 +321,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         // ---- observation staging (aie_obs.cuh: ObsScratch) ----
         const int ww = c.win * c.win, HW4 = (c.HW + 3) & ~3;
         c.wc_stride = (ww + 7) & ~7;
+        c.wcu_magic = (c.wc_stride >> 3) > 1 ? (uint32_t)((1ull << 32) / (uint64_t)(c.wc_stride >> 3)) + 1u : 0u;
         c.pl_stride_a = 4 * ((ww + 31) / 32);
         c.pl_stride_p = 4 * ((c.HW + 31) / 32);
         int need[OB_COUNT];
@@ -336,28 +340,42 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         };
         const int early_ids[] = {OB_NET_HIST, OB_SHF, OB_SC_A, OB_LIM, OB_PSH, OB_LOCMAP};
         const int late_ids[] = {OB_WI, OB_PL, OB_BITS, OB_WC};
-        // device placement.  Pools (byte ranges of the env's shared-memory region): the MT19937 key image (free from the
-        // start of the pass), the dead tail of the record image + the step scratch (free once the scalars are staged), and
-        // extra memory behind them (grows as needed).
+        // a staged run of n floats may start up to 3 floats into its (16-byte aligned) staging area and is copied in
+        // whole 16-byte groups
+        auto pad_run = [](int n) { return (n + 6) & ~3; };
+        auto vals_needs = [&](int fc, bool commit) {
+            int off = 0, o[4];
+            o[0] = off; off += pad_run(fc * c.Fa);
+            o[1] = off; off += pad_run(fc * c.Na);
+            o[2] = off; off += pad_run(fc * c.Fpa);
+            o[3] = off; off += pad_run(c.Fp);
+            if (commit) for (int i = 0; i < 4; i++) c.vals_off[i] = o[i];
+            need[OB_VALS] = align16(4 * off + 16);
+        };
+        // Device placement.  One region of the env's shared memory becomes free during the pass: [off_mt, resident + step
+        // scratch).  Its first part, the MT19937 key image, is free from the start (the key goes out as its own bulk group);
+        // the rest - the other kept state, price history, order slots, step scratch - once the scalars are staged and the
+        // record's write-back has been read (DevExec::record_stored).  Early buffers (used before that point) therefore sit in
+        // the key image, or in extra memory when they do not fit; the late buffers follow them and run on into extra memory
+        // behind the region as far as needed.  The flat-value staging shares its bytes with the window buffers.
         const int mt_lo = c.off_mt, mt_hi = c.off_mt + 4 * 624;
-        const int late_lo = c.split ? c.resident_bytes : c.off_price_hist, late_hi = c.resident_bytes + c.step_scratch_bytes;
-        auto place = [&](int ac, bool commit) {
+        const int late_hi = c.resident_bytes + c.step_scratch_bytes;
+        auto place = [&](int ac, int fc, bool commit) {
             chunk_needs(ac);
-            int cur_mt = mt_lo, cur_late = late_lo, extra = 0;
+            vals_needs(fc, commit);
             int off[OB_COUNT];
-            auto take_extra = [&](int bytes) { int o = late_hi + extra; extra += bytes; return o; };
             int early_total = 0;
             for (int id : early_ids) early_total += need[id];
             const bool early_in_mt = early_total <= mt_hi - mt_lo;
-            for (int id : early_ids) {
-                if (early_in_mt) { off[id] = cur_mt; cur_mt += need[id]; }
-                else off[id] = take_extra(need[id]);
-            }
-            for (int id : late_ids) {
-                if (need[id] <= mt_hi - cur_mt) { off[id] = cur_mt; cur_mt += need[id]; }
-                else if (need[id] <= late_hi - cur_late) { off[id] = cur_late; cur_late += need[id]; }
-                else off[id] = take_extra(need[id]);
-            }
+            int cur = mt_lo;
+            if (early_in_mt) for (int id : early_ids) { off[id] = cur; cur += need[id]; }
+            const int late_lo = cur;
+            for (int id : late_ids) { off[id] = cur; cur += need[id]; }
+            off[OB_VALS] = late_lo;
+            int end = std::max(cur, late_lo + need[OB_VALS]);
+            if (end < late_hi) end = late_hi;
+            if (!early_in_mt) for (int id : early_ids) { off[id] = end; end += need[id]; }
+            const int extra = end - late_hi;
             if (commit) {
                 for (int i = 0; i < OB_COUNT; i++) c.ob[i] = off[i];
                 c.obs_extra_bytes = align16(extra);
@@ -366,17 +384,22 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             return extra;
         };
         {
-            // agents per chunk: the largest count (<= 16) whose staging needs no extra shared memory, else 4
+            // agents per window chunk: the largest count (<= 16) whose staging needs no more shared memory than one agent's;
+            // agents per flat chunk: likewise, given the window chunk
+            const int base_extra = place(1, 1, false);
             int best = 0;
-            for (int ac = std::min(A, 16); ac >= 1; ac--) {
-                const int base_extra = place(1, false) ;
-                if (place(ac, false) <= base_extra) { best = ac; break; }
-            }
+            for (int ac = std::min(A, 16); ac >= 1; ac--)
+                if (place(ac, 1, false) <= base_extra) { best = ac; break; }
             c.ob_chunk = best ? best : std::min(A, 4);
-            place(c.ob_chunk, true);
+            const int chunk_extra = place(c.ob_chunk, 1, false);
+            c.fl_chunk = 1;
+            for (int fc = A; fc >= 1; fc--)
+                if (place(c.ob_chunk, fc, false) <= chunk_extra) { c.fl_chunk = fc; break; }
+            place(c.ob_chunk, c.fl_chunk, true);
         }
         {   // emulation: everything in a separate scratch allocation, nothing aliases the (live) record
             chunk_needs(c.ob_chunk);
+            vals_needs(c.fl_chunk, false);
             int off = 0;
             for (int i = 0; i < OB_COUNT; i++) { c.ob_emu[i] = off; off += need[i]; }
             c.obs_scratch_bytes = off;

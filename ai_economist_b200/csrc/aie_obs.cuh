@@ -129,6 +129,33 @@ AIE_DEV void store_bytes_i16(int16_t *dst, int n, const uint8_t *bytes, int tid,
     }
 }
 
+// ---- staged runs ---------------------------------------------------------------------------------------------------
+// Small float tensors (flat vectors, masks) are first written element by element into shared memory, laid out exactly like
+// the output run and shifted so that the 16-byte groups of the destination are 16-byte groups of the staging area
+// (element x of the run at vals[a + x], a = the destination's offset inside its 16-byte group, in floats); a second phase
+// copies the run out front to back, whole groups as float4 and the <= 3 elements at either end one by one.
+AIE_DEV int run_align(const float *dst) { return (int)(((uintptr_t)dst >> 2) & 3); }
+AIE_DEV void copy_run_f32(float *dst, int total, const float *vals, int tid, int NT) {
+    const int a = run_align(dst);
+    float *g0 = dst - a;
+    const int ng = (a + total + 3) >> 2;
+#if AIE_ON_DEVICE
+    AIE_UNROLL(1)
+#endif
+    for (int k = tid; k < ng; k += NT) {
+        const int lo = 4 * k - a;   // run index of the group's first float
+        if (lo >= 0 && lo + 4 <= total) {
+#if AIE_ON_DEVICE
+            *reinterpret_cast<float4 *>(g0 + 4 * k) = *reinterpret_cast<const float4 *>(vals + 4 * k);
+#else
+            for (int j = 0; j < 4; j++) g0[4 * k + j] = vals[4 * k + j];
+#endif
+        } else {
+            for (int j = 0; j < 4; j++) if (lo + j >= 0 && lo + j < total) g0[4 * k + j] = vals[4 * k + j];
+        }
+    }
+}
+
 // ---- bit planes ----------------------------------------------------------------------------------------------------
 // 8x8 bit-matrix transpose of 8 bytes held little-endian in (lo, hi): afterwards byte k holds bit k of the 8 input bytes
 // (bit j of output byte k = bit k of input byte j).
@@ -144,10 +171,27 @@ AIE_DEV void transpose8(uint32_t &lo, uint32_t &hi) {
 AIE_DEV void planes_from_cells(const uint8_t *cells, int n, uint8_t *planes, int stride, int np, const uint8_t *psh,
                                int tid, int NT) {
     const uint32_t *c32 = reinterpret_cast<const uint32_t *>(cells);
+    const uint32_t s0 = reinterpret_cast<const uint32_t *>(psh)[0], s1 = reinterpret_cast<const uint32_t *>(psh)[1];
     for (int u = tid; 8 * u < n; u += NT) {
         uint32_t lo = c32[2 * u], hi = c32[2 * u + 1];
         transpose8(lo, hi);
-        for (int m = 0; m < np; m++) planes[m * stride + u] = (uint8_t)prmt(lo, hi, psh[m]);
+        uint8_t *q = planes + u;
+        for (int m = 0; m < np; m++) { q[0] = (uint8_t)prmt(lo, hi, ((m < 4 ? s0 : s1) >> (8 * (m & 3))) & 7u); q += stride; }
+    }
+}
+// the same for `count` cell arrays `cell_stride` bytes apart (cell_stride = 8 * units: a multiple of 8), array k's planes at
+// planes + k * np * stride: ONE loop over all (array, unit) pairs, units_magic = floor(2^32 / units) + 1
+AIE_DEV void planes_from_cells_multi(const uint8_t *cells, int units, uint32_t units_magic, int count, uint8_t *planes, int stride,
+                                     int np, const uint8_t *psh, int tid, int NT) {
+    const uint32_t *c32 = reinterpret_cast<const uint32_t *>(cells);
+    const uint32_t s0 = reinterpret_cast<const uint32_t *>(psh)[0], s1 = reinterpret_cast<const uint32_t *>(psh)[1];
+    const int total = count * units, blk = np * stride;
+    for (int t = tid; t < total; t += NT) {
+        const int k = (int)div_magic((uint32_t)t, units_magic), u = t - k * units;
+        uint32_t lo = c32[2 * t], hi = c32[2 * t + 1];   // arrays are contiguous: unit t of the concatenation
+        transpose8(lo, hi);
+        uint8_t *q = planes + k * blk + u;
+        for (int m = 0; m < np; m++) { q[0] = (uint8_t)prmt(lo, hi, ((m < 4 ? s0 : s1) >> (8 * (m & 3))) & 7u); q += stride; }
     }
 }
 // 32 bits of a plane-local bitmap starting at bit i (the word after the last one of the bitmap must be readable)
@@ -164,6 +208,22 @@ AIE_DEV float plane_value(const uint8_t *planes, int stride, int n, uint32_t n_m
 // `planes`, `stride` bytes apart), for J in [0, nwords)
 AIE_DEV void concat_planes(uint32_t *bits, int nwords, int head, const uint8_t *planes, int stride, int nplanes, int n,
                            uint32_t n_magic, int tid, int NT) {
+    if (n >= 32) {   // a word of the string spans at most two planes
+        for (int J = tid; J < nwords; J += NT) {
+            const int x = head + 32 * J;
+            const int p = (int)div_magic((uint32_t)x, n_magic), i = x - p * n, rem = n - i;
+            uint32_t w = 0;
+            if (p < nplanes) {
+                w = take32(planes + p * stride, i);
+                if (rem < 32) {
+                    w &= (1u << rem) - 1u;
+                    if (p + 1 < nplanes) w |= reinterpret_cast<const uint32_t *>(planes + (p + 1) * stride)[0] << rem;
+                }
+            }
+            bits[J] = w;
+        }
+        return;
+    }
     for (int J = tid; J < nwords; J += NT) {
         const int x = head + 32 * J;
         int p = (int)div_magic((uint32_t)x, n_magic), i = x - p * n, filled = 0;
@@ -179,25 +239,42 @@ AIE_DEV void concat_planes(uint32_t *bits, int nwords, int head, const uint8_t *
         bits[J] = w;
     }
 }
-// the run dst[0 .. total) = the concatenated planes as 0.0f / 1.0f: 16-byte groups from the bit string, edges one by one
+// the run dst[0 .. total) = the concatenated planes as 0.0f / 1.0f: 16-byte groups from the bit string, edges one by one.
+// Thread tid owns groups tid, tid + NT, ...: group g is nibble (g & 1) of byte g >> 1 of the string, so with NT even the
+// thread's nibble position is fixed and its byte index advances by NT / 2 per group; four groups per iteration.
 AIE_DEV void stream_bits_f32(float *dst, int total, const uint32_t *bits, const float *lut, const uint8_t *planes, int stride,
                              int n, uint32_t n_magic, int tid, int NT) {
     const RunSplit r = run_split(dst, total, 2);
     store_edges(dst, r, total, tid, NT, [&](int x) { return plane_value(planes, stride, n, n_magic, x); });
     float *q = dst + r.head + 4 * tid;
+    if (NT & 1) {   // (host emulation with one thread)
+        for (int g = tid; g < r.nq; g += NT) {
+            const uint32_t nib = (bits[g >> 3] >> (4 * (g & 7))) & 15u;
+            store4(q, lut[4 * nib], lut[4 * nib + 1], lut[4 * nib + 2], lut[4 * nib + 3]);
+            q += 4 * NT;
+        }
+        return;
+    }
+    const uint8_t *b8 = reinterpret_cast<const uint8_t *>(bits) + (tid >> 1);
+    const int sh = 4 * (tid & 1), hb = NT >> 1;
+    int g = tid;
 #if AIE_ON_DEVICE
     const float4 *lut4 = reinterpret_cast<const float4 *>(lut);
+    float4 *q4 = reinterpret_cast<float4 *>(q);
     AIE_UNROLL(1)
-    for (int g = tid; g < r.nq; g += NT) {
-        const uint32_t nib = (bits[g >> 3] >> (4 * (g & 7))) & 15u;
-        *reinterpret_cast<float4 *>(q) = lut4[nib];
-        q += 4 * NT;
+    for (; g + 3 * NT < r.nq; g += 4 * NT) {
+        const uint32_t v0 = b8[0], v1 = b8[hb], v2 = b8[2 * hb], v3 = b8[3 * hb];
+        q4[0] = lut4[(v0 >> sh) & 15u]; q4[NT] = lut4[(v1 >> sh) & 15u];
+        q4[2 * NT] = lut4[(v2 >> sh) & 15u]; q4[3 * NT] = lut4[(v3 >> sh) & 15u];
+        b8 += 4 * hb; q4 += 4 * NT;
     }
+    AIE_UNROLL(1)
+    for (; g < r.nq; g += NT) { q4[0] = lut4[((uint32_t)b8[0] >> sh) & 15u]; b8 += hb; q4 += NT; }
 #else
-    for (int g = tid; g < r.nq; g += NT) {
-        const uint32_t nib = (bits[g >> 3] >> (4 * (g & 7))) & 15u;
+    for (; g < r.nq; g += NT) {
+        const uint32_t nib = ((uint32_t)b8[0] >> sh) & 15u;
         store4(q, lut[4 * nib], lut[4 * nib + 1], lut[4 * nib + 2], lut[4 * nib + 3]);
-        q += 4 * NT;
+        b8 += hb; q += 4 * NT;
     }
 #endif
 }
@@ -220,6 +297,7 @@ struct ObsScratch {
     uint8_t *wi;          // [chunk][2][ww] owner code, agent-location code (the int16 index planes as bytes)
     uint8_t *pl;          // plane-local bitmaps (agent chunk: [chunk][M+1] planes of ww bits; planner: [M] planes of HW bits)
     uint32_t *bits;       // concatenated bit string of the run being streamed
+    float *vals;          // staged runs of the flat vectors / masks (shares its bytes with wc / wi / pl / bits)
 };
 // base: the env's shared-memory region on the device (offsets c.ob[] may alias dead parts of the record image), or a
 // separate scratch allocation in emulation (c.ob_emu[])
@@ -235,6 +313,7 @@ AIE_DEV ObsScratch obs_scratch_view(uint8_t *base, const int32_t *ob) {
     s.wi = base + ob[OB_WI];
     s.pl = base + ob[OB_PL];
     s.bits = (uint32_t *)(base + ob[OB_BITS]);
+    s.vals = (float *)(base + ob[OB_VALS]);
     return s;
 }
 
@@ -404,28 +483,12 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     // live on top of them: the record's write-back must have finished reading shared memory first.
     ex.record_stored();
 
-    // ---- phase B: small tensors (flat vectors, masks), one run each ---------------------------------------------------
+    // ---- phase B: the planner's flat vector (staged; copied out with the first agent chunk below), planner mask, policy ----
     ex([&](int tid) {
-        const float *shf = s.shf, *sc = s.sc_a;
-        const uint8_t *hist = e.bid_hist;
-        const int sh_full = c.sh_full;
         {
-            const uint16_t *tpa = tab + c.tab_pa, *tp = tab + c.tab_p;
-            if (!EXT || c.Fpa > 0)
-                store_rows_f32(o.p_agents(), A, c.Fpa, c.Fpa_magic, tid, NT,
-                               [=](int a, int j) { return flat_value(shf, sc + a * AS_COUNT, hist, hoff, a * P, sh_full, tpa[j]); });
-            store_run_f32(o.p_flat(), c.Fp, tid, NT, [=](int j) { return flat_value(shf, shf, hist, hoff, 0, sh_full, tp[j]); });
-            // agents' flat vectors: A x Fa, sorted-key concatenation (base_env.py:562-612)
-            store_rows_f32(o.a_flat(), A, c.Fa, c.Fa_magic, tid, NT,
-                           [=](int a, int j) { return flat_value(shf, sc + a * AS_COUNT, hist, hoff, a * P, sh_full, tab[j]); });
-        }
-        {
-            const uint16_t *mt = tab + c.tab_m;
-            const uint8_t *lim = s.lim;
-            store_rows_f32(o.a_mask(), A, c.Na, c.Na_magic, tid, NT, [=](int a, int j) {
-                const uint32_t en = mt[j];
-                return ((en & 255u) < lim[a * MS_COUNT + (en >> 8)]) ? 1.0f : 0.0f;
-            });
+            const uint16_t *tp = tab + c.tab_p;
+            float *v = s.vals + c.vals_off[3] + run_align(o.p_flat());
+            for (int j = tid; j < c.Fp; j += NT) v[j] = flat_value(s.shf, s.shf, e.bid_hist, hoff, 0, c.sh_full, tp[j]);
         }
         if (c.planner_acts) {  // redistribution.py:1025-1104, multi-action planner: per bracket [1] ++ rates
             const bool first_day = e.hdr[HDR_TAX_POS] == 1;
@@ -483,6 +546,51 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
         }
     });
 
+    // ---- flat vectors / masks of the agents (base_env.py:562-612, base_agent.py:440-460), fl_chunk agents at a time:
+    // phase 1 stages the chunk's rows of the three tensors as runs, phase 2 copies them out
+    for (int a0 = 0; a0 < A; a0 += c.fl_chunk) {
+        const int na = (A - a0 < c.fl_chunk) ? A - a0 : c.fl_chunk;
+        float *d_flat = o.a_flat() + (size_t)a0 * c.Fa, *d_mask = o.a_mask() + (size_t)a0 * c.Na, *d_pa = o.p_agents() + (size_t)a0 * c.Fpa;
+        ex([&](int tid) {
+            const float *shf = s.shf;
+            const uint8_t *hist = e.bid_hist;
+            const int sh_full = c.sh_full;
+            {   // agents' flat vectors: sorted-key concatenation
+                float *v = s.vals + c.vals_off[0] + run_align(d_flat);
+                const int n = c.Fa, total = na * n;
+                for (int x = tid; x < total; x += NT) {
+                    const int al = (int)div_magic((uint32_t)x, c.Fa_magic), j = x - al * n, a = a0 + al;
+                    v[x] = flat_value(shf, s.sc_a + a * AS_COUNT, hist, hoff, a * P, sh_full, tab[j]);
+                }
+            }
+            {   // action masks: entry (slot, idx) is open iff idx < limit[agent][slot]
+                float *v = s.vals + c.vals_off[1] + run_align(d_mask);
+                const uint16_t *mt = tab + c.tab_m;
+                const int n = c.Na, total = na * n;
+                for (int x = tid; x < total; x += NT) {
+                    const int al = (int)div_magic((uint32_t)x, c.Na_magic), j = x - al * n;
+                    const uint32_t en = mt[j];
+                    v[x] = ((en & 255u) < s.lim[(a0 + al) * MS_COUNT + (en >> 8)]) ? 1.0f : 0.0f;
+                }
+            }
+            if (!EXT || c.Fpa > 0) {   // the planner's per-agent vectors p<i>
+                float *v = s.vals + c.vals_off[2] + run_align(d_pa);
+                const uint16_t *tpa = tab + c.tab_pa;
+                const int n = c.Fpa, total = na * n;
+                for (int x = tid; x < total; x += NT) {
+                    const int al = (int)div_magic((uint32_t)x, c.Fpa_magic), j = x - al * n, a = a0 + al;
+                    v[x] = flat_value(shf, s.sc_a + a * AS_COUNT, hist, hoff, a * P, sh_full, tpa[j]);
+                }
+            }
+        });
+        ex([&](int tid) {
+            copy_run_f32(d_flat, na * c.Fa, s.vals + c.vals_off[0], tid, NT);
+            copy_run_f32(d_mask, na * c.Na, s.vals + c.vals_off[1], tid, NT);
+            if (!EXT || c.Fpa > 0) copy_run_f32(d_pa, na * c.Fpa, s.vals + c.vals_off[2], tid, NT);
+            if (a0 == 0) copy_run_f32(o.p_flat(), c.Fp, s.vals + c.vals_off[3], tid, NT);
+        });
+    }
+
     // ---- phase C: the planner's spatial tensors: M bit planes of the whole map + the two index planes -----------------
     const int psp = c.pl_stride_p;   // bytes per whole-map plane bitmap
     if (c.planner_spatial || (EXT && c.full_obs)) {
@@ -536,35 +644,27 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
         int head = 0;
         const int nwords = bits_words_for(am, na * np1 * ww, &head);
         ex([&](int tid) {
-            // thread's first window cell and the (dr, dc) step for q += NT
-            const int dr_first = (int)div_magic((uint32_t)tid, c.win_magic), dc_first = tid - dr_first * win;
-            const int dr_step = NT / win, dc_step = NT - dr_step * win;
-            for (int al = 0; al < na; al++) {
-                const int a = a0 + al;
-                const int r0 = e.loc[2 * a] - w, c0 = e.loc[2 * a + 1] - w;
-                uint8_t *wc = s.wc + al * wcs, *wi = s.wi + al * 2 * ww;
-                int dr = dr_first, dc = dc_first;
-                for (int q = tid; q < ww; q += NT) {
-                    const int r2 = r0 + dr, c2 = c0 + dc;
-                    const bool inside = (unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W;
-                    uint32_t cb = 0; int vo = 0, vl = 0;
-                    if (inside) {
-                        const int k = r2 * W + c2;
-                        cb = e.cell[k] | 0x40u;
-                        const int ow = e.owner[k];
-                        vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
-                        vl = s.locmap[k];
-                        if (vl == a + 2) vl = 1;
-                    }
-                    wc[q] = (uint8_t)cb; wi[q] = (uint8_t)vo; wi[ww + q] = (uint8_t)vl;
-                    dr += dr_step; dc += dc_step;
-                    while (dc >= win) { dc -= win; dr += 1; }
+            const int total = na * ww;
+            for (int t = tid; t < total; t += NT) {   // one (agent, window cell) pair per thread and iteration
+                const int al = (int)div_magic((uint32_t)t, c.ww_magic), q = t - al * ww, a = a0 + al;
+                const int dr = (int)div_magic((uint32_t)q, c.win_magic), dc = q - dr * win;
+                const int r2 = e.loc[2 * a] - w + dr, c2 = e.loc[2 * a + 1] - w + dc;
+                uint32_t cb = 0; int vo = 0, vl = 0;
+                if ((unsigned)r2 < (unsigned)H && (unsigned)c2 < (unsigned)W) {
+                    const int k = r2 * W + c2;
+                    cb = e.cell[k] | 0x40u;
+                    const int ow = e.owner[k];
+                    vo = ow < 0 ? 0 : (ow == a ? 1 : ow + 2);
+                    vl = s.locmap[k];
+                    if (vl == a + 2) vl = 1;
                 }
+                s.wc[al * wcs + q] = (uint8_t)cb;
+                uint8_t *wi = s.wi + al * 2 * ww + q;
+                wi[0] = (uint8_t)vo; wi[ww] = (uint8_t)vl;
             }
         });
         ex([&](int tid) {
-            for (int al = 0; al < na; al++)
-                planes_from_cells(s.wc + al * wcs, ww, s.pl + al * np1 * psa, psa, np1, s.psh, tid, NT);
+            planes_from_cells_multi(s.wc, wcs >> 3, c.wcu_magic, na, s.pl, psa, np1, s.psh, tid, NT);
             store_bytes_i16<false>(o.a_idx() + (size_t)a0 * 2 * ww, na * 2 * ww, s.wi, tid, NT);
         });
         ex([&](int tid) { concat_planes(s.bits, nwords, head, s.pl, psa, na * np1, ww, c.ww_magic, tid, NT); });

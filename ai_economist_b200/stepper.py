@@ -169,9 +169,10 @@ class BatchStepper:
 
     def host_timing(self):
         """Host-clock breakdown (ms) of the last compacted step_host call (aie_get_host_timing)."""
-        out = (C.c_double * 8)()
-        self.lib.aie_get_host_timing(self._h, out, 8)
-        k = ["enqueued", "first_slice", "last_slice", "expanded", "slices", "threads", "d2h_bytes", "before_transfer"]
+        out = (C.c_double * 16)()
+        self.lib.aie_get_host_timing(self._h, out, 16)
+        k = ["enqueued", "first_slice", "last_slice", "expanded", "slices", "threads", "d2h_bytes", "before_transfer",
+             "wait_sum", "busy_sum", "first_slice_dev", "last_slice_dev", "expand_only"]
         return dict(zip(k, list(out)))
 
     def compact_bytes_per_env(self):

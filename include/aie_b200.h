@@ -331,8 +331,10 @@ int32_t aie_compact_bytes_per_env(const aie_env *env);
 /* Host-clock breakdown of the last aie_step_host_compact call, milliseconds from the start of its transfer phase:
  * [0] copies enqueued, [1] first transfer slice on the host, [2] last slice on the host, [3] expansion finished,
  * [4] number of slices, [5] host threads used, [6] bytes moved device->host, [7] time before the transfer phase (action
- * upload + launches enqueued).  Returns the number of words defined (diagnostics for tuning n_threads). */
-#define AIE_HOST_TIMING_WORDS 8
+ * upload + launches enqueued), [8] time the threads spent waiting for their slice and [9] expanding (summed over threads),
+ * [10] / [11] device-clock arrival of the first / last slice since the call's first enqueue, [12] the expansion alone
+ * (only with AIE_E2E_REPEAT_EXPAND=n in the environment).  Returns the number of words defined (diagnostics for tuning). */
+#define AIE_HOST_TIMING_WORDS 16
 int aie_get_host_timing(const aie_env *env, double *out, int32_t cap);
 
 /* Test/debug readback of env `e` (synchronous). */

@@ -40,6 +40,8 @@ int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
 int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
 int download_slice(aie_env *, int k, void *host, const void *dev, size_t n, void *stream);
 int wait_slice(aie_env *, int k);
+double slice_device_ms(aie_env *, int k);
+int mark_call_start(aie_env *, void *stream);
 void *const_upload(const void *host, size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
@@ -69,6 +71,8 @@ int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
 }
 int download_slice(aie_env *, int, void *host, const void *dev, size_t n, void *) { memcpy(host, dev, n); return AIE_OK; }
 int wait_slice(aie_env *, int) { return AIE_OK; }
+double slice_device_ms(aie_env *, int) { return -1.0; }
+int mark_call_start(aie_env *, void *) { return AIE_OK; }
 int launch_pack(aie_env *env, const CompactLayout &L, uint8_t *dev, void *) {
     for (int e = 0; e < env->n_envs; e++) pack_env(env->cfg, env->bufs, L, (size_t)e, dev + (size_t)e * L.bytes, 0);
     return AIE_OK;
