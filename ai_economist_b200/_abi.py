@@ -1,8 +1,10 @@
 """ctypes mirror of include/aie_b200.h (the C-ABI of the CUDA library).  No compute happens here."""
 import ctypes as C
+
+import numpy as np
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 8, 16, 64
 AIE_OK = 0
 
@@ -42,6 +44,8 @@ class AieConfig(C.Structure):
         ("single_action_planner", C.c_int32), ("regen_halfwidth", C.c_int32 * 2),
         ("full_observability", C.c_int32),
         ("split_layout", C.c_int32), ("split_water_row", C.c_int32), ("split_top_ranks", C.c_uint64),
+        ("dyn_layout", C.c_int32), ("dyn_checker", C.c_int32), ("dyn_coverage", C.c_double * 2), ("dyn_clump", C.c_double * 2),
+        ("dyn_prob", C.c_void_p),
     ]
 
 
@@ -232,4 +236,13 @@ def config_from_spec(spec, auto_reset=True):
     cfg.split_layout = int(spec.get("split_layout", 0))
     cfg.split_water_row = int(spec.get("split_water_row", 0))
     cfg.split_top_ranks = int(spec.get("split_top_ranks", 0))
+    cfg.dyn_layout = int(spec.get("dyn_layout", 0)) if cfg.reset_mode == 1 else 0
+    if cfg.dyn_layout:
+        cfg.dyn_checker = int(spec.get("dyn_checker", 0))
+        cfg.dyn_coverage[0], cfg.dyn_coverage[1] = [float(v) for v in spec["dyn_coverage"]]
+        cfg.dyn_clump[0], cfg.dyn_clump[1] = [float(v) for v in spec["dyn_clump"]]
+        prob = np.ascontiguousarray(np.asarray(spec["dyn_prob"], np.float64))
+        assert prob.shape == (2, spec["height"], spec["width"]), "dyn_prob must be float64 [2][height][width]"
+        cfg._dyn_prob_keep = prob    # aie_create copies it; kept alive until then
+        cfg.dyn_prob = prob.ctypes.data
     return cfg

@@ -69,6 +69,7 @@ int wait_slice(aie_env *, int k);
 double slice_device_ms(aie_env *, int k);
 int mark_call_start(aie_env *, void *stream);
 void *const_upload(const void *host, size_t bytes);
+void *dev_alloc(size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
 int covid_launch_step(aie_covid_env *, void *stream);
@@ -220,7 +221,8 @@ __device__ __forceinline__ void warp_step(const DevCfg &c, const DevBufs &b, int
             hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
         }
         __syncwarp();
-        if (c.reset_mode == 1) device_reset_env<EXT>(c, rec, grec, scratch, lane);  // reference-exact placement / skills
+        if (c.reset_mode == 1)   // reference-exact layout (dynamic scenarios) / placement / skills
+            device_reset_env<EXT>(c, rec, grec, scratch, lane, b.dyn_prob, b.dyn_work ? b.dyn_work + (size_t)env * c.HW : nullptr);
         finish_reset_env(c, rec, grec, scratch, lane);  // metric_0 under the new completions count
     }
 
@@ -588,6 +590,12 @@ void *const_upload(const void *host, size_t bytes) {
     void *d = nullptr;
     if (cudaMalloc(&d, bytes) != cudaSuccess) return nullptr;
     if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+}
+void *dev_alloc(size_t bytes) {
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(d, 0, bytes) != cudaSuccess) { cudaFree(d); return nullptr; }
     return d;
 }
 void const_free(void *dev) { cudaFree(dev); }

@@ -15,6 +15,7 @@
 //   int download_slice(aie_env*, int k, void *host, const void *dev, size_t n, void *stream);   (async copy + event k)
 //   int wait_slice(aie_env*, int k);                                                           (any thread)
 //   double slice_device_ms(aie_env*, int k);   device-clock time of slice k's arrival since the call's first enqueue (-1: n/a)
+//   void *const_upload(const void *host, size_t bytes);  void *dev_alloc(size_t bytes);  void const_free(void *dev);
 //   struct DevScope { DevScope(int device); ~DevScope(); bool ok() const; };   makes `device` current for the scope of one
 //       entry point and restores the caller's device on exit (a handle can be used while another device is current)
 #include <stdio.h>
@@ -38,6 +39,7 @@ struct aie_env {
     uint64_t sample_calls;
     aie::be::State be;
     std::vector<aie_flat_field> flat_layout[3];
+    void *dyn_prob_dev = nullptr, *dyn_work_dev = nullptr;   // dynamic layouts: probability maps, per-env work maps
     aie::HostPool *pool = nullptr;   // aie_step_host_compact: created on first use
     double host_timing[AIE_HOST_TIMING_WORDS] = {};   // last aie_step_host_compact call (aie_get_host_timing)
 };
@@ -74,6 +76,14 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     aie::be::DevScope dev_scope_(device);   // init() validates the ordinal itself and reports the precise error
     rc = aie::be::init(env);
     if (rc != AIE_OK) { delete env; return rc; }
+    if (env->cfg.dyn_layout) {   // library-owned device memory of the layout generator
+        const size_t hw = (size_t)env->cfg.HW;
+        env->dyn_prob_dev = aie::be::const_upload(cfg->dyn_prob, 2 * hw * sizeof(double));
+        env->dyn_work_dev = aie::be::dev_alloc((size_t)n_envs * hw * sizeof(double));
+        if (!env->dyn_prob_dev || !env->dyn_work_dev) { aie_destroy(env); return fail(AIE_ENOMEM, "aie_create: device memory for the layout generator"); }
+        env->bufs.dyn_prob = (const double *)env->dyn_prob_dev; env->bufs.dyn_work = (double *)env->dyn_work_dev;
+    }
+    env->ucfg.dyn_prob = nullptr;   // the caller's pointer is not kept
     *out = env;
     return AIE_OK;
 }
@@ -82,6 +92,8 @@ int aie_destroy(aie_env *env) {
     if (!env) return AIE_OK;
     aie::be::DevScope dev_scope_(env->device);
     aie::be::destroy(env);
+    if (env->dyn_prob_dev) aie::be::const_free(env->dyn_prob_dev);
+    if (env->dyn_work_dev) aie::be::const_free(env->dyn_work_dev);
     delete env->pool;
     delete env;
     return AIE_OK;

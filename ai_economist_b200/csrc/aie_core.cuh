@@ -855,7 +855,10 @@ AIE_DEV void current_metrics(const DevCfg &c, const Env &e, double *out, double 
     const double coef = energy_weight(c, e) * c.energy_cost;
     for (int a = lane; a < A; a += NL) {
         double x = e.coin[a] + e.esc_coin[a];
-        double util_c = (c.eta == 1.0) ? log(fmax(1.0, x)) : (pow(x, 1.0 - c.eta) - 1.0) / (1.0 - c.eta);
+        // eta == 0: x ** 1.0 is x exactly in IEEE arithmetic (numpy / libm); the device pow() is not guaranteed to return
+        // it, and with energy_warmup_method "auto" a last-place difference can flip `mean reward > 0` when linear utilities
+        // cancel exactly (found by the CUDA-vs-oracle configuration fuzz)
+        double util_c = (c.eta == 1.0) ? log(fmax(1.0, x)) : ((c.eta == 0.0 ? x : pow(x, 1.0 - c.eta)) - 1.0) / (1.0 - c.eta);
         out[a] = util_c - e.labor[a] * coef;
     }
     wsync();
@@ -1046,16 +1049,227 @@ AIE_DEV double rng_gauss(Rng &r, double *g) {   // warp-uniform call
 }
 AIE_DEV double rng_lognormal(Rng &r, double *g, double mean, double sigma) { return exp(mean + sigma * rng_gauss(r, g)); }
 
+
+// ------------------------------------------------------------------------------------------------
+// Dynamic layouts at reset (aie_config::dyn_layout): Uniform.reset_starting_layout, dynamic_layout.py:313-392
+// ------------------------------------------------------------------------------------------------
+// n uniform doubles (np.random.rand: random_sample) into out[0 .. n), drawn lane-parallel: double i is key words 2i, 2i + 1
+// of the run.  A double straddling a key regeneration is finished by the sequential path.
+AIE_DEV void rng_fill_double(Rng &r, double *out, int n) {
+    int i = 0;
+    while (i < n) {
+        if (r.pos == 624) { mt_twist(r.mt, r.lane); r.pos = 0; }
+        const int avail = (624 - r.pos) >> 1;
+        if (avail == 0) {
+            const double v = rng_double(r);
+            if (r.lane == 0) out[i] = v;
+            i++;
+            continue;
+        }
+        const int m = avail < n - i ? avail : n - i;
+        for (int j = r.lane; j < m; j += NL) {
+            const int32_t a = (int32_t)(mt_temper(r.mt[r.pos + 2 * j]) >> 5), b = (int32_t)(mt_temper(r.mt[r.pos + 2 * j + 1]) >> 6);
+            out[i + j] = (a * 67108864.0 + b) / 9007199254740992.0;
+        }
+        wsync();
+        r.pos += 2 * m; i += m;
+    }
+}
+AIE_DEV int kth_set_bit(uint32_t m, int k) {   // position of the k-th (1-based) set bit of m
+#if AIE_ON_DEVICE
+    return (int)__fns(m, 0, k);
+#else
+    for (int i = 0; i < 32; i++) if ((m >> i) & 1u) { if (--k == 0) return i; }
+    return -1;
+#endif
+}
+// n standard normals (np.random.randn: legacy_gauss) into out[0 .. n).  The polar method draws trial pairs of uniforms
+// until one falls inside the unit circle and then yields TWO normals - f * x2 at once, f * x1 cached for the next call.
+// Every trial consumes exactly four key words whether it is accepted or not, so trials are evaluated lane-parallel and
+// the accepted ones numbered by a ballot; the stream stops right after the trial that supplies the last normal needed.
+// g: the cache {value, has} in the record (shared with every other Gaussian draw of the env).
+AIE_DEV void rng_fill_gauss(Rng &r, double *g, double *out, int n) {
+    const int lane = r.lane;
+    int i = 0;
+    if (n > 0 && g[1] != 0.0) {
+        const double cached = g[0];
+        wsync();
+        if (lane == 0) { out[0] = cached; g[0] = 0.0; g[1] = 0.0; }
+        wsync();
+        i = 1;
+    }
+    while (i < n) {
+        const int need = (n - i + 1) >> 1;   // accepted pairs still needed
+        if (r.pos == 624) { mt_twist(r.mt, lane); r.pos = 0; }
+        const int avail = (624 - r.pos) >> 2;
+        if (avail == 0) {   // a trial straddling a key regeneration: sequential
+            const double x1 = 2.0 * rng_double(r) - 1.0, x2 = 2.0 * rng_double(r) - 1.0, r2 = x1 * x1 + x2 * x2;
+            if (!(r2 >= 1.0 || r2 == 0.0)) {
+                const double f = sqrt(-2.0 * log(r2) / r2);
+                wsync();
+                if (lane == 0) {
+                    out[i] = f * x2;
+                    if (i + 1 < n) out[i + 1] = f * x1; else { g[0] = f * x1; g[1] = 1.0; }
+                }
+                wsync();
+                i += 2;
+            }
+            continue;
+        }
+        const int nb = avail < NL ? avail : NL;
+        bool acc = false;
+        double x1 = 0.0, x2 = 0.0, r2 = 1.0;
+        if (lane < nb) {
+            const uint32_t *w = r.mt + r.pos + 4 * lane;
+            const int32_t a1 = (int32_t)(mt_temper(w[0]) >> 5), b1 = (int32_t)(mt_temper(w[1]) >> 6);
+            const int32_t a2 = (int32_t)(mt_temper(w[2]) >> 5), b2 = (int32_t)(mt_temper(w[3]) >> 6);
+            x1 = 2.0 * ((a1 * 67108864.0 + b1) / 9007199254740992.0) - 1.0;
+            x2 = 2.0 * ((a2 * 67108864.0 + b2) / 9007199254740992.0) - 1.0;
+            r2 = x1 * x1 + x2 * x2;
+            acc = !(r2 >= 1.0 || r2 == 0.0);
+        }
+        const uint32_t m = wballot(acc);
+        const int cnt = __popc_u32(m);
+        int use_pairs = cnt, used_trials = nb;
+        if (cnt >= need) { use_pairs = need; used_trials = kth_set_bit(m, need) + 1; }
+        if (acc) {
+            const int rank = __popc_u32(m & ((1u << lane) - 1u));
+            if (rank < use_pairs) {
+                const double f = sqrt(-2.0 * log(r2) / r2);
+                const int idx = i + 2 * rank;
+                out[idx] = f * x2;
+                if (idx + 1 < n) out[idx + 1] = f * x1; else { g[0] = f * x1; g[1] = 1.0; }
+            }
+        }
+        wsync();
+        r.pos += 4 * used_trials; i += 2 * use_pairs;
+    }
+}
+
+// One output of scipy.signal.convolve2d(x, kernel, "same") for a 7 x 7 kernel of zeros and ones (bit j * 7 + k of
+// `kern`): out[m, n] = sum_{j, k} x[m - j + 3, n - k + 3] * kernel[j, k], zero outside the map.  The float64 sum is
+// accumulated in the order of scipy's C loop (verified bit for bit against scipy 1.18 on random inputs, see
+// tests/test_dynamic_layout.py): kernel rows in ascending order; inside a row the first four taps as one expression
+// ((t0 + t1) + t2) + t3 added to the accumulator, then taps 4, 5, 6 one by one.
+AIE_DEV double conv7_same(const double *x, int H, int W, int m, int n, uint64_t kern) {
+    double acc = 0.0;
+    for (int j = 0; j < 7; j++) {
+        const int rr = m - j + 3;
+        double t[7];
+        for (int k = 0; k < 7; k++) {
+            const int cc = n - k + 3;
+            const bool in = (unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W && ((kern >> (j * 7 + k)) & 1ull);
+            t[k] = in ? x[rr * W + cc] : 0.0;
+        }
+        acc += ((t[0] + t[1]) + t[2]) + t[3];
+        acc += t[4]; acc += t[5]; acc += t[6];
+    }
+    return acc;
+}
+
+constexpr uint8_t CELL_CAND = 0x80;   // scratch bit of the cell byte while a layout is being generated
+
+// Clumped random source placement.  prob: float64 [2][HW] (Wood, Stone); work: this env's float64 [HW] scratch map.
+// Leaves the Wood / Stone resource and source bits of e.cell set; water and house bits are not touched.
+AIE_DEV void gen_layout(const DevCfg &c, Env &e, Rng &r, const double *prob, double *work) {
+    const int HW = c.HW, H = c.H, W = c.W, lane = r.lane;
+    const uint8_t res_bits[2] = {(uint8_t)(CELL_WOOD | CELL_WOOD_SRC), (uint8_t)(CELL_STONE | CELL_STONE_SRC)};
+    auto count_cand = [&]() {
+        int n = 0;
+        for (int k = lane; k < HW; k += NL) n += (e.cell[k] & CELL_CAND) ? 1 : 0;
+        return (double)wsum((double)n) / (double)HW;   // np.mean of a boolean map
+    };
+    for (int attempt = 0; attempt < 100; attempt++) {
+        for (int k = lane; k < HW; k += NL) e.cell[k] &= (uint8_t)~(res_bits[0] | res_bits[1] | CELL_CAND);   // maps.clear()
+        wsync();
+        double mean_res[2];
+        for (int ri = 0; ri < 2; ri++) {   // Wood, then Stone on what Wood left empty
+            const double clump = c.dyn_clump[ri], cover = c.dyn_cov[ri];
+            const double *sp = prob + (size_t)ri * HW;
+            auto threshold_pass = [&](bool decay) {
+                for (int k = lane; k < HW; k += NL) {
+                    double v = work[k];
+                    if (decay) { v *= 0.9; work[k] = v; }
+                    const uint8_t cb = e.cell[k];
+                    const bool empty = !(cb & (res_bits[0] | res_bits[1]));
+                    e.cell[k] = (uint8_t)((cb & ~CELL_CAND) | ((v < sp[k] * 0.1 * clump && empty) ? CELL_CAND : 0));
+                }
+                wsync();
+            };
+            rng_fill_double(r, work, HW);
+            threshold_pass(false);
+            double mean = count_cand();
+            for (int tries = 0; mean < cover * clump;) {
+                threshold_pass(true);
+                mean = count_cand();
+                if (++tries > 200) break;
+            }
+            for (int grow = 0; mean < cover && grow < 100000; grow++) {
+                // kernel = np.random.randn(7, 7) > 0
+                rng_fill_gauss(r, e.gauss, work, 49);
+                wsync();
+                uint64_t kern = 0;
+                for (int q = 0; q < 49; q++) kern |= (uint64_t)(work[q] > 0.0 ? 1 : 0) << q;
+                wsync();
+                // x = candidate + 0.2 * np.random.randn(H, W) - 0.25
+                rng_fill_gauss(r, e.gauss, work, HW);
+                wsync();
+                for (int k = lane; k < HW; k += NL) work[k] = (((e.cell[k] & CELL_CAND) ? 1.0 : 0.0) + 0.2 * work[k]) - 0.25;
+                wsync();
+                // candidate = max(convolve2d(x, kernel, "same") > 0, candidate) * empty
+                for (int k = lane; k < HW; k += NL) {
+                    const uint8_t cb = e.cell[k];
+                    if (cb & (CELL_CAND | res_bits[0] | res_bits[1])) continue;   // already a candidate, or not empty
+                    const int m = k / W, n = k - m * W;
+                    if (conv7_same(work, H, W, m, n, kern) > 0.0) e.cell[k] = (uint8_t)(cb | CELL_CAND);
+                }
+                wsync();
+                mean = count_cand();
+            }
+            mean_res[ri] = mean;
+            for (int k = lane; k < HW; k += NL) {   // world.maps.set(resource, ...), set(resource + "SourceBlock", ...)
+                const uint8_t cb = e.cell[k];
+                if (cb & CELL_CAND) e.cell[k] = (uint8_t)((cb & ~CELL_CAND) | res_bits[ri]);
+            }
+            wsync();
+        }
+        bool happy = true;   // both coverages within 1.4x of their targets, else start over
+        for (int ri = 0; ri < 2; ri++) {
+            const double q = mean_res[ri] / c.dyn_cov[ri];
+            if (!((1.0 / (1.0 + 0.4)) <= q && q <= (1.0 + 0.4))) happy = false;
+        }
+        if (happy) break;
+    }
+    if (c.dyn_checker || c.dyn_layout == 2) {
+        const int col_line = H / 2, row_line = W / 2;   // Quadrant: state[:, height // 2] = 0; state[width // 2, :] = 0
+        for (int k = lane; k < HW; k += NL) {
+            const int m = k / W, n = k - m * W;
+            const bool drop = (c.dyn_checker && ((m + n) & 1) == 0) || (c.dyn_layout == 2 && (n == col_line || m == row_line));
+            if (drop) e.cell[k] &= (uint8_t)~(res_bits[0] | res_bits[1]);
+        }
+        wsync();
+    }
+}
+
 template <bool EXT>
-AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
+AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, const double *dyn_prob, double *dyn_work) {
     const int A = c.A, lane = r.lane;
-    for (int a = 0; a < A; a++) {  // np.random.randint(0, H), randint(0, W) until the cell is free and not water
+    const bool dyn = c.dyn_layout != 0;   // (not behind EXT: the whole reset is one out-of-line call, cold code)
+    if (dyn) {   // dynamic_layout.py:313-392, then reset_agent_states places the agents in a random order (:418-429)
+        gen_layout(c, e, r, dyn_prob, dyn_work);
+        rng_permutation(r, s.perm, A);
+        for (int a = lane; a < A; a += NL) { e.loc[2 * a] = -1; e.loc[2 * a + 1] = -1; }
+        wsync();
+    }
+    for (int i = 0; i < A; i++) {  // np.random.randint(0, H), randint(0, W) until the cell is free and not water
+        const int a = dyn ? s.perm[i] : i;
         int row = 0, col = 0;
         for (int tries = 0; tries <= 201; tries++) {
             row = (int)rng_interval(r, (uint32_t)(c.H - 1));
             col = (int)rng_interval(r, (uint32_t)(c.W - 1));
             bool blocked = (e.cell[row * c.W + col] & CELL_WATER) != 0;
-            for (int a2 = 0; a2 < a && !blocked; a2++) blocked = e.loc[2 * a2] == row && e.loc[2 * a2 + 1] == col;
+            if (dyn) { for (int a2 = 0; a2 < A && !blocked; a2++) blocked = e.loc[2 * a2] == row && e.loc[2 * a2 + 1] == col; }
+            else { for (int a2 = 0; a2 < a && !blocked; a2++) blocked = e.loc[2 * a2] == row && e.loc[2 * a2 + 1] == col; }
             if (!blocked) break;
         }
         wsync();
@@ -1121,12 +1335,13 @@ AIE_DEV void device_reset_draws(const DevCfg &c, Env &e, const StepScratch &s, R
 
 // What the step kernel does when an env finishes with auto_reset on and reset_mode == 1, after the snapshot restore.
 template <bool EXT = false>
-AIE_DEV_NOINLINE void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane) {
+AIE_DEV_NOINLINE void device_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scratch, int lane,
+                                       const double *dyn_prob = nullptr, double *dyn_work = nullptr) {
     Env e = env_view(rec, grec, c);
     StepScratch s = step_scratch_view(scratch, c);
     Rng r; r.mt = e.mt; r.pos = e.hdr[HDR_MT_POS]; r.lane = lane;
     wsync();
-    device_reset_draws<EXT>(c, e, s, r);
+    device_reset_draws<EXT>(c, e, s, r, dyn_prob, dyn_work);
     if (lane == 0) e.hdr[HDR_MT_POS] = r.pos;
     wsync();
 }

@@ -158,6 +158,16 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     c.split_water_row = u.split_water_row; c.split_top_ranks = u.split_top_ranks;
     if (c.split_layout && (c.split_water_row < 1 || c.split_water_row >= c.H - 1)) return bad("split_water_row outside the world");
     if (c.split_layout && c.fixed_four) return bad("split_layout does not support fixed_four_skill_and_loc");
+    c.dyn_layout = (c.reset_mode == 1) ? u.dyn_layout : 0;
+    if (c.dyn_layout < 0 || c.dyn_layout > 2) return bad("unknown dyn_layout");
+    if (c.dyn_layout && !u.dyn_prob) return bad("dyn_layout needs the source probability maps (dyn_prob)");
+    if (c.dyn_layout && c.fixed_four) return bad("dynamic layouts have no fixed_four_skill_and_loc");
+    c.dyn_checker = u.dyn_checker ? 1 : 0;
+    for (int i = 0; i < 2; i++) {
+        c.dyn_cov[i] = u.dyn_coverage[i]; c.dyn_clump[i] = u.dyn_clump[i];
+        if (c.dyn_layout && !(c.dyn_cov[i] > 0.0 && c.dyn_cov[i] < 1.0 && c.dyn_clump[i] > 0.0 && c.dyn_clump[i] <= 1.0))
+            return bad("dyn_coverage must be in (0, 1) and dyn_clump in (0, 1]");
+    }
     c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs || c.split_layout ||
              (c.has[COMP_TAX] && c.tax_model == AIE_TAX_FIXED_RATES && u.tax_annealing) ||
              (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2))) ? 1 : 0;
@@ -293,7 +303,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             // Saez model: current bracket rates [16], their running average [16] and the rates the observations show
             // [16] (float64), kept across resets
             c.off_saez = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_SAEZ) ? take(8 * 48) : 0;
-            c.off_gauss = (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2)) ? take(16) : 0;
+            c.off_gauss = (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2 || c.dyn_layout)) ? take(16) : 0;
             c.off_split_skill = c.split_layout ? take(8 * A) : 0;
             c.keep_bytes = off - c.off_mt;
             c.off_price_hist = take(8 * 2 * A * P);

@@ -154,6 +154,9 @@ struct DevCfg {
     // split_layout device reset: per-replica rank -> build payment table f64[A] in the kept part of the record
     int32_t split_layout, split_water_row, off_split_skill;
     uint64_t split_top_ranks;
+    // dynamic-layout scenarios: device-side layout generation at reset (see aie_config::dyn_layout)
+    int32_t dyn_layout, dyn_checker;
+    double dyn_cov[2], dyn_clump[2];   // [Wood, Stone]
 };
 
 // raw device pointers (mirrors aie_buffers)
@@ -168,6 +171,8 @@ struct DevBufs {
     const uint16_t *tab;
     // optional per-step event log of the first event_envs replicas (dense logs): int32 [event_envs][event_cap + 1][8]
     int32_t *events; int32_t event_envs, event_cap;
+    // dynamic layouts (library-owned): source probability maps f64 [2][HW] and one f64 [HW] work map per env
+    const double *dyn_prob; double *dyn_work;
     // non-zero (aie_set_fused_policy): the observation pass also draws the NEXT step's uniformly random unmasked actions
     // into the action buffers, from the mask limits it has just staged - instead of a separate sampler launch per step
     uint64_t policy_seed;

@@ -264,6 +264,13 @@ class BatchedFoundationEnv:
         self._rs = [np.random.RandomState(s) for s in seeds]
 
     # ------------------------------------------------------------------ reset / step
+    def _has_gauss_state(self):
+        """numpy's legacy Gaussian cache is part of the record when the device reset draws Gaussians (lognormal skills,
+        dynamic layouts): the host stream and the record's copy are kept in step."""
+        sp = self._spec
+        return sp.get("reset_mode", 0) == 1 and (2 in (sp.get("build_skill_dist", 0), sp.get("gather_skill_dist", 0))
+                                                 or bool(sp.get("dyn_layout", 0)))
+
     def _sync_streams_from_device(self):
         """The device advanced each env's numpy-legacy stream while stepping; continue from there
         (the reference's reset() keeps drawing from the same global stream, base_env.py:896-911)."""
@@ -271,8 +278,7 @@ class BatchedFoundationEnv:
         key = st.to_numpy(st.state_view("mt_key")) if hasattr(st, "state_view") else None
         pos = st.to_numpy(st.state_view("mt_pos")) if hasattr(st, "state_view") else None
         gauss = None
-        if key is not None and self._spec.get("reset_mode", 0) == 1 and 2 in (self._spec.get("build_skill_dist", 0),
-                                                                             self._spec.get("gather_skill_dist", 0)):
+        if key is not None and self._has_gauss_state():
             gauss = st.to_numpy(st.state_view("gauss_state"))   # the device reset may have consumed / refilled the cache
         for e, rs in enumerate(self._rs):
             if key is None:
@@ -325,7 +331,7 @@ class BatchedFoundationEnv:
             pos = int(st.to_numpy(st.state_view("mt_pos")[e]))
             s = self._rs[e].get_state()
             has_g, val_g = s[3], s[4]
-            if self._spec.get("reset_mode", 0) == 1 and 2 in (self._spec.get("build_skill_dist", 0), self._spec.get("gather_skill_dist", 0)):
+            if self._has_gauss_state():
                 g = st.to_numpy(st.state_view("gauss_state")[e])
                 has_g, val_g = int(g[1] != 0.0), float(g[0])
             self._rs[e].set_state((s[0], np.asarray(key, np.uint32), pos, has_g, val_g))
@@ -348,7 +354,7 @@ class BatchedFoundationEnv:
                 else:
                     import torch
                     v[e] = torch.as_tensor(val, device=v.device).to(v.dtype)
-            if self._spec.get("reset_mode", 0) == 1 and 2 in (self._spec.get("build_skill_dist", 0), self._spec.get("gather_skill_dist", 0)):
+            if self._has_gauss_state():
                 g = st.state_view("gauss_state")
                 vals = np.array([ss[4], float(ss[3])])
                 if isinstance(g, np.ndarray):

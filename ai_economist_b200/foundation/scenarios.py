@@ -277,10 +277,27 @@ class Uniform(BaseScenario):
         self._component_resets(rs, st)
         return st
 
+    dyn_layout_kind = 1   # aie_config.dyn_layout: the device-side twin of _generate_layout (0: none)
+
     def scenario_spec_fields(self):
         d = super().scenario_spec_fields()
         d.update(has_water=0, regen_weight=[self.regen["Stone"], self.regen["Wood"]],
                  regen_halfwidth=[self.regen_halfwidth["Stone"], self.regen_halfwidth["Wood"]])
+        # device-side reset with reference semantics (auto_reset): clumped layout + random-order placement + skills
+        dists = {"none": 0, "pareto": 1, "lognormal": 2}
+        comps = {c.name: c for c in self.env.components}
+        b, g = comps.get("Build"), comps.get("Gather")
+        ok = self.dyn_layout_kind and (b is None or b.skill_dist in dists) and (g is None or g.skill_dist in dists)
+        if ok:
+            d.update(reset_mode=1, dyn_layout=int(self.dyn_layout_kind), dyn_checker=int(self.checker),
+                     dyn_coverage=[self.coverage["Wood"], self.coverage["Stone"]],
+                     dyn_clump=[float(1 - np.clip(self.clumpiness["Wood"], 0.0, 0.99)),
+                                float(1 - np.clip(self.clumpiness["Stone"], 0.0, 0.99))],
+                     dyn_prob=[np.asarray(self.source_prob_maps["Wood"], np.float64).tolist(),
+                               np.asarray(self.source_prob_maps["Stone"], np.float64).tolist()],
+                     build_skill_dist=dists.get(b.skill_dist, 0) if b else 0,
+                     gather_skill_dist=dists.get(g.skill_dist, 0) if g else 0,
+                     payment_max_skill_multiplier=b.payment_max_skill_multiplier if b else 1)
         return d
 
 
@@ -289,6 +306,7 @@ class MultiZone(Uniform):
     """Wood / stone / mixed source zones on a shuffled partition grid (dynamic_layout.py:706-873).  The zone
     assignment is re-shuffled from the env's stream at every reset, before the clumped layout is drawn."""
     name = "multi_zone/simple_wood_and_stone"
+    dyn_layout_kind = 0   # the zone assignment is re-shuffled at every reset: auto-reset restores the load-time snapshot
 
     def __init__(self, env, num_partitions_row=8, num_partitions_col=8, num_wood_zones=6, num_stone_zones=6,
                  num_wood_and_stone_zones=4, **kw):
@@ -335,6 +353,7 @@ class Quadrant(Uniform):
     stone towards the left columns (dynamic_layout.py:876-1021)."""
     name = "quadrant/simple_wood_and_stone"
     required_entities = Uniform.required_entities + ["Water"]
+    dyn_layout_kind = 2
 
     def __init__(self, env, **kw):
         super().__init__(env, **kw)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AIE_ABI_VERSION 3
+#define AIE_ABI_VERSION 4
 
 #define AIE_MAX_COMPONENTS 8
 #define AIE_MAX_BRACKETS 16
@@ -129,6 +129,19 @@ typedef struct aie_config {
      * re-places everybody - the agents at the ranks in split_top_ranks above split_water_row, the others below */
     int32_t split_layout, split_water_row;
     uint64_t split_top_ranks;       /* bit i: the i-th agent of the random order starts above the water row */
+    /* ABI 4.  Device-side reset of the dynamic-layout scenarios (uniform/..., quadrant/...): with reset_mode == 1 an
+     * auto-reset also re-draws the clumped source layout from the env's own numpy stream exactly as
+     * Uniform.reset_starting_layout does (scenarios/simple_wood_and_stone/dynamic_layout.py:313-392: np.random.rand
+     * noise thinned by 0.9 until the clumped coverage is reached, then repeated growth by a random 7x7 kernel convolved
+     * - scipy.signal.convolve2d, 'same' - with the candidate map plus Gaussian noise; up to 100 attempts until both
+     * coverages are within 1.4x of their targets), then places the agents in a random order (:418-429). */
+    int32_t dyn_layout;             /* 0: layout fixed at load time; 1: Uniform generator; 2: Quadrant (generator, then
+                                       resources cleared on the two water lines, dynamic_layout.py:992-1030) */
+    int32_t dyn_checker;            /* checker_source_blocks: sources only on cells with (row + col) odd (:387-392) */
+    double dyn_coverage[2];         /* target coverage [Wood, Stone] (doubled when checkered, :181-186) */
+    double dyn_clump[2];            /* 1 - clip(clumpiness, 0, 0.99), [Wood, Stone] */
+    const double *dyn_prob;         /* HOST pointer: source probability maps float64 [2][height][width] (Wood, Stone),
+                                       copied by aie_create (source_prob_maps, :289-308 / :960-990) */
 } aie_config;
 
 /* Sizes the caller needs to allocate the device buffers. */

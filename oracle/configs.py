@@ -275,3 +275,28 @@ EDGE_CONFIGS = {
         n_agents=33, world_size=[12, 37], episode_length=30, starting_agent_coin=30,
         starting_wood_coverage=0.10, starting_stone_coverage=0.10, **_BASE),
 }
+
+# device-side reset of the dynamic-layout scenarios: every reset draws a new clumped layout (np.random.rand thinning, then
+# randn + convolve2d growth) and places the agents in a random order (dynamic_layout.py:313-429)
+CONFIGS["uniform_reset"] = dict(
+    scenario_name="uniform/simple_wood_and_stone",
+    components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                ("Gather", dict(skill_dist="pareto"))],
+    n_agents=5, world_size=[18, 22], episode_length=30,
+    multi_action_mode_agents=False, multi_action_mode_planner=True,
+    flatten_observations=True, flatten_masks=True,
+    starting_agent_coin=10, starting_wood_coverage=0.12, starting_stone_coverage=0.10,
+    wood_regen_weight=0.3, stone_regen_weight=0.2)
+# Quadrant: normalised probability maps, water lines, checkered sources, lognormal skills (the Gaussian cache is shared
+# between the layout generator and the skill draws)
+CONFIGS["quadrant_reset"] = dict(
+    scenario_name="quadrant/simple_wood_and_stone",
+    components=[("Build", dict(skill_dist="lognormal", payment_max_skill_multiplier=2)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                ("Gather", dict(skill_dist="lognormal"))],
+    n_agents=6, world_size=[21, 21], episode_length=28,
+    multi_action_mode_agents=False, multi_action_mode_planner=True,
+    flatten_observations=True, flatten_masks=True,
+    starting_agent_coin=10, starting_wood_coverage=0.08, starting_stone_coverage=0.08,
+    wood_regen_weight=0.04, stone_regen_weight=0.04, checker_source_blocks=True)

@@ -46,6 +46,8 @@ PLAN = [
     ("lognormal_reset", 1001, 95, 10),
     ("split_reset", 1001, 90, 10),
     ("us_federal_annealed_reset", 1001, 90, 5),
+    ("uniform_reset", 1001, 100, 10),
+    ("quadrant_reset", 1001, 95, 7),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

@@ -43,6 +43,7 @@ int wait_slice(aie_env *, int k);
 double slice_device_ms(aie_env *, int k);
 int mark_call_start(aie_env *, void *stream);
 void *const_upload(const void *host, size_t bytes);
+void *dev_alloc(size_t bytes);
 void const_free(void *dev);
 int covid_launch_reset(aie_covid_env *, void *stream);
 int covid_launch_step(aie_covid_env *, void *stream);
@@ -118,7 +119,11 @@ int launch_step(aie_env *env, int emit_obs, void *) {
             memcpy(rec + c.off_price_hist, b.state0 + (size_t)e * c.rec_bytes + c.off_price_hist, c.rec_bytes - c.off_price_hist);
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
             hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
-            if (c.reset_mode == 1) { if (c.ext) device_reset_env<true>(c, rec, rec, env->be.scratch.data(), 0); else device_reset_env<false>(c, rec, rec, env->be.scratch.data(), 0); }
+            if (c.reset_mode == 1) {
+                double *work = b.dyn_work ? b.dyn_work + (size_t)e * c.HW : nullptr;
+                if (c.ext) device_reset_env<true>(c, rec, rec, env->be.scratch.data(), 0, b.dyn_prob, work);
+                else device_reset_env<false>(c, rec, rec, env->be.scratch.data(), 0, b.dyn_prob, work);
+            }
             finish_reset_env(c, rec, rec, env->be.scratch.data(), 0);
         }
     }
@@ -158,6 +163,7 @@ int launch_sample(aie_env *env, uint64_t seed, void *) {
     return AIE_OK;
 }
 void *const_upload(const void *host, size_t bytes) { void *d = malloc(bytes ? bytes : 1); if (d) memcpy(d, host, bytes); return d; }
+void *dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
 void const_free(void *dev) { free(dev); }
 int covid_launch_reset(aie_covid_env *env, void *) {
     for (int e = 0; e < env->n_envs; e++) covid_reset_env(env->cfg, e, env->bufs, 0, 1, false);

@@ -103,6 +103,21 @@ def test_fuzz_device_reset_matches_live_reference(i):
 @needs_reference
 @pytest.mark.reference
 @pytest.mark.parametrize("i", range(N_CASES))
+def test_fuzz_dynamic_layout_device_reset_matches_live_reference(i):
+    """uniform / quadrant: the device generates a new clumped layout at every auto-reset (rand thinning, randn + convolve2d
+    growth, coverage retries, checkering, water lines) and must land on the reference's maps, placements and stream."""
+    import fuzz_device_reset_vs_reference as fr
+
+    cfg = _configs(11, draw=fr.random_dynamic_config)[i]
+    try:
+        fr.run_one(cfg, seed=600 + i, episodes=3)
+    except TimeoutError as ex:   # the reference's own placement loop giving up on a crowded map
+        pytest.skip(repr(ex))
+
+
+@needs_reference
+@pytest.mark.reference
+@pytest.mark.parametrize("i", range(N_CASES))
 def test_fuzz_reference_api_matches_live_reference(i):
     import fuzz_reference_api_vs_reference as fa
 

@@ -1,7 +1,8 @@
 """Randomised multi-episode fuzz (build container only): the device-side reference-exact reset (auto_reset, 1-lane
 emulation of the device source) against the LIVE reference, which calls env.reset() between episodes on one continuing
 global numpy stream.  layout_from_file configurations with skill_dist in {none, pareto, lognormal}, with / without
-fixed_four_skill_and_loc.   python tools/fuzz_device_reset_vs_reference.py [n] [seed]"""
+fixed_four_skill_and_loc; with --dynamic: uniform / quadrant scenarios (device-side layout generation).
+python tools/fuzz_device_reset_vs_reference.py [n] [seed] [--dynamic]"""
 import os
 import sys
 import traceback
@@ -46,6 +47,24 @@ def random_config(rng):
                 multi_action_mode_agents=bool(rng.rand() < 0.3), multi_action_mode_planner=True,
                 flatten_observations=True, flatten_masks=True,
                 energy_warmup_constant=float(rng.choice([0, 4])), energy_warmup_method="decay")
+
+
+def random_dynamic_config(rng):
+    """uniform/... and quadrant/... : every reset generates a new clumped layout on the device (dynamic_layout.py:313-429)."""
+    fam = str(rng.choice(["uniform", "quadrant"]))
+    H = int(rng.randint(9, 27)); W = H if fam == "quadrant" else int(rng.randint(9, 27))
+    A = int(rng.choice([2, 3, 5, 8]))
+    comps = [("Build", dict(skill_dist=str(rng.choice(["none", "pareto", "lognormal"])), payment_max_skill_multiplier=int(rng.randint(1, 4)))),
+             ("ContinuousDoubleAuction", dict(max_num_orders=int(rng.choice([1, 5])))),
+             ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto", "lognormal"]))))]
+    return dict(scenario_name=fam + "/simple_wood_and_stone", components=comps, n_agents=A, world_size=[H, W],
+                episode_length=int(rng.choice([6, 12])), starting_agent_coin=float(rng.choice([0, 10])),
+                multi_action_mode_agents=bool(rng.rand() < 0.3), multi_action_mode_planner=True,
+                flatten_observations=True, flatten_masks=True,
+                starting_wood_coverage=float(rng.choice([0.05, 0.1, 0.15])), starting_stone_coverage=float(rng.choice([0.05, 0.1])),
+                wood_clumpiness=float(rng.choice([0.0, 0.35, 0.8])), stone_clumpiness=float(rng.choice([0.2, 0.5, 1.0])),
+                gradient_steepness=float(rng.choice([1, 4, 8])), checker_source_blocks=bool(rng.rand() < 0.3),
+                wood_regen_weight=float(rng.choice([0.05, 0.5])), stone_regen_weight=float(rng.choice([0.05, 0.5])))
 
 
 def run_one(cfg, seed, episodes=4):
@@ -99,11 +118,13 @@ def run_one(cfg, seed, episodes=4):
 
 
 if __name__ == "__main__":
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    n = int(args[0]) if len(args) > 0 else 30
+    rng = np.random.RandomState(int(args[1]) if len(args) > 1 else 0)
     bad, kinds = 0, {}
+    dynamic = "--dynamic" in sys.argv
     for i in range(n):
-        cfg = random_config(rng)
+        cfg = (random_dynamic_config if dynamic else random_config)(rng)
         kinds[cfg["scenario_name"].split("/")[0]] = kinds.get(cfg["scenario_name"].split("/")[0], 0) + 1
         try:
             run_one(cfg, seed=500 + i)
