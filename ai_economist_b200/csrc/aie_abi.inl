@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -41,6 +42,8 @@ struct aie_env {
     std::vector<aie_flat_field> flat_layout[3];
     void *dyn_prob_dev = nullptr, *dyn_work_dev = nullptr;   // dynamic layouts: probability maps, per-env work maps
     aie::HostPool *pool = nullptr;   // aie_step_host_compact: created on first use
+    std::vector<signed char> item_node;   // NUMA node of every work item's destination (cached per output pointer)
+    const void *item_node_key = nullptr; size_t item_node_n = 0;
     double host_timing[AIE_HOST_TIMING_WORDS] = {};   // last aie_step_host_compact call (aie_get_host_timing)
 };
 
@@ -288,10 +291,29 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     if (want < 1) want = 1;
     if (want > aie::AIE_MAX_HOST_THREADS) want = aie::AIE_MAX_HOST_THREADS;
-    if (!env->pool || env->pool->size() != want - 1) { delete env->pool; env->pool = new aie::HostPool(want - 1); }
+    // AIE_E2E_NUMA: 0 unpinned threads, one queue; 1 node-local items first, then help the other nodes; 2 node-local only
+    // (default: measured fastest on a two-socket host, profiles/r02g_e2e_probe_c2.log - remote non-temporal stores cost
+    // more than the idle threads would add)
+    int numa_mode = 2;
+    if (const char *v = getenv("AIE_E2E_NUMA")) numa_mode = atoi(v);
+    if (numa_mode < 0 || numa_mode > 2) numa_mode = 2;
+    if (!env->pool || env->pool->size() != want - 1 || env->pool->mode() != numa_mode) {
+        delete env->pool; env->pool = new aie::HostPool(want - 1, numa_mode); env->item_node_key = nullptr;
+    }
+    if (numa_mode && env->pool->nodes() > 1 && o->obs_agent_map &&
+        (env->item_node_key != (const void *)o->obs_agent_map || env->item_node_n != (size_t)n_items)) {
+        env->item_node.assign((size_t)n_items, -1);   // where the (dominant) agent-map rows of every item live
+        for (int i = 0; i < n_items; i++)
+            env->item_node[i] = (signed char)aie::numa_node_of(o->obs_agent_map + ((size_t)i * chunk + chunk / 2) * (size_t)L.n_a_map);
+        env->item_node_key = (const void *)o->obs_agent_map; env->item_node_n = (size_t)n_items;
+    }
+    const signed char *item_node = (numa_mode && env->item_node_n == (size_t)n_items && env->item_node_key == (const void *)o->obs_agent_map)
+                                       ? env->item_node.data() : nullptr;
     const aie_host_out out = *o;
     std::atomic<int> failed{0};
     std::atomic<int64_t> first_slice_us{-1}, last_slice_us{-1}, wait_us{0}, busy_us{0};
+    std::mutex overflow_m;
+    std::vector<size_t> overflow;   // envs whose index planes hold more non-zero elements than the compact record carries
     auto job = [&](int item) {
         const int k = item / items_per_slice;
         const clk::time_point w0 = clk::now();
@@ -300,12 +322,16 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
         if (item % items_per_slice == 0 && (k == 0 || k == n_slices - 1))
             (k == 0 ? first_slice_us : last_slice_us).store((int64_t)(1e3 * ms_since(w1)));
         const size_t hi = (size_t)(item + 1) * chunk < E ? (size_t)(item + 1) * chunk : E;
-        for (size_t e = (size_t)item * chunk; e < hi; e++) aie::expand_env(L, host + e * (size_t)L.bytes, e, out);
+        for (size_t e = (size_t)item * chunk; e < hi; e++)
+            if (!aie::expand_env(L, host + e * (size_t)L.bytes, e, out, env->tables.w, env->tables.w + c.tab_cslot)) {
+                std::lock_guard<std::mutex> g(overflow_m);
+                overflow.push_back(e);
+            }
         const clk::time_point w2 = clk::now();
         wait_us.fetch_add(std::chrono::duration_cast<std::chrono::microseconds>(w1 - w0).count());
         busy_us.fetch_add(std::chrono::duration_cast<std::chrono::microseconds>(w2 - w1).count());
     };
-    env->pool->run(n_items, job);
+    env->pool->run(n_items, item_node, job);
     const double t_expanded = ms_since(clk::now());
     double *ht = env->host_timing;
     ht[0] = t_enqueued; ht[1] = 1e-3 * first_slice_us.load(); ht[2] = 1e-3 * (n_slices > 1 ? last_slice_us.load() : first_slice_us.load());
@@ -316,10 +342,15 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     if (const char *rep = getenv("AIE_E2E_REPEAT_EXPAND")) {   // tuning aid: the expansion alone, every slice already on the host
         const int n = atoi(rep);
         const clk::time_point r0 = clk::now();
-        for (int i = 0; i < n; i++) env->pool->run(n_items, job);
+        for (int i = 0; i < n; i++) env->pool->run(n_items, item_node, job);
         ht[12] = n > 0 ? std::chrono::duration<double, std::milli>(clk::now() - r0).count() / n : 0.0;
     }
     if (failed.load()) return fail(AIE_ECUDA, "aie_step_host_compact: waiting for a transfer slice failed");
+    for (size_t e : overflow) {   // rare: fetch those envs' index planes as they are
+        if (out.obs_agent_idx) { rc = aie::be::download(env, out.obs_agent_idx + e * L.n_a_idx, env->bufs.a_idx + e * L.n_a_idx, 2 * (size_t)L.n_a_idx, stream); if (rc != AIE_OK) return rc; }
+        if (out.obs_planner_idx && L.n_p_idx) { rc = aie::be::download(env, out.obs_planner_idx + e * L.n_p_idx, env->bufs.p_idx + e * L.n_p_idx, 2 * (size_t)L.n_p_idx, stream); if (rc != AIE_OK) return rc; }
+    }
+    env->host_timing[13] = (double)overflow.size();
     rc = aie::be::sync(env, stream);
     if (rc != AIE_OK) return rc;
     return AIE_OK;

@@ -4,7 +4,14 @@
 // groups go out with non-temporal stores (no read-for-ownership of the destination lines): whole 64-byte lines from a
 // 16-bit mask with AVX-512, 16-byte groups from a 16-entry nibble table with SSE2.
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
 #if defined(__x86_64__) || defined(__i386__)
 #include <immintrin.h>
 #endif
@@ -60,5 +67,61 @@ void expand_bits(const uint32_t *src, int n, float *dst) { for (int i = 0; i < n
 void expand_fence() {}
 const char *expand_isa() { return "scalar"; }
 #endif
+
+
+// ---- NUMA placement of the expansion (Linux; everything degrades to "unknown node" elsewhere) ------------------------
+// The expansion is bound by the host's memory controllers: a thread writing to the other socket's memory goes through the
+// inter-socket link.  The pool therefore pins its workers to nodes and hands each work item to the node its destination
+// pages live on (get_mempolicy(MPOL_F_NODE | MPOL_F_ADDR), no libnuma needed).
+int numa_node_of(const void *addr) {
+#if defined(__linux__) && defined(SYS_get_mempolicy)
+    int node = -1;
+    if (syscall(SYS_get_mempolicy, &node, nullptr, 0UL, const_cast<void *>(addr), 3UL /* MPOL_F_NODE | MPOL_F_ADDR */) == 0) return node;
+#endif
+    (void)addr;
+    return -1;
+}
+int numa_node_count() {
+#if defined(__linux__)
+    int n = 0;
+    for (; n < 64; n++) {
+        char path[96];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", n);
+        if (access(path, R_OK) != 0) break;
+    }
+    return n > 0 ? n : 1;
+#else
+    return 1;
+#endif
+}
+bool pin_current_thread_to_node(int node) {
+#if defined(__linux__)
+    char path[96];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    char buf[1024];
+    const bool ok = fgets(buf, sizeof(buf), f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int any = 0;
+    for (char *p = buf; *p;) {   // "0-31,64-95"
+        char *end;
+        long a = strtol(p, &end, 10);
+        if (end == p) break;
+        long b = a;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, &set); any = 1; }
+        p = (*end == ',') ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    return any && sched_setaffinity(0, sizeof(set), &set) == 0;
+#else
+    (void)node;
+    return false;
+#endif
+}
 
 }  // namespace aie

@@ -276,7 +276,15 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         float *lut = (float *)(tb.w + c.tab_lut);   // nibble -> four floats (bit k of the nibble -> element k)
         for (int k = 0; k < 16; k++) for (int j = 0; j < 4; j++) lut[4 * k + j] = (float)((k >> j) & 1);
         c.tab_n = c.tab_lut + 128;
-        if (c.tab_n > TAB_WORDS) return bad("internal: table overflow");
+        // compacted transfer: every entry of the agents' flat program gets its index inside its class
+        c.tab_cslot = c.tab_n;
+        c.cf_n_sh = c.cf_n_ag = c.cf_n_cnt = 0;
+        for (int j = 0; j < c.Fa; j++) {
+            const int kind = AIE_FLAT_KIND(prog_a[j]);
+            int &n = kind == FK_SHARED ? c.cf_n_sh : (kind == FK_AGENT ? c.cf_n_ag : c.cf_n_cnt);
+            tb.w[c.tab_cslot + j] = (uint16_t)n++;
+        }
+        if (c.tab_cslot + c.Fa > TAB_WORDS) return bad("internal: table overflow");
     }
     // record layout
     {

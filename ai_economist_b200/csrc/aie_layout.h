@@ -135,6 +135,8 @@ struct DevCfg {
     int32_t sh_curr_rates, sh_last_incomes, sh_full, sh_count;  // offsets / size of the shared float staging array
     int32_t tab_p, tab_pa, tab_m, tab_n;               // offsets (u16 words) into the program table, total words (even)
     int32_t tab_hoff, tab_seg, tab_lut;                // more tables in the same array: histogram offsets [4P], mask segments, nibble -> float4 table (16-byte aligned)
+    int32_t tab_cslot;                                 // [Fa] (behind tab_n, not staged): index of agent-flat entry j inside its class (shared / agent scalar / order count), for the compacted transfer
+    int32_t cf_n_sh, cf_n_ag, cf_n_cnt;                // entries per class of the agents' flat vector
     int32_t seg_lo[10];                                // mask segments of action subspace si: [seg_lo[si], seg_lo[si + 1]) (single-action agents: si = 0 covers everything)
     uint32_t HW_magic, ww_magic, Fa_magic, Fpa_magic, Na_magic;  // floor(2^32 / n) + 1: run index -> (row, column)
     uint32_t wcu_magic;     // floor(2^32 / (wc_stride / 8)) + 1: (agent, 8-cell unit) pairs of a chunk
@@ -179,7 +181,7 @@ struct DevBufs {
 };
 // compact program table: [agent flat (Fa) | planner flat (Fp) | p<i> flat (Fpa) | agent mask (Na)], offsets in DevCfg
 // then: histogram offsets u16 [4P <= 128], mask segments u16 [<= 64], nibble -> float4 table (64 floats = 128 u16)
-constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK + 128 + 64 + 128 + 16;
+constexpr int TAB_WORDS = 2 * MAX_FLAT + 16 + MAX_MASK + 128 + 64 + 128 + 16 + MAX_FLAT;
 struct Tables { uint16_t w[TAB_WORDS]; };
 
 }  // namespace aie

@@ -359,7 +359,7 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     import ctypes as C
 
     torch, args, rank, world, dev = ctx.torch, ctx.args, ctx.rank, ctx.world, ctx.dev
-    from ai_economist_b200 import foundation, workloads as wl
+    from ai_economist_b200 import foundation, hostmem, workloads as wl
     from ai_economist_b200.sharding import shard_seeds
 
     w = WORKLOADS[key]
@@ -465,7 +465,9 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     for nm in ["obs_agent_map", "obs_agent_idx", "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx",
                "obs_planner_flat", "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]:
         if nm in st.buf:
-            t = torch.empty(st.buf[nm].shape, dtype=st.buf[nm].dtype, pin_memory=True)
+            # pinned host tensors from the package's allocator: one contiguous block of replicas per NUMA node, which is
+            # what the node-pinned expansion threads of aie_step_host_compact are matched to (ai_economist_b200/hostmem.py)
+            t = hostmem.pinned_empty(st.buf[nm].shape, st.buf[nm].dtype, numa="split" if e2e_mode == "compact" else None)
             out_host[nm] = t
             out_ptrs[nm] = C.c_void_p(t.data_ptr())
             d2h += t.numel() * t.element_size()
@@ -496,7 +498,8 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
                    what="aie_step_host: pinned host actions in, every observation/mask/reward/done tensor copied back "
                         "to pinned host memory each step (PCIe-bound)")
     else:
-        e2e.update(d2h_bytes_per_step=E * st.compact_bytes_per_env(), host_tensor_bytes_per_step=d2h,
+        e2e.update(d2h_bytes_per_step=E * st.compact_bytes_per_env(), host_tensor_bytes_per_step=d2h, host_threads=e2e_threads,
+                   last_call_timing_ms={k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.host_timing().items()},
                    what="aie_step_host_compact: pinned host actions in; every observation/mask/reward/done tensor lands "
                         "in pinned host memory each step, bit-/byte-packed over PCIe and expanded by host threads "
                         "(same bytes in the host tensors as the plain path)")
@@ -732,6 +735,8 @@ def main():
     if clocks:
         clocks.start()
     fn = measure_covid if key == "c4" else measure_gtb
+    if args.e2e_threads == 0:   # expansion threads of the e2e leg: this rank's share of the host's hardware threads
+        args.e2e_threads = max(8, host_cores() // max(1, world))
     kw = {} if key == "c4" else dict(e2e_mode=args.e2e_mode, e2e_threads=args.e2e_threads)
     res = fn(ctx, key, args.steps, args.warmup, with_cpu, clocks=clocks, e2e_steps=args.e2e_steps, **kw)
     clk = clocks.stop() if clocks else None

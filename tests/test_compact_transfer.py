@@ -67,3 +67,17 @@ def test_emulated_compact_transfer_delivers_the_same_bytes(cfg):
 @pytest.mark.parametrize("cfg", CASES)
 def test_cuda_compact_transfer_delivers_the_same_bytes(cfg):
     _check(cfg, 300, device="cuda:0")
+
+
+def test_emulated_compact_transfer_index_plane_overflow_is_fetched_directly(monkeypatch):
+    """An env whose index planes hold more non-zero elements than the compact record carries is completed by a direct
+    copy of those planes (capacities forced down to 4 entries here, so every env takes that path)."""
+    from tests.emu.emu_stepper import emu_factory
+    monkeypatch.setenv("AIE_COMPACT_TINY_CAPS", "1")
+    _check("c3_paper_tax", 4, factory=emu_factory, threads=(2,))
+
+
+@pytest.mark.gpu
+def test_cuda_compact_transfer_index_plane_overflow_is_fetched_directly(monkeypatch):
+    monkeypatch.setenv("AIE_COMPACT_TINY_CAPS", "1")
+    _check("c1_tutorial", 64, device="cuda:0", threads=(4,))

@@ -6,7 +6,7 @@ import os
 import sys
 import time
 
-os.environ.setdefault("AIE_E2E_REPEAT_EXPAND", "3")
+os.environ.setdefault("AIE_E2E_REPEAT_EXPAND", "2")
 import numpy as np
 import torch
 
@@ -24,14 +24,16 @@ names = ["obs_agent_map", "obs_agent_idx", "obs_agent_flat", "mask_agent", "obs_
          "obs_planner_flat", "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]
 seg_a, seg_p = wl.mask_segments(env.spec, "a"), wl.mask_segments(env.spec, "p")
 out = {"workload": key, "runs": []}
-for interleave in (False, True):
-    host = {n: hostmem.pinned_empty(st.buf[n].shape, st.buf[n].dtype, interleave=interleave) for n in names if n in st.buf}
+for interleave, numa_mode in (("plain", "2"), ("split", "2"), ("split", "1")):
+    os.environ["AIE_E2E_NUMA"] = numa_mode
+    host = {n: hostmem.pinned_empty(st.buf[n].shape, st.buf[n].dtype, numa=(interleave if interleave != "plain" else None))
+            for n in names if n in st.buf}
     ptrs = {n: C.c_void_p(t.data_ptr()) for n, t in host.items()}
     act_a = torch.zeros(st.buf["actions_agent"].shape, dtype=torch.int32, pin_memory=True)
     act_p = torch.zeros(st.buf["actions_planner"].shape, dtype=torch.int32, pin_memory=True)
     host["mask_agent"].copy_(st.buf["mask_agent"]); host["mask_planner"].copy_(st.buf["mask_planner"])
     rng = np.random.RandomState(0)
-    for threads in (16, 32, 64, 128):
+    for threads in (32, 64, 96, 128):
         ts, tim = [], []
         for i in range(8):
             act_a.copy_(torch.from_numpy(wl.sample_from_masks(host["mask_agent"].numpy(), seg_a, rng)))
@@ -45,7 +47,7 @@ for interleave in (False, True):
             tim.append(st.host_timing())
         med = sorted(ts[2:])[len(ts[2:]) // 2]
         t = tim[-1]
-        r = dict(interleave=interleave, threads=threads, ms=1e3 * med, rate=cfg[1] * env.n_agents / med,
+        r = dict(alloc=interleave, numa_mode=numa_mode, threads=threads, ms=1e3 * med, rate=cfg[1] * env.n_agents / med,
                  before_transfer=t["before_transfer"], first_slice=t["first_slice"], last_slice=t["last_slice"], expanded=t["expanded"],
                  d2h_MB=t["d2h_bytes"] / 1e6, wait_sum=t["wait_sum"], busy_sum=t["busy_sum"], first_dev=t["first_slice_dev"],
                  last_dev=t["last_slice_dev"], expand_only=t["expand_only"])
