@@ -9,7 +9,7 @@ MAX_COMPONENTS, MAX_BRACKETS, MAX_RATES = 8, 16, 64
 AIE_OK = 0
 
 COMPONENT_KIND = {"Build": 0, "ContinuousDoubleAuction": 1, "Gather": 2, "PeriodicBracketTax": 3,
-                  "WealthRedistribution": 4}
+                  "WealthRedistribution": 4, "SimpleLabor": 5}
 
 CSRC_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 DEFAULT_LIB = os.path.join(CSRC_DIR, "libaie_b200.so")
@@ -46,6 +46,8 @@ class AieConfig(C.Structure):
         ("split_layout", C.c_int32), ("split_water_row", C.c_int32), ("split_top_ranks", C.c_uint64),
         ("dyn_layout", C.c_int32), ("dyn_checker", C.c_int32), ("dyn_coverage", C.c_double * 2), ("dyn_clump", C.c_double * 2),
         ("dyn_prob", C.c_void_p),
+        ("scenario_kind", C.c_int32), ("agent_reward_type", C.c_int32), ("labor_exponent", C.c_double), ("labor_cost", C.c_double),
+        ("labor_mask_first_step", C.c_int32), ("labor_skill_scale", C.c_double),
     ]
 
 
@@ -236,6 +238,12 @@ def config_from_spec(spec, auto_reset=True):
     cfg.split_layout = int(spec.get("split_layout", 0))
     cfg.split_water_row = int(spec.get("split_water_row", 0))
     cfg.split_top_ranks = int(spec.get("split_top_ranks", 0))
+    cfg.scenario_kind = int(spec.get("scenario_kind", 0))
+    cfg.agent_reward_type = int(spec.get("agent_reward_type", 0))
+    cfg.labor_exponent = float(spec.get("labor_exponent", 2.0))
+    cfg.labor_cost = float(spec.get("labor_cost", 1.0))
+    cfg.labor_mask_first_step = int(spec.get("labor_mask_first_step", 1))
+    cfg.labor_skill_scale = float(spec.get("labor_skill_scale", 1.0))
     cfg.dyn_layout = int(spec.get("dyn_layout", 0)) if cfg.reset_mode == 1 else 0
     if cfg.dyn_layout:
         cfg.dyn_checker = int(spec.get("dyn_checker", 0))

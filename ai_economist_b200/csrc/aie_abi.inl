@@ -124,7 +124,7 @@ int aie_get_flat_layout(const aie_env *env, int32_t which, aie_flat_field *out, 
 int aie_bind_buffers(aie_env *env, const aie_buffers *b) {
     if (!env || !b) return fail(AIE_EINVAL, "null argument");
     const aie::DevCfg &c = env->cfg;
-    if (!b->state || !b->state0 || !b->actions_agent || !b->obs_agent_map || !b->obs_agent_idx || !b->obs_agent_flat ||
+    if (!b->state || !b->state0 || !b->actions_agent || (!c.no_spatial && (!b->obs_agent_map || !b->obs_agent_idx)) || !b->obs_agent_flat ||
         !b->mask_agent || !b->obs_planner_flat || (c.Fpa > 0 && !b->obs_planner_agents) || !b->mask_planner || !b->obs_time ||
         !b->reward || !b->done)
         return fail(AIE_EINVAL, "aie_bind_buffers: a required buffer is NULL");

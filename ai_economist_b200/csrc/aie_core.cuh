@@ -321,6 +321,7 @@ AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t
                 else if (slot == MS_BUY1) buy1 = (uint8_t)(idx + 1);
                 else if (slot == MS_SELL0) sell0 = (uint8_t)(idx + 1);
                 else if (slot == MS_SELL1) sell1 = (uint8_t)(idx + 1);
+                else if (EXT && slot == MS_LABOR) move = (uint8_t)(idx + 1);   // hours of labor travel in the Gather slot
                 else if (slot >= MS_G0) move = (uint8_t)(slot - MS_G0 + 1);
             }
         } else
@@ -331,7 +332,7 @@ AIE_DEV void decode_actions(const DevCfg &c, const StepScratch &s, const int32_t
             if (v < 0 || v > c.sub_n[si]) v = 0;  // out-of-range input is treated as NO-OP
             int kind = c.sub_kind[si];
             if (kind == SUB_BUILD) build = (uint8_t)v;
-            else if (kind == SUB_GATHER) move = (uint8_t)v;
+            else if (kind == SUB_GATHER || kind == SUB_LABOR) move = (uint8_t)v;
             else if (kind == SUB_BUY) { if (c.sub_c[si] == 0) buy0 = (uint8_t)v; else buy1 = (uint8_t)v; }
             else { if (c.sub_c[si] == 0) sell0 = (uint8_t)v; else sell1 = (uint8_t)v; }
         }
@@ -940,10 +941,63 @@ AIE_DEV void wealth_step(const DevCfg &c, Env &e, const StepScratch &s, int lane
     wsync();
 }
 
+// ------------------------------------------------------------------------------------------------
+// SimpleLabor (components/simple_labor.py:100-126): action h in 1..100 sets the agent's labor to h hours and pays
+// h * skill into its coin and its cumulative production.  The random order only consumes the permutation draw.
+// Record reuse: skill lives in the build_skill field, production in build_payment.
+// ------------------------------------------------------------------------------------------------
+AIE_DEV void labor_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) {
+    rng_permutation(r, s.perm, c.A);
+    for (int a = r.lane; a < c.A; a += NL) {
+        const int h = s.act_move[a];
+        if (h >= 1 && h <= 100) {
+            const double payoff = h * e.bskill[a];
+            e.labor[a] = (double)h;
+            e.bpay[a] += payoff;
+            e.coin[a] += payoff;
+        }
+    }
+    wsync();
+}
+
+// one-step-economy utilities (one_step_economy.py:264-336; rewards.py:12-70, 84-133): agents coin minus a labor cost,
+// planner a social welfare function over them (weights from the pre-tax incomes = production)
+AIE_DEV void one_step_metrics(const DevCfg &c, const Env &e, double *out, double *tmp, int lane) {
+    const int A = c.A;
+    // coin_eq_times_productivity only looks at the coin endowments: take the planner's value from the family's own routine
+    // (both Gini forms), then replace the agents' utilities
+    double planner = 0.0;
+    if (c.swf == 0) { current_metrics(c, e, out, tmp, lane); planner = out[A]; wsync(); }
+    for (int a = lane; a < A; a += NL) {
+        const double x = e.coin[a] + e.esc_coin[a], l = e.labor[a];
+        double u;
+        if (c.agent_reward_type == 1) {   // coin_minus_labor_cost: x - l ** exponent * coefficient
+            const double lp = c.labor_exponent == 2.0 ? l * l : pow(l, c.labor_exponent);
+            u = x - lp * c.labor_cost;
+        } else {                          // isoelastic_coin_minus_labor (no energy warm-up here)
+            const double uc = (c.eta == 1.0) ? log(fmax(1.0, x)) : ((c.eta == 0.0 ? x : pow(x, 1.0 - c.eta)) - 1.0) / (1.0 - c.eta);
+            u = uc - l * c.labor_cost;
+        }
+        out[a] = u;
+    }
+    wsync();
+    if (c.swf != 0) {   // inv_income_weighted_utility(coin_endowments = pretax incomes, utilities)
+        double wsum_ = 0.0, acc = 0.0;
+        for (int a = 0; a < A; a++) wsum_ += 1.0 / fmax(e.bpay[a], 1.0);
+        for (int a = 0; a < A; a++) acc += out[a] * ((1.0 / fmax(e.bpay[a], 1.0)) / wsum_);
+        planner = acc;
+    }
+    wsync();
+    if (lane == 0) out[A] = planner;
+    wsync();
+}
+
+template <bool EXT = false>
 AIE_DEV void compute_reward(const DevCfg &c, Env &e, const StepScratch &s, double *rew_out, int lane) {
     const int A = c.A;
     double *cur = s.tmp;  // [A+1] new metrics; the second half of tmp is sort / staging scratch
-    current_metrics(c, e, cur, cur + (A + 2), lane);
+    if (EXT && c.one_step) one_step_metrics(c, e, cur, cur + (A + 2), lane);
+    else current_metrics(c, e, cur, cur + (A + 2), lane);
     double *rw_s = cur + (A + 2);  // rewards staged so the mean can be formed in numpy's summation order
     for (int a = lane; a <= A; a += NL) {
         double rw = cur[a] - e.util_prev[a];
@@ -982,13 +1036,15 @@ AIE_DEV void step_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *scr
             case COMP_GATHER: gather_step(c, e, s, r); break;
             case COMP_TAX: tax_step<EXT>(c, e, s, r, lane); break;
             case COMP_WEALTH: wealth_step(c, e, s, lane); break;
+            case COMP_LABOR: if (EXT) labor_step(c, e, s, r); break;
         }
     }
 #if AIE_ON_DEVICE
 #pragma unroll 1
 #endif
-    for (int ri = 0; ri < 2; ri++) regen_resource<EXT>(c, e, 1 - ri, r);  // Wood, then Stone (one inlined copy)
-    compute_reward(c, e, s, rew_out, lane);
+    for (int ri = 0; ri < 2; ri++)   // Wood, then Stone (one inlined copy); the one-step-economy has no map: scenario_step() is empty
+        if (!(EXT && c.one_step)) regen_resource<EXT>(c, e, 1 - ri, r);
+    compute_reward<EXT>(c, e, s, rew_out, lane);
     if (lane == 0) {
         e.hdr[HDR_MT_POS] = r.pos;
         if (done_out) *done_out = (t >= c.T) ? 1 : 0;
@@ -1013,7 +1069,8 @@ AIE_DEV_NOINLINE void finish_reset_env(const DevCfg &c, uint8_t *rec, uint8_t *g
     if (c.has[COMP_TAX] && c.tax_model == 2)
         for (int b = lane; b < 16; b += NL) { e.saez[32 + b] = e.saez[b]; e.saez[b] = e.saez[16 + b]; }
     wsync();
-    current_metrics(c, e, e.util_prev, s.tmp, lane);
+    if (c.one_step) one_step_metrics(c, e, e.util_prev, s.tmp, lane);
+    else current_metrics(c, e, e.util_prev, s.tmp, lane);
     wsync();
 }
 

@@ -69,6 +69,22 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         if (c.has[k]) return bad("duplicate component");
         c.comp[i] = k; c.has[k] = 1;
     }
+    c.one_step = u.scenario_kind == 1 ? 1 : 0;
+    if (u.scenario_kind != 0 && u.scenario_kind != 1) return bad("unknown scenario_kind");
+    if (c.one_step) {   // one_step_economy.py: SimpleLabor (+ PeriodicBracketTax), nothing spatial
+        for (int i = 0; i < c.n_comp; i++)
+            if (c.comp[i] != COMP_LABOR && c.comp[i] != COMP_TAX) return bad("one-step-economy takes SimpleLabor and PeriodicBracketTax only");
+        if (!c.has[COMP_LABOR]) return bad("one-step-economy needs the SimpleLabor component");
+        if (u.agent_reward_type != 0 && u.agent_reward_type != 1) return bad("unknown agent_reward_type");
+        if (u.agent_reward_type == 1 && !(u.labor_exponent > 1.0)) return bad("labor_exponent must be > 1");
+        if (!(u.labor_skill_scale > 0.0)) return bad("labor_skill_scale (payment_max_skill_multiplier) must be > 0");
+        if (u.planner_reward_type == 1) return bad("one-step-economy has no inv_income_weighted_coin_endowments planner reward");
+        if (u.reset_mode != 0) return bad("one-step-economy resets from the snapshot (its reset draws nothing)");
+        if (u.full_observability || u.planner_gets_spatial_info) return bad("one-step-economy has no spatial observations");
+    } else if (c.has[COMP_LABOR]) return bad("SimpleLabor belongs to the one-step-economy scenario");
+    c.no_spatial = c.one_step;
+    c.agent_reward_type = u.agent_reward_type; c.labor_exponent = u.labor_exponent; c.labor_cost = u.labor_cost;
+    c.labor_mask_first = u.labor_mask_first_step ? 1 : 0; c.labor_skill_scale = u.labor_skill_scale;
     c.has_water = u.has_water ? 1 : 0;
     c.M = c.has_water ? 6 : 5;
     c.w = u.obs_range; c.win = 2 * u.obs_range + 1;
@@ -146,14 +162,15 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         if (c.comp[i] == COMP_BUILD) add(SUB_BUILD, 0, 1);
         else if (c.comp[i] == COMP_CDA) { for (int cc = 0; cc < 2; cc++) { add(SUB_BUY, cc, c.P); add(SUB_SELL, cc, c.P); } }
         else if (c.comp[i] == COMP_GATHER) add(SUB_GATHER, 0, 4);
+        else if (c.comp[i] == COMP_LABOR) add(SUB_LABOR, 0, 100);   // simple_labor.py:56 num_labor_hours
     }
     c.n_act_a = c.multi_action ? c.n_sub : 1;
     if (c.n_sub == 0) return bad("mobile agents need at least one action component");
     c.planner_acts = (c.has[COMP_TAX] && c.tax_model == AIE_TAX_MODEL_WRAPPER && !c.disable_taxes) ? 1 : 0;
     c.planner_single = (c.planner_acts && u.single_action_planner) ? 1 : 0;
     c.full_obs = u.full_observability ? 1 : 0;
-    c.a_map_elems = c.full_obs ? c.M * c.HW : (c.M + 1) * c.win * c.win;
-    c.a_idx_elems = c.full_obs ? 2 * c.HW : 2 * c.win * c.win;
+    c.a_map_elems = c.no_spatial ? 0 : (c.full_obs ? c.M * c.HW : (c.M + 1) * c.win * c.win);
+    c.a_idx_elems = c.no_spatial ? 0 : (c.full_obs ? 2 * c.HW : 2 * c.win * c.win);
     c.split_layout = (u.split_layout && c.reset_mode == 1) ? 1 : 0;
     c.split_water_row = u.split_water_row; c.split_top_ranks = u.split_top_ranks;
     if (c.split_layout && (c.split_water_row < 1 || c.split_water_row >= c.H - 1)) return bad("split_water_row outside the world");
@@ -168,7 +185,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         if (c.dyn_layout && !(c.dyn_cov[i] > 0.0 && c.dyn_cov[i] < 1.0 && c.dyn_clump[i] > 0.0 && c.dyn_clump[i] <= 1.0))
             return bad("dyn_coverage must be in (0, 1) and dyn_clump in (0, 1]");
     }
-    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs || c.split_layout ||
+    c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs || c.split_layout || c.one_step ||
              (c.has[COMP_TAX] && c.tax_model == AIE_TAX_FIXED_RATES && u.tax_annealing) ||
              (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2))) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
@@ -193,6 +210,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
                 if (c.sub_kind[si] == SUB_BUILD) mp[n++] = AIE_MASK_ENTRY(MS_BUILD, 0);
                 else if (c.sub_kind[si] == SUB_BUY) mp[n++] = AIE_MASK_ENTRY(MS_BUY0 + c.sub_c[si], j);
                 else if (c.sub_kind[si] == SUB_SELL) mp[n++] = AIE_MASK_ENTRY(MS_SELL0 + c.sub_c[si], j);
+                else if (c.sub_kind[si] == SUB_LABOR) mp[n++] = AIE_MASK_ENTRY(MS_LABOR, j);
                 else mp[n++] = AIE_MASK_ENTRY(MS_G0 + j, 0);
             }
         }
@@ -202,13 +220,20 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         static const char *CN[2] = {"Stone", "Wood"};
         std::vector<FlatKey> ka, kp, kpa;
         auto K = [](const std::string &k, int kind, int payload, int n) { return FlatKey{k, kind, payload, n}; };
+        if (c.one_step) {   // one_step_economy.py:138-160: nothing for the agents, two scalars for the planner
+            ka.push_back(K("time", FK_SHARED, SH_TIME, 1)); kp.push_back(K("time", FK_SHARED, SH_TIME, 1));
+            kp.push_back(K("world-normalized_per_capita_productivity", FK_SHARED, SH_ONE_PROD, 1));
+            kp.push_back(K("world-equality", FK_SHARED, SH_ONE_EQ, 1));
+            ka.push_back(K("SimpleLabor-skill", FK_AGENT, AS_LABOR_SKILL, 1));   // simple_labor.py:128-134
+        } else {
         if (!c.full_obs) { ka.push_back(K("world-loc-row", FK_AGENT, AS_LOC_ROW, 1)); ka.push_back(K("world-loc-col", FK_AGENT, AS_LOC_COL, 1)); }
         ka.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); ka.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
         ka.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1)); ka.push_back(K("time", FK_SHARED, SH_TIME, 1));
         kp.push_back(K("world-inventory-Coin", FK_SHARED, SH_ZERO, 1)); kp.push_back(K("world-inventory-Stone", FK_SHARED, SH_ZERO, 1));
         kp.push_back(K("world-inventory-Wood", FK_SHARED, SH_ZERO, 1)); kp.push_back(K("time", FK_SHARED, SH_TIME, 1));
+        }
         // with full_observability the scenario sets no p<i> entries at all (layout_from_file.py:465-472 vs :509-513)
-        if (!c.full_obs) {
+        if (!c.full_obs && !c.one_step) {
             kpa.push_back(K("world-inventory-Coin", FK_AGENT, AS_INV_COIN, 1)); kpa.push_back(K("world-inventory-Stone", FK_AGENT, AS_INV_STONE, 1));
             kpa.push_back(K("world-inventory-Wood", FK_AGENT, AS_INV_WOOD, 1));
         }

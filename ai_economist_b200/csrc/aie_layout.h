@@ -45,8 +45,8 @@ enum { ST_TAX_PERIODS = 0, ST_TAX_COLLECTED = 1, ST_TAX_EFF_SUM = 2, ST_TAX_SCHE
 //   EV_TRADE  {kind, seller, buyer, commodity, ask, bid, ask_lifetime, bid_lifetime}
 enum { EV_BUILD = 1, EV_GATHER = 2, EV_TRADE = 3 };
 
-enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3, COMP_WEALTH = 4, COMP_KINDS = 5 };
-enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3 };
+enum { COMP_BUILD = 0, COMP_CDA = 1, COMP_GATHER = 2, COMP_TAX = 3, COMP_WEALTH = 4, COMP_LABOR = 5, COMP_KINDS = 6 };
+enum { SUB_BUILD = 0, SUB_BUY = 1, SUB_SELL = 2, SUB_GATHER = 3, SUB_LABOR = 4 };
 
 // Observation "programs" (built once on the host from the reference's sorted-key flattening, base_env.py:562-612).
 // flat entry  = kind << 13 | payload:
@@ -61,10 +61,10 @@ enum { FK_SHARED = 0, FK_AGENT = 1, FK_MY = 2, FK_AVAIL = 3 };
 // observation staging buffers (see ObsScratch in aie_obs.cuh); offsets DevCfg::ob[] / ob_emu[]
 enum { OB_NET_HIST = 0, OB_SHF, OB_SC_A, OB_LIM, OB_PSH, OB_LOCMAP, OB_WC, OB_WI, OB_PL, OB_BITS, OB_VALS, OB_COUNT };
 enum { AS_LOC_ROW = 0, AS_LOC_COL, AS_INV_COIN, AS_INV_STONE, AS_INV_WOOD, AS_BUILD_PAYMENT, AS_BUILD_SKILL, AS_BONUS,
-       AS_TAX_MARG, AS_TAX_LAST_INCOME, AS_TAX_LAST_MARG, AS_COUNT = 12 };
-enum { SH_ZERO = 0, SH_TIME = 1, SH_MARKET_RATE = 2, SH_TAX_IS_TAX_DAY = 4, SH_TAX_IS_FIRST = 5, SH_TAX_PHASE = 6,
+       AS_TAX_MARG, AS_TAX_LAST_INCOME, AS_TAX_LAST_MARG, AS_LABOR_SKILL /* one-step-economy */, AS_COUNT = 12 };
+enum { SH_ZERO = 0, SH_TIME = 1, SH_MARKET_RATE = 2, SH_ONE_PROD = 2, SH_ONE_EQ = 3 /* one-step-economy (no auction): planner scalars */, SH_TAX_IS_TAX_DAY = 4, SH_TAX_IS_FIRST = 5, SH_TAX_PHASE = 6,
        SH_PRICE_HIST = 8 /* [2][P], then curr_rates [16], then sorted last incomes [A] */ };
-enum { MS_ONE = 0, MS_BUILD, MS_BUY0, MS_BUY1, MS_SELL0, MS_SELL1, MS_G0, MS_G1, MS_G2, MS_G3, MS_COUNT = 12 };
+enum { MS_ONE = 0, MS_BUILD, MS_BUY0, MS_BUY1, MS_SELL0, MS_SELL1, MS_G0, MS_G1, MS_G2, MS_G3, MS_LABOR, MS_COUNT = 12 };
 
 #define AIE_FLAT_ENTRY(kind, payload) ((uint16_t)(((kind) << 13) | (payload)))
 #define AIE_FLAT_KIND(e) ((e) >> 13)
@@ -156,6 +156,9 @@ struct DevCfg {
     // split_layout device reset: per-replica rank -> build payment table f64[A] in the kept part of the record
     int32_t split_layout, split_water_row, off_split_skill;
     uint64_t split_top_ranks;
+    // one-step-economy (aie_config::scenario_kind == 1): no map, SimpleLabor, coin-minus-labor-cost utilities
+    int32_t one_step, agent_reward_type, labor_mask_first, no_spatial;
+    double labor_exponent, labor_cost, labor_skill_scale;
     // dynamic-layout scenarios: device-side layout generation at reset (see aie_config::dyn_layout)
     int32_t dyn_layout, dyn_checker;
     double dyn_cov[2], dyn_clump[2];   // [Wood, Stone]

@@ -430,9 +430,10 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
     });
     ex([&](int tid) {
         for (int a = tid; a < A; a += NT) {
-            const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
-            s.locmap[row * W + col] = (uint8_t)(a + 2);
+            const int row = (EXT && c.no_spatial) ? 0 : e.loc[2 * a], col = (EXT && c.no_spatial) ? 0 : e.loc[2 * a + 1];
+            if (!(EXT && c.no_spatial)) s.locmap[row * W + col] = (uint8_t)(a + 2);
             float *sc = s.sc_a + a * AS_COUNT;
+            if (EXT && c.one_step) sc[AS_LABOR_SKILL] = (float)(e.bskill[a] / c.labor_skill_scale);   // simple_labor.py:128-134
             sc[AS_LOC_ROW] = (float)((double)row / H);
             sc[AS_LOC_COL] = (float)((double)col / W);
             sc[AS_INV_COIN] = (float)(e.coin[a] * inv_scale);
@@ -441,6 +442,27 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             sc[AS_BUILD_PAYMENT] = (float)(e.bpay[a] / c.build_payment);
             sc[AS_BUILD_SKILL] = (float)e.bskill[a];
             sc[AS_BONUS] = (float)e.bonus[a];
+        }
+        if (EXT && c.one_step && tid == 0) {   // one_step_economy.py:146-158: equality and per-capita productivity / 1000
+            double total = 0.0, diff = 0.0;
+            for (int a = 0; a < A; a++) total += e.coin[a] + e.esc_coin[a];
+            double eq;
+            if (A < 30) {
+                for (int i = 0; i < A; i++) for (int j = 0; j < A; j++) diff += fabs((e.coin[i] + e.esc_coin[i]) - (e.coin[j] + e.esc_coin[j]));
+                eq = 1.0 - (diff / (2 * A * total + 1e-10)) / ((A - 1) / (double)A);
+            } else {   // social_metrics.py: sorted form for larger populations
+                double acc = 0.0;
+                // O(A^2) without scratch: sum over sorted position k of cumsum_k = sum_i x_i * (number of positions >= rank_i)
+                for (int i = 0; i < A; i++) {
+                    const double xi = e.coin[i] + e.esc_coin[i];
+                    int rank = 0;
+                    for (int j = 0; j < A; j++) { const double xj = e.coin[j] + e.esc_coin[j]; rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
+                    acc += xi * (double)(A - rank);
+                }
+                eq = (2.0 / (A + 1)) * (acc / (total + 1e-10));   // 1 - gini
+            }
+            s.shf[SH_ONE_PROD] = (float)(total / A / 1000.0);
+            s.shf[SH_ONE_EQ] = (float)eq;
         }
         if (c.has[COMP_CDA])
             for (int cc = tid; cc < 2; cc += NT) {  // market_rate (:504-513)
@@ -453,6 +475,10 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
         for (int a = tid; a < A; a += NT) {  // mask limits (build.py:180-193, move.py:167-188, cda :544-580)
             uint8_t *lim = s.lim + a * MS_COUNT;
             lim[MS_ONE] = 1;
+            if (EXT && c.one_step) {   // simple_labor.py:93-98: everything masked in the reset observation, open afterwards
+                lim[MS_LABOR] = (uint8_t)((c.labor_mask_first && e.hdr[HDR_T] == 0) ? 0 : 100);
+                continue;
+            }
             lim[MS_BUILD] = can_build(c, e, a) ? 1 : 0;
             const int row = e.loc[2 * a], col = e.loc[2 * a + 1];
             const int roff[4] = {0, 0, -1, 1}, coff[4] = {-1, 1, 0, 0};
@@ -590,6 +616,8 @@ AIE_DEV void observe_env(const DevCfg &c, uint8_t *rec, uint8_t *grec, uint8_t *
             if (a0 == 0) copy_run_f32(o.p_flat(), c.Fp, s.vals + c.vals_off[3], tid, NT);
         });
     }
+
+    if (EXT && c.no_spatial) return;   // one-step-economy: nothing spatial
 
     // ---- phase C: the planner's spatial tensors: M bit planes of the whole map + the two index planes -----------------
     const int psp = c.pl_stride_p;   // bytes per whole-map plane bitmap

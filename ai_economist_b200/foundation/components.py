@@ -235,3 +235,40 @@ class WealthRedistribution(BaseComponent):
     name = "WealthRedistribution"
     required_entities = ["Coin"]
     agent_subclasses = ["BasicMobileAgent"]
+
+
+@component_registry.add
+class SimpleLabor(BaseComponent):
+    """reference: components/simple_labor.py:16-134.  100 labor actions (hours worked); income = hours x skill.  The skill
+    table is the mean of 1000 sorted, clipped Pareto draws, taken in the reference's constructor from the global stream:
+    here every replica draws its own table from its own stream (`draw_skills`, called by the one-step-economy scenario
+    right after the env has been seeded, like the reference seeds before it builds its components)."""
+    name = "SimpleLabor"
+    required_entities = ["Coin"]
+    agent_subclasses = ["BasicMobileAgent"]
+    num_labor_hours = 100
+
+    def __init__(self, *a, mask_first_step=True, payment_max_skill_multiplier=3, pareto_param=4.0, **k):
+        super().__init__(*a, **k)
+        assert isinstance(mask_first_step, bool)
+        self.mask_first_step = mask_first_step
+        self.pareto_param = float(pareto_param)
+        assert self.pareto_param > 0
+        self.payment_max_skill_multiplier = float(payment_max_skill_multiplier)
+        self.skills = None   # [n_envs, n_agents], set by draw_skills
+
+    def get_n_actions(self, agent_cls_name):
+        return self.num_labor_hours if agent_cls_name == "BasicMobileAgent" else None
+
+    def draw_skills(self, streams):
+        """simple_labor.py:72-81 (sic: the shape parameter is the literal 4, not pareto_param)."""
+        pmsm, n = self.payment_max_skill_multiplier, self.n_agents
+        out = []
+        for rs in streams:
+            samples = rs.pareto(4, size=(1000, n))
+            out.append(np.sort(np.minimum(pmsm, (pmsm - 1) * samples + 1), axis=1).mean(axis=0))
+        self.skills = np.stack(out)
+        return self.skills
+
+    def spec_fields(self):
+        return dict(labor_mask_first_step=int(self.mask_first_step), labor_skill_scale=self.payment_max_skill_multiplier)

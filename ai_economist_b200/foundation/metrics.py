@@ -43,6 +43,23 @@ def metrics_from_state(spec, st, saez_elasticity=None):
     coin = np.asarray(st["coin"], np.float64) + np.asarray(st["esc_coin"], np.float64)  # total_endowment("Coin")
     util = np.asarray(st["util_prev"], np.float64)  # curr_optimization_metric: agents then planner
     m = {}
+    if int(spec.get("scenario_kind", 0)) == 1:
+        # one-step-economy (scenarios/one_step_economy/one_step_economy.py:210-262): averages instead of per-agent entries;
+        # the pre-tax incomes (production) travel in the record's build_payment field
+        prod = np.asarray(st["build_payment"], np.float64)
+        m["social/productivity"] = float(np.sum(coin))
+        m["social/equality"] = float(1 - gini(coin))
+        m["social_welfare/coin_eq_times_productivity"] = float((1 - gini(coin)) * (np.sum(coin) / A))
+        w = 1 / np.maximum(prod, 1)
+        w = w / np.sum(w)
+        m["social_welfare/inv_income_weighted_utility"] = float(np.sum(util[:A] * w))
+        m["endow/avg_agent/Coin"] = float(np.mean(coin))
+        m["endogenous/avg_agent/Labor"] = float(np.mean(np.asarray(st["labor"], np.float64)))
+        m["util/avg_agent"] = float(np.mean(util[:A]))
+        m["endow/p/Coin"] = 0
+        m["util/p"] = float(util[A])
+        _component_metrics(m, spec, st, A, coin, saez_elasticity)
+        return m
     m["social/productivity"] = float(np.sum(coin))
     m["social/equality"] = float(1 - gini(coin))
     m["social_welfare/coin_eq_times_productivity"] = float((1.0 * (1 - gini(coin)) + 0.0) * (np.sum(coin) / A))
@@ -66,6 +83,12 @@ def metrics_from_state(spec, st, saez_elasticity=None):
     m["labor/weighted_cost"] = float(spec["energy_cost"]) * ew
     m["labor/warmup_integrator"] = warm_int
 
+    _component_metrics(m, spec, st, A, coin, saez_elasticity)
+    return m
+
+
+def _component_metrics(m, spec, st, A, coin, saez_elasticity):
+    """Every component's get_metrics() under its shorthand, from the running sums in the record's stats section."""
     stats = np.asarray(st["stats"], np.float64)
     comps = list(spec["components"])
     st_trade = 1 + A
@@ -105,4 +128,3 @@ def metrics_from_state(spec, st, saez_elasticity=None):
                     m["PeriodicTax/avg_tax_rate/%s" % tag] = float(paid[i] / max(0.001, inc[i]))
                 if int(spec["tax_model"]) == 2:  # the running elasticity estimate lives in the host-side estimator
                     m["PeriodicTax/saez/estimated_elasticity"] = float(saez_elasticity)
-    return m

@@ -473,3 +473,62 @@ class SplitLayout(LayoutFromFile):
             top |= 1 << int(rank)
         d.update(split_layout=1, split_water_row=int(self._water_line), split_top_ranks=top)
         return d
+
+
+@scenario_registry.add
+class OneStepEconomy(BaseScenario):
+    """reference: scenarios/one_step_economy/one_step_economy.py:15-336.  Two-step episodes: the planner sets taxes, then
+    every agent picks its hours of labor.  No map, no spatial observations; utilities are coin minus a labor cost.
+    Its reset draws nothing, so the device's snapshot restore IS the reference's reset."""
+    name = "one-step-economy"
+    agent_subclasses = ["BasicMobileAgent", "BasicPlanner"]
+    required_entities = ["Coin"]
+
+    def __init__(self, env, agent_reward_type="coin_minus_labor_cost", isoelastic_eta=0.23, labor_exponent=2.0,
+                 labor_cost=1.0, planner_reward_type="inv_income_weighted_utility", mixing_weight_gini_vs_coin=0):
+        self.env = env
+        self.agent_reward_type = str(agent_reward_type)
+        if self.agent_reward_type not in ("isoelastic_coin_minus_labor", "coin_minus_labor_cost"):
+            raise NotImplementedError("unknown agent_reward_type")
+        self.isoelastic_eta = float(isoelastic_eta)
+        self.labor_exponent = float(labor_exponent)
+        self.labor_cost = float(labor_cost)
+        self.planner_reward_type = str(planner_reward_type)
+        if self.planner_reward_type not in ("coin_eq_times_productivity", "inv_income_weighted_utility"):
+            print("No valid planner reward selected!")
+            raise NotImplementedError
+        self.mixing_weight_gini_vs_coin = float(mixing_weight_gini_vs_coin)
+        if self.agent_reward_type == "isoelastic_coin_minus_labor":
+            assert 0.0 <= self.isoelastic_eta <= 1.0
+        else:
+            assert self.labor_exponent > 1.0
+        labor = env._components_dict.get("SimpleLabor")
+        if labor is None or any(c.name not in ("SimpleLabor", "PeriodicBracketTax") for c in env._components):
+            raise NotImplementedError("the one-step-economy runs with SimpleLabor (+ PeriodicBracketTax)")
+        # the reference's component constructors run after the seeding and before the scenario's: SimpleLabor's skill table
+        # is the only constructor-time draw
+        streams = env._rs if env._rs is not None else [np.random.RandomState() for _ in range(env.n_envs)]
+        labor.draw_skills(streams)
+
+    def host_reset(self, rs, e=0):
+        """reset_agent_states + component resets (one_step_economy.py:93-109, simple_labor.py:88-91): nothing is drawn."""
+        env = self.env
+        A = env.n_agents
+        H, W = env.world_size
+        z = np.zeros((H, W), np.uint8)
+        skills = env._components_dict["SimpleLabor"].skills[e]
+        return dict(stone=z, wood=z.copy(), stone_src=z.copy(), wood_src=z.copy(), water=z.copy(),
+                    loc=np.zeros((A, 2), np.int16),   # nobody is placed (one_step_economy.py:93-105); not observed
+                    coin=np.zeros(A), inv_stone=np.zeros(A, np.int32),
+                    inv_wood=np.zeros(A, np.int32),
+                    build_payment=np.zeros(A),              # record reuse: cumulative production
+                    build_skill=np.asarray(skills, float),  # record reuse: the SimpleLabor skill
+                    bonus_gather_prob=np.zeros(A))
+
+    def scenario_spec_fields(self):
+        return dict(scenario_kind=1, has_water=0, obs_range=0, planner_gets_spatial_info=0, regen_weight=[0.0, 0.0],
+                    isoelastic_eta=self.isoelastic_eta, energy_cost=0.0, energy_warmup_constant=0.0, energy_warmup_auto=0,
+                    planner_reward_type=_SWF[self.planner_reward_type],
+                    mixing_weight_gini_vs_coin=self.mixing_weight_gini_vs_coin,
+                    agent_reward_type=int(self.agent_reward_type == "coin_minus_labor_cost"),
+                    labor_exponent=self.labor_exponent, labor_cost=self.labor_cost, reset_mode=0)

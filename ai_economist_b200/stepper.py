@@ -29,14 +29,15 @@ class BatchStepper:
         d, E, A = self.dims, self.n_envs, spec["n_agents"]
         H, W = spec["height"], spec["width"]
         full = bool(spec.get("full_observability", 0))   # agents see the whole map: [M, H, W] / [2, H, W] per agent
-        assert d.agent_map_elems == (d.n_map_channels * H * W if full else (d.n_map_channels + 1) * d.window ** 2)
+        none = bool(spec.get("scenario_kind", 0) == 1)   # one-step-economy: no spatial observations (zero-size tensors)
+        assert d.agent_map_elems == (0 if none else d.n_map_channels * H * W if full else (d.n_map_channels + 1) * d.window ** 2)
         shapes = {
             "state": ("u8", (E, d.state_bytes)), "state0": ("u8", (E, d.state_bytes)),
             "actions_agent": ("i32", (E, A, d.n_act_agent)),
             "actions_planner": ("i32", (E, max(1, d.n_act_planner))),
-            "obs_agent_map": ("f32", (E, A, d.n_map_channels, H, W) if full else
+            "obs_agent_map": ("f32", (E, A, 0) if none else (E, A, d.n_map_channels, H, W) if full else
                               (E, A, d.n_map_channels + 1, d.window, d.window)),
-            "obs_agent_idx": ("i16", (E, A, 2, H, W) if full else (E, A, 2, d.window, d.window)),
+            "obs_agent_idx": ("i16", (E, A, 0) if none else (E, A, 2, H, W) if full else (E, A, 2, d.window, d.window)),
             "obs_agent_flat": ("f32", (E, A, d.flat_agent)),
             "mask_agent": ("f32", (E, A, d.mask_agent)),
             "obs_planner_map": ("f32", (E, d.n_map_channels, H, W)),
@@ -216,6 +217,9 @@ class BatchStepper:
         self._check(fn(self._h, int(e), C.byref(d)))
         out["books"] = {(c, s): out["book_rows"][c, s, :out["book_count"][c, s]].copy()
                         for c in (0, 1) for s in (0, 1)}
+        if hasattr(self, "state_view"):   # skills / payments (one-step-economy: SimpleLabor skill / cumulative production)
+            for k in ("build_payment", "build_skill"):
+                out[k] = np.asarray(self.to_numpy(self.state_view(k, final=final)[e]), np.float64).copy()
         return out
 
     def read_events(self, e):

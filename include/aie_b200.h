@@ -52,7 +52,8 @@ extern "C" {
  *   Gather                   components/move.py:16
  *   PeriodicBracketTax       components/redistribution.py:78 */
 enum { AIE_COMP_BUILD = 0, AIE_COMP_CDA = 1, AIE_COMP_GATHER = 2, AIE_COMP_TAX = 3,
-       AIE_COMP_WEALTH = 4 /* WealthRedistribution, components/redistribution.py:21-75 */ };
+       AIE_COMP_WEALTH = 4 /* WealthRedistribution, components/redistribution.py:21-75 */,
+       AIE_COMP_SIMPLE_LABOR = 5 /* SimpleLabor, components/simple_labor.py:16-134 (one-step-economy scenario only) */ };
 /* tax_model (redistribution.py:160-166): planner-driven discretised rates, or a fixed schedule
  * ("us-federal-single-filer-2018-scaled" / "fixed-bracket-rates", rates supplied by the host). */
 enum { AIE_TAX_MODEL_WRAPPER = 0, AIE_TAX_FIXED_RATES = 1,
@@ -142,6 +143,15 @@ typedef struct aie_config {
     double dyn_clump[2];            /* 1 - clip(clumpiness, 0, 0.99), [Wood, Stone] */
     const double *dyn_prob;         /* HOST pointer: source probability maps float64 [2][height][width] (Wood, Stone),
                                        copied by aie_create (source_prob_maps, :289-308 / :960-990) */
+    /* The "one-step-economy" scenario (scenarios/one_step_economy/one_step_economy.py:15-336) with SimpleLabor
+     * (+ PeriodicBracketTax): no world map and no spatial observations (the map tensors have zero elements and may be
+     * NULL in aie_buffers), agents choose 0..100 hours of labor once, utilities are coin minus a labor cost.
+     * State reuse: aie_host_state.build_skill carries the SimpleLabor skill, build_payment the cumulative production. */
+    int32_t scenario_kind;          /* 0: gather-trade-build family; 1: one-step-economy */
+    int32_t agent_reward_type;      /* one-step-economy: 0 "isoelastic_coin_minus_labor", 1 "coin_minus_labor_cost" (:283-301) */
+    double labor_exponent, labor_cost;      /* rewards.py:46-70 */
+    int32_t labor_mask_first_step;  /* SimpleLabor mask_first_step: every labor action masked in the reset observation */
+    double labor_skill_scale;       /* SimpleLabor payment_max_skill_multiplier: the skill observation is skill / this */
 } aie_config;
 
 /* Sizes the caller needs to allocate the device buffers. */

@@ -10,6 +10,8 @@ profiles/); here every fuzzer contributes N_CASES configurations drawn from a fi
   * oracle vs reference      -m reference           the C oracle against the live imported reference
   * device reset vs ref.     -m reference           reference-exact auto-reset across 4 episodes against env.reset()
   * reference API vs ref.    -m reference           ReferenceApiEnv against the reference: obs, rewards, metrics, dense logs
+  * dynamic layouts vs ref.  -m reference           uniform / quadrant: device-side layout generation at every auto-reset
+  * one-step-economy vs ref. -m reference           SimpleLabor + one-step-economy incl. finished-episode metrics
   * COVID vs reference       -m reference           COVID device code (scan and change list) under parameter variants
 
 `-m reference` cases need /root/reference (build container) and are skipped elsewhere.
@@ -123,6 +125,18 @@ def test_fuzz_reference_api_matches_live_reference(i):
 
     name, kw = _configs(0)[i]
     _skip_unsupported(fa.run_one, name, kw, seed=700 + i)
+
+
+@needs_reference
+@pytest.mark.reference
+@pytest.mark.parametrize("i", range(N_CASES))
+def test_fuzz_one_step_economy_matches_live_reference(i):
+    """SimpleLabor + one-step-economy (components/simple_labor.py, scenarios/one_step_economy): observations, masks, rewards,
+    numpy stream and finished-episode metrics across auto-resets, random reward types / tax settings / populations."""
+    import fuzz_one_step_vs_reference as fo
+
+    cfg = _configs(3, draw=fo.random_config)[i]
+    fo.run_one(cfg, seed=300 + i, episodes=3)
 
 
 @needs_reference
