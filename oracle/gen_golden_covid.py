@@ -63,16 +63,25 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--steps", type=int, default=540)
     ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--cooldown", type=int, default=None, help="action_cooldown_period of the variant (default: the workload's 28)")
+    ap.add_argument("--episode-length", type=int, default=None)
+    ap.add_argument("--name", default=None, help="file name stem (default covid_seed<seed>)")
     args = ap.parse_args()
+    kwargs = dict(COVID_KWARGS)
+    if args.cooldown is not None:
+        kwargs["action_cooldown_period"] = args.cooldown
+    if args.episode_length is not None:
+        kwargs["episode_length"] = args.episode_length
+        args.steps = min(args.steps, args.episode_length)
     f = rh.load_reference_foundation()
     with contextlib.redirect_stdout(io.StringIO()):
-        env = f.make_env_instance(**reference_config(COVID_KWARGS))
+        env = f.make_env_instance(**reference_config(kwargs))
         obs = env.reset()
     orc = None
     if args.check:
         from ai_economist_b200.foundation.covid19 import build_covid_params
         from oracle.covid_oracle import CovidOracleEnv
-        orc = CovidOracleEnv(build_covid_params(**COVID_KWARGS))
+        orc = CovidOracleEnv(build_covid_params(**kwargs))
     rng = np.random.RandomState(args.seed)
     rec = {k: [v] for k, v in ref_arrays(env, obs).items()}
     acts_a, acts_p = [], []
@@ -105,7 +114,7 @@ def main():
     if orc:
         print("oracle matches the reference for %d steps (bit-exact float32 observations on %d of them)" % (args.steps, n_exact))
     os.makedirs(OUT, exist_ok=True)
-    out = {"meta_json": np.array(json.dumps(dict(kwargs=COVID_KWARGS, seed=args.seed, n_steps=args.steps)))}
+    out = {"meta_json": np.array(json.dumps(dict(kwargs=kwargs, seed=args.seed, n_steps=args.steps)))}
     out["act_a"] = np.stack(acts_a).astype(np.int8)
     out["act_p"] = np.array(acts_p, np.int8)
     for k, v in rec.items():
@@ -113,7 +122,7 @@ def main():
             out[k] = np.stack(v)          # steps 1..N
         else:
             out[k] = np.stack(v)          # steps 0..N
-    path = os.path.join(OUT, "covid_seed%d.npz" % args.seed)
+    path = os.path.join(OUT, "%s.npz" % (args.name or "covid_seed%d" % args.seed))
     np.savez_compressed(path, **out)
     print(path, "%.1f KB" % (os.path.getsize(path) / 1024))
 

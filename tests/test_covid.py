@@ -22,8 +22,11 @@ OBS_KEYS = ["agent_state", "postsubsidy", "lagged", "policy_ind", "scalars", "ma
 RTOL, ATOL = 1e-6, 1e-9
 
 
-def load():
-    z = np.load(GOLDEN)
+VARIANTS = ["covid_seed3.npz", "covid_cooldown1_seed11.npz", "covid_cooldown7_seed12.npz"]   # cooldown 28 / 1 / 7, own action seeds
+
+
+def load(name=None):
+    z = np.load(GOLDEN if name is None else os.path.join(os.path.dirname(GOLDEN), name))
     meta = json.loads(str(z["meta_json"]))
     return z, meta, build_covid_params(**meta["kwargs"])
 
@@ -45,8 +48,9 @@ def replay(stepper_step, stepper_obs, z, n, label):
         check(z, t, stepper_obs(), label)
 
 
-def test_covid_oracle_matches_reference_golden_trace():
-    z, meta, p = load()
+@pytest.mark.parametrize("name", VARIANTS)
+def test_covid_oracle_matches_reference_golden_trace(name):
+    z, meta, p = load(name)
     env = CovidOracleEnv(p)
     replay(lambda a, pl: env.step(a, pl), env.obs, z, meta["n_steps"], "oracle")
 
@@ -63,10 +67,11 @@ def _drive(stepper, e=0):
     return step, (lambda: stepper.read_obs(e))
 
 
+@pytest.mark.parametrize("name", VARIANTS)
 @pytest.mark.parametrize("change_list", [False, True], ids=["scan", "change_list"])
-def test_covid_emulated_device_code_matches_reference_golden_trace(change_list):
+def test_covid_emulated_device_code_matches_reference_golden_trace(change_list, name):
     from tests.emu.emu_stepper import EmuCovidStepper
-    z, meta, p = load()
+    z, meta, p = load(name)
     s = EmuCovidStepper(p, 2, change_list=change_list)
     s.reset()
     step, obs = _drive(s, e=1)
@@ -132,10 +137,11 @@ def test_covid_emulated_auto_reset_starts_a_fresh_episode(change_list):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", VARIANTS)
 @pytest.mark.parametrize("change_list", [False, True], ids=["scan", "change_list"])
-def test_covid_cuda_matches_reference_golden_trace(change_list):
+def test_covid_cuda_matches_reference_golden_trace(change_list, name):
     from ai_economist_b200.covid_stepper import CudaCovidStepper
-    z, meta, p = load()
+    z, meta, p = load(name)
     s = CudaCovidStepper(p, 3, auto_reset=False, change_list=change_list)
     s.reset()
     step, obs = _drive(s, e=2)

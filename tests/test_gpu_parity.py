@@ -92,6 +92,7 @@ def test_cuda_full_size_c2_against_oracle_and_invariants():
         s = orc.state(e)
         assert np.array_equal(s["loc"], loc[e]) and np.array_equal(s["inv"], inv[e]), e
         assert int(s["mt_pos"][0]) == int(mt_pos[e]), e
+    print("c2 full size, max relative float error over all replicas:", _batch_wide_float_error(env, orc, E))
     # invariants: order counts equal histogram mass; escrowed units equal open asks; agents on distinct cells
     assert np.array_equal(n_orders, bid_hist.sum(-1) + ask_hist.sum(-1))
     assert np.array_equal(esc.transpose(0, 2, 1), ask_hist.sum(-1))
@@ -149,6 +150,7 @@ def test_cuda_full_size_c3_c5_against_oracle_and_invariants(cfg, E, steps):
         s = orc.state(e)
         assert np.array_equal(s["loc"], loc[e]) and np.array_equal(s["inv"], inv[e]), e
         assert int(s["mt_pos"][0]) == int(mt_pos[e]), e
+    print(cfg, "full size, max relative float error over all replicas:", _batch_wide_float_error(env, orc, E))
     assert np.array_equal(n_orders, bid_hist.sum(-1) + ask_hist.sum(-1))          # order counts = histogram mass
     assert np.array_equal(esc.transpose(0, 2, 1), ask_hist.sum(-1))               # escrowed units = open asks
     assert n_orders.max() <= env.spec["max_num_orders"]
@@ -156,6 +158,24 @@ def test_cuda_full_size_c3_c5_against_oracle_and_invariants(cfg, E, steps):
     assert all(len(set(row)) == A for row in flat)                                # agents on distinct cells
     assert (loc >= 0).all() and (loc[..., 0] < H).all() and (loc[..., 1] < W).all()
     assert (inv >= 0).all() and (esc >= 0).all() and (coin > -1e-9).all()
+
+
+
+def _batch_wide_float_error(env, orc, E, rtol=1e-6):
+    """Max relative error of the float64 state (coin, escrowed coin, labor) and of the last step's rewards over EVERY
+    replica of the batch against the oracle - the north star's "within 1e-6 relative for coin/utility floats"."""
+    st = env.stepper
+    dev = {k: st.state_view(k).cpu().numpy() for k in ("coin", "esc_coin", "labor")}
+    rew = st.to_numpy(st.buf["reward"])
+    worst = {}
+    for e in range(E):
+        s, o = orc.state(e), orc.obs(e)
+        for k, got in list((k, dev[k][e]) for k in dev) + [("rew", rew[e])]:
+            want = np.asarray(o["rew"] if k == "rew" else s[k], np.float64).reshape(np.asarray(got).shape)
+            err = float(np.max(np.abs(want - got) / np.maximum(np.abs(want), 1.0)))   # relative, absolute below 1
+            worst[k] = max(worst.get(k, 0.0), err)
+    assert all(v <= rtol for v in worst.values()), worst
+    return worst
 
 
 def test_auto_reset_restores_snapshot_and_continues_stream():

@@ -47,7 +47,7 @@ if [[ $PH == all || $PH == *ncx* ]]; then   # full captures of the other workloa
   B="--no-cpu-baseline --no-extra-workloads --e2e-steps 3 --steps 20 --warmup 5"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step -s 1030 -c 1 -f -o gpurun_out/prof_step_c3 \
       python bench.py --workload c3 $B > gpurun_out/ncu_step_c3.log 2>&1; echo "ncu step c3 rc=$?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step -s 180 -c 1 -f -o gpurun_out/prof_step_c5 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_step -s 200 -c 1 -f -o gpurun_out/prof_step_c5 \
       python bench.py --workload c5 $B > gpurun_out/ncu_step_c5.log 2>&1; echo "ncu step c5 rc=$?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:aie_covid_step -s 60 -c 1 -f -o gpurun_out/prof_step_c4 \
       python bench.py --workload c4 $B > gpurun_out/ncu_step_c4.log 2>&1; echo "ncu step c4 rc=$?"
