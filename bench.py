@@ -479,7 +479,7 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     st.set_fused_policy(0)   # the e2e leg takes its actions from the host
     out_host["mask_agent"].copy_(st.buf["mask_agent"])
     out_host["mask_planner"].copy_(st.buf["mask_planner"])
-    e2e_s, n_e2e = 0.0, max(3, e2e_steps)
+    e2e_s, n_e2e, e2e_each = 0.0, max(3, e2e_steps), []
     for i in range(n_e2e + 2):
         act_a.copy_(torch.from_numpy(wl.sample_from_masks(out_host["mask_agent"].numpy(), seg_a, rng)))
         if seg_p:
@@ -491,8 +491,11 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
         dt = time.perf_counter() - t0  # the host entry points synchronise the stream before returning
         if i >= 2:
             e2e_s += dt
+            e2e_each.append(dt)
     e2e_value = world * E * A * n_e2e / ctx.max_over_ranks(e2e_s)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "steps": n_e2e, "mode": e2e_mode}
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "steps": n_e2e, "mode": e2e_mode,
+           "ms_per_step": {"mean": 1e3 * e2e_s / n_e2e, "median": 1e3 * float(np.median(e2e_each)), "min": 1e3 * min(e2e_each),
+                           "max": 1e3 * max(e2e_each)}}
     if e2e_mode == "plain":
         e2e.update(d2h_bytes_per_step=d2h,
                    what="aie_step_host: pinned host actions in, every observation/mask/reward/done tensor copied back "
@@ -736,7 +739,9 @@ def main():
         clocks.start()
     fn = measure_covid if key == "c4" else measure_gtb
     if args.e2e_threads == 0:   # expansion threads of the e2e leg: this rank's share of the host's hardware threads
-        args.e2e_threads = max(8, host_cores() // max(1, world))
+        # (three quarters of them: the main thread, the clock sampler and the CUDA driver's threads need cores too, and a
+        # straggler among the expansion workers delays the whole step)
+        args.e2e_threads = max(8, (3 * host_cores()) // (4 * max(1, world)))
     kw = {} if key == "c4" else dict(e2e_mode=args.e2e_mode, e2e_threads=args.e2e_threads)
     res = fn(ctx, key, args.steps, args.warmup, with_cpu, clocks=clocks, e2e_steps=args.e2e_steps, **kw)
     clk = clocks.stop() if clocks else None

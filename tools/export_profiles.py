@@ -18,12 +18,11 @@ for src, dst in [("bench.json", "bench_c2_all_workloads.json"), ("bench_ref.json
     if os.path.exists(os.path.join(OUT, src)):
         shutil.copy(os.path.join(OUT, src), os.path.join(PROF, "%s_%s" % (tag, dst)))
 for w in ("c2", "c3", "c4", "c5"):
-    rep = os.path.join(OUT, "prof_step_%s.ncu-rep" % w)
-    if not os.path.exists(rep):
+    raw_csv, src_csv = os.path.join(OUT, "prof_step_%s_raw.csv" % w), os.path.join(OUT, "prof_step_%s_src.csv" % w)
+    if not os.path.exists(raw_csv):
         continue
     kernel = "aie_covid_step_kernel" if w == "c4" else "aie_step_kernel"
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
+    rows = list(csv.reader(open(raw_csv)))
     name = "%s_ncu_full_%s%s_raw.csv" % (tag, kernel, "" if w == "c2" else "_" + w)
     with open(os.path.join(PROF, name), "w", newline="") as f:
         csv.writer(f).writerows(rows[:3])
@@ -32,9 +31,6 @@ for w in ("c2", "c3", "c4", "c5"):
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread"]
     print(w, {k: (d.get(k), u.get(k)) for k in keys})
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-    tmp = os.path.join("/tmp", "src_%s_%s.csv" % (tag, w))
-    open(tmp, "w").write(src)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, str(ENVS[w]), "40"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src_csv, str(ENVS[w]), "40"],
                          capture_output=True, text=True, cwd=ROOT).stdout
     open(os.path.join(PROF, "%s_step_kernel_by_line_%s.txt" % (tag, w)), "w").write(out)

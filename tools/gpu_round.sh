@@ -58,4 +58,12 @@ if [[ $PH == all || $PH == *race* ]]; then
   timeout 600 compute-sanitizer --tool memcheck python tools/sanitizer_run.py > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"
   tail -5 gpurun_out/memcheck.log
 fi
-ls -la gpurun_out | head -60
+# gpurun_out/ is capped at 64 MiB: keep the CSV pages of every full capture, not the reports
+for rep in gpurun_out/prof_*.ncu-rep; do
+  [[ -f $rep ]] || continue
+  b=${rep%.ncu-rep}
+  ncu -i $rep --page raw --csv > ${b}_raw.csv 2>/dev/null
+  ncu -i $rep --page source --csv --print-source cuda,sass > ${b}_src.csv 2>/dev/null
+  rm -f $rep
+done
+du -sh gpurun_out; ls -la gpurun_out | head -60
