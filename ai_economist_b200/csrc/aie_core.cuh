@@ -1148,9 +1148,10 @@ AIE_DEV int kth_set_bit(uint32_t m, int k) {   // position of the k-th (1-based)
 AIE_DEV void rng_fill_gauss(Rng &r, double *g, double *out, int n) {
     const int lane = r.lane;
     int i = 0;
-    if (n > 0 && g[1] != 0.0) {
-        const double cached = g[0];
-        wsync();
+    const bool has_cached = n > 0 && g[1] != 0.0;
+    const double cached = g[0];
+    wsync();   // every lane has read the cache before any lane (this call's last accepted trial) refills it
+    if (has_cached) {
         if (lane == 0) { out[0] = cached; g[0] = 0.0; g[1] = 0.0; }
         wsync();
         i = 1;

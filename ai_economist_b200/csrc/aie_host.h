@@ -402,27 +402,49 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
         // the key image, or in extra memory when they do not fit; the late buffers follow them and run on into extra memory
         // behind the region as far as needed.  The flat-value staging shares its bytes with the window buffers.
         const int mt_lo = c.off_mt, mt_hi = c.off_mt + 4 * 624;
-        const int late_hi = c.resident_bytes + c.step_scratch_bytes;
+        const int scr_lo = c.resident_bytes, scr_hi = c.resident_bytes + c.step_scratch_bytes;
         auto place = [&](int ac, int fc, bool commit) {
             chunk_needs(ac);
             vals_needs(fc, commit);
             int off[OB_COUNT];
-            int early_total = 0;
-            for (int id : early_ids) early_total += need[id];
-            const bool early_in_mt = early_total <= mt_hi - mt_lo;
-            int cur = mt_lo;
-            if (early_in_mt) for (int id : early_ids) { off[id] = cur; cur += need[id]; }
-            const int late_lo = cur;
+            // early buffers: first fit, largest first, into the key image and then into the step scratch (dead as soon as the
+            // dynamics are done and never part of the write-back); if one does not fit, all of them go to extra memory
+            int order[6] = {OB_NET_HIST, OB_SHF, OB_SC_A, OB_LIM, OB_PSH, OB_LOCMAP};
+            std::sort(order, order + 6, [&](int a, int b) { return need[a] > need[b]; });
+            int cur_mt = mt_lo, cur_scr = scr_lo;
+            bool early_fits = true;
+            for (int id : order) {
+                if (need[id] <= mt_hi - cur_mt) { off[id] = cur_mt; cur_mt += need[id]; }
+                else if (need[id] <= scr_hi - cur_scr) { off[id] = cur_scr; cur_scr += need[id]; }
+                else { early_fits = false; break; }
+            }
+            if (!early_fits) { cur_mt = mt_lo; cur_scr = scr_lo; }
+            // late buffers: from the end of the early ones in the key image on, through the rest of the dead region (they
+            // stop short of early buffers parked in the scratch) and on into extra memory behind it
+            const int late_lo = cur_mt;
+            const int late_hi = (early_fits && cur_scr > scr_lo) ? scr_lo : scr_hi;
+            int cur = late_lo;
             for (int id : late_ids) { off[id] = cur; cur += need[id]; }
             off[OB_VALS] = late_lo;
             int end = std::max(cur, late_lo + need[OB_VALS]);
-            if (end < late_hi) end = late_hi;
-            if (!early_in_mt) for (int id : early_ids) { off[id] = end; end += need[id]; }
-            const int extra = end - late_hi;
+            int extra = 0;
+            if (end > late_hi) {   // the overflow continues behind the whole region: shift what lies beyond late_hi
+                const int shift = scr_hi - late_hi;   // 0, or the scratch bytes the early buffers occupy
+                if (shift) {
+                    // simplest correct placement: when the late block does not fit in front of the parked early buffers, put
+                    // the whole late block behind the region
+                    int c2 = scr_hi;
+                    for (int id : late_ids) { off[id] = c2; c2 += need[id]; }
+                    off[OB_VALS] = scr_hi;
+                    end = std::max(c2, scr_hi + need[OB_VALS]);
+                }
+                extra = end - scr_hi;
+            }
+            if (!early_fits) { int c2 = std::max(end, scr_hi); for (int id : early_ids) { off[id] = c2; c2 += need[id]; } extra = c2 - scr_hi; }
             if (commit) {
                 for (int i = 0; i < OB_COUNT; i++) c.ob[i] = off[i];
                 c.obs_extra_bytes = align16(extra);
-                c.obs_alias_mt = early_in_mt ? 1 : 0;
+                c.obs_alias_mt = early_fits ? 1 : 0;
             }
             return extra;
         };
