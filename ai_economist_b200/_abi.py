@@ -47,6 +47,7 @@ class AieConfig(C.Structure):
         ("dyn_layout", C.c_int32), ("dyn_checker", C.c_int32), ("dyn_coverage", C.c_double * 2), ("dyn_clump", C.c_double * 2),
         ("dyn_prob", C.c_void_p),
         ("scenario_kind", C.c_int32), ("agent_reward_type", C.c_int32), ("labor_exponent", C.c_double), ("labor_cost", C.c_double),
+        ("mz_partitions", C.c_int32 * 2), ("mz_zones", C.c_int32 * 3),
         ("labor_mask_first_step", C.c_int32), ("labor_skill_scale", C.c_double),
     ]
 
@@ -249,8 +250,13 @@ def config_from_spec(spec, auto_reset=True):
         cfg.dyn_checker = int(spec.get("dyn_checker", 0))
         cfg.dyn_coverage[0], cfg.dyn_coverage[1] = [float(v) for v in spec["dyn_coverage"]]
         cfg.dyn_clump[0], cfg.dyn_clump[1] = [float(v) for v in spec["dyn_clump"]]
-        prob = np.ascontiguousarray(np.asarray(spec["dyn_prob"], np.float64))
-        assert prob.shape == (2, spec["height"], spec["width"]), "dyn_prob must be float64 [2][height][width]"
-        cfg._dyn_prob_keep = prob    # aie_create copies it; kept alive until then
-        cfg.dyn_prob = prob.ctypes.data
+        if cfg.dyn_layout == 3:   # MultiZone: the maps follow from the per-reset zone shuffle
+            cfg.mz_partitions[0], cfg.mz_partitions[1] = [int(v) for v in spec["mz_partitions"]]
+            for i, v in enumerate(spec["mz_zones"]):
+                cfg.mz_zones[i] = int(v)
+        else:
+            prob = np.ascontiguousarray(np.asarray(spec["dyn_prob"], np.float64))
+            assert prob.shape == (2, spec["height"], spec["width"]), "dyn_prob must be float64 [2][height][width]"
+            cfg._dyn_prob_keep = prob    # aie_create copies it; kept alive until then
+            cfg.dyn_prob = prob.ctypes.data
     return cfg

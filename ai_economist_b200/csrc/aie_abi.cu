@@ -222,7 +222,7 @@ __device__ __forceinline__ void warp_step(const DevCfg &c, const DevBufs &b, int
         }
         __syncwarp();
         if (c.reset_mode == 1)   // reference-exact layout (dynamic scenarios) / placement / skills
-            device_reset_env<EXT>(c, rec, grec, scratch, lane, b.dyn_prob, b.dyn_work ? b.dyn_work + (size_t)env * c.HW : nullptr);
+            device_reset_env<EXT>(c, rec, grec, scratch, lane, b.dyn_prob, b.dyn_work ? b.dyn_work + (size_t)env * (c.HW + 16) : nullptr);
         finish_reset_env(c, rec, grec, scratch, lane);  // metric_0 under the new completions count
     }
 

@@ -81,8 +81,9 @@ int aie_create(const aie_config *cfg, int32_t n_envs, int32_t device, aie_env **
     if (rc != AIE_OK) { delete env; return rc; }
     if (env->cfg.dyn_layout) {   // library-owned device memory of the layout generator
         const size_t hw = (size_t)env->cfg.HW;
-        env->dyn_prob_dev = aie::be::const_upload(cfg->dyn_prob, 2 * hw * sizeof(double));
-        env->dyn_work_dev = aie::be::dev_alloc((size_t)n_envs * hw * sizeof(double));
+        // per env: the float64 work map + 16 doubles holding MultiZone's region -> zone-type bytes
+        env->dyn_prob_dev = cfg->dyn_prob ? aie::be::const_upload(cfg->dyn_prob, 2 * hw * sizeof(double)) : aie::be::dev_alloc(2 * hw * sizeof(double));
+        env->dyn_work_dev = aie::be::dev_alloc((size_t)n_envs * (hw + 16) * sizeof(double));
         if (!env->dyn_prob_dev || !env->dyn_work_dev) { aie_destroy(env); return fail(AIE_ENOMEM, "aie_create: device memory for the layout generator"); }
         env->bufs.dyn_prob = (const double *)env->dyn_prob_dev; env->bufs.dyn_work = (double *)env->dyn_work_dev;
     }

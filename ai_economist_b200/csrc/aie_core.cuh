@@ -1237,6 +1237,35 @@ AIE_DEV void gen_layout(const DevCfg &c, Env &e, Rng &r, const double *prob, dou
         for (int k = lane; k < HW; k += NL) n += (e.cell[k] & CELL_CAND) ? 1 : 0;
         return (double)wsum((double)n) / (double)HW;   // np.mean of a boolean map
     };
+    // MultiZone (dynamic_layout.py:778-872): np.random.shuffle of the region -> zone-type vector (Wood 0, Stone 1, WoodStone 2,
+    // none 255), then probability (1 / share of the world inside the resource's zones) * Wood coverage inside them, 0 outside
+    uint8_t *grid = reinterpret_cast<uint8_t *>(work + HW);
+    double mz_val[2] = {0.0, 0.0};
+    auto in_zone = [&](int ri, int k) {
+        const int m = k / W, n = k - m * W;
+        const uint8_t z = grid[(m / c.mz_psr) * c.mz_cols + (n / c.mz_psc)];
+        return z == 2 || z == (uint8_t)ri;   // ri 0 = Wood, 1 = Stone
+    };
+    if (c.dyn_layout == 3) {
+        const int nreg = c.mz_rows * c.mz_cols;
+        if (lane == 0) {
+            int at = 0;
+            for (int z = 0; z < 3; z++) for (int q = 0; q < c.mz_zones[z]; q++) grid[at++] = (uint8_t)z;
+            while (at < nreg) grid[at++] = 255;
+        }
+        wsync();
+        for (int i = nreg - 1; i >= 1; i--) {   // legacy shuffle: swap x[i] with x[random_interval(i)]
+            const int j = (int)rng_interval(r, (uint32_t)i);
+            if (lane == 0) { const uint8_t t = grid[j]; grid[j] = grid[i]; grid[i] = t; }
+            wsync();
+        }
+        for (int ri = 0; ri < 2; ri++) {
+            int cnt = 0;
+            for (int k = lane; k < HW; k += NL) cnt += in_zone(ri, k) ? 1 : 0;
+            const double mean = wsum((double)cnt) / (double)HW;
+            mz_val[ri] = (1.0 / mean) * c.dyn_cov[0];   // sic: both maps are scaled by the Wood coverage (:860-863)
+        }
+    }
     for (int attempt = 0; attempt < 100; attempt++) {
         for (int k = lane; k < HW; k += NL) e.cell[k] &= (uint8_t)~(res_bits[0] | res_bits[1] | CELL_CAND);   // maps.clear()
         wsync();
@@ -1250,7 +1279,8 @@ AIE_DEV void gen_layout(const DevCfg &c, Env &e, Rng &r, const double *prob, dou
                     if (decay) { v *= 0.9; work[k] = v; }
                     const uint8_t cb = e.cell[k];
                     const bool empty = !(cb & (res_bits[0] | res_bits[1]));
-                    e.cell[k] = (uint8_t)((cb & ~CELL_CAND) | ((v < sp[k] * 0.1 * clump && empty) ? CELL_CAND : 0));
+                    const double spk = c.dyn_layout == 3 ? (in_zone(ri, k) ? mz_val[ri] : 0.0) : sp[k];
+                    e.cell[k] = (uint8_t)((cb & ~CELL_CAND) | ((v < spk * 0.1 * clump && empty) ? CELL_CAND : 0));
                 }
                 wsync();
             };

@@ -176,8 +176,16 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     if (c.split_layout && (c.split_water_row < 1 || c.split_water_row >= c.H - 1)) return bad("split_water_row outside the world");
     if (c.split_layout && c.fixed_four) return bad("split_layout does not support fixed_four_skill_and_loc");
     c.dyn_layout = (c.reset_mode == 1) ? u.dyn_layout : 0;
-    if (c.dyn_layout < 0 || c.dyn_layout > 2) return bad("unknown dyn_layout");
-    if (c.dyn_layout && !u.dyn_prob) return bad("dyn_layout needs the source probability maps (dyn_prob)");
+    if (c.dyn_layout < 0 || c.dyn_layout > 3) return bad("unknown dyn_layout");
+    if ((c.dyn_layout == 1 || c.dyn_layout == 2) && !u.dyn_prob) return bad("dyn_layout needs the source probability maps (dyn_prob)");
+    if (c.dyn_layout == 3) {
+        c.mz_rows = u.mz_partitions[0]; c.mz_cols = u.mz_partitions[1];
+        if (c.mz_rows < 1 || c.mz_cols < 1 || c.mz_rows * c.mz_cols > 128) return bad("MultiZone: 1..128 regions");
+        int total = 0;
+        for (int i = 0; i < 3; i++) { c.mz_zones[i] = u.mz_zones[i]; if (c.mz_zones[i] < 0) return bad("MultiZone: negative zone count"); total += c.mz_zones[i]; }
+        if (total > c.mz_rows * c.mz_cols) return bad("MultiZone: more zones than regions");
+        c.mz_psr = (c.H + c.mz_rows - 1) / c.mz_rows; c.mz_psc = (c.W + c.mz_cols - 1) / c.mz_cols;   // int(np.ceil(size / partitions))
+    }
     if (c.dyn_layout && c.fixed_four) return bad("dynamic layouts have no fixed_four_skill_and_loc");
     c.dyn_checker = u.dyn_checker ? 1 : 0;
     for (int i = 0; i < 2; i++) {

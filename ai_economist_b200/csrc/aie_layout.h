@@ -162,6 +162,7 @@ struct DevCfg {
     // dynamic-layout scenarios: device-side layout generation at reset (see aie_config::dyn_layout)
     int32_t dyn_layout, dyn_checker;
     double dyn_cov[2], dyn_clump[2];   // [Wood, Stone]
+    int32_t mz_rows, mz_cols, mz_psr, mz_psc, mz_zones[3];   // MultiZone: partitions, partition size in cells, zones per type
 };
 
 // raw device pointers (mirrors aie_buffers)

@@ -293,8 +293,9 @@ class Uniform(BaseScenario):
                      dyn_coverage=[self.coverage["Wood"], self.coverage["Stone"]],
                      dyn_clump=[float(1 - np.clip(self.clumpiness["Wood"], 0.0, 0.99)),
                                 float(1 - np.clip(self.clumpiness["Stone"], 0.0, 0.99))],
-                     dyn_prob=[np.asarray(self.source_prob_maps["Wood"], np.float64).tolist(),
-                               np.asarray(self.source_prob_maps["Stone"], np.float64).tolist()],
+                     dyn_prob=(None if self.dyn_layout_kind == 3 else
+                               [np.asarray(self.source_prob_maps["Wood"], np.float64).tolist(),
+                                np.asarray(self.source_prob_maps["Stone"], np.float64).tolist()]),
                      build_skill_dist=dists.get(b.skill_dist, 0) if b else 0,
                      gather_skill_dist=dists.get(g.skill_dist, 0) if g else 0,
                      payment_max_skill_multiplier=b.payment_max_skill_multiplier if b else 1)
@@ -306,7 +307,7 @@ class MultiZone(Uniform):
     """Wood / stone / mixed source zones on a shuffled partition grid (dynamic_layout.py:706-873).  The zone
     assignment is re-shuffled from the env's stream at every reset, before the clumped layout is drawn."""
     name = "multi_zone/simple_wood_and_stone"
-    dyn_layout_kind = 0   # the zone assignment is re-shuffled at every reset: auto-reset restores the load-time snapshot
+    dyn_layout_kind = 3   # the zone assignment is re-shuffled on the device at every reset (np.random.shuffle), then the layout
 
     def __init__(self, env, num_partitions_row=8, num_partitions_col=8, num_wood_zones=6, num_stone_zones=6,
                  num_wood_and_stone_zones=4, **kw):
@@ -319,6 +320,15 @@ class MultiZone(Uniform):
             n_regions = self.num_partitions_row * self.num_partitions_col
             for rs in env._rs[1:]:
                 rs.shuffle(np.arange(n_regions))
+
+    def scenario_spec_fields(self):
+        d = super().scenario_spec_fields()
+        if d.get("dyn_layout") == 3:
+            assert self.num_partitions_row * self.num_partitions_col <= 128, "device-side MultiZone reset: at most 128 regions"
+            d.update(mz_partitions=[int(self.num_partitions_row), int(self.num_partitions_col)],
+                     mz_zones=[int(self.zone_specs[k][1]) for k in ("Wood", "Stone", "WoodStone")])
+            d.pop("dyn_prob", None)
+        return d
 
     def make_source_prob_maps(self, rs):
         """dynamic_layout.py:778-864 (one np.random.shuffle of the region -> zone-type vector)."""

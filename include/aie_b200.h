@@ -137,7 +137,10 @@ typedef struct aie_config {
      * - scipy.signal.convolve2d, 'same' - with the candidate map plus Gaussian noise; up to 100 attempts until both
      * coverages are within 1.4x of their targets), then places the agents in a random order (:418-429). */
     int32_t dyn_layout;             /* 0: layout fixed at load time; 1: Uniform generator; 2: Quadrant (generator, then
-                                       resources cleared on the two water lines, dynamic_layout.py:992-1030) */
+                                       resources cleared on the two water lines, dynamic_layout.py:992-1030); 3: MultiZone
+                                       (the region -> zone-type vector is re-shuffled from the env's stream before every
+                                       layout, np.random.shuffle, and the probability maps follow from it, :778-872;
+                                       dyn_prob is not used) */
     int32_t dyn_checker;            /* checker_source_blocks: sources only on cells with (row + col) odd (:387-392) */
     double dyn_coverage[2];         /* target coverage [Wood, Stone] (doubled when checkered, :181-186) */
     double dyn_clump[2];            /* 1 - clip(clumpiness, 0, 0.99), [Wood, Stone] */
@@ -150,6 +153,8 @@ typedef struct aie_config {
     int32_t scenario_kind;          /* 0: gather-trade-build family; 1: one-step-economy */
     int32_t agent_reward_type;      /* one-step-economy: 0 "isoelastic_coin_minus_labor", 1 "coin_minus_labor_cost" (:283-301) */
     double labor_exponent, labor_cost;      /* rewards.py:46-70 */
+    int32_t mz_partitions[2];       /* MultiZone: num_partitions_row, num_partitions_col (at most 128 regions) */
+    int32_t mz_zones[3];            /* MultiZone: number of Wood, Stone and WoodStone zones */
     int32_t labor_mask_first_step;  /* SimpleLabor mask_first_step: every labor action masked in the reset observation */
     double labor_skill_scale;       /* SimpleLabor payment_max_skill_multiplier: the skill observation is skill / this */
 } aie_config;

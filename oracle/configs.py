@@ -300,3 +300,15 @@ CONFIGS["quadrant_reset"] = dict(
     flatten_observations=True, flatten_masks=True,
     starting_agent_coin=10, starting_wood_coverage=0.08, starting_stone_coverage=0.08,
     wood_regen_weight=0.04, stone_regen_weight=0.04, checker_source_blocks=True)
+
+# MultiZone: the region -> zone-type vector is re-shuffled (np.random.shuffle) before every layout
+CONFIGS["multi_zone_reset"] = dict(
+    scenario_name="multi_zone/simple_wood_and_stone",
+    components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                ("ContinuousDoubleAuction", dict(max_num_orders=5)),
+                ("Gather", dict(skill_dist="none"))],
+    n_agents=4, world_size=[20, 17], episode_length=26,
+    multi_action_mode_agents=False, multi_action_mode_planner=True,
+    flatten_observations=True, flatten_masks=True,
+    starting_agent_coin=5, starting_wood_coverage=0.1, starting_stone_coverage=0.1,
+    num_partitions_row=4, num_partitions_col=3, num_wood_zones=3, num_stone_zones=3, num_wood_and_stone_zones=2)

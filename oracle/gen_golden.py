@@ -48,6 +48,7 @@ PLAN = [
     ("us_federal_annealed_reset", 1001, 90, 5),
     ("uniform_reset", 1001, 100, 10),
     ("quadrant_reset", 1001, 95, 7),
+    ("multi_zone_reset", 1001, 90, 8),
 ]
 
 EXACT_OBS = ["a_map", "a_idx", "a_mask", "p_map", "p_idx", "p_mask"]

@@ -120,7 +120,7 @@ int launch_step(aie_env *env, int emit_obs, void *) {
             hdr[HDR_COMPLETIONS] = completions; hdr[HDR_AUTO_WARMUP] = warm; hdr[HDR_MT_POS] = mt_pos;
             hdr[HDR_EPISODES] = episodes; hdr[HDR_SAEZ_N] = saez_n;
             if (c.reset_mode == 1) {
-                double *work = b.dyn_work ? b.dyn_work + (size_t)e * c.HW : nullptr;
+                double *work = b.dyn_work ? b.dyn_work + (size_t)e * (c.HW + 16) : nullptr;
                 if (c.ext) device_reset_env<true>(c, rec, rec, env->be.scratch.data(), 0, b.dyn_prob, work);
                 else device_reset_env<false>(c, rec, rec, env->be.scratch.data(), 0, b.dyn_prob, work);
             }

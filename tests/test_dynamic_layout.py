@@ -53,6 +53,6 @@ def test_dynamic_scenarios_select_the_device_generator():
         assert env.spec["reset_mode"] == 1 and env.spec["dyn_layout"] == kind
     mz = foundation.make_env_instance("multi_zone/simple_wood_and_stone", num_partitions_row=3, num_partitions_col=3,
                                       num_wood_zones=3, num_stone_zones=3, num_wood_and_stone_zones=2, **base)
-    assert mz.spec.get("reset_mode", 0) == 0   # zone shuffle per reset: snapshot restore
+    assert mz.spec["reset_mode"] == 1 and mz.spec["dyn_layout"] == 3 and mz.spec["mz_zones"] == [3, 3, 2]
     snap = foundation.make_env_instance("uniform/simple_wood_and_stone", device_reset="snapshot", **base)
     assert snap.spec["reset_mode"] == 0

@@ -119,6 +119,23 @@ def test_fuzz_dynamic_layout_device_reset_matches_live_reference(i):
 
 @needs_reference
 @pytest.mark.reference
+@pytest.mark.parametrize("i", range(10))
+def test_fuzz_multi_zone_device_reset_matches_live_reference(i, monkeypatch):
+    """multi_zone: np.random.shuffle of the region -> zone-type vector on the device before every layout."""
+    import fuzz_device_reset_vs_reference as fr
+
+    monkeypatch.setattr(fr, "FAMILIES", ["multi_zone"])
+    cfg = _configs(21, n=10, draw=fr.random_dynamic_config)[i]
+    try:
+        fr.run_one(cfg, seed=650 + i, episodes=3)
+    except (TimeoutError, AssertionError) as ex:
+        if isinstance(ex, AssertionError) and "coverage" not in str(ex) and "World" not in str(ex):
+            raise
+        pytest.skip(repr(ex))   # the reference refusing its own configuration
+
+
+@needs_reference
+@pytest.mark.reference
 @pytest.mark.parametrize("i", range(N_CASES))
 def test_fuzz_reference_api_matches_live_reference(i):
     import fuzz_reference_api_vs_reference as fa

@@ -49,9 +49,12 @@ def random_config(rng):
                 energy_warmup_constant=float(rng.choice([0, 4])), energy_warmup_method="decay")
 
 
+FAMILIES = ["uniform", "quadrant"]   # tests/test_fuzz_subsets.py: the multi_zone subset sets ["multi_zone"]
+
+
 def random_dynamic_config(rng):
     """uniform/... and quadrant/... : every reset generates a new clumped layout on the device (dynamic_layout.py:313-429)."""
-    fam = str(rng.choice(["uniform", "quadrant"]))
+    fam = str(rng.choice(FAMILIES))
     H = int(rng.randint(9, 27)); W = H if fam == "quadrant" else int(rng.randint(9, 27))
     A = int(rng.choice([2, 3, 5, 8]))
     comps = [("Build", dict(skill_dist=str(rng.choice(["none", "pareto", "lognormal"])), payment_max_skill_multiplier=int(rng.randint(1, 4)))),
@@ -64,7 +67,10 @@ def random_dynamic_config(rng):
                 starting_wood_coverage=float(rng.choice([0.05, 0.1, 0.15])), starting_stone_coverage=float(rng.choice([0.05, 0.1])),
                 wood_clumpiness=float(rng.choice([0.0, 0.35, 0.8])), stone_clumpiness=float(rng.choice([0.2, 0.5, 1.0])),
                 gradient_steepness=float(rng.choice([1, 4, 8])), checker_source_blocks=bool(rng.rand() < 0.3),
-                wood_regen_weight=float(rng.choice([0.05, 0.5])), stone_regen_weight=float(rng.choice([0.05, 0.5])))
+                wood_regen_weight=float(rng.choice([0.05, 0.5])), stone_regen_weight=float(rng.choice([0.05, 0.5])),
+                **(dict(num_partitions_row=int(rng.choice([2, 3, 4])), num_partitions_col=int(rng.choice([2, 3, 5])),
+                        num_wood_zones=int(rng.choice([1, 2])), num_stone_zones=int(rng.choice([1, 2])),
+                        num_wood_and_stone_zones=int(rng.choice([0, 1]))) if fam == "multi_zone" else {}))
 
 
 def run_one(cfg, seed, episodes=4):
@@ -122,7 +128,9 @@ if __name__ == "__main__":
     n = int(args[0]) if len(args) > 0 else 30
     rng = np.random.RandomState(int(args[1]) if len(args) > 1 else 0)
     bad, kinds = 0, {}
-    dynamic = "--dynamic" in sys.argv
+    dynamic = "--dynamic" in sys.argv or "--multi-zone" in sys.argv
+    if "--multi-zone" in sys.argv:
+        FAMILIES[:] = ["multi_zone"]
     for i in range(n):
         cfg = (random_dynamic_config if dynamic else random_config)(rng)
         kinds[cfg["scenario_name"].split("/")[0]] = kinds.get(cfg["scenario_name"].split("/")[0], 0) + 1
