@@ -531,9 +531,11 @@ class BatchedFoundationEnv:
             st = self._stepper
             lay_a, lay_p, lay_pa = st.flat_layout("agent"), st.flat_layout("planner"), st.flat_layout("planner_agent")
         obs = {}
+        spatial = int(self._spec.get("scenario_kind", 0)) != 1   # the one-step-economy has no spatial observations at all
         for i in range(A):
-            obs[str(i)] = {"world-map": b["obs_agent_map"][:, i], "world-idx_map": b["obs_agent_idx"][:, i],
-                           "time": b["obs_time"]}
+            obs[str(i)] = {"time": b["obs_time"]}
+            if spatial:
+                obs[str(i)].update({"world-map": b["obs_agent_map"][:, i], "world-idx_map": b["obs_agent_idx"][:, i]})
             if flat_o:
                 obs[str(i)]["flat"] = b["obs_agent_flat"][:, i]
             else:
@@ -565,9 +567,10 @@ class BatchedFoundationEnv:
             time_a = time_a.expand(self.n_envs, A) if hasattr(time_a, "expand") else np.broadcast_to(time_a, (self.n_envs, A))
             if not (flat_o and flat_m):
                 raise NotImplementedError("collate_agent_step_and_reset_data needs flattened observations and masks")
-            obs = {"a": {"world-map": last(b["obs_agent_map"]), "world-idx_map": last(b["obs_agent_idx"]),
-                         "flat": last(b["obs_agent_flat"]), "time": time_a, "action_mask": last(b["mask_agent"])},
+            obs = {"a": {"flat": last(b["obs_agent_flat"]), "time": time_a, "action_mask": last(b["mask_agent"])},
                    "p": obs["p"]}
+            if spatial:
+                obs["a"].update({"world-map": last(b["obs_agent_map"]), "world-idx_map": last(b["obs_agent_idx"])})
             self.rew = {"a": b["reward"][:, :A], "p": b["reward"][:, A]}
             self.info = {"a": {str(i): {} for i in range(A)}, "p": {}}
         self.obs = obs
@@ -577,9 +580,11 @@ class BatchedFoundationEnv:
         o = self._stepper.read_obs(e)
         A = self.n_agents
         obs = {}
+        spatial = int(self._spec.get("scenario_kind", 0)) != 1
         for i in range(A):
-            obs[str(i)] = {"world-map": o["a_map"][i], "world-idx_map": o["a_idx"][i], "flat": o["a_flat"][i],
-                           "time": o["time"].astype(np.float64), "action_mask": o["a_mask"][i]}
+            obs[str(i)] = {"flat": o["a_flat"][i], "time": o["time"].astype(np.float64), "action_mask": o["a_mask"][i]}
+            if spatial:
+                obs[str(i)].update({"world-map": o["a_map"][i], "world-idx_map": o["a_idx"][i]})
         obs["p"] = {"flat": o["p_flat"], "time": o["time"].astype(np.float64), "action_mask": o["p_mask"]}
         if "p_map" in o:
             obs["p"]["world-map"], obs["p"]["world-idx_map"] = o["p_map"], o["p_idx"]

@@ -68,7 +68,7 @@ def random_dynamic_config(rng):
                 wood_clumpiness=float(rng.choice([0.0, 0.35, 0.8])), stone_clumpiness=float(rng.choice([0.2, 0.5, 1.0])),
                 gradient_steepness=float(rng.choice([1, 4, 8])), checker_source_blocks=bool(rng.rand() < 0.3),
                 wood_regen_weight=float(rng.choice([0.05, 0.5])), stone_regen_weight=float(rng.choice([0.05, 0.5])),
-                **(dict(num_partitions_row=int(rng.choice([2, 3, 4])), num_partitions_col=int(rng.choice([2, 3, 5])),
+                **(dict(num_partitions_row=int(rng.choice([3, 4])), num_partitions_col=int(rng.choice([2, 3, 5])),   # >= 6 regions >= 5 zones
                         num_wood_zones=int(rng.choice([1, 2])), num_stone_zones=int(rng.choice([1, 2])),
                         num_wood_and_stone_zones=int(rng.choice([0, 1]))) if fam == "multi_zone" else {}))
 
