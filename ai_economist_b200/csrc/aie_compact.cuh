@@ -62,12 +62,16 @@ inline CompactLayout compact_layout(const DevCfg &c) {
 // ---- device side: one warp packs one env -----------------------------------------------------------------------
 AIE_DEV void pack_bits(const float *src, int n, uint32_t *dst, int lane) {
 #if AIE_ON_DEVICE
-    // four independent loads in flight per lane (the pass is latency-bound otherwise: one 128-byte row per round trip)
+    // eight independent loads in flight per lane (the pass is latency-bound otherwise: one 128-byte row per round trip)
     int w0 = 0;
-    for (; w0 + 128 <= n; w0 += 128) {
-        const float v0 = src[w0 + lane], v1 = src[w0 + 32 + lane], v2 = src[w0 + 64 + lane], v3 = src[w0 + 96 + lane];
-        const uint32_t b0 = wballot(v0 != 0.0f), b1 = wballot(v1 != 0.0f), b2 = wballot(v2 != 0.0f), b3 = wballot(v3 != 0.0f);
-        if (lane < 4) dst[(w0 >> 5) + lane] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
+    for (; w0 + 256 <= n; w0 += 256) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = src[w0 + 32 * j + lane];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const uint32_t b = wballot(v[j] != 0.0f); if (lane == j) mine = b; }
+        if (lane < 8) dst[(w0 >> 5) + lane] = mine;
     }
     for (; w0 < n; w0 += 32) {
         const int i = w0 + lane;
@@ -86,7 +90,21 @@ AIE_DEV void pack_bits(const float *src, int n, uint32_t *dst, int lane) {
 AIE_DEV int pack_sparse_u8(const int16_t *src, int n, uint32_t *mask, uint8_t *vals, int cap, int lane) {
     int running = 0;
 #if AIE_ON_DEVICE
-    for (int w0 = 0; w0 < n; w0 += 32) {
+    int w0 = 0;
+    for (; w0 + 128 <= n; w0 += 128) {   // four rows in flight
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (int)src[w0 + 32 * j + lane];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b = wballot(v[j] != 0);
+            if (lane == 0) mask[(w0 >> 5) + j] = b;
+            const int pos = running + __popc(b & ((1u << lane) - 1u));
+            if (v[j] != 0 && pos < cap) vals[pos] = (uint8_t)v[j];
+            running += __popc(b);
+        }
+    }
+    for (; w0 < n; w0 += 32) {
         const int i = w0 + lane;
         const int v = i < n ? (int)src[i] : 0;
         const uint32_t b = wballot(v != 0);
