@@ -257,11 +257,13 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * wpb + warp;
     const uint16_t *tab = stage_tables(smem, wpb, c, b);
-    if (env >= c.n_envs) return;  // from here on warps are independent: no block-wide barrier below
+    const bool phase_sync = emit_obs & 2;   // tuning aid (AIE_PHASE_SYNC): all warps of a CTA enter the observation pass together
+    if (env >= c.n_envs && !phase_sync) return;  // from here on warps are independent: no block-wide barrier below
     uint64_t *bar = (uint64_t *)smem + warp;
     uint8_t *rec = warp_region(smem, wpb, warp, c);
-    warp_step<false, EXT>(c, b, env, rec, bar, tab, lane);
-    if (emit_obs) observe_env<EXT>(c, rec, b.state + (size_t)env * c.rec_bytes, rec, c.ob, obs_out_for(c, b, env), tab, DevExec<32, true>{lane});
+    if (env < c.n_envs) warp_step<false, EXT>(c, b, env, rec, bar, tab, lane);
+    if (phase_sync) { __syncthreads(); if (env >= c.n_envs) return; }
+    if (emit_obs & 1) observe_env<EXT>(c, rec, b.state + (size_t)env * c.rec_bytes, rec, c.ob, obs_out_for(c, b, env), tab, DevExec<32, true>{lane});
     else if (lane == 0) bulk_wait_read();
 }
 
@@ -521,6 +523,8 @@ int launch_step(aie_env *env, int emit_obs, void *stream) {
     const int wpb = env->be.step_wpb;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = env->be.step_smem;
+    static const int phase_sync = getenv("AIE_PHASE_SYNC") ? 2 : 0;
+    if (env->cfg.mw == 1) emit_obs = (emit_obs ? 1 : 0) | phase_sync;
     if (env->cfg.mw > 1) {   // large records: one CTA of four warps per env
         const dim3 grid(env->n_envs), block(32 * env->cfg.mw);
         if (env->cfg.ext) {

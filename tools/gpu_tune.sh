@@ -1,9 +1,9 @@
 #!/bin/bash
-# Tuning sweep on the box: envs per CTA (wave quantisation) for c2 / c3, warps-per-env x split for c5.
+# Tuning sweep on the box: launch-shape knobs of the fused step kernel (AIE_STEP_WPB, AIE_STEP_MINB, AIE_PHASE_SYNC, AIE_MW, AIE_SPLIT).
+# usage: bash tools/gpu_tune.sh [phase|wpb|c5]...
 set -u
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or batch" > gpurun_out/pytest_tune.log 2>&1; tail -2 gpurun_out/pytest_tune.log
 B="--no-cpu-baseline --no-extra-workloads --e2e-steps 3 --steps 100 --warmup 10"
 run() {  # label, env assignments..., -- bench args
   local label=$1; shift
@@ -21,8 +21,20 @@ except Exception as ex:
     print(sys.argv[1], "failed:", ex)
 PY
 }
-for w in 8 7 6; do run c2_wpb$w AIE_STEP_WPB=$w -- --workload c2; done
-for w in 8 7 6 5; do run c3_wpb$w AIE_STEP_WPB=$w -- --workload c3 --preroll 300; done
-run c5_mw4_split0 AIE_MW=4 AIE_SPLIT=0 -- --workload c5 --steps 40 --preroll 100
-run c5_mw4_split1 AIE_MW=4 AIE_SPLIT=1 -- --workload c5 --steps 40 --preroll 100
-run c5_mw1_split1 AIE_MW=1 AIE_SPLIT=1 -- --workload c5 --steps 40 --preroll 100
+WHAT="${*:-phase}"
+if [[ $WHAT == *phase* ]]; then
+  timeout 300 env AIE_PHASE_SYNC=1 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden" > gpurun_out/pytest_tune.log 2>&1; tail -2 gpurun_out/pytest_tune.log
+  run c2_base X=1 -- --workload c2
+  run c2_phase_sync AIE_PHASE_SYNC=1 -- --workload c2
+  run c3_base X=1 -- --workload c3 --preroll 300
+  run c3_phase_sync AIE_PHASE_SYNC=1 -- --workload c3 --preroll 300
+fi
+if [[ $WHAT == *wpb* ]]; then
+  for w in 8 7 6; do run c2_wpb$w AIE_STEP_WPB=$w -- --workload c2; done
+  for w in 8 7 6 5; do run c3_wpb$w AIE_STEP_WPB=$w -- --workload c3 --preroll 300; done
+fi
+if [[ $WHAT == *c5* ]]; then
+  run c5_mw4_split0 AIE_MW=4 AIE_SPLIT=0 -- --workload c5 --steps 40 --preroll 100
+  run c5_mw4_split1 AIE_MW=4 AIE_SPLIT=1 -- --workload c5 --steps 40 --preroll 100
+  run c5_mw1_split1 AIE_MW=1 AIE_SPLIT=1 -- --workload c5 --steps 40 --preroll 100
+fi
