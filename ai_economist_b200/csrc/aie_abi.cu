@@ -33,8 +33,11 @@ struct State {
     size_t obs_smem;
     uint16_t *tab_dev;   // observation programs (device copy)
     uint8_t *compact_dev = nullptr, *compact_host = nullptr;   // aie_step_host_compact: device + pinned host staging
-    size_t compact_bytes = 0;
+    size_t compact_bytes = 0, compact_host_bytes = 0;
+    int compact_host_node = -1;   // >= 0: staging pages bound to that NUMA node (mmap + mbind + cudaHostRegister)
     cudaEvent_t slice_ev[AIE_MAX_SLICES_BE] = {};
+    cudaStream_t copy_st = nullptr;   // aie_step_host_compact: the slices go down on this stream while later chunks still step
+    cudaEvent_t chunk_ev = nullptr, tail_ev = nullptr;
     cudaEvent_t call_ev = nullptr;   // recorded when a host-buffer step starts enqueueing (timing reference of the slices)   // one per transfer slice of the compacted D2H copy
 };
 // Makes `device` current for the lifetime of the object and restores the caller's device afterwards, so a handle
@@ -60,10 +63,14 @@ int sync(aie_env *, void *stream);
 int sync_all(aie_env *);
 int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, int emit_obs, void *stream);
+int launch_step_range(aie_env *, int emit_obs, int lo, int hi, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
 int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
-int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
+int staging_node(aie_env *);
+int launch_pack_range(aie_env *, const CompactLayout &L, uint8_t *dev, int lo, int hi, void *stream);
+int chunk_ready(aie_env *, void *stream);
+int copies_done(aie_env *, void *stream);
 int download_slice(aie_env *, int k, void *host, const void *dev, size_t n, void *stream);
 int wait_slice(aie_env *, int k);
 double slice_device_ms(aie_env *, int k);
@@ -84,8 +91,8 @@ namespace aie {
 
 // compacted D2H transfer (aie_compact.cuh): one warp rewrites one env's outputs as a compact record
 __global__ void __launch_bounds__(256) aie_pack_kernel(const __grid_constant__ DevCfg c, const DevBufs b, const CompactLayout L,
-                                                       uint8_t *dst) {
-    const size_t env = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+                                                       uint8_t *dst, int env_lo) {
+    const size_t env = (size_t)env_lo + ((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);   // c.n_envs = end of the range
     if (env >= (size_t)c.n_envs) return;
     pack_env(c, b, L, env, dst + env * (size_t)L.bytes, threadIdx.x & 31);
 }
@@ -252,10 +259,10 @@ __device__ __forceinline__ void warp_step(const DevCfg &c, const DevBufs &b, int
 // (occupancy vs. registers per thread).
 template <int MINB, bool EXT = false>
 __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
-                                                              const int emit_obs) {
+                                                              const int emit_obs, const int env_lo) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * wpb + warp;
+    const int env = env_lo + blockIdx.x * wpb + warp;   // the launch covers envs [env_lo, c.n_envs)
     const uint16_t *tab = stage_tables(smem, wpb, c, b);
     const bool phase_sync = emit_obs & 2;   // tuning aid (AIE_PHASE_SYNC): all warps of a CTA enter the observation pass together
     if (env >= c.n_envs && !phase_sync) return;  // from here on warps are independent: no block-wide barrier below
@@ -270,9 +277,9 @@ __global__ void __launch_bounds__(256, MINB) aie_step_kernel(const __grid_consta
 // Large records: one CTA of four warps per env.  Warp 0 runs the (serial) dynamics; all four stream the observations.
 template <bool BIG, bool EXT = false>
 __global__ void __launch_bounds__(128, 4) aie_step_mw_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ DevBufs b,
-                                                             const int emit_obs) {
+                                                             const int emit_obs, const int env_lo) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int env = blockIdx.x;
+    const int env = env_lo + blockIdx.x;
     const uint16_t *tab = stage_tables(smem, 1, c, b);
     uint8_t *rec = warp_region(smem, 1, 0, c);
     if (threadIdx.x < 32) warp_step<BIG, EXT>(c, b, env, rec, (uint64_t *)smem, tab, threadIdx.x);
@@ -446,18 +453,23 @@ int init(aie_env *env) {
     }
     return AIE_OK;
 }
+static void free_compact_host(aie_env *env);
 void destroy(aie_env *env) {
     if (env->be.tab_dev) cudaFree(env->be.tab_dev);
+    if (env->be.copy_st) cudaStreamDestroy(env->be.copy_st);
+    if (env->be.chunk_ev) cudaEventDestroy(env->be.chunk_ev);
+    if (env->be.tail_ev) cudaEventDestroy(env->be.tail_ev);
     if (env->be.compact_dev) cudaFree(env->be.compact_dev);
-    if (env->be.compact_host) cudaFreeHost(env->be.compact_host);
+    free_compact_host(env);
     for (cudaEvent_t &ev : env->be.slice_ev) if (ev) cudaEventDestroy(ev);
     if (env->be.call_ev) cudaEventDestroy(env->be.call_ev);
 }
 int download_slice(aie_env *env, int k, void *host, const void *dev, size_t n, void *stream) {
     if (k < 0 || k >= AIE_MAX_SLICES_BE) return fail(AIE_EINVAL, "transfer slice index");
     if (!env->be.slice_ev[k]) AIE_CUDA(cudaEventCreate(&env->be.slice_ev[k]), "cudaEventCreate");
-    AIE_CUDA(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H slice");
-    AIE_CUDA(cudaEventRecord(env->be.slice_ev[k], (cudaStream_t)stream), "cudaEventRecord");
+    cudaStream_t cs = env->be.copy_st ? env->be.copy_st : (cudaStream_t)stream;   // after chunk_ready: the copy stream
+    AIE_CUDA(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, cs), "D2H slice");
+    AIE_CUDA(cudaEventRecord(env->be.slice_ev[k], cs), "cudaEventRecord");
     return AIE_OK;
 }
 int wait_slice(aie_env *env, int k) { return cudaEventSynchronize(env->be.slice_ev[k]) == cudaSuccess ? AIE_OK : AIE_ECUDA; }
@@ -472,23 +484,70 @@ double slice_device_ms(aie_env *env, int k) {
     if (cudaEventElapsedTime(&ms, env->be.call_ev, env->be.slice_ev[k]) != cudaSuccess) { cudaGetLastError(); return -1.0; }
     return (double)ms;
 }
+static void free_compact_host(aie_env *env) {
+    if (!env->be.compact_host) return;
+    if (env->be.compact_host_node >= 0) { cudaHostUnregister(env->be.compact_host); free_on_node(env->be.compact_host, env->be.compact_host_bytes); }
+    else cudaFreeHost(env->be.compact_host);
+    env->be.compact_host = nullptr; env->be.compact_host_node = -1;
+}
 int compact_buffers(aie_env *env, size_t bytes, uint8_t **dev, uint8_t **host) {
     if (env->be.compact_bytes < bytes) {
         if (env->be.compact_dev) cudaFree(env->be.compact_dev);
-        if (env->be.compact_host) cudaFreeHost(env->be.compact_host);
-        env->be.compact_dev = env->be.compact_host = nullptr; env->be.compact_bytes = 0;
+        free_compact_host(env);
+        env->be.compact_dev = nullptr; env->be.compact_bytes = 0;
         AIE_CUDA(cudaMalloc((void **)&env->be.compact_dev, bytes), "cudaMalloc compact buffer");
-        AIE_CUDA(cudaHostAlloc((void **)&env->be.compact_host, bytes, cudaHostAllocDefault), "cudaHostAlloc compact buffer");
+        // AIE_E2E_STAGING_NODE: -1 (default) plain cudaHostAlloc, k >= 0 pages bound to NUMA node k, -2 the node the GPU
+        // hangs off.  No placement was reliably faster than the plain allocation on the B200 host (the staging traffic is
+        // 7 % of the expansion's), so this stays a tuning aid.
+        int node = -1;
+        if (const char *v = getenv("AIE_E2E_STAGING_NODE")) node = atoi(v);
+        if (node == -2) {
+            char bus[64] = {0};
+            node = (numa_node_count() > 1 && cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), env->device) == cudaSuccess) ? pci_numa_node(bus) : -1;
+            cudaGetLastError();
+        }
+        if (node >= 0) {
+            const size_t rounded = (bytes + 4095) & ~(size_t)4095;
+            void *p = alloc_on_node(rounded, node);
+            if (p && cudaHostRegister(p, rounded, cudaHostRegisterDefault) == cudaSuccess) {
+                env->be.compact_host = (uint8_t *)p; env->be.compact_host_node = node; env->be.compact_host_bytes = rounded;
+            } else { cudaGetLastError(); free_on_node(p, rounded); }
+        }
+        if (!env->be.compact_host) {
+            AIE_CUDA(cudaHostAlloc((void **)&env->be.compact_host, bytes, cudaHostAllocDefault), "cudaHostAlloc compact buffer");
+            env->be.compact_host_node = -1;
+        }
         env->be.compact_bytes = bytes;
     }
     *dev = env->be.compact_dev; *host = env->be.compact_host;
     return AIE_OK;
 }
-int launch_pack(aie_env *env, const CompactLayout &L, uint8_t *dev, void *stream) {
-    const long long warps = env->n_envs;
-    aie_pack_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(env->cfg, env->bufs, L, dev);
+int staging_node(aie_env *env) { return env->be.compact_host_node; }
+int launch_pack_range(aie_env *env, const CompactLayout &L, uint8_t *dev, int lo, int hi, void *stream) {
+    if (lo < 0 || hi > env->n_envs || hi <= lo) return fail(AIE_EINVAL, "launch_pack_range: env range");
+    const long long warps = hi - lo;
+    DevCfg ranged;
+    const DevCfg *cp = &env->cfg;
+    if (hi != env->n_envs) { ranged = env->cfg; ranged.n_envs = hi; cp = &ranged; }
+    aie_pack_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(*cp, env->bufs, L, dev, lo);
     AIE_CUDA(cudaGetLastError(), "aie_pack_kernel launch");
     env->launches++;
+    return AIE_OK;
+}
+// The compact records of everything enqueued on `stream` so far may go down: later download_slice calls (copy stream) wait for it.
+int chunk_ready(aie_env *env, void *stream) {
+    if (!env->be.copy_st) AIE_CUDA(cudaStreamCreateWithFlags(&env->be.copy_st, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!env->be.chunk_ev) AIE_CUDA(cudaEventCreateWithFlags(&env->be.chunk_ev, cudaEventDisableTiming), "cudaEventCreate");
+    AIE_CUDA(cudaEventRecord(env->be.chunk_ev, (cudaStream_t)stream), "cudaEventRecord");
+    AIE_CUDA(cudaStreamWaitEvent(env->be.copy_st, env->be.chunk_ev, 0), "cudaStreamWaitEvent");
+    return AIE_OK;
+}
+// `stream` continues only after every slice enqueued so far has arrived (stream-order semantics of the call are the caller's stream's).
+int copies_done(aie_env *env, void *stream) {
+    if (!env->be.copy_st) return AIE_OK;
+    if (!env->be.tail_ev) AIE_CUDA(cudaEventCreateWithFlags(&env->be.tail_ev, cudaEventDisableTiming), "cudaEventCreate");
+    AIE_CUDA(cudaEventRecord(env->be.tail_ev, env->be.copy_st), "cudaEventRecord");
+    AIE_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, env->be.tail_ev, 0), "cudaStreamWaitEvent");
     return AIE_OK;
 }
 
@@ -519,27 +578,34 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *stream) {
     env->launches++;
     return AIE_OK;
 }
-int launch_step(aie_env *env, int emit_obs, void *stream) {
-    const int wpb = env->be.step_wpb;
+int launch_step(aie_env *env, int emit_obs, void *stream) { return launch_step_range(env, emit_obs, 0, env->n_envs, stream); }
+// One launch over envs [lo, hi): the kernels take the range as (env_lo, cfg.n_envs = hi); env replicas never interact.
+int launch_step_range(aie_env *env, int emit_obs, int lo, int hi, void *stream) {
+    const int wpb = env->be.step_wpb, n = hi - lo;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t sm = env->be.step_smem;
+    if (lo < 0 || hi > env->n_envs || n <= 0) return fail(AIE_EINVAL, "launch_step_range: env range");
     static const int phase_sync = getenv("AIE_PHASE_SYNC") ? 2 : 0;
     if (env->cfg.mw == 1) emit_obs = (emit_obs ? 1 : 0) | phase_sync;
+    DevCfg ranged;
+    const DevCfg *cp = &env->cfg;
+    if (hi != env->n_envs) { ranged = env->cfg; ranged.n_envs = hi; cp = &ranged; }
+    const DevCfg &cfg = *cp;
     if (env->cfg.mw > 1) {   // large records: one CTA of four warps per env
-        const dim3 grid(env->n_envs), block(32 * env->cfg.mw);
+        const dim3 grid(n), block(32 * env->cfg.mw);
         if (env->cfg.ext) {
-            if (env->cfg.split) aie_step_mw_kernel<true, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-            else aie_step_mw_kernel<false, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        } else if (env->cfg.split) aie_step_mw_kernel<true, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        else aie_step_mw_kernel<false, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+            if (env->cfg.split) aie_step_mw_kernel<true, true><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+            else aie_step_mw_kernel<false, true><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+        } else if (env->cfg.split) aie_step_mw_kernel<true, false><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+        else aie_step_mw_kernel<false, false><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
     } else {
-        const dim3 grid((env->n_envs + wpb - 1) / wpb), block(wpb * 32);
+        const dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
         if (env->cfg.ext) {  // rarely used options compiled in (single-action planner, regen halfwidth); 48-register variant omitted
-            if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-            else aie_step_kernel<3, true><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
-        else aie_step_kernel<3, false><<<grid, block, sm, st>>>(env->cfg, env->bufs, emit_obs);
+            if (env->be.step_minb >= 4) aie_step_kernel<4, true><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+            else aie_step_kernel<3, true><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+        } else if (env->be.step_minb == 5) aie_step_kernel<5, false><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+        else if (env->be.step_minb == 4) aie_step_kernel<4, false><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
+        else aie_step_kernel<3, false><<<grid, block, sm, st>>>(cfg, env->bufs, emit_obs, lo);
     }
     AIE_CUDA(cudaGetLastError(), "aie_step_kernel launch");
     env->launches++;

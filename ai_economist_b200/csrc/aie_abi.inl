@@ -266,28 +266,46 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
         rc = aie::be::upload(env, (void *)env->bufs.act_p, act_p, E * c.n_act_p * 4, stream);
         if (rc != AIE_OK) return rc;
     }
-    rc = aie_step(env, stream);
-    if (rc != AIE_OK) return rc;
     const aie::CompactLayout L = aie::compact_layout(c);
     uint8_t *dev = nullptr, *host = nullptr;
     rc = aie::be::compact_buffers(env, E * (size_t)L.bytes, &dev, &host);
     if (rc != AIE_OK) return rc;
-    rc = aie::be::launch_pack(env, L, dev, stream);
-    if (rc != AIE_OK) return rc;
-    // The compact records go down in up to AIE_MAX_SLICES slices, each followed by an event; a work item first waits for
-    // the slice holding its envs, so the expansion of the early slices overlaps the transfer of the later ones.
+    // The batch is stepped in up to AIE_E2E_CHUNKS launches (env replicas never interact); the compact records of a chunk go
+    // down, on the library's copy stream, in slices (AIE_MAX_SLICES in total), each followed by an event, while the next chunk
+    // still steps.  A work item first waits for the slice holding its envs, so the expansion of the early slices overlaps
+    // the later chunks' kernels and transfers.
     using clk = std::chrono::steady_clock;
     const clk::time_point t0 = clk::now();
     auto ms_since = [&](clk::time_point t) { return std::chrono::duration<double, std::milli>(t - t0).count(); };
-    const int chunk = 32, n_items = (int)((E + chunk - 1) / chunk);   // envs per work item
+    int chunk = 16;   // envs per work item (AIE_E2E_ITEM_ENVS: 8 .. 64); short items keep the tail after the last slice short
+    if (const char *v = getenv("AIE_E2E_ITEM_ENVS")) { const int k = atoi(v); if (k >= 8 && k <= 64) chunk = k; }
+    const int n_items = (int)((E + chunk - 1) / chunk);
     int n_slices = n_items < aie::AIE_MAX_SLICES ? n_items : aie::AIE_MAX_SLICES;
     const int items_per_slice = (n_items + n_slices - 1) / n_slices;
     n_slices = (n_items + items_per_slice - 1) / items_per_slice;
+    int n_chunks = 4;
+    if (const char *v = getenv("AIE_E2E_CHUNKS")) n_chunks = atoi(v);
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > n_slices) n_chunks = n_slices;
+    const int slices_per_chunk = (n_slices + n_chunks - 1) / n_chunks;
+    auto slice_lo = [&](int k) { const size_t v = (size_t)k * items_per_slice * chunk; return v < E ? v : E; };
     for (int k = 0; k < n_slices; k++) {
-        const size_t lo = (size_t)k * items_per_slice * chunk, hi = (size_t)(k + 1) * items_per_slice * chunk < E ? (size_t)(k + 1) * items_per_slice * chunk : E;
+        if (k % slices_per_chunk == 0) {
+            const int k_end = k + slices_per_chunk < n_slices ? k + slices_per_chunk : n_slices;
+            const int lo = (int)slice_lo(k), hi = (int)slice_lo(k_end);
+            rc = aie::be::launch_step_range(env, 1, lo, hi, stream);
+            if (rc != AIE_OK) return rc;
+            rc = aie::be::launch_pack_range(env, L, dev, lo, hi, stream);
+            if (rc != AIE_OK) return rc;
+            rc = aie::be::chunk_ready(env, stream);
+            if (rc != AIE_OK) return rc;
+        }
+        const size_t lo = slice_lo(k), hi = slice_lo(k + 1);
         rc = aie::be::download_slice(env, k, host + lo * (size_t)L.bytes, dev + lo * (size_t)L.bytes, (hi - lo) * (size_t)L.bytes, stream);
         if (rc != AIE_OK) return rc;
     }
+    rc = aie::be::copies_done(env, stream);
+    if (rc != AIE_OK) return rc;
     const double t_enqueued = ms_since(clk::now());
     int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     if (want < 1) want = 1;
@@ -304,8 +322,11 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     if (numa_mode && env->pool->nodes() > 1 && o->obs_agent_map &&
         (env->item_node_key != (const void *)o->obs_agent_map || env->item_node_n != (size_t)n_items)) {
         env->item_node.assign((size_t)n_items, -1);   // where the (dominant) agent-map rows of every item live
-        for (int i = 0; i < n_items; i++)
-            env->item_node[i] = (signed char)aie::numa_node_of(o->obs_agent_map + ((size_t)i * chunk + chunk / 2) * (size_t)L.n_a_map);
+        for (int i = 0; i < n_items; i++) {
+            size_t mid = (size_t)i * chunk + chunk / 2;
+            if (mid >= E) mid = E - 1;
+            env->item_node[i] = (signed char)aie::numa_node_of(o->obs_agent_map + mid * (size_t)L.n_a_map);
+        }
         env->item_node_key = (const void *)o->obs_agent_map; env->item_node_n = (size_t)n_items;
     }
     const signed char *item_node = (numa_mode && env->item_node_n == (size_t)n_items && env->item_node_key == (const void *)o->obs_agent_map)
@@ -315,10 +336,44 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     std::atomic<int64_t> first_slice_us{-1}, last_slice_us{-1}, wait_us{0}, busy_us{0};
     std::mutex overflow_m;
     std::vector<size_t> overflow;   // envs whose index planes hold more non-zero elements than the compact record carries
+    // One thread per slice waits for its event in the driver; the others watch a flag (hundreds of concurrent
+    // cudaEventSynchronize calls serialise on the driver's lock and cost more than the transfer they wait for).  The watchers
+    // spin, yielding their CPU on every round: measured on the two-socket B200 host, sleeping waiters (futex) let the sockets'
+    // uncore clock down and the DMA itself takes twice as long (profiles/r02z_e2e_transfer_knobs.txt).  AIE_E2E_SPIN_US=n
+    // makes them sleep after n microseconds - for hosts where the process runs under a tight CPU quota.
+    std::atomic<int> claimed[aie::AIE_MAX_SLICES], arrived[aie::AIE_MAX_SLICES];
+    for (int k = 0; k < aie::AIE_MAX_SLICES; k++) { claimed[k].store(0); arrived[k].store(0); }
+    int spin_us = -1;
+    if (const char *v = getenv("AIE_E2E_SPIN_US")) spin_us = atoi(v);
+    auto slice_arrived = [&](int k) {
+        int v = arrived[k].load(std::memory_order_acquire);
+        if (v == 0) {
+            int expected = 0;
+            if (claimed[k].compare_exchange_strong(expected, 1)) {
+                v = aie::be::wait_slice(env, k) == AIE_OK ? 1 : -1;
+                arrived[k].store(v, std::memory_order_release);
+                aie::flag_wake_all(&arrived[k]);
+            } else {
+                const clk::time_point s0 = clk::now();
+                while ((v = arrived[k].load(std::memory_order_acquire)) == 0) {
+                    if (spin_us >= 0 && std::chrono::duration<double, std::micro>(clk::now() - s0).count() >= spin_us) {
+                        aie::flag_wait_zero(&arrived[k]);
+                        v = arrived[k].load(std::memory_order_acquire);
+                        break;
+                    }
+#if defined(__x86_64__) || defined(__i386__)
+                    for (int i = 0; i < 32; i++) __builtin_ia32_pause();
+#endif
+                    std::this_thread::yield();   // never hold a CPU against the thread that waits in the driver
+                }
+            }
+        }
+        return v == 1;
+    };
     auto job = [&](int item) {
         const int k = item / items_per_slice;
         const clk::time_point w0 = clk::now();
-        if (aie::be::wait_slice(env, k) != AIE_OK) { failed.store(1); return; }
+        if (!slice_arrived(k)) { failed.store(1); return; }
         const clk::time_point w1 = clk::now();
         if (item % items_per_slice == 0 && (k == 0 || k == n_slices - 1))
             (k == 0 ? first_slice_us : last_slice_us).store((int64_t)(1e3 * ms_since(w1)));
@@ -336,7 +391,7 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     const double t_expanded = ms_since(clk::now());
     double *ht = env->host_timing;
     ht[0] = t_enqueued; ht[1] = 1e-3 * first_slice_us.load(); ht[2] = 1e-3 * (n_slices > 1 ? last_slice_us.load() : first_slice_us.load());
-    ht[3] = t_expanded; ht[4] = (double)n_slices; ht[5] = (double)want; ht[6] = (double)(E * (size_t)L.bytes);
+    ht[3] = t_expanded; ht[4] = (double)n_slices; ht[14] = (double)n_chunks; ht[15] = (double)aie::be::staging_node(env); ht[5] = (double)want; ht[6] = (double)(E * (size_t)L.bytes);
     ht[7] = std::chrono::duration<double, std::milli>(t0 - t_call).count();
     ht[8] = 1e-3 * wait_us.load(); ht[9] = 1e-3 * busy_us.load();   // summed over the threads
     ht[10] = aie::be::slice_device_ms(env, 0); ht[11] = aie::be::slice_device_ms(env, n_slices - 1);

@@ -19,6 +19,11 @@ constexpr int AIE_MAX_HOST_THREADS = 128;  // expansion threads
 int numa_node_of(const void *addr);          // node of the page holding addr (-1: unknown)           (aie_expand_host.cpp)
 int numa_node_count();
 bool pin_current_thread_to_node(int node);
+void flag_wait_zero(std::atomic<int> *flag);  // sleeps while *flag == 0 (futex)
+void flag_wake_all(std::atomic<int> *flag);
+int pci_numa_node(const char *bus_id);       // node a PCI device hangs off (-1: unknown)
+void *alloc_on_node(size_t bytes, int node);  // anonymous pages bound to one node (nullptr: not possible here)
+void free_on_node(void *p, size_t bytes);
 
 // Persistent workers: run(items, fn) calls fn(i) for every item on the pool plus the calling thread and returns when all
 // are done.  One job at a time (calls on a handle are serialised by contract).  numa_mode 0: one queue, unpinned threads.

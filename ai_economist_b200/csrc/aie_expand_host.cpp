@@ -7,8 +7,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
+#include <thread>
 #if defined(__linux__)
+#include <linux/futex.h>
 #include <sched.h>
+#include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 #endif
@@ -121,6 +126,68 @@ bool pin_current_thread_to_node(int node) {
 #else
     (void)node;
     return false;
+#endif
+}
+
+// Block while *flag == 0 / wake every thread blocked on it (futex(2): sleeping waiters cost no CPU time, which matters when
+// the process runs under a CPU quota; elsewhere: yield loop).
+void flag_wait_zero(std::atomic<int> *flag) {
+    static_assert(sizeof(std::atomic<int>) == sizeof(int), "futex word");
+    while (flag->load(std::memory_order_acquire) == 0) {
+#if defined(__linux__) && defined(SYS_futex)
+        syscall(SYS_futex, reinterpret_cast<int *>(flag), FUTEX_WAIT_PRIVATE, 0, nullptr, nullptr, 0);
+#else
+        std::this_thread::yield();
+#endif
+    }
+}
+void flag_wake_all(std::atomic<int> *flag) {
+#if defined(__linux__) && defined(SYS_futex)
+    syscall(SYS_futex, reinterpret_cast<int *>(flag), FUTEX_WAKE_PRIVATE, 0x7fffffff, nullptr, nullptr, 0);
+#else
+    (void)flag;
+#endif
+}
+
+// NUMA node a PCI device hangs off ("0000:3b:00.0" as cudaDeviceGetPCIBusId prints it), -1 when the kernel does not say.
+int pci_numa_node(const char *bus_id) {
+#if defined(__linux__)
+    char path[160], low[64];
+    size_t n = 0;
+    for (; bus_id[n] && n + 1 < sizeof(low); n++) low[n] = (char)((bus_id[n] >= 'A' && bus_id[n] <= 'F') ? bus_id[n] + 32 : bus_id[n]);
+    low[n] = 0;
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", low);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+#else
+    (void)bus_id;
+    return -1;
+#endif
+}
+// Page-aligned anonymous memory bound to one NUMA node (mbind(2) before first touch); nullptr when that is not possible.
+void *alloc_on_node(size_t bytes, int node) {
+#if defined(__linux__) && defined(SYS_mbind)
+    if (node < 0 || node >= 64 || bytes == 0) return nullptr;
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    unsigned long mask = 1UL << node;
+    if (syscall(SYS_mbind, p, (unsigned long)bytes, 2 /* MPOL_BIND */, &mask, 65UL, 0U) != 0) { munmap(p, bytes); return nullptr; }
+    memset(p, 0, bytes);   // first touch
+    return p;
+#else
+    (void)bytes; (void)node;
+    return nullptr;
+#endif
+}
+void free_on_node(void *p, size_t bytes) {
+#if defined(__linux__)
+    if (p) munmap(p, bytes);
+#else
+    (void)p; (void)bytes;
 #endif
 }
 

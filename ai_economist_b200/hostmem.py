@@ -2,10 +2,10 @@
 
 The e2e step ends in a pure write stream into the caller's host tensors (c2: 296 MB per step).  On a two-socket host
 a tensor allocated the usual way lives on the socket of the thread that first touched it, and the stream is then limited
-by ONE socket's memory controllers.  `pinned_empty(..., interleave=True)` sets the calling thread's memory policy to
-MPOL_INTERLEAVE over all nodes (Linux set_mempolicy(2), no libnuma needed) for the duration of the allocation, so the
-pages of the pinned buffer alternate between the sockets; the policy is restored afterwards.  Falls back to a plain pinned
-allocation where the syscall is unavailable.
+by ONE socket's memory controllers.  `pinned_empty(..., numa="blocks")` binds blocks of env replicas (one transfer slice
+each) to alternating nodes with mbind(2) (no libnuma needed) and pins the buffer in place; `numa="split"` makes one block
+per node; `interleave=True` sets MPOL_INTERLEAVE for the duration of the allocation so that 4 KB pages alternate.  Falls
+back to a plain pinned allocation where the syscalls are unavailable.
 """
 import ctypes
 import os
@@ -48,11 +48,22 @@ _MPOL_BIND = 2
 _keep = []                    # mmap objects backing node-split tensors (registered with CUDA; never unmapped)
 
 
-def pinned_empty(shape, dtype, interleave=False, numa=None):
-    """A pinned host tensor.  numa="split": the leading axis is cut into one contiguous block per NUMA node (block k bound
-    to node k with mbind(2) before first touch, then pinned in place with cudaHostRegister) - the placement the expansion
-    threads of aie_step_host_compact are matched to: each is pinned to a node and writes the rows that live there.
-    interleave=True (or numa="interleave"): 4 KB pages alternate between the nodes.  Default: plain pinned allocation."""
+def transfer_block_rows(n_envs, max_slices=16, item_envs=16):
+    """Envs per transfer slice of aie_step_host_compact (csrc/aie_abi.inl: work items of 16 envs, at most 16 slices): the
+    block size to pass to pinned_empty(numa="blocks") so that consecutive slices land on alternating NUMA nodes."""
+    n_items = (int(n_envs) + item_envs - 1) // item_envs
+    n_slices = min(n_items, max_slices)
+    return max(1, (n_items + n_slices - 1) // n_slices) * item_envs
+
+
+def pinned_empty(shape, dtype, interleave=False, numa=None, block_rows=None):
+    """A pinned host tensor.
+    numa="blocks": blocks of `block_rows` rows of the leading axis (env replicas) alternate between the NUMA nodes (bound
+    with mbind(2) before first touch, then pinned in place with cudaHostRegister).  With block_rows =
+    transfer_block_rows(n_envs) consecutive transfer slices of aie_step_host_compact belong to alternating nodes, so the
+    node-pinned expansion threads of every socket have work from the first slice on (the placement the bench uses).
+    numa="split": one contiguous block of rows per node.  interleave=True (or numa="interleave"): 4 KB pages alternate
+    between the nodes.  Default: plain pinned allocation."""
     import mmap
 
     import numpy as np
@@ -61,7 +72,7 @@ def pinned_empty(shape, dtype, interleave=False, numa=None):
     if numa == "interleave":
         interleave = True
     nodes = numa_nodes()
-    if numa == "split" and len(nodes) > 1 and os.uname().machine == "x86_64":
+    if numa in ("split", "blocks") and len(nodes) > 1 and os.uname().machine == "x86_64":
         t0 = torch.empty(0, dtype=dtype)
         n_el = int(np.prod(shape))
         nbytes = max(n_el * t0.element_size(), 1)
@@ -71,12 +82,20 @@ def pinned_empty(shape, dtype, interleave=False, numa=None):
         buf = (ctypes.c_char * size).from_buffer(mm)
         base = ctypes.addressof(buf)
         libc = ctypes.CDLL(None, use_errno=True)
-        per = (size // len(nodes)) // page * page
+        if numa == "split":
+            per = (size // len(nodes)) // page * page
+            cuts = [i * per for i in range(len(nodes))] + [size]
+        else:
+            rows = int(shape[0]) if len(shape) else 1
+            row_bytes = nbytes // max(rows, 1)
+            br = int(block_rows or transfer_block_rows(rows))
+            cuts = sorted({min(size, (b * br * row_bytes + page // 2) // page * page) for b in range((rows + br - 1) // br)} | {0, size})
         ok = True
-        for i, node in enumerate(nodes):
-            lo = i * per
-            hi = size if i == len(nodes) - 1 else (i + 1) * per
-            mask = ctypes.c_ulong(1 << node)
+        for i in range(len(cuts) - 1):
+            lo, hi = cuts[i], cuts[i + 1]
+            if hi <= lo:
+                continue
+            mask = ctypes.c_ulong(1 << nodes[i % len(nodes)])
             ok &= libc.syscall(_SYS_MBIND, ctypes.c_void_p(base + lo), ctypes.c_ulong(hi - lo), ctypes.c_int(_MPOL_BIND),
                                ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2), ctypes.c_uint(0)) == 0
         t = torch.frombuffer(buf, dtype=dtype, count=n_el).reshape(shape)

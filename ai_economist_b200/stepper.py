@@ -173,7 +173,7 @@ class BatchStepper:
         out = (C.c_double * 16)()
         self.lib.aie_get_host_timing(self._h, out, 16)
         k = ["enqueued", "first_slice", "last_slice", "expanded", "slices", "threads", "d2h_bytes", "before_transfer",
-             "wait_sum", "busy_sum", "first_slice_dev", "last_slice_dev", "expand_only", "overflow_envs"]
+             "wait_sum", "busy_sum", "first_slice_dev", "last_slice_dev", "expand_only", "overflow_envs", "chunks", "staging_node"]
         return dict(zip(k, list(out)))
 
     def compact_bytes_per_env(self):

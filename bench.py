@@ -81,6 +81,23 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_quota_cores():
+    """CPU time the container may use per second of wall clock, in cores (cgroup v2 cpu.max / v1 cfs quota); None: unlimited.
+    The CPU arm and the expansion threads of the e2e leg both run under it: a 128-thread host with a 16-core quota delivers
+    16 cores' worth of sustained CPU time whatever the thread count."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -242,7 +259,7 @@ class OracleRunner:
             dt = time.perf_counter() - t0
             if t >= warmup:
                 total += dt
-        return self.n_envs * self.A * steps / total, total
+        return (self.n_envs * self.A * steps / total if total > 0 else 0.0), total
 
 
 def cpu_baseline_for(key, min_seconds=6.0):
@@ -259,7 +276,7 @@ def cpu_baseline_for(key, min_seconds=6.0):
     probe, _ = runner.run(5, warmup=2)
     steps_cpu = int(max(10, min(5000, min_seconds * probe / (n_cpu * runner.A))))
     rate, total = runner.run(steps_cpu, warmup=0)
-    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "cpu_quota_cores": cpu_quota_cores(),
             "sample": "%d env replicas x %d steps of the same workload on %d pinned host threads "
                       "(C oracle of the reference step), %.1f s" % (n_cpu, steps_cpu, threads, total)}
 
@@ -298,7 +315,7 @@ def run_reference_arm(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / steps_run, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32+f64" if key != "c4" else "f32+f64", "data": "synthetic",
         "config": workload_config(key, w["envs_per_gpu"]),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "cpu_quota_cores": cpu_quota_cores(),
                          "sample": "%d env replicas x %d steps per step-sample (C oracle, %d pinned pthreads), %.1f s"
                                    % (n_envs, steps_run, threads, total)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -465,9 +482,11 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     for nm in ["obs_agent_map", "obs_agent_idx", "obs_agent_flat", "mask_agent", "obs_planner_map", "obs_planner_idx",
                "obs_planner_flat", "obs_planner_agents", "mask_planner", "obs_time", "reward", "done"]:
         if nm in st.buf:
-            # pinned host tensors from the package's allocator: one contiguous block of replicas per NUMA node, which is
-            # what the node-pinned expansion threads of aie_step_host_compact are matched to (ai_economist_b200/hostmem.py)
-            t = hostmem.pinned_empty(st.buf[nm].shape, st.buf[nm].dtype, numa="split" if e2e_mode == "compact" else None)
+            # pinned host tensors from the package's allocator: blocks of replicas (one transfer slice each) on alternating
+            # NUMA nodes, which is what the node-pinned expansion threads of aie_step_host_compact are matched to: every
+            # socket has work from the first slice on (ai_economist_b200/hostmem.py)
+            t = hostmem.pinned_empty(st.buf[nm].shape, st.buf[nm].dtype,
+                                     numa=os.environ.get("AIE_BENCH_E2E_ALLOC", "blocks") if e2e_mode == "compact" else None)
             out_host[nm] = t
             out_ptrs[nm] = C.c_void_p(t.data_ptr())
             d2h += t.numel() * t.element_size()
@@ -502,6 +521,7 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
                         "to pinned host memory each step (PCIe-bound)")
     else:
         e2e.update(d2h_bytes_per_step=E * st.compact_bytes_per_env(), host_tensor_bytes_per_step=d2h, host_threads=e2e_threads,
+                   cpu_quota_cores=cpu_quota_cores(),
                    last_call_timing_ms={k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.host_timing().items()},
                    what="aie_step_host_compact: pinned host actions in; every observation/mask/reward/done tensor lands "
                         "in pinned host memory each step, bit-/byte-packed over PCIe and expanded by host threads "

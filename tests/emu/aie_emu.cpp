@@ -34,10 +34,14 @@ int sync(aie_env *, void *stream);
 int sync_all(aie_env *);
 int launch_finish_reset(aie_env *, int lo, int n, void *stream);
 int launch_step(aie_env *, int emit_obs, void *stream);
+int launch_step_range(aie_env *, int emit_obs, int lo, int hi, void *stream);
 int launch_observe(aie_env *, int lo, int n, void *stream);
 int launch_sample(aie_env *, uint64_t seed, void *stream);
 int compact_buffers(aie_env *, size_t bytes, uint8_t **dev, uint8_t **host);
-int launch_pack(aie_env *, const CompactLayout &L, uint8_t *dev, void *stream);
+int staging_node(aie_env *);
+int launch_pack_range(aie_env *, const CompactLayout &L, uint8_t *dev, int lo, int hi, void *stream);
+int chunk_ready(aie_env *, void *stream);
+int copies_done(aie_env *, void *stream);
 int download_slice(aie_env *, int k, void *host, const void *dev, size_t n, void *stream);
 int wait_slice(aie_env *, int k);
 double slice_device_ms(aie_env *, int k);
@@ -74,8 +78,11 @@ int download_slice(aie_env *, int, void *host, const void *dev, size_t n, void *
 int wait_slice(aie_env *, int) { return AIE_OK; }
 double slice_device_ms(aie_env *, int) { return -1.0; }
 int mark_call_start(aie_env *, void *) { return AIE_OK; }
-int launch_pack(aie_env *env, const CompactLayout &L, uint8_t *dev, void *) {
-    for (int e = 0; e < env->n_envs; e++) pack_env(env->cfg, env->bufs, L, (size_t)e, dev + (size_t)e * L.bytes, 0);
+int staging_node(aie_env *) { return -1; }
+int chunk_ready(aie_env *, void *) { return AIE_OK; }
+int copies_done(aie_env *, void *) { return AIE_OK; }
+int launch_pack_range(aie_env *env, const CompactLayout &L, uint8_t *dev, int lo, int hi, void *) {
+    for (int e = lo; e < hi; e++) pack_env(env->cfg, env->bufs, L, (size_t)e, dev + (size_t)e * L.bytes, 0);
     return AIE_OK;
 }
 int upload(aie_env *, void *dst, const void *src, size_t n, void *) { if (dst != src) memcpy(dst, src, n); return AIE_OK; }
@@ -96,10 +103,11 @@ int launch_finish_reset(aie_env *env, int lo, int n, void *) {
     return AIE_OK;
 }
 int launch_observe(aie_env *env, int lo, int n, void *);
-int launch_step(aie_env *env, int emit_obs, void *) {
+int launch_step(aie_env *env, int emit_obs, void *) { return launch_step_range(env, emit_obs, 0, env->n_envs, nullptr); }
+int launch_step_range(aie_env *env, int emit_obs, int lo, int hi, void *) {
     const DevCfg &c = env->cfg;
     const DevBufs &b = env->bufs;
-    for (int e = 0; e < env->n_envs; e++) {
+    for (int e = lo; e < hi; e++) {
         uint8_t *rec = b.state + (size_t)e * c.rec_bytes;
         int32_t *events = (b.events && e < b.event_envs) ? b.events + (size_t)e * 8 * (b.event_cap + 1) : nullptr;
         const int32_t *aa = b.act_a + (size_t)e * c.A * c.n_act_a;
@@ -128,7 +136,7 @@ int launch_step(aie_env *env, int emit_obs, void *) {
         }
     }
     env->launches++;
-    if (emit_obs) { launch_observe(env, 0, env->n_envs, nullptr); env->launches--; }
+    if (emit_obs) { launch_observe(env, lo, hi - lo, nullptr); env->launches--; }
     return AIE_OK;
 }
 int launch_observe(aie_env *env, int lo, int n, void *) {

@@ -81,3 +81,20 @@ def test_emulated_compact_transfer_index_plane_overflow_is_fetched_directly(monk
 def test_cuda_compact_transfer_index_plane_overflow_is_fetched_directly(monkeypatch):
     monkeypatch.setenv("AIE_COMPACT_TINY_CAPS", "1")
     _check("c1_tutorial", 64, device="cuda:0", threads=(4,))
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_emulated_compact_transfer_chunked_stepping(monkeypatch, chunks):
+    """The batch may step in several launches over env ranges (AIE_E2E_CHUNKS) so that early slices go down while the rest
+    still steps: same bytes whatever the chunk count (70 envs = 5 work items of 16 envs = 5 slices)."""
+    from tests.emu.emu_stepper import emu_factory
+    monkeypatch.setenv("AIE_E2E_CHUNKS", str(chunks))
+    _check("c1_tutorial", 70, factory=emu_factory, threads=(2,))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [1, 2, 5, 16])
+def test_cuda_compact_transfer_chunked_stepping(monkeypatch, chunks):
+    """1 000 envs = 63 work items = 16 slices; ragged last chunk with 5 chunks; one chunk per slice with 16."""
+    monkeypatch.setenv("AIE_E2E_CHUNKS", str(chunks))
+    _check("c3_paper_tax", 1000, device="cuda:0", threads=(0,))
