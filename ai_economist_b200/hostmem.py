@@ -101,10 +101,10 @@ def pinned_empty(shape, dtype, interleave=False, numa=None, block_rows=None):
         t = torch.frombuffer(buf, dtype=dtype, count=n_el).reshape(shape)
         t.zero_()                                             # first touch: pages land on their nodes
         rc = torch.cuda.cudart().cudaHostRegister(base, size, 0)
-        if int(rc) == 0 and ok:
+        if int(rc) == 0:     # pinned in place (ok False: some block could not be bound - still valid, just not placed)
             _keep.append((mm, buf))
             return t
-        # fall through to a plain pinned allocation when binding / registering is not possible here
+        del t                # registering failed: fall through to a plain pinned allocation
     if not interleave:
         return torch.empty(shape, dtype=dtype, pin_memory=True)
     with interleaved():
