@@ -98,6 +98,20 @@ def cpu_quota_cores():
         return None
 
 
+def cpu_throttle_counters():
+    """(nr_throttled, throttled seconds) of this container's cgroup so far; None where the kernel does not say."""
+    for path in ("/sys/fs/cgroup/cpu.stat", "/sys/fs/cgroup/cpu/cpu.stat"):
+        try:
+            kv = dict(line.split()[:2] for line in open(path).read().splitlines() if line.strip())
+            if "throttled_usec" in kv:
+                return int(kv.get("nr_throttled", 0)), float(kv["throttled_usec"]) * 1e-6
+            if "throttled_time" in kv:
+                return int(kv.get("nr_throttled", 0)), float(kv["throttled_time"]) * 1e-9
+        except Exception:
+            pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -499,6 +513,7 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
     out_host["mask_agent"].copy_(st.buf["mask_agent"])
     out_host["mask_planner"].copy_(st.buf["mask_planner"])
     e2e_s, n_e2e, e2e_each = 0.0, max(3, e2e_steps), []
+    thr0 = cpu_throttle_counters()
     for i in range(n_e2e + 2):
         act_a.copy_(torch.from_numpy(wl.sample_from_masks(out_host["mask_agent"].numpy(), seg_a, rng)))
         if seg_p:
@@ -511,6 +526,7 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
         if i >= 2:
             e2e_s += dt
             e2e_each.append(dt)
+    thr1 = cpu_throttle_counters()
     e2e_value = world * E * A * n_e2e / ctx.max_over_ranks(e2e_s)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "steps": n_e2e, "mode": e2e_mode,
            "ms_per_step": {"mean": 1e3 * e2e_s / n_e2e, "median": 1e3 * float(np.median(e2e_each)), "min": 1e3 * min(e2e_each),
@@ -521,7 +537,11 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
                         "to pinned host memory each step (PCIe-bound)")
     else:
         e2e.update(d2h_bytes_per_step=E * st.compact_bytes_per_env(), host_tensor_bytes_per_step=d2h, host_threads=e2e_threads,
-                   cpu_quota_cores=cpu_quota_cores(),
+                   cpu_quota_cores=cpu_quota_cores(), ms_each=[round(1e3 * x, 3) for x in e2e_each],
+                   cpu_quota_throttling=(None if thr0 is None or thr1 is None else
+                                         {"periods_throttled": thr1[0] - thr0[0], "seconds_throttled": round(thr1[1] - thr0[1], 4),
+                                          "what": "cgroup cpu.stat deltas over this leg: the container's CPU quota stopping "
+                                                  "the process (all threads) until the next 100 ms period"}),
                    last_call_timing_ms={k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.host_timing().items()},
                    what="aie_step_host_compact: pinned host actions in; every observation/mask/reward/done tensor lands "
                         "in pinned host memory each step, bit-/byte-packed over PCIe and expanded by host threads "
@@ -748,6 +768,8 @@ def main():
 
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     torch.cuda.set_device(local_rank)
+    torch.set_num_threads(1)   # no OpenMP team for the small host-side tensor ops of the e2e loop (its idle threads would spin
+    #                            on the container's CPU quota); the expansion threads are the library's own
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -758,10 +780,10 @@ def main():
     if clocks:
         clocks.start()
     fn = measure_covid if key == "c4" else measure_gtb
-    if args.e2e_threads == 0:   # expansion threads of the e2e leg: this rank's share of the host's hardware threads
-        # (three quarters of them: the main thread, the clock sampler and the CUDA driver's threads need cores too, and a
-        # straggler among the expansion workers delays the whole step)
-        args.e2e_threads = max(8, (3 * host_cores()) // (4 * max(1, world)))
+    if args.e2e_threads == 0:   # expansion threads of the e2e leg: this rank's share of half the host's hardware threads
+        # (one per physical core: the expansion is bound by the memory controllers, 48 - 64 threads are as fast as 96 on the
+        # 2 x 32-core B200 host and burn half the CPU time, profiles/r02z_e2e_transfer_knobs.txt section 7)
+        args.e2e_threads = max(8, host_cores() // (2 * max(1, world)))
     kw = {} if key == "c4" else dict(e2e_mode=args.e2e_mode, e2e_threads=args.e2e_threads)
     res = fn(ctx, key, args.steps, args.warmup, with_cpu, clocks=clocks, e2e_steps=args.e2e_steps, **kw)
     clk = clocks.stop() if clocks else None
