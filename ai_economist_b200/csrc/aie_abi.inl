@@ -283,7 +283,9 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     int n_slices = n_items < aie::AIE_MAX_SLICES ? n_items : aie::AIE_MAX_SLICES;
     const int items_per_slice = (n_items + n_slices - 1) / n_slices;
     n_slices = (n_items + items_per_slice - 1) / items_per_slice;
-    int n_chunks = 4;
+    // small records (one warp per env): 4 launches; large records (one CTA per env, a few hundred resident per wave): 2, more
+    // would lose to wave quantisation what the earlier first slice gains (profiles/r02z_e2e_transfer_knobs.txt section 8)
+    int n_chunks = c.mw > 1 ? 2 : 4;
     if (const char *v = getenv("AIE_E2E_CHUNKS")) n_chunks = atoi(v);
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > n_slices) n_chunks = n_slices;

@@ -362,7 +362,7 @@ int32_t aie_compact_bytes_per_env(const aie_env *env);
  * upload + launches enqueued), [8] time the threads spent waiting for their slice and [9] expanding (summed over threads),
  * [10] / [11] device-clock arrival of the first / last slice since the call's first enqueue, [12] the expansion alone
  * (only with AIE_E2E_REPEAT_EXPAND=n in the environment), [13] envs whose index planes were fetched directly, [14] number of
- * step chunks (the batch steps in up to AIE_E2E_CHUNKS launches, default 4, so that the first slices go down while the rest
+ * step chunks (the batch steps in up to AIE_E2E_CHUNKS launches, default 4, or 2 for large records, so that the first slices go down while the rest
  * of the batch still steps), [15] NUMA node of the library's pinned staging buffer (-1: plain cudaHostAlloc).  Returns the number of words defined (diagnostics for tuning). */
 #define AIE_HOST_TIMING_WORDS 16
 int aie_get_host_timing(const aie_env *env, double *out, int32_t cap);

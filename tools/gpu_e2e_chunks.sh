@@ -9,7 +9,7 @@ w=$1; shift
 i=0
 for combo in "$@"; do
   i=$((i+1))
-  env $(echo "$combo" | tr ',' ' ') timeout 300 python bench.py --workload $w ${BENCH_ARGS:-} --no-cpu-baseline --no-extra-workloads --e2e-steps 20 --steps 50 --warmup 10 \
+  env $(echo "$combo" | tr ',' ' ') timeout 300 python bench.py --workload $w --no-cpu-baseline --no-extra-workloads --e2e-steps 20 --steps 50 --warmup 10 ${BENCH_ARGS:-} \
       > gpurun_out/e2e_${w}_$i.json 2> gpurun_out/e2e_${w}_$i.err
   python - $w $i "$combo" <<'PY'
 import json, sys
