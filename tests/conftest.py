@@ -15,7 +15,7 @@ def pytest_configure(config):
 
 # GPU cases that have not run on a B200 yet go here (substring of the node id): they are ordered last, so that with `-x`
 # a surprise there cannot mask the cases that are known to pass on the hardware.  Empty: every `-m gpu` case has run on a
-# B200 (profiles/r02z_pytest_gpu.log: 137 passed).
+# B200 (profiles/r02z_pytest_gpu.log: 141 passed).
 NOT_YET_RUN_ON_B200 = ()
 
 
