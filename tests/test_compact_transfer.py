@@ -98,3 +98,19 @@ def test_cuda_compact_transfer_chunked_stepping(monkeypatch, chunks):
     """1 000 envs = 63 work items = 16 slices; ragged last chunk with 5 chunks; one chunk per slice with 16."""
     monkeypatch.setenv("AIE_E2E_CHUNKS", str(chunks))
     _check("c3_paper_tax", 1000, device="cuda:0", threads=(0,))
+
+
+@pytest.mark.parametrize("n_envs", [5, 70, 300])
+def test_hostmem_block_rows_match_the_transfer_slices(n_envs):
+    """hostmem.transfer_block_rows restates the library's slicing (work items of 16 envs, at most 16 slices): the NUMA
+    blocks of pinned_empty(numa="blocks") must be exactly the transfer slices."""
+    from ai_economist_b200 import hostmem
+    from tests.emu.emu_stepper import emu_factory
+    env = _env("c1_tutorial", n_envs, emu_factory, None)
+    st = env.stepper
+    out, ptrs = _host_outputs(st)
+    aa = np.zeros(tuple(st.buf["actions_agent"].shape), np.int32)
+    st.step_host(aa.ctypes.data_as(C.c_void_p), None, ptrs, compact=True, n_threads=2)
+    rows = hostmem.transfer_block_rows(n_envs)
+    assert rows % 16 == 0
+    assert int(st.host_timing()["slices"]) == -(-n_envs // rows)
