@@ -660,24 +660,29 @@ AIE_DEV void gather_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r) 
 // ------------------------------------------------------------------------------------------------
 // PeriodicBracketTax  (components/redistribution.py)
 // ------------------------------------------------------------------------------------------------
+// curr_rate_max (:390-394): rate_max, or under a tax_annealing_schedule (fixed schedules and the Saez model; behind EXT) the
+// annealed maximum of this episode (components/utils.py:10-57, refreshed whenever the completion count changes).
+// Quirk kept: the limit is refreshed in generate_masks, which runs AFTER the observations of a reset are built
+// (base_env.py:614-704), so the reset observation (t == 0) still shows the previous episode's limit.
 template <bool EXT = false>
-AIE_DEV double tax_rate(const DevCfg &c, const Env &e, int b) {  // curr_marginal_rates :381-405
-    if (c.tax_model == 2) return fmin(e.saez[b], c.rate_max);  // Saez: np.minimum(curr_bracket_tax_rates, curr_rate_max)
-    if (EXT && c.tax_model == 1 && c.tax_annealing) {
-        // a fixed schedule under a tax_annealing_schedule: np.minimum(schedule, curr_rate_max) with the annealed maximum of
-        // this episode (:390-394, :400-413; components/utils.py:10-57, refreshed whenever the completion count changes)
-        // Quirk kept: the limit is refreshed in generate_masks, which runs AFTER the observations of a reset are built
-        // (base_env.py:614-704), so the reset observation (t == 0) still shows the previous episode's limit.
+AIE_DEV double tax_rate_cap(const DevCfg &c, const Env &e) {
+    if (EXT && c.tax_annealing && c.tax_model != 0) {
         int done_eps = e.hdr[HDR_COMPLETIONS];
         if (e.hdr[HDR_T] == 0 && done_eps > 0) done_eps -= 1;
         const double vis = fmax(0.0, fmin(1.0, c.ann_slope * ((double)done_eps - c.ann_warm)));
-        return fmin(c.fixed_rates[b], vis * c.rate_max);
+        return vis * c.rate_max;
     }
+    return c.rate_max;
+}
+template <bool EXT = false>
+AIE_DEV double tax_rate(const DevCfg &c, const Env &e, int b) {  // curr_marginal_rates :381-405
+    if (c.tax_model == 2) return fmin(e.saez[b], tax_rate_cap<EXT>(c, e));  // Saez: np.minimum(curr_bracket_tax_rates, curr_rate_max)
+    if (EXT && c.tax_model == 1 && c.tax_annealing) return fmin(c.fixed_rates[b], tax_rate_cap<EXT>(c, e));  // np.minimum(schedule, curr_rate_max)
     return c.tax_model == 0 ? c.disc_rates[e.rate_idx[b]] : c.fixed_rates[b];
 }
 template <bool EXT = false>
 AIE_DEV double tax_rate_observed(const DevCfg &c, const Env &e, int b) {  // _curr_rates_obs (:960, :1123)
-    return c.tax_model == 2 ? fmin(e.saez[32 + b], c.rate_max) : tax_rate<EXT>(c, e, b);
+    return c.tax_model == 2 ? fmin(e.saez[32 + b], tax_rate_cap<EXT>(c, e)) : tax_rate<EXT>(c, e, b);
 }
 AIE_DEV int tax_income_bin(const DevCfg &c, double income) {  // :828-835 (bracket index; negative income -> 0)
     int arg = 0;
@@ -709,11 +714,12 @@ AIE_DEV void tax_step(const DevCfg &c, Env &e, const StepScratch &s, Rng &r, int
     int pos = e.hdr[HDR_TAX_POS];
     if (pos == 1 && c.tax_model == 2 && e.hdr[HDR_SAEZ_N] < 500) {
         // Saez warm-up (:444-457): until 500 (income, rate) samples exist the period's rates are
-        // np.random.uniform(rate_min, rate_max, n_brackets) from the env's stream; afterwards the host estimator has
+        // np.random.uniform(rate_min, curr_rate_max, n_brackets) from the env's stream; afterwards the host estimator has
         // already written this period's rates into the record.
+        const double cap = tax_rate_cap<EXT>(c, e);
         for (int b = 0; b < c.B; b++) {
             const double u = rng_double(r);
-            if (lane == 0) e.saez[b] = c.rate_min + (c.rate_max - c.rate_min) * u;
+            if (lane == 0) e.saez[b] = c.rate_min + (cap - c.rate_min) * u;
         }
         wsync();
     }

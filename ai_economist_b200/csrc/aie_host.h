@@ -127,7 +127,6 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
     if (c.has[COMP_TAX]) {
         if (c.tax_model != AIE_TAX_MODEL_WRAPPER && c.tax_model != AIE_TAX_FIXED_RATES && c.tax_model != AIE_TAX_SAEZ)
             return bad("unsupported tax_model");
-        if (c.tax_model == AIE_TAX_SAEZ && u.tax_annealing) return bad("tax annealing with the Saez model is not supported");
         if (c.B < 2 || c.B > AIE_MAX_BRACKETS) return bad("n_brackets must be in [2, 16]");
         if (c.tax_model == AIE_TAX_MODEL_WRAPPER && (c.R < 1 || c.R > AIE_MAX_RATES)) return bad("n_disc_rates must be in [1, 64]");
         if (c.period < 1) return bad("tax period must be >= 1");
@@ -194,7 +193,7 @@ inline int build_devcfg(const aie_config &u, int n_envs, DevCfg &c, Tables &tb, 
             return bad("dyn_coverage must be in (0, 1) and dyn_clump in (0, 1]");
     }
     c.ext = (c.planner_single || c.regen_hw[0] || c.regen_hw[1] || c.full_obs || c.split_layout || c.one_step ||
-             (c.has[COMP_TAX] && c.tax_model == AIE_TAX_FIXED_RATES && u.tax_annealing) ||
+             (c.has[COMP_TAX] && (c.tax_model == AIE_TAX_FIXED_RATES || c.tax_model == AIE_TAX_SAEZ) && u.tax_annealing) ||
              (c.reset_mode == 1 && (c.build_skill_dist == 2 || c.gather_skill_dist == 2))) ? 1 : 0;
     c.n_act_p = c.planner_acts ? (c.planner_single ? 1 : c.B) : 0;
     c.Na = c.multi_action ? n_single + c.n_sub : 1 + n_single;

@@ -207,8 +207,6 @@ class PeriodicBracketTax(BaseComponent):
         if tax_annealing_schedule is not None:
             assert isinstance(tax_annealing_schedule, (tuple, list))
             self._annealing_warmup, self._annealing_slope = tax_annealing_schedule[0], tax_annealing_schedule[1]
-            if tax_model == "saez":
-                raise NotImplementedError("tax annealing together with the Saez model is not on the device path")
         else:
             self._annealing_warmup = self._annealing_slope = None
 

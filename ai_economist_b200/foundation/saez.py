@@ -119,8 +119,9 @@ class SaezEstimator:
         out.append(bin_rates[-1])
         return np.array(out)
 
-    def new_period_rates(self):
-        """compute_and_set_new_period_rates_from_saez_formula (:437-511) for a full buffer -> bracket rates [B]."""
+    def new_period_rates(self, rate_max=None):
+        """compute_and_set_new_period_rates_from_saez_formula (:437-511) for a full buffer -> bracket rates [B].
+        rate_max: curr_rate_max (:390-394) - the annealed maximum of the running episode under a tax_annealing_schedule."""
         data = np.array(self.buffer)
         self.elas_tm1, self.log_z0_tm1 = float(self.elas_t), float(self.log_z0_t)
         elas_t, log_z0_t = self._elasticity(data)
@@ -128,7 +129,8 @@ class SaezEstimator:
         if self.fixed_elas is not None:
             elas_t = self.fixed_elas
         gz, az = self._binned(data[:, 0])
-        rates = np.clip(self._bracketize(self._bin_rates(gz, az, elas_t)), self.rate_min, self.rate_max)
+        rates = np.clip(self._bracketize(self._bin_rates(gz, az, elas_t)), self.rate_min,
+                        self.rate_max if rate_max is None else float(rate_max))
         self.running_avg = self.running_avg * 0.99 + rates * 0.01
         return rates
 
@@ -256,11 +258,14 @@ class SaezBatch:
 
     CHUNK = 256   # replicas per pass: keeps the [chunk, 500] temporaries inside the CPU caches
 
-    def new_period_rates(self, rows):
-        """Rates [R, B] of the replicas in `rows` (all with a full buffer); updates their smoothed state."""
+    def new_period_rates(self, rows, rate_max=None):
+        """Rates [R, B] of the replicas in `rows` (all with a full buffer); updates their smoothed state.  rate_max [R]:
+        every replica's curr_rate_max (tax annealing), default the component's rate_max."""
         rows = np.asarray(rows, np.int64)
+        cap = np.full(len(rows), self.rate_max) if rate_max is None else np.asarray(rate_max, np.float64)
         if len(rows) > self.CHUNK:
-            return np.concatenate([self.new_period_rates(rows[i:i + self.CHUNK]) for i in range(0, len(rows), self.CHUNK)])
+            return np.concatenate([self.new_period_rates(rows[i:i + self.CHUNK], cap[i:i + self.CHUNK])
+                                   for i in range(0, len(rows), self.CHUNK)])
         data = self._data(rows)
         self.elas_tm1[rows], self.log_z0_tm1[rows] = self.elas_t[rows], self.log_z0_t[rows]
         elas_t, log_z0_t = self._elasticity(rows, data)
@@ -268,7 +273,7 @@ class SaezBatch:
         if self.fixed_elas is not None:
             elas_t = np.full(len(rows), self.fixed_elas)
         gz, az = self._binned(data[:, :, 0])
-        rates = np.clip(self._bracketize(self._bin_rates(gz, az, elas_t)), self.rate_min, self.rate_max)
+        rates = np.clip(self._bracketize(self._bin_rates(gz, az, elas_t)), self.rate_min, cap[:, None])
         self.running_avg[rows] = self.running_avg[rows] * 0.99 + rates * 0.01
         return rates
 
@@ -292,8 +297,9 @@ class SaezLoop:
         for r, inc, marg in zip(rows, incomes, marginal_rates):
             self.est[int(r)].add_samples(inc, marg)
 
-    def new_period_rates(self, rows):
-        return np.stack([self.est[int(r)].new_period_rates() for r in rows])
+    def new_period_rates(self, rows, rate_max=None):
+        caps = [None] * len(rows) if rate_max is None else list(rate_max)
+        return np.stack([self.est[int(r)].new_period_rates(c) for r, c in zip(rows, caps)])
 
 
 class _ReplicaView:
@@ -323,6 +329,10 @@ class SaezHost:
         self.batch = (SaezBatch if batched else SaezLoop)(env.n_envs, t.bracket_cutoffs, t.rate_min, t.rate_max,
                                                           t.pareto_weight_type, t.saez_fixed_elas)
         self.est = [_ReplicaView(self.batch, e) for e in range(env.n_envs)]
+        # tax annealing (redistribution.py:311-330, :390-394): the maximum rate of the running episode follows the number
+        # of completed episodes (components/utils.py:10-57); the formula's rates are clipped to it
+        self.annealing = None if t.tax_annealing_schedule is None else (float(t._annealing_warmup), float(t._annealing_slope),
+                                                                         float(t.rate_max))
         self._seen = np.zeros(env.n_envs, np.int64)   # samples already copied from the device, per replica
         self.elas_at_episode_end = [None] * env.n_envs  # saez/estimated_elasticity of previous_episode_metrics
 
@@ -383,7 +393,12 @@ class SaezHost:
             return
         B = self.batch.B
         rates, avg = np.zeros((len(starting), 16)), np.zeros((len(starting), 16))
-        rates[:, :B] = self.batch.new_period_rates(starting)
+        cap = None
+        if self.annealing is not None:
+            warm, slope, full = self.annealing
+            done = self._np("completions")[starting].astype(np.float64)
+            cap = np.maximum(0.0, np.minimum(1.0, slope * (done - warm))) * full
+        rates[:, :B] = self.batch.new_period_rates(starting, cap)
         avg[:, :B] = np.asarray(self.batch.running_avg)[starting]
         self._write_rows("saez_rates", starting, rates)
         self._write_rows("saez_avg_rates", starting, avg)

@@ -79,6 +79,19 @@ CONFIGS = {
         fixed_four_skill_and_loc=False, n_agents=10, world_size=[25, 25], episode_length=100,
         multi_action_mode_agents=False, multi_action_mode_planner=True,
         flatten_observations=True, flatten_masks=True),
+    # the same under a tax_annealing_schedule: the maximum rate of an episode (warm-up draws, the formula's clip, the rates
+    # in force and observed) follows the completed-episode count - 0.3, 0.45, 0.6, ... of rate_max over the trace's episodes
+    "saez_annealed_reset": dict(
+        scenario_name="layout_from_file/simple_wood_and_stone",
+        components=[("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=3)),
+                    ("ContinuousDoubleAuction", dict(max_num_orders=3, order_duration=7)),
+                    ("Gather", dict(skill_dist="pareto")),
+                    ("PeriodicBracketTax", dict(bracket_spacing="us-federal", period=10, tax_model="saez",
+                                                usd_scaling=10000.0, tax_annealing_schedule=[-2, 0.15]))],
+        env_layout_file="quadrant_25x25_20each_30clump.txt", starting_agent_coin=5,
+        fixed_four_skill_and_loc=False, n_agents=10, world_size=[25, 25], episode_length=100,
+        multi_action_mode_agents=False, multi_action_mode_planner=True,
+        flatten_observations=True, flatten_masks=True),
     # short episodes for the multi-episode (device-side reset) traces
     "c1_reset": dict(
         scenario_name="layout_from_file/simple_wood_and_stone", components=_GTB,

@@ -835,8 +835,8 @@ static void compute_reward(const orc_batch *b, env_t *s) { /* :519-559 */
     memcpy(prev, s->curr_metric, sizeof(double) * (A + 1));
     current_metrics(b, s, s->curr_metric);
     for (a = 0; a <= A; a++) s->rew[a] = s->curr_metric[a] - prev[a];
-    for (a = 0; a < A; a++) avg += s->rew[a];
-    avg /= A;
+    avg = np_sum(s->rew, A) / A; /* np.mean([...]) :552 - numpy's pairwise order: the sign of a sum that cancels to
+                                  * rounding noise (a step of trades only) decides `avg > 0` */
     if (avg > 0) s->auto_warmup_integrator += 1;
 }
 

@@ -43,6 +43,7 @@ PLAN = [
     ("c1_reset", 1001, 80, 10),
     ("c3_reset", 1001, 95, 10),
     ("saez_reset", 1001, 790, 50),
+    ("saez_annealed_reset", 1001, 790, 50),
     ("lognormal_reset", 1001, 95, 10),
     ("split_reset", 1001, 90, 10),
     ("us_federal_annealed_reset", 1001, 90, 5),

@@ -14,9 +14,11 @@ def pytest_configure(config):
 
 
 # GPU cases that have not run on a B200 yet go here (substring of the node id): they are ordered last, so that with `-x`
-# a surprise there cannot mask the cases that are known to pass on the hardware.  Empty: every `-m gpu` case has run on a
-# B200 (profiles/r02z_pytest_gpu.log: 141 passed).
-NOT_YET_RUN_ON_B200 = ()
+# a surprise there cannot mask the cases that are known to pass on the hardware.  Everything else has run on a B200
+# (profiles/r02z_pytest_gpu.log: 141 passed).  saez_annealed: the Saez model under a tax_annealing_schedule was added after
+# the round's last GPU minute; it is green on the host emulation of the same device source and changes only the `EXT`
+# kernel instantiations (the SASS of every other kernel is byte-identical to the measured build).
+NOT_YET_RUN_ON_B200 = ("saez_annealed",)
 
 
 def pytest_collection_modifyitems(config, items):

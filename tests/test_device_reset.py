@@ -98,7 +98,7 @@ def test_cuda_previous_episode_metrics_match_reference(path):
     _replay_previous_episode_metrics(path, None)
 
 
-@pytest.mark.parametrize("which", ["saez", "c3_reset", "c1_reset", "lognormal_reset", "us_federal_annealed"])
+@pytest.mark.parametrize("which", ["saez_reset", "saez_annealed_reset", "c3_reset", "c1_reset", "lognormal_reset", "us_federal_annealed"])
 def test_emulated_explicit_host_resets_match_reference(which):
     """auto_reset off: env.reset() between episodes goes through the host reset path.  It has to carry the Saez
     estimator's persistent state (sample counter, rates in force / observed) across the repacked records, and the

@@ -75,3 +75,51 @@ def test_oracle_and_host_reset_track_live_reference_on_edge_config(cfg):
 @pytest.mark.parametrize("cfg", EDGE)
 def test_cuda_matches_oracle_on_edge_config(cfg):
     run_against_oracle(make_product_env(cfg, 24, None, seed=900, device="cuda:0"), steps=40, check_every=20)
+
+
+def test_mean_agent_reward_sign_follows_numpys_pairwise_sum():
+    """layout_from_file.py:552 / dynamic_layout.py:615: `np.mean([rew ...]) > 0` feeds the automatic energy warm-up.  In a
+    step of trades only the agents' rewards cancel to rounding noise and the *order* of the sum decides the sign: numpy's
+    pairwise order gives exactly 0.0 at t = 24 of this run (found by tools/fuzz_emu_vs_oracle.py 4000 1777, case 1329), a
+    left-to-right sum 4.4e-17.  Device code and oracle must both take numpy's order (10 agents: the 8-accumulator path)."""
+    import numpy as np
+    from ai_economist_b200 import foundation
+    from oracle.oracle import OracleBatch
+    from tests import batch_utils as bu
+    from tests.emu.emu_stepper import emu_factory
+
+    kw = {'components': [('Build', {'skill_dist': 'lognormal', 'payment_max_skill_multiplier': 1, 'build_labor': 2.5}),
+                         ('ContinuousDoubleAuction', {'max_num_orders': 2, 'order_duration': 3, 'max_bid_ask': 17, 'order_labor': 0.25}),
+                         ('Gather', {'skill_dist': 'lognormal', 'move_labor': 0.5}),
+                         ('PeriodicBracketTax', {'period': 10, 'tax_model': 'us-federal-single-filer-2018-scaled',
+                                                 'bracket_spacing': 'us-federal'})],
+          'n_agents': 10, 'episode_length': 30, 'multi_action_mode_agents': False, 'multi_action_mode_planner': True,
+          'flatten_observations': True, 'flatten_masks': True, 'starting_agent_coin': 5.0, 'mobile_agent_observation_range': 2,
+          'planner_gets_spatial_info': True, 'full_observability': False, 'allow_observation_scaling': True,
+          'isoelastic_eta': 0.0, 'energy_cost': 1.0, 'energy_warmup_constant': 3.0, 'energy_warmup_method': 'auto',
+          'planner_reward_type': 'inv_income_weighted_utility', 'mixing_weight_gini_vs_coin': 0.0, 'world_size': [24, 24],
+          'starting_wood_coverage': 0.1, 'starting_stone_coverage': 0.1, 'wood_regen_weight': 0.01, 'stone_regen_weight': 0.01,
+          'wood_regen_halfwidth': 0, 'stone_regen_halfwidth': 0}
+    seed = 1330
+    env = foundation.make_env_instance("quadrant/simple_wood_and_stone", n_envs=2, stepper_factory=emu_factory,
+                                       auto_reset=False, seed=seed, **kw)
+    host = env.host_reset_arrays()
+    env.load_host_state(host)
+    orc = OracleBatch(env.spec, 2)   # two replicas as in the fuzz run: the action sampler's stream covers both
+    for e in range(2):
+        orc.load_env(e, {k: v[e] for k, v in host.items()})
+    st, rng = env.stepper, np.random.RandomState(seed)
+    seg_a, seg_p = bu.segments(env.spec, "a"), bu.segments(env.spec, "p")
+    hit = False
+    for t in range(1, 31):
+        aa = bu.sample_from_masks(st.to_numpy(st.buf["mask_agent"]), seg_a, rng)
+        ap = bu.sample_from_masks(st.to_numpy(st.buf["mask_planner"]), seg_p, rng)
+        env.step((aa, ap))
+        orc.step(aa, ap)
+        rew = [float(x) for x in st.to_numpy(st.buf["reward"])[0][:-1]]
+        seq = 0.0
+        for x in rew:
+            seq += x
+        hit |= (np.mean(rew) > 0) != (seq > 0)
+        assert np.allclose(orc.state(0)["util_prev"], st.read_state(0)["util_prev"], rtol=1e-9, atol=1e-12), t
+    assert hit, "the run no longer contains a step where the summation order decides the sign"

@@ -38,7 +38,7 @@ def _configs(seed, n=N_CASES, draw=None):
 
 
 def _skip_unsupported(fn, *a, **k):
-    """Configurations the product rejects loudly (e.g. Saez + annealing) or that the reference itself cannot build
+    """Configurations the product rejects loudly or that the reference itself cannot build
     (layout coverage asserts) are skipped, like the tools do."""
     try:
         fn(*a, **k)

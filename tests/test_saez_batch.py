@@ -30,8 +30,11 @@ def test_batched_estimator_tracks_the_per_replica_estimator(weights, fixed):
         sel = np.nonzero(ready)[0]
         if len(sel) == 0:
             continue
-        want = np.stack([one[e].new_period_rates() for e in sel])
-        got = bat.new_period_rates(sel)
+        caps = None if t % 3 else rng.choice([0.3, 0.45, 1.0], size=len(sel))   # per-replica curr_rate_max (tax annealing)
+        want = np.stack([one[e].new_period_rates(None if caps is None else caps[i]) for i, e in enumerate(sel)])
+        got = bat.new_period_rates(sel, caps)
+        if caps is not None:
+            assert np.all(got <= caps[:, None] + 1e-15)
         assert np.allclose(want, got, rtol=1e-10, atol=1e-12), (t, np.abs(want - got).max())
         assert np.allclose([one[e].elas_t for e in sel], bat.elas_t[sel], rtol=1e-10, atol=1e-13)
         assert np.allclose(np.stack([one[e].running_avg for e in sel]), bat.running_avg[sel], rtol=1e-10, atol=1e-13)
