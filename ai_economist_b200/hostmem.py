@@ -56,6 +56,20 @@ def transfer_block_rows(n_envs, max_slices=16, item_envs=16):
     return max(1, (n_items + n_slices - 1) // n_slices) * item_envs
 
 
+def _placement(size, page, n_nodes, numa, rows, row_bytes, block_rows):
+    """[(byte lo, byte hi, node index)] covering [0, size) in page-aligned pieces.  "split": one piece per node.  "blocks":
+    block b of `block_rows` rows goes to node b % n_nodes; a block boundary is rounded to the nearest page, and a piece takes
+    the node of the block that owns its middle byte (tiny tensors: several blocks share a page)."""
+    if numa == "split":
+        per = (size // n_nodes) // page * page
+        cuts = [i * per for i in range(n_nodes)] + [size]
+        return [(cuts[i], cuts[i + 1], i) for i in range(n_nodes) if cuts[i + 1] > cuts[i]]
+    block_bytes = max(1, block_rows * row_bytes)
+    n_blocks = (rows + block_rows - 1) // block_rows
+    cuts = sorted({min(size, (b * block_bytes + page // 2) // page * page) for b in range(n_blocks)} | {0, size})
+    return [(lo, hi, min(n_blocks - 1, ((lo + hi) // 2) // block_bytes) % n_nodes) for lo, hi in zip(cuts[:-1], cuts[1:]) if hi > lo]
+
+
 def pinned_empty(shape, dtype, interleave=False, numa=None, block_rows=None):
     """A pinned host tensor.
     numa="blocks": blocks of `block_rows` rows of the leading axis (env replicas) alternate between the NUMA nodes (bound
@@ -82,20 +96,12 @@ def pinned_empty(shape, dtype, interleave=False, numa=None, block_rows=None):
         buf = (ctypes.c_char * size).from_buffer(mm)
         base = ctypes.addressof(buf)
         libc = ctypes.CDLL(None, use_errno=True)
-        if numa == "split":
-            per = (size // len(nodes)) // page * page
-            cuts = [i * per for i in range(len(nodes))] + [size]
-        else:
-            rows = int(shape[0]) if len(shape) else 1
-            row_bytes = nbytes // max(rows, 1)
-            br = int(block_rows or transfer_block_rows(rows))
-            cuts = sorted({min(size, (b * br * row_bytes + page // 2) // page * page) for b in range((rows + br - 1) // br)} | {0, size})
+        rows = int(shape[0]) if len(shape) else 1
+        pieces = _placement(size, page, len(nodes), numa, rows, nbytes // max(rows, 1),
+                            int(block_rows or transfer_block_rows(rows)))
         ok = True
-        for i in range(len(cuts) - 1):
-            lo, hi = cuts[i], cuts[i + 1]
-            if hi <= lo:
-                continue
-            mask = ctypes.c_ulong(1 << nodes[i % len(nodes)])
+        for lo, hi, k in pieces:
+            mask = ctypes.c_ulong(1 << nodes[k])
             ok &= libc.syscall(_SYS_MBIND, ctypes.c_void_p(base + lo), ctypes.c_ulong(hi - lo), ctypes.c_int(_MPOL_BIND),
                                ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2), ctypes.c_uint(0)) == 0
         t = torch.frombuffer(buf, dtype=dtype, count=n_el).reshape(shape)

@@ -114,3 +114,20 @@ def test_hostmem_block_rows_match_the_transfer_slices(n_envs):
     rows = hostmem.transfer_block_rows(n_envs)
     assert rows % 16 == 0
     assert int(st.host_timing()["slices"]) == -(-n_envs // rows)
+
+
+def test_hostmem_block_placement_covers_the_buffer_and_alternates_nodes():
+    """hostmem._placement: page-aligned pieces covering the whole mapping; with numa="blocks" piece b holds block b's rows
+    (up to half a page at either edge) and goes to node b % nodes; tiny tensors degrade to whole pages."""
+    from ai_economist_b200 import hostmem as h
+    page, row = 4096, 13552                                   # c2 agent map: 8 192 rows of 13 552 bytes, slices of 512 rows
+    size = (8192 * row + page - 1) // page * page
+    pc = h._placement(size, page, 2, "blocks", 8192, row, 512)
+    assert len(pc) == 16 and [k for _, _, k in pc] == [b % 2 for b in range(16)]
+    assert pc[0][0] == 0 and pc[-1][1] == size and all(a[1] == b[0] for a, b in zip(pc, pc[1:]))
+    assert all(lo % page == 0 and abs(lo - b * 512 * row) <= page // 2 for b, (lo, _, _) in enumerate(pc))
+    for args in [(32768, page, 2, "blocks", 8192, 4, 512), (4096, page, 2, "blocks", 300, 1, 32),
+                 (5 * page, page, 4, "blocks", 70, 290, 16), (1 << 20, page, 2, "split", 8192, 128, 512)]:
+        pc = h._placement(*args)
+        assert pc[0][0] == 0 and pc[-1][1] == args[0] and all(a[1] == b[0] for a, b in zip(pc, pc[1:]))
+        assert all(0 <= k < args[2] and hi > lo and lo % page == 0 for lo, hi, k in pc)
