@@ -10,11 +10,12 @@ from ai_economist_b200 import _abi
 from ai_economist_b200.stepper import BatchStepper
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libaie_emu.so")
+_SANITIZE = bool(os.environ.get("AIE_EMU_SANITIZE"))   # ASan + UBSan build (the caller preloads libasan: tools/emu_sanitizers.sh)
+_LIB = os.path.join(_HERE, "libaie_emu_asan.so" if _SANITIZE else "libaie_emu.so")
 
 
 def build():
-    subprocess.check_call(["make", "-C", _HERE, "-s"], stderr=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _HERE, "-s", os.path.basename(_LIB)], stderr=subprocess.DEVNULL)
     return _LIB
 
 
