@@ -12,6 +12,7 @@ profiles/); here every fuzzer contributes N_CASES configurations drawn from a fi
   * reference API vs ref.    -m reference           ReferenceApiEnv against the reference: obs, rewards, metrics, dense logs
   * dynamic layouts vs ref.  -m reference           uniform / quadrant: device-side layout generation at every auto-reset
   * one-step-economy vs ref. -m reference           SimpleLabor + one-step-economy incl. finished-episode metrics
+  * Saez hybrid vs reference -m reference           the Saez tax model (device / host), with and without tax annealing
   * COVID vs reference       -m reference           COVID device code (scan and change list) under parameter variants
 
 `-m reference` cases need /root/reference (build container) and are skipped elsewhere.
@@ -132,6 +133,19 @@ def test_fuzz_multi_zone_device_reset_matches_live_reference(i, monkeypatch):
         if isinstance(ex, AssertionError) and "coverage" not in str(ex) and "World" not in str(ex):
             raise
         pytest.skip(repr(ex))   # the reference refusing its own configuration
+
+
+@needs_reference
+@pytest.mark.reference
+@pytest.mark.parametrize("i", range(10))
+def test_fuzz_saez_hybrid_matches_live_reference(i):
+    """PeriodicBracketTax(tax_model="saez"): warm-up draws on the device, buffer / regression / formula on the host, rates in
+    force and observed across resets - random bracket layouts, weights, fixed elasticities, rate bounds, with and without a
+    tax_annealing_schedule, over enough episodes to run the formula for two of them."""
+    import fuzz_device_reset_vs_reference as fr
+
+    cfg = _configs(31, n=10, draw=fr.random_saez_config)[i]
+    fr.run_one(cfg, seed=800 + i, episodes=fr.saez_episodes(cfg))
 
 
 @needs_reference

@@ -1,8 +1,10 @@
 """Randomised multi-episode fuzz (build container only): the device-side reference-exact reset (auto_reset, 1-lane
 emulation of the device source) against the LIVE reference, which calls env.reset() between episodes on one continuing
 global numpy stream.  layout_from_file configurations with skill_dist in {none, pareto, lognormal}, with / without
-fixed_four_skill_and_loc; with --dynamic: uniform / quadrant scenarios (device-side layout generation).
-python tools/fuzz_device_reset_vs_reference.py [n] [seed] [--dynamic]"""
+fixed_four_skill_and_loc; with --dynamic: uniform / quadrant scenarios (device-side layout generation); with --saez: the Saez
+tax model (device / host hybrid, foundation/saez.py) over enough episodes to fill its 500-sample buffer and run the formula,
+with and without a tax_annealing_schedule.
+python tools/fuzz_device_reset_vs_reference.py [n] [seed] [--dynamic | --multi-zone | --saez]"""
 import os
 import sys
 import traceback
@@ -73,6 +75,38 @@ def random_dynamic_config(rng):
                         num_wood_and_stone_zones=int(rng.choice([0, 1]))) if fam == "multi_zone" else {}))
 
 
+def random_saez_config(rng):
+    """PeriodicBracketTax(tax_model="saez") (redistribution.py:437-823): warm-up draws, sample buffer, elasticity regression,
+    binned welfare weights, bracketisation, running average across resets - and curr_rate_max under annealing."""
+    size = list(LAYOUTS)[rng.randint(len(LAYOUTS))]
+    A = int(rng.choice([5, 8, 10, 12]))
+    spacing = str(rng.choice(["us-federal", "linear", "log"]))
+    tkw = dict(tax_model="saez", period=int(rng.choice([2, 5])), bracket_spacing=spacing,
+               usd_scaling=float(rng.choice([1000.0, 10000.0])), pareto_weight_type=str(rng.choice(["inverse_income", "uniform"])),
+               rate_min=float(rng.choice([0.0, 0.1])), rate_max=float(rng.choice([1.0, 0.8])))
+    if spacing != "us-federal":
+        tkw.update(n_brackets=int(rng.choice([3, 5, 7])), top_bracket_cutoff=float(rng.choice([20, 100])))
+    if rng.rand() < 0.3:
+        tkw["saez_fixed_elas"] = float(rng.choice([0.0, 0.4, 1.0]))
+    if rng.rand() < 0.6:
+        tkw["tax_annealing_schedule"] = [int(rng.choice([-2, 0, 1])), float(rng.choice([0.15, 0.3, 0.6]))]
+    comps = [("Build", dict(skill_dist="pareto", payment_max_skill_multiplier=int(rng.randint(1, 4)))),
+             ("ContinuousDoubleAuction", dict(max_num_orders=int(rng.choice([1, 3, 5])), order_duration=int(rng.choice([2, 50])))),
+             ("Gather", dict(skill_dist=str(rng.choice(["none", "pareto"])))), ("PeriodicBracketTax", tkw)]
+    return dict(scenario_name="layout_from_file/simple_wood_and_stone", components=comps, n_agents=A,
+                world_size=list(size), env_layout_file=LAYOUTS[size], episode_length=int(rng.choice([40, 60])),
+                fixed_four_skill_and_loc=False, starting_agent_coin=float(rng.choice([5, 20])),
+                multi_action_mode_agents=bool(rng.rand() < 0.3), multi_action_mode_planner=True,
+                flatten_observations=True, flatten_masks=True)
+
+
+def saez_episodes(cfg):
+    """episodes until the 500-sample buffer has been full for at least two more episodes (one tax day = n_agents samples)"""
+    tax = [kw for name, kw in cfg["components"] if name == "PeriodicBracketTax"][0]
+    per_episode = (cfg["episode_length"] // tax["period"]) * cfg["n_agents"]
+    return -(-500 // per_episode) + 2
+
+
 def run_one(cfg, seed, episodes=4):
     f = rh.load_reference_foundation()
     ref = f.make_env_instance(**cfg)
@@ -129,14 +163,16 @@ if __name__ == "__main__":
     rng = np.random.RandomState(int(args[1]) if len(args) > 1 else 0)
     bad, kinds = 0, {}
     dynamic = "--dynamic" in sys.argv or "--multi-zone" in sys.argv
+    saez = "--saez" in sys.argv
     if "--multi-zone" in sys.argv:
         FAMILIES[:] = ["multi_zone"]
     for i in range(n):
-        cfg = (random_dynamic_config if dynamic else random_config)(rng)
-        kinds[cfg["scenario_name"].split("/")[0]] = kinds.get(cfg["scenario_name"].split("/")[0], 0) + 1
+        cfg = (random_saez_config if saez else random_dynamic_config if dynamic else random_config)(rng)
+        kind = "saez" + ("+annealing" if "tax_annealing_schedule" in cfg["components"][-1][1] else "") if saez else cfg["scenario_name"].split("/")[0]
+        kinds[kind] = kinds.get(kind, 0) + 1
         try:
-            run_one(cfg, seed=500 + i)
+            run_one(cfg, seed=500 + i, **(dict(episodes=saez_episodes(cfg)) if saez else {}))
         except Exception as ex:  # noqa: BLE001
             bad += 1
             print("[%d] FAILED %r\n    %s" % (i, cfg, "".join(traceback.format_exception_only(type(ex), ex)).strip()[:500]))
-    print("%d configs x 4 episodes, %d failures" % (n, bad), kinds)
+    print("%d configs x %s episodes, %d failures" % (n, "enough" if saez else "4", bad), kinds)
