@@ -35,10 +35,10 @@ struct State {
     uint8_t *compact_dev = nullptr, *compact_host = nullptr;   // aie_step_host_compact: device + pinned host staging
     size_t compact_bytes = 0, compact_host_bytes = 0;
     int compact_host_node = -1;   // >= 0: staging pages bound to that NUMA node (mmap + mbind + cudaHostRegister)
-    cudaEvent_t slice_ev[AIE_MAX_SLICES_BE] = {};
+    cudaEvent_t slice_ev[AIE_MAX_SLICES_BE] = {};   // one per transfer slice of the compacted D2H copy
     cudaStream_t copy_st = nullptr;   // aie_step_host_compact: the slices go down on this stream while later chunks still step
-    cudaEvent_t chunk_ev = nullptr, tail_ev = nullptr;
-    cudaEvent_t call_ev = nullptr;   // recorded when a host-buffer step starts enqueueing (timing reference of the slices)   // one per transfer slice of the compacted D2H copy
+    cudaEvent_t chunk_ev = nullptr, tail_ev = nullptr;   // caller's stream -> copy stream (a chunk is packed), and back (all slices down)
+    cudaEvent_t call_ev = nullptr;   // recorded when a host-buffer step starts enqueueing (timing reference of the slices)
 };
 // Makes `device` current for the lifetime of the object and restores the caller's device afterwards, so a handle
 // created for cuda:1 works while cuda:0 is current (streams passed in must belong to the handle's device).
