@@ -201,8 +201,7 @@ class VaccinationCampaign(BaseComponent):
         self.delivery_interval = int(delivery_interval)
         assert 1 <= self.delivery_interval <= 5000
         self.vaccine_delivery_start_date = vaccine_delivery_start_date
-        if observe_rate:
-            raise NotImplementedError("observe_rate=True is not on the GPU path")
+        self.observe_rate = bool(observe_rate)   # adds the `next_vaccination_rate` observation (covid19_components.py:659-661)
 
     def spec_fields(self):
         return dict(daily_vaccines_per_million_people=self.daily_vaccines_per_million_people,
@@ -260,6 +259,7 @@ class CovidBatchedEnv:
             self._stepper = stepper_factory(self.params, self.n_envs, auto_reset)
         self._loaded = False
         self._build_views()
+        self._build_rate_observation()
 
     @property
     def episode_length(self):
@@ -304,9 +304,47 @@ class CovidBatchedEnv:
         self.done = {"__all__": b["done"]}
         self.info = {"a": {}, "p": {}}
 
+    def _build_rate_observation(self):
+        """VaccinationCampaign(observe_rate=True) (covid19_components.py:629-661): the vaccination rate of the NEXT timestep, 0
+        until deliveries have begun.  It depends on the timestep alone, so it is a table lookup by the replica's timestep after
+        every step / reset (the reference's own CUDA path does not emit it; no kernel involved)."""
+        vac = self._components[2]
+        self._rate_tab = None
+        if not vac.observe_rate:
+            return
+        T, t_first = self._episode_length, int(self.params["t_first_delivery"])
+        rate = np.float32(vac.daily_vaccines_per_million_people / 1e6)
+        tab = np.array([np.float32(0.0) if t + 1 <= t_first else rate for t in range(T + 1)], np.float32)
+        sc = self._stepper.buf["obs_scalars"]
+        E, S = self.n_envs, self.n_agents
+        if isinstance(sc, np.ndarray):
+            self._rate_tab, self._rate_a, self._rate_p = tab, np.zeros((E, S), np.float32), np.zeros(E, np.float32)
+        else:
+            import torch
+            self._rate_tab = torch.as_tensor(tab, device=sc.device)
+            self._rate_a, self._rate_p = torch.zeros((E, S), dtype=torch.float32, device=sc.device), torch.zeros(E, dtype=torch.float32, device=sc.device)
+        self.obs["a"]["VaccinationCampaign-next_vaccination_rate"] = self._rate_a
+        self.obs["p"]["VaccinationCampaign-next_vaccination_rate"] = self._rate_p
+
+    def _refresh_rate_observation(self):
+        if self._rate_tab is None:
+            return
+        sc = self._stepper.buf["obs_scalars"]   # [:, 0] = timestep / time_scale (episode_length under observation scaling)
+        scale = float(self.params["time_scale"])
+        if isinstance(sc, np.ndarray):
+            t = np.rint(sc[:, 0].astype(np.float64) * scale).astype(np.int64)
+            self._rate_p[...] = self._rate_tab[t]
+            self._rate_a[...] = self._rate_p[:, None]
+        else:
+            import torch
+            t = torch.round(sc[:, 0].double() * scale).long()
+            self._rate_p.copy_(self._rate_tab[t])
+            self._rate_a.copy_(self._rate_p[:, None].expand_as(self._rate_a))
+
     def reset(self):
         self._stepper.reset()
         self._loaded = True
+        self._refresh_rate_observation()
         return self.obs
 
     def step(self, actions=None):
@@ -329,6 +367,7 @@ class CovidBatchedEnv:
                         buf[...] = torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v,
                                                    device=buf.device).to(buf.dtype).reshape(buf.shape)
         self._stepper.step()
+        self._refresh_rate_observation()
         return self.obs, self.rew, self.done, self.info
 
 

@@ -237,3 +237,82 @@ def test_covid_env_api_through_make_env_instance():
         obs, rew, done, info = env.step({"a": a, "p": pl})
         check(z, t, env.stepper.read_obs(1), "api")
     assert rew["a"].shape == (2, 51) and rew["p"].shape == (2,) and "__all__" in done
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not present")
+@pytest.mark.parametrize("variant", range(4))
+def test_covid_observe_rate_matches_live_reference(variant):
+    """VaccinationCampaign(observe_rate=True) (covid19_components.py:629-661): `next_vaccination_rate` for agents and planner is
+    a function of the timestep alone; the facade serves it by table lookup after every step / reset.  Variants: deliveries from
+    the start, a delivery interval that shifts the first delivery, unscaled time observations, deliveries that never begin."""
+    import contextlib
+    import io
+
+    from ai_economist_b200 import foundation
+    from oracle import gen_golden_covid as gg
+    from oracle import ref_harness as rh
+    from tests.emu.emu_stepper import EmuCovidStepper
+
+    kw = dict(gg.COVID_KWARGS)
+    kw.update(episode_length=60, start_date=["2020-03-22", "2020-12-01", "2020-12-20", "2020-06-01"][variant],
+              delivery_interval=[1, 7, 3, 7][variant],
+              vaccine_delivery_start_date=["2020-04-15", "2020-12-22", "2021-01-05", "2021-06-01"][variant],
+              allow_observation_scaling=variant != 2)
+    cfg = gg.reference_config(kw)
+    for c in cfg["components"]:
+        if "VaccinationCampaign" in c:
+            c["VaccinationCampaign"]["observe_rate"] = True
+    f = rh.load_reference_foundation()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = f.make_env_instance(**cfg)
+        obs = ref.reset()
+    ours = dict(cfg)
+    env = foundation.make_env_instance(ours.pop("scenario_name"), n_envs=2, auto_reset=False,
+                                       stepper_factory=lambda p, n, ar: EmuCovidStepper(p, n, auto_reset=ar), **ours)
+    o = env.reset()
+    rng, seen, key = np.random.RandomState(variant), set(), "VaccinationCampaign-next_vaccination_rate"
+    for t in range(kw["episode_length"] + 1):
+        assert np.array_equal(np.asarray(obs["a"][key], np.float32), np.asarray(o["a"][key])[1]), t
+        assert np.float32(obs["p"][key]) == np.asarray(o["p"][key])[1], t
+        seen.add(float(np.float32(obs["p"][key])))
+        if t == kw["episode_length"]:
+            break
+        act_a, act_p = gg.sample(obs, rng)
+        actions = {str(i): int(act_a[i]) for i in range(51)}
+        actions["p"] = int(act_p)
+        obs, _, _, _ = ref.step(actions)
+        o, _, _, _ = env.step((np.repeat(act_a[None], 2, 0), np.repeat(np.asarray(act_p)[None], 2, 0)))
+    assert len(seen) == (1 if variant == 3 else 2)
+
+
+def test_covid_observe_rate_torch_and_numpy_lookups_agree():
+    """the facade's table lookup has a numpy (emulation) and a torch (CUDA buffers) branch: same values from the same scalars"""
+    import torch
+
+    from ai_economist_b200 import foundation
+    from ai_economist_b200.workloads import COVID_KWARGS, covid_reference_config
+    from tests.emu.emu_stepper import EmuCovidStepper
+
+    kw = dict(COVID_KWARGS, episode_length=40, start_date="2020-12-01", delivery_interval=7, vaccine_delivery_start_date="2020-12-15")
+    cfg = covid_reference_config(kw)
+    for c in cfg["components"]:
+        if "VaccinationCampaign" in c:
+            c["VaccinationCampaign"]["observe_rate"] = True
+    env = foundation.make_env_instance(cfg.pop("scenario_name"), n_envs=3, auto_reset=False,
+                                       stepper_factory=lambda p, n, ar: EmuCovidStepper(p, n, auto_reset=ar), **cfg)
+    env.reset()
+    key = "VaccinationCampaign-next_vaccination_rate"
+    want = []
+    for t in range(30):
+        env.step(None)
+        want.append((np.array(env.obs["a"][key]), np.array(env.obs["p"][key]), np.array(env.stepper.buf["obs_scalars"])))
+    # the same lookups through the torch branch: scalars as (CPU) torch tensors
+    sc = torch.zeros(tuple(env.stepper.buf["obs_scalars"].shape), dtype=torch.float32)
+    env._stepper.buf = dict(env._stepper.buf, obs_scalars=sc)
+    env._build_rate_observation()
+    for a, p, scalars in want:
+        sc.copy_(torch.from_numpy(scalars))
+        env._refresh_rate_observation()
+        assert np.array_equal(a, env.obs["a"][key].numpy()) and np.array_equal(p, env.obs["p"][key].numpy())
+    assert len({float(p[0]) for _, p, _ in want}) == 2
