@@ -499,8 +499,12 @@ def measure_gtb(ctx, key, K, W, with_cpu, clocks=None, e2e_steps=20, e2e_mode="c
             # pinned host tensors from the package's allocator: blocks of replicas (one transfer slice each) on alternating
             # NUMA nodes, which is what the node-pinned expansion threads of aie_step_host_compact are matched to: every
             # socket has work from the first slice on (ai_economist_b200/hostmem.py)
-            t = hostmem.pinned_empty(st.buf[nm].shape, st.buf[nm].dtype,
-                                     numa=os.environ.get("AIE_BENCH_E2E_ALLOC", "blocks") if e2e_mode == "compact" else None)
+            try:
+                t = hostmem.pinned_empty(st.buf[nm].shape, st.buf[nm].dtype,
+                                         numa=os.environ.get("AIE_BENCH_E2E_ALLOC", "blocks") if e2e_mode == "compact" else None)
+            except Exception as ex:   # placement is an optimisation: never lose the line over it
+                sys.stderr.write("hostmem.pinned_empty failed (%s: %s): plain pinned tensor for %s\n" % (type(ex).__name__, ex, nm))
+                t = torch.empty(tuple(st.buf[nm].shape), dtype=st.buf[nm].dtype, pin_memory=True)
             out_host[nm] = t
             out_ptrs[nm] = C.c_void_p(t.data_ptr())
             d2h += t.numel() * t.element_size()
