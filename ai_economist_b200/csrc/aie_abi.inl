@@ -309,7 +309,9 @@ int aie_step_host_compact(aie_env *env, const int32_t *act_a, const int32_t *act
     rc = aie::be::copies_done(env, stream);
     if (rc != AIE_OK) return rc;
     const double t_enqueued = ms_since(clk::now());
-    int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    // <= 0: one thread per physical core of an SMT-2 host - the expansion is bound by the memory controllers, 64 threads were
+    // as fast as 96 or 128 on the 2 x 32-core B200 host and burn half the CPU time (profiles/r02z_e2e_transfer_knobs.txt)
+    int want = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency() / 2;
     if (want < 1) want = 1;
     if (want > aie::AIE_MAX_HOST_THREADS) want = aie::AIE_MAX_HOST_THREADS;
     // AIE_E2E_NUMA: 0 unpinned threads, one queue; 1 node-local items first, then help the other nodes; 2 node-local only

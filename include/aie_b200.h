@@ -347,11 +347,13 @@ int aie_step_host(aie_env *env, const int32_t *actions_agent_host, const int32_t
                   const aie_host_out *out, void *stream);
 
 /* ABI 3.  Same contract as aie_step_host - the caller's host tensors receive exactly the same bytes - with a compacted
- * device->host transfer: the 0/1-valued float planes (maps, masks) cross PCIe as bits and the int16 index planes as
- * bytes.  A pack kernel rewrites each env's outputs into a library-owned compact device buffer, one D2H copy moves it
- * into a library-owned pinned host buffer, and n_threads host threads (<= 0: hardware concurrency, at most 64) expand it
- * into the caller's tensors (a transfer format: no simulation work runs on the host).  c2: 5.5 KB instead of 36 KB
- * per env-step over PCIe.  Synchronous. */
+ * device->host transfer: the 0/1-valued float planes (maps, masks) cross PCIe as bits, the int16 index planes as a bitmap of
+ * their non-zero cells plus byte values, the agents' flat vectors de-duplicated by entry class.  The batch steps in a few
+ * launches over env ranges; after each, a pack kernel rewrites that chunk's outputs into a library-owned compact device
+ * buffer and the records go down in slices on a library-owned copy stream into a pinned staging buffer while the next chunk
+ * steps; n_threads host threads (<= 0: half the hardware threads; at most 128) expand each slice as it lands into the
+ * caller's tensors (a transfer format: no simulation work runs on the host).  c2: 2.7 KB instead of 36 KB per env-step over
+ * PCIe.  Synchronous; ordered on `stream` like aie_step_host. */
 int aie_step_host_compact(aie_env *env, const int32_t *actions_agent, const int32_t *actions_planner,
                           const aie_host_out *out, int32_t n_threads, void *stream);
 /* bytes one env contributes to the compacted transfer (0 on error) */
